@@ -1,0 +1,199 @@
+/*
+ * libicp_b200.so -- C ABI of the B200-native ICP registration + occupancy
+ * raycast hot path (sm_100a).
+ *
+ * The reference (DUBSON0/iterative-closest-point-avmi) is pure Python and has
+ * no FFI of its own; its boundary for this path is the Python call surface
+ *     utilities/icp.py:132-134      ICP(source, target, error_threshold, ...)
+ *     utilities/icp.py:117          voxel_downsample(points, voxel_size)
+ *     utilities/mapping.py:28-37    OccupancyGrid2D(...)
+ *     utilities/mapping.py:103      OccupancyGrid2D.update_scan(origin, hits)
+ *     utilities/mapping.py:143      OccupancyGrid2D.reset()
+ *     utilities/mapping.py:47       OccupancyGrid2D.log_odds  (ny, nx) float32
+ * Each entry point below names the reference lines it replaces.  A ctypes
+ * binding (the one the drop-in `utilities` shim uses) is shown in
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; every host buffer is owned by the caller and is not
+ *     retained after the call returns; all device memory, streams and handles
+ *     are owned by the library;
+ *   - calls are blocking: results are valid on return (the *_dev variants are
+ *     stream-ordered instead and return after enqueueing);
+ *   - return value 0 = success, negative = failure (see ICPB200_ERR_*), text in
+ *     icpb200_last_error().  Numerical outcomes the reference treats as normal
+ *     (singular normal equations -> identity step; too few inliers -> early
+ *     exit) are NOT errors: they are reported per pair in status_out;
+ *   - there is no CPU fallback: without a usable CUDA device every compute
+ *     call fails with ICPB200_ERR_CUDA;
+ *   - one process drives one GPU (torch.distributed / torchrun style);
+ *     icpb200_init(device) selects it.  Calls are serialised by an internal
+ *     mutex.
+ */
+#ifndef ICP_B200_H
+#define ICP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICPB200_OK            0
+#define ICPB200_ERR_CUDA     -1   /* CUDA runtime / driver failure, or no device */
+#define ICPB200_ERR_ARG      -2   /* invalid argument */
+#define ICPB200_ERR_LIMIT    -3   /* input exceeds a documented limit of this build */
+
+/* per-pair status codes (status_out) */
+#define ICPB200_CONVERGED     0   /* |prev_error - error| < error_threshold   (icp.py:216-219) */
+#define ICPB200_MAX_ITER      1   /* loop exhausted                           (icp.py:222-223) */
+#define ICPB200_FEW_INLIERS   2   /* inliers < max(3, N/10): loop left early  (icp.py:186-187) */
+#define ICPB200_BAD_VOXELS    3   /* voxel index range does not fit 62 bits; pair not processed */
+
+/* method (icp.py:133, 162) */
+#define ICPB200_POINT_TO_POINT 0
+#define ICPB200_POINT_TO_LINE  1  /* 2-D only; silently point-to-point for dim 3, as the reference */
+
+/* nn_mode */
+#define ICPB200_NN_AUTO  0        /* brute force up to ICPB200_BRUTE_MAX_POINTS raw points, else grid */
+#define ICPB200_NN_BRUTE 1        /* shared-memory tiled brute force (fp32 sweep + fp64 decision) */
+#define ICPB200_NN_GRID  2        /* uniform-grid exact nearest neighbour (fp64) */
+
+#define ICPB200_BRUTE_MAX_POINTS 4096
+
+/* ---- library / device ------------------------------------------------- */
+
+/* Bind this process to CUDA device `device` (-1: keep the current device) and
+ * create the library's stream and workspaces.  Idempotent for the same
+ * device. */
+int icpb200_init(int device);
+void icpb200_shutdown(void);
+const char *icpb200_last_error(void);
+/* Number of CUDA kernels this library has launched since load (bench.py's
+ * gpu_launches). */
+int64_t icpb200_launch_count(void);
+/* Compile-time facts for tests: returns the sm architecture the kernels were
+ * built for (100 for sm_100a). */
+int icpb200_built_arch(void);
+
+/* ---- ICP registration  (replaces utilities/icp.py:132-223) ------------- */
+
+/*
+ * Register n_pairs independent (source, target) pairs.  Pair p's source is
+ * src[src_off[p] .. src_off[p+1]) (rows of `dim` float64, C order), likewise
+ * the target.  R_init / t_init: n_pairs*dim*dim / n_pairs*dim values, or NULL
+ * for the identity start (the reference uses the initial guess only when
+ * BOTH are given, icp.py:153).  max_corr_dist < 0 means None (icp.py:169).
+ * Outputs: R_out n_pairs*dim*dim (row major), t_out n_pairs*dim, err_out,
+ * prev_err_out (error of the iteration before the last one, +inf if none; may
+ * be NULL -- it lets a caller print the reference's `delta`, icp.py:216-218),
+ * iters_out (completed solve steps), status_out (ICPB200_* above); the
+ * forward transform is p' = R p + t as in the reference.
+ * A single ICP() call is n_pairs = 1.
+ */
+int icpb200_icp_batch(int n_pairs, int dim,
+                      const double *src, const int64_t *src_off,
+                      const double *tgt, const int64_t *tgt_off,
+                      const double *R_init, const double *t_init,
+                      double error_threshold, int max_iterations, double voxel_size,
+                      int method, int normal_k, double max_corr_dist, int nn_mode,
+                      double *R_out, double *t_out, double *err_out, double *prev_err_out,
+                      int32_t *iters_out, int32_t *status_out);
+
+/*
+ * Same registration loop over pairs drawn from one set of clouds (scan
+ * history): cloud c is pts[cloud_off[c] .. cloud_off[c+1]); pair p registers
+ * cloud src_idx[p] onto cloud tgt_idx[p].  This is the batch seam of the
+ * reference's loop-closure candidate loop (slam.py:575-579) and of offline
+ * scan-pair sweeps; the clouds cross PCIe once.
+ */
+int icpb200_icp_pairs(int n_clouds, int dim,
+                      const double *pts, const int64_t *cloud_off,
+                      int n_pairs, const int32_t *src_idx, const int32_t *tgt_idx,
+                      const double *R_init, const double *t_init,
+                      double error_threshold, int max_iterations, double voxel_size,
+                      int method, int normal_k, double max_corr_dist, int nn_mode,
+                      double *R_out, double *t_out, double *err_out, double *prev_err_out,
+                      int32_t *iters_out, int32_t *status_out);
+
+/*
+ * Device-resident variant of icpb200_icp_pairs: every pointer is a device
+ * pointer, work is enqueued on `stream` (a cudaStream_t; NULL = the library
+ * stream) and the call returns without synchronising.  max_cloud_points is an
+ * upper bound on the raw size of any cloud (sizes workspaces).
+ */
+int icpb200_icp_pairs_dev(int n_clouds, int dim,
+                          const double *d_pts, const int64_t *d_cloud_off,
+                          int64_t max_cloud_points,
+                          int n_pairs, const int32_t *d_src_idx, const int32_t *d_tgt_idx,
+                          const double *d_R_init, const double *d_t_init,
+                          double error_threshold, int max_iterations, double voxel_size,
+                          int method, int normal_k, double max_corr_dist, int nn_mode,
+                          double *d_R_out, double *d_t_out, double *d_err_out, double *d_prev_err_out,
+                          int32_t *d_iters_out, int32_t *d_status_out, void *stream);
+
+/*
+ * One registration with its intermediate state exposed, for parity tests:
+ * the voxel-downsampled clouds (icp.py:150-151), the target normals
+ * (icp.py:165-167; 2-D point-to-line only) and the correspondence indices of
+ * the first trace_iters iterations (icp.py:179).  Buffers may be NULL.
+ * src_ds / tgt_ds need n_src*dim / n_tgt*dim doubles, normals n_tgt*2,
+ * matches trace_iters*n_src int32 (row i = iteration i, -1 where unused).
+ */
+int icpb200_icp_trace(int dim, const double *src, int64_t n_src,
+                      const double *tgt, int64_t n_tgt,
+                      const double *R_init, const double *t_init,
+                      double error_threshold, int max_iterations, double voxel_size,
+                      int method, int normal_k, double max_corr_dist, int nn_mode,
+                      double *R_out, double *t_out, double *err_out, double *prev_err_out,
+                      int32_t *iters_out, int32_t *status_out,
+                      double *src_ds, int64_t *n_src_ds,
+                      double *tgt_ds, int64_t *n_tgt_ds,
+                      double *normals, int32_t *matches, int trace_iters);
+
+/* Voxel-grid mean downsample (replaces utilities/icp.py:117-129).  `out`
+ * needs n*dim doubles; *n_out receives the number of occupied voxels; rows
+ * are in lexicographic voxel-index order like np.unique(axis=0). */
+int icpb200_voxel_downsample(const double *pts, int64_t n, int dim, double voxel_size,
+                             double *out, int64_t *n_out);
+
+/* ---- occupancy grid  (replaces utilities/mapping.py:28-145) ------------ */
+
+/* mapping.py:28-52.  The caller computes nx, ny, l_hit, l_miss exactly as the
+ * reference does (ceil of extent/resolution; log(p/(1-p)) in float64). */
+void *icpb200_grid_create(int nx, int ny, double min_x, double min_y, double resolution,
+                          double l_hit, double l_miss, double lo_min, double lo_max);
+void icpb200_grid_destroy(void *grid);
+
+/* Multi-GPU spatial sharding: this process updates only the tiles t with
+ * t % world == rank (block-cyclic over 64x64-cell tiles); all other cells
+ * stay 0, so an element-wise sum over ranks reassembles the map. */
+int icpb200_grid_set_shard(void *grid, int rank, int world);
+
+/* mapping.py:103-141 for n_scans scans applied in array order (n_scans = 1 is
+ * update_scan; n_scans > 1 is the _rebuild_map replay, slam.py:271-277).
+ * origins: n_scans*2; hits: rows of 2 float64; scan s owns rows
+ * hit_off[s] .. hit_off[s+1]. */
+int icpb200_grid_update(void *grid, int n_scans, const double *origins,
+                        const double *hits, const int64_t *hit_off);
+/* Device-resident inputs, stream-ordered on `stream` (NULL = library stream).
+ * total_hits = hit_off[n_scans] must be supplied by the caller. */
+int icpb200_grid_update_dev(void *grid, int n_scans, const double *d_origins,
+                            const double *d_hits, const int64_t *d_hit_off,
+                            int64_t total_hits, void *stream);
+/* Copy the (ny, nx) float32 log-odds array, row major [iy][ix], to `out`. */
+int icpb200_grid_read(void *grid, float *out);
+/* mapping.py:143-145 */
+int icpb200_grid_reset(void *grid);
+/* Raw device pointer of the ny*nx float32 grid (for NCCL reductions issued by
+ * the host framework). */
+void *icpb200_grid_device_ptr(void *grid);
+/* Counters of the most recent update call: stats[0] = rays, stats[1] =
+ * in-bounds free-cell updates (traversed cells), stats[2] = in-bounds hit
+ * updates, stats[3] = tile runs.  Used by bench.py for the roofline bytes. */
+int icpb200_grid_last_stats(void *grid, int64_t *stats4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICP_B200_H */

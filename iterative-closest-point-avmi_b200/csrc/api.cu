@@ -1,0 +1,578 @@
+// C ABI of libicp_b200.so (declared in include/icp_b200.h): argument checking,
+// host <-> device staging, workspace management and kernel launches.  No
+// compute happens on the host and there is no CPU fallback: every compute
+// entry point fails with ICPB200_ERR_CUDA when no CUDA device is usable.
+#include <stdarg.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "icp_b200.h"
+#include "common.cuh"
+#include "icp_kernel.h"
+#include "occupancy.h"
+
+namespace icpb {
+
+std::mutex g_api_mutex;
+long long g_launches = 0;
+static char g_error[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 4 + 256;            // grow geometrically
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        e = cudaMalloc(&p, bytes);                    // exact size as a second try
+        want = bytes;
+    }
+    if (e != cudaSuccess) {
+        p = nullptr;
+        set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return ICPB200_ERR_CUDA;
+    }
+    cap = want;
+    return 0;
+}
+
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+static Context g_ctx;
+Context& ctx() { return g_ctx; }
+
+static int init_locked(int device) {
+    Context& c = g_ctx;
+    if (c.ready && (device < 0 || device == c.device)) {
+        ICPB_CUDA(cudaSetDevice(c.device));
+        return ICPB200_OK;
+    }
+    if (c.ready) {
+        set_error("icpb200_init: already bound to device %d (one process drives one GPU)", c.device);
+        return ICPB200_ERR_ARG;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("no usable CUDA device (%s); libicp_b200 has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return ICPB200_ERR_CUDA;
+    }
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= count) {
+        set_error("icpb200_init: device %d requested but only %d visible", device, count);
+        return ICPB200_ERR_ARG;
+    }
+    ICPB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    ICPB_CUDA(cudaGetDeviceProperties(&prop, device));
+    c.device = device;
+    c.sm_count = prop.multiProcessorCount;
+    c.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    ICPB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    c.ready = true;
+    return ICPB200_OK;
+}
+
+int ensure_ready() { return g_ctx.ready ? init_locked(-1) : init_locked(-1); }
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+struct IcpCommon {
+    int dim;
+    double error_threshold;
+    int max_iterations;
+    double voxel_size;
+    int method, normal_k;
+    double max_corr_dist;
+    int nn_mode;
+};
+
+static int check_common(const IcpCommon& k, const char* who) {
+    if (k.dim != 2 && k.dim != 3) { set_error("%s: dim must be 2 or 3 (got %d)", who, k.dim); return ICPB200_ERR_ARG; }
+    if (!(k.voxel_size > 0.0)) { set_error("%s: voxel_size must be > 0", who); return ICPB200_ERR_ARG; }
+    if (k.max_iterations < 0) { set_error("%s: max_iterations must be >= 0", who); return ICPB200_ERR_ARG; }
+    if (k.method != ICPB200_POINT_TO_POINT && k.method != ICPB200_POINT_TO_LINE) {
+        set_error("%s: unknown method %d", who, k.method); return ICPB200_ERR_ARG;
+    }
+    if (k.method == ICPB200_POINT_TO_LINE && k.dim == 2) {
+        if (k.normal_k < 1) { set_error("%s: normal_k must be >= 1 for point_to_line", who); return ICPB200_ERR_ARG; }
+        if (k.normal_k > 63) { set_error("%s: normal_k > 63 is not supported by this build", who); return ICPB200_ERR_LIMIT; }
+    }
+    if (k.nn_mode < 0 || k.nn_mode > 2) { set_error("%s: unknown nn_mode %d", who, k.nn_mode); return ICPB200_ERR_ARG; }
+    return ICPB200_OK;
+}
+
+struct DevClouds {                 // one set of clouds resident on the device
+    const double* pts;
+    const long long* off;
+    const int* idx;                // per pair, or nullptr (pair p -> cloud p)
+    long long max_points;          // largest raw cloud
+};
+
+// Enqueue the registration of n_pairs pairs on `st` (device pointers everywhere).
+static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, const DevClouds& t,
+                       const double* d_R_init, const double* d_t_init, double* d_R, double* d_t,
+                       double* d_err, double* d_prev, int* d_iters, int* d_status, cudaStream_t st,
+                       double* tr_src, double* tr_tgt, double* tr_nrm, int* tr_match, int tr_iters, int* tr_counts) {
+    Context& c = g_ctx;
+    if (n_pairs == 0) return ICPB200_OK;
+    const long long biggest = std::max(s.max_points, t.max_points);
+    if (k.nn_mode == ICPB200_NN_GRID || biggest > ICPB200_BRUTE_MAX_POINTS) {
+        set_error("icp: clouds of %lld raw points need the grid nearest-neighbour path, which this build "
+                  "does not contain yet (brute-force limit %d)", biggest, ICPB200_BRUTE_MAX_POINTS);
+        return ICPB200_ERR_LIMIT;
+    }
+    IcpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_pairs = n_pairs;
+    a.src = s.pts; a.src_off = s.off; a.src_idx = s.idx;
+    a.tgt = t.pts; a.tgt_off = t.off; a.tgt_idx = t.idx;
+    a.R_init = d_R_init; a.t_init = d_t_init;
+    a.err_thr = k.error_threshold; a.max_iter = k.max_iterations; a.voxel = k.voxel_size;
+    a.method = k.method; a.normal_k = k.normal_k; a.max_corr = k.max_corr_dist;
+    a.R_out = d_R; a.t_out = d_t; a.err_out = d_err; a.prev_out = d_prev; a.iters_out = d_iters; a.status_out = d_status;
+    a.cap_s = round_up((int)std::max<long long>(s.max_points, 32), 32);
+    a.cap_t = round_up((int)std::max<long long>(t.max_points, 32), 32);
+    a.sort_pad = next_pow2((int)std::max<long long>(biggest, 256));
+    const size_t smem = icp_smem_bytes(k.dim, a.cap_s, a.cap_t, a.sort_pad);
+    if (smem > (size_t)c.max_smem_optin) {
+        set_error("icp: %zu bytes of shared memory needed, device allows %d", smem, c.max_smem_optin);
+        return ICPB200_ERR_LIMIT;
+    }
+    const int per_sm = icp_max_ctas_per_sm(k.dim, smem);
+    const int n_ctas = std::min(n_pairs, c.sm_count * per_sm);
+    a.ws_stride = icp_ws_doubles(k.dim, a.cap_s, a.cap_t);
+    if (c.icp_ws.reserve(sizeof(double) * a.ws_stride * (size_t)n_ctas)) return ICPB200_ERR_CUDA;
+    if (c.queue.reserve(sizeof(unsigned))) return ICPB200_ERR_CUDA;
+    a.ws = c.icp_ws.as<double>();
+    a.queue = c.queue.as<unsigned>();
+    a.trace_src = tr_src; a.trace_tgt = tr_tgt; a.trace_nrm = tr_nrm;
+    a.trace_match = tr_match; a.trace_iters = tr_iters; a.trace_counts = tr_counts;
+    ICPB_CUDA(cudaMemsetAsync(a.queue, 0, sizeof(unsigned), st));
+    return launch_icp_pairs(a, k.dim, n_ctas, smem, st);
+}
+
+static int check_offsets(const int64_t* off, int n, const char* what, long long* max_points) {
+    long long mx = 0;
+    if (off[0] != 0) { set_error("%s[0] must be 0", what); return ICPB200_ERR_ARG; }
+    for (int i = 0; i < n; ++i) {
+        const long long len = off[i + 1] - off[i];
+        if (len <= 0) { set_error("%s: cloud %d is empty or offsets decrease", what, i); return ICPB200_ERR_ARG; }
+        mx = std::max(mx, len);
+    }
+    *max_points = mx;
+    return ICPB200_OK;
+}
+
+struct IcpOutputs { double* R; double* t; double* err; double* prev; int32_t* iters; int32_t* status; };
+
+static int fetch_outputs(Context& c, int n_pairs, int dim, const IcpOutputs& o) {
+    ICPB_CUDA(cudaMemcpyAsync(o.R, c.out_r.p, sizeof(double) * dim * dim * (size_t)n_pairs, cudaMemcpyDeviceToHost, c.stream));
+    ICPB_CUDA(cudaMemcpyAsync(o.t, c.out_t.p, sizeof(double) * dim * (size_t)n_pairs, cudaMemcpyDeviceToHost, c.stream));
+    ICPB_CUDA(cudaMemcpyAsync(o.err, c.out_err.p, sizeof(double) * (size_t)n_pairs, cudaMemcpyDeviceToHost, c.stream));
+    if (o.prev) ICPB_CUDA(cudaMemcpyAsync(o.prev, c.out_prev.p, sizeof(double) * (size_t)n_pairs, cudaMemcpyDeviceToHost, c.stream));
+    ICPB_CUDA(cudaMemcpyAsync(o.iters, c.out_iters.p, sizeof(int) * (size_t)n_pairs, cudaMemcpyDeviceToHost, c.stream));
+    ICPB_CUDA(cudaMemcpyAsync(o.status, c.out_status.p, sizeof(int) * (size_t)n_pairs, cudaMemcpyDeviceToHost, c.stream));
+    ICPB_CUDA(cudaStreamSynchronize(c.stream));
+    return ICPB200_OK;
+}
+
+static int reserve_outputs(Context& c, int n_pairs, int dim) {
+    if (c.out_r.reserve(sizeof(double) * dim * dim * (size_t)n_pairs) || c.out_t.reserve(sizeof(double) * dim * (size_t)n_pairs) ||
+        c.out_err.reserve(sizeof(double) * (size_t)n_pairs) || c.out_prev.reserve(sizeof(double) * (size_t)n_pairs) || c.out_iters.reserve(sizeof(int) * (size_t)n_pairs) ||
+        c.out_status.reserve(sizeof(int) * (size_t)n_pairs))
+        return ICPB200_ERR_CUDA;
+    return ICPB200_OK;
+}
+
+static int upload_init(Context& c, int n_pairs, int dim, const double* R_init, const double* t_init,
+                       const double** d_R, const double** d_t) {
+    *d_R = nullptr; *d_t = nullptr;
+    if (R_init && t_init) {                         // icp.py:153: both or neither
+        if (c.rinit.reserve(sizeof(double) * dim * dim * (size_t)n_pairs) || c.tinit.reserve(sizeof(double) * dim * (size_t)n_pairs))
+            return ICPB200_ERR_CUDA;
+        ICPB_CUDA(cudaMemcpyAsync(c.rinit.p, R_init, sizeof(double) * dim * dim * (size_t)n_pairs, cudaMemcpyHostToDevice, c.stream));
+        ICPB_CUDA(cudaMemcpyAsync(c.tinit.p, t_init, sizeof(double) * dim * (size_t)n_pairs, cudaMemcpyHostToDevice, c.stream));
+        *d_R = c.rinit.as<double>();
+        *d_t = c.tinit.as<double>();
+    }
+    return ICPB200_OK;
+}
+
+}  // namespace icpb
+
+using namespace icpb;
+
+extern "C" {
+
+int icpb200_init(int device) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    return init_locked(device);
+}
+
+void icpb200_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    Context& c = g_ctx;
+    if (!c.ready) return;
+    cudaSetDevice(c.device);
+    cudaStreamSynchronize(c.stream);
+    DevBuf* bufs[] = {&c.pts_a, &c.pts_b, &c.off_a, &c.off_b, &c.idx_a, &c.idx_b, &c.rinit, &c.tinit, &c.out_r,
+                      &c.out_t, &c.out_err, &c.out_prev, &c.out_iters, &c.out_status, &c.icp_ws, &c.queue, &c.trace,
+                      &c.vox_in, &c.vox_out};
+    for (DevBuf* b : bufs) b->release();
+    cudaStreamDestroy(c.stream);
+    c.stream = nullptr;
+    c.ready = false;
+    c.device = -1;
+}
+
+const char* icpb200_last_error(void) { return g_error; }
+int64_t icpb200_launch_count(void) { return g_launches; }
+int icpb200_built_arch(void) { return 100; }
+
+int icpb200_icp_batch(int n_pairs, int dim, const double* src, const int64_t* src_off, const double* tgt,
+                      const int64_t* tgt_off, const double* R_init, const double* t_init, double error_threshold,
+                      int max_iterations, double voxel_size, int method, int normal_k, double max_corr_dist,
+                      int nn_mode, double* R_out, double* t_out, double* err_out, double* prev_err_out,
+                      int32_t* iters_out, int32_t* status_out) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    const IcpCommon k{dim, error_threshold, max_iterations, voxel_size, method, normal_k, max_corr_dist, nn_mode};
+    int rc = check_common(k, "icpb200_icp_batch");
+    if (rc) return rc;
+    if (n_pairs < 0 || (n_pairs > 0 && (!src || !src_off || !tgt || !tgt_off || !R_out || !t_out || !err_out || !iters_out || !status_out))) {
+        set_error("icpb200_icp_batch: null pointer or negative n_pairs");
+        return ICPB200_ERR_ARG;
+    }
+    if (n_pairs == 0) return ICPB200_OK;
+    long long max_s, max_t;
+    if ((rc = check_offsets(src_off, n_pairs, "src_off", &max_s))) return rc;
+    if ((rc = check_offsets(tgt_off, n_pairs, "tgt_off", &max_t))) return rc;
+    if ((rc = init_locked(-1))) return rc;
+    Context& c = g_ctx;
+    const size_t ns = (size_t)src_off[n_pairs], nt = (size_t)tgt_off[n_pairs];
+    if (c.pts_a.reserve(sizeof(double) * dim * ns) || c.pts_b.reserve(sizeof(double) * dim * nt) ||
+        c.off_a.reserve(sizeof(int64_t) * (n_pairs + 1)) || c.off_b.reserve(sizeof(int64_t) * (n_pairs + 1)))
+        return ICPB200_ERR_CUDA;
+    if ((rc = reserve_outputs(c, n_pairs, dim))) return rc;
+    ICPB_CUDA(cudaMemcpyAsync(c.pts_a.p, src, sizeof(double) * dim * ns, cudaMemcpyHostToDevice, c.stream));
+    ICPB_CUDA(cudaMemcpyAsync(c.pts_b.p, tgt, sizeof(double) * dim * nt, cudaMemcpyHostToDevice, c.stream));
+    ICPB_CUDA(cudaMemcpyAsync(c.off_a.p, src_off, sizeof(int64_t) * (n_pairs + 1), cudaMemcpyHostToDevice, c.stream));
+    ICPB_CUDA(cudaMemcpyAsync(c.off_b.p, tgt_off, sizeof(int64_t) * (n_pairs + 1), cudaMemcpyHostToDevice, c.stream));
+    const double *d_Ri, *d_ti;
+    if ((rc = upload_init(c, n_pairs, dim, R_init, t_init, &d_Ri, &d_ti))) return rc;
+    const DevClouds s{c.pts_a.as<double>(), c.off_a.as<long long>(), nullptr, max_s};
+    const DevClouds t{c.pts_b.as<double>(), c.off_b.as<long long>(), nullptr, max_t};
+    rc = icp_enqueue(k, n_pairs, s, t, d_Ri, d_ti, c.out_r.as<double>(), c.out_t.as<double>(), c.out_err.as<double>(),
+                     c.out_prev.as<double>(), c.out_iters.as<int>(), c.out_status.as<int>(), c.stream, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
+    if (rc) return rc;
+    return fetch_outputs(c, n_pairs, dim, IcpOutputs{R_out, t_out, err_out, prev_err_out, iters_out, status_out});
+}
+
+int icpb200_icp_pairs(int n_clouds, int dim, const double* pts, const int64_t* cloud_off, int n_pairs,
+                      const int32_t* src_idx, const int32_t* tgt_idx, const double* R_init, const double* t_init,
+                      double error_threshold, int max_iterations, double voxel_size, int method, int normal_k,
+                      double max_corr_dist, int nn_mode, double* R_out, double* t_out, double* err_out,
+                      double* prev_err_out, int32_t* iters_out, int32_t* status_out) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    const IcpCommon k{dim, error_threshold, max_iterations, voxel_size, method, normal_k, max_corr_dist, nn_mode};
+    int rc = check_common(k, "icpb200_icp_pairs");
+    if (rc) return rc;
+    if (n_pairs < 0 || n_clouds < 0 || (n_pairs > 0 && (!pts || !cloud_off || !src_idx || !tgt_idx || !R_out || !t_out || !err_out || !iters_out || !status_out))) {
+        set_error("icpb200_icp_pairs: null pointer or negative count");
+        return ICPB200_ERR_ARG;
+    }
+    if (n_pairs == 0) return ICPB200_OK;
+    long long max_pts;
+    if ((rc = check_offsets(cloud_off, n_clouds, "cloud_off", &max_pts))) return rc;
+    for (int p = 0; p < n_pairs; ++p)
+        if (src_idx[p] < 0 || src_idx[p] >= n_clouds || tgt_idx[p] < 0 || tgt_idx[p] >= n_clouds) {
+            set_error("icpb200_icp_pairs: pair %d references a cloud outside [0, %d)", p, n_clouds);
+            return ICPB200_ERR_ARG;
+        }
+    if ((rc = init_locked(-1))) return rc;
+    Context& c = g_ctx;
+    const size_t np = (size_t)cloud_off[n_clouds];
+    if (c.pts_a.reserve(sizeof(double) * dim * np) || c.off_a.reserve(sizeof(int64_t) * (n_clouds + 1)) ||
+        c.idx_a.reserve(sizeof(int32_t) * (size_t)n_pairs) || c.idx_b.reserve(sizeof(int32_t) * (size_t)n_pairs))
+        return ICPB200_ERR_CUDA;
+    if ((rc = reserve_outputs(c, n_pairs, dim))) return rc;
+    ICPB_CUDA(cudaMemcpyAsync(c.pts_a.p, pts, sizeof(double) * dim * np, cudaMemcpyHostToDevice, c.stream));
+    ICPB_CUDA(cudaMemcpyAsync(c.off_a.p, cloud_off, sizeof(int64_t) * (n_clouds + 1), cudaMemcpyHostToDevice, c.stream));
+    ICPB_CUDA(cudaMemcpyAsync(c.idx_a.p, src_idx, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyHostToDevice, c.stream));
+    ICPB_CUDA(cudaMemcpyAsync(c.idx_b.p, tgt_idx, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyHostToDevice, c.stream));
+    const double *d_Ri, *d_ti;
+    if ((rc = upload_init(c, n_pairs, dim, R_init, t_init, &d_Ri, &d_ti))) return rc;
+    const DevClouds s{c.pts_a.as<double>(), c.off_a.as<long long>(), c.idx_a.as<int>(), max_pts};
+    const DevClouds t{c.pts_a.as<double>(), c.off_a.as<long long>(), c.idx_b.as<int>(), max_pts};
+    rc = icp_enqueue(k, n_pairs, s, t, d_Ri, d_ti, c.out_r.as<double>(), c.out_t.as<double>(), c.out_err.as<double>(),
+                     c.out_prev.as<double>(), c.out_iters.as<int>(), c.out_status.as<int>(), c.stream, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
+    if (rc) return rc;
+    return fetch_outputs(c, n_pairs, dim, IcpOutputs{R_out, t_out, err_out, prev_err_out, iters_out, status_out});
+}
+
+int icpb200_icp_pairs_dev(int n_clouds, int dim, const double* d_pts, const int64_t* d_cloud_off,
+                          int64_t max_cloud_points, int n_pairs, const int32_t* d_src_idx, const int32_t* d_tgt_idx,
+                          const double* d_R_init, const double* d_t_init, double error_threshold, int max_iterations,
+                          double voxel_size, int method, int normal_k, double max_corr_dist, int nn_mode,
+                          double* d_R_out, double* d_t_out, double* d_err_out, double* d_prev_err_out,
+                          int32_t* d_iters_out, int32_t* d_status_out, void* stream) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    const IcpCommon k{dim, error_threshold, max_iterations, voxel_size, method, normal_k, max_corr_dist, nn_mode};
+    int rc = check_common(k, "icpb200_icp_pairs_dev");
+    if (rc) return rc;
+    if (n_pairs < 0 || n_clouds <= 0 || max_cloud_points <= 0 || !d_pts || !d_cloud_off || !d_src_idx || !d_tgt_idx ||
+        !d_R_out || !d_t_out || !d_err_out || !d_iters_out || !d_status_out) {
+        set_error("icpb200_icp_pairs_dev: null pointer or bad count");
+        return ICPB200_ERR_ARG;
+    }
+    if ((rc = init_locked(-1))) return rc;
+    Context& c = g_ctx;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c.stream;
+    const DevClouds s{d_pts, (const long long*)d_cloud_off, d_src_idx, max_cloud_points};
+    const DevClouds t{d_pts, (const long long*)d_cloud_off, d_tgt_idx, max_cloud_points};
+    const bool init = d_R_init && d_t_init;
+    return icp_enqueue(k, n_pairs, s, t, init ? d_R_init : nullptr, init ? d_t_init : nullptr, d_R_out, d_t_out,
+                       d_err_out, d_prev_err_out, d_iters_out, d_status_out, st, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
+}
+
+int icpb200_icp_trace(int dim, const double* src, int64_t n_src, const double* tgt, int64_t n_tgt,
+                      const double* R_init, const double* t_init, double error_threshold, int max_iterations,
+                      double voxel_size, int method, int normal_k, double max_corr_dist, int nn_mode, double* R_out,
+                      double* t_out, double* err_out, double* prev_err_out, int32_t* iters_out, int32_t* status_out, double* src_ds,
+                      int64_t* n_src_ds, double* tgt_ds, int64_t* n_tgt_ds, double* normals, int32_t* matches,
+                      int trace_iters) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    const IcpCommon k{dim, error_threshold, max_iterations, voxel_size, method, normal_k, max_corr_dist, nn_mode};
+    int rc = check_common(k, "icpb200_icp_trace");
+    if (rc) return rc;
+    if (!src || !tgt || n_src <= 0 || n_tgt <= 0 || !R_out || !t_out || !err_out || !iters_out || !status_out || trace_iters < 0) {
+        set_error("icpb200_icp_trace: null pointer or empty cloud");
+        return ICPB200_ERR_ARG;
+    }
+    if ((rc = init_locked(-1))) return rc;
+    Context& c = g_ctx;
+    const int64_t off_s[2] = {0, n_src}, off_t[2] = {0, n_tgt};
+    if (c.pts_a.reserve(sizeof(double) * dim * (size_t)n_src) || c.pts_b.reserve(sizeof(double) * dim * (size_t)n_tgt) ||
+        c.off_a.reserve(sizeof(int64_t) * 2) || c.off_b.reserve(sizeof(int64_t) * 2))
+        return ICPB200_ERR_CUDA;
+    if ((rc = reserve_outputs(c, 1, dim))) return rc;
+    // trace buffer: src_ds | tgt_ds | normals | counts(2 ints, padded) | matches
+    const size_t b_src = sizeof(double) * dim * (size_t)n_src, b_tgt = sizeof(double) * dim * (size_t)n_tgt;
+    const size_t b_nrm = sizeof(double) * 2 * (size_t)n_tgt, b_cnt = 16;
+    const size_t b_mat = sizeof(int) * (size_t)n_src * (size_t)trace_iters;
+    if (c.trace.reserve(b_src + b_tgt + b_nrm + b_cnt + b_mat + 64)) return ICPB200_ERR_CUDA;
+    unsigned char* base = c.trace.as<unsigned char>();
+    double* d_src_ds = reinterpret_cast<double*>(base);
+    double* d_tgt_ds = reinterpret_cast<double*>(base + b_src);
+    double* d_nrm = reinterpret_cast<double*>(base + b_src + b_tgt);
+    int* d_cnt = reinterpret_cast<int*>(base + b_src + b_tgt + b_nrm);
+    int* d_mat = reinterpret_cast<int*>(base + b_src + b_tgt + b_nrm + b_cnt);
+    ICPB_CUDA(cudaMemsetAsync(base, 0, b_src + b_tgt + b_nrm + b_cnt, c.stream));
+    if (b_mat) ICPB_CUDA(cudaMemsetAsync(d_mat, 0xff, b_mat, c.stream));
+    ICPB_CUDA(cudaMemcpyAsync(c.pts_a.p, src, b_src, cudaMemcpyHostToDevice, c.stream));
+    ICPB_CUDA(cudaMemcpyAsync(c.pts_b.p, tgt, b_tgt, cudaMemcpyHostToDevice, c.stream));
+    ICPB_CUDA(cudaMemcpyAsync(c.off_a.p, off_s, sizeof(off_s), cudaMemcpyHostToDevice, c.stream));
+    ICPB_CUDA(cudaMemcpyAsync(c.off_b.p, off_t, sizeof(off_t), cudaMemcpyHostToDevice, c.stream));
+    const double *d_Ri, *d_ti;
+    if ((rc = upload_init(c, 1, dim, R_init, t_init, &d_Ri, &d_ti))) return rc;
+    const DevClouds s{c.pts_a.as<double>(), c.off_a.as<long long>(), nullptr, n_src};
+    const DevClouds t{c.pts_b.as<double>(), c.off_b.as<long long>(), nullptr, n_tgt};
+    rc = icp_enqueue(k, 1, s, t, d_Ri, d_ti, c.out_r.as<double>(), c.out_t.as<double>(), c.out_err.as<double>(),
+                     c.out_prev.as<double>(), c.out_iters.as<int>(), c.out_status.as<int>(), c.stream, d_src_ds, d_tgt_ds, d_nrm,
+                     trace_iters > 0 && matches ? d_mat : nullptr, trace_iters, d_cnt);
+    if (rc) return rc;
+    int counts[2] = {0, 0};
+    ICPB_CUDA(cudaMemcpyAsync(counts, d_cnt, sizeof(counts), cudaMemcpyDeviceToHost, c.stream));
+    if (src_ds) ICPB_CUDA(cudaMemcpyAsync(src_ds, d_src_ds, b_src, cudaMemcpyDeviceToHost, c.stream));
+    if (tgt_ds) ICPB_CUDA(cudaMemcpyAsync(tgt_ds, d_tgt_ds, b_tgt, cudaMemcpyDeviceToHost, c.stream));
+    if (normals) ICPB_CUDA(cudaMemcpyAsync(normals, d_nrm, b_nrm, cudaMemcpyDeviceToHost, c.stream));
+    if (matches && b_mat) ICPB_CUDA(cudaMemcpyAsync(matches, d_mat, b_mat, cudaMemcpyDeviceToHost, c.stream));
+    rc = fetch_outputs(c, 1, dim, IcpOutputs{R_out, t_out, err_out, prev_err_out, iters_out, status_out});
+    if (rc) return rc;
+    if (n_src_ds) *n_src_ds = counts[0];
+    if (n_tgt_ds) *n_tgt_ds = counts[1];
+    return ICPB200_OK;
+}
+
+int icpb200_voxel_downsample(const double* pts, int64_t n, int dim, double voxel_size, double* out, int64_t* n_out) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!pts || !out || !n_out || n <= 0 || (dim != 2 && dim != 3) || !(voxel_size > 0.0)) {
+        set_error("icpb200_voxel_downsample: bad argument (n=%lld, dim=%d, voxel=%g)", (long long)n, dim, voxel_size);
+        return ICPB200_ERR_ARG;
+    }
+    int rc = init_locked(-1);
+    if (rc) return rc;
+    Context& c = g_ctx;
+    const int sort_pad = next_pow2((int)std::max<int64_t>(n, 256));
+    if (n > 16384) {
+        set_error("icpb200_voxel_downsample: %lld points exceed the single-CTA limit of 16384 in this build", (long long)n);
+        return ICPB200_ERR_LIMIT;
+    }
+    if (c.vox_in.reserve(sizeof(double) * dim * (size_t)n) || c.vox_out.reserve(sizeof(double) * dim * (size_t)n + 16))
+        return ICPB200_ERR_CUDA;
+    ICPB_CUDA(cudaMemcpyAsync(c.vox_in.p, pts, sizeof(double) * dim * (size_t)n, cudaMemcpyHostToDevice, c.stream));
+    int* d_n = reinterpret_cast<int*>(c.vox_out.as<unsigned char>() + sizeof(double) * dim * (size_t)n);
+    if ((rc = launch_voxel(c.vox_in.as<double>(), (int)n, dim, voxel_size, c.vox_out.as<double>(), d_n, sort_pad, c.stream)))
+        return rc;
+    int m = 0;
+    ICPB_CUDA(cudaMemcpyAsync(&m, d_n, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    ICPB_CUDA(cudaStreamSynchronize(c.stream));
+    if (m < 0) {
+        set_error("icpb200_voxel_downsample: voxel index range does not fit 62 bits");
+        return ICPB200_ERR_LIMIT;
+    }
+    ICPB_CUDA(cudaMemcpy(out, c.vox_out.p, sizeof(double) * dim * (size_t)m, cudaMemcpyDeviceToHost));
+    *n_out = m;
+    return ICPB200_OK;
+}
+
+// ---- occupancy grid --------------------------------------------------------------
+
+void OccGrid::release_all() {
+    DevBuf* bufs[] = {&grid, &origins, &hits, &hit_off, &origin_cell, &ray_cell, &ray_scan,
+                      &counts, &offsets, &sums, &runs, &order, &small};
+    for (DevBuf* b : bufs) b->release();
+}
+
+void* icpb200_grid_create(int nx, int ny, double min_x, double min_y, double resolution, double l_hit,
+                          double l_miss, double lo_min, double lo_max) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (nx <= 0 || ny <= 0 || !(resolution > 0.0) || !(lo_min <= lo_max)) {
+        set_error("icpb200_grid_create: bad argument (nx=%d ny=%d resolution=%g clamp=[%g,%g])", nx, ny, resolution, lo_min, lo_max);
+        return nullptr;
+    }
+    if ((long long)nx * ny > (1LL << 31)) { set_error("icpb200_grid_create: grid larger than 2^31 cells"); return nullptr; }
+    if (init_locked(-1)) return nullptr;
+    OccGrid* g = new OccGrid();
+    g->nx = nx; g->ny = ny;
+    g->tiles_x = (nx + kOccTile - 1) / kOccTile;
+    g->tiles_y = (ny + kOccTile - 1) / kOccTile;
+    g->min_x = min_x; g->min_y = min_y; g->res = resolution;
+    g->l_hit = l_hit; g->l_miss = l_miss; g->lo_min = lo_min; g->lo_max = lo_max;
+    g->zero_outside_clamp = ((float)lo_min > 0.f) || ((float)lo_max < 0.f);
+    g->apply_ctas = occ_apply_ctas(g_ctx.sm_count);
+    if (g->grid.reserve(sizeof(float) * (size_t)nx * ny) ||
+        cudaMemsetAsync(g->grid.p, 0, sizeof(float) * (size_t)nx * ny, g_ctx.stream) != cudaSuccess ||
+        cudaStreamSynchronize(g_ctx.stream) != cudaSuccess) {
+        if (!g_error[0]) set_error("icpb200_grid_create: device allocation failed");
+        g->release_all();
+        delete g;
+        return nullptr;
+    }
+    return g;
+}
+
+void icpb200_grid_destroy(void* grid) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!grid) return;
+    OccGrid* g = static_cast<OccGrid*>(grid);
+    if (g_ctx.ready) cudaStreamSynchronize(g_ctx.stream);
+    g->release_all();
+    delete g;
+}
+
+int icpb200_grid_set_shard(void* grid, int rank, int world) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!grid || world < 1 || rank < 0 || rank >= world) { set_error("icpb200_grid_set_shard: bad rank/world"); return ICPB200_ERR_ARG; }
+    OccGrid* g = static_cast<OccGrid*>(grid);
+    g->rank = rank; g->world = world;
+    return ICPB200_OK;
+}
+
+int icpb200_grid_update(void* grid, int n_scans, const double* origins, const double* hits, const int64_t* hit_off) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!grid || n_scans < 0 || (n_scans > 0 && (!origins || !hit_off))) { set_error("icpb200_grid_update: null pointer"); return ICPB200_ERR_ARG; }
+    if (n_scans == 0) return ICPB200_OK;
+    if (hit_off[0] != 0) { set_error("icpb200_grid_update: hit_off[0] must be 0"); return ICPB200_ERR_ARG; }
+    for (int s = 0; s < n_scans; ++s)
+        if (hit_off[s + 1] < hit_off[s]) { set_error("icpb200_grid_update: hit_off decreases at scan %d", s); return ICPB200_ERR_ARG; }
+    const long long n_rays = hit_off[n_scans];
+    if (n_rays > 0 && !hits) { set_error("icpb200_grid_update: hits is null"); return ICPB200_ERR_ARG; }
+    int rc = init_locked(-1);
+    if (rc) return rc;
+    OccGrid* g = static_cast<OccGrid*>(grid);
+    cudaStream_t st = g_ctx.stream;
+    if (n_rays == 0) { g->stats[0] = g->stats[1] = g->stats[2] = g->stats[3] = 0; return ICPB200_OK; }
+    if (g->origins.reserve(sizeof(double) * 2 * (size_t)n_scans) || g->hits.reserve(sizeof(double) * 2 * (size_t)n_rays) ||
+        g->hit_off.reserve(sizeof(int64_t) * ((size_t)n_scans + 1)))
+        return ICPB200_ERR_CUDA;
+    ICPB_CUDA(cudaMemcpyAsync(g->origins.p, origins, sizeof(double) * 2 * (size_t)n_scans, cudaMemcpyHostToDevice, st));
+    ICPB_CUDA(cudaMemcpyAsync(g->hits.p, hits, sizeof(double) * 2 * (size_t)n_rays, cudaMemcpyHostToDevice, st));
+    ICPB_CUDA(cudaMemcpyAsync(g->hit_off.p, hit_off, sizeof(int64_t) * ((size_t)n_scans + 1), cudaMemcpyHostToDevice, st));
+    return occ_update_device(*g, n_scans, g->origins.as<double>(), g->hits.as<double>(), g->hit_off.as<long long>(),
+                             reinterpret_cast<const long long*>(hit_off), st);
+}
+
+int icpb200_grid_update_dev(void* grid, int n_scans, const double* d_origins, const double* d_hits,
+                            const int64_t* d_hit_off, int64_t total_hits, void* stream) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!grid || n_scans < 0 || total_hits < 0 || (n_scans > 0 && (!d_origins || !d_hit_off || (total_hits > 0 && !d_hits)))) {
+        set_error("icpb200_grid_update_dev: null pointer or negative count");
+        return ICPB200_ERR_ARG;
+    }
+    if (n_scans == 0 || total_hits == 0) return ICPB200_OK;
+    int rc = init_locked(-1);
+    if (rc) return rc;
+    OccGrid* g = static_cast<OccGrid*>(grid);
+    cudaStream_t st = stream ? (cudaStream_t)stream : g_ctx.stream;
+    std::vector<long long> h_off((size_t)n_scans + 1);
+    ICPB_CUDA(cudaMemcpyAsync(h_off.data(), d_hit_off, sizeof(long long) * h_off.size(), cudaMemcpyDeviceToHost, st));
+    ICPB_CUDA(cudaStreamSynchronize(st));
+    if (h_off[0] != 0 || h_off[n_scans] != total_hits) {
+        set_error("icpb200_grid_update_dev: hit_off[0] must be 0 and hit_off[n_scans] must equal total_hits");
+        return ICPB200_ERR_ARG;
+    }
+    return occ_update_device(*g, n_scans, d_origins, d_hits, reinterpret_cast<const long long*>(d_hit_off), h_off.data(), st);
+}
+
+int icpb200_grid_read(void* grid, float* out) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!grid || !out) { set_error("icpb200_grid_read: null pointer"); return ICPB200_ERR_ARG; }
+    int rc = init_locked(-1);
+    if (rc) return rc;
+    OccGrid* g = static_cast<OccGrid*>(grid);
+    ICPB_CUDA(cudaMemcpyAsync(out, g->grid.p, sizeof(float) * (size_t)g->nx * g->ny, cudaMemcpyDeviceToHost, g_ctx.stream));
+    ICPB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return ICPB200_OK;
+}
+
+int icpb200_grid_reset(void* grid) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!grid) { set_error("icpb200_grid_reset: null pointer"); return ICPB200_ERR_ARG; }
+    int rc = init_locked(-1);
+    if (rc) return rc;
+    OccGrid* g = static_cast<OccGrid*>(grid);
+    ICPB_CUDA(cudaMemsetAsync(g->grid.p, 0, sizeof(float) * (size_t)g->nx * g->ny, g_ctx.stream));   // mapping.py:143-145
+    ICPB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    g->seen_nonempty_scan = false;
+    g->virgin_finalised = false;
+    return ICPB200_OK;
+}
+
+void* icpb200_grid_device_ptr(void* grid) {
+    return grid ? static_cast<OccGrid*>(grid)->grid.p : nullptr;
+}
+
+int icpb200_grid_last_stats(void* grid, int64_t* stats4) {
+    if (!grid || !stats4) { set_error("icpb200_grid_last_stats: null pointer"); return ICPB200_ERR_ARG; }
+    OccGrid* g = static_cast<OccGrid*>(grid);
+    for (int i = 0; i < 4; ++i) stats4[i] = g->stats[i];
+    return ICPB200_OK;
+}
+
+}  // extern "C"

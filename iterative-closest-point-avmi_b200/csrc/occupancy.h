@@ -1,0 +1,39 @@
+// Host-side state of one occupancy grid handle and the device entry point.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace icpb {
+
+constexpr int kOccTile = 64;                       // cells per tile edge (power of two)
+constexpr int kOccMaxChunkScans = 2048;            // scans replayed per tile pass
+constexpr long long kOccMaxMatrix = 16LL << 20;    // (tile, scan) counters per pass
+
+struct OccGrid {
+    int nx = 0, ny = 0, tiles_x = 0, tiles_y = 0;
+    double min_x = 0, min_y = 0, res = 1;
+    double l_hit = 0, l_miss = 0, lo_min = 0, lo_max = 0;
+    int rank = 0, world = 1;
+    int apply_ctas = 0;
+    // A clamp interval that excludes 0 makes the reference's whole-grid clip
+    // (mapping.py:141) move every untouched cell on the first non-empty scan.
+    bool zero_outside_clamp = false;
+    bool seen_nonempty_scan = false;
+    bool virgin_finalised = false;
+    long long stats[4] = {0, 0, 0, 0};
+    DevBuf grid;                                   // ny * nx float32, row major
+    DevBuf origins, hits, hit_off;                 // staging for the host-buffer entry point
+    DevBuf origin_cell, ray_cell, ray_scan;
+    DevBuf counts, offsets, sums, runs, order, small;
+    void release_all();
+};
+
+// d_* are device pointers; h_hit_off is the same offsets array on the host
+// (n_scans + 1 entries, h_hit_off[0] == 0).  Stream-ordered except for one
+// small readback per scan chunk.
+int occ_update_device(OccGrid& g, int n_scans, const double* d_origins, const double* d_hits,
+                      const long long* d_hit_off, const long long* h_hit_off, cudaStream_t st);
+int occ_apply_ctas(int sm_count);
+
+}  // namespace icpb

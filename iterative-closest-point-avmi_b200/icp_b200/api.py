@@ -1,0 +1,184 @@
+"""numpy-facing wrappers over the C ABI: batched registration, voxel
+downsample, occupancy-grid handle.  Host arrays in, host arrays out; all
+compute happens in libicp_b200.so on the GPU."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import (c_double_p, c_float_p, c_int32_p, c_int64_p, check)
+
+METHODS = {"point_to_point": _lib.POINT_TO_POINT, "point_to_line": _lib.POINT_TO_LINE}
+NN_MODES = {"auto": _lib.NN_AUTO, "brute": _lib.NN_BRUTE, "grid": _lib.NN_GRID}
+
+
+def init(device=-1):
+    check(_lib.load().icpb200_init(int(device)), "icpb200_init")
+
+
+def shutdown():
+    _lib.load().icpb200_shutdown()
+
+
+def launch_count():
+    return int(_lib.load().icpb200_launch_count())
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a, typ):
+    return a.ctypes.data_as(typ) if a is not None else None
+
+
+def _method_code(method):
+    # the reference compares the string (icp.py:162); anything that is not
+    # "point_to_line" takes the point-to-point branch
+    return _lib.POINT_TO_LINE if method == "point_to_line" else _lib.POINT_TO_POINT
+
+
+def _init_arrays(R_init, t_init, n_pairs, dim):
+    if R_init is None or t_init is None:          # icp.py:153: both or neither
+        return None, None
+    r = _f64(R_init).reshape(n_pairs, dim, dim)
+    t = _f64(t_init).reshape(n_pairs, dim)
+    return r, t
+
+
+def _alloc_out(n_pairs, dim):
+    return (np.empty((n_pairs, dim, dim)), np.empty((n_pairs, dim)), np.empty(n_pairs), np.empty(n_pairs),
+            np.empty(n_pairs, dtype=np.int32), np.empty(n_pairs, dtype=np.int32))
+
+
+def icp_batch(sources, targets, error_threshold, max_iterations, voxel_size, R_init=None, t_init=None,
+              method="point_to_point", normal_k=10, max_corr_dist=None, nn_mode="auto"):
+    """Register sources[p] onto targets[p] for every p.  Returns dict of arrays
+    R (n,d,d), t (n,d), error (n,), iters (n,), status (n,)."""
+    n_pairs = len(sources)
+    assert len(targets) == n_pairs
+    dim = int(np.asarray(sources[0]).shape[1])
+    from .synth import pack_ragged
+    src, src_off = pack_ragged([_f64(s) for s in sources], dim)
+    tgt, tgt_off = pack_ragged([_f64(t) for t in targets], dim)
+    r0, t0 = _init_arrays(R_init, t_init, n_pairs, dim)
+    R, t, err, prev, iters, status = _alloc_out(n_pairs, dim)
+    rc = _lib.load().icpb200_icp_batch(
+        n_pairs, dim, _ptr(src, c_double_p), _ptr(src_off, c_int64_p), _ptr(tgt, c_double_p), _ptr(tgt_off, c_int64_p),
+        _ptr(r0, c_double_p), _ptr(t0, c_double_p), float(error_threshold), int(max_iterations), float(voxel_size),
+        _method_code(method), int(normal_k), -1.0 if max_corr_dist is None else float(max_corr_dist), NN_MODES[nn_mode],
+        _ptr(R, c_double_p), _ptr(t, c_double_p), _ptr(err, c_double_p), _ptr(prev, c_double_p), _ptr(iters, c_int32_p), _ptr(status, c_int32_p))
+    check(rc, "icpb200_icp_batch")
+    return dict(R=R, t=t, error=err, prev_error=prev, iters=iters, status=status)
+
+
+def icp_pairs(points, cloud_off, src_idx, tgt_idx, error_threshold, max_iterations, voxel_size, R_init=None,
+              t_init=None, method="point_to_point", normal_k=10, max_corr_dist=None, nn_mode="auto"):
+    """Register cloud src_idx[p] onto cloud tgt_idx[p]; clouds are rows
+    cloud_off[c]:cloud_off[c+1] of ``points``."""
+    pts = _f64(points)
+    dim = int(pts.shape[1])
+    off = np.ascontiguousarray(cloud_off, dtype=np.int64)
+    si = np.ascontiguousarray(src_idx, dtype=np.int32)
+    ti = np.ascontiguousarray(tgt_idx, dtype=np.int32)
+    n_pairs = len(si)
+    r0, t0 = _init_arrays(R_init, t_init, n_pairs, dim)
+    R, t, err, prev, iters, status = _alloc_out(n_pairs, dim)
+    rc = _lib.load().icpb200_icp_pairs(
+        len(off) - 1, dim, _ptr(pts, c_double_p), _ptr(off, c_int64_p), n_pairs, _ptr(si, c_int32_p), _ptr(ti, c_int32_p),
+        _ptr(r0, c_double_p), _ptr(t0, c_double_p), float(error_threshold), int(max_iterations), float(voxel_size),
+        _method_code(method), int(normal_k), -1.0 if max_corr_dist is None else float(max_corr_dist), NN_MODES[nn_mode],
+        _ptr(R, c_double_p), _ptr(t, c_double_p), _ptr(err, c_double_p), _ptr(prev, c_double_p), _ptr(iters, c_int32_p), _ptr(status, c_int32_p))
+    check(rc, "icpb200_icp_pairs")
+    return dict(R=R, t=t, error=err, prev_error=prev, iters=iters, status=status)
+
+
+def icp_trace(source, target, error_threshold, max_iterations, voxel_size, R_init=None, t_init=None,
+              method="point_to_point", normal_k=10, max_corr_dist=None, nn_mode="auto", trace_iters=4):
+    """One registration plus its intermediate state (parity tests)."""
+    src, tgt = _f64(source), _f64(target)
+    dim = int(src.shape[1])
+    r0, t0 = _init_arrays(R_init, t_init, 1, dim)
+    R, t, err, prev, iters, status = _alloc_out(1, dim)
+    src_ds, tgt_ds = np.empty_like(src), np.empty_like(tgt)
+    normals = np.zeros((len(tgt), 2))
+    matches = np.full((max(trace_iters, 1), len(src)), -1, dtype=np.int32)
+    n_s, n_t = ctypes.c_int64(0), ctypes.c_int64(0)
+    rc = _lib.load().icpb200_icp_trace(
+        dim, _ptr(src, c_double_p), len(src), _ptr(tgt, c_double_p), len(tgt), _ptr(r0, c_double_p), _ptr(t0, c_double_p),
+        float(error_threshold), int(max_iterations), float(voxel_size), _method_code(method), int(normal_k),
+        -1.0 if max_corr_dist is None else float(max_corr_dist), NN_MODES[nn_mode],
+        _ptr(R, c_double_p), _ptr(t, c_double_p), _ptr(err, c_double_p), _ptr(prev, c_double_p), _ptr(iters, c_int32_p), _ptr(status, c_int32_p),
+        _ptr(src_ds, c_double_p), ctypes.byref(n_s), _ptr(tgt_ds, c_double_p), ctypes.byref(n_t),
+        _ptr(normals, c_double_p), _ptr(matches, c_int32_p), int(trace_iters))
+    check(rc, "icpb200_icp_trace")
+    ns, nt = int(n_s.value), int(n_t.value)
+    return dict(R=R[0], t=t[0], error=float(err[0]), prev_error=float(prev[0]), iters=int(iters[0]), status=int(status[0]),
+                src=src_ds[:ns].copy(), tgt=tgt_ds[:nt].copy(), normals=normals[:nt].copy(),
+                matches=matches[:trace_iters, :ns].copy())
+
+
+def voxel_downsample(points, voxel_size):
+    pts = _f64(points)
+    out = np.empty_like(pts)
+    n_out = ctypes.c_int64(0)
+    rc = _lib.load().icpb200_voxel_downsample(_ptr(pts, c_double_p), pts.shape[0], pts.shape[1], float(voxel_size),
+                                              _ptr(out, c_double_p), ctypes.byref(n_out))
+    check(rc, "icpb200_voxel_downsample")
+    return out[:int(n_out.value)].copy()
+
+
+class DeviceGrid:
+    """Owner of one device-resident occupancy grid handle."""
+
+    def __init__(self, nx, ny, min_x, min_y, resolution, l_hit, l_miss, lo_min, lo_max):
+        self.nx, self.ny = int(nx), int(ny)
+        self._lib = _lib.load()
+        self._h = self._lib.icpb200_grid_create(self.nx, self.ny, float(min_x), float(min_y), float(resolution),
+                                                float(l_hit), float(l_miss), float(lo_min), float(lo_max))
+        if not self._h:
+            raise RuntimeError(f"icpb200_grid_create failed: {_lib.last_error()}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.icpb200_grid_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_shard(self, rank, world):
+        check(self._lib.icpb200_grid_set_shard(self._h, int(rank), int(world)), "icpb200_grid_set_shard")
+
+    def update(self, origins, hits, hit_off):
+        org = _f64(origins).reshape(-1, 2)
+        pts = _f64(hits).reshape(-1, 2)
+        off = np.ascontiguousarray(hit_off, dtype=np.int64)
+        check(self._lib.icpb200_grid_update(self._h, len(off) - 1, _ptr(org, c_double_p), _ptr(pts, c_double_p),
+                                            _ptr(off, c_int64_p)), "icpb200_grid_update")
+
+    def update_dev(self, n_scans, d_origins, d_hits, d_hit_off, total_hits, stream=0):
+        check(self._lib.icpb200_grid_update_dev(self._h, int(n_scans), d_origins, d_hits, d_hit_off, int(total_hits),
+                                                stream), "icpb200_grid_update_dev")
+
+    def read(self, out=None):
+        if out is None:
+            out = np.empty((self.ny, self.nx), dtype=np.float32)
+        check(self._lib.icpb200_grid_read(self._h, _ptr(out, c_float_p)), "icpb200_grid_read")
+        return out
+
+    def reset(self):
+        check(self._lib.icpb200_grid_reset(self._h), "icpb200_grid_reset")
+
+    def device_ptr(self):
+        return int(self._lib.icpb200_grid_device_ptr(self._h) or 0)
+
+    def last_stats(self):
+        st = np.zeros(4, dtype=np.int64)
+        check(self._lib.icpb200_grid_last_stats(self._h, _ptr(st, c_int64_p)), "icpb200_grid_last_stats")
+        return dict(rays=int(st[0]), traversed=int(st[1]), hits=int(st[2]), runs=int(st[3]))
