@@ -1,0 +1,448 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native ICP registration + occupancy raycast hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c2|c5|teapot] [--scans 2000]
+
+Headline workload (BASELINE.json configs[1], "C2"): 2000 synthetic 1080-beam
+2-D scans -> 1999 consecutive scan-to-scan point_to_line registrations with
+the reference's config.yaml parameters.  One "step" = one pass of the hot path
+over that whole batch.  Prints ONE JSON line (rank 0):
+
+  value      registrations/s with the clouds already resident in HBM, timed with
+             CUDA events on the launching stream, max over ranks
+  e2e        the same batch through the host-buffer C ABI call
+             (icpb200_icp_pairs): H2D of the clouds and D2H of the poses inside
+             the timed region
+  roofline   FP32-FMA-pipe roofline of the per-pair ICP kernel (BASELINE.md
+             section 4: pair evaluations x 5 flop vs SMs x 128 lanes x clock / 4)
+  cpu_baseline  the oracle port of the reference (numpy/scipy, same arithmetic
+             and library calls as /root/reference/utilities/icp.py) timed on
+             this box's host cores on a bounded sample of the same pairs
+  occupancy  the second metric of BASELINE.json (configs[3], "C4"): rays/s of the
+             occupancy raycast, 4096x4096 grid @ 5 cm, with its own value / e2e /
+             roofline (HBM) / cpu_baseline
+
+--impl reference times the reference's CPU implementation (the oracle port:
+the reference is pure Python and /root/reference does not exist on the GPU
+box) on all host cores.  Multi-GPU (torchrun): every rank registers its own
+1999-pair batch (weak scaling); poses are gathered with one NCCL all_gather
+inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "iterative-closest-point-avmi_b200")
+for _p in (PKG, ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+ICP_CFG = dict(error_threshold=1e-10, max_iterations=150, voxel_size=0.04,
+               method="point_to_line", normal_k=12)          # /root/reference/config.yaml:19-24
+GRID_CFG = dict(resolution=0.05, p_hit=0.85, p_miss=0.42, log_odds_min=-8.0, log_odds_max=8.0)  # config.yaml:85-90
+GRID_BOUNDS = (-102.4, 102.4, -102.4, 102.4)                  # 4096 x 4096 cells
+FMA_LANES_PER_SM = 128
+FLOP_PER_PAIR_EVAL_2D = 5
+FMA_INSTR_PER_PAIR_EVAL_2D = 4
+
+
+# --------------------------------------------------------------------------- helpers
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=float(d["hbm_gbs"]), sm_max_mhz=float(d.get("sm_max_mhz", 1965.0)), source="measured")
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, r[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx or None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def build_c2(n_scans, seed):
+    from icp_b200 import synth
+    scans, poses = synth.make_sequence(n_scans, world="room", seed=seed)
+    flat, off = synth.pack_ragged(scans)
+    idx = np.arange(n_scans - 1, dtype=np.int32)
+    return scans, poses, flat, off, idx, idx + 1
+
+
+def build_c5(n_scans, n_pairs, seed):
+    from icp_b200 import synth
+    scans, poses = synth.make_sequence(n_scans, world="room", seed=seed)
+    flat, off = synth.pack_ragged(scans)
+    pairs = synth.loop_closure_pairs(poses, n_pairs, seed=seed, max_dist=3.0).astype(np.int32)
+    return scans, poses, flat, off, pairs[:, 0].copy(), pairs[:, 1].copy()
+
+
+def build_c4(n_scans, seed):
+    from icp_b200 import synth
+    scans, poses = synth.make_sequence(n_scans, world="campus", seed=seed)
+    hits = [synth.to_world_frame(s, p) for s, p in zip(scans, poses)]
+    flat, off = synth.pack_ragged(hits)
+    return poses[:, :2].copy(), flat, off
+
+
+# --------------------------------------------------------------------------- CPU baseline (oracle port)
+def _cpu_icp_one(args):
+    os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    from oracle import icp_oracle
+    src, tgt = args
+    t0 = time.perf_counter()
+    out = icp_oracle.register(src, tgt, **ICP_CFG)
+    return time.perf_counter() - t0, int(out[3])
+
+
+def cpu_icp_baseline(scans, src_idx, tgt_idx, n_sample, cores):
+    """Oracle port timed on `cores` processes over n_sample disjoint pairs."""
+    sel = np.linspace(0, len(src_idx) - 1, n_sample).astype(int)
+    jobs = [(scans[src_idx[i]], scans[tgt_idx[i]]) for i in sel]
+    os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = "1"     # inherited by the workers
+    if cores > 1:
+        # spawn: the parent may hold a CUDA context, which must not be forked
+        with mp.get_context("spawn").Pool(cores) as pool:
+            pool.map(_cpu_icp_one, jobs[:cores])                 # start-up + imports, untimed
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_icp_one, jobs, chunksize=1)
+            wall = time.perf_counter() - t0
+    else:
+        t0 = time.perf_counter()
+        res = [_cpu_icp_one(j) for j in jobs]
+        wall = time.perf_counter() - t0
+    per_call = float(np.mean([r[0] for r in res]))
+    return dict(value=n_sample / wall, unit="registrations/s", cores=cores, kind="port",
+                sample=f"{n_sample} of {len(src_idx)} pairs, oracle/icp_oracle.py (numpy+scipy KDTree), "
+                       f"{cores} processes x 1 thread; mean {per_call * 1e3:.1f} ms/registration/core",
+                one_core_value=1.0 / per_call, mean_iters=float(np.mean([r[1] for r in res])))
+
+
+def cpu_raycast_baseline(origins, flat, off, n_sample):
+    from oracle import occupancy_oracle
+    g = occupancy_oracle.GridOracleC(*GRID_BOUNDS, **GRID_CFG)
+    sel_off = off[:n_sample + 1]
+    t0 = time.perf_counter()
+    g.update_many(origins[:n_sample], flat[:sel_off[-1]], sel_off, fast=False)
+    wall = time.perf_counter() - t0
+    return dict(value=float(sel_off[-1]) / wall, unit="rays/s", cores=1, kind="port",
+                sample=f"first {n_sample} of {len(off) - 1} scans, oracle/occupancy_oracle.c (plain C restatement, "
+                       f"whole-grid clip per scan as the reference), 1 thread; the reference's pure-Python "
+                       f"update_scan measured 2.8k rays/s/core in BASELINE.md")
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    scans, poses, flat, off, si, ti = build_c2(args.scans, seed=0)
+    n_sample = min(len(si), max(cores * 4, 128))
+    for _ in range(max(args.warmup, 0)):
+        cpu_icp_baseline(scans, si, ti, min(cores, 8), cores)
+    t_all, last = [], None
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        last = cpu_icp_baseline(scans, si, ti, n_sample, cores)
+        t_all.append(time.perf_counter() - t0)
+    value = n_sample * args.steps / sum(t_all)
+    line = dict(metric="icp_registrations_per_s", value=value, unit="registrations/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * float(np.mean(t_all)),
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                impl="reference",
+                config=dict(workload="C2 scan-to-scan point_to_line ICP, 1080-beam 2-D scans (bounded sample per step)",
+                            pairs_per_step=n_sample, **{k: v for k, v in ICP_CFG.items()}),
+                cpu_baseline=dict(value=value, unit="registrations/s", cores=cores, kind="port", sample=last["sample"]),
+                e2e=dict(value=value, unit="registrations/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from icp_b200 import _lib, api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libicp_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    api.init(local_rank)
+    lib = _lib.load()
+    dev = torch.device("cuda", local_rank)
+    pk = peaks()
+
+    if args.workload == "c5":
+        scans, poses, flat, off, si, ti = build_c5(args.scans, args.pairs, seed=rank)
+        wl = f"C5 loop-closure candidate batch: {len(si)} scan-pair point_to_line registrations from {args.scans} scans"
+    else:
+        scans, poses, flat, off, si, ti = build_c2(args.scans, seed=rank)
+        wl = f"C2 scan-to-scan point_to_line ICP: {len(si)} consecutive pairs of {args.scans} synthetic 1080-beam 2-D scans"
+    n_pairs, dim = len(si), 2
+    max_pts = int(np.max(np.diff(off)))
+
+    # ---- device-resident inputs / outputs (torch owns the memory; the library gets raw pointers)
+    d_pts = torch.from_numpy(flat).to(dev)
+    d_off = torch.from_numpy(off).to(dev)
+    d_si, d_ti = torch.from_numpy(si).to(dev), torch.from_numpy(ti).to(dev)
+    d_R = torch.empty((n_pairs, 2, 2), dtype=torch.float64, device=dev)
+    d_t = torch.empty((n_pairs, 2), dtype=torch.float64, device=dev)
+    d_err = torch.empty(n_pairs, dtype=torch.float64, device=dev)
+    d_prev = torch.empty(n_pairs, dtype=torch.float64, device=dev)
+    d_it = torch.empty(n_pairs, dtype=torch.int32, device=dev)
+    d_st = torch.empty(n_pairs, dtype=torch.int32, device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2
+    gather_buf = [torch.empty((n_pairs, 3), dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
+    stream = torch.cuda.Stream(device=dev)          # explicit stream: the library launches on it too
+    torch.cuda.set_stream(stream)
+
+    def step_resident():
+        rc = lib.icpb200_icp_pairs_dev(
+            len(off) - 1, dim, d_pts.data_ptr(), d_off.data_ptr(), max_pts, n_pairs, d_si.data_ptr(), d_ti.data_ptr(),
+            None, None, ICP_CFG["error_threshold"], ICP_CFG["max_iterations"], ICP_CFG["voxel_size"],
+            _lib.POINT_TO_LINE, ICP_CFG["normal_k"], -1.0, _lib.NN_AUTO,
+            d_R.data_ptr(), d_t.data_ptr(), d_err.data_ptr(), d_prev.data_ptr(), d_it.data_ptr(), d_st.data_ptr(),
+            stream.cuda_stream)
+        _lib.check(rc, "icpb200_icp_pairs_dev")
+        if world > 1:   # pose results (theta, tx, ty) to every rank: the path's only exchange
+            mine = torch.stack([torch.atan2(d_R[:, 1, 0], d_R[:, 0, 0]), d_t[:, 0], d_t[:, 1]], dim=1)
+            dist.all_gather(gather_buf, mine)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    launches0 = api.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        wall0 = time.perf_counter()
+        for a, b in ev:
+            flush.zero_()                       # evict L2 between timed iterations (outside the events)
+            a.record(stream)
+            step_resident()
+            b.record(stream)
+        barrier()
+        wall = time.perf_counter() - wall0
+    launches = api.launch_count() - launches0
+    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    t_local = sum(ms_steps) / 1e3
+    clocks = clk.summary()
+    iters = d_it.cpu().numpy().astype(np.int64)
+    status = d_st.cpu().numpy()
+
+    # ---- e2e: host buffers through the C ABI (H2D + kernel + D2H per step)
+    e2e_t = []
+    for k in range(2 + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        out = api.icp_pairs(flat, off, si, ti, **ICP_CFG)
+        if world > 1:
+            mine = torch.from_numpy(np.column_stack([np.arctan2(out["R"][:, 1, 0], out["R"][:, 0, 0]), out["t"]])).to(dev)
+            dist.all_gather(gather_buf, mine)
+            torch.cuda.synchronize()
+        if k >= 2:
+            e2e_t.append(time.perf_counter() - t0)
+    h2d = flat.nbytes + off.nbytes + si.nbytes + ti.nbytes
+    d2h = sum(out[k].nbytes for k in ("R", "t", "error", "prev_error", "iters", "status"))
+    assert np.array_equal(out["iters"], iters.astype(np.int32)), "host-buffer and device-resident paths disagree"
+
+    # ---- max over ranks
+    t_max, e2e_max = t_local, float(np.mean(e2e_t))
+    if world > 1:
+        red = torch.tensor([t_local, e2e_max], dtype=torch.float64, device=dev)
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        t_max, e2e_max = float(red[0]), float(red[1])
+
+    if rank != 0:
+        return
+    # ---- roofline of the per-pair kernel (rank 0's batch)
+    from utilities import voxel_downsample
+    n_ds = np.array([len(voxel_downsample(s, ICP_CFG["voxel_size"])) for s in scans], dtype=np.int64)
+    ns, nt = n_ds[si], n_ds[ti]
+    pair_evals = float(np.sum(iters * ns * nt + nt * nt))      # + M^2 once for the p2l normals
+    kernel_s = float(np.mean(ms_steps)) / 1e3                  # the step is one memset + one kernel launch
+    clk_mhz = clocks["sm_mhz"] or pk["sm_max_mhz"]
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    peak_evals = sm_count * FMA_LANES_PER_SM * clk_mhz * 1e6 / FMA_INSTR_PER_PAIR_EVAL_2D
+    achieved_tf = pair_evals * FLOP_PER_PAIR_EVAL_2D / kernel_s / 1e12
+    peak_tf = peak_evals * FLOP_PER_PAIR_EVAL_2D / 1e12
+    roofline = dict(bound="fp32_fma", achieved=achieved_tf, peak=peak_tf, unit="TFLOP/s", frac=achieved_tf / peak_tf,
+                    traffic=None, kernel="icp_pairs_kernel<2>", kernel_ms=kernel_s * 1e3,
+                    pair_evals_per_launch=pair_evals,
+                    peak_basis=f"{sm_count} SMs x {FMA_LANES_PER_SM} FP32 lanes x {clk_mhz:.0f} MHz (median SM clock "
+                               f"sampled during the timed region) / {FMA_INSTR_PER_PAIR_EVAL_2D} FMA-pipe instr per 2-D "
+                               f"pair evaluation x {FLOP_PER_PAIR_EVAL_2D} flop (BASELINE.md section 4)")
+
+    cores = os.cpu_count() or 1
+    cpu = cpu_icp_baseline(scans, si, ti, min(n_pairs, max(4 * cores, 256)), cores) if not args.no_cpu else None
+
+    line = dict(metric="icp_registrations_per_s", value=world * n_pairs * args.steps / t_max, unit="registrations/s",
+                n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=1e3 * t_max / args.steps,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=wl, pairs_per_gpu=n_pairs, points_per_cloud_after_voxel=float(n_ds.mean()),
+                            mean_iterations=float(iters.mean()), converged=int((status == 0).sum()),
+                            max_iter_pairs=int((status == 1).sum()), l2="flushed between timed steps (512 MiB memset)",
+                            sharding="pairs partitioned by rank, no data-path collective; one NCCL all_gather of poses",
+                            **ICP_CFG),
+                e2e=dict(value=world * n_pairs / e2e_max, unit="registrations/s", h2d_bytes_per_step=int(h2d),
+                         d2h_bytes_per_step=int(d2h), api="icpb200_icp_pairs (host buffers, blocking)"),
+                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, clocks=clocks,
+                wall_s_timed_region=wall, peaks_source=pk["source"])
+    if not args.no_raycast:
+        line["occupancy"] = bench_raycast(args, lib, api, dev, local_rank, pk)
+    print(json.dumps(line))
+
+
+def bench_raycast(args, lib, api, dev, local_rank, pk):
+    """C4: 2000 scans x 1080 rays into a 4096 x 4096 grid @ 5 cm (rank 0, one GPU)."""
+    import torch
+    from utilities import OccupancyGrid2D
+    origins, flat, off = build_c4(args.scans, seed=0)
+    grid = OccupancyGrid2D(*GRID_BOUNDS, **GRID_CFG)
+    d_org = torch.from_numpy(origins).to(dev)
+    d_hits = torch.from_numpy(flat).to(dev)
+    d_off = torch.from_numpy(off).to(dev)
+    n_rays = int(off[-1])
+    stream = torch.cuda.current_stream()            # the explicit stream set by run_ours
+    assert stream.cuda_stream != 0
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    ms, launches0 = [], api.launch_count()
+    steps = max(args.steps, 1)
+    with ClockSampler(local_rank) as clk:
+        for k in range(3 + steps):
+            grid.reset()
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if k == 3:
+                launches0 = api.launch_count()
+            a.record(stream)
+            grid._dev.update_dev(len(off) - 1, d_org.data_ptr(), d_hits.data_ptr(), d_off.data_ptr(), n_rays,
+                                 stream.cuda_stream)
+            b.record(stream)
+            torch.cuda.synchronize()
+            if k >= 3:
+                ms.append(a.elapsed_time(b))
+    launches = api.launch_count() - launches0
+    st = grid._dev.last_stats()
+    sec = float(np.mean(ms)) / 1e3
+    # algorithmic bytes: 16 B endpoint + 8 B per traversed cell + 8 B hit-cell RMW
+    alg_bytes = 16.0 * n_rays + 8.0 * st["traversed"] + 8.0 * st["hits"]
+    e2e_t = []
+    host_out = np.empty((grid.ny, grid.nx), dtype=np.float32)
+    for k in range(1 + steps):
+        grid.reset()
+        t0 = time.perf_counter()
+        grid._dev.update(origins, flat, off)
+        grid._dev.read(host_out)
+        if k >= 1:
+            e2e_t.append(time.perf_counter() - t0)
+    cpu = cpu_raycast_baseline(origins, flat, off, min(len(off) - 1, 60)) if not args.no_cpu else None
+    return dict(metric="occupancy_rays_per_s", value=n_rays / sec, unit="rays/s", ms_per_step=sec * 1e3,
+                config=dict(workload=f"C4 occupancy log-odds raycast: {len(off) - 1} scans, {n_rays} rays, "
+                                     f"{grid.nx}x{grid.ny} grid @ 0.05 m, campus world", **GRID_CFG,
+                            cells_per_ray=st["traversed"] / n_rays, tile_runs=st["runs"]),
+                e2e=dict(value=n_rays / float(np.mean(e2e_t)), unit="rays/s",
+                         h2d_bytes_per_step=int(origins.nbytes + flat.nbytes + off.nbytes),
+                         d2h_bytes_per_step=int(host_out.nbytes), api="icpb200_grid_update + icpb200_grid_read"),
+                gpu_launches=int(launches),
+                roofline=dict(bound="hbm", achieved=alg_bytes / sec / 1e9, peak=pk["hbm_gbs"], unit="GB/s",
+                              frac=alg_bytes / sec / 1e9 / pk["hbm_gbs"], traffic=None,
+                              kernel="occ_tile_apply (+ binning passes; whole update timed)",
+                              algorithmic_bytes=alg_bytes, peak_basis=f"{pk['source']} HBM copy bandwidth"),
+                cpu_baseline=cpu, clocks=clk.summary())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"])
+    ap.add_argument("--scans", type=int, default=2000)
+    ap.add_argument("--pairs", type=int, default=8192)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-raycast", action="store_true", help="skip the occupancy (C4) leg")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

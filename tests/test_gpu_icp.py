@@ -1,0 +1,162 @@
+"""GPU parity: ICP registration through the C ABI vs golden fixtures written
+from the live reference, and vs the oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): final poses within 1e-4 m and 1e-5 rad;
+correspondence indices identical (except documented exact-distance ties);
+voxel-downsample output is integer/sort work plus an input-order sum, so it is
+held to bit-exactness."""
+import numpy as np
+import pytest
+
+from conftest import case_kwargs, icp_cases, load_golden, pose_delta
+from icp_b200 import api, synth
+from oracle import icp_oracle
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL = 1e-4      # metres   (north_star)
+ROT_TOL = 1e-5      # radians  (north_star)
+CFG = dict(error_threshold=1e-10, max_iterations=150, voxel_size=0.04, method="point_to_line", normal_k=12)
+
+
+def test_voxel_downsample_bit_exact():
+    from utilities import voxel_downsample
+    g = load_golden("voxel.npz")
+    for tag in sorted({k[:-3] for k in g.files if k.endswith("_in")}):
+        out = voxel_downsample(g[f"{tag}_in"], float(g[f"{tag}_v"]))
+        want = g[f"{tag}_out"]
+        assert out.shape == want.shape, tag
+        assert out.tobytes() == want.tobytes(), f"{tag}: max diff {np.abs(out - want).max()}"
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(-5, 5, size=(3000, 2))
+    for v in (0.05, 0.7, 30.0):
+        assert voxel_downsample(pts, v).tobytes() == icp_oracle.voxel_means(pts, v).tobytes()
+    p3 = rng.normal(size=(1500, 3))
+    assert voxel_downsample(p3, 0.2).tobytes() == icp_oracle.voxel_means(p3, 0.2).tobytes()
+
+
+def test_teapot_known_answer_and_fixture():
+    from utilities import ICP
+    g = load_golden("teapot.npz")
+    R, t, err = ICP(source=g["moved"], target=g["teapot"], error_threshold=1e-12, max_iterations=300,
+                    voxel_size=0.005, method="point_to_point")
+    assert R.shape == (3, 3) and t.shape == (3,) and isinstance(err, float)
+    # analytic answer of demos/teapot_icp_demo.py:38-47
+    assert np.abs(R - g["ry"].T).max() < 1e-9 and np.abs(t + g["ry"].T @ g["shift"]).max() < 1e-9
+    dt, dr = pose_delta(R, t, g["R"], g["t"])
+    assert dt < POS_TOL and dr < ROT_TOL
+    assert abs(err - float(g["err"])) < 1e-12
+    # 3-D "point_to_line" means point_to_point (icp.py:162)
+    R2, t2, _ = ICP(g["moved"], g["teapot"], 1e-12, 300, 0.005, method="point_to_line")
+    assert R2.tobytes() == R.tobytes() and t2.tobytes() == t.tobytes()
+
+
+def test_golden_2d_cases():
+    """Every 2-D case pinned from the reference: p2l with config.yaml and code
+    default parameters, initial guess, p2p, gated scan->submap, the
+    too-few-inliers break (error stays +inf) and the max-iterations exit."""
+    cases = icp_cases(load_golden("icp2d.npz"))
+    for name, c in cases.items():
+        kw = case_kwargs(c)
+        tr = api.icp_trace(c["src"], c["tgt"], trace_iters=1, **kw)
+        assert tr["status"] == int(c["status"]), name
+        assert tr["iters"] == int(c["iters"]), f"{name}: {tr['iters']} iterations, reference {int(c['iters'])}"
+        dt, dr = pose_delta(tr["R"], tr["t"], c["R"], c["t"])
+        assert dt < POS_TOL and dr < ROT_TOL, f"{name}: dt={dt:.3e} dr={dr:.3e}"
+        if np.isinf(c["err"]):
+            assert np.isinf(tr["error"]), name
+        else:
+            assert abs(tr["error"] - float(c["err"])) < 1e-9, name
+        assert len(tr["src"]) == int(c["n_src"]) and len(tr["tgt"]) == int(c["n_tgt"]), name
+        if len(c["first_match"]):
+            assert np.array_equal(tr["matches"][0], c["first_match"]), f"{name}: first-iteration correspondences"
+
+
+def test_normals_match_reference_up_to_sign():
+    g = load_golden("normals.npz")
+    for tag in ("scan0_k12", "scan1_k10"):
+        cloud, k = g[f"{tag}_in"], int(g[f"{tag}_k"])
+        # voxel far below the point spacing leaves the cloud unchanged, so the
+        # trace's normals are the normals of `cloud` itself
+        tr = api.icp_trace(cloud, cloud, 1e-10, 1, 1e-7, method="point_to_line", normal_k=k, trace_iters=0)
+        assert len(tr["tgt"]) == len(cloud)
+        order = np.lexsort((cloud[:, 1], cloud[:, 0]))     # trace rows are in voxel (lexicographic) order
+        want = g[f"{tag}_out"][order]
+        assert np.allclose(tr["tgt"], cloud[order], rtol=0, atol=0)
+        dots = np.abs(np.sum(tr["normals"] * want, axis=1))
+        assert dots.min() > 1.0 - 1e-9, f"{tag}: worst |n.n_ref| = {dots.min()}"
+
+
+def test_correspondences_identical_every_iteration():
+    scans, _ = synth.make_sequence(6, world="room", seed=11)
+    for i in range(4):
+        trace = {}
+        R, t, err, iters, status = icp_oracle.register(scans[i], scans[i + 1], trace=trace, **CFG)
+        tr = api.icp_trace(scans[i], scans[i + 1], trace_iters=iters, **CFG)
+        assert tr["src"].tobytes() == trace["src"].tobytes() and tr["tgt"].tobytes() == trace["tgt"].tobytes()
+        assert tr["iters"] == iters and tr["status"] == status
+        for it in range(iters):
+            same = tr["matches"][it] == trace["matches"][it]
+            assert same.all(), f"pair {i} iteration {it}: {np.count_nonzero(~same)} correspondences differ"
+        dt, dr = pose_delta(tr["R"], tr["t"], R, t)
+        assert dt < 1e-9 and dr < 1e-9
+
+
+def test_batch_equals_single_and_pairs_api():
+    scans, poses = synth.make_sequence(24, world="room", seed=3)
+    batch = api.icp_batch(scans[:-1], scans[1:], **CFG)
+    flat, off = synth.pack_ragged(scans)
+    idx = np.arange(len(scans) - 1, dtype=np.int32)
+    pairs = api.icp_pairs(flat, off, idx, idx + 1, **CFG)
+    for key in ("R", "t", "error", "iters", "status"):
+        assert batch[key].tobytes() == pairs[key].tobytes(), key     # bitwise reproducible
+    for i in (0, 7, 22):
+        one = api.icp_batch([scans[i]], [scans[i + 1]], **CFG)
+        assert one["R"][0].tobytes() == batch["R"][i].tobytes()
+        R, t, err, iters, status = icp_oracle.register(scans[i], scans[i + 1], **CFG)
+        dt, dr = pose_delta(batch["R"][i], batch["t"][i], R, t)
+        assert dt < POS_TOL and dr < ROT_TOL and batch["iters"][i] == iters and batch["status"][i] == status
+    # loop-closure style pairs (far apart in time, close in space), with initial guesses
+    lc = synth.loop_closure_pairs(poses, 6, seed=1, max_dist=1.0, min_gap=3).astype(np.int32)
+    th = poses[lc[:, 1], 2] - poses[lc[:, 0], 2]
+    R0 = np.stack([[[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]] for a in -th])
+    t0 = np.zeros((len(lc), 2))
+    out = api.icp_pairs(flat, off, lc[:, 0], lc[:, 1], R_init=R0, t_init=t0, **CFG)
+    for p, (i, j) in enumerate(lc):
+        R, t, err, iters, status = icp_oracle.register(scans[i], scans[j], R_init=R0[p], t_init=t0[p], **CFG)
+        dt, dr = pose_delta(out["R"][p], out["t"][p], R, t)
+        if status == icp_oracle.STATUS_CONVERGED:
+            assert dt < POS_TOL and dr < ROT_TOL, (p, dt, dr)
+        assert out["status"][p] == status
+
+
+def test_shim_prints_reference_line(capsys):
+    from utilities import ICP
+    scans, _ = synth.make_sequence(2, world="room", seed=4)
+    R, t, err = ICP(scans[0], scans[1], 1e-10, 150, 0.04, method="point_to_line", normal_k=12)
+    line = capsys.readouterr().out
+    Ro, to, eo, iters, status = icp_oracle.register(scans[0], scans[1], **CFG)
+    if status == icp_oracle.STATUS_CONVERGED:     # icp.py:218
+        assert line.startswith(f"  ICP converged: iter={iters - 1}, error={eo:.8f}, delta=")
+    else:                                         # icp.py:222
+        assert line == f"  ICP max iterations reached: iter=150, error={eo:.8f}\n"
+    R1, t1, err1 = ICP(scans[0], scans[1], 1e-7, 100, 0.06, method="point_to_line")   # slam.py:92-97 defaults
+    assert capsys.readouterr().out.startswith("  ICP converged: iter=")
+    R2, t2, err2 = ICP(scans[0], scans[1], 1e-10, 2, 0.04, method="point_to_line", normal_k=12)
+    assert capsys.readouterr().out.startswith("  ICP max iterations reached: iter=2, error=")
+    # one of R_init / t_init alone is ignored (icp.py:153)
+    R3, t3, _ = ICP(scans[0], scans[1], 1e-10, 150, 0.04, R_init=np.eye(2) * 0.5, method="point_to_line", normal_k=12)
+    assert R3.tobytes() == R.tobytes()
+    # inputs are not mutated and need not be contiguous / float64
+    a = np.asfortranarray(scans[0]).astype(np.float32)
+    keep = a.copy()
+    ICP(a, scans[1], 1e-10, 5, 0.04)
+    assert np.array_equal(a, keep)
+
+
+def test_limits_and_errors():
+    pts = np.random.default_rng(0).normal(size=(5000, 2))
+    with pytest.raises(RuntimeError, match="grid nearest-neighbour"):
+        api.icp_batch([pts], [pts], 1e-7, 5, 0.01)
+    with pytest.raises(RuntimeError):
+        api.icp_batch([np.zeros((0, 2))], [pts[:10]], 1e-7, 5, 0.01)

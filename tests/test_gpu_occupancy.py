@@ -1,0 +1,160 @@
+"""GPU parity: occupancy raycast through the C ABI vs the oracle / golden
+fixtures.  Bar: bit-exact float32 log-odds (north_star: Bresenham cell sets
+bit-exact, log-odds within 1e-9 abs -- i.e. identical float32 values)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from icp_b200 import api, synth
+from oracle import occupancy_oracle as oo
+
+pytestmark = pytest.mark.gpu
+
+GKW = dict(resolution=0.05, p_hit=0.85, p_miss=0.42, log_odds_min=-8.0, log_odds_max=8.0)
+
+
+def make_pair(bounds, **kw):
+    from utilities import OccupancyGrid2D
+    return OccupancyGrid2D(*bounds, **kw), oo.GridOracleC(*bounds, **kw)
+
+
+def assert_same(gpu_grid, ref_grid, what=""):
+    a, b = gpu_grid.log_odds, ref_grid.log_odds
+    assert a.dtype == np.float32 and a.shape == b.shape
+    if a.tobytes() != b.tobytes():
+        bad = np.argwhere(a != b)
+        raise AssertionError(f"{what}: {len(bad)} cells differ, first {bad[:5].tolist()} "
+                             f"gpu={a[tuple(bad[0])]!r} ref={b[tuple(bad[0])]!r}")
+
+
+def test_golden_fixture_scan_by_scan():
+    """The reference's own outputs (tests/golden/occupancy.npz) reproduced
+    through update_scan, one scan per call: duplicates, zero-length rays, an
+    empty scan, an out-of-grid origin and out-of-bounds endpoints included."""
+    from utilities import OccupancyGrid2D
+    g = load_golden("occupancy.npz")
+    grid = OccupancyGrid2D(*g["bounds"], **GKW)
+    assert (grid.ny, grid.nx) == g["snap_0"].shape
+    assert grid.l_hit == 1.7346010553881064 and grid.l_miss == -0.3227733922630512
+    off = g["hit_off"]
+    for s in range(40):
+        grid.update_scan(g["origins"][s], g["hits"][off[s]:off[s + 1]])
+        if s in (0, 13, 39):
+            assert grid.log_odds.tobytes() == g[f"snap_{s}"].tobytes(), f"after scan {s}"
+    grid.reset()
+    assert not grid.log_odds.any()
+    grid.update_scan(g["origins"][0], g["hits"][off[0]:off[1]])
+    assert grid.log_odds.tobytes() == g["snap_0"].tobytes()
+
+
+def test_golden_fixture_batched_and_clamp_excluding_zero():
+    from utilities import OccupancyGrid2D
+    g = load_golden("occupancy.npz")
+    grid = OccupancyGrid2D(*g["bounds"], **GKW)
+    grid._dev.update(g["origins"], g["hits"], g["hit_off"])
+    assert grid._dev.read().tobytes() == g["snap_39"].tobytes()
+    st = grid._dev.last_stats()
+    assert st["rays"] == int(g["hit_off"][-1]) and st["traversed"] > 0 and st["hits"] > 0
+    odd = OccupancyGrid2D(*g["bounds"], **dict(GKW, log_odds_min=0.5, log_odds_max=3.0))
+    off = g["hit_off"]
+    for s in range(3):
+        odd.update_scan(g["origins"][s], g["hits"][off[s]:off[s + 1]])
+    assert odd.log_odds.tobytes() == g["odd_final"].tobytes()
+    odd2 = OccupancyGrid2D(*g["bounds"], **dict(GKW, log_odds_min=0.5, log_odds_max=3.0))
+    odd2._dev.update(g["origins"][:3], g["hits"][:off[3]], off[:4])
+    assert odd2._dev.read().tobytes() == g["odd_final"].tobytes()
+
+
+def test_random_scans_vs_oracle_non_multiple_of_tile():
+    """Grid whose size is not a multiple of the 64-cell tile, rays from random
+    origins (inside and outside), many collisions in few cells."""
+    rng = np.random.default_rng(5)
+    bounds = (-7.3, 9.1, -4.4, 6.05)                       # 328 x 209 cells
+    gpu, ref = make_pair(bounds, **GKW)
+    for s in range(25):
+        n = int(rng.integers(1, 700))
+        org = rng.uniform([-9, -6], [11, 8])
+        pts = org + rng.normal(size=(n, 2)) * rng.uniform(0.05, 6.0)
+        if s % 5 == 0:
+            pts[: n // 2] = pts[0]                         # heavy duplicates in one cell
+        gpu.update_scan(org, pts)
+        ref.update_scan(org, pts)
+        if s % 6 == 0:
+            assert_same(gpu, ref, f"scan {s}")
+    assert_same(gpu, ref, "final")
+
+
+def test_saturation_and_sign_conventions():
+    """Many repeats drive cells into both clamps; p_miss > 0.5 flips the sign
+    of l_miss (no early-exit shortcut may change the result)."""
+    rng = np.random.default_rng(8)
+    bounds = (-4.0, 4.0, -4.0, 4.0)
+    for kw in (dict(GKW, log_odds_min=-2.0, log_odds_max=3.5),
+               dict(resolution=0.1, p_hit=0.3, p_miss=0.6, log_odds_min=-1.0, log_odds_max=1.5),
+               dict(resolution=0.1, p_hit=0.7, p_miss=0.5, log_odds_min=-5.0, log_odds_max=5.0)):
+        gpu, ref = make_pair(bounds, **kw)
+        pts0 = rng.uniform(-3.5, 3.5, size=(300, 2))
+        origins = [np.array([0.2, -0.1])] * 30
+        clouds = [pts0 + rng.normal(0, 0.01, size=pts0.shape) for _ in range(30)]
+        gpu.update_scans(origins, clouds)
+        for o, c in zip(origins, clouds):
+            ref.update_scan(o, c, fast=True)
+        assert_same(gpu, ref, str(kw))
+
+
+def test_campus_replay_batched_vs_oracle():
+    """300 synthetic scans replayed in one call (the _rebuild_map shape) on a
+    2048 x 2048 grid, against the C oracle scan by scan."""
+    scans, poses = synth.make_sequence(300, world="campus", seed=1)
+    hits = [synth.to_world_frame(s, p) for s, p in zip(scans, poses)]
+    bounds = (poses[:, 0].mean() - 51.2, poses[:, 0].mean() + 51.2,
+              poses[:, 1].mean() - 51.2, poses[:, 1].mean() + 51.2)
+    gpu, ref = make_pair(bounds, **GKW)
+    assert gpu.nx == 2048 and gpu.ny == 2048
+    flat, off = synth.pack_ragged(hits)
+    gpu._dev.update(poses[:, :2].copy(), flat, off)
+    cells = ref.update_many(poses[:, :2].copy(), flat, off, fast=True)
+    assert_same(gpu, ref, "campus replay")
+    st = gpu._dev.last_stats()
+    assert st["traversed"] == cells                       # same number of free-cell updates
+    # splitting the batch anywhere gives the same map (scan order is preserved)
+    gpu2, _ = make_pair(bounds, **GKW)
+    gpu2._dev.update(poses[:120, :2].copy(), flat[:off[120]], off[:121])
+    gpu2._dev.update(poses[120:, :2].copy(), flat[off[120]:], off[120:] - off[120])
+    assert gpu2.log_odds.tobytes() == gpu.log_odds.tobytes()
+
+
+def test_spatial_shards_sum_to_whole_map():
+    """Multi-GPU seam emulated on one GPU: world=4 shards, each replaying all
+    scans clipped to its own tiles; the element-wise sum equals the unsharded map."""
+    scans, poses = synth.make_sequence(40, world="room", seed=2)
+    hits = [synth.to_world_frame(s, p) for s, p in zip(scans, poses)]
+    flat, off = synth.pack_ragged(hits)
+    bounds = (-25.6, 25.6, -25.6, 25.6)
+    whole, ref = make_pair(bounds, **GKW)
+    whole._dev.update(poses[:, :2].copy(), flat, off)
+    ref.update_many(poses[:, :2].copy(), flat, off)
+    assert_same(whole, ref, "unsharded")
+    total = np.zeros_like(whole.log_odds)
+    for rank in range(4):
+        part, _ = make_pair(bounds, **GKW)
+        part._dev.set_shard(rank, 4)
+        part._dev.update(poses[:, :2].copy(), flat, off)
+        piece = part.log_odds
+        assert not np.any((piece != 0) & (total != 0))    # shards are disjoint
+        total += piece
+    assert total.tobytes() == whole.log_odds.tobytes()
+
+
+def test_empty_inputs_and_limits():
+    from utilities import OccupancyGrid2D
+    grid = OccupancyGrid2D(-1, 1, -1, 1, **GKW)
+    grid.update_scan([0.0, 0.0], np.zeros((0, 2)))          # mapping.py:113-114
+    assert not grid.log_odds.any()
+    grid.update_scan([0.0, 0.0], np.array([[0.001, 0.001]]))  # hit in the origin cell: no free cells
+    lo = grid.log_odds
+    assert np.count_nonzero(lo) == 1 and lo.max() == np.float32(1.7346010553881064)
+    grid.update_scan([0.0, 0.0], np.array([[1e12, -3e11]]))   # absurdly far endpoint: clipped walk
+    assert np.isfinite(grid.log_odds).all()
+    with pytest.raises(RuntimeError):
+        grid._dev.update(np.zeros((1, 2)), np.zeros((3, 2)), np.array([1, 3]))   # hit_off[0] != 0
