@@ -151,6 +151,15 @@ int icpb200_icp_trace(int dim, const double *src, int64_t n_src,
                       double *tgt_ds, int64_t *n_tgt_ds,
                       double *normals, int32_t *matches, int trace_iters);
 
+/* Work counters of the most recent registration call (synchronises with it):
+ * stats[0] fp32 sweep pair evaluations executed, stats[1] source points
+ * re-decided by the full fp64 scan, stats[2] iterations over all pairs,
+ * stats[3] source points swept, stats[4] source points whose correspondence
+ * was carried over by the exact movement bound; stats[5..7] device time in ns
+ * of the voxel (K1), normals (K2) and pair (K3) kernels (CUDA events).
+ * bench.py uses them for the FP32-FMA roofline. */
+int icpb200_icp_last_stats(int64_t *stats8);
+
 /* Voxel-grid mean downsample (replaces utilities/icp.py:117-129).  `out`
  * needs n*dim doubles; *n_out receives the number of occupied voxels; rows
  * are in lexicographic voxel-index order like np.unique(axis=0). */

@@ -83,11 +83,11 @@ static int init_locked(int device) {
     c.sm_count = prop.multiProcessorCount;
     c.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     ICPB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) ICPB_CUDA(cudaEventCreate(&c.ev[i]));
     c.ready = true;
     return ICPB200_OK;
 }
 
-int ensure_ready() { return g_ctx.ready ? init_locked(-1) : init_locked(-1); }
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 static inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
@@ -117,18 +117,44 @@ static int check_common(const IcpCommon& k, const char* who) {
     return ICPB200_OK;
 }
 
-struct DevClouds {                 // one set of clouds resident on the device
+struct DevClouds {                 // one set of raw clouds resident on the device
     const double* pts;
     const long long* off;
-    const int* idx;                // per pair, or nullptr (pair p -> cloud p)
+    int n_clouds;
     long long max_points;          // largest raw cloud
+    long long total_points;        // upper bound on off[n_clouds]
 };
 
-// Enqueue the registration of n_pairs pairs on `st` (device pointers everywhere).
-static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, const DevClouds& t,
+struct IcpTrace {                  // optional debug outputs of a single-pair call
+    int* match = nullptr;
+    int iters = 0;
+    int stride = 0;
+};
+
+// Device buffers for the preprocessed form of cloud set `slot` (0 or 1).
+static int make_cloud_set(Context& c, int slot, const DevClouds& d, int dim, bool want_normals, CloudSet* out) {
+    const size_t np = (size_t)d.total_points, nc = (size_t)d.n_clouds;
+    if (c.aux_ds[slot].reserve(sizeof(double) * dim * np) || c.aux_n[slot].reserve(sizeof(int) * nc) ||
+        c.aux_box[slot].reserve(sizeof(double) * 6 * nc) || c.aux_flags[slot].reserve(2 * nc) ||
+        (want_normals && c.aux_nrm[slot].reserve(sizeof(double) * 2 * np)))
+        return ICPB200_ERR_CUDA;
+    out->raw = d.pts; out->off = d.off; out->n_clouds = d.n_clouds;
+    out->ds = c.aux_ds[slot].as<double>();
+    out->ds_n = c.aux_n[slot].as<int>();
+    out->box = c.aux_box[slot].as<double>();
+    out->nrm = want_normals ? c.aux_nrm[slot].as<double>() : nullptr;
+    out->used = c.aux_flags[slot].as<unsigned char>();
+    out->is_tgt = out->used + nc;
+    return ICPB200_OK;
+}
+
+// Enqueue the registration of n_pairs pairs on `st` (device pointers everywhere):
+// K0 mark -> K1 voxel means per referenced cloud -> K2 normals per p2l target -> K3 pairs.
+static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, const DevClouds& t, bool same_set,
+                       const int* d_src_idx, const int* d_tgt_idx,
                        const double* d_R_init, const double* d_t_init, double* d_R, double* d_t,
                        double* d_err, double* d_prev, int* d_iters, int* d_status, cudaStream_t st,
-                       double* tr_src, double* tr_tgt, double* tr_nrm, int* tr_match, int tr_iters, int* tr_counts) {
+                       const IcpTrace& tr, IcpArgs* args_out) {
     Context& c = g_ctx;
     if (n_pairs == 0) return ICPB200_OK;
     const long long biggest = std::max(s.max_points, t.max_points);
@@ -137,11 +163,15 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
                   "does not contain yet (brute-force limit %d)", biggest, ICPB200_BRUTE_MAX_POINTS);
         return ICPB200_ERR_LIMIT;
     }
+    const bool p2l = k.method == ICPB200_POINT_TO_LINE && k.dim == 2;
     IcpArgs a;
     memset(&a, 0, sizeof(a));
+    int rc;
+    if ((rc = make_cloud_set(c, 0, s, k.dim, p2l && same_set, &a.s))) return rc;
+    if (same_set) a.t = a.s;
+    else if ((rc = make_cloud_set(c, 1, t, k.dim, p2l, &a.t))) return rc;
     a.n_pairs = n_pairs;
-    a.src = s.pts; a.src_off = s.off; a.src_idx = s.idx;
-    a.tgt = t.pts; a.tgt_off = t.off; a.tgt_idx = t.idx;
+    a.src_idx = d_src_idx; a.tgt_idx = d_tgt_idx;
     a.R_init = d_R_init; a.t_init = d_t_init;
     a.err_thr = k.error_threshold; a.max_iter = k.max_iterations; a.voxel = k.voxel_size;
     a.method = k.method; a.normal_k = k.normal_k; a.max_corr = k.max_corr_dist;
@@ -149,22 +179,34 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
     a.cap_s = round_up((int)std::max<long long>(s.max_points, 32), 32);
     a.cap_t = round_up((int)std::max<long long>(t.max_points, 32), 32);
     a.sort_pad = next_pow2((int)std::max<long long>(biggest, 256));
-    const size_t smem = icp_smem_bytes(k.dim, a.cap_s, a.cap_t, a.sort_pad);
-    if (smem > (size_t)c.max_smem_optin) {
+    const size_t smem = icp_pair_smem_bytes(k.dim, a.cap_s, a.cap_t);
+    if (smem > (size_t)c.max_smem_optin || icp_normals_smem_bytes(a.cap_t) > (size_t)c.max_smem_optin ||
+        icp_voxel_smem_bytes(a.sort_pad) > (size_t)c.max_smem_optin) {
         set_error("icp: %zu bytes of shared memory needed, device allows %d", smem, c.max_smem_optin);
         return ICPB200_ERR_LIMIT;
     }
+    if (c.queue.reserve(sizeof(unsigned)) || c.stats.reserve(8 * sizeof(unsigned long long))) return ICPB200_ERR_CUDA;
+    a.queue = c.queue.as<unsigned>();
+    a.stats = c.stats.as<unsigned long long>();
+    a.trace_match = tr.match; a.trace_iters = tr.iters; a.trace_stride = tr.stride;
+    ICPB_CUDA(cudaMemsetAsync(a.queue, 0, sizeof(unsigned), st));
+    ICPB_CUDA(cudaMemsetAsync(a.stats, 0, 8 * sizeof(unsigned long long), st));
+    ICPB_CUDA(cudaMemsetAsync(a.s.used, 0, 2 * (size_t)s.n_clouds, st));
+    if (!same_set) ICPB_CUDA(cudaMemsetAsync(a.t.used, 0, 2 * (size_t)t.n_clouds, st));
+    if ((rc = launch_mark_used(a, p2l, st))) return rc;
+    ICPB_CUDA(cudaEventRecord(c.ev[0], st));
+    if ((rc = launch_voxel_clouds(a.s, k.dim, k.voxel_size, a.sort_pad, st))) return rc;
+    if (!same_set && (rc = launch_voxel_clouds(a.t, k.dim, k.voxel_size, a.sort_pad, st))) return rc;
+    ICPB_CUDA(cudaEventRecord(c.ev[1], st));
+    if (p2l && (rc = launch_normals(a.t, a.cap_t, k.normal_k, st))) return rc;
+    ICPB_CUDA(cudaEventRecord(c.ev[2], st));
     const int per_sm = icp_max_ctas_per_sm(k.dim, smem);
     const int n_ctas = std::min(n_pairs, c.sm_count * per_sm);
-    a.ws_stride = icp_ws_doubles(k.dim, a.cap_s, a.cap_t);
-    if (c.icp_ws.reserve(sizeof(double) * a.ws_stride * (size_t)n_ctas)) return ICPB200_ERR_CUDA;
-    if (c.queue.reserve(sizeof(unsigned))) return ICPB200_ERR_CUDA;
-    a.ws = c.icp_ws.as<double>();
-    a.queue = c.queue.as<unsigned>();
-    a.trace_src = tr_src; a.trace_tgt = tr_tgt; a.trace_nrm = tr_nrm;
-    a.trace_match = tr_match; a.trace_iters = tr_iters; a.trace_counts = tr_counts;
-    ICPB_CUDA(cudaMemsetAsync(a.queue, 0, sizeof(unsigned), st));
-    return launch_icp_pairs(a, k.dim, n_ctas, smem, st);
+    c.last_icp_stream = st;
+    if (args_out) *args_out = a;
+    if ((rc = launch_icp_pairs(a, k.dim, n_ctas, smem, st))) return rc;
+    ICPB_CUDA(cudaEventRecord(c.ev[3], st));
+    return ICPB200_OK;
 }
 
 static int check_offsets(const int64_t* off, int n, const char* what, long long* max_points) {
@@ -232,9 +274,11 @@ void icpb200_shutdown(void) {
     cudaSetDevice(c.device);
     cudaStreamSynchronize(c.stream);
     DevBuf* bufs[] = {&c.pts_a, &c.pts_b, &c.off_a, &c.off_b, &c.idx_a, &c.idx_b, &c.rinit, &c.tinit, &c.out_r,
-                      &c.out_t, &c.out_err, &c.out_prev, &c.out_iters, &c.out_status, &c.icp_ws, &c.queue, &c.trace,
-                      &c.vox_in, &c.vox_out};
+                      &c.out_t, &c.out_err, &c.out_prev, &c.out_iters, &c.out_status, &c.queue, &c.trace, &c.stats,
+                      &c.aux_ds[0], &c.aux_ds[1], &c.aux_n[0], &c.aux_n[1], &c.aux_box[0], &c.aux_box[1],
+                      &c.aux_nrm[0], &c.aux_nrm[1], &c.aux_flags[0], &c.aux_flags[1], &c.vox_in, &c.vox_out};
     for (DevBuf* b : bufs) b->release();
+    for (int i = 0; i < 4; ++i) if (c.ev[i]) { cudaEventDestroy(c.ev[i]); c.ev[i] = nullptr; }
     cudaStreamDestroy(c.stream);
     c.stream = nullptr;
     c.ready = false;
@@ -275,10 +319,11 @@ int icpb200_icp_batch(int n_pairs, int dim, const double* src, const int64_t* sr
     ICPB_CUDA(cudaMemcpyAsync(c.off_b.p, tgt_off, sizeof(int64_t) * (n_pairs + 1), cudaMemcpyHostToDevice, c.stream));
     const double *d_Ri, *d_ti;
     if ((rc = upload_init(c, n_pairs, dim, R_init, t_init, &d_Ri, &d_ti))) return rc;
-    const DevClouds s{c.pts_a.as<double>(), c.off_a.as<long long>(), nullptr, max_s};
-    const DevClouds t{c.pts_b.as<double>(), c.off_b.as<long long>(), nullptr, max_t};
-    rc = icp_enqueue(k, n_pairs, s, t, d_Ri, d_ti, c.out_r.as<double>(), c.out_t.as<double>(), c.out_err.as<double>(),
-                     c.out_prev.as<double>(), c.out_iters.as<int>(), c.out_status.as<int>(), c.stream, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
+    const DevClouds s{c.pts_a.as<double>(), c.off_a.as<long long>(), n_pairs, max_s, (long long)ns};
+    const DevClouds t{c.pts_b.as<double>(), c.off_b.as<long long>(), n_pairs, max_t, (long long)nt};
+    rc = icp_enqueue(k, n_pairs, s, t, false, nullptr, nullptr, d_Ri, d_ti, c.out_r.as<double>(), c.out_t.as<double>(),
+                     c.out_err.as<double>(), c.out_prev.as<double>(), c.out_iters.as<int>(), c.out_status.as<int>(),
+                     c.stream, IcpTrace{}, nullptr);
     if (rc) return rc;
     return fetch_outputs(c, n_pairs, dim, IcpOutputs{R_out, t_out, err_out, prev_err_out, iters_out, status_out});
 }
@@ -317,10 +362,10 @@ int icpb200_icp_pairs(int n_clouds, int dim, const double* pts, const int64_t* c
     ICPB_CUDA(cudaMemcpyAsync(c.idx_b.p, tgt_idx, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyHostToDevice, c.stream));
     const double *d_Ri, *d_ti;
     if ((rc = upload_init(c, n_pairs, dim, R_init, t_init, &d_Ri, &d_ti))) return rc;
-    const DevClouds s{c.pts_a.as<double>(), c.off_a.as<long long>(), c.idx_a.as<int>(), max_pts};
-    const DevClouds t{c.pts_a.as<double>(), c.off_a.as<long long>(), c.idx_b.as<int>(), max_pts};
-    rc = icp_enqueue(k, n_pairs, s, t, d_Ri, d_ti, c.out_r.as<double>(), c.out_t.as<double>(), c.out_err.as<double>(),
-                     c.out_prev.as<double>(), c.out_iters.as<int>(), c.out_status.as<int>(), c.stream, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
+    const DevClouds s{c.pts_a.as<double>(), c.off_a.as<long long>(), n_clouds, max_pts, (long long)np};
+    rc = icp_enqueue(k, n_pairs, s, s, true, c.idx_a.as<int>(), c.idx_b.as<int>(), d_Ri, d_ti, c.out_r.as<double>(),
+                     c.out_t.as<double>(), c.out_err.as<double>(), c.out_prev.as<double>(), c.out_iters.as<int>(),
+                     c.out_status.as<int>(), c.stream, IcpTrace{}, nullptr);
     if (rc) return rc;
     return fetch_outputs(c, n_pairs, dim, IcpOutputs{R_out, t_out, err_out, prev_err_out, iters_out, status_out});
 }
@@ -343,11 +388,12 @@ int icpb200_icp_pairs_dev(int n_clouds, int dim, const double* d_pts, const int6
     if ((rc = init_locked(-1))) return rc;
     Context& c = g_ctx;
     cudaStream_t st = stream ? (cudaStream_t)stream : c.stream;
-    const DevClouds s{d_pts, (const long long*)d_cloud_off, d_src_idx, max_cloud_points};
-    const DevClouds t{d_pts, (const long long*)d_cloud_off, d_tgt_idx, max_cloud_points};
+    const DevClouds s{d_pts, (const long long*)d_cloud_off, n_clouds, max_cloud_points,
+                      (long long)n_clouds * max_cloud_points};
     const bool init = d_R_init && d_t_init;
-    return icp_enqueue(k, n_pairs, s, t, init ? d_R_init : nullptr, init ? d_t_init : nullptr, d_R_out, d_t_out,
-                       d_err_out, d_prev_err_out, d_iters_out, d_status_out, st, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
+    return icp_enqueue(k, n_pairs, s, s, true, d_src_idx, d_tgt_idx, init ? d_R_init : nullptr,
+                       init ? d_t_init : nullptr, d_R_out, d_t_out, d_err_out, d_prev_err_out, d_iters_out,
+                       d_status_out, st, IcpTrace{}, nullptr);
 }
 
 int icpb200_icp_trace(int dim, const double* src, int64_t n_src, const double* tgt, int64_t n_tgt,
@@ -371,41 +417,63 @@ int icpb200_icp_trace(int dim, const double* src, int64_t n_src, const double* t
         c.off_a.reserve(sizeof(int64_t) * 2) || c.off_b.reserve(sizeof(int64_t) * 2))
         return ICPB200_ERR_CUDA;
     if ((rc = reserve_outputs(c, 1, dim))) return rc;
-    // trace buffer: src_ds | tgt_ds | normals | counts(2 ints, padded) | matches
     const size_t b_src = sizeof(double) * dim * (size_t)n_src, b_tgt = sizeof(double) * dim * (size_t)n_tgt;
-    const size_t b_nrm = sizeof(double) * 2 * (size_t)n_tgt, b_cnt = 16;
+    const size_t b_nrm = sizeof(double) * 2 * (size_t)n_tgt;
     const size_t b_mat = sizeof(int) * (size_t)n_src * (size_t)trace_iters;
-    if (c.trace.reserve(b_src + b_tgt + b_nrm + b_cnt + b_mat + 64)) return ICPB200_ERR_CUDA;
-    unsigned char* base = c.trace.as<unsigned char>();
-    double* d_src_ds = reinterpret_cast<double*>(base);
-    double* d_tgt_ds = reinterpret_cast<double*>(base + b_src);
-    double* d_nrm = reinterpret_cast<double*>(base + b_src + b_tgt);
-    int* d_cnt = reinterpret_cast<int*>(base + b_src + b_tgt + b_nrm);
-    int* d_mat = reinterpret_cast<int*>(base + b_src + b_tgt + b_nrm + b_cnt);
-    ICPB_CUDA(cudaMemsetAsync(base, 0, b_src + b_tgt + b_nrm + b_cnt, c.stream));
-    if (b_mat) ICPB_CUDA(cudaMemsetAsync(d_mat, 0xff, b_mat, c.stream));
+    int* d_mat = nullptr;
+    if (b_mat && matches) {
+        if (c.trace.reserve(b_mat)) return ICPB200_ERR_CUDA;
+        d_mat = c.trace.as<int>();
+        ICPB_CUDA(cudaMemsetAsync(d_mat, 0xff, b_mat, c.stream));
+    }
     ICPB_CUDA(cudaMemcpyAsync(c.pts_a.p, src, b_src, cudaMemcpyHostToDevice, c.stream));
     ICPB_CUDA(cudaMemcpyAsync(c.pts_b.p, tgt, b_tgt, cudaMemcpyHostToDevice, c.stream));
     ICPB_CUDA(cudaMemcpyAsync(c.off_a.p, off_s, sizeof(off_s), cudaMemcpyHostToDevice, c.stream));
     ICPB_CUDA(cudaMemcpyAsync(c.off_b.p, off_t, sizeof(off_t), cudaMemcpyHostToDevice, c.stream));
     const double *d_Ri, *d_ti;
     if ((rc = upload_init(c, 1, dim, R_init, t_init, &d_Ri, &d_ti))) return rc;
-    const DevClouds s{c.pts_a.as<double>(), c.off_a.as<long long>(), nullptr, n_src};
-    const DevClouds t{c.pts_b.as<double>(), c.off_b.as<long long>(), nullptr, n_tgt};
-    rc = icp_enqueue(k, 1, s, t, d_Ri, d_ti, c.out_r.as<double>(), c.out_t.as<double>(), c.out_err.as<double>(),
-                     c.out_prev.as<double>(), c.out_iters.as<int>(), c.out_status.as<int>(), c.stream, d_src_ds, d_tgt_ds, d_nrm,
-                     trace_iters > 0 && matches ? d_mat : nullptr, trace_iters, d_cnt);
+    const DevClouds s{c.pts_a.as<double>(), c.off_a.as<long long>(), 1, n_src, n_src};
+    const DevClouds t{c.pts_b.as<double>(), c.off_b.as<long long>(), 1, n_tgt, n_tgt};
+    IcpTrace tr;
+    tr.match = d_mat; tr.iters = d_mat ? trace_iters : 0; tr.stride = (int)n_src;
+    IcpArgs a;
+    memset(&a, 0, sizeof(a));
+    rc = icp_enqueue(k, 1, s, t, false, nullptr, nullptr, d_Ri, d_ti, c.out_r.as<double>(), c.out_t.as<double>(),
+                     c.out_err.as<double>(), c.out_prev.as<double>(), c.out_iters.as<int>(), c.out_status.as<int>(),
+                     c.stream, tr, &a);
     if (rc) return rc;
+    // the preprocessed clouds and normals are the kernels' own intermediate buffers
     int counts[2] = {0, 0};
-    ICPB_CUDA(cudaMemcpyAsync(counts, d_cnt, sizeof(counts), cudaMemcpyDeviceToHost, c.stream));
-    if (src_ds) ICPB_CUDA(cudaMemcpyAsync(src_ds, d_src_ds, b_src, cudaMemcpyDeviceToHost, c.stream));
-    if (tgt_ds) ICPB_CUDA(cudaMemcpyAsync(tgt_ds, d_tgt_ds, b_tgt, cudaMemcpyDeviceToHost, c.stream));
-    if (normals) ICPB_CUDA(cudaMemcpyAsync(normals, d_nrm, b_nrm, cudaMemcpyDeviceToHost, c.stream));
-    if (matches && b_mat) ICPB_CUDA(cudaMemcpyAsync(matches, d_mat, b_mat, cudaMemcpyDeviceToHost, c.stream));
+    ICPB_CUDA(cudaMemcpyAsync(&counts[0], a.s.ds_n, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    ICPB_CUDA(cudaMemcpyAsync(&counts[1], a.t.ds_n, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    if (src_ds) ICPB_CUDA(cudaMemcpyAsync(src_ds, a.s.ds, b_src, cudaMemcpyDeviceToHost, c.stream));
+    if (tgt_ds) ICPB_CUDA(cudaMemcpyAsync(tgt_ds, a.t.ds, b_tgt, cudaMemcpyDeviceToHost, c.stream));
+    if (normals && a.t.nrm) ICPB_CUDA(cudaMemcpyAsync(normals, a.t.nrm, b_nrm, cudaMemcpyDeviceToHost, c.stream));
+    if (d_mat) ICPB_CUDA(cudaMemcpyAsync(matches, d_mat, b_mat, cudaMemcpyDeviceToHost, c.stream));
     rc = fetch_outputs(c, 1, dim, IcpOutputs{R_out, t_out, err_out, prev_err_out, iters_out, status_out});
     if (rc) return rc;
-    if (n_src_ds) *n_src_ds = counts[0];
-    if (n_tgt_ds) *n_tgt_ds = counts[1];
+    if (n_src_ds) *n_src_ds = counts[0] > 0 ? counts[0] : 0;
+    if (n_tgt_ds) *n_tgt_ds = counts[1] > 0 ? counts[1] : 0;
+    return ICPB200_OK;
+}
+
+int icpb200_icp_last_stats(int64_t* stats8) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!stats8) { set_error("icpb200_icp_last_stats: null pointer"); return ICPB200_ERR_ARG; }
+    int rc = init_locked(-1);
+    if (rc) return rc;
+    Context& c = g_ctx;
+    for (int i = 0; i < 8; ++i) stats8[i] = 0;
+    if (!c.stats.p) return ICPB200_OK;
+    cudaStream_t st = c.last_icp_stream ? c.last_icp_stream : c.stream;
+    ICPB_CUDA(cudaMemcpyAsync(stats8, c.stats.p, 8 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    ICPB_CUDA(cudaStreamSynchronize(st));
+    // device time of the three kernels of the last call, in nanoseconds (CUDA events on its stream)
+    for (int i = 0; i < 3; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c.ev[i], c.ev[i + 1]) == cudaSuccess) stats8[5 + i] = (int64_t)(ms * 1e6);
+        else cudaGetLastError();
+    }
     return ICPB200_OK;
 }
 
@@ -418,19 +486,28 @@ int icpb200_voxel_downsample(const double* pts, int64_t n, int dim, double voxel
     int rc = init_locked(-1);
     if (rc) return rc;
     Context& c = g_ctx;
-    const int sort_pad = next_pow2((int)std::max<int64_t>(n, 256));
     if (n > 16384) {
         set_error("icpb200_voxel_downsample: %lld points exceed the single-CTA limit of 16384 in this build", (long long)n);
         return ICPB200_ERR_LIMIT;
     }
-    if (c.vox_in.reserve(sizeof(double) * dim * (size_t)n) || c.vox_out.reserve(sizeof(double) * dim * (size_t)n + 16))
-        return ICPB200_ERR_CUDA;
-    ICPB_CUDA(cudaMemcpyAsync(c.vox_in.p, pts, sizeof(double) * dim * (size_t)n, cudaMemcpyHostToDevice, c.stream));
-    int* d_n = reinterpret_cast<int*>(c.vox_out.as<unsigned char>() + sizeof(double) * dim * (size_t)n);
-    if ((rc = launch_voxel(c.vox_in.as<double>(), (int)n, dim, voxel_size, c.vox_out.as<double>(), d_n, sort_pad, c.stream)))
-        return rc;
+    const int sort_pad = next_pow2((int)std::max<int64_t>(n, 256));
+    // vox_in: points | offsets[2] ; vox_out: ds points | box[6] | count
+    const size_t b_pts = sizeof(double) * dim * (size_t)n;
+    if (c.vox_in.reserve(b_pts + 16) || c.vox_out.reserve(b_pts + 6 * sizeof(double) + 16)) return ICPB200_ERR_CUDA;
+    const int64_t off[2] = {0, n};
+    ICPB_CUDA(cudaMemcpyAsync(c.vox_in.p, pts, b_pts, cudaMemcpyHostToDevice, c.stream));
+    ICPB_CUDA(cudaMemcpyAsync(c.vox_in.as<unsigned char>() + b_pts, off, sizeof(off), cudaMemcpyHostToDevice, c.stream));
+    CloudSet cs;
+    memset(&cs, 0, sizeof(cs));
+    cs.raw = c.vox_in.as<double>();
+    cs.off = reinterpret_cast<const long long*>(c.vox_in.as<unsigned char>() + b_pts);
+    cs.n_clouds = 1;
+    cs.ds = c.vox_out.as<double>();
+    cs.box = reinterpret_cast<double*>(c.vox_out.as<unsigned char>() + b_pts);
+    cs.ds_n = reinterpret_cast<int*>(c.vox_out.as<unsigned char>() + b_pts + 6 * sizeof(double));
+    if ((rc = launch_voxel_clouds(cs, dim, voxel_size, sort_pad, c.stream))) return rc;
     int m = 0;
-    ICPB_CUDA(cudaMemcpyAsync(&m, d_n, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    ICPB_CUDA(cudaMemcpyAsync(&m, cs.ds_n, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
     ICPB_CUDA(cudaStreamSynchronize(c.stream));
     if (m < 0) {
         set_error("icpb200_voxel_downsample: voxel index range does not fit 62 bits");

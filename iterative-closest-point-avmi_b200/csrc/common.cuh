@@ -46,15 +46,17 @@ struct Context {
     int sm_count = 0;
     int max_smem_optin = 0;
     cudaStream_t stream = nullptr;     // library-owned stream for the host-buffer entry points
-    // ICP staging / workspace
+    // ICP staging (host-buffer entry points)
     DevBuf pts_a, pts_b, off_a, off_b, idx_a, idx_b, rinit, tinit;
-    DevBuf out_r, out_t, out_err, out_prev, out_iters, out_status, icp_ws, queue;
-    DevBuf trace;
+    DevBuf out_r, out_t, out_err, out_prev, out_iters, out_status, queue, trace, stats;
+    // preprocessed form of cloud sets A and B (see CloudSet in icp_kernel.h)
+    DevBuf aux_ds[2], aux_n[2], aux_box[2], aux_nrm[2], aux_flags[2];
+    cudaStream_t last_icp_stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // K1 start | K2 start | K3 start | K3 end
     // voxel_downsample entry point
     DevBuf vox_in, vox_out;
 };
 
 Context& ctx();
-int ensure_ready();                    // lazily binds to the current / default device
 
 }  // namespace icpb

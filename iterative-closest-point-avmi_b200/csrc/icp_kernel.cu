@@ -1,22 +1,35 @@
-// Persistent per-pair ICP registration kernel for sm_100a.
+// ICP registration kernels for sm_100a.
 //
-// One CTA owns one (source, target) pair from the queue and runs the whole of
-// /root/reference/utilities/icp.py:132-223 for it without leaving the SM:
-//   A  voxel-grid mean of both clouds            (icp.py:150-151, 117-129)
-//   B  stage the target in shared memory (fp64 for decisions, fp32 for the sweep)
-//   C  target normals by exact (k+1)-NN + 2x2 PCA (icp.py:165-167, 51-76)
-//   D  iterate: nearest neighbour -> gate -> solve -> apply -> error -> test
-//                                                 (icp.py:177-220)
-// Nearest neighbour (brute mode): every thread keeps S source points in
-// registers and sweeps the whole target, 32 points per tile, with the
-// direct-difference fp32 distance (2 FADD + FMUL + FFMA per pair, the form
-// SURVEY.md H2 found to reproduce the fp64 argmin).  Only the per-tile minimum
-// is tracked in the sweep; the winning tile is then re-evaluated in fp64 and
-// the runner-up tile minimum bounds every other target.  If that bound cannot
-// exclude a closer point (margin = fp32 rounding of the recentred
-// coordinates) the point is re-decided by a full fp64 scan, so the
-// correspondence is the exact fp64 nearest neighbour (lowest index on exact
-// ties), as scipy's KDTree query returns.
+//   K1 voxel_clouds_kernel  one CTA per referenced cloud: voxel-grid mean
+//                           (/root/reference/utilities/icp.py:150-151, 117-129)
+//   K2 normals_kernel       one CTA per point-to-line target cloud: exact
+//                           (k+1)-NN + 2x2 PCA normals (icp.py:165-167, 51-76)
+//   K3 icp_pairs_kernel     persistent, one CTA per (source, target) pair from
+//                           an atomic queue; the whole loop of icp.py:175-220
+//                           (nearest neighbour -> gate -> solve -> apply ->
+//                           error -> convergence test) runs out of shared
+//                           memory without leaving the SM.
+//
+// Nearest neighbour in K3 (brute mode).  A warp takes 32 source points per
+// "chunk" (one per lane, up to 8 chunks in registers) and sweeps the whole
+// target, 32 points per tile, with the direct-difference fp32 distance
+// (2 FADD + FMUL + FFMA per pair, the form SURVEY.md H2 found to reproduce
+// the fp64 argmin).  The sweep only tracks per-tile minima; the winning tile
+// is re-evaluated in fp64 and the runner-up tile minimum bounds every other
+// target.  If that bound cannot exclude a closer point (margin = fp32
+// rounding of the recentred coordinates) the point is re-decided by a full
+// fp64 scan.  The correspondence is therefore the exact fp64 nearest
+// neighbour (lowest index on exact ties), as scipy's KDTree query returns.
+//
+// Exact carry-over between iterations.  Each decision also yields D2, a lower
+// bound on the distance from the point to every target other than its match.
+// In later iterations a point that has moved by at most `moved` since then
+// keeps its match without a sweep whenever dist(p, match) < D2 - moved
+// (triangle inequality: every other target is still farther).  Points that
+// fail the test are compacted and swept again.  ICP steps shrink
+// geometrically, so most of the 150-iteration limit-cycle pairs' work
+// disappears while every correspondence stays the exact nearest neighbour.
+//
 // All reductions are fp64, fixed-order (warp butterfly, then warps in order):
 // no atomics in any sum, so results are bitwise reproducible run to run.
 #include "icp_b200.h"
@@ -27,50 +40,217 @@
 
 namespace icpb {
 
-constexpr int kSMax = 8;               // source points per thread per sweep round
+constexpr int kSMax = 8;               // chunks (of 32 source points) per warp per sweep round
 constexpr int kKnnMax = 64;            // normal_k + 1 upper bound
 constexpr int kGridCells = 4096;       // shared-memory uniform grid for the normals kNN
 constexpr float kFar = 3.0e18f;        // padding target coordinate (distance^2 ~ 1.8e37, finite)
 
 __host__ __device__ inline int pad_index(int j) { return j + (j >> 5); }   // 33-stride tiles
+__host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~size_t(15); }
 
-// ---- shared-memory carve-up (must match icp_smem_bytes) --------------------
-struct Carve {
-    CtaShared* sh;
-    double* tgt64;          // DIM arrays of (cap_t + cap_t/32) doubles, tile-padded SoA
-    unsigned char* scratch; // phase-local region
-    size_t tgt64_stride;
-};
+// ---- shared-memory sizes (must match the carve-up in the kernels) -----------
+size_t icp_pair_smem_bytes(int dim, int cap_s, int cap_t) {
+    size_t b = align16(sizeof(CtaShared));
+    b += sizeof(double) * dim * (size_t)(cap_t + cap_t / 32);          // tgt64, tile-padded SoA
+    b = align16(b);
+    b += sizeof(float) * (dim == 2 ? 2 : 4) * (size_t)cap_t;           // tgt32
+    b += sizeof(double) * dim * (size_t)cap_s;                         // cur64 SoA
+    b += sizeof(int) * (size_t)cap_s;                                  // match
+    b += sizeof(float) * 2 * (size_t)cap_s;                            // d2lb, moved
+    b += sizeof(unsigned short) * 2 * (size_t)cap_s;                   // todo, ambiguous
+    return align16(b);
+}
+size_t icp_voxel_smem_bytes(int sort_pad) { return align16(sizeof(CtaShared)) + (size_t)sort_pad * 12; }
+size_t icp_normals_smem_bytes(int cap_t) {
+    return align16(sizeof(CtaShared)) + align16(sizeof(double) * 2 * (size_t)(cap_t + cap_t / 32)) +
+           sizeof(int) * (kGridCells + 1) + sizeof(unsigned short) * (size_t)cap_t + 16;
+}
 
+// ---- K0: which clouds are referenced / are point-to-line targets -------------
+__global__ void mark_used_kernel(int n_pairs, const int* __restrict__ src_idx, const int* __restrict__ tgt_idx,
+                                 unsigned char* used_s, unsigned char* used_t, unsigned char* is_tgt) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const int cs = src_idx ? src_idx[p] : p, ct = tgt_idx ? tgt_idx[p] : p;
+    used_s[cs] = 1;
+    used_t[ct] = 1;
+    if (is_tgt) is_tgt[ct] = 1;
+}
+
+// ---- K1: voxel-grid means, one CTA per cloud -----------------------------------
 template <int DIM>
-__host__ __device__ inline size_t smem_persistent_bytes(int cap_t) {
-    size_t b = (sizeof(CtaShared) + 15) & ~size_t(15);
-    b += sizeof(double) * DIM * (size_t)(cap_t + cap_t / 32);
-    return (b + 15) & ~size_t(15);
+__global__ void __launch_bounds__(kNT) voxel_clouds_kernel(const CloudSet cs, double voxel, int sort_pad) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    CtaShared& sh = *reinterpret_cast<CtaShared*>(smem);
+    const int c = blockIdx.x;
+    if (cs.used && !cs.used[c]) return;
+    const long long beg = cs.off[c];
+    const long long n = cs.off[c + 1] - beg;
+    if (n <= 0 || n > sort_pad) {
+        if (threadIdx.x == 0) cs.ds_n[c] = -1;
+        return;
+    }
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + align16(sizeof(CtaShared)));
+    unsigned int* sidx = reinterpret_cast<unsigned int*>(smem + align16(sizeof(CtaShared)) + (size_t)sort_pad * 8);
+    int phase = 0;
+    double lo[DIM], hi[DIM];
+    const int m = cta_voxel_means<DIM>(cs.raw + beg * DIM, (int)n, voxel, cs.ds + beg * DIM, keys, sidx, sort_pad,
+                                       sh, phase, lo, hi);
+    if (threadIdx.x == 0) {
+        cs.ds_n[c] = m;
+        for (int k = 0; k < 3; ++k) {
+            cs.box[(size_t)c * 6 + k] = k < DIM ? lo[k] : 0.0;
+            cs.box[(size_t)c * 6 + 3 + k] = k < DIM ? hi[k] : 0.0;
+        }
+    }
 }
-template <int DIM>
-__host__ __device__ inline size_t smem_loop_bytes(int cap_s, int cap_t) {
-    size_t b = sizeof(float) * (DIM == 2 ? 2 : 4) * (size_t)cap_t;      // tgt32
-    b += sizeof(double) * DIM * (size_t)cap_s;                          // cur64 SoA
-    b += sizeof(int) * (size_t)cap_s * 2;                               // match + ambiguous list
-    return b;
-}
-__host__ __device__ inline size_t smem_grid_bytes(int cap_t) {
-    return sizeof(int) * (kGridCells + 1) + sizeof(unsigned short) * (size_t)cap_t + 16;
-}
-__host__ __device__ inline size_t smem_sort_bytes(int sort_pad) { return (size_t)sort_pad * 12; }
 
-size_t icp_smem_bytes(int dim, int cap_s, int cap_t, int sort_pad) {
-    const size_t pers = dim == 2 ? smem_persistent_bytes<2>(cap_t) : smem_persistent_bytes<3>(cap_t);
-    size_t loop = dim == 2 ? smem_loop_bytes<2>(cap_s, cap_t) : smem_loop_bytes<3>(cap_s, cap_t);
-    if (smem_grid_bytes(cap_t) > loop) loop = smem_grid_bytes(cap_t);
-    size_t total = pers + loop;
-    const size_t hdr = (sizeof(CtaShared) + 15) & ~size_t(15);
-    if (hdr + smem_sort_bytes(sort_pad) > total) total = hdr + smem_sort_bytes(sort_pad);
-    return total;
+// ---- K2: normals: exact (k+1)-NN on a shared-memory uniform grid + 2x2 PCA -------
+// Restates utilities/icp.py:51-76.  All distances fp64; the neighbour set is
+// the exact (k+1)-NN (ties broken by lower index).  np.cov's 1/(K-1) scale is
+// dropped: it does not change the eigenvector.
+__device__ void cta_normals_2d(const double* tx, const double* ty, int n_t, int normal_k,
+                               double* __restrict__ normals_out, int* cell_start,
+                               unsigned short* items, CtaShared& sh) {
+    const int K = min(normal_k, n_t - 1) + 1;
+    if (threadIdx.x == 0) {
+        const double w = sh.hi_t[0] - sh.lo_t[0], hgt = sh.hi_t[1] - sh.lo_t[1];
+        double h = sqrt(fmax(w * hgt, 1e-300) / (0.9 * kGridCells));
+        h = fmax(h, fmax(w, hgt) / 2048.0);
+        if (!(h > 0.0)) h = 1.0;
+        int gx = (int)(w / h) + 1, gy = (int)(hgt / h) + 1;
+        while ((long long)gx * gy > kGridCells) {
+            h *= 1.25;
+            gx = (int)(w / h) + 1;
+            gy = (int)(hgt / h) + 1;
+        }
+        sh.grid_h = h; sh.grid_nx = gx; sh.grid_ny = gy;
+    }
+    for (int c = threadIdx.x; c <= kGridCells; c += kNT) cell_start[c] = 0;
+    __syncthreads();
+    const double h = sh.grid_h, lox = sh.lo_t[0], loy = sh.lo_t[1];
+    const int gx = sh.grid_nx, gy = sh.grid_ny;
+    auto cell_of = [&](double x, double y, int& cxi, int& cyi) {
+        cxi = min(gx - 1, max(0, (int)((x - lox) / h)));
+        cyi = min(gy - 1, max(0, (int)((y - loy) / h)));
+    };
+    for (int i = threadIdx.x; i < n_t; i += kNT) {
+        int cxi, cyi;
+        cell_of(tx[pad_index(i)], ty[pad_index(i)], cxi, cyi);
+        atomicAdd(&cell_start[cyi * gx + cxi], 1);
+    }
+    __syncthreads();
+    {   // in-place exclusive scan over the cells (kGridCells / kNT per thread)
+        constexpr int per = kGridCells / kNT;
+        const int beg = threadIdx.x * per;
+        int local = 0;
+        for (int c = beg; c < beg + per; ++c) local += cell_start[c];
+        int total;
+        int run = block_excl_scan(local, sh, total);
+        for (int c = beg; c < beg + per; ++c) {
+            const int v = cell_start[c];
+            cell_start[c] = run;
+            run += v;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_t; i += kNT) {
+        int cxi, cyi;
+        cell_of(tx[pad_index(i)], ty[pad_index(i)], cxi, cyi);
+        const int pos = atomicAdd(&cell_start[cyi * gx + cxi], 1);
+        items[pos] = (unsigned short)i;
+    }
+    __syncthreads();
+    // now cell c holds items[(c ? cell_start[c-1] : 0) .. cell_start[c])
+    for (int i = threadIdx.x; i < n_t; i += kNT) {
+        const double px = tx[pad_index(i)], py = ty[pad_index(i)];
+        int cxi, cyi;
+        cell_of(px, py, cxi, cyi);
+        double bd[kKnnMax];
+        int bi[kKnnMax];
+        int cnt = 0;
+        for (int r = 0;; ++r) {
+            const int x0 = cxi - r, x1 = cxi + r, y0 = cyi - r, y1 = cyi + r;
+            for (int y = max(y0, 0); y <= min(y1, gy - 1); ++y) {
+                const bool edge_row = (y == y0) || (y == y1);
+                const int xstep = edge_row ? 1 : max(2 * r, 1);
+                for (int x = x0; x <= x1; x += xstep) {
+                    if (x < 0 || x >= gx) continue;
+                    const int c = y * gx + x;
+                    const int beg = c ? cell_start[c - 1] : 0, end = cell_start[c];
+                    for (int e = beg; e < end; ++e) {
+                        const int j = items[e];
+                        const double dx = px - tx[pad_index(j)], dy = py - ty[pad_index(j)];
+                        const double d = dx * dx + dy * dy;
+                        if (cnt == K && !(d < bd[K - 1] || (d == bd[K - 1] && j < bi[K - 1]))) continue;
+                        int m = cnt < K ? cnt : K - 1;          // slot to fill
+                        while (m > 0 && (bd[m - 1] > d || (bd[m - 1] == d && bi[m - 1] > j))) {
+                            bd[m] = bd[m - 1];
+                            bi[m] = bi[m - 1];
+                            --m;
+                        }
+                        bd[m] = d;
+                        bi[m] = j;
+                        if (cnt < K) ++cnt;
+                    }
+                }
+            }
+            // everything not yet visited lies outside the (2r+1)^2 block of cells
+            const bool all = (x0 <= 0) && (y0 <= 0) && (x1 >= gx - 1) && (y1 >= gy - 1);
+            if (all) break;
+            if (cnt == K) {
+                double bound = INFINITY;
+                if (x0 > 0) bound = fmin(bound, px - (lox + x0 * h));
+                if (x1 < gx - 1) bound = fmin(bound, (lox + (x1 + 1) * h) - px);
+                if (y0 > 0) bound = fmin(bound, py - (loy + y0 * h));
+                if (y1 < gy - 1) bound = fmin(bound, (loy + (y1 + 1) * h) - py);
+                bound = bound * (1.0 - 1e-9) - 1e-12 * h;
+                if (bound > 0.0 && bd[K - 1] < bound * bound) break;
+            }
+        }
+        // PCA of the neighbourhood (np.cov is two-pass: subtract the mean first)
+        double mx = 0.0, my = 0.0;
+        for (int m = 0; m < cnt; ++m) { mx += tx[pad_index(bi[m])]; my += ty[pad_index(bi[m])]; }
+        mx /= (double)cnt; my /= (double)cnt;
+        double sxx = 0.0, sxy = 0.0, syy = 0.0;
+        for (int m = 0; m < cnt; ++m) {
+            const double dx = tx[pad_index(bi[m])] - mx, dy = ty[pad_index(bi[m])] - my;
+            sxx += dx * dx; sxy += dx * dy; syy += dy * dy;
+        }
+        double nrm[2];
+        sym2_min_eigvec(sxx, sxy, syy, nrm);
+        normals_out[2 * i] = nrm[0];
+        normals_out[2 * i + 1] = nrm[1];
+    }
 }
 
-// ---- fp32 sweep ------------------------------------------------------------
+__global__ void __launch_bounds__(kNT) normals_kernel(const CloudSet cs, int normal_k, int cap_t) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    CtaShared& sh = *reinterpret_cast<CtaShared*>(smem);
+    const int c = blockIdx.x;
+    if (!cs.is_tgt[c]) return;
+    const int n = cs.ds_n[c];
+    if (n <= 0) return;
+    const int tstride = cap_t + cap_t / 32;
+    double* tx = reinterpret_cast<double*>(smem + align16(sizeof(CtaShared)));
+    double* ty = tx + tstride;
+    unsigned char* rest = smem + align16(sizeof(CtaShared)) + align16(sizeof(double) * 2 * (size_t)tstride);
+    int* cell_start = reinterpret_cast<int*>(rest);
+    unsigned short* items = reinterpret_cast<unsigned short*>(rest + sizeof(int) * (kGridCells + 1));
+    const long long beg = cs.off[c];
+    const double* ds = cs.ds + beg * 2;
+    for (int j = threadIdx.x; j < n; j += kNT) {
+        tx[pad_index(j)] = ds[2 * j];
+        ty[pad_index(j)] = ds[2 * j + 1];
+    }
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 3; ++k) { sh.lo_t[k] = cs.box[(size_t)c * 6 + k]; sh.hi_t[k] = cs.box[(size_t)c * 6 + 3 + k]; }
+    }
+    __syncthreads();
+    cta_normals_2d(tx, ty, n, normal_k, cs.nrm + beg * 2, cell_start, items, sh);
+}
+
+// ---- K3: fp32 sweep --------------------------------------------------------------
 // Tracks, per source point, the smallest per-tile minimum (b1, tile bt) and
 // the smallest minimum over all OTHER tiles (b2).
 template <int S>
@@ -141,18 +321,21 @@ __device__ __forceinline__ void sweep3d(const float4* __restrict__ t32, int n_ti
 
 template <int DIM>
 struct Loop {
-    // views into shared memory, valid during phase D
+    // views into shared memory, valid during the iteration loop
     const double* tx; const double* ty; const double* tz;     // tile-padded target fp64
     double* cx; double* cy; double* cz;                        // current source fp64 (SoA)
     float4* t32;
     int* match;
-    int* amb;
+    float* d2lb;             // lower bound on the distance to every non-match target at decision time
+    float* moved;            // upper bound on the movement since that decision
+    unsigned short* todo;    // points that need a sweep this iteration
+    unsigned short* amb;     // points that need the full fp64 scan
     int n_s, n_t, n_tiles;
     double c0, c1, c2;       // recentring offset
     float ta;                // sum over axes of max |target - centre|
 };
 
-// exact squared distance in fp64 between source i and target j
+// exact squared distance in fp64 between a point and target j
 template <int DIM>
 __device__ __forceinline__ double dist2_64(const Loop<DIM>& L, double px, double py, double pz, int j) {
     const int jp = pad_index(j);
@@ -162,71 +345,81 @@ __device__ __forceinline__ double dist2_64(const Loop<DIM>& L, double px, double
     return d;
 }
 
-// One sweep round: source points base + threadIdx.x + s*kNT, s < S.
+__device__ __forceinline__ float f32_down(double v) { return __double2float_rd(v); }
+
+// One sweep round for this warp: chunks first_chunk + s * kNW, s < S, of the todo list.
 template <int DIM, int S>
-__device__ __forceinline__ void nn_round(const Loop<DIM>& L, CtaShared& sh, int base) {
+__device__ __forceinline__ void nn_round(const Loop<DIM>& L, CtaShared& sh, int first_chunk, int n_todo) {
+    const int lane = threadIdx.x & 31;
     float sx[S], sy[S], sz[S];
     float b1[S], b2[S];
-    int bt[S];
+    int bt[S], pt[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-        const int i = base + threadIdx.x + s * kNT;
-        const bool ok = i < L.n_s;
-        sx[s] = ok ? (float)(L.cx[i] - L.c0) : 0.f;
-        sy[s] = ok ? (float)(L.cy[i] - L.c1) : 0.f;
-        sz[s] = (DIM == 3 && ok) ? (float)(L.cz[i] - L.c2) : 0.f;
+        const int q = (first_chunk + s * kNW) * 32 + lane;
+        pt[s] = q < n_todo ? (int)L.todo[q] : -1;
+        const int i = max(pt[s], 0);
+        sx[s] = pt[s] >= 0 ? (float)(L.cx[i] - L.c0) : 0.f;
+        sy[s] = pt[s] >= 0 ? (float)(L.cy[i] - L.c1) : 0.f;
+        sz[s] = (DIM == 3 && pt[s] >= 0) ? (float)(L.cz[i] - L.c2) : 0.f;
     }
     if (DIM == 2) sweep2d<S>(L.t32, L.n_tiles, sx, sy, b1, b2, bt);
     else          sweep3d<S>(L.t32, L.n_tiles, sx, sy, sz, b1, b2, bt);
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-        const int i = base + threadIdx.x + s * kNT;
-        if (i >= L.n_s) continue;
+        const int i = pt[s];
+        if (i < 0) continue;
         const double px = L.cx[i], py = L.cy[i], pz = DIM == 3 ? L.cz[i] : 0.0;
         const int j0 = bt[s] * 32;
         const int j1 = min(j0 + 32, L.n_t);
-        double best = INFINITY;
+        double best = INFINITY, second = INFINITY;
         int bj = j0;
         for (int j = j0; j < j1; ++j) {
             const double d = dist2_64<DIM>(L, px, py, pz, j);
-            if (d < best) { best = d; bj = j; }
+            if (d < best) { second = best; best = d; bj = j; }
+            else if (d < second) second = d;
         }
-        L.match[i] = bj;
         // Can a target outside the winning tile be closer?  fp32 coordinate
         // rounding moves a distance by at most eps32 * (|s| + |t|) summed over
-        // axes; 3x safety on the 2^-24 unit roundoff plus the arithmetic's own
-        // relative error (4 roundings) folded into `rel`.
+        // axes; 3x safety on the 2^-24 unit roundoff, and the sweep's own four
+        // roundings folded into `rel`.
         const float mag = fabsf(sx[s]) + fabsf(sy[s]) + (DIM == 3 ? fabsf(sz[s]) : 0.f) + L.ta;
         const double slack = 1.8e-7 * (double)mag;
-        const double rel = 1.0 - 1.0e-6;
-        const double other = sqrt((double)b2[s]) * rel - slack;
-        if (!(other > sqrt(best))) {
-            const int k = atomicAdd(&sh.amb_n, 1);
-            L.amb[k] = i;
+        const double other = sqrt((double)b2[s]) * (1.0 - 1.0e-6) - slack;
+        const double d1 = sqrt(best);
+        if (!(other > d1)) {
+            L.amb[atomicAdd(&sh.amb_n, 1)] = (unsigned short)i;
+        } else {
+            L.match[i] = bj;
+            L.d2lb[i] = f32_down(fmin(other, sqrt(second) * (1.0 - 1e-12)));
+            L.moved[i] = 0.f;
         }
     }
 }
 
 template <int DIM>
-__device__ __forceinline__ void nn_dispatch(const Loop<DIM>& L, CtaShared& sh) {
-    for (int base = 0; base < L.n_s; base += kSMax * kNT) {
-        const int rem = L.n_s - base;
-        const int s_need = min(kSMax, (rem + kNT - 1) / kNT);
-        switch (s_need) {
-            case 1: nn_round<DIM, 1>(L, sh, base); break;
-            case 2: nn_round<DIM, 2>(L, sh, base); break;
-            case 3: nn_round<DIM, 3>(L, sh, base); break;
-            case 4: nn_round<DIM, 4>(L, sh, base); break;
-            case 5: nn_round<DIM, 5>(L, sh, base); break;
-            case 6: nn_round<DIM, 6>(L, sh, base); break;
-            case 7: nn_round<DIM, 7>(L, sh, base); break;
-            default: nn_round<DIM, 8>(L, sh, base); break;
+__device__ __forceinline__ void nn_dispatch(const Loop<DIM>& L, CtaShared& sh, int n_todo) {
+    const int w = threadIdx.x >> 5;
+    const int n_chunks = (n_todo + 31) >> 5;
+    for (int base = 0; base < n_chunks; base += kSMax * kNW) {
+        const int first = base + w;
+        const int mine = first < n_chunks ? min(kSMax, (n_chunks - first + kNW - 1) / kNW) : 0;   // warp-uniform
+        switch (mine) {
+            case 0: break;
+            case 1: nn_round<DIM, 1>(L, sh, first, n_todo); break;
+            case 2: nn_round<DIM, 2>(L, sh, first, n_todo); break;
+            case 3: nn_round<DIM, 3>(L, sh, first, n_todo); break;
+            case 4: nn_round<DIM, 4>(L, sh, first, n_todo); break;
+            case 5: nn_round<DIM, 5>(L, sh, first, n_todo); break;
+            case 6: nn_round<DIM, 6>(L, sh, first, n_todo); break;
+            case 7: nn_round<DIM, 7>(L, sh, first, n_todo); break;
+            default: nn_round<DIM, 8>(L, sh, first, n_todo); break;
         }
     }
 }
 
 // Points whose runner-up bound was inconclusive: one warp per point scans the
-// whole target in fp64 (lowest index wins exact ties).
+// whole target in fp64 (lowest index wins exact ties) and keeps the two best.
 template <int DIM>
 __device__ __forceinline__ void resolve_ambiguous(const Loop<DIM>& L, const CtaShared& sh) {
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -234,159 +427,62 @@ __device__ __forceinline__ void resolve_ambiguous(const Loop<DIM>& L, const CtaS
     for (int a = w; a < n_amb; a += kNW) {
         const int i = L.amb[a];
         const double px = L.cx[i], py = L.cy[i], pz = DIM == 3 ? L.cz[i] : 0.0;
-        double best = INFINITY;
+        double best = INFINITY, second = INFINITY;
         int bj = 0x7fffffff;
         for (int j = l; j < L.n_t; j += 32) {
             const double d = dist2_64<DIM>(L, px, py, pz, j);
-            if (d < best) { best = d; bj = j; }
+            if (d < best) { second = best; best = d; bj = j; }
+            else if (d < second) second = d;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const double od = __shfl_xor_sync(0xffffffffu, best, o);
+            const double os = __shfl_xor_sync(0xffffffffu, second, o);
             const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
-            if (od < best || (od == best && oj < bj)) { best = od; bj = oj; }
+            if (od < best || (od == best && oj < bj)) {
+                second = fmin(best, os);
+                best = od; bj = oj;
+            } else {
+                second = fmin(second, od);
+            }
         }
-        if (l == 0) L.match[i] = bj;
+        if (l == 0) {
+            L.match[i] = bj;
+            L.d2lb[i] = f32_down(sqrt(second) * (1.0 - 1e-12));
+            L.moved[i] = 0.f;
+        }
     }
 }
 
-// ---- normals: exact (k+1)-NN on a shared-memory uniform grid + 2x2 PCA ------
-// Restates utilities/icp.py:51-76.  All distances fp64; the neighbour set is
-// the exact (k+1)-NN (ties broken by lower index).  np.cov's 1/(K-1) scale is
-// dropped: it does not change the eigenvector.
-__device__ void cta_normals_2d(const double* tx, const double* ty, int n_t, int normal_k,
-                               double* __restrict__ normals_out, int* cell_start,
-                               unsigned short* items, CtaShared& sh) {
-    const int K = min(normal_k, n_t - 1) + 1;
-    if (threadIdx.x == 0) {
-        const double w = sh.hi_t[0] - sh.lo_t[0], hgt = sh.hi_t[1] - sh.lo_t[1];
-        double h = sqrt(fmax(w * hgt, 1e-300) / (0.9 * kGridCells));
-        h = fmax(h, fmax(w, hgt) / 2048.0);
-        if (!(h > 0.0)) h = 1.0;
-        int gx = (int)(w / h) + 1, gy = (int)(hgt / h) + 1;
-        while ((long long)gx * gy > kGridCells) {
-            h *= 1.25;
-            gx = (int)(w / h) + 1;
-            gy = (int)(hgt / h) + 1;
-        }
-        sh.grid_h = h; sh.grid_nx = gx; sh.grid_ny = gy;
-    }
-    for (int c = threadIdx.x; c <= kGridCells; c += kNT) cell_start[c] = 0;
-    __syncthreads();
-    const double h = sh.grid_h, lox = sh.lo_t[0], loy = sh.lo_t[1];
-    const int gx = sh.grid_nx, gy = sh.grid_ny, ncell = gx * gy;
-    auto cell_of = [&](double x, double y, int& cxi, int& cyi) {
-        cxi = min(gx - 1, max(0, (int)((x - lox) / h)));
-        cyi = min(gy - 1, max(0, (int)((y - loy) / h)));
-    };
-    for (int i = threadIdx.x; i < n_t; i += kNT) {
-        int cxi, cyi;
-        cell_of(tx[pad_index(i)], ty[pad_index(i)], cxi, cyi);
-        atomicAdd(&cell_start[cyi * gx + cxi], 1);
-    }
-    __syncthreads();
-    {   // in-place exclusive scan over the cells (kGridCells / kNT per thread)
-        constexpr int per = kGridCells / kNT;
-        const int beg = threadIdx.x * per;
-        int local = 0;
-        for (int c = beg; c < beg + per; ++c) local += cell_start[c];
-        int total;
-        int run = block_excl_scan(local, sh, total);
-        for (int c = beg; c < beg + per; ++c) {
-            const int v = cell_start[c];
-            cell_start[c] = run;
-            run += v;
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < n_t; i += kNT) {
-        int cxi, cyi;
-        cell_of(tx[pad_index(i)], ty[pad_index(i)], cxi, cyi);
-        const int pos = atomicAdd(&cell_start[cyi * gx + cxi], 1);
-        items[pos] = (unsigned short)i;
-    }
-    __syncthreads();
-    // now cell c holds items[(c ? cell_start[c-1] : 0) .. cell_start[c])
-    (void)ncell;
-    for (int i = threadIdx.x; i < n_t; i += kNT) {
-        const double px = tx[pad_index(i)], py = ty[pad_index(i)];
-        int cxi, cyi;
-        cell_of(px, py, cxi, cyi);
-        double bd[kKnnMax];
-        int bi[kKnnMax];
-        int cnt = 0;
-        for (int r = 0;; ++r) {
-            const int x0 = cxi - r, x1 = cxi + r, y0 = cyi - r, y1 = cyi + r;
-            for (int y = max(y0, 0); y <= min(y1, gy - 1); ++y) {
-                const bool edge_row = (y == y0) || (y == y1);
-                const int xstep = edge_row ? 1 : max(2 * r, 1);
-                for (int x = x0; x <= x1; x += xstep) {
-                    if (x < 0 || x >= gx) continue;
-                    const int c = y * gx + x;
-                    const int beg = c ? cell_start[c - 1] : 0, end = cell_start[c];
-                    for (int e = beg; e < end; ++e) {
-                        const int j = items[e];
-                        const double dx = px - tx[pad_index(j)], dy = py - ty[pad_index(j)];
-                        const double d = dx * dx + dy * dy;
-                        if (cnt == K && !(d < bd[K - 1] || (d == bd[K - 1] && j < bi[K - 1]))) continue;
-                        int m = cnt < K ? cnt : K - 1;          // slot to fill
-                        while (m > 0 && (bd[m - 1] > d || (bd[m - 1] == d && bi[m - 1] > j))) {
-                            bd[m] = bd[m - 1];
-                            bi[m] = bi[m - 1];
-                            --m;
-                        }
-                        bd[m] = d;
-                        bi[m] = j;
-                        if (cnt < K) ++cnt;
-                    }
-                }
-            }
-            // everything not yet visited lies outside the (2r+1)^2 block of cells
-            const bool all = (x0 <= 0) && (y0 <= 0) && (x1 >= gx - 1) && (y1 >= gy - 1);
-            if (all) break;
-            if (cnt == K) {
-                double bound = INFINITY;
-                if (x0 > 0) bound = fmin(bound, px - (lox + x0 * h));
-                if (x1 < gx - 1) bound = fmin(bound, (lox + (x1 + 1) * h) - px);
-                if (y0 > 0) bound = fmin(bound, py - (loy + y0 * h));
-                if (y1 < gy - 1) bound = fmin(bound, (loy + (y1 + 1) * h) - py);
-                bound = bound * (1.0 - 1e-9) - 1e-12 * h;
-                if (bound > 0.0 && bd[K - 1] < bound * bound) break;
-            }
-        }
-        // PCA of the neighbourhood (np.cov is two-pass: subtract the mean first)
-        double mx = 0.0, my = 0.0;
-        for (int m = 0; m < cnt; ++m) { mx += tx[pad_index(bi[m])]; my += ty[pad_index(bi[m])]; }
-        mx /= (double)cnt; my /= (double)cnt;
-        double sxx = 0.0, sxy = 0.0, syy = 0.0;
-        for (int m = 0; m < cnt; ++m) {
-            const double dx = tx[pad_index(bi[m])] - mx, dy = ty[pad_index(bi[m])] - my;
-            sxx += dx * dx; sxy += dx * dy; syy += dy * dy;
-        }
-        double nrm[2];
-        sym2_min_eigvec(sxx, sxy, syy, nrm);
-        normals_out[2 * i] = nrm[0];
-        normals_out[2 * i + 1] = nrm[1];
-    }
-    __syncthreads();
-}
-
-// ---- the kernel --------------------------------------------------------------
+// ---- K3: the kernel ----------------------------------------------------------------
 template <int DIM>
 __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     CtaShared& sh = *reinterpret_cast<CtaShared*>(smem);
-    const size_t hdr = (sizeof(CtaShared) + 15) & ~size_t(15);
     const int tid = threadIdx.x;
     const int tstride = a.cap_t + a.cap_t / 32;
-    double* tgt64 = reinterpret_cast<double*>(smem + hdr);
-    unsigned char* scratch = smem + smem_persistent_bytes<DIM>(a.cap_t);
-    // workspace of this CTA
-    double* ws = a.ws + (size_t)blockIdx.x * a.ws_stride;
-    double* src_ds = ws;
-    double* tgt_ds = ws + (size_t)DIM * a.cap_s;
-    double* normals = tgt_ds + (size_t)DIM * a.cap_t;
+    Loop<DIM> L;
+    {
+        unsigned char* q = smem + align16(sizeof(CtaShared));
+        double* tgt64 = reinterpret_cast<double*>(q);
+        L.tx = tgt64; L.ty = tgt64 + tstride; L.tz = tgt64 + 2 * (size_t)tstride;
+        q += sizeof(double) * DIM * (size_t)tstride;
+        q = smem + align16((size_t)(q - smem));
+        L.t32 = reinterpret_cast<float4*>(q);          q += sizeof(float) * (DIM == 2 ? 2 : 4) * (size_t)a.cap_t;
+        L.cx = reinterpret_cast<double*>(q);           q += sizeof(double) * (size_t)a.cap_s;
+        L.cy = reinterpret_cast<double*>(q);           q += sizeof(double) * (size_t)a.cap_s;
+        L.cz = reinterpret_cast<double*>(q);           if (DIM == 3) q += sizeof(double) * (size_t)a.cap_s;
+        L.match = reinterpret_cast<int*>(q);           q += sizeof(int) * (size_t)a.cap_s;
+        L.d2lb = reinterpret_cast<float*>(q);          q += sizeof(float) * (size_t)a.cap_s;
+        L.moved = reinterpret_cast<float*>(q);         q += sizeof(float) * (size_t)a.cap_s;
+        L.todo = reinterpret_cast<unsigned short*>(q); q += sizeof(unsigned short) * (size_t)a.cap_s;
+        L.amb = reinterpret_cast<unsigned short*>(q);
+    }
+    double* tx = const_cast<double*>(L.tx);
+    double* ty = const_cast<double*>(L.ty);
+    double* tz = const_cast<double*>(L.tz);
     int phase = 0;
+    unsigned long long st_evals = 0, st_amb = 0, st_iters = 0, st_swept = 0, st_kept = 0;   // thread 0 only
 
     for (;;) {
         __syncthreads();
@@ -397,13 +493,8 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
 
         const int cs = a.src_idx ? a.src_idx[p] : p;
         const int ct = a.tgt_idx ? a.tgt_idx[p] : p;
-        const long long s_beg = a.src_off[cs], t_beg = a.tgt_off[ct];
-        const int n_s_raw = (int)(a.src_off[cs + 1] - s_beg);
-        const int n_t_raw = (int)(a.tgt_off[ct + 1] - t_beg);
-
-        if (n_s_raw <= 0 || n_t_raw <= 0 || n_s_raw > a.cap_s || n_t_raw > a.cap_t ||
-            n_s_raw > a.sort_pad || n_t_raw > a.sort_pad) {
-            // sizes outside what the host provisioned (device-resident entry point only)
+        const int n_s = a.s.ds_n[cs], n_t = a.t.ds_n[ct];
+        if (n_s <= 0 || n_t <= 0 || n_s > a.cap_s || n_t > a.cap_t) {
             if (tid == 0) {
                 for (int k = 0; k < DIM * DIM; ++k) a.R_out[(size_t)p * DIM * DIM + k] = (k % (DIM + 1) == 0) ? 1.0 : 0.0;
                 for (int k = 0; k < DIM; ++k) a.t_out[(size_t)p * DIM + k] = 0.0;
@@ -414,91 +505,41 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
             }
             continue;
         }
+        const double* src_ds = a.s.ds + a.s.off[cs] * DIM;
+        const double* tgt_ds = a.t.ds + a.t.off[ct] * DIM;
+        const double* normals = a.t.nrm ? a.t.nrm + a.t.off[ct] * 2 : nullptr;
+        const double* box = a.t.box + (size_t)ct * 6;
+        L.n_s = n_s; L.n_t = n_t; L.n_tiles = (n_t + 31) / 32;
+        L.c0 = 0.5 * (box[0] + box[3]); L.c1 = 0.5 * (box[1] + box[4]); L.c2 = 0.5 * (box[2] + box[5]);
 
-        // ---- A: voxel-grid means (sort scratch aliases everything after the header)
-        unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + hdr);
-        unsigned int* sidx = reinterpret_cast<unsigned int*>(smem + hdr + (size_t)a.sort_pad * 8);
-        double lo[DIM], hi[DIM];
-        const int n_s = cta_voxel_means<DIM>(a.src + s_beg * DIM, n_s_raw, a.voxel, src_ds, keys, sidx,
-                                             a.sort_pad, sh, phase, lo, hi);
-        const int n_t = cta_voxel_means<DIM>(a.tgt + t_beg * DIM, n_t_raw, a.voxel, tgt_ds, keys, sidx,
-                                             a.sort_pad, sh, phase, lo, hi);
-        if (n_s < 0 || n_t < 0) {
-            if (tid == 0) {
-                for (int k = 0; k < DIM * DIM; ++k) a.R_out[(size_t)p * DIM * DIM + k] = (k % (DIM + 1) == 0) ? 1.0 : 0.0;
-                for (int k = 0; k < DIM; ++k) a.t_out[(size_t)p * DIM + k] = 0.0;
-                a.err_out[p] = INFINITY;
-                if (a.prev_out) a.prev_out[p] = INFINITY;
-                a.iters_out[p] = 0;
-                a.status_out[p] = ICPB200_BAD_VOXELS;
-            }
-            continue;
-        }
         if (tid == 0) {
-            sh.n_s = n_s; sh.n_t = n_t;
-            for (int k = 0; k < DIM; ++k) {
-                sh.lo_t[k] = lo[k]; sh.hi_t[k] = hi[k];
-                sh.center[k] = 0.5 * (lo[k] + hi[k]);
-            }
-            if (DIM == 2) { sh.lo_t[2] = sh.hi_t[2] = sh.center[2] = 0.0; }
             // icp.py:153-160
             const bool init = a.R_init != nullptr && a.t_init != nullptr;
             for (int k = 0; k < DIM * DIM; ++k)
                 sh.r_tot[k] = init ? a.R_init[(size_t)p * DIM * DIM + k] : ((k % (DIM + 1) == 0) ? 1.0 : 0.0);
             for (int k = 0; k < DIM; ++k) sh.t_tot[k] = init ? a.t_init[(size_t)p * DIM + k] : 0.0;
-            if (a.trace_counts) { a.trace_counts[0] = n_s; a.trace_counts[1] = n_t; }
+            sh.amb_n = 0;
+            sh.bcast_i[0] = 0;                     // todo counter
         }
-        __syncthreads();
-
-        // ---- B1: target fp64 into shared memory (tile-padded SoA)
-        double* tx = tgt64; double* ty = tgt64 + tstride; double* tz = tgt64 + 2 * (size_t)tstride;
-        for (int j = tid; j < n_t; j += kNT) {
-            const int jp = pad_index(j);
-            tx[jp] = tgt_ds[(size_t)j * DIM];
-            ty[jp] = tgt_ds[(size_t)j * DIM + 1];
-            if (DIM == 3) tz[jp] = tgt_ds[(size_t)j * DIM + 2];
-        }
-        if (a.trace_src) for (int i = tid; i < n_s * DIM; i += kNT) a.trace_src[i] = src_ds[i];
-        if (a.trace_tgt) for (int i = tid; i < n_t * DIM; i += kNT) a.trace_tgt[i] = tgt_ds[i];
-        __syncthreads();
-
-        // ---- C: normals (2-D point-to-line only, icp.py:162-167)
-        const bool p2l = (a.method == ICPB200_POINT_TO_LINE) && DIM == 2;
-        if (p2l) {
-            int* cell_start = reinterpret_cast<int*>(scratch);
-            unsigned short* items = reinterpret_cast<unsigned short*>(scratch + sizeof(int) * (kGridCells + 1));
-            cta_normals_2d(tx, ty, n_t, a.normal_k, normals, cell_start, items, sh);
-            if (a.trace_nrm) for (int i = tid; i < n_t * 2; i += kNT) a.trace_nrm[i] = normals[i];
-        }
-
-        // ---- B2: loop state
-        Loop<DIM> L;
-        L.tx = tx; L.ty = ty; L.tz = tz;
-        {
-            unsigned char* q = scratch;
-            L.t32 = reinterpret_cast<float4*>(q);  q += sizeof(float) * (DIM == 2 ? 2 : 4) * (size_t)a.cap_t;
-            L.cx = reinterpret_cast<double*>(q);   q += sizeof(double) * (size_t)a.cap_s;
-            L.cy = reinterpret_cast<double*>(q);   q += sizeof(double) * (size_t)a.cap_s;
-            L.cz = reinterpret_cast<double*>(q);   if (DIM == 3) q += sizeof(double) * (size_t)a.cap_s;
-            L.match = reinterpret_cast<int*>(q);   q += sizeof(int) * (size_t)a.cap_s;
-            L.amb = reinterpret_cast<int*>(q);
-        }
-        L.n_s = n_s; L.n_t = n_t; L.n_tiles = (n_t + 31) / 32;
-        L.c0 = sh.center[0]; L.c1 = sh.center[1]; L.c2 = sh.center[2];
+        // ---- stage the target: fp64 (tile-padded SoA) and recentred fp32
         {
             float* f = reinterpret_cast<float*>(L.t32);
-            const int per = DIM == 2 ? 2 : 4;
+            constexpr int per = DIM == 2 ? 2 : 4;
             double ext[DIM];
 #pragma unroll
             for (int k = 0; k < DIM; ++k) ext[k] = 0.0;
             for (int j = tid; j < L.n_tiles * 32; j += kNT) {
                 if (j < n_t) {
                     const int jp = pad_index(j);
-                    const double v0 = tx[jp] - L.c0, v1 = ty[jp] - L.c1;
+                    const double x = tgt_ds[(size_t)j * DIM], y = tgt_ds[(size_t)j * DIM + 1];
+                    tx[jp] = x; ty[jp] = y;
+                    const double v0 = x - L.c0, v1 = y - L.c1;
                     f[j * per] = (float)v0; f[j * per + 1] = (float)v1;
                     ext[0] = fmax(ext[0], fabs(v0)); ext[1] = fmax(ext[1], fabs(v1));
                     if (DIM == 3) {
-                        const double v2 = tz[jp] - L.c2;
+                        const double z = tgt_ds[(size_t)j * DIM + 2];
+                        tz[jp] = z;
+                        const double v2 = z - L.c2;
                         f[j * per + 2] = (float)v2; f[j * per + 3] = 0.f;
                         ext[DIM - 1] = fmax(ext[DIM - 1], fabs(v2));
                     }
@@ -510,7 +551,7 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
             double neg[DIM];
 #pragma unroll
             for (int k = 0; k < DIM; ++k) neg[k] = -ext[k];
-            block_reduce<DIM, MinOp>(neg, sh, phase);
+            block_reduce<DIM, MinOp>(neg, sh, phase);       // includes the barrier that publishes sh.r_tot
             double s = 0.0;
 #pragma unroll
             for (int k = 0; k < DIM; ++k) s += -neg[k];
@@ -531,26 +572,47 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
                     L.cy[i] = x * r[3] + y * r[4] + z * r[5] + t[1];
                     L.cz[i] = x * r[6] + y * r[7] + z * r[8] + t[2];
                 }
+                L.d2lb[i] = -1.f;                  // no decision yet: forces a sweep
+                L.moved[i] = 0.f;
+                L.match[i] = 0;
             }
         }
-        if (tid == 0) sh.amb_n = 0;
         __syncthreads();
 
-        // ---- D: iterate (icp.py:175-220)
+        // ---- iterate (icp.py:175-220)
+        const bool p2l = (a.method == ICPB200_POINT_TO_LINE) && DIM == 2 && normals != nullptr;
         const bool gated = a.max_corr >= 0.0;
         const double gate2 = a.max_corr * a.max_corr;                 // icp.py:169
         const int min_inl = max(3, n_s / 10);                         // icp.py:186
         double prev = INFINITY, err = INFINITY;
         int iters = 0, status = ICPB200_MAX_ITER;
         for (int it = 0; it < a.max_iter; ++it) {
-            // correspondences (icp.py:179)
-            nn_dispatch<DIM>(L, sh);
+            // ---- correspondences (icp.py:179): carry over where the movement bound allows
+            for (int i = tid; i < n_s; i += kNT) {
+                bool keep = false;
+                const float lb = L.d2lb[i];
+                if (lb >= 0.f) {
+                    const double d1 = sqrt(dist2_64<DIM>(L, L.cx[i], L.cy[i], DIM == 3 ? L.cz[i] : 0.0, L.match[i]));
+                    keep = d1 * (1.0 + 1e-9) + 1e-12 < (double)lb - (double)L.moved[i];
+                }
+                if (!keep) L.todo[atomicAdd(&sh.bcast_i[0], 1)] = (unsigned short)i;
+            }
             __syncthreads();
-            resolve_ambiguous<DIM>(L, sh);
+            const int n_todo = sh.bcast_i[0];
+            if (n_todo > 0) {
+                nn_dispatch<DIM>(L, sh, n_todo);
+                __syncthreads();
+                if (sh.amb_n > 0) resolve_ambiguous<DIM>(L, sh);
+            }
+            if (tid == 0) {
+                const int n_chunks = (n_todo + 31) >> 5;
+                st_evals += (unsigned long long)n_chunks * 32ull * (unsigned long long)L.n_tiles * 32ull;
+                st_swept += n_todo; st_kept += n_s - n_todo; st_iters += 1;
+            }
             __syncthreads();
-            if (tid == 0) sh.amb_n = 0;
-            if (a.trace_match && it < a.trace_iters)
-                for (int i = tid; i < n_s; i += kNT) a.trace_match[(size_t)it * n_s_raw + i] = L.match[i];
+            if (tid == 0) { st_amb += sh.amb_n; sh.amb_n = 0; sh.bcast_i[0] = 0; }
+            if (a.trace_match && p == 0 && it < a.trace_iters)
+                for (int i = tid; i < n_s; i += kNT) a.trace_match[(size_t)it * a.trace_stride + i] = L.match[i];
 
             double rr[9], tt[3];
             if (p2l) {
@@ -579,8 +641,8 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
                     const double atb[3] = {acc[6], acc[7], acc[8]};
                     double x[3];
                     if (solve3_lu(ata, atb, x) == 0) {
-                        const double ct = cos(x[0]), st = sin(x[0]);          // icp.py:110-114
-                        sh.r[0] = ct; sh.r[1] = -st; sh.r[2] = st; sh.r[3] = ct;
+                        const double ct_ = cos(x[0]), st_ = sin(x[0]);        // icp.py:110-114
+                        sh.r[0] = ct_; sh.r[1] = -st_; sh.r[2] = st_; sh.r[3] = ct_;
                         sh.t[0] = x[1]; sh.t[1] = x[2];
                     } else {                                                  // icp.py:107-108
                         sh.r[0] = 1.0; sh.r[1] = 0.0; sh.r[2] = 0.0; sh.r[3] = 1.0;
@@ -662,18 +724,22 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
             for (int i = tid; i < n_s; i += kNT) {
                 const int jp = pad_index(L.match[i]);
                 const double x = L.cx[i], y = L.cy[i];
-                double nx_, ny_, nz_ = 0.0;
+                double nx_, ny_, nz_ = 0.0, mv;
                 if (DIM == 2) {
                     nx_ = x * rr[0] + y * rr[1] + tt[0];
                     ny_ = x * rr[2] + y * rr[3] + tt[1];
+                    mv = (nx_ - x) * (nx_ - x) + (ny_ - y) * (ny_ - y);
                 } else {
                     const double z = L.cz[i];
                     nx_ = x * rr[0] + y * rr[1] + z * rr[2] + tt[0];
                     ny_ = x * rr[3] + y * rr[4] + z * rr[5] + tt[1];
                     nz_ = x * rr[6] + y * rr[7] + z * rr[8] + tt[2];
                     L.cz[i] = nz_;
+                    mv = (nx_ - x) * (nx_ - x) + (ny_ - y) * (ny_ - y) + (nz_ - z) * (nz_ - z);
                 }
                 L.cx[i] = nx_; L.cy[i] = ny_;
+                // movement since the last decision, rounded up
+                L.moved[i] = __fadd_ru(L.moved[i], __double2float_ru(sqrt(mv) * (1.0 + 1e-9)));
                 const double dx = tx[jp] - nx_, dy = ty[jp] - ny_;
                 double d = dx * dx + dy * dy;
                 if (DIM == 3) { const double dz = tz[jp] - nz_; d += dz * dz; }
@@ -696,24 +762,44 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
             a.status_out[p] = status;
         }
     }
+    if (tid == 0 && a.stats) {
+        atomicAdd(&a.stats[0], st_evals);
+        atomicAdd(&a.stats[1], st_amb);
+        atomicAdd(&a.stats[2], st_iters);
+        atomicAdd(&a.stats[3], st_swept);
+        atomicAdd(&a.stats[4], st_kept);
+    }
 }
 
-// ---- standalone voxel downsample (utilities/icp.py:117-129) ------------------
-template <int DIM>
-__global__ void __launch_bounds__(kNT) voxel_kernel(const double* __restrict__ pts, int n, double voxel,
-                                                    double* __restrict__ out, int* n_out, int sort_pad) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    CtaShared& sh = *reinterpret_cast<CtaShared*>(smem);
-    const size_t hdr = (sizeof(CtaShared) + 15) & ~size_t(15);
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + hdr);
-    unsigned int* sidx = reinterpret_cast<unsigned int*>(smem + hdr + (size_t)sort_pad * 8);
-    int phase = 0;
-    double lo[DIM], hi[DIM];
-    const int m = cta_voxel_means<DIM>(pts, n, voxel, out, keys, sidx, sort_pad, sh, phase, lo, hi);
-    if (threadIdx.x == 0) *n_out = m;
+// ---- host-side launchers -------------------------------------------------------------
+int launch_mark_used(const IcpArgs& a, bool p2l, cudaStream_t stream) {
+    mark_used_kernel<<<(a.n_pairs + 255) / 256, 256, 0, stream>>>(a.n_pairs, a.src_idx, a.tgt_idx, a.s.used, a.t.used,
+                                                                  p2l ? a.t.is_tgt : nullptr);
+    ICPB_LAUNCH_CHECK();
+    return ICPB200_OK;
 }
 
-// ---- host-side launchers -------------------------------------------------------
+int launch_voxel_clouds(const CloudSet& cs, int dim, double voxel, int sort_pad, cudaStream_t stream) {
+    const size_t smem = icp_voxel_smem_bytes(sort_pad);
+    if (dim == 2) {
+        ICPB_CUDA(cudaFuncSetAttribute(voxel_clouds_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        voxel_clouds_kernel<2><<<cs.n_clouds, kNT, smem, stream>>>(cs, voxel, sort_pad);
+    } else {
+        ICPB_CUDA(cudaFuncSetAttribute(voxel_clouds_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        voxel_clouds_kernel<3><<<cs.n_clouds, kNT, smem, stream>>>(cs, voxel, sort_pad);
+    }
+    ICPB_LAUNCH_CHECK();
+    return ICPB200_OK;
+}
+
+int launch_normals(const CloudSet& cs, int cap_t, int normal_k, cudaStream_t stream) {
+    const size_t smem = icp_normals_smem_bytes(cap_t);
+    ICPB_CUDA(cudaFuncSetAttribute(normals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    normals_kernel<<<cs.n_clouds, kNT, smem, stream>>>(cs, normal_k, cap_t);
+    ICPB_LAUNCH_CHECK();
+    return ICPB200_OK;
+}
+
 int launch_icp_pairs(const IcpArgs& a, int dim, int n_ctas, size_t smem, cudaStream_t stream) {
     if (dim == 2) {
         ICPB_CUDA(cudaFuncSetAttribute(icp_pairs_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -738,20 +824,6 @@ int icp_max_ctas_per_sm(int dim, size_t smem) {
     }
     if (e != cudaSuccess || n < 1) n = 1;
     return n;
-}
-
-int launch_voxel(const double* d_pts, int n, int dim, double voxel, double* d_out, int* d_n_out,
-                 int sort_pad, cudaStream_t stream) {
-    const size_t smem = ((sizeof(CtaShared) + 15) & ~size_t(15)) + smem_sort_bytes(sort_pad);
-    if (dim == 2) {
-        ICPB_CUDA(cudaFuncSetAttribute(voxel_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        voxel_kernel<2><<<1, kNT, smem, stream>>>(d_pts, n, voxel, d_out, d_n_out, sort_pad);
-    } else {
-        ICPB_CUDA(cudaFuncSetAttribute(voxel_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        voxel_kernel<3><<<1, kNT, smem, stream>>>(d_pts, n, voxel, d_out, d_n_out, sort_pad);
-    }
-    ICPB_LAUNCH_CHECK();
-    return ICPB200_OK;
 }
 
 }  // namespace icpb

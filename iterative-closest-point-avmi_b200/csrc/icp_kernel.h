@@ -1,4 +1,10 @@
-// Host <-> kernel argument block and launchers for the per-pair ICP kernel.
+// Host <-> kernel argument blocks and launchers for the ICP kernels.
+//
+// Three kernels (SURVEY.md section 2 kernel inventory K1/K2/K3):
+//   K1 voxel_clouds_kernel   one CTA per referenced cloud: voxel-grid mean
+//   K2 normals_kernel        one CTA per cloud used as a point-to-line target
+//   K3 icp_pairs_kernel      persistent, one CTA per (source, target) pair:
+//                            the whole iteration loop on-chip
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -6,15 +12,26 @@
 
 namespace icpb {
 
+// One set of clouds on the device plus its preprocessed (downsampled) form.
+// Cloud c owns raw rows off[c] .. off[c+1]) of `raw`; its downsampled rows live
+// at the same offset in `ds` (count ds_n[c] <= raw count), its normals at the
+// same offset in `nrm` (2 doubles per row), its raw bounding box in box[c*6..].
+struct CloudSet {
+    const double* raw;
+    const long long* off;
+    int n_clouds;
+    double* ds;
+    int* ds_n;              // -1: voxel index range does not fit (cloud unusable)
+    double* box;            // lo[3], hi[3] per cloud
+    double* nrm;            // may be nullptr when no cloud of the set is a p2l target
+    unsigned char* used;    // per cloud: 1 if referenced by any pair (nullptr: all are)
+    unsigned char* is_tgt;  // per cloud: 1 if it is the target of a point-to-line pair
+};
+
 struct IcpArgs {
     int n_pairs;
-    // clouds: pair p uses cloud (src_idx ? src_idx[p] : p) of the source set,
-    // rows src_off[c] .. src_off[c+1]) of `src`; likewise for the target set
-    const double* src;
-    const long long* src_off;
-    const int* src_idx;
-    const double* tgt;
-    const long long* tgt_off;
+    CloudSet s, t;             // may describe the same set
+    const int* src_idx;        // per pair, or nullptr (pair p -> cloud p)
     const int* tgt_idx;
     const double* R_init;      // n_pairs * dim * dim or nullptr
     const double* t_init;      // n_pairs * dim or nullptr
@@ -30,28 +47,26 @@ struct IcpArgs {
     double* prev_out;          // may be nullptr
     int* iters_out;
     int* status_out;
-    // per-CTA global workspace: src_ds | tgt_ds | normals
-    double* ws;
-    size_t ws_stride;          // doubles per CTA
-    int cap_s, cap_t;          // multiples of 32, >= largest raw cloud
+    int cap_s, cap_t;          // multiples of 32, >= largest raw cloud of each set
     int sort_pad;              // power of two >= largest raw cloud, >= 256
     unsigned int* queue;       // zeroed before launch
-    // optional trace outputs (single-pair debug entry point)
-    double* trace_src;
-    double* trace_tgt;
-    double* trace_nrm;
-    int* trace_match;
+    unsigned long long* stats; // [0] fp32 sweep pair evaluations executed, [1] points re-decided by the
+                               // full fp64 scan, [2] iterations, [3] source points swept, [4] source points
+                               // whose correspondence was carried over by the movement bound; may be nullptr
+    int* trace_match;          // optional: correspondences of the first trace_iters iterations (pair 0)
     int trace_iters;
-    int* trace_counts;
+    int trace_stride;
 };
 
-size_t icp_smem_bytes(int dim, int cap_s, int cap_t, int sort_pad);
-inline size_t icp_ws_doubles(int dim, int cap_s, int cap_t) {
-    return (size_t)dim * cap_s + (size_t)dim * cap_t + 2 * (size_t)cap_t;
-}
+size_t icp_pair_smem_bytes(int dim, int cap_s, int cap_t);
+size_t icp_voxel_smem_bytes(int sort_pad);
+size_t icp_normals_smem_bytes(int cap_t);
 int icp_max_ctas_per_sm(int dim, size_t smem);
+
+// used[c] = 1 for every referenced cloud, is_tgt[c] = 1 for p2l targets (device-side, from the idx arrays)
+int launch_mark_used(const IcpArgs& a, bool p2l, cudaStream_t stream);
+int launch_voxel_clouds(const CloudSet& cs, int dim, double voxel, int sort_pad, cudaStream_t stream);
+int launch_normals(const CloudSet& cs, int cap_t, int normal_k, cudaStream_t stream);
 int launch_icp_pairs(const IcpArgs& a, int dim, int n_ctas, size_t smem, cudaStream_t stream);
-int launch_voxel(const double* d_pts, int n, int dim, double voxel, double* d_out, int* d_n_out,
-                 int sort_pad, cudaStream_t stream);
 
 }  // namespace icpb

@@ -33,9 +33,10 @@ namespace icpb {
 
 constexpr int TS = kOccTile;                 // tile edge in cells
 constexpr int TCELLS = TS * TS;
-constexpr int kOccNT = 256;
+constexpr int kOccNT = 512;
 constexpr unsigned kHitUnit = 1u << 20;      // counter word: hits << 20 | misses
 constexpr unsigned kMissMask = kHitUnit - 1u;
+constexpr size_t kOccSmem = sizeof(float) * TCELLS + 2 * sizeof(unsigned) * TCELLS + sizeof(unsigned short) * kOccMaxChunkScans;
 
 struct Run {                                  // 16 bytes
     unsigned int ray;                         // global ray index
@@ -280,12 +281,58 @@ __device__ __forceinline__ float chain(float x, unsigned m, unsigned k, double l
     return fminf(fmaxf(x, lo), hi);           // mapping.py:141
 }
 
+// Work item = one "slot" of a run: slot k of a miss run covers its cells
+// [8k, 8k+8); a hit is slot 0 of a zero-length run.  A run has TS/8 slots, most
+// of them empty for short runs; consecutive lanes share a run, so its 16-byte
+// record is one broadcast load.
+constexpr int kSub = 8;
+constexpr int kSlots = TS / kSub;
+
+struct Slot {
+    int idx;            // first local cell index
+    int ncell;          // cells in this slot (0: nothing to do)
+    int maj_stride, min_stride;
+    RunWalker wk;
+    bool hit;
+};
+
+__device__ __forceinline__ Slot load_slot(const ApplyArgs& a, unsigned item, int2 o, int tx0, int ty0) {
+    Slot s;
+    s.ncell = 0; s.hit = false; s.idx = 0; s.maj_stride = 0; s.min_stride = 0;
+    const int4 raw = __ldg(reinterpret_cast<const int4*>(a.runs) + item / kSlots);
+    const int sub = (int)(item % kSlots);
+    if (raw.w == 0) {                                      // hit: n0 is the local cell
+        if (sub == 0) { s.hit = true; s.ncell = 1; s.idx = raw.y; }
+        return s;
+    }
+    const int first = sub * kSub;
+    if (first >= raw.w) return s;
+    s.ncell = min(kSub, raw.w - first);
+    const int2 h = __ldg(&a.ray_cell[(unsigned)raw.x]);
+    const RayGeom g = make_ray(o.x, o.y, h.x, h.y);
+    const int n = raw.y + first;
+    int j = raw.z;
+    if (sub != 0) {
+        // minor_steps(g, n); 32-bit division whenever the numerator fits
+        const unsigned long long num = 2ull * (unsigned)n * (unsigned)g.dmin + (unsigned)g.dmaj - 1u;
+        j = (num >> 32) == 0 ? (int)((unsigned)num / (2u * (unsigned)g.dmaj)) : (int)(num / (2ull * (unsigned)g.dmaj));
+    }
+    int x, y;
+    cell_at(g, n, j, x, y);
+    s.idx = (y - ty0) * TS + (x - tx0);
+    s.maj_stride = g.xmajor ? g.smaj : g.smaj * TS;
+    s.min_stride = g.xmajor ? g.smin * TS : g.smin;
+    s.wk.start(g, n, j);
+    return s;
+}
+
 __global__ void __launch_bounds__(kOccNT) occ_tile_apply(const ApplyArgs a) {
-    __shared__ float tile[TCELLS];
-    __shared__ unsigned cnt[TCELLS];
-    __shared__ unsigned short touched[TCELLS];
-    __shared__ unsigned short scan_list[kOccMaxChunkScans];
-    __shared__ int n_touched[2];
+    extern __shared__ __align__(16) unsigned char occ_smem[];
+    float* tile = reinterpret_cast<float*>(occ_smem);
+    // double-buffered counters: count scan s+1 while applying scan s
+    unsigned (*cnt)[TCELLS] = reinterpret_cast<unsigned (*)[TCELLS]>(occ_smem + sizeof(float) * TCELLS);
+    unsigned short* scan_list = reinterpret_cast<unsigned short*>(occ_smem + sizeof(float) * TCELLS + 2 * sizeof(unsigned) * TCELLS);
+    __shared__ int wcount[kOccNT / 32];
     __shared__ int n_list;
     __shared__ int cur_tile;
     const int tid = threadIdx.x;
@@ -296,7 +343,7 @@ __global__ void __launch_bounds__(kOccNT) occ_tile_apply(const ApplyArgs a) {
         if (tid == 0) {
             const unsigned q = atomicAdd(a.queue, 1u);
             cur_tile = q < (unsigned)n_active ? a.order[q] : -1;
-            n_touched[0] = 0; n_touched[1] = 0; n_list = 0;
+            n_list = 0;
         }
         __syncthreads();
         const int t = cur_tile;
@@ -305,7 +352,8 @@ __global__ void __launch_bounds__(kOccNT) occ_tile_apply(const ApplyArgs a) {
         for (int c = tid; c < TCELLS; c += kOccNT) {
             const int x = tx0 + (c & (TS - 1)), y = ty0 + (c / TS);
             tile[c] = (x < a.nx && y < a.ny) ? a.grid[(size_t)y * a.nx + x] : 0.f;
-            cnt[c] = 0u;
+            cnt[0][c] = 0u;
+            cnt[1][c] = 0u;
         }
         // scans that have runs in this tile, ascending
         const unsigned* off = a.offsets + (size_t)t * a.chunk_scans;
@@ -313,7 +361,6 @@ __global__ void __launch_bounds__(kOccNT) occ_tile_apply(const ApplyArgs a) {
             const int s = s0 + tid;
             const bool has = s < a.chunk_scans && off[s + 1] > off[s];
             const unsigned bal = __ballot_sync(0xffffffffu, has);
-            __shared__ int wcount[kOccNT / 32];
             if ((tid & 31) == 0) wcount[tid >> 5] = __popc(bal);
             __syncthreads();
             int base = n_list;
@@ -324,52 +371,62 @@ __global__ void __launch_bounds__(kOccNT) occ_tile_apply(const ApplyArgs a) {
             __syncthreads();
         }
         const int n_scans_here = n_list;
-        int par = 0;
-        for (int li = 0; li < n_scans_here; ++li) {
+
+        auto count_scan = [&](int li) {
             const int s = scan_list[li];
-            const unsigned beg = off[s], end = off[s + 1];
+            unsigned* c = cnt[li & 1];
+            const unsigned beg = off[s] * kSlots, end = off[s + 1] * kSlots;
             const int2 o = a.origin_cell[s];
-            // ---- count phase
-            for (unsigned e0 = beg; e0 < end; e0 += kOccNT) {
-                const unsigned e = e0 + tid;
-                if (e < end) {
-                    const int4 raw = reinterpret_cast<const int4*>(a.runs)[e];
-                    if (raw.w == 0) {                                   // hit
-                        const unsigned old = atomicAdd(&cnt[raw.y], kHitUnit);
-                        if ((old >> 20) == 4095u) *a.error_flag = 1;
-                        if (old == 0u) touched[atomicAdd(&n_touched[par], 1)] = (unsigned short)raw.y;
-                    } else {
-                        const int2 h = a.ray_cell[(unsigned)raw.x];
-                        const RayGeom g = make_ray(o.x, o.y, h.x, h.y);
-                        int x, y;
-                        cell_at(g, raw.y, raw.z, x, y);
-                        int idx = (y - ty0) * TS + (x - tx0);
-                        const int maj_stride = g.xmajor ? g.smaj : g.smaj * TS;
-                        const int min_stride = g.xmajor ? g.smin * TS : g.smin;
-                        RunWalker wk;
-                        wk.start(g, raw.y, raw.z);
-                        for (int c = 0; c < raw.w; ++c) {
-                            const unsigned old = atomicAdd(&cnt[idx], 1u);
-                            if (old == 0u) touched[atomicAdd(&n_touched[par], 1)] = (unsigned short)idx;
-                            idx += maj_stride + (wk.step() ? min_stride : 0);
-                        }
+            for (unsigned item = beg + tid; item < end; item += kOccNT) {
+                Slot sl = load_slot(a, item, o, tx0, ty0);
+                if (sl.hit) {
+                    const unsigned old = atomicAdd(&c[sl.idx], kHitUnit);
+                    if ((old >> 20) == 4095u) *a.error_flag = 1;
+                } else {
+                    int idx = sl.idx;
+                    for (int k = 0; k < sl.ncell; ++k) {
+                        atomicAdd(&c[idx], 1u);                       // result unused: fire and forget
+                        idx += sl.maj_stride + (sl.wk.step() ? sl.min_stride : 0);
                     }
                 }
             }
-            __syncthreads();
-            // ---- apply phase: touched cells only
-            const int nt = n_touched[par];
+        };
+        auto apply_scan = [&](int li) {
+            const int s = scan_list[li];
+            unsigned* c = cnt[li & 1];
+            const unsigned beg = off[s] * kSlots, end = off[s + 1] * kSlots;
+            const int2 o = a.origin_cell[s];
             const bool virgin_fix = s >= a.virgin_after;
-            for (int i = tid; i < nt; i += kOccNT) {
-                const int idx = touched[i];
-                const unsigned c = cnt[idx];
-                cnt[idx] = 0u;
-                float x = tile[idx];
-                if (virgin_fix && x == 0.0f) x = a.clamp0;
-                tile[idx] = chain(x, c >> 20, c & kMissMask, a.l_hit, a.l_miss, a.lo, a.hi);
+            for (unsigned item = beg + tid; item < end; item += kOccNT) {
+                Slot sl = load_slot(a, item, o, tx0, ty0);
+                if (sl.ncell == 0) continue;
+                int idxs[kSub];
+                unsigned got[kSub];
+                int idx = sl.idx;
+#pragma unroll
+                for (int k = 0; k < kSub; ++k) {
+                    idxs[k] = idx;
+                    if (k < sl.ncell && !sl.hit) idx += sl.maj_stride + (sl.wk.step() ? sl.min_stride : 0);
+                }
+                // the thread whose exchange returns a non-zero count owns the cell for this scan
+#pragma unroll
+                for (int k = 0; k < kSub; ++k) got[k] = k < sl.ncell ? atomicExch(&c[idxs[k]], 0u) : 0u;
+#pragma unroll
+                for (int k = 0; k < kSub; ++k) {
+                    if (got[k]) {
+                        float x = tile[idxs[k]];
+                        if (virgin_fix && x == 0.0f) x = a.clamp0;
+                        tile[idxs[k]] = chain(x, got[k] >> 20, got[k] & kMissMask, a.l_hit, a.l_miss, a.lo, a.hi);
+                    }
+                }
             }
-            if (tid == 0) n_touched[par ^ 1] = 0;
-            par ^= 1;
+        };
+
+        if (n_scans_here > 0) count_scan(0);
+        __syncthreads();
+        for (int li = 0; li < n_scans_here; ++li) {
+            if (li + 1 < n_scans_here) count_scan(li + 1);    // other counter buffer
+            apply_scan(li);
             __syncthreads();
         }
         for (int c = tid; c < TCELLS; c += kOccNT) {
@@ -500,7 +557,8 @@ int occ_update_device(OccGrid& g, int n_scans, const double* d_origins, const do
             }
         }
         ap.error_flag = reinterpret_cast<int*>(d_small + 3);
-        occ_tile_apply<<<g.apply_ctas, kOccNT, 0, st>>>(ap);
+        ICPB_CUDA(cudaFuncSetAttribute(occ_tile_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOccSmem));
+        occ_tile_apply<<<g.apply_ctas, kOccNT, kOccSmem, st>>>(ap);
         ICPB_LAUNCH_CHECK();
         g.seen_nonempty_scan = true;
     }
@@ -527,7 +585,8 @@ int occ_update_device(OccGrid& g, int n_scans, const double* d_origins, const do
 
 int occ_apply_ctas(int sm_count) {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, occ_tile_apply, kOccNT, 0) != cudaSuccess || per_sm < 1)
+    cudaFuncSetAttribute(occ_tile_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOccSmem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, occ_tile_apply, kOccNT, kOccSmem) != cudaSuccess || per_sm < 1)
         per_sm = 1;
     return sm_count * per_sm;
 }

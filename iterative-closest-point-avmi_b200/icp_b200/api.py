@@ -120,6 +120,15 @@ def icp_trace(source, target, error_threshold, max_iterations, voxel_size, R_ini
                 matches=matches[:trace_iters, :ns].copy())
 
 
+def icp_last_stats():
+    """Work counters + per-kernel device times of the most recent registration call."""
+    st = np.zeros(8, dtype=np.int64)
+    check(_lib.load().icpb200_icp_last_stats(_ptr(st, c_int64_p)), "icpb200_icp_last_stats")
+    return dict(sweep_pair_evals=int(st[0]), fp64_rescans=int(st[1]), iterations=int(st[2]), points_swept=int(st[3]),
+                points_carried=int(st[4]), voxel_kernel_ns=int(st[5]), normals_kernel_ns=int(st[6]),
+                pair_kernel_ns=int(st[7]))
+
+
 def voxel_downsample(points, voxel_size):
     pts = _f64(points)
     out = np.empty_like(pts)

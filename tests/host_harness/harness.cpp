@@ -2,6 +2,7 @@
 // The same headers are compiled into the CUDA kernels; here g++ compiles them
 // as plain C++ so tests/test_bres_host.py and tests/test_linalg_host.py can
 // check them against the oracle and numpy without a GPU.
+#include <math.h>
 #include <stdint.h>
 #include <vector>
 
@@ -38,6 +39,34 @@ int64_t harness_ray_cells(int ts, int ox, int oy, int hx, int hy, int nx, int ny
     else if (ts == 4) for_each_tile_run<4>(g, nx, ny, tiles_x, emit);
     else return -1;
     return n;
+}
+
+
+// Per-tile load statistics of a batch of scans (mirrors occ_bin): for each
+// tile the number of runs, traversed cells and distinct scans touching it.
+// cells_out / runs_out / scans_out have tiles_x * tiles_y entries.
+void harness_tile_stats(int n_scans, const double* origins, const double* hits, const int64_t* hit_off,
+                        double min_x, double min_y, double res, int nx, int ny,
+                        int64_t* cells_out, int64_t* runs_out, int64_t* scans_out, int64_t* maxrun_out) {
+    const int tiles_x = (nx + 63) / 64, tiles_y = (ny + 63) / 64;
+    std::vector<int> last(tiles_x * tiles_y, -1);
+    std::vector<int64_t> cur(tiles_x * tiles_y, 0);
+    for (int s = 0; s < n_scans; ++s) {
+        const int ox = sat_cell(floor((origins[2 * s] - min_x) / res));
+        const int oy = sat_cell(floor((origins[2 * s + 1] - min_y) / res));
+        for (int64_t r = hit_off[s]; r < hit_off[s + 1]; ++r) {
+            const int hx = sat_cell(floor((hits[2 * r] - min_x) / res));
+            const int hy = sat_cell(floor((hits[2 * r + 1] - min_y) / res));
+            const RayGeom g = make_ray(ox, oy, hx, hy);
+            for_each_tile_run<64>(g, nx, ny, tiles_x, [&](const TileRun& t) {
+                cells_out[t.tile] += t.len;
+                runs_out[t.tile] += 1;
+                if (last[t.tile] != s) { last[t.tile] = s; scans_out[t.tile] += 1; cur[t.tile] = 0; }
+                cur[t.tile] += 1;
+                if (cur[t.tile] > maxrun_out[t.tile]) maxrun_out[t.tile] = cur[t.tile];
+            });
+        }
+    }
 }
 
 int harness_minor_steps(int ox, int oy, int hx, int hy, int n) {
