@@ -202,6 +202,12 @@ void *icpb200_grid_device_ptr(void *grid);
  * updates, stats[3] = tile runs.  Used by bench.py for the roofline bytes. */
 int icpb200_grid_last_stats(void *grid, int64_t *stats4);
 
+/* Profiling aid: the first call switches per-tile timing on; after the next
+ * update, a call with a buffer of 4*cap_tiles int64 receives, per tile index,
+ * {tile, scans replayed, runs, SM cycles spent on the tile} of the last scan
+ * chunk (zeros for idle tiles) and returns the number of tiles written. */
+int icpb200_grid_tile_profile(void *grid, int64_t *out, int64_t cap_tiles);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,6 +3,7 @@
 // compute happens on the host and there is no CPU fallback: every compute
 // entry point fails with ICPB200_ERR_CUDA when no CUDA device is usable.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -198,7 +199,7 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
     if ((rc = launch_voxel_clouds(a.s, k.dim, k.voxel_size, a.sort_pad, st))) return rc;
     if (!same_set && (rc = launch_voxel_clouds(a.t, k.dim, k.voxel_size, a.sort_pad, st))) return rc;
     ICPB_CUDA(cudaEventRecord(c.ev[1], st));
-    if (p2l && (rc = launch_normals(a.t, a.cap_t, k.normal_k, st))) return rc;
+    if (p2l && (rc = launch_normals(a.t, a.cap_t, k.normal_k, k.voxel_size, st))) return rc;
     ICPB_CUDA(cudaEventRecord(c.ev[2], st));
     const int per_sm = icp_max_ctas_per_sm(k.dim, smem);
     const int n_ctas = std::min(n_pairs, c.sm_count * per_sm);
@@ -522,7 +523,7 @@ int icpb200_voxel_downsample(const double* pts, int64_t n, int dim, double voxel
 
 void OccGrid::release_all() {
     DevBuf* bufs[] = {&grid, &origins, &hits, &hit_off, &origin_cell, &ray_cell, &ray_scan,
-                      &counts, &offsets, &sums, &runs, &order, &small};
+                      &counts, &offsets, &sums, &runs, &order, &small, &tile_prof};
     for (DevBuf* b : bufs) b->release();
 }
 
@@ -543,6 +544,7 @@ void* icpb200_grid_create(int nx, int ny, double min_x, double min_y, double res
     g->l_hit = l_hit; g->l_miss = l_miss; g->lo_min = lo_min; g->lo_max = lo_max;
     g->zero_outside_clamp = ((float)lo_min > 0.f) || ((float)lo_max < 0.f);
     g->apply_ctas = occ_apply_ctas(g_ctx.sm_count);
+    if (const char* e = getenv("ICPB200_OCC_SPLIT")) g->split = std::max(1, std::min(8, atoi(e)));
     if (g->grid.reserve(sizeof(float) * (size_t)nx * ny) ||
         cudaMemsetAsync(g->grid.p, 0, sizeof(float) * (size_t)nx * ny, g_ctx.stream) != cudaSuccess ||
         cudaStreamSynchronize(g_ctx.stream) != cudaSuccess) {
@@ -643,6 +645,19 @@ int icpb200_grid_reset(void* grid) {
 
 void* icpb200_grid_device_ptr(void* grid) {
     return grid ? static_cast<OccGrid*>(grid)->grid.p : nullptr;
+}
+
+int icpb200_grid_tile_profile(void* grid, int64_t* out, int64_t cap_tiles) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!grid) { set_error("icpb200_grid_tile_profile: null pointer"); return ICPB200_ERR_ARG; }
+    OccGrid* g = static_cast<OccGrid*>(grid);
+    g->profile_tiles = true;                       // takes effect from the next update
+    if (!out || cap_tiles <= 0 || !g->tile_prof.p) return 0;
+    int rc = init_locked(-1);
+    if (rc) return rc;
+    const int64_t n = std::min<int64_t>(cap_tiles, (int64_t)g->tiles_x * g->tiles_y);
+    ICPB_CUDA(cudaMemcpy(out, g->tile_prof.p, sizeof(int64_t) * 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    return (int)n;
 }
 
 int icpb200_grid_last_stats(void* grid, int64_t* stats4) {

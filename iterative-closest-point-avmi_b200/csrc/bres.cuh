@@ -29,10 +29,11 @@
 
 namespace icpb {
 
-// Cell coordinates are saturated to +-2^29 so every product below fits int64
-// and every sum of two coordinates fits int32.  A hit 2^29 cells away from the
-// grid is ~26,000 km at 5 cm; the reference's own int cast is undefined there.
-constexpr int32_t kCellSat = 1 << 29;
+// Cell coordinates are saturated to +-2^27 so every product below fits int64,
+// every sum of two coordinates fits int32 and the walker's error term
+// (|d| <= 2*dmaj + 2*dmin) fits int32.  A hit 2^27 cells away from the grid is
+// ~6,700 km at 5 cm; the reference's own int cast is undefined far beyond that.
+constexpr int32_t kCellSat = 1 << 27;
 
 ICPB_HD int32_t sat_cell(double c) {
     if (!(c > -(double)kCellSat)) return -kCellSat;      // also catches NaN
@@ -149,16 +150,55 @@ ICPB_HD void for_each_tile_run(const RayGeom& g, int32_t nx, int32_t ny, int32_t
     }
 }
 
+// Iterator form of for_each_tile_run (same runs, same order) for code that must
+// keep all lanes of a warp converged while each walks its own ray.
+template <int TS>
+struct TileRunIter {
+    RayGeom g;
+    int64_t n, nb;
+    int32_t tiles_x;
+    ICPB_HD void init(const RayGeom& geom, int32_t nx, int32_t ny, int32_t tiles_x_) {
+        g = geom; tiles_x = tiles_x_;
+        n = 0; nb = 0;
+        if (g.dmaj != 0) clip_to_grid(g, nx, ny, n, nb);
+    }
+    ICPB_HD void init_empty() { n = 0; nb = 0; }
+    ICPB_HD bool next(TileRun& r) {
+        if (n >= nb) return false;
+        const int32_t j = minor_steps(g, (int32_t)n);
+        int32_t x, y;
+        cell_at(g, (int32_t)n, j, x, y);
+        const int32_t tx = x / TS, ty = y / TS;
+        const int32_t cmaj = g.xmajor ? x : y, cmin = g.xmajor ? y : x;
+        const int32_t inmaj = cmaj & (TS - 1);
+        int64_t end = n + (g.smaj > 0 ? (TS - inmaj) : (inmaj + 1));
+        if (g.dmin != 0) {
+            const int32_t inmin = cmin & (TS - 1);
+            const int64_t jleave = (int64_t)j + (g.smin > 0 ? (TS - inmin) : (inmin + 1));
+            const int64_t nleave = first_step_reaching(g, jleave);
+            if (nleave < end) end = nleave;
+        }
+        if (end > nb) end = nb;
+        r.tile = ty * tiles_x + tx;
+        r.n0 = (int32_t)n;
+        r.j0 = j;
+        r.len = (int32_t)(end - n);
+        n = end;
+        return true;
+    }
+};
+
 // Incremental walker used inside a tile: starts at (n0, j0) and reproduces the
 // reference's minor-axis decisions without divisions.
 struct RunWalker {
-    int64_t d;          // (2n+2)*dmin - 2*dmaj*j - dmaj ; minor step taken iff d > 0
-    int64_t inc_maj;    // 2*dmin
-    int64_t dec_min;    // 2*dmaj
+    int32_t d;          // (2n+2)*dmin - 2*dmaj*j - dmaj ; minor step taken iff d > 0
+    int32_t inc_maj;    // 2*dmin
+    int32_t dec_min;    // 2*dmaj
     ICPB_HD void start(const RayGeom& g, int32_t n0, int32_t j0) {
-        inc_maj = 2 * (int64_t)g.dmin;
-        dec_min = 2 * (int64_t)g.dmaj;
-        d = (2 * (int64_t)n0 + 2) * g.dmin - dec_min * j0 - g.dmaj;
+        inc_maj = 2 * g.dmin;
+        dec_min = 2 * g.dmaj;
+        // the products need 64 bits, the result is bounded by 2*dmaj + 2*dmin
+        d = (int32_t)((2 * (int64_t)n0 + 2) * g.dmin - (int64_t)dec_min * j0 - g.dmaj);
     }
     // advance one major step; returns 1 if the minor coordinate also steps
     ICPB_HD int32_t step() {

@@ -26,6 +26,9 @@ struct CtaShared {
     int grid_nx, grid_ny;
     int n_s, n_t;
     int amb_n;
+    // split-sweep partials (K3): [warp][lane]
+    float part_b1[kNW][32], part_b2[kNW][32];
+    int part_bt[kNW][32];
 };
 
 struct SumOp { __device__ static double f(double a, double b) { return a + b; } };

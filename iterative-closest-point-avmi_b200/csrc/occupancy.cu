@@ -36,14 +36,20 @@ constexpr int TCELLS = TS * TS;
 constexpr int kOccNT = 512;
 constexpr unsigned kHitUnit = 1u << 20;      // counter word: hits << 20 | misses
 constexpr unsigned kMissMask = kHitUnit - 1u;
-constexpr size_t kOccSmem = sizeof(float) * TCELLS + 2 * sizeof(unsigned) * TCELLS + sizeof(unsigned short) * kOccMaxChunkScans;
 
-struct Run {                                  // 16 bytes
-    unsigned int ray;                         // global ray index
-    int n0;                                   // first step (miss run) / local cell (hit)
+constexpr size_t kOccSmem = 3 * sizeof(float) * TCELLS + (2 * sizeof(unsigned) + sizeof(unsigned short)) * kOccMaxChunkScans;
+
+// A run is self-contained: the tile kernel needs neither the ray's endpoint nor
+// the scan's origin to walk it (no dependent loads on its critical path).
+struct __align__(16) Run {                    // 32 bytes
+    int n0;                                   // first step of the run
     int j0;                                   // minor steps at n0
     int len;                                  // cells in run; 0 marks a hit
+    int idx0;                                 // local cell index at n0 (hit: the hit cell) | flags << 16
+    int dmaj, dmin;                           // ray slope
+    int pad0, pad1;
 };
+constexpr int kRunXMajor = 1 << 16, kRunMajPos = 1 << 17, kRunMinPos = 1 << 18;
 
 // ---- 1. setup ----------------------------------------------------------------
 __global__ void occ_scan_setup(const double* __restrict__ origins, int n_scans, double min_x,
@@ -86,50 +92,75 @@ struct BinArgs {
     unsigned long long* stats;                // [rays, traversed, hits, runs]
 };
 
+// All lanes of a warp walk their rays' tile runs in lock step.  Runs of the
+// warp that fall into the same (tile, scan) group are allocated as one block
+// of consecutive slots in lane order, so rays that arrive sorted by angle (a
+// lidar scan) stay sorted inside the group: the tile kernel relies on that
+// for its neighbour-lane de-duplication (performance only, never correctness).
 template <bool FILL>
 __global__ void __launch_bounds__(256) occ_bin(const BinArgs a) {
     const long long r = a.ray_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     unsigned long long cells = 0, hits = 0, nruns = 0;
+    TileRunIter<TS> it;
+    it.init_empty();
+    int sl = 0;
+    bool hit_pending = false;
+    int hit_tile = 0, hit_cell = 0;
     if (r < a.ray_end) {
         const int s = a.ray_scan[r];
-        const int sl = s - a.scan_begin;
+        sl = s - a.scan_begin;
         const int2 o = a.origin_cell[s], h = a.ray_cell[r];
-        const RayGeom g = make_ray(o.x, o.y, h.x, h.y);
-        for_each_tile_run<TS>(g, a.nx, a.ny, a.tiles_x, [&](const TileRun& t) {
-            if (t.tile % a.world != a.rank) return;
-            const size_t gi = (size_t)t.tile * a.chunk_scans + sl;
-            if (FILL) {
-                const unsigned slot = atomicAdd(&a.counts[gi], 1u);
-                Run run;
-                run.ray = (unsigned)(r - a.ray_begin);
-                run.n0 = t.n0; run.j0 = t.j0; run.len = t.len;
-                reinterpret_cast<int4*>(a.runs)[a.offsets[gi] + slot] = *reinterpret_cast<int4*>(&run);
-            } else {
-                atomicAdd(&a.counts[gi], 1u);
-                cells += t.len;
-                ++nruns;
-            }
-        });
+        it.init(make_ray(o.x, o.y, h.x, h.y), a.nx, a.ny, a.tiles_x);
         if (h.x >= 0 && h.x < a.nx && h.y >= 0 && h.y < a.ny) {       // mapping.py:124-127
-            const int tile = (h.y / TS) * a.tiles_x + (h.x / TS);
-            if (tile % a.world == a.rank) {
-                const size_t gi = (size_t)tile * a.chunk_scans + sl;
-                if (FILL) {
-                    const unsigned slot = atomicAdd(&a.counts[gi], 1u);
-                    Run run;
-                    run.ray = (unsigned)(r - a.ray_begin);
-                    run.n0 = (h.y % TS) * TS + (h.x % TS); run.j0 = 0; run.len = 0;
-                    reinterpret_cast<int4*>(a.runs)[a.offsets[gi] + slot] = *reinterpret_cast<int4*>(&run);
+            hit_pending = true;
+            hit_tile = (h.y / TS) * a.tiles_x + (h.x / TS);
+            hit_cell = (h.y % TS) * TS + (h.x % TS);
+        }
+    }
+    for (;;) {
+        TileRun t;
+        bool has = it.next(t);
+        if (!has && hit_pending) {                                    // the hit goes last
+            hit_pending = false;
+            has = true;
+            t.tile = hit_tile; t.n0 = hit_cell; t.j0 = 0; t.len = 0;
+        }
+        if (!__any_sync(0xffffffffu, has)) break;
+        const bool owned = has && (t.tile % a.world == a.rank);
+        const unsigned long long gi = owned ? (unsigned long long)t.tile * a.chunk_scans + sl : ~0ull;
+        const unsigned peers = __match_any_sync(0xffffffffu, gi);
+        const int leader = __ffs(peers) - 1;
+        unsigned base = 0;
+        if (owned && lane == leader) base = atomicAdd(&a.counts[gi], (unsigned)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (owned) {
+            if (FILL) {
+                Run run;
+                run.n0 = t.n0; run.j0 = t.j0; run.len = t.len;
+                run.dmaj = it.g.dmaj; run.dmin = it.g.dmin; run.pad0 = 0; run.pad1 = 0;
+                if (t.len == 0) {
+                    run.idx0 = t.n0;                                  // hit: n0 carried the local cell
+                    run.n0 = 0;
                 } else {
-                    atomicAdd(&a.counts[gi], 1u);
-                    ++hits;
-                    ++nruns;
+                    int x, y;
+                    cell_at(it.g, t.n0, t.j0, x, y);
+                    run.idx0 = ((y % TS) * TS + (x % TS)) | (it.g.xmajor ? kRunXMajor : 0) |
+                               (it.g.smaj > 0 ? kRunMajPos : 0) | (it.g.smin > 0 ? kRunMinPos : 0);
                 }
+                int4* dst = reinterpret_cast<int4*>(a.runs + (a.offsets[gi] + base + __popc(peers & lt_mask)));
+                dst[0] = reinterpret_cast<const int4*>(&run)[0];
+                dst[1] = reinterpret_cast<const int4*>(&run)[1];
+            } else {
+                cells += t.len;
+                hits += t.len == 0;
+                ++nruns;
             }
         }
     }
     if (!FILL) {
-        // block totals -> four global atomics per block
+        // block totals -> three global atomics per block
         __shared__ unsigned long long part[3][8];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -138,7 +169,7 @@ __global__ void __launch_bounds__(256) occ_bin(const BinArgs a) {
             nruns += __shfl_xor_sync(0xffffffffu, nruns, o);
         }
         const int w = threadIdx.x >> 5;
-        if ((threadIdx.x & 31) == 0) { part[0][w] = cells; part[1][w] = hits; part[2][w] = nruns; }
+        if (lane == 0) { part[0][w] = cells; part[1][w] = hits; part[2][w] = nruns; }
         __syncthreads();
         if (threadIdx.x == 0) {
             unsigned long long c = 0, h = 0, n = 0;
@@ -261,6 +292,8 @@ struct ApplyArgs {
     int virgin_after;                         // first chunk-local scan index at which virgin cells read clamp(0); INT_MAX = never
     float clamp0;
     int* error_flag;
+    long long* tile_prof;                     // optional: per queue slot {tile, scans, runs, cycles}
+    int split;                                // lock-step windows per 32-run chunk
 };
 
 __device__ __forceinline__ float chain(float x, unsigned m, unsigned k, double l_hit, double l_miss,
@@ -272,6 +305,12 @@ __device__ __forceinline__ float chain(float x, unsigned m, unsigned k, double l
     }
     // mapping.py:139 -- k misses.  The adds are monotone, so once past the
     // clamp bound in the direction of travel the final clamp decides the value.
+    // Each add moves x by l_miss up to one float rounding (< 1e-6 for |x| <= 16),
+    // so k adds certainly cross the bound when k * (|l_miss| - 1e-6) covers the gap.
+    if (k > 4 && fabsf(x) <= 16.f && lo >= -16.f && hi <= 16.f) {
+        if (l_miss < -1e-5 && (double)x + (double)k * (l_miss + 1e-6) <= (double)lo) return lo;
+        if (l_miss > 1e-5 && (double)x + (double)k * (l_miss - 1e-6) >= (double)hi) return hi;
+    }
     if (l_miss != 0.0) {
         for (unsigned i = 0; i < k; ++i) {
             x = (float)((double)x + l_miss);
@@ -281,61 +320,130 @@ __device__ __forceinline__ float chain(float x, unsigned m, unsigned k, double l
     return fminf(fmaxf(x, lo), hi);           // mapping.py:141
 }
 
-// Work item = one "slot" of a run: slot k of a miss run covers its cells
-// [8k, 8k+8); a hit is slot 0 of a zero-length run.  A run has TS/8 slots, most
-// of them empty for short runs; consecutive lanes share a run, so its 16-byte
-// record is one broadcast load.
-constexpr int kSub = 8;
-constexpr int kSlots = TS / kSub;
+// One CTA per tile.  For every scan that touches the tile (in scan order):
+//   count  a task = 32 consecutive runs (one per lane) x one quarter of their
+//          common step window; the warp walks it in lock step over the ray
+//          step index n.  Rays of one scan share their origin, so neighbouring
+//          lanes sit on the same cell for long stretches: each maximal group of
+//          equal neighbours issues ONE shared atomicAdd carrying the group size
+//          (no same-address conflicts, far fewer atomics near the sensor, and
+//          nothing waits on a return value).
+//   apply  every thread scans 8 counters (two 128-bit loads); non-zero ones
+//          run the fp64->fp32 add chain and the clamp, and are zeroed.
+// The counters are double buffered: scan s+1 is counted while scan s is
+// applied, so there is one barrier per scan.
+constexpr int kWin = 16;                       // lock-step block (unrolled)
 
-struct Slot {
-    int idx;            // first local cell index
-    int ncell;          // cells in this slot (0: nothing to do)
-    int maj_stride, min_stride;
-    RunWalker wk;
-    bool hit;
-};
+// Shared-memory slot of local cell idx = y * TS + x.  Rays of one scan that are
+// x-major sit in the same column at a given step; without the swizzle their
+// counters would all fall into one bank (row stride TS = 64 words).
+__device__ __forceinline__ int swz(int idx) { return idx ^ ((idx >> 6) & 31); }
 
-__device__ __forceinline__ Slot load_slot(const ApplyArgs& a, unsigned item, int2 o, int tx0, int ty0) {
-    Slot s;
-    s.ncell = 0; s.hit = false; s.idx = 0; s.maj_stride = 0; s.min_stride = 0;
-    const int4 raw = __ldg(reinterpret_cast<const int4*>(a.runs) + item / kSlots);
-    const int sub = (int)(item % kSlots);
-    if (raw.w == 0) {                                      // hit: n0 is the local cell
-        if (sub == 0) { s.hit = true; s.ncell = 1; s.idx = raw.y; }
-        return s;
+__device__ __forceinline__ void occ_count_scan(const ApplyArgs& a, unsigned beg, unsigned end, unsigned* cnt,
+                                               int warp, int lane) {
+    const unsigned n_chunks = (end - beg + 31u) >> 5;
+    const unsigned above = lane == 31 ? 0u : (0xffffffffu << (lane + 1));
+    for (unsigned task = warp; task < n_chunks * a.split; task += kOccNT / 32) {
+        const unsigned e = beg + (task / a.split) * 32u + lane;
+        const int q = (int)(task % a.split);
+        int n0 = 0x7fffffff, nend = 0, j0 = 0, idx0 = 0, dmaj = 1, dmin = 0;
+        // a tile's runs are contiguous across its scans: pull the records two thousand runs ahead into L2
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.runs + e + 2048));
+        if (e < end) {
+            const int4 ra = __ldg(reinterpret_cast<const int4*>(a.runs + e));
+            const int2 rb = __ldg(reinterpret_cast<const int2*>(a.runs + e) + 2);
+            if (ra.z == 0) {                                       // hit: one add of the hit unit
+                if (q == 0) {
+                    const unsigned old = atomicAdd(&cnt[swz(ra.w & 0xffff)], kHitUnit);
+                    if ((old >> 20) == 4095u) *a.error_flag = 1;
+                }
+            } else {
+                n0 = ra.x; j0 = ra.y; nend = ra.x + ra.z; idx0 = ra.w; dmaj = rb.x; dmin = rb.y;
+            }
+        }
+        const int nmin = (int)__reduce_min_sync(0xffffffffu, (unsigned)n0);
+        const int nmax = (int)__reduce_max_sync(0xffffffffu, (unsigned)nend);
+        if (nmax <= nmin) continue;                                // no miss runs in this chunk
+        const int win = (nmax - nmin + a.split - 1) / a.split;
+        const int lo = nmin + q * win, hi = min(lo + win, nmax);
+        const int s0 = max(n0, lo), s1 = min(nend, hi);            // this lane's steps in the window
+        int idx = 0, step_maj = 0, step_both = 0, d = 0, inc = 0, dec = 0;
+        if (s0 < s1) {
+            const int maj = (idx0 & kRunXMajor) ? ((idx0 & kRunMajPos) ? 1 : -1) : ((idx0 & kRunMajPos) ? TS : -TS);
+            const int mnr = (idx0 & kRunXMajor) ? ((idx0 & kRunMinPos) ? TS : -TS) : ((idx0 & kRunMinPos) ? 1 : -1);
+            int j = j0;
+            if (s0 > n0) {                                         // enter mid-run: closed form (bres.cuh)
+                const unsigned long long num = 2ull * (unsigned)s0 * (unsigned)dmin + (unsigned)dmaj - 1u;
+                j = (num >> 32) == 0 ? (int)((unsigned)num / (2u * (unsigned)dmaj))
+                                     : (int)(num / (2ull * (unsigned)dmaj));
+            }
+            idx = (idx0 & 0xffff) + (s0 - n0) * maj + (j - j0) * mnr;
+            step_maj = maj; step_both = maj + mnr;
+            inc = 2 * dmin; dec = 2 * dmaj;
+            d = (int)((2ll * s0 + 2) * dmin - (long long)dec * j - dmaj);   // RunWalker::start
+        }
+        for (int b = lo; b < hi; b += kWin) {
+            // cells of this lane for the next kWin steps (pure ALU), then the votes + atomics
+            int cell[kWin];
+            unsigned actbits = 0;
+#pragma unroll
+            for (int k = 0; k < kWin; ++k) {
+                const int n = b + k;
+                const bool act = n >= s0 && n < s1 && n < hi;
+                cell[k] = idx;
+                actbits |= act ? (1u << k) : 0u;
+                if (act) { const bool m = d > 0; idx += m ? step_both : step_maj; d += inc - (m ? dec : 0); }
+            }
+#pragma unroll
+            for (int k = 0; k < kWin; ++k) {
+                const bool act = (actbits >> k) & 1u;
+                const unsigned am = __ballot_sync(0xffffffffu, act);
+                if (am == 0u) continue;
+                const int prev = __shfl_up_sync(0xffffffffu, cell[k], 1);
+                const bool prev_act = lane > 0 && ((am >> (lane - 1)) & 1u);
+                const bool lead = act && !(prev_act && prev == cell[k]);
+                const unsigned lm = __ballot_sync(0xffffffffu, lead);
+                if (lead) {
+                    // group = this lane and the active lanes right after it on the same cell
+                    const unsigned stop = (lm | ~am) & above;
+                    const int nxt = stop ? __ffs(stop) - 1 : 32;
+                    atomicAdd(&cnt[swz(cell[k])], (unsigned)(nxt - lane));   // result unused
+                }
+            }
+        }
     }
-    const int first = sub * kSub;
-    if (first >= raw.w) return s;
-    s.ncell = min(kSub, raw.w - first);
-    const int2 h = __ldg(&a.ray_cell[(unsigned)raw.x]);
-    const RayGeom g = make_ray(o.x, o.y, h.x, h.y);
-    const int n = raw.y + first;
-    int j = raw.z;
-    if (sub != 0) {
-        // minor_steps(g, n); 32-bit division whenever the numerator fits
-        const unsigned long long num = 2ull * (unsigned)n * (unsigned)g.dmin + (unsigned)g.dmaj - 1u;
-        j = (num >> 32) == 0 ? (int)((unsigned)num / (2u * (unsigned)g.dmaj)) : (int)(num / (2ull * (unsigned)g.dmaj));
+}
+
+__device__ __forceinline__ void occ_apply_scan(const ApplyArgs& a, float* tile, unsigned* cnt, bool virgin_fix, int tid) {
+    for (int c0 = tid * 4; c0 < TCELLS; c0 += kOccNT * 4) {
+        const uint4 c4 = *reinterpret_cast<const uint4*>(&cnt[c0]);
+        if ((c4.x | c4.y | c4.z | c4.w) == 0u) continue;
+        const unsigned cv[4] = {c4.x, c4.y, c4.z, c4.w};
+        *reinterpret_cast<uint4*>(&cnt[c0]) = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (cv[k]) {
+                float x = tile[c0 + k];
+                if (virgin_fix && x == 0.0f) x = a.clamp0;
+                tile[c0 + k] = chain(x, cv[k] >> 20, cv[k] & kMissMask, a.l_hit, a.l_miss, a.lo, a.hi);
+            }
+        }
     }
-    int x, y;
-    cell_at(g, n, j, x, y);
-    s.idx = (y - ty0) * TS + (x - tx0);
-    s.maj_stride = g.xmajor ? g.smaj : g.smaj * TS;
-    s.min_stride = g.xmajor ? g.smin * TS : g.smin;
-    s.wk.start(g, n, j);
-    return s;
 }
 
 __global__ void __launch_bounds__(kOccNT) occ_tile_apply(const ApplyArgs a) {
     extern __shared__ __align__(16) unsigned char occ_smem[];
     float* tile = reinterpret_cast<float*>(occ_smem);
-    // double-buffered counters: count scan s+1 while applying scan s
-    unsigned (*cnt)[TCELLS] = reinterpret_cast<unsigned (*)[TCELLS]>(occ_smem + sizeof(float) * TCELLS);
-    unsigned short* scan_list = reinterpret_cast<unsigned short*>(occ_smem + sizeof(float) * TCELLS + 2 * sizeof(unsigned) * TCELLS);
+    unsigned* cnt0 = reinterpret_cast<unsigned*>(occ_smem + sizeof(float) * TCELLS);
+    unsigned* cnt1 = cnt0 + TCELLS;
+    unsigned* scan_beg = cnt1 + TCELLS;
+    unsigned* scan_end = scan_beg + kOccMaxChunkScans;
+    unsigned short* scan_list = reinterpret_cast<unsigned short*>(scan_end + kOccMaxChunkScans);
     __shared__ int wcount[kOccNT / 32];
     __shared__ int n_list;
     __shared__ int cur_tile;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int n_active = *a.n_active;
 
     for (;;) {
@@ -348,90 +456,53 @@ __global__ void __launch_bounds__(kOccNT) occ_tile_apply(const ApplyArgs a) {
         __syncthreads();
         const int t = cur_tile;
         if (t < 0) break;
+        const long long t_start = clock64();
         const int tx0 = (t % a.tiles_x) * TS, ty0 = (t / a.tiles_x) * TS;
         for (int c = tid; c < TCELLS; c += kOccNT) {
             const int x = tx0 + (c & (TS - 1)), y = ty0 + (c / TS);
-            tile[c] = (x < a.nx && y < a.ny) ? a.grid[(size_t)y * a.nx + x] : 0.f;
-            cnt[0][c] = 0u;
-            cnt[1][c] = 0u;
+            tile[swz(c)] = (x < a.nx && y < a.ny) ? a.grid[(size_t)y * a.nx + x] : 0.f;
+            cnt0[c] = 0u;
+            cnt1[c] = 0u;
         }
-        // scans that have runs in this tile, ascending
+        // scans that have runs in this tile, ascending, with their run ranges
         const unsigned* off = a.offsets + (size_t)t * a.chunk_scans;
         for (int s0 = 0; s0 < a.chunk_scans; s0 += kOccNT) {
             const int s = s0 + tid;
-            const bool has = s < a.chunk_scans && off[s + 1] > off[s];
+            unsigned ob = 0, oe = 0;
+            if (s < a.chunk_scans) { ob = off[s]; oe = off[s + 1]; }
+            const bool has = oe > ob;
             const unsigned bal = __ballot_sync(0xffffffffu, has);
-            if ((tid & 31) == 0) wcount[tid >> 5] = __popc(bal);
+            if (lane == 0) wcount[warp] = __popc(bal);
             __syncthreads();
             int base = n_list;
-            for (int w = 0; w < (tid >> 5); ++w) base += wcount[w];
-            if (has) scan_list[base + __popc(bal & ((1u << (tid & 31)) - 1u))] = (unsigned short)s;
+            for (int w = 0; w < warp; ++w) base += wcount[w];
+            if (has) {
+                const int slot = base + __popc(bal & lt_mask);
+                scan_list[slot] = (unsigned short)s; scan_beg[slot] = ob; scan_end[slot] = oe;
+            }
             __syncthreads();
             if (tid == 0) { int tot = 0; for (int w = 0; w < kOccNT / 32; ++w) tot += wcount[w]; n_list += tot; }
             __syncthreads();
         }
         const int n_scans_here = n_list;
-
-        auto count_scan = [&](int li) {
-            const int s = scan_list[li];
-            unsigned* c = cnt[li & 1];
-            const unsigned beg = off[s] * kSlots, end = off[s + 1] * kSlots;
-            const int2 o = a.origin_cell[s];
-            for (unsigned item = beg + tid; item < end; item += kOccNT) {
-                Slot sl = load_slot(a, item, o, tx0, ty0);
-                if (sl.hit) {
-                    const unsigned old = atomicAdd(&c[sl.idx], kHitUnit);
-                    if ((old >> 20) == 4095u) *a.error_flag = 1;
-                } else {
-                    int idx = sl.idx;
-                    for (int k = 0; k < sl.ncell; ++k) {
-                        atomicAdd(&c[idx], 1u);                       // result unused: fire and forget
-                        idx += sl.maj_stride + (sl.wk.step() ? sl.min_stride : 0);
-                    }
-                }
-            }
-        };
-        auto apply_scan = [&](int li) {
-            const int s = scan_list[li];
-            unsigned* c = cnt[li & 1];
-            const unsigned beg = off[s] * kSlots, end = off[s + 1] * kSlots;
-            const int2 o = a.origin_cell[s];
-            const bool virgin_fix = s >= a.virgin_after;
-            for (unsigned item = beg + tid; item < end; item += kOccNT) {
-                Slot sl = load_slot(a, item, o, tx0, ty0);
-                if (sl.ncell == 0) continue;
-                int idxs[kSub];
-                unsigned got[kSub];
-                int idx = sl.idx;
-#pragma unroll
-                for (int k = 0; k < kSub; ++k) {
-                    idxs[k] = idx;
-                    if (k < sl.ncell && !sl.hit) idx += sl.maj_stride + (sl.wk.step() ? sl.min_stride : 0);
-                }
-                // the thread whose exchange returns a non-zero count owns the cell for this scan
-#pragma unroll
-                for (int k = 0; k < kSub; ++k) got[k] = k < sl.ncell ? atomicExch(&c[idxs[k]], 0u) : 0u;
-#pragma unroll
-                for (int k = 0; k < kSub; ++k) {
-                    if (got[k]) {
-                        float x = tile[idxs[k]];
-                        if (virgin_fix && x == 0.0f) x = a.clamp0;
-                        tile[idxs[k]] = chain(x, got[k] >> 20, got[k] & kMissMask, a.l_hit, a.l_miss, a.lo, a.hi);
-                    }
-                }
-            }
-        };
-
-        if (n_scans_here > 0) count_scan(0);
+        if (n_scans_here > 0) occ_count_scan(a, scan_beg[0], scan_end[0], cnt0, warp, lane);
         __syncthreads();
         for (int li = 0; li < n_scans_here; ++li) {
-            if (li + 1 < n_scans_here) count_scan(li + 1);    // other counter buffer
-            apply_scan(li);
+            unsigned* cur = (li & 1) ? cnt1 : cnt0;
+            unsigned* nxt = (li & 1) ? cnt0 : cnt1;
+            if (li + 1 < n_scans_here) occ_count_scan(a, scan_beg[li + 1], scan_end[li + 1], nxt, warp, lane);
+            occ_apply_scan(a, tile, cur, (int)scan_list[li] >= a.virgin_after, tid);
             __syncthreads();
         }
         for (int c = tid; c < TCELLS; c += kOccNT) {
             const int x = tx0 + (c & (TS - 1)), y = ty0 + (c / TS);
-            if (x < a.nx && y < a.ny) a.grid[(size_t)y * a.nx + x] = tile[c];
+            if (x < a.nx && y < a.ny) a.grid[(size_t)y * a.nx + x] = tile[swz(c)];
+        }
+        if (a.tile_prof && tid == 0) {
+            long long* rec = a.tile_prof + 4ll * t;
+            rec[0] = t; rec[1] = n_scans_here;
+            rec[2] = (long long)(off[a.chunk_scans] - off[0]);
+            rec[3] = clock64() - t_start;
         }
     }
 }
@@ -522,7 +593,7 @@ int occ_update_device(OccGrid& g, int n_scans, const double* d_origins, const do
         ICPB_CUDA(cudaMemcpyAsync(&total_runs, d_small, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         ICPB_CUDA(cudaStreamSynchronize(st));
         if (total_runs == 0) continue;
-        if (g.runs.reserve(sizeof(Run) * (size_t)total_runs)) return ICPB200_ERR_CUDA;
+        if (g.runs.reserve(sizeof(Run) * ((size_t)total_runs + 4096))) return ICPB200_ERR_CUDA;   // + prefetch slack
         ICPB_CUDA(cudaMemsetAsync(g.counts.p, 0, sizeof(unsigned) * cells, st));
         b.offsets = g.offsets.as<unsigned>();
         b.runs = g.runs.as<Run>();
@@ -557,6 +628,13 @@ int occ_update_device(OccGrid& g, int n_scans, const double* d_origins, const do
             }
         }
         ap.error_flag = reinterpret_cast<int*>(d_small + 3);
+        ap.tile_prof = nullptr;
+        ap.split = g.split;
+        if (g.profile_tiles) {
+            if (g.tile_prof.reserve(sizeof(long long) * 4 * (size_t)n_tiles)) return ICPB200_ERR_CUDA;
+            ICPB_CUDA(cudaMemsetAsync(g.tile_prof.p, 0, sizeof(long long) * 4 * (size_t)n_tiles, st));
+            ap.tile_prof = g.tile_prof.as<long long>();
+        }
         ICPB_CUDA(cudaFuncSetAttribute(occ_tile_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOccSmem));
         occ_tile_apply<<<g.apply_ctas, kOccNT, kOccSmem, st>>>(ap);
         ICPB_LAUNCH_CHECK();

@@ -25,7 +25,9 @@ struct OccGrid {
     DevBuf grid;                                   // ny * nx float32, row major
     DevBuf origins, hits, hit_off;                 // staging for the host-buffer entry point
     DevBuf origin_cell, ray_cell, ray_scan;
-    DevBuf counts, offsets, sums, runs, order, small;
+    DevBuf counts, offsets, sums, runs, order, small, tile_prof;
+    int split = 4;                                 // lock-step windows per 32-run chunk (tuning knob)
+    bool profile_tiles = false;                    // icpb200_grid_tile_profile() requested per-tile timings
     void release_all();
 };
 

@@ -58,6 +58,9 @@ def harness():
     lib.harness_ray_cells.restype = ctypes.c_int64
     lib.harness_ray_cells.argtypes = [ctypes.c_int] * 7 + [ctypes.POINTER(ctypes.c_int32), ctypes.c_int64]
     lib.harness_minor_steps.argtypes = [ctypes.c_int] * 5
+    for fn in (lib.harness_ray_runs_iter, lib.harness_ray_runs_cb):
+        fn.restype = ctypes.c_int64
+        fn.argtypes = [ctypes.c_int] * 6 + [ctypes.POINTER(ctypes.c_int32), ctypes.c_int64]
     lib.harness_sat_cell.argtypes = [ctypes.c_double]
     lib.harness_solve3.argtypes = [dp, dp, dp]
     lib.harness_kabsch2.argtypes = [dp, dp]

@@ -69,6 +69,28 @@ void harness_tile_stats(int n_scans, const double* origins, const double* hits, 
     }
 }
 
+// Same walk through the iterator form (TileRunIter) used by the binning kernel.
+int64_t harness_ray_runs_iter(int ox, int oy, int hx, int hy, int nx, int ny, int32_t* out4, int64_t cap) {
+    TileRunIter<64> it;
+    it.init(make_ray(ox, oy, hx, hy), nx, ny, (nx + 63) / 64);
+    TileRun r;
+    int64_t n = 0;
+    while (it.next(r)) {
+        if (n < cap) { out4[4 * n] = r.tile; out4[4 * n + 1] = r.n0; out4[4 * n + 2] = r.j0; out4[4 * n + 3] = r.len; }
+        ++n;
+    }
+    return n;
+}
+
+int64_t harness_ray_runs_cb(int ox, int oy, int hx, int hy, int nx, int ny, int32_t* out4, int64_t cap) {
+    int64_t n = 0;
+    for_each_tile_run<64>(make_ray(ox, oy, hx, hy), nx, ny, (nx + 63) / 64, [&](const TileRun& r) {
+        if (n < cap) { out4[4 * n] = r.tile; out4[4 * n + 1] = r.n0; out4[4 * n + 2] = r.j0; out4[4 * n + 3] = r.len; }
+        ++n;
+    });
+    return n;
+}
+
 int harness_minor_steps(int ox, int oy, int hx, int hy, int n) {
     const RayGeom g = make_ray(ox, oy, hx, hy);
     return minor_steps(g, n);
