@@ -120,9 +120,11 @@ static int check_common(const IcpCommon& k, const char* who) {
 
 struct DevClouds {                 // one set of raw clouds resident on the device
     const double* pts;
-    const long long* off;
+    const long long* off;          // device
+    const int64_t* h_off;          // the same offsets on the host (nullptr: not available)
     int n_clouds;
-    long long max_points;          // largest raw cloud
+    long long role_max;            // largest raw cloud referenced in this role (source / target)
+    long long set_max;             // largest raw cloud of the whole set
     long long total_points;        // upper bound on off[n_clouds]
 };
 
@@ -149,8 +151,20 @@ static int make_cloud_set(Context& c, int slot, const DevClouds& d, int dim, boo
     return ICPB200_OK;
 }
 
+// voxel-grid means of a whole set: shared-memory kernel for scan-sized clouds,
+// global-memory radix-sort kernel when any cloud of the set exceeds one CTA
+static int voxel_set(Context& c, const CloudSet& cs, const DevClouds& d, int dim, double voxel, cudaStream_t st) {
+    if (d.set_max <= ICPB200_BRUTE_MAX_POINTS)
+        return launch_voxel_clouds(cs, dim, voxel, next_pow2((int)std::max<long long>(d.set_max, 256)), st);
+    const size_t np = (size_t)d.total_points;
+    if (c.big_keys.reserve(sizeof(unsigned long long) * 2 * np) || c.big_idx.reserve(sizeof(unsigned) * 2 * np))
+        return ICPB200_ERR_CUDA;
+    return launch_big_voxel(cs, dim, voxel, c.big_keys.as<unsigned long long>(), c.big_idx.as<unsigned>(),
+                            d.total_points, st);
+}
+
 // Enqueue the registration of n_pairs pairs on `st` (device pointers everywhere):
-// K0 mark -> K1 voxel means per referenced cloud -> K2 normals per p2l target -> K3 pairs.
+// K0 mark -> K1 voxel means per referenced cloud -> [K4 hash grids] -> K2 normals per p2l target -> K3 pairs.
 static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, const DevClouds& t, bool same_set,
                        const int* d_src_idx, const int* d_tgt_idx,
                        const double* d_R_init, const double* d_t_init, double* d_R, double* d_t,
@@ -158,10 +172,18 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
                        const IcpTrace& tr, IcpArgs* args_out) {
     Context& c = g_ctx;
     if (n_pairs == 0) return ICPB200_OK;
-    const long long biggest = std::max(s.max_points, t.max_points);
-    if (k.nn_mode == ICPB200_NN_GRID || biggest > ICPB200_BRUTE_MAX_POINTS) {
-        set_error("icp: clouds of %lld raw points need the grid nearest-neighbour path, which this build "
-                  "does not contain yet (brute-force limit %d)", biggest, ICPB200_BRUTE_MAX_POINTS);
+    const bool grid = k.nn_mode == ICPB200_NN_GRID ||
+                      (k.nn_mode == ICPB200_NN_AUTO && t.role_max > ICPB200_BRUTE_MAX_POINTS);
+    if (!grid && t.role_max > ICPB200_BRUTE_MAX_POINTS) {
+        set_error("icp: nn_mode brute supports targets of at most %d raw points (got %lld)", ICPB200_BRUTE_MAX_POINTS, t.role_max);
+        return ICPB200_ERR_LIMIT;
+    }
+    if (s.role_max > ICPB200_BRUTE_MAX_POINTS) {
+        set_error("icp: source clouds of more than %d raw points are not supported (got %lld)", ICPB200_BRUTE_MAX_POINTS, s.role_max);
+        return ICPB200_ERR_LIMIT;
+    }
+    if (grid && k.dim != 2) {
+        set_error("icp: the grid nearest-neighbour path is 2-D only in this build");
         return ICPB200_ERR_LIMIT;
     }
     const bool p2l = k.method == ICPB200_POINT_TO_LINE && k.dim == 2;
@@ -177,11 +199,11 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
     a.err_thr = k.error_threshold; a.max_iter = k.max_iterations; a.voxel = k.voxel_size;
     a.method = k.method; a.normal_k = k.normal_k; a.max_corr = k.max_corr_dist;
     a.R_out = d_R; a.t_out = d_t; a.err_out = d_err; a.prev_out = d_prev; a.iters_out = d_iters; a.status_out = d_status;
-    a.cap_s = round_up((int)std::max<long long>(s.max_points, 32), 32);
-    a.cap_t = round_up((int)std::max<long long>(t.max_points, 32), 32);
-    a.sort_pad = next_pow2((int)std::max<long long>(biggest, 256));
+    a.cap_s = round_up((int)std::max<long long>(s.role_max, 32), 32);
+    a.cap_t = grid ? 32 : round_up((int)std::max<long long>(t.role_max, 32), 32);
+    a.sort_pad = next_pow2((int)std::max<long long>(std::min<long long>(std::max(s.set_max, t.set_max), ICPB200_BRUTE_MAX_POINTS), 256));
     const size_t smem = icp_pair_smem_bytes(k.dim, a.cap_s, a.cap_t);
-    if (smem > (size_t)c.max_smem_optin || icp_normals_smem_bytes(a.cap_t) > (size_t)c.max_smem_optin ||
+    if (smem > (size_t)c.max_smem_optin || (!grid && p2l && icp_normals_smem_bytes(a.cap_t) > (size_t)c.max_smem_optin) ||
         icp_voxel_smem_bytes(a.sort_pad) > (size_t)c.max_smem_optin) {
         set_error("icp: %zu bytes of shared memory needed, device allows %d", smem, c.max_smem_optin);
         return ICPB200_ERR_LIMIT;
@@ -194,18 +216,58 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
     ICPB_CUDA(cudaMemsetAsync(a.stats, 0, 8 * sizeof(unsigned long long), st));
     ICPB_CUDA(cudaMemsetAsync(a.s.used, 0, 2 * (size_t)s.n_clouds, st));
     if (!same_set) ICPB_CUDA(cudaMemsetAsync(a.t.used, 0, 2 * (size_t)t.n_clouds, st));
-    if ((rc = launch_mark_used(a, p2l, st))) return rc;
+    a.grids = nullptr;
+    if ((rc = launch_mark_used(a, p2l || grid, st))) return rc;
     ICPB_CUDA(cudaEventRecord(c.ev[0], st));
-    if ((rc = launch_voxel_clouds(a.s, k.dim, k.voxel_size, a.sort_pad, st))) return rc;
-    if (!same_set && (rc = launch_voxel_clouds(a.t, k.dim, k.voxel_size, a.sort_pad, st))) return rc;
+    if ((rc = voxel_set(c, a.s, s, k.dim, k.voxel_size, st))) return rc;
+    if (!same_set && (rc = voxel_set(c, a.t, t, k.dim, k.voxel_size, st))) return rc;
     ICPB_CUDA(cudaEventRecord(c.ev[1], st));
-    if (p2l && (rc = launch_normals(a.t, a.cap_t, k.normal_k, k.voxel_size, st))) return rc;
+    if (grid) {
+        // one hash grid per target cloud; bucket counts from the raw sizes (host side)
+        std::vector<int64_t> fetched;
+        const int64_t* h_off = t.h_off;
+        if (!h_off) {
+            fetched.resize((size_t)t.n_clouds + 1);
+            ICPB_CUDA(cudaMemcpyAsync(fetched.data(), t.off, sizeof(int64_t) * fetched.size(), cudaMemcpyDeviceToHost, st));
+            ICPB_CUDA(cudaStreamSynchronize(st));
+            h_off = fetched.data();
+        }
+        std::vector<long long> goff((size_t)t.n_clouds);
+        std::vector<int> gbuckets((size_t)t.n_clouds);
+        long long total_start = 0;
+        for (int i = 0; i < t.n_clouds; ++i) {
+            const long long n = h_off[i + 1] - h_off[i];
+            int b = 1024;
+            while (b < 2 * n && b < (1 << 24)) b <<= 1;
+            gbuckets[i] = b;
+            goff[i] = total_start;
+            total_start += b + 1;
+        }
+        const size_t np = (size_t)t.total_points, nc = (size_t)t.n_clouds;
+        if (c.grid_start.reserve(sizeof(int) * (size_t)total_start) || c.grid_items.reserve(sizeof(int) * np) ||
+            c.grid_cell.reserve(sizeof(int2) * np) || c.grid_desc.reserve(sizeof(BigGrid) * nc) ||
+            c.grid_off.reserve(sizeof(long long) * nc) || c.grid_buckets.reserve(sizeof(int) * nc))
+            return ICPB200_ERR_CUDA;
+        ICPB_CUDA(cudaMemcpyAsync(c.grid_off.p, goff.data(), sizeof(long long) * nc, cudaMemcpyHostToDevice, st));
+        ICPB_CUDA(cudaMemcpyAsync(c.grid_buckets.p, gbuckets.data(), sizeof(int) * nc, cudaMemcpyHostToDevice, st));
+        ICPB_CUDA(cudaStreamSynchronize(st));          // goff / gbuckets are stack-owned
+        ICPB_CUDA(cudaMemsetAsync(c.grid_desc.p, 0, sizeof(BigGrid) * nc, st));
+        // cell edge: 8 voxels (a 3x3 block of cells holds a few dozen wall points)
+        if ((rc = launch_big_grid(a.t, 8.0 * k.voxel_size, c.grid_off.as<long long>(), c.grid_buckets.as<int>(),
+                                  c.grid_start.as<int>(), c.grid_items.as<int>(), c.grid_cell.as<int2>(),
+                                  c.grid_desc.as<BigGrid>(), st)))
+            return rc;
+        a.grids = c.grid_desc.as<BigGrid>();
+        if (p2l && (rc = launch_big_normals(a.t, a.grids, k.normal_k, t.role_max, st))) return rc;
+    } else if (p2l) {
+        if ((rc = launch_normals(a.t, a.cap_t, k.normal_k, k.voxel_size, st))) return rc;
+    }
     ICPB_CUDA(cudaEventRecord(c.ev[2], st));
-    const int per_sm = icp_max_ctas_per_sm(k.dim, smem);
+    const int per_sm = icp_max_ctas_per_sm(k.dim, grid, smem);
     const int n_ctas = std::min(n_pairs, c.sm_count * per_sm);
     c.last_icp_stream = st;
     if (args_out) *args_out = a;
-    if ((rc = launch_icp_pairs(a, k.dim, n_ctas, smem, st))) return rc;
+    if ((rc = launch_icp_pairs(a, k.dim, grid, n_ctas, smem, st))) return rc;
     ICPB_CUDA(cudaEventRecord(c.ev[3], st));
     return ICPB200_OK;
 }
@@ -277,7 +339,9 @@ void icpb200_shutdown(void) {
     DevBuf* bufs[] = {&c.pts_a, &c.pts_b, &c.off_a, &c.off_b, &c.idx_a, &c.idx_b, &c.rinit, &c.tinit, &c.out_r,
                       &c.out_t, &c.out_err, &c.out_prev, &c.out_iters, &c.out_status, &c.queue, &c.trace, &c.stats,
                       &c.aux_ds[0], &c.aux_ds[1], &c.aux_n[0], &c.aux_n[1], &c.aux_box[0], &c.aux_box[1],
-                      &c.aux_nrm[0], &c.aux_nrm[1], &c.aux_flags[0], &c.aux_flags[1], &c.vox_in, &c.vox_out};
+                      &c.aux_nrm[0], &c.aux_nrm[1], &c.aux_flags[0], &c.aux_flags[1], &c.vox_in, &c.vox_out,
+                      &c.big_keys, &c.big_idx, &c.grid_start, &c.grid_items, &c.grid_cell, &c.grid_desc, &c.grid_off,
+                      &c.grid_buckets};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 4; ++i) if (c.ev[i]) { cudaEventDestroy(c.ev[i]); c.ev[i] = nullptr; }
     cudaStreamDestroy(c.stream);
@@ -320,8 +384,8 @@ int icpb200_icp_batch(int n_pairs, int dim, const double* src, const int64_t* sr
     ICPB_CUDA(cudaMemcpyAsync(c.off_b.p, tgt_off, sizeof(int64_t) * (n_pairs + 1), cudaMemcpyHostToDevice, c.stream));
     const double *d_Ri, *d_ti;
     if ((rc = upload_init(c, n_pairs, dim, R_init, t_init, &d_Ri, &d_ti))) return rc;
-    const DevClouds s{c.pts_a.as<double>(), c.off_a.as<long long>(), n_pairs, max_s, (long long)ns};
-    const DevClouds t{c.pts_b.as<double>(), c.off_b.as<long long>(), n_pairs, max_t, (long long)nt};
+    const DevClouds s{c.pts_a.as<double>(), c.off_a.as<long long>(), src_off, n_pairs, max_s, max_s, (long long)ns};
+    const DevClouds t{c.pts_b.as<double>(), c.off_b.as<long long>(), tgt_off, n_pairs, max_t, max_t, (long long)nt};
     rc = icp_enqueue(k, n_pairs, s, t, false, nullptr, nullptr, d_Ri, d_ti, c.out_r.as<double>(), c.out_t.as<double>(),
                      c.out_err.as<double>(), c.out_prev.as<double>(), c.out_iters.as<int>(), c.out_status.as<int>(),
                      c.stream, IcpTrace{}, nullptr);
@@ -363,8 +427,14 @@ int icpb200_icp_pairs(int n_clouds, int dim, const double* pts, const int64_t* c
     ICPB_CUDA(cudaMemcpyAsync(c.idx_b.p, tgt_idx, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyHostToDevice, c.stream));
     const double *d_Ri, *d_ti;
     if ((rc = upload_init(c, n_pairs, dim, R_init, t_init, &d_Ri, &d_ti))) return rc;
-    const DevClouds s{c.pts_a.as<double>(), c.off_a.as<long long>(), n_clouds, max_pts, (long long)np};
-    rc = icp_enqueue(k, n_pairs, s, s, true, c.idx_a.as<int>(), c.idx_b.as<int>(), d_Ri, d_ti, c.out_r.as<double>(),
+    long long max_src = 0, max_tgt = 0;
+    for (int p = 0; p < n_pairs; ++p) {
+        max_src = std::max<long long>(max_src, cloud_off[src_idx[p] + 1] - cloud_off[src_idx[p]]);
+        max_tgt = std::max<long long>(max_tgt, cloud_off[tgt_idx[p] + 1] - cloud_off[tgt_idx[p]]);
+    }
+    const DevClouds s{c.pts_a.as<double>(), c.off_a.as<long long>(), cloud_off, n_clouds, max_src, max_pts, (long long)np};
+    const DevClouds t{c.pts_a.as<double>(), c.off_a.as<long long>(), cloud_off, n_clouds, max_tgt, max_pts, (long long)np};
+    rc = icp_enqueue(k, n_pairs, s, t, true, c.idx_a.as<int>(), c.idx_b.as<int>(), d_Ri, d_ti, c.out_r.as<double>(),
                      c.out_t.as<double>(), c.out_err.as<double>(), c.out_prev.as<double>(), c.out_iters.as<int>(),
                      c.out_status.as<int>(), c.stream, IcpTrace{}, nullptr);
     if (rc) return rc;
@@ -389,10 +459,33 @@ int icpb200_icp_pairs_dev(int n_clouds, int dim, const double* d_pts, const int6
     if ((rc = init_locked(-1))) return rc;
     Context& c = g_ctx;
     cudaStream_t st = stream ? (cudaStream_t)stream : c.stream;
-    const DevClouds s{d_pts, (const long long*)d_cloud_off, n_clouds, max_cloud_points,
-                      (long long)n_clouds * max_cloud_points};
+    DevClouds s{d_pts, (const long long*)d_cloud_off, nullptr, n_clouds, max_cloud_points, max_cloud_points,
+                (long long)n_clouds * max_cloud_points};
+    DevClouds t = s;
+    std::vector<int64_t> h_off;
+    if (max_cloud_points > ICPB200_BRUTE_MAX_POINTS && n_pairs > 0) {
+        // big clouds: the source / target roles need their own size bounds -> one small readback
+        h_off.resize((size_t)n_clouds + 1);
+        std::vector<int32_t> h_si((size_t)n_pairs), h_ti((size_t)n_pairs);
+        ICPB_CUDA(cudaMemcpyAsync(h_off.data(), d_cloud_off, sizeof(int64_t) * h_off.size(), cudaMemcpyDeviceToHost, st));
+        ICPB_CUDA(cudaMemcpyAsync(h_si.data(), d_src_idx, sizeof(int32_t) * h_si.size(), cudaMemcpyDeviceToHost, st));
+        ICPB_CUDA(cudaMemcpyAsync(h_ti.data(), d_tgt_idx, sizeof(int32_t) * h_ti.size(), cudaMemcpyDeviceToHost, st));
+        ICPB_CUDA(cudaStreamSynchronize(st));
+        long long ms = 0, mt = 0;
+        for (int p = 0; p < n_pairs; ++p) {
+            if (h_si[p] < 0 || h_si[p] >= n_clouds || h_ti[p] < 0 || h_ti[p] >= n_clouds) {
+                set_error("icpb200_icp_pairs_dev: pair %d references a cloud outside [0, %d)", p, n_clouds);
+                return ICPB200_ERR_ARG;
+            }
+            ms = std::max<long long>(ms, h_off[h_si[p] + 1] - h_off[h_si[p]]);
+            mt = std::max<long long>(mt, h_off[h_ti[p] + 1] - h_off[h_ti[p]]);
+        }
+        s.h_off = t.h_off = h_off.data();
+        s.role_max = ms; t.role_max = mt;
+        s.total_points = t.total_points = h_off[n_clouds];
+    }
     const bool init = d_R_init && d_t_init;
-    return icp_enqueue(k, n_pairs, s, s, true, d_src_idx, d_tgt_idx, init ? d_R_init : nullptr,
+    return icp_enqueue(k, n_pairs, s, t, true, d_src_idx, d_tgt_idx, init ? d_R_init : nullptr,
                        init ? d_t_init : nullptr, d_R_out, d_t_out, d_err_out, d_prev_err_out, d_iters_out,
                        d_status_out, st, IcpTrace{}, nullptr);
 }
@@ -433,8 +526,8 @@ int icpb200_icp_trace(int dim, const double* src, int64_t n_src, const double* t
     ICPB_CUDA(cudaMemcpyAsync(c.off_b.p, off_t, sizeof(off_t), cudaMemcpyHostToDevice, c.stream));
     const double *d_Ri, *d_ti;
     if ((rc = upload_init(c, 1, dim, R_init, t_init, &d_Ri, &d_ti))) return rc;
-    const DevClouds s{c.pts_a.as<double>(), c.off_a.as<long long>(), 1, n_src, n_src};
-    const DevClouds t{c.pts_b.as<double>(), c.off_b.as<long long>(), 1, n_tgt, n_tgt};
+    const DevClouds s{c.pts_a.as<double>(), c.off_a.as<long long>(), off_s, 1, n_src, n_src, n_src};
+    const DevClouds t{c.pts_b.as<double>(), c.off_b.as<long long>(), off_t, 1, n_tgt, n_tgt, n_tgt};
     IcpTrace tr;
     tr.match = d_mat; tr.iters = d_mat ? trace_iters : 0; tr.stride = (int)n_src;
     IcpArgs a;
@@ -487,11 +580,12 @@ int icpb200_voxel_downsample(const double* pts, int64_t n, int dim, double voxel
     int rc = init_locked(-1);
     if (rc) return rc;
     Context& c = g_ctx;
-    if (n > 16384) {
-        set_error("icpb200_voxel_downsample: %lld points exceed the single-CTA limit of 16384 in this build", (long long)n);
+    if (n > 0x7fffffffLL / 4) {
+        set_error("icpb200_voxel_downsample: %lld points exceed the 2^29 limit of this build", (long long)n);
         return ICPB200_ERR_LIMIT;
     }
-    const int sort_pad = next_pow2((int)std::max<int64_t>(n, 256));
+    const bool big = n > 16384;                    // beyond one CTA's shared memory: global-memory radix sort
+    const int sort_pad = big ? 256 : next_pow2((int)std::max<int64_t>(n, 256));
     // vox_in: points | offsets[2] ; vox_out: ds points | box[6] | count
     const size_t b_pts = sizeof(double) * dim * (size_t)n;
     if (c.vox_in.reserve(b_pts + 16) || c.vox_out.reserve(b_pts + 6 * sizeof(double) + 16)) return ICPB200_ERR_CUDA;
@@ -506,7 +600,14 @@ int icpb200_voxel_downsample(const double* pts, int64_t n, int dim, double voxel
     cs.ds = c.vox_out.as<double>();
     cs.box = reinterpret_cast<double*>(c.vox_out.as<unsigned char>() + b_pts);
     cs.ds_n = reinterpret_cast<int*>(c.vox_out.as<unsigned char>() + b_pts + 6 * sizeof(double));
-    if ((rc = launch_voxel_clouds(cs, dim, voxel_size, sort_pad, c.stream))) return rc;
+    if (big) {
+        if (c.big_keys.reserve(sizeof(unsigned long long) * 2 * (size_t)n) || c.big_idx.reserve(sizeof(unsigned) * 2 * (size_t)n))
+            return ICPB200_ERR_CUDA;
+        rc = launch_big_voxel(cs, dim, voxel_size, c.big_keys.as<unsigned long long>(), c.big_idx.as<unsigned>(), n, c.stream);
+    } else {
+        rc = launch_voxel_clouds(cs, dim, voxel_size, sort_pad, c.stream);
+    }
+    if (rc) return rc;
     int m = 0;
     ICPB_CUDA(cudaMemcpyAsync(&m, cs.ds_n, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
     ICPB_CUDA(cudaStreamSynchronize(c.stream));

@@ -405,15 +405,31 @@ struct Loop {
     int n_s, n_t, n_tiles;
     double c0, c1, c2;       // recentring offset
     float ta;                // sum over axes of max |target - centre|
+    // grid mode: the target stays in global memory (rows of DIM doubles) behind a hash grid
+    const double* tg;
+    BigGrid grid;
 };
 
+// target point j: shared memory (tile-padded SoA) in brute mode, global memory in grid mode
+template <int DIM, bool GRID>
+__device__ __forceinline__ void tgt_at(const Loop<DIM>& L, int j, double& x, double& y, double& z) {
+    if (GRID) {
+        if (DIM == 2) { const double2 v = __ldg(reinterpret_cast<const double2*>(L.tg) + j); x = v.x; y = v.y; z = 0.0; }
+        else { x = __ldg(L.tg + 3 * (size_t)j); y = __ldg(L.tg + 3 * (size_t)j + 1); z = __ldg(L.tg + 3 * (size_t)j + 2); }
+    } else {
+        const int jp = pad_index(j);
+        x = L.tx[jp]; y = L.ty[jp]; z = DIM == 3 ? L.tz[jp] : 0.0;
+    }
+}
+
 // exact squared distance in fp64 between a point and target j
-template <int DIM>
+template <int DIM, bool GRID = false>
 __device__ __forceinline__ double dist2_64(const Loop<DIM>& L, double px, double py, double pz, int j) {
-    const int jp = pad_index(j);
-    const double dx = px - L.tx[jp], dy = py - L.ty[jp];
+    double qx, qy, qz;
+    tgt_at<DIM, GRID>(L, j, qx, qy, qz);
+    const double dx = px - qx, dy = py - qy;
     double d = dx * dx + dy * dy;
-    if (DIM == 3) { const double dz = pz - L.tz[jp]; d += dz * dz; }
+    if (DIM == 3) { const double dz = pz - qz; d += dz * dz; }
     return d;
 }
 
@@ -568,8 +584,73 @@ __device__ __forceinline__ void resolve_ambiguous(const Loop<DIM>& L, const CtaS
     }
 }
 
-// ---- K3: the kernel ----------------------------------------------------------------
+// ---- grid-mode nearest neighbour (big targets): exact fp64 ring search ------------------
+// One thread per source point that needs a decision.  Cells are visited ring by
+// ring around the query's cell; after ring r every unvisited target lies outside
+// the (2r+1)^2 block, i.e. at least `bound` away, so the search stops as soon as
+// the best distance found is below that bound.  The runner-up distance (needed by
+// the carry-over test) is min(second best seen, bound).  Queries that would need
+// more than kGridMaxRing rings fall back to a scan of the whole target.
+constexpr int kGridMaxRing = 24;
+
 template <int DIM>
+__device__ __forceinline__ void grid_nn(const Loop<DIM>& L, int n_todo) {
+    const BigGrid& G = L.grid;
+    for (int q = threadIdx.x; q < n_todo; q += kNT) {
+        const int i = L.todo[q];
+        const double px = L.cx[i], py = L.cy[i];
+        // the query may lie outside the target's bounding box: clamp its cell, keep exact bounds
+        const double fx = (px - G.lox) / G.h, fy = (py - G.loy) / G.h;
+        const int cxi = min(G.nx - 1, max(0, (int)floor(fx)));
+        const int cyi = min(G.ny - 1, max(0, (int)floor(fy)));
+        double best = INFINITY, second = INFINITY;
+        int bj = 0x7fffffff;
+        bool done = false;
+        double bound = 0.0;
+        for (int r = 0; r <= kGridMaxRing; ++r) {
+            const int x0 = cxi - r, x1 = cxi + r, y0 = cyi - r, y1 = cyi + r;
+            for (int y = max(y0, 0); y <= min(y1, G.ny - 1); ++y) {
+                const bool edge_row = (y == y0) || (y == y1);
+                const int xstep = edge_row ? 1 : max(2 * r, 1);
+                for (int x = x0; x <= x1; x += xstep) {
+                    if (x < 0 || x >= G.nx) continue;
+                    const unsigned b = big_cell_hash(x, y) & G.mask;
+                    const int beg = b ? G.start[b - 1] : 0, end = G.start[b];
+                    for (int e = beg; e < end; ++e) {
+                        const int2 cc = G.cell[e];
+                        if (cc.x != x || cc.y != y) continue;          // another cell hashed to this bucket
+                        const int j = G.items[e];
+                        const double d = dist2_64<DIM, true>(L, px, py, 0.0, j);
+                        if (d < best || (d == best && j < bj)) { second = best; best = d; bj = j; }
+                        else if (d < second) second = d;
+                    }
+                }
+            }
+            if ((x0 <= 0) && (y0 <= 0) && (x1 >= G.nx - 1) && (y1 >= G.ny - 1)) { done = true; bound = INFINITY; break; }
+            bound = INFINITY;
+            if (x0 > 0) bound = fmin(bound, px - (G.lox + x0 * G.h));
+            if (x1 < G.nx - 1) bound = fmin(bound, (G.lox + (x1 + 1) * G.h) - px);
+            if (y0 > 0) bound = fmin(bound, py - (G.loy + y0 * G.h));
+            if (y1 < G.ny - 1) bound = fmin(bound, (G.loy + (y1 + 1) * G.h) - py);
+            bound = bound * (1.0 - 1e-9) - 1e-12 * G.h;
+            if (bound > 0.0 && best < bound * bound) { done = true; break; }
+        }
+        if (!done) {                                   // far from everything: exact scan of the whole target
+            best = INFINITY; second = INFINITY; bj = 0x7fffffff; bound = INFINITY;
+            for (int j = 0; j < L.n_t; ++j) {
+                const double d = dist2_64<DIM, true>(L, px, py, 0.0, j);
+                if (d < best) { second = best; best = d; bj = j; }
+                else if (d < second) second = d;
+            }
+        }
+        L.match[i] = bj;
+        L.d2lb[i] = f32_down(fmin(sqrt(second), bound) * (1.0 - 1e-12));
+        L.moved[i] = 0.f;
+    }
+}
+
+// ---- K3: the kernel ----------------------------------------------------------------
+template <int DIM, bool GRID>
 __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     CtaShared& sh = *reinterpret_cast<CtaShared*>(smem);
@@ -608,7 +689,7 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
         const int cs = a.src_idx ? a.src_idx[p] : p;
         const int ct = a.tgt_idx ? a.tgt_idx[p] : p;
         const int n_s = a.s.ds_n[cs], n_t = a.t.ds_n[ct];
-        if (n_s <= 0 || n_t <= 0 || n_s > a.cap_s || n_t > a.cap_t) {
+        if (n_s <= 0 || n_t <= 0 || n_s > a.cap_s || (!GRID && n_t > a.cap_t)) {
             if (tid == 0) {
                 for (int k = 0; k < DIM * DIM; ++k) a.R_out[(size_t)p * DIM * DIM + k] = (k % (DIM + 1) == 0) ? 1.0 : 0.0;
                 for (int k = 0; k < DIM; ++k) a.t_out[(size_t)p * DIM + k] = 0.0;
@@ -625,6 +706,8 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
         const double* box = a.t.box + (size_t)ct * 6;
         L.n_s = n_s; L.n_t = n_t; L.n_tiles = (n_t + 31) / 32;
         L.c0 = 0.5 * (box[0] + box[3]); L.c1 = 0.5 * (box[1] + box[4]); L.c2 = 0.5 * (box[2] + box[5]);
+        L.tg = tgt_ds;
+        if (GRID) L.grid = a.grids[ct];
 
         if (tid == 0) {
             // icp.py:153-160
@@ -636,7 +719,10 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
             sh.bcast_i[0] = 0;                     // todo counter
         }
         // ---- stage the target: fp64 (tile-padded SoA) and recentred fp32
-        {
+        if (GRID) {
+            __syncthreads();                        // publishes sh.r_tot
+            L.ta = 0.f;
+        } else {
             float* f = reinterpret_cast<float*>(L.t32);
             constexpr int per = DIM == 2 ? 2 : 4;
             double ext[DIM];
@@ -706,7 +792,7 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
                 bool keep = false;
                 const float lb = L.d2lb[i];
                 if (lb >= 0.f) {
-                    const double d1 = sqrt(dist2_64<DIM>(L, L.cx[i], L.cy[i], DIM == 3 ? L.cz[i] : 0.0, L.match[i]));
+                    const double d1 = sqrt(dist2_64<DIM, GRID>(L, L.cx[i], L.cy[i], DIM == 3 ? L.cz[i] : 0.0, L.match[i]));
                     keep = d1 * (1.0 + 1e-9) + 1e-12 < (double)lb - (double)L.moved[i];
                 }
                 if (!keep) L.todo[atomicAdd(&sh.bcast_i[0], 1)] = (unsigned short)i;
@@ -714,13 +800,17 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
             __syncthreads();
             const int n_todo = sh.bcast_i[0];
             if (n_todo > 0) {
-                nn_dispatch<DIM>(L, sh, n_todo);
-                __syncthreads();
-                if (sh.amb_n > 0) resolve_ambiguous<DIM>(L, sh);
+                if (GRID) {
+                    grid_nn<DIM>(L, n_todo);
+                } else {
+                    nn_dispatch<DIM>(L, sh, n_todo);
+                    __syncthreads();
+                    if (sh.amb_n > 0) resolve_ambiguous<DIM>(L, sh);
+                }
             }
             if (tid == 0) {
                 const int n_chunks = (n_todo + 31) >> 5;
-                st_evals += (unsigned long long)n_chunks * 32ull * (unsigned long long)L.n_tiles * 32ull;
+                if (!GRID) st_evals += (unsigned long long)n_chunks * 32ull * (unsigned long long)L.n_tiles * 32ull;
                 st_swept += n_todo; st_kept += n_s - n_todo; st_iters += 1;
             }
             __syncthreads();
@@ -735,9 +825,11 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
 #pragma unroll
                 for (int k = 0; k < 10; ++k) acc[k] = 0.0;
                 for (int i = tid; i < n_s; i += kNT) {
-                    const int j = L.match[i], jp = pad_index(j);
+                    const int j = L.match[i];
                     const double px = L.cx[i], py = L.cy[i];
-                    const double dx = px - tx[jp], dy = py - ty[jp];
+                    double qx_, qy_, qz_;
+                    tgt_at<DIM, GRID>(L, j, qx_, qy_, qz_);
+                    const double dx = px - qx_, dy = py - qy_;
                     const double nd = sqrt(dx * dx + dy * dy);        // KDTree distance
                     if (gated && !(nd * nd < gate2)) continue;        // icp.py:184-185
                     const double nx = normals[2 * j], ny = normals[2 * j + 1];
@@ -769,9 +861,9 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
 #pragma unroll
                 for (int k = 0; k < 2 * DIM + 1; ++k) m[k] = 0.0;
                 for (int i = tid; i < n_s; i += kNT) {
-                    const int jp = pad_index(L.match[i]);
                     const double px = L.cx[i], py = L.cy[i], pz = DIM == 3 ? L.cz[i] : 0.0;
-                    const double qx = tx[jp], qy = ty[jp], qz = DIM == 3 ? tz[jp] : 0.0;
+                    double qx, qy, qz;
+                    tgt_at<DIM, GRID>(L, L.match[i], qx, qy, qz);
                     if (gated) {
                         const double dx = px - qx, dy = py - qy, dz = pz - qz;
                         const double nd = sqrt(dx * dx + dy * dy + dz * dz);
@@ -791,9 +883,9 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
 #pragma unroll
                 for (int k = 0; k < DIM * DIM; ++k) w[k] = 0.0;
                 for (int i = tid; i < n_s; i += kNT) {
-                    const int jp = pad_index(L.match[i]);
                     double ps[3] = {L.cx[i], L.cy[i], DIM == 3 ? L.cz[i] : 0.0};
-                    double qs[3] = {tx[jp], ty[jp], DIM == 3 ? tz[jp] : 0.0};
+                    double qs[3];
+                    tgt_at<DIM, GRID>(L, L.match[i], qs[0], qs[1], qs[2]);
                     if (gated) {
                         const double dx = ps[0] - qs[0], dy = ps[1] - qs[1], dz = ps[2] - qs[2];
                         const double nd = sqrt(dx * dx + dy * dy + dz * dz);
@@ -836,7 +928,8 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
             // icp.py:212 apply to ALL points; icp.py:215 error vs the OLD matches
             double e[1] = {0.0};
             for (int i = tid; i < n_s; i += kNT) {
-                const int jp = pad_index(L.match[i]);
+                double qx, qy, qz;
+                tgt_at<DIM, GRID>(L, L.match[i], qx, qy, qz);
                 const double x = L.cx[i], y = L.cy[i];
                 double nx_, ny_, nz_ = 0.0, mv;
                 if (DIM == 2) {
@@ -854,9 +947,9 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
                 L.cx[i] = nx_; L.cy[i] = ny_;
                 // movement since the last decision, rounded up
                 L.moved[i] = __fadd_ru(L.moved[i], __double2float_ru(sqrt(mv) * (1.0 + 1e-9)));
-                const double dx = tx[jp] - nx_, dy = ty[jp] - ny_;
+                const double dx = qx - nx_, dy = qy - ny_;
                 double d = dx * dx + dy * dy;
-                if (DIM == 3) { const double dz = tz[jp] - nz_; d += dz * dz; }
+                if (DIM == 3) { const double dz = qz - nz_; d += dz * dz; }
                 e[0] += d;
             }
             block_reduce<1, SumOp>(e, sh, phase);
@@ -914,27 +1007,31 @@ int launch_normals(const CloudSet& cs, int cap_t, int normal_k, double voxel, cu
     return ICPB200_OK;
 }
 
-int launch_icp_pairs(const IcpArgs& a, int dim, int n_ctas, size_t smem, cudaStream_t stream) {
-    if (dim == 2) {
-        ICPB_CUDA(cudaFuncSetAttribute(icp_pairs_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        icp_pairs_kernel<2><<<n_ctas, kNT, smem, stream>>>(a);
-    } else {
-        ICPB_CUDA(cudaFuncSetAttribute(icp_pairs_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        icp_pairs_kernel<3><<<n_ctas, kNT, smem, stream>>>(a);
-    }
+template <int DIM, bool GRID>
+static int launch_pairs_t(const IcpArgs& a, int n_ctas, size_t smem, cudaStream_t stream) {
+    ICPB_CUDA(cudaFuncSetAttribute(icp_pairs_kernel<DIM, GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    icp_pairs_kernel<DIM, GRID><<<n_ctas, kNT, smem, stream>>>(a);
     ICPB_LAUNCH_CHECK();
     return ICPB200_OK;
 }
 
-int icp_max_ctas_per_sm(int dim, size_t smem) {
+int launch_icp_pairs(const IcpArgs& a, int dim, bool grid, int n_ctas, size_t smem, cudaStream_t stream) {
+    if (grid) return launch_pairs_t<2, true>(a, n_ctas, smem, stream);        // grid mode is 2-D only
+    return dim == 2 ? launch_pairs_t<2, false>(a, n_ctas, smem, stream) : launch_pairs_t<3, false>(a, n_ctas, smem, stream);
+}
+
+int icp_max_ctas_per_sm(int dim, bool grid, size_t smem) {
     int n = 0;
     cudaError_t e;
-    if (dim == 2) {
-        cudaFuncSetAttribute(icp_pairs_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, icp_pairs_kernel<2>, kNT, smem);
+    if (grid) {
+        cudaFuncSetAttribute(icp_pairs_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, icp_pairs_kernel<2, true>, kNT, smem);
+    } else if (dim == 2) {
+        cudaFuncSetAttribute(icp_pairs_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, icp_pairs_kernel<2, false>, kNT, smem);
     } else {
-        cudaFuncSetAttribute(icp_pairs_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, icp_pairs_kernel<3>, kNT, smem);
+        cudaFuncSetAttribute(icp_pairs_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, icp_pairs_kernel<3, false>, kNT, smem);
     }
     if (e != cudaSuccess || n < 1) n = 1;
     return n;

@@ -28,6 +28,22 @@ struct CloudSet {
     unsigned char* is_tgt;  // per cloud: 1 if it is the target of a point-to-line pair
 };
 
+// Hash grid over one (downsampled) target cloud in global memory (grid mode).
+// Bucket b holds items[(b ? start[b-1] : 0) .. start[b]); cell[e] is the grid cell
+// of items[e] (several cells may share a bucket).
+struct BigGrid {
+    const int* start;
+    const int* items;
+    const int2* cell;
+    double h, lox, loy;
+    int nx, ny;
+    unsigned mask;             // buckets - 1 (power of two)
+};
+
+__host__ __device__ inline unsigned big_cell_hash(int cx, int cy) {
+    return ((unsigned)cx * 73856093u) ^ ((unsigned)cy * 19349663u);
+}
+
 struct IcpArgs {
     int n_pairs;
     CloudSet s, t;             // may describe the same set
@@ -53,6 +69,7 @@ struct IcpArgs {
     unsigned long long* stats; // [0] fp32 sweep pair evaluations executed, [1] points re-decided by the
                                // full fp64 scan, [2] iterations, [3] source points swept, [4] source points
                                // whose correspondence was carried over by the movement bound; may be nullptr
+    const BigGrid* grids;      // grid mode: one per target cloud (device array), else nullptr
     int* trace_match;          // optional: correspondences of the first trace_iters iterations (pair 0)
     int trace_iters;
     int trace_stride;
@@ -61,12 +78,20 @@ struct IcpArgs {
 size_t icp_pair_smem_bytes(int dim, int cap_s, int cap_t);
 size_t icp_voxel_smem_bytes(int sort_pad);
 size_t icp_normals_smem_bytes(int cap_t);
-int icp_max_ctas_per_sm(int dim, size_t smem);
+int icp_max_ctas_per_sm(int dim, bool grid, size_t smem);
 
 // used[c] = 1 for every referenced cloud, is_tgt[c] = 1 for p2l targets (device-side, from the idx arrays)
 int launch_mark_used(const IcpArgs& a, bool p2l, cudaStream_t stream);
 int launch_voxel_clouds(const CloudSet& cs, int dim, double voxel, int sort_pad, cudaStream_t stream);
 int launch_normals(const CloudSet& cs, int cap_t, int normal_k, double voxel, cudaStream_t stream);
-int launch_icp_pairs(const IcpArgs& a, int dim, int n_ctas, size_t smem, cudaStream_t stream);
+int launch_icp_pairs(const IcpArgs& a, int dim, bool grid, int n_ctas, size_t smem, cudaStream_t stream);
+
+// big-cloud kernels (icp_big.cu)
+int launch_big_voxel(const CloudSet& cs, int dim, double voxel, unsigned long long* key_buf, unsigned* idx_buf,
+                     long long total_points, cudaStream_t stream);
+int launch_big_grid(const CloudSet& cs, double cell_size, const long long* d_grid_off, const int* d_buckets,
+                    int* start_buf, int* items_buf, int2* cell_buf, BigGrid* d_grids, cudaStream_t stream);
+int launch_big_normals(const CloudSet& cs, const BigGrid* d_grids, int normal_k, long long max_points,
+                       cudaStream_t stream);
 
 }  // namespace icpb

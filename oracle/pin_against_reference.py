@@ -171,6 +171,35 @@ def main():
     add("few_iters", scans[0], scans[1], dict(cfg, max_iterations=3))
     np.savez_compressed(os.path.join(GOLDEN, "icp2d.npz"), **cases)
 
+    # ------------------------------------------ scan -> large submap (grid path)
+    print("scan -> 20-scan submap, p2p + gate (slam.py:103-108, 217-225)")
+    big_scans, big_poses = synth.make_sequence(22, world="room", seed=21, traj_seed=5)
+    raw_sub = np.vstack([synth.to_world_frame(big_scans[i], big_poses[i]) for i in range(20)])
+    submap = ref_icp.voxel_downsample(raw_sub, 0.04)                 # slam.py:108
+    check(same_bits(submap, icp_oracle.voxel_means(raw_sub, 0.04)), f"big voxel {len(raw_sub)} -> {len(submap)}")
+    big = {}
+    for tag, si, (ex, ey, eth) in (("a", 20, (0.05, -0.04, 0.01)), ("b", 21, (-0.08, 0.06, -0.02))):
+        x, y, a = big_poses[si]
+        rin = np.array([[np.cos(a + eth), -np.sin(a + eth)], [np.sin(a + eth), np.cos(a + eth)]])
+        tin = np.array([x + ex, y + ey])
+        kwb = dict(error_threshold=1e-10, max_iterations=150, voxel_size=0.04, R_init=rin, t_init=tin,
+                   method="point_to_point", max_corr_dist=1.5)
+        res = pin_icp_case(ref_icp, f"submap_big_{tag}", big_scans[si], submap, kwb)
+        big[f"{tag}/src"], big[f"{tag}/R_init"], big[f"{tag}/t_init"] = big_scans[si], rin, tin
+        for key, val in res.items():
+            big[f"{tag}/{key}"] = val
+    # the un-downsampled stack as the target: 21k raw points go through ICP's own voxel pass (icp.py:151)
+    resr = pin_icp_case(ref_icp, "submap_raw_target", big_scans[20], raw_sub,
+                        dict(error_threshold=1e-10, max_iterations=150, voxel_size=0.04, R_init=big["a/R_init"],
+                             t_init=big["a/t_init"], method="point_to_point", max_corr_dist=1.5))
+    for key, val in resr.items():
+        big[f"raw/{key}"] = val
+    resl = pin_icp_case(ref_icp, "submap_big_p2l", big_scans[20], submap,
+                        dict(cfg, R_init=big["a/R_init"], t_init=big["a/t_init"]))
+    for key, val in resl.items():
+        big[f"p2l/{key}"] = val
+    np.savez_compressed(os.path.join(GOLDEN, "submap.npz"), raw_sub=raw_sub, submap=submap, **big)
+
     # ---------------------------------------------------------- bresenham
     print("Bresenham cells (mapping.py:68-89)")
     rng = np.random.default_rng(11)

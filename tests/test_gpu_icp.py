@@ -156,7 +156,11 @@ def test_shim_prints_reference_line(capsys):
 
 def test_limits_and_errors():
     pts = np.random.default_rng(0).normal(size=(5000, 2))
-    with pytest.raises(RuntimeError, match="grid nearest-neighbour"):
+    with pytest.raises(RuntimeError, match="source clouds of more than 4096"):
         api.icp_batch([pts], [pts], 1e-7, 5, 0.01)
+    with pytest.raises(RuntimeError, match="nn_mode brute supports targets"):
+        api.icp_batch([pts[:100]], [pts], 1e-7, 5, 0.01, nn_mode="brute")
+    with pytest.raises(RuntimeError, match="2-D only"):
+        api.icp_batch([np.zeros((10, 3))], [np.random.default_rng(1).normal(size=(5000, 3))], 1e-7, 5, 0.01)
     with pytest.raises(RuntimeError):
         api.icp_batch([np.zeros((0, 2))], [pts[:10]], 1e-7, 5, 0.01)

@@ -102,3 +102,13 @@ def test_occupancy_fixture_py_oracle_and_batch():
                                         log_odds_min=-8.0, log_odds_max=8.0)
     cells = many.update_many(g["origins"], g["hits"], g["hit_off"], fast=True)
     assert same_bits(many.log_odds, g["snap_39"]) and cells > 0
+
+
+def test_submap_fixture():
+    g = load_golden("submap.npz")
+    assert same_bits(icp_oracle.voxel_means(g["raw_sub"], 0.04), g["submap"])
+    for tag in ("a", "b"):
+        R, t, err, iters, status = icp_oracle.register(
+            g[f"{tag}/src"], g["submap"], 1e-10, 150, 0.04, R_init=g[f"{tag}/R_init"], t_init=g[f"{tag}/t_init"],
+            method="point_to_point", max_corr_dist=1.5)
+        assert same_bits(R, g[f"{tag}/R"]) and same_bits(t, g[f"{tag}/t"]) and iters == int(g[f"{tag}/iters"])
