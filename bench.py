@@ -55,6 +55,7 @@ GRID_BOUNDS = (-102.4, 102.4, -102.4, 102.4)                  # 4096 x 4096 cell
 FMA_LANES_PER_SM = 128
 FLOP_PER_PAIR_EVAL_2D = 5
 FMA_INSTR_PER_PAIR_EVAL_2D = 4
+_REAL_STDOUT = None
 
 
 # --------------------------------------------------------------------------- helpers
@@ -215,7 +216,8 @@ def run_reference(args, rank, world):
                 cpu_baseline=dict(value=value, unit="registrations/s", cores=cores, kind="port", sample=last["sample"]),
                 e2e=dict(value=value, unit="registrations/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
-    print(json.dumps(line))
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
 
 
 # --------------------------------------------------------------------------- our arm
@@ -319,6 +321,9 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         t_max, e2e_max = float(red[0]), float(red[1])
 
+    occ = None
+    if not args.no_raycast:
+        occ = bench_raycast(args, lib, api, dev, local_rank, pk, rank, world)      # all ranks take part
     if rank != 0:
         return
     # ---- roofline of the per-pair kernel K3 (rank 0's batch, last timed step)
@@ -363,19 +368,30 @@ def run_ours(args, rank, world, local_rank):
                          d2h_bytes_per_step=int(d2h), api="icpb200_icp_pairs (host buffers, blocking)"),
                 gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, clocks=clocks,
                 wall_s_timed_region=wall, peaks_source=pk["source"])
-    if not args.no_raycast:
-        line["occupancy"] = bench_raycast(args, lib, api, dev, local_rank, pk)
+    if occ is not None:
+        line["occupancy"] = occ
+    if not args.no_extras:
+        line["extras"] = bench_extras(args, api)
     if args.no_icp_line:
         line = line["occupancy"]
-    print(json.dumps(line))
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
 
 
-def bench_raycast(args, lib, api, dev, local_rank, pk):
-    """C4: 2000 scans x 1080 rays into a 4096 x 4096 grid @ 5 cm (rank 0, one GPU)."""
+def bench_raycast(args, lib, api, dev, local_rank, pk, rank=0, world=1):
+    """C4: 2000 scans x 1080 rays into a 4096 x 4096 grid @ 5 cm.
+
+    Multi-GPU: the grid is tiled spatially (64x64-cell tiles, block-cyclic owner = tile % world);
+    every rank replays every scan clipped to its own tiles, then one NCCL all_reduce(SUM) over
+    the device grids reassembles the map (strong scaling: the job is fixed)."""
     import torch
+    import torch.distributed as dist
+    from icp_b200 import dist as icpd
     from utilities import OccupancyGrid2D
     origins, flat, off = build_c4(args.scans, seed=0)
     grid = OccupancyGrid2D(*GRID_BOUNDS, **GRID_CFG)
+    if world > 1:
+        grid._dev.set_shard(rank, world)
     d_org = torch.from_numpy(origins).to(dev)
     d_hits = torch.from_numpy(flat).to(dev)
     d_off = torch.from_numpy(off).to(dev)
@@ -389,12 +405,17 @@ def bench_raycast(args, lib, api, dev, local_rank, pk):
         for k in range(3 + steps):
             grid.reset()
             flush.zero_()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             if k == 3:
                 launches0 = api.launch_count()
             a.record(stream)
             grid._dev.update_dev(len(off) - 1, d_org.data_ptr(), d_hits.data_ptr(), d_off.data_ptr(), n_rays,
                                  stream.cuda_stream)
+            if world > 1:
+                dist.all_reduce(icpd.grid_device_tensor(grid._dev), op=dist.ReduceOp.SUM)
             b.record(stream)
             torch.cuda.synchronize()
             if k >= 3:
@@ -402,37 +423,122 @@ def bench_raycast(args, lib, api, dev, local_rank, pk):
     launches = api.launch_count() - launches0
     st = grid._dev.last_stats()
     sec = float(np.mean(ms)) / 1e3
-    # algorithmic bytes (BASELINE.md section 4): 16 B endpoint + 8 B per traversed cell + 8 B hit-cell RMW
-    alg_bytes = 16.0 * n_rays + 8.0 * st["traversed"] + 8.0 * st["hits"]
     e2e_t = []
     host_out = np.empty((grid.ny, grid.nx), dtype=np.float32)
     for k in range(1 + steps):
         grid.reset()
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         grid._dev.update(origins, flat, off)
+        if world > 1:
+            icpd.grid_allreduce_device(grid._dev)
         grid._dev.read(host_out)
         if k >= 1:
             e2e_t.append(time.perf_counter() - t0)
+    e2e_s = float(np.mean(e2e_t))
+    cells, hits_in = float(st["traversed"]), float(st["hits"])
+    if world > 1:
+        red = torch.tensor([sec, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        tot = torch.tensor([cells, hits_in], dtype=torch.float64, device=dev)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        sec, e2e_s, cells, hits_in = float(red[0]), float(red[1]), float(tot[0]), float(tot[1])
+    if rank != 0:
+        return None
+    # algorithmic bytes (BASELINE.md section 4): 16 B endpoint + 8 B per traversed cell + 8 B hit-cell RMW
+    alg_bytes = 16.0 * n_rays + 8.0 * cells + 8.0 * hits_in
     cpu = cpu_raycast_baseline(origins, flat, off, min(len(off) - 1, 60)) if not args.no_cpu else None
     return dict(metric="occupancy_rays_per_s", value=n_rays / sec, unit="rays/s", ms_per_step=sec * 1e3,
+                n_gpus=world, scaling="strong",
                 config=dict(workload=f"C4 occupancy log-odds raycast: {len(off) - 1} scans, {n_rays} rays, "
                                      f"{grid.nx}x{grid.ny} grid @ 0.05 m, campus world", **GRID_CFG,
-                            cells_per_ray=st["traversed"] / n_rays, tile_runs=st["runs"]),
-                e2e=dict(value=n_rays / float(np.mean(e2e_t)), unit="rays/s",
+                            cells_per_ray=cells / n_rays, tile_runs=st["runs"],
+                            sharding="64x64-cell tiles, owner = tile % n_gpus; one NCCL all_reduce(SUM) of the grids"),
+                e2e=dict(value=n_rays / e2e_s, unit="rays/s",
                          h2d_bytes_per_step=int(origins.nbytes + flat.nbytes + off.nbytes),
                          d2h_bytes_per_step=int(host_out.nbytes), api="icpb200_grid_update + icpb200_grid_read"),
                 gpu_launches=int(launches),
-                roofline=dict(bound="hbm", achieved=alg_bytes / sec / 1e9, peak=pk["hbm_gbs"], unit="GB/s",
-                              frac=alg_bytes / sec / 1e9 / pk["hbm_gbs"], traffic=None,
-                              kernel="occ_tile_apply (+ binning passes; whole update timed)",
+                roofline=dict(bound="hbm", achieved=alg_bytes / sec / 1e9 / world, peak=pk["hbm_gbs"], unit="GB/s",
+                              frac=alg_bytes / sec / 1e9 / world / pk["hbm_gbs"], traffic=None,
+                              kernel="occ_tile_apply (+ binning passes; whole update timed); per GPU",
                               algorithmic_bytes=alg_bytes, peak_basis=f"{pk['source']} HBM copy bandwidth"),
                 cpu_baseline=cpu, clocks=clk.summary())
+
+
+def bench_extras(args, api):
+    """Smaller configs of BASELINE.json on one GPU (rank 0): C1 teapot, C3 scan -> 50k submap."""
+    out = {}
+    golden = os.path.join(ROOT, "tests", "golden", "teapot.npz")
+    if os.path.exists(golden):                                  # C1: demos/teapot_icp_demo.py:58-65
+        g = np.load(golden)
+        kw = dict(error_threshold=1e-12, max_iterations=300, voxel_size=0.005, method="point_to_point")
+        api.icp_batch([g["moved"]], [g["teapot"]], **kw)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            one = api.icp_batch([g["moved"]], [g["teapot"]], **kw)
+        lat = (time.perf_counter() - t0) / 20
+        n = 2048
+        rng = np.random.default_rng(0)
+        srcs = []
+        for _ in range(n):                                      # random rigid perturbations (SURVEY 8(d) C1)
+            ax = rng.normal(size=3); ax /= np.linalg.norm(ax)
+            ang = rng.uniform(-0.4, 0.4)
+            K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+            rot = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+            srcs.append(g["teapot"] @ rot.T + rng.uniform(-0.2, 0.2, size=3))
+        api.icp_batch(srcs, [g["teapot"]] * n, **kw)
+        t0 = time.perf_counter()
+        res = api.icp_batch(srcs, [g["teapot"]] * n, **kw)
+        dt = time.perf_counter() - t0
+        out["C1_teapot_p2p_3d"] = dict(single_call_ms=lat * 1e3, iters=int(one["iters"][0]),
+                                       batch_pairs=n, batch_e2e_registrations_per_s=n / dt,
+                                       batch_mean_iters=float(res["iters"].mean()))
+    # C3: scans against one ~47k-voxel submap, p2p + max_corr_dist (slam.py:217-225)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from icp_b200 import synth
+    target = synth.submap_cloud(n_raw=52000, seed=3)
+    rng = np.random.default_rng(103)
+    clouds, R0, t0s = [target], [], []
+    while len(clouds) < 1 + 64:
+        c = target[rng.integers(len(target))]
+        near = target[np.hypot(*(target - c).T) < 12.0]
+        if len(near) < 1500:
+            continue
+        pts = near[rng.choice(len(near), 1080, replace=False)] + rng.normal(0, 0.01, size=(1080, 2))
+        th = rng.uniform(-0.3, 0.3)
+        rot = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        shift = rng.uniform(-5, 5, size=2)
+        clouds.append((pts - shift) @ rot)
+        a = th + 0.01
+        R0.append([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+        t0s.append(shift + [0.05, -0.04])
+    flat, off = synth.pack_ragged(clouds)
+    kw = dict(error_threshold=1e-10, max_iterations=150, voxel_size=0.04, method="point_to_point", max_corr_dist=1.5,
+              R_init=np.asarray(R0), t_init=np.asarray(t0s))
+    si, ti = np.arange(1, 65, dtype=np.int32), np.zeros(64, dtype=np.int32)
+    api.icp_pairs(flat, off, si, ti, **kw)
+    t0 = time.perf_counter()
+    res = api.icp_pairs(flat, off, si, ti, **kw)
+    dt = time.perf_counter() - t0
+    ks = api.icp_last_stats()
+    one_t = time.perf_counter()
+    api.icp_pairs(flat, off, si[:1], ti[:1], error_threshold=1e-10, max_iterations=150, voxel_size=0.04,
+                  method="point_to_point", max_corr_dist=1.5, R_init=np.asarray(R0)[:1], t_init=np.asarray(t0s)[:1])
+    one_t = time.perf_counter() - one_t
+    out["C3_scan_to_submap"] = dict(target_raw_points=len(target), pairs=64, e2e_registrations_per_s=64 / dt,
+                                    single_call_ms=one_t * 1e3, mean_iters=float(res["iters"].mean()),
+                                    voxel_kernel_ms=ks["voxel_kernel_ns"] / 1e6, grid_kernel_ms=ks["normals_kernel_ns"] / 1e6,
+                                    pair_kernel_ms=ks["pair_kernel_ns"] / 1e6,
+                                    note="the 52k-point target is re-downsampled and re-gridded inside every call, "
+                                         "as ICP() does (icp.py:150-151)")
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"])
@@ -441,11 +547,18 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-raycast", action="store_true", help="skip the occupancy (C4) leg")
     ap.add_argument("--no-icp-line", action="store_true", help="print only the occupancy object (profiling aid)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C1 / C3 extras")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: anything libraries print (NCCL's version banner, the
+    # shim's per-call ICP line) goes to stderr instead
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
