@@ -160,6 +160,12 @@ int icpb200_icp_trace(int dim, const double *src, int64_t n_src,
  * bench.py uses them for the FP32-FMA roofline. */
 int icpb200_icp_last_stats(int64_t *stats8);
 
+/* Profiling aid: SM cycles spent by thread 0 of the pair kernel in the five
+ * phases of an iteration (classify, nearest neighbour, accumulate + reduce,
+ * solve, apply + error), summed over iterations >= 8 of all pairs of the last
+ * call; out8[5] is the number of such iterations. */
+int icpb200_icp_phase_profile(int64_t *out8);
+
 /* Voxel-grid mean downsample (replaces utilities/icp.py:117-129).  `out`
  * needs n*dim doubles; *n_out receives the number of occupied voxels; rows
  * are in lexicographic voxel-index order like np.unique(axis=0). */

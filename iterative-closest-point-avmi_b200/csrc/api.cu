@@ -208,12 +208,31 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
         set_error("icp: %zu bytes of shared memory needed, device allows %d", smem, c.max_smem_optin);
         return ICPB200_ERR_LIMIT;
     }
-    if (c.queue.reserve(sizeof(unsigned)) || c.stats.reserve(8 * sizeof(unsigned long long))) return ICPB200_ERR_CUDA;
+    if (c.queue.reserve(4 * sizeof(unsigned)) || c.stats.reserve(16 * sizeof(unsigned long long))) return ICPB200_ERR_CUDA;
     a.queue = c.queue.as<unsigned>();
+    // two-phase schedule (see icp_kernel.h): worthwhile once the batch fills the machine
+    const int kPhaseCap = 12;
+    const bool two_phase = n_pairs >= 2 * c.sm_count && k.max_iterations > 2 * kPhaseCap;
+    a.phase_cap = two_phase ? kPhaseCap : 0;
+    a.resume = 0;
+    if (two_phase) {
+        const size_t np_ = (size_t)n_pairs, cs_ = (size_t)a.cap_s;
+        if (c.cont_cur.reserve(sizeof(double) * k.dim * cs_ * np_) || c.cont_match.reserve(sizeof(int) * cs_ * np_) ||
+            c.cont_d2lb.reserve(sizeof(float) * cs_ * np_) || c.cont_moved.reserve(sizeof(float) * cs_ * np_) ||
+            c.cont_scalar.reserve(sizeof(double) * 16 * np_) || c.cont_list.reserve(sizeof(int) * np_))
+            return ICPB200_ERR_CUDA;
+        a.cont_count = a.queue + 2;
+        a.cont_list = c.cont_list.as<int>();
+        a.cont_cur = c.cont_cur.as<double>();
+        a.cont_match = c.cont_match.as<int>();
+        a.cont_d2lb = c.cont_d2lb.as<float>();
+        a.cont_moved = c.cont_moved.as<float>();
+        a.cont_scalar = c.cont_scalar.as<double>();
+    }
     a.stats = c.stats.as<unsigned long long>();
     a.trace_match = tr.match; a.trace_iters = tr.iters; a.trace_stride = tr.stride;
-    ICPB_CUDA(cudaMemsetAsync(a.queue, 0, sizeof(unsigned), st));
-    ICPB_CUDA(cudaMemsetAsync(a.stats, 0, 8 * sizeof(unsigned long long), st));
+    ICPB_CUDA(cudaMemsetAsync(a.queue, 0, 4 * sizeof(unsigned), st));
+    ICPB_CUDA(cudaMemsetAsync(a.stats, 0, 16 * sizeof(unsigned long long), st));
     ICPB_CUDA(cudaMemsetAsync(a.s.used, 0, 2 * (size_t)s.n_clouds, st));
     if (!same_set) ICPB_CUDA(cudaMemsetAsync(a.t.used, 0, 2 * (size_t)t.n_clouds, st));
     a.grids = nullptr;
@@ -268,6 +287,14 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
     c.last_icp_stream = st;
     if (args_out) *args_out = a;
     if ((rc = launch_icp_pairs(a, k.dim, grid, n_ctas, smem, st))) return rc;
+    if (two_phase) {
+        // the handed-over pairs: one CTA per SM (shared memory request above half an SM forces it)
+        IcpArgs b = a;
+        b.resume = 1;
+        b.queue = a.queue + 1;
+        const size_t smem2 = std::max(smem, (size_t)c.max_smem_optin / 2 + 1024);
+        if ((rc = launch_icp_pairs(b, k.dim, grid, c.sm_count, std::min(smem2, (size_t)c.max_smem_optin), st))) return rc;
+    }
     ICPB_CUDA(cudaEventRecord(c.ev[3], st));
     return ICPB200_OK;
 }
@@ -341,7 +368,7 @@ void icpb200_shutdown(void) {
                       &c.aux_ds[0], &c.aux_ds[1], &c.aux_n[0], &c.aux_n[1], &c.aux_box[0], &c.aux_box[1],
                       &c.aux_nrm[0], &c.aux_nrm[1], &c.aux_flags[0], &c.aux_flags[1], &c.vox_in, &c.vox_out,
                       &c.big_keys, &c.big_idx, &c.grid_start, &c.grid_items, &c.grid_cell, &c.grid_desc, &c.grid_off,
-                      &c.grid_buckets};
+                      &c.grid_buckets, &c.cont_cur, &c.cont_match, &c.cont_d2lb, &c.cont_moved, &c.cont_scalar, &c.cont_list};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 4; ++i) if (c.ev[i]) { cudaEventDestroy(c.ev[i]); c.ev[i] = nullptr; }
     cudaStreamDestroy(c.stream);
@@ -568,6 +595,20 @@ int icpb200_icp_last_stats(int64_t* stats8) {
         if (cudaEventElapsedTime(&ms, c.ev[i], c.ev[i + 1]) == cudaSuccess) stats8[5 + i] = (int64_t)(ms * 1e6);
         else cudaGetLastError();
     }
+    return ICPB200_OK;
+}
+
+int icpb200_icp_phase_profile(int64_t* out8) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!out8) { set_error("icpb200_icp_phase_profile: null pointer"); return ICPB200_ERR_ARG; }
+    int rc = init_locked(-1);
+    if (rc) return rc;
+    Context& c = g_ctx;
+    for (int i = 0; i < 8; ++i) out8[i] = 0;
+    if (!c.stats.p) return ICPB200_OK;
+    cudaStream_t st = c.last_icp_stream ? c.last_icp_stream : c.stream;
+    ICPB_CUDA(cudaMemcpyAsync(out8, c.stats.as<int64_t>() + 8, 8 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    ICPB_CUDA(cudaStreamSynchronize(st));
     return ICPB200_OK;
 }
 

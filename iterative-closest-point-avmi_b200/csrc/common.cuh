@@ -53,6 +53,7 @@ struct Context {
     DevBuf aux_ds[2], aux_n[2], aux_box[2], aux_nrm[2], aux_flags[2];
     // big-cloud path: radix-sort scratch and hash grids
     DevBuf big_keys, big_idx, grid_start, grid_items, grid_cell, grid_desc, grid_off, grid_buckets;
+    DevBuf cont_cur, cont_match, cont_d2lb, cont_moved, cont_scalar, cont_list;
     cudaStream_t last_icp_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // K1 start | K2 start | K3 start | K3 end
     // voxel_downsample entry point

@@ -63,7 +63,7 @@ size_t icp_pair_smem_bytes(int dim, int cap_s, int cap_t) {
 size_t icp_voxel_smem_bytes(int sort_pad) { return align16(sizeof(CtaShared)) + (size_t)sort_pad * 12; }
 size_t icp_normals_smem_bytes(int cap_t) {
     return align16(sizeof(CtaShared)) + align16(sizeof(double) * 2 * (size_t)(cap_t + cap_t / 32)) +
-           sizeof(int) * (kGridCells + 1) + 4 + sizeof(unsigned short) * 3 * (size_t)cap_t + 16;
+           sizeof(int) * (kGridCells + 1) + 4 + sizeof(unsigned short) * 4 * (size_t)cap_t + 16;
 }
 
 // ---- K0: which clouds are referenced / are point-to-line targets -------------
@@ -166,10 +166,12 @@ constexpr int kKnnMaxRing = 12;        // beyond this ring the query falls back 
 template <bool REG>
 __device__ void knn_normals_pass(const double* tx, const double* ty, int n_t, int K, double* __restrict__ normals_out,
                                  const int* cell_start, const unsigned short* items, const ushort2* item_cell,
-                                 const CtaShared& sh) {
+                                 const CtaShared& sh, const unsigned short* list, int n_list) {
     const double h = sh.grid_h, lox = sh.lo_t[0], loy = sh.lo_t[1];
     const int gx = sh.grid_nx, gy = sh.grid_ny;
-    for (int i = threadIdx.x; i < n_t; i += kNT) {
+    const int count = list ? n_list : n_t;
+    for (int q = threadIdx.x; q < count; q += kNT) {
+        const int i = list ? (int)list[q] : q;
         const double px = tx[pad_index(i)], py = ty[pad_index(i)];
         const int cxi = min(gx - 1, max(0, (int)((px - lox) / h)));
         const int cyi = min(gy - 1, max(0, (int)((py - loy) / h)));
@@ -234,13 +236,112 @@ __device__ void knn_normals_pass(const double* tx, const double* ty, int n_t, in
     }
 }
 
+// Fast selection for K <= 16 and clouds of at most 4096 points: candidates are
+// ranked by a 32-bit key = fp32 distance^2 with its low 12 mantissa bits replaced by
+// the point index, kept in a 16-slot min/max bubble network (2 integer ops per
+// slot).  The keys only pre-select: the 16 survivors are re-evaluated in fp64 and
+// the first K are accepted as the exact (k+1)-NN set when they are separated from
+// everything else (the other survivors exactly, the rejected candidates through
+// the key's truncation bound).  Points that fail the test are redone by the exact
+// fp64 pass.  The normal itself is always computed from fp64 coordinates.
+__device__ void knn_normals_fast(const double* tx, const double* ty, int n_t, int K, double* __restrict__ normals_out,
+                                 const int* cell_start, const unsigned short* items, const ushort2* item_cell,
+                                 CtaShared& sh, unsigned short* redo) {
+    const double h = sh.grid_h, lox = sh.lo_t[0], loy = sh.lo_t[1];
+    const int gx = sh.grid_nx, gy = sh.grid_ny;
+    for (int i = threadIdx.x; i < n_t; i += kNT) {
+        const double px = tx[pad_index(i)], py = ty[pad_index(i)];
+        const int cxi = min(gx - 1, max(0, (int)((px - lox) / h)));
+        const int cyi = min(gy - 1, max(0, (int)((py - loy) / h)));
+        unsigned key[kKnnReg];
+#pragma unroll
+        for (int m = 0; m < kKnnReg; ++m) key[m] = 0xffffffffu;
+        bool done = false;
+        for (int r = 0; r <= kKnnMaxRing && !done; ++r) {
+            const int x0 = cxi - r, x1 = cxi + r, y0 = cyi - r, y1 = cyi + r;
+            for (int y = max(y0, 0); y <= min(y1, gy - 1); ++y) {
+                const bool edge_row = (y == y0) || (y == y1);
+                const int xstep = edge_row ? 1 : max(2 * r, 1);
+                for (int x = x0; x <= x1; x += xstep) {
+                    if (x < 0 || x >= gx) continue;
+                    const unsigned b = cell_hash(x, y);
+                    const int beg = b ? cell_start[b - 1] : 0, end = cell_start[b];
+                    for (int e = beg; e < end; ++e) {
+                        const ushort2 cc = item_cell[e];
+                        if (cc.x != x || cc.y != y) continue;
+                        const int j = items[e];
+                        const float dx = (float)(px - tx[pad_index(j)]), dy = (float)(py - ty[pad_index(j)]);
+                        unsigned kk = (__float_as_uint(fmaf(dy, dy, dx * dx)) & 0xfffff000u) | (unsigned)j;
+                        if (kk >= key[kKnnReg - 1]) continue;
+#pragma unroll
+                        for (int m = 0; m < kKnnReg; ++m) {
+                            const unsigned lo_ = min(key[m], kk);
+                            kk = max(key[m], kk);
+                            key[m] = lo_;
+                        }
+                    }
+                }
+            }
+            if ((x0 <= 0) && (y0 <= 0) && (x1 >= gx - 1) && (y1 >= gy - 1)) { done = true; break; }
+            unsigned kth = 0xffffffffu;
+#pragma unroll
+            for (int m = 0; m < kKnnReg; ++m) kth = (m == K - 1) ? key[m] : kth;
+            if (kth != 0xffffffffu) {
+                double bound = INFINITY;
+                if (x0 > 0) bound = fmin(bound, px - (lox + x0 * h));
+                if (x1 < gx - 1) bound = fmin(bound, (lox + (x1 + 1) * h) - px);
+                if (y0 > 0) bound = fmin(bound, py - (loy + y0 * h));
+                if (y1 < gy - 1) bound = fmin(bound, (loy + (y1 + 1) * h) - py);
+                bound = bound * (1.0 - 1e-9) - 1e-12 * h;
+                const double kth_ub = (double)__uint_as_float(kth | 0xfffu) * (1.0 + 1e-6);   // >= true distance^2
+                if (bound > 0.0 && kth_ub < bound * bound) done = true;
+            }
+        }
+        // exact re-evaluation of the survivors
+        double e_in = -1.0, e_out = INFINITY;          // largest of the first K, smallest of the rest
+        double mx = 0.0, my = 0.0;
+#pragma unroll
+        for (int m = 0; m < kKnnReg; ++m) {
+            if (key[m] == 0xffffffffu) continue;
+            const int j = (int)(key[m] & 0xfffu);
+            const double qx = tx[pad_index(j)], qy = ty[pad_index(j)];
+            const double d = (px - qx) * (px - qx) + (py - qy) * (py - qy);
+            if (m < K) { e_in = fmax(e_in, d); mx += qx; my += qy; }
+            else e_out = fmin(e_out, d);
+        }
+        const double lb_rejected = key[kKnnReg - 1] == 0xffffffffu
+                                       ? INFINITY
+                                       : (double)__uint_as_float(key[kKnnReg - 1] & 0xfffff000u) * (1.0 - 1e-6);
+        unsigned kthk = 0xffffffffu;
+#pragma unroll
+        for (int m = 0; m < kKnnReg; ++m) kthk = (m == K - 1) ? key[m] : kthk;
+        if (!done || kthk == 0xffffffffu || !(e_in < e_out) || !(e_in < lb_rejected)) {
+            redo[atomicAdd(&sh.bcast_i[1], 1)] = (unsigned short)i;     // exact pass decides
+            continue;
+        }
+        mx /= (double)K; my /= (double)K;
+        double sxx = 0.0, sxy = 0.0, syy = 0.0;
+#pragma unroll
+        for (int m = 0; m < kKnnReg; ++m)
+            if (m < K) {
+                const int j = (int)(key[m] & 0xfffu);
+                const double dx = tx[pad_index(j)] - mx, dy = ty[pad_index(j)] - my;
+                sxx += dx * dx; sxy += dx * dy; syy += dy * dy;
+            }
+        double nrm[2];
+        sym2_min_eigvec(sxx, sxy, syy, nrm);
+        normals_out[2 * i] = nrm[0];
+        normals_out[2 * i + 1] = nrm[1];
+    }
+}
+
 // ---- K2: normals: exact (k+1)-NN on a shared-memory uniform grid + 2x2 PCA -------
 // Restates utilities/icp.py:51-76.  All distances fp64; the neighbour set is
 // the exact (k+1)-NN (ties broken by lower index).  np.cov's 1/(K-1) scale is
 // dropped: it does not change the eigenvector.
 __device__ void cta_normals_2d(const double* tx, const double* ty, int n_t, int normal_k, double voxel,
                                double* __restrict__ normals_out, int* cell_start,
-                               unsigned short* items, ushort2* item_cell, CtaShared& sh) {
+                               unsigned short* items, ushort2* item_cell, unsigned short* redo, CtaShared& sh) {
     const int K = min(normal_k, n_t - 1) + 1;
     if (threadIdx.x == 0) {
         // cell edge: K voxel spacings.  Measured on 1080-beam scans (13 neighbours, 4 cm voxels): the
@@ -291,8 +392,18 @@ __device__ void cta_normals_2d(const double* tx, const double* ty, int n_t, int 
     }
     __syncthreads();
     // now bucket b holds items[(b ? cell_start[b-1] : 0) .. cell_start[b])
-    if (K <= kKnnReg) knn_normals_pass<true>(tx, ty, n_t, K, normals_out, cell_start, items, item_cell, sh);
-    else              knn_normals_pass<false>(tx, ty, n_t, K, normals_out, cell_start, items, item_cell, sh);
+    if (K <= kKnnReg && n_t <= 4096) {
+        if (threadIdx.x == 0) sh.bcast_i[1] = 0;
+        __syncthreads();
+        knn_normals_fast(tx, ty, n_t, K, normals_out, cell_start, items, item_cell, sh, redo);
+        __syncthreads();
+        const int n_redo = sh.bcast_i[1];
+        if (n_redo > 0) knn_normals_pass<true>(tx, ty, n_t, K, normals_out, cell_start, items, item_cell, sh, redo, n_redo);
+    } else if (K <= kKnnReg) {
+        knn_normals_pass<true>(tx, ty, n_t, K, normals_out, cell_start, items, item_cell, sh, nullptr, 0);
+    } else {
+        knn_normals_pass<false>(tx, ty, n_t, K, normals_out, cell_start, items, item_cell, sh, nullptr, 0);
+    }
 }
 
 __global__ void __launch_bounds__(kNT) normals_kernel(const CloudSet cs, int normal_k, int cap_t, double voxel) {
@@ -309,6 +420,7 @@ __global__ void __launch_bounds__(kNT) normals_kernel(const CloudSet cs, int nor
     int* cell_start = reinterpret_cast<int*>(rest);
     ushort2* item_cell = reinterpret_cast<ushort2*>(rest + sizeof(int) * (kGridCells + 1));
     unsigned short* items = reinterpret_cast<unsigned short*>(item_cell + cap_t);
+    unsigned short* redo = items + cap_t;
     const long long beg = cs.off[c];
     const double* ds = cs.ds + beg * 2;
     for (int j = threadIdx.x; j < n; j += kNT) {
@@ -319,7 +431,7 @@ __global__ void __launch_bounds__(kNT) normals_kernel(const CloudSet cs, int nor
         for (int k = 0; k < 3; ++k) { sh.lo_t[k] = cs.box[(size_t)c * 6 + k]; sh.hi_t[k] = cs.box[(size_t)c * 6 + 3 + k]; }
     }
     __syncthreads();
-    cta_normals_2d(tx, ty, n, normal_k, voxel, cs.nrm + beg * 2, cell_start, items, item_cell, sh);
+    cta_normals_2d(tx, ty, n, normal_k, voxel, cs.nrm + beg * 2, cell_start, items, item_cell, redo, sh);
 }
 
 // ---- K3: fp32 sweep --------------------------------------------------------------
@@ -490,38 +602,75 @@ __device__ __forceinline__ void nn_round(const Loop<DIM>& L, CtaShared& sh, int 
         if (pt[s] >= 0) decide<DIM>(L, sh, pt[s], sx[s], sy[s], sz[s], b2[s], bt[s]);
 }
 
-// Fewer chunks than warps: F warps share one chunk, each sweeping 1/F of the
-// target tiles; partial (best, runner-up, tile) triples are merged through
-// shared memory.  Keeps the per-iteration latency of nearly-converged pairs low.
+// Fewer chunks than warps (the nearly-converged regime): F warps share one chunk,
+// each sweeping 1/F of the target.  With one point per lane the sweep can afford
+// to track the argmin itself and the runner-up distance (3 more instructions per
+// pair), so the decision needs a single fp64 evaluation instead of a 32-point
+// tile scan: accept j1 when the fp32 runner-up, shrunk by the rounding slack, is
+// still farther than the exact distance to j1; otherwise the full fp64 scan decides.
 template <int DIM>
 __device__ __forceinline__ void nn_split(const Loop<DIM>& L, CtaShared& sh, int n_todo, int n_chunks, int F) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunk = w / F, part = w % F;
     const bool live = chunk < n_chunks;
-    float sx[1] = {0.f}, sy[1] = {0.f}, sz[1] = {0.f}, b1[1], b2[1];
-    int bt[1], pt = -1;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    int pt = -1;
     if (live) {
         const int q = chunk * 32 + lane;
         pt = q < n_todo ? (int)L.todo[q] : -1;
         const int i = max(pt, 0);
-        sx[0] = pt >= 0 ? (float)(L.cx[i] - L.c0) : 0.f;
-        sy[0] = pt >= 0 ? (float)(L.cy[i] - L.c1) : 0.f;
-        sz[0] = (DIM == 3 && pt >= 0) ? (float)(L.cz[i] - L.c2) : 0.f;
-        const int t0 = (int)((long long)part * L.n_tiles / F), t1 = (int)((long long)(part + 1) * L.n_tiles / F);
-        if (DIM == 2) sweep2d<1>(L.t32, t0, t1, sx, sy, b1, b2, bt);
-        else          sweep3d<1>(L.t32, t0, t1, sx, sy, sz, b1, b2, bt);
-        sh.part_b1[w][lane] = b1[0]; sh.part_b2[w][lane] = b2[0]; sh.part_bt[w][lane] = bt[0];
+        sx = pt >= 0 ? (float)(L.cx[i] - L.c0) : 0.f;
+        sy = pt >= 0 ? (float)(L.cy[i] - L.c1) : 0.f;
+        sz = (DIM == 3 && pt >= 0) ? (float)(L.cz[i] - L.c2) : 0.f;
+        const int j0 = (int)((long long)part * L.n_tiles / F) * 32, j1 = (int)((long long)(part + 1) * L.n_tiles / F) * 32;
+        float b1 = INFINITY, b2 = INFINITY;
+        int bj = j0;
+        if (DIM == 2) {
+            const float2* t = reinterpret_cast<const float2*>(L.t32);
+#pragma unroll 8
+            for (int j = j0; j < j1; ++j) {
+                const float2 q2 = t[j];
+                const float dx = sx - q2.x, dy = sy - q2.y;
+                const float d = fmaf(dy, dy, dx * dx);
+                const bool lt = d < b1;
+                b2 = lt ? b1 : fminf(b2, d);
+                bj = lt ? j : bj;
+                b1 = fminf(b1, d);
+            }
+        } else {
+#pragma unroll 8
+            for (int j = j0; j < j1; ++j) {
+                const float4 q4 = L.t32[j];
+                const float dx = sx - q4.x, dy = sy - q4.y, dz = sz - q4.z;
+                const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                const bool lt = d < b1;
+                b2 = lt ? b1 : fminf(b2, d);
+                bj = lt ? j : bj;
+                b1 = fminf(b1, d);
+            }
+        }
+        sh.part_b1[w][lane] = b1; sh.part_b2[w][lane] = b2; sh.part_bt[w][lane] = bj;
     }
     __syncthreads();
     if (live && part == 0 && pt >= 0) {
         float m1 = INFINITY, m2 = INFINITY;
-        int mt = 0;
+        int mj = 0;
         for (int f = 0; f < F; ++f) {
             const float p1 = sh.part_b1[w + f][lane], p2 = sh.part_b2[w + f][lane];
-            if (p1 < m1) { m2 = fminf(m1, p2); m1 = p1; mt = sh.part_bt[w + f][lane]; }
+            if (p1 < m1) { m2 = fminf(m1, p2); m1 = p1; mj = sh.part_bt[w + f][lane]; }
             else m2 = fminf(m2, p1);
         }
-        decide<DIM>(L, sh, pt, sx[0], sy[0], sz[0], m2, mt);
+        mj = min(mj, L.n_t - 1);                       // padding targets can only win if n_t == 0
+        const double d1 = sqrt(dist2_64<DIM>(L, L.cx[pt], L.cy[pt], DIM == 3 ? L.cz[pt] : 0.0, mj));
+        const float mag = fabsf(sx) + fabsf(sy) + (DIM == 3 ? fabsf(sz) : 0.f) + L.ta;
+        const double other = sqrt((double)m2) * (1.0 - 1.0e-6) - 1.8e-7 * (double)mag;
+        if (!(other > d1)) {
+            L.amb[atomicAdd(&sh.amb_n, 1)] = (unsigned short)pt;
+        } else {
+            L.match[pt] = mj;
+            L.d2lb[pt] = f32_down(other);
+            L.moved[pt] = 0.f;
+        }
     }
 }
 
@@ -678,13 +827,23 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
     double* tz = const_cast<double*>(L.tz);
     int phase = 0;
     unsigned long long st_evals = 0, st_amb = 0, st_iters = 0, st_swept = 0, st_kept = 0;   // thread 0 only
+    // thread 0's cycles per phase over iterations >= 8 (the nearly-converged regime): profiling aid
+    long long ph[6] = {0, 0, 0, 0, 0, 0}, ph_t = 0;
+    unsigned long long ph_iters = 0;
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) sh.pair = atomicAdd(a.queue, 1u);
+        // phase 1 takes pairs in order; phase 2 (a.resume) takes the pairs phase 1 handed over
+        if (tid == 0) {
+            const unsigned q = atomicAdd(a.queue, 1u);
+            const unsigned limit = a.resume ? *a.cont_count : (unsigned)a.n_pairs;
+            sh.pair = q < limit ? (a.resume ? (unsigned)a.cont_list[q] : q) : 0xffffffffu;
+            sh.bcast_i[2] = (int)q;                 // continuation slot when resuming
+        }
         __syncthreads();
+        if (sh.pair == 0xffffffffu) break;
         const int p = (int)sh.pair;
-        if (p >= a.n_pairs) break;
+        const int slot_in = sh.bcast_i[2];
 
         const int cs = a.src_idx ? a.src_idx[p] : p;
         const int ct = a.tgt_idx ? a.tgt_idx[p] : p;
@@ -777,6 +936,26 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
                 L.match[i] = 0;
             }
         }
+        double prev = INFINITY, err = INFINITY;
+        int iters = 0;
+        if (a.resume) {                            // continue where phase 1 stopped
+            const size_t so = (size_t)slot_in * a.cap_s;
+            const double* cc = a.cont_cur + so * DIM;
+            for (int i = tid; i < n_s; i += kNT) {
+                L.cx[i] = cc[i]; L.cy[i] = cc[(size_t)a.cap_s + i];
+                if (DIM == 3) L.cz[i] = cc[2 * (size_t)a.cap_s + i];
+                L.match[i] = a.cont_match[so + i];
+                L.d2lb[i] = a.cont_d2lb[so + i];
+                L.moved[i] = a.cont_moved[so + i];
+            }
+            const double* sc = a.cont_scalar + (size_t)slot_in * 16;
+            prev = sc[12]; err = sc[13]; iters = (int)sc[14];
+            __syncthreads();
+            if (tid == 0) {
+                for (int k = 0; k < DIM * DIM; ++k) sh.r_tot[k] = sc[k];
+                for (int k = 0; k < DIM; ++k) sh.t_tot[k] = sc[9 + k];
+            }
+        }
         __syncthreads();
 
         // ---- iterate (icp.py:175-220)
@@ -784,20 +963,49 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
         const bool gated = a.max_corr >= 0.0;
         const double gate2 = a.max_corr * a.max_corr;                 // icp.py:169
         const int min_inl = max(3, n_s / 10);                         // icp.py:186
-        double prev = INFINITY, err = INFINITY;
-        int iters = 0, status = ICPB200_MAX_ITER;
-        for (int it = 0; it < a.max_iter; ++it) {
+        int status = ICPB200_MAX_ITER;
+        bool handed_over = false;
+        for (int it = iters; it < a.max_iter; ++it) {
+            if (!a.resume && a.phase_cap > 0 && it == a.phase_cap) {
+                // not converged within the bulk budget: park the state, a dedicated launch finishes it
+                if (tid == 0) sh.bcast_i[3] = (int)atomicAdd(a.cont_count, 1u);
+                __syncthreads();
+                const int slot = sh.bcast_i[3];
+                const size_t so = (size_t)slot * a.cap_s;
+                double* cc = a.cont_cur + so * DIM;
+                for (int i = tid; i < n_s; i += kNT) {
+                    cc[i] = L.cx[i]; cc[(size_t)a.cap_s + i] = L.cy[i];
+                    if (DIM == 3) cc[2 * (size_t)a.cap_s + i] = L.cz[i];
+                    a.cont_match[so + i] = L.match[i];
+                    a.cont_d2lb[so + i] = L.d2lb[i];
+                    a.cont_moved[so + i] = L.moved[i];
+                }
+                if (tid == 0) {
+                    double* sc = a.cont_scalar + (size_t)slot * 16;
+                    for (int k = 0; k < DIM * DIM; ++k) sc[k] = sh.r_tot[k];
+                    for (int k = 0; k < DIM; ++k) sc[9 + k] = sh.t_tot[k];
+                    sc[12] = prev; sc[13] = err; sc[14] = (double)iters;
+                    a.cont_list[slot] = p;
+                }
+                handed_over = true;
+                break;
+            }
+            const bool prof = tid == 0 && it >= 8;
+            if (prof) ph_t = clock64();
             // ---- correspondences (icp.py:179): carry over where the movement bound allows
             for (int i = tid; i < n_s; i += kNT) {
                 bool keep = false;
                 const float lb = L.d2lb[i];
                 if (lb >= 0.f) {
-                    const double d1 = sqrt(dist2_64<DIM, GRID>(L, L.cx[i], L.cy[i], DIM == 3 ? L.cz[i] : 0.0, L.match[i]));
-                    keep = d1 * (1.0 + 1e-9) + 1e-12 < (double)lb - (double)L.moved[i];
+                    // dist(p, match) < D2 - moved, compared on squares (no fp64 sqrt), with rounding slack
+                    const double room = (double)lb - (double)L.moved[i] - 1e-12;
+                    const double d2 = dist2_64<DIM, GRID>(L, L.cx[i], L.cy[i], DIM == 3 ? L.cz[i] : 0.0, L.match[i]);
+                    keep = room > 0.0 && d2 * (1.0 + 4e-9) < room * room;
                 }
                 if (!keep) L.todo[atomicAdd(&sh.bcast_i[0], 1)] = (unsigned short)i;
             }
             __syncthreads();
+            if (prof) { const long long c = clock64(); ph[0] += c - ph_t; ph_t = c; }
             const int n_todo = sh.bcast_i[0];
             if (n_todo > 0) {
                 if (GRID) {
@@ -814,6 +1022,7 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
                 st_swept += n_todo; st_kept += n_s - n_todo; st_iters += 1;
             }
             __syncthreads();
+            if (prof) { const long long c = clock64(); ph[1] += c - ph_t; ph_t = c; }
             if (tid == 0) { st_amb += sh.amb_n; sh.amb_n = 0; sh.bcast_i[0] = 0; }
             if (a.trace_match && p == 0 && it < a.trace_iters)
                 for (int i = tid; i < n_s; i += kNT) a.trace_match[(size_t)it * a.trace_stride + i] = L.match[i];
@@ -824,30 +1033,46 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
                 double acc[10];
 #pragma unroll
                 for (int k = 0; k < 10; ++k) acc[k] = 0.0;
-                for (int i = tid; i < n_s; i += kNT) {
-                    const int j = L.match[i];
-                    const double px = L.cx[i], py = L.cy[i];
-                    double qx_, qy_, qz_;
-                    tgt_at<DIM, GRID>(L, j, qx_, qy_, qz_);
-                    const double dx = px - qx_, dy = py - qy_;
-                    const double nd = sqrt(dx * dx + dy * dy);        // KDTree distance
-                    if (gated && !(nd * nd < gate2)) continue;        // icp.py:184-185
-                    const double nx = normals[2 * j], ny = normals[2 * j + 1];
-                    const double c = ny * px - nx * py;               // icp.py:97
-                    const double b = -(nx * dx + ny * dy);            // icp.py:101
-                    acc[0] += c * c;  acc[1] += c * nx;  acc[2] += c * ny;
-                    acc[3] += nx * nx; acc[4] += nx * ny; acc[5] += ny * ny;
-                    acc[6] += c * b;  acc[7] += nx * b;  acc[8] += ny * b;
-                    acc[9] += 1.0;
+                for (int i0 = tid; i0 < n_s; i0 += 4 * kNT) {
+                    int jj[4];
+                    double2 nn[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {                     // the normals live in global memory (L2)
+                        const int i = i0 + u * kNT;
+                        jj[u] = i < n_s ? L.match[i] : 0;
+                        nn[u] = __ldg(reinterpret_cast<const double2*>(normals) + jj[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u * kNT;
+                        if (i >= n_s) continue;
+                        const double px = L.cx[i], py = L.cy[i];
+                        double qx_, qy_, qz_;
+                        tgt_at<DIM, GRID>(L, jj[u], qx_, qy_, qz_);
+                        const double dx = px - qx_, dy = py - qy_;
+                        if (gated) {
+                            const double nd = sqrt(dx * dx + dy * dy);    // KDTree distance, squared again (icp.py:184)
+                            if (!(nd * nd < gate2)) continue;             // icp.py:185
+                        }
+                        const double nx = nn[u].x, ny = nn[u].y;
+                        const double c = ny * px - nx * py;               // icp.py:97
+                        const double b = -(nx * dx + ny * dy);            // icp.py:101
+                        acc[0] += c * c;  acc[1] += c * nx;  acc[2] += c * ny;
+                        acc[3] += nx * nx; acc[4] += nx * ny; acc[5] += ny * ny;
+                        acc[6] += c * b;  acc[7] += nx * b;  acc[8] += ny * b;
+                        acc[9] += 1.0;
+                    }
                 }
                 block_reduce<10, SumOp>(acc, sh, phase);
                 if (gated && acc[9] < (double)min_inl) { status = ICPB200_FEW_INLIERS; break; }
+                if (prof) { const long long c = clock64(); ph[2] += c - ph_t; ph_t = c; }
                 if (tid == 0) {
                     const double ata[9] = {acc[0], acc[1], acc[2], acc[1], acc[3], acc[4], acc[2], acc[4], acc[5]};
                     const double atb[3] = {acc[6], acc[7], acc[8]};
                     double x[3];
                     if (solve3_lu(ata, atb, x) == 0) {
-                        const double ct_ = cos(x[0]), st_ = sin(x[0]);        // icp.py:110-114
+                        double ct_, st_;
+                        sincos(x[0], &st_, &ct_);                             // icp.py:110-114
                         sh.r[0] = ct_; sh.r[1] = -st_; sh.r[2] = st_; sh.r[3] = ct_;
                         sh.t[0] = x[1]; sh.t[1] = x[2];
                     } else {                                                  // icp.py:107-108
@@ -922,6 +1147,7 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
                 for (int k = 0; k < DIM * DIM; ++k) sh.r_tot[k] = nr[k];
                 for (int k = 0; k < DIM; ++k) sh.t_tot[k] = nt[k];
             }
+            if (prof) { const long long c = clock64(); ph[3] += c - ph_t; ph_t = c; }
             __syncthreads();
             for (int k = 0; k < DIM * DIM; ++k) rr[k] = sh.r[k];
             for (int k = 0; k < DIM; ++k) tt[k] = sh.t[k];
@@ -946,13 +1172,14 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
                 }
                 L.cx[i] = nx_; L.cy[i] = ny_;
                 // movement since the last decision, rounded up
-                L.moved[i] = __fadd_ru(L.moved[i], __double2float_ru(sqrt(mv) * (1.0 + 1e-9)));
+                L.moved[i] = __fadd_ru(L.moved[i], __fmul_ru(__fsqrt_ru(__double2float_ru(mv)), 1.000001f));
                 const double dx = qx - nx_, dy = qy - ny_;
                 double d = dx * dx + dy * dy;
                 if (DIM == 3) { const double dz = qz - nz_; d += dz * dz; }
                 e[0] += d;
             }
             block_reduce<1, SumOp>(e, sh, phase);
+            if (prof) { const long long c = clock64(); ph[4] += c - ph_t; ph_t = c; ++ph_iters; }
             err = e[0] / (double)n_s;
             ++iters;
             const double delta = fabs(prev - err);                   // icp.py:216
@@ -960,7 +1187,7 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
             prev = err;
         }
         __syncthreads();
-        if (tid == 0) {
+        if (tid == 0 && !handed_over) {
             for (int k = 0; k < DIM * DIM; ++k) a.R_out[(size_t)p * DIM * DIM + k] = sh.r_tot[k];
             for (int k = 0; k < DIM; ++k) a.t_out[(size_t)p * DIM + k] = sh.t_tot[k];
             a.err_out[p] = err;
@@ -975,6 +1202,8 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
         atomicAdd(&a.stats[2], st_iters);
         atomicAdd(&a.stats[3], st_swept);
         atomicAdd(&a.stats[4], st_kept);
+        for (int k = 0; k < 5; ++k) atomicAdd(&a.stats[8 + k], (unsigned long long)ph[k]);
+        atomicAdd(&a.stats[13], ph_iters);
     }
 }
 

@@ -70,6 +70,17 @@ struct IcpArgs {
                                // full fp64 scan, [2] iterations, [3] source points swept, [4] source points
                                // whose correspondence was carried over by the movement bound; may be nullptr
     const BigGrid* grids;      // grid mode: one per target cloud (device array), else nullptr
+    // two-phase schedule: the bulk launch hands pairs that need more than phase_cap iterations to a
+    // second launch (resume = 1) that runs one CTA per SM, so the long tail does not share its SM
+    int phase_cap;             // <= 0: single launch
+    int resume;
+    unsigned int* cont_count;  // pairs handed over
+    int* cont_list;            // [slot] -> pair
+    double* cont_cur;          // [slot][dim][cap_s]
+    int* cont_match;           // [slot][cap_s]
+    float* cont_d2lb;
+    float* cont_moved;
+    double* cont_scalar;       // [slot][16]: r_tot(9) t_tot(3) prev err iters
     int* trace_match;          // optional: correspondences of the first trace_iters iterations (pair 0)
     int trace_iters;
     int trace_stride;

@@ -164,3 +164,19 @@ def test_limits_and_errors():
         api.icp_batch([np.zeros((10, 3))], [np.random.default_rng(1).normal(size=(5000, 3))], 1e-7, 5, 0.01)
     with pytest.raises(RuntimeError):
         api.icp_batch([np.zeros((0, 2))], [pts[:10]], 1e-7, 5, 0.01)
+
+
+def test_two_phase_schedule_is_bitwise_identical():
+    """Batches of >= 2 x SM-count pairs hand slow pairs to a second launch after 12
+    iterations; the results must equal those of small single-launch batches bit for bit."""
+    scans, _ = synth.make_sequence(40, world="room", seed=6)
+    flat, off = synth.pack_ragged(scans)
+    rng = np.random.default_rng(0)
+    si = rng.integers(0, 38, size=640).astype(np.int32)
+    ti = (si + rng.integers(1, 3, size=640)).astype(np.int32)
+    big = api.icp_pairs(flat, off, si, ti, **CFG)
+    assert big["iters"].max() > 12 and (big["status"] == 0).sum() > 500
+    for lo in range(0, 640, 128):
+        part = api.icp_pairs(flat, off, si[lo:lo + 128], ti[lo:lo + 128], **CFG)
+        for key in ("R", "t", "error", "prev_error", "iters", "status"):
+            assert part[key].tobytes() == big[key][lo:lo + 128].tobytes(), (key, lo)
