@@ -381,7 +381,7 @@ def run_ours(args, rank, world, local_rank):
 def bench_raycast(args, lib, api, dev, local_rank, pk, rank=0, world=1):
     """C4: 2000 scans x 1080 rays into a 4096 x 4096 grid @ 5 cm.
 
-    Multi-GPU: the grid is tiled spatially (64x64-cell tiles, block-cyclic owner = tile % world);
+    Multi-GPU: the grid is tiled spatially (32x32-cell tiles, block-cyclic owner = tile % world);
     every rank replays every scan clipped to its own tiles, then one NCCL all_reduce(SUM) over
     the device grids reassembles the map (strong scaling: the job is fixed)."""
     import torch
@@ -454,7 +454,7 @@ def bench_raycast(args, lib, api, dev, local_rank, pk, rank=0, world=1):
                 config=dict(workload=f"C4 occupancy log-odds raycast: {len(off) - 1} scans, {n_rays} rays, "
                                      f"{grid.nx}x{grid.ny} grid @ 0.05 m, campus world", **GRID_CFG,
                             cells_per_ray=cells / n_rays, tile_runs=st["runs"],
-                            sharding="64x64-cell tiles, owner = tile % n_gpus; one NCCL all_reduce(SUM) of the grids"),
+                            sharding="32x32-cell tiles, owner = tile % n_gpus; one NCCL all_reduce(SUM) of the grids"),
                 e2e=dict(value=n_rays / e2e_s, unit="rays/s",
                          h2d_bytes_per_step=int(origins.nbytes + flat.nbytes + off.nbytes),
                          d2h_bytes_per_step=int(host_out.nbytes), api="icpb200_grid_update + icpb200_grid_read"),

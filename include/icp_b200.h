@@ -181,7 +181,7 @@ void *icpb200_grid_create(int nx, int ny, double min_x, double min_y, double res
 void icpb200_grid_destroy(void *grid);
 
 /* Multi-GPU spatial sharding: this process updates only the tiles t with
- * t % world == rank (block-cyclic over 64x64-cell tiles); all other cells
+ * t % world == rank (block-cyclic over 32x32-cell tiles); all other cells
  * stay 0, so an element-wise sum over ranks reassembles the map. */
 int icpb200_grid_set_shard(void *grid, int rank, int world);
 

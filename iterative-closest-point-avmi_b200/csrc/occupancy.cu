@@ -33,11 +33,11 @@ namespace icpb {
 
 constexpr int TS = kOccTile;                 // tile edge in cells
 constexpr int TCELLS = TS * TS;
-constexpr int kOccNT = 512;
+constexpr int kOccNT = 256;
 constexpr unsigned kHitUnit = 1u << 20;      // counter word: hits << 20 | misses
 constexpr unsigned kMissMask = kHitUnit - 1u;
 
-constexpr size_t kOccSmem = 3 * sizeof(float) * TCELLS + (2 * sizeof(unsigned) + sizeof(unsigned short)) * kOccMaxChunkScans;
+constexpr size_t kOccSmem = sizeof(float) * TCELLS * (1 + 8 /* kOccBatch */) + 3 * sizeof(unsigned) * 256 /* kOccList */;
 
 // A run is self-contained: the tile kernel needs neither the ray's endpoint nor
 // the scan's origin to walk it (no dependent loads on its critical path).
@@ -298,6 +298,12 @@ struct ApplyArgs {
 
 __device__ __forceinline__ float chain(float x, unsigned m, unsigned k, double l_hit, double l_miss,
                                        float lo, float hi) {
+    // steady state of free space: the cell already sits on the lower clamp and only misses arrive
+    // (every add keeps it at or below the clamp, the final clamp returns it) -- likewise at the top
+    if (m == 0u) {
+        if (l_miss < 0.0 && x <= lo) return lo;
+        if (l_miss > 0.0 && x >= hi) return hi;
+    }
     // mapping.py:129 -- m hits, each x = f32(f64(x) + l_hit)
     for (unsigned i = 0; i < m; ++i) {
         x = (float)((double)x + l_hit);
@@ -320,112 +326,88 @@ __device__ __forceinline__ float chain(float x, unsigned m, unsigned k, double l
     return fminf(fmaxf(x, lo), hi);           // mapping.py:141
 }
 
-// One CTA per tile.  For every scan that touches the tile (in scan order):
-//   count  a task = 32 consecutive runs (one per lane) x one quarter of their
-//          common step window; the warp walks it in lock step over the ray
-//          step index n.  Rays of one scan share their origin, so neighbouring
-//          lanes sit on the same cell for long stretches: each maximal group of
-//          equal neighbours issues ONE shared atomicAdd carrying the group size
-//          (no same-address conflicts, far fewer atomics near the sensor, and
-//          nothing waits on a return value).
-//   apply  every thread scans 8 counters (two 128-bit loads); non-zero ones
-//          run the fp64->fp32 add chain and the clamp, and are zeroed.
-// The counters are double buffered: scan s+1 is counted while scan s is
-// applied, so there is one barrier per scan.
+// One CTA per tile; the tile stays in shared memory while ITS scans are replayed in order.
+// Scans are taken kOccBatch at a time, each with its own counter plane, so that one pair
+// of barriers covers a whole batch:
+//   count  a task = 32 consecutive runs of one scan (one per lane) x one window of their
+//          common step range; the warp walks it in lock step over the ray step index n.
+//          Rays of one scan share their origin, so neighbouring lanes sit on the same cell
+//          for long stretches: each maximal group of equal neighbours issues ONE shared
+//          atomicAdd carrying the group size (no same-address conflicts, far fewer atomics
+//          near the sensor, nothing waits on a return value).  All tasks of the batch are
+//          independent, so the warps stay busy instead of waiting on a per-scan barrier.
+//   apply  every thread owns four cells: it keeps them in registers and runs, scan by scan
+//          in order, the fp64->fp32 add chain + clamp for the non-zero counters.
 constexpr int kWin = 16;                       // lock-step block (unrolled)
+constexpr int kOccBatch = 8;                   // scans per barrier pair
+constexpr int kOccList = 256;                  // scans compacted per pass over the offsets row
 
 // Shared-memory slot of local cell idx = y * TS + x.  Rays of one scan that are
 // x-major sit in the same column at a given step; without the swizzle their
-// counters would all fall into one bank (row stride TS = 64 words).
-__device__ __forceinline__ int swz(int idx) { return idx ^ ((idx >> 6) & 31); }
+// counters would all fall into one bank.
+__device__ __forceinline__ int swz(int idx) { return idx ^ ((idx / TS) & 31); }
 
-__device__ __forceinline__ void occ_count_scan(const ApplyArgs& a, unsigned beg, unsigned end, unsigned* cnt,
-                                               int warp, int lane) {
-    const unsigned n_chunks = (end - beg + 31u) >> 5;
+// One task = 32 consecutive runs of the batch (the runs of a tile are contiguous across its
+// scans, so a warp is full even when single scans bring only a few runs).  `bounds` are the
+// run-index boundaries between the batch's scans; lane e belongs to counter plane
+// #{bounds <= e}.  Lanes are merged only with neighbours of the same scan.
+__device__ __forceinline__ void occ_count_task(const ApplyArgs& a, unsigned e, unsigned end, const unsigned* bounds,
+                                               int n_bounds, unsigned* cnt, int lane) {
     const unsigned above = lane == 31 ? 0u : (0xffffffffu << (lane + 1));
-    for (unsigned task = warp; task < n_chunks * a.split; task += kOccNT / 32) {
-        const unsigned e = beg + (task / a.split) * 32u + lane;
-        const int q = (int)(task % a.split);
-        int n0 = 0x7fffffff, nend = 0, j0 = 0, idx0 = 0, dmaj = 1, dmin = 0;
-        // a tile's runs are contiguous across its scans: pull the records two thousand runs ahead into L2
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.runs + e + 2048));
-        if (e < end) {
-            const int4 ra = __ldg(reinterpret_cast<const int4*>(a.runs + e));
-            const int2 rb = __ldg(reinterpret_cast<const int2*>(a.runs + e) + 2);
-            if (ra.z == 0) {                                       // hit: one add of the hit unit
-                if (q == 0) {
-                    const unsigned old = atomicAdd(&cnt[swz(ra.w & 0xffff)], kHitUnit);
-                    if ((old >> 20) == 4095u) *a.error_flag = 1;
-                }
-            } else {
-                n0 = ra.x; j0 = ra.y; nend = ra.x + ra.z; idx0 = ra.w; dmaj = rb.x; dmin = rb.y;
-            }
-        }
-        const int nmin = (int)__reduce_min_sync(0xffffffffu, (unsigned)n0);
-        const int nmax = (int)__reduce_max_sync(0xffffffffu, (unsigned)nend);
-        if (nmax <= nmin) continue;                                // no miss runs in this chunk
-        const int win = (nmax - nmin + a.split - 1) / a.split;
-        const int lo = nmin + q * win, hi = min(lo + win, nmax);
-        const int s0 = max(n0, lo), s1 = min(nend, hi);            // this lane's steps in the window
-        int idx = 0, step_maj = 0, step_both = 0, d = 0, inc = 0, dec = 0;
-        if (s0 < s1) {
-            const int maj = (idx0 & kRunXMajor) ? ((idx0 & kRunMajPos) ? 1 : -1) : ((idx0 & kRunMajPos) ? TS : -TS);
-            const int mnr = (idx0 & kRunXMajor) ? ((idx0 & kRunMinPos) ? TS : -TS) : ((idx0 & kRunMinPos) ? 1 : -1);
-            int j = j0;
-            if (s0 > n0) {                                         // enter mid-run: closed form (bres.cuh)
-                const unsigned long long num = 2ull * (unsigned)s0 * (unsigned)dmin + (unsigned)dmaj - 1u;
-                j = (num >> 32) == 0 ? (int)((unsigned)num / (2u * (unsigned)dmaj))
-                                     : (int)(num / (2ull * (unsigned)dmaj));
-            }
-            idx = (idx0 & 0xffff) + (s0 - n0) * maj + (j - j0) * mnr;
-            step_maj = maj; step_both = maj + mnr;
-            inc = 2 * dmin; dec = 2 * dmaj;
-            d = (int)((2ll * s0 + 2) * dmin - (long long)dec * j - dmaj);   // RunWalker::start
-        }
-        for (int b = lo; b < hi; b += kWin) {
-            // cells of this lane for the next kWin steps (pure ALU), then the votes + atomics
-            int cell[kWin];
-            unsigned actbits = 0;
-#pragma unroll
-            for (int k = 0; k < kWin; ++k) {
-                const int n = b + k;
-                const bool act = n >= s0 && n < s1 && n < hi;
-                cell[k] = idx;
-                actbits |= act ? (1u << k) : 0u;
-                if (act) { const bool m = d > 0; idx += m ? step_both : step_maj; d += inc - (m ? dec : 0); }
-            }
-#pragma unroll
-            for (int k = 0; k < kWin; ++k) {
-                const bool act = (actbits >> k) & 1u;
-                const unsigned am = __ballot_sync(0xffffffffu, act);
-                if (am == 0u) continue;
-                const int prev = __shfl_up_sync(0xffffffffu, cell[k], 1);
-                const bool prev_act = lane > 0 && ((am >> (lane - 1)) & 1u);
-                const bool lead = act && !(prev_act && prev == cell[k]);
-                const unsigned lm = __ballot_sync(0xffffffffu, lead);
-                if (lead) {
-                    // group = this lane and the active lanes right after it on the same cell
-                    const unsigned stop = (lm | ~am) & above;
-                    const int nxt = stop ? __ffs(stop) - 1 : 32;
-                    atomicAdd(&cnt[swz(cell[k])], (unsigned)(nxt - lane));   // result unused
-                }
-            }
+    int n0 = 0x7fffffff, nend = 0, j0 = 0, idx0 = 0, dmaj = 1, dmin = 0, plane = 0;
+    // a tile's runs are contiguous across its scans: pull the records far ahead into L2
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.runs + e + 2048));
+    if (e < end) {
+        for (int i = 0; i < n_bounds; ++i) plane += e >= bounds[i];
+        const int4 ra = __ldg(reinterpret_cast<const int4*>(a.runs + e));
+        const int2 rb = __ldg(reinterpret_cast<const int2*>(a.runs + e) + 2);
+        if (ra.z == 0) {                                           // hit: one add of the hit unit
+            const unsigned old = atomicAdd(&cnt[plane * TCELLS + swz(ra.w & 0xffff)], kHitUnit);
+            if ((old >> 20) == 4095u) *a.error_flag = 1;
+        } else {
+            n0 = ra.x; j0 = ra.y; nend = ra.x + ra.z; idx0 = ra.w; dmaj = rb.x; dmin = rb.y;
         }
     }
-}
-
-__device__ __forceinline__ void occ_apply_scan(const ApplyArgs& a, float* tile, unsigned* cnt, bool virgin_fix, int tid) {
-    for (int c0 = tid * 4; c0 < TCELLS; c0 += kOccNT * 4) {
-        const uint4 c4 = *reinterpret_cast<const uint4*>(&cnt[c0]);
-        if ((c4.x | c4.y | c4.z | c4.w) == 0u) continue;
-        const unsigned cv[4] = {c4.x, c4.y, c4.z, c4.w};
-        *reinterpret_cast<uint4*>(&cnt[c0]) = make_uint4(0u, 0u, 0u, 0u);
+    // Every lane walks its own run from its first cell (local step k); a run never exceeds TS
+    // cells, so two unrolled blocks cover it.  Lanes that sit on the same cell of the same scan
+    // in the same step -- always the case near the sensor, where all rays start together --
+    // are merged with their neighbours into one add.
+    const int len = nend - n0 > 0 && n0 != 0x7fffffff ? nend - n0 : 0;
+    const int maxlen = (int)__reduce_max_sync(0xffffffffu, (unsigned)len);
+    if (maxlen == 0) return;                                       // no miss runs in this chunk
+    unsigned* my = cnt + plane * TCELLS;
+    const int prev_plane = __shfl_up_sync(0xffffffffu, plane, 1);
+    const bool same_scan = lane > 0 && prev_plane == plane;
+    int idx = idx0 & 0xffff, step_maj = 0, step_both = 0, d = 0, inc = 0, dec = 0;
+    if (len > 0) {
+        const int maj = (idx0 & kRunXMajor) ? ((idx0 & kRunMajPos) ? 1 : -1) : ((idx0 & kRunMajPos) ? TS : -TS);
+        const int mnr = (idx0 & kRunXMajor) ? ((idx0 & kRunMinPos) ? TS : -TS) : ((idx0 & kRunMinPos) ? 1 : -1);
+        step_maj = maj; step_both = maj + mnr;
+        inc = 2 * dmin; dec = 2 * dmaj;
+        d = (int)((2ll * n0 + 2) * dmin - (long long)dec * j0 - dmaj);      // RunWalker::start
+    }
+    for (int b = 0; b < maxlen; b += kWin) {
+        // cells of this lane for the next kWin steps (pure ALU), then the votes + atomics
+        int cell[kWin];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (cv[k]) {
-                float x = tile[c0 + k];
-                if (virgin_fix && x == 0.0f) x = a.clamp0;
-                tile[c0 + k] = chain(x, cv[k] >> 20, cv[k] & kMissMask, a.l_hit, a.l_miss, a.lo, a.hi);
+        for (int k = 0; k < kWin; ++k) {
+            cell[k] = idx;
+            if (b + k < len) { const bool m = d > 0; idx += m ? step_both : step_maj; d += inc - (m ? dec : 0); }
+        }
+#pragma unroll
+        for (int k = 0; k < kWin; ++k) {
+            const bool act = b + k < len;
+            const unsigned am = __ballot_sync(0xffffffffu, act);
+            if (am == 0u) break;                                   // runs only get shorter
+            const int prev = __shfl_up_sync(0xffffffffu, cell[k], 1);
+            const bool prev_act = same_scan && ((am >> (lane - 1)) & 1u);
+            const bool lead = act && !(prev_act && prev == cell[k]);
+            const unsigned lm = __ballot_sync(0xffffffffu, lead);
+            if (lead) {
+                // group = this lane and the active lanes right after it on the same cell of the same scan
+                const unsigned stop = (lm | ~am) & above;
+                const int nxt = stop ? __ffs(stop) - 1 : 32;
+                atomicAdd(&my[swz(cell[k])], (unsigned)(nxt - lane));        // result unused
             }
         }
     }
@@ -434,11 +416,10 @@ __device__ __forceinline__ void occ_apply_scan(const ApplyArgs& a, float* tile, 
 __global__ void __launch_bounds__(kOccNT) occ_tile_apply(const ApplyArgs a) {
     extern __shared__ __align__(16) unsigned char occ_smem[];
     float* tile = reinterpret_cast<float*>(occ_smem);
-    unsigned* cnt0 = reinterpret_cast<unsigned*>(occ_smem + sizeof(float) * TCELLS);
-    unsigned* cnt1 = cnt0 + TCELLS;
-    unsigned* scan_beg = cnt1 + TCELLS;
-    unsigned* scan_end = scan_beg + kOccMaxChunkScans;
-    unsigned short* scan_list = reinterpret_cast<unsigned short*>(scan_end + kOccMaxChunkScans);
+    unsigned* cnt = reinterpret_cast<unsigned*>(occ_smem + sizeof(float) * TCELLS);      // [kOccBatch][TCELLS]
+    unsigned* lst_beg = cnt + kOccBatch * TCELLS;
+    unsigned* lst_end = lst_beg + kOccList;
+    int* lst_scan = reinterpret_cast<int*>(lst_end + kOccList);
     __shared__ int wcount[kOccNT / 32];
     __shared__ int n_list;
     __shared__ int cur_tile;
@@ -451,7 +432,6 @@ __global__ void __launch_bounds__(kOccNT) occ_tile_apply(const ApplyArgs a) {
         if (tid == 0) {
             const unsigned q = atomicAdd(a.queue, 1u);
             cur_tile = q < (unsigned)n_active ? a.order[q] : -1;
-            n_list = 0;
         }
         __syncthreads();
         const int t = cur_tile;
@@ -461,38 +441,67 @@ __global__ void __launch_bounds__(kOccNT) occ_tile_apply(const ApplyArgs a) {
         for (int c = tid; c < TCELLS; c += kOccNT) {
             const int x = tx0 + (c & (TS - 1)), y = ty0 + (c / TS);
             tile[swz(c)] = (x < a.nx && y < a.ny) ? a.grid[(size_t)y * a.nx + x] : 0.f;
-            cnt0[c] = 0u;
-            cnt1[c] = 0u;
         }
-        // scans that have runs in this tile, ascending, with their run ranges
+        for (int c = tid; c < kOccBatch * TCELLS; c += kOccNT) cnt[c] = 0u;
         const unsigned* off = a.offsets + (size_t)t * a.chunk_scans;
-        for (int s0 = 0; s0 < a.chunk_scans; s0 += kOccNT) {
-            const int s = s0 + tid;
-            unsigned ob = 0, oe = 0;
-            if (s < a.chunk_scans) { ob = off[s]; oe = off[s + 1]; }
-            const bool has = oe > ob;
-            const unsigned bal = __ballot_sync(0xffffffffu, has);
-            if (lane == 0) wcount[warp] = __popc(bal);
+        int scans_done = 0;
+        for (int s0 = 0; s0 < a.chunk_scans; s0 += kOccList) {
+            // ---- non-empty scans of this block of the offsets row, ascending
+            if (tid == 0) n_list = 0;
             __syncthreads();
-            int base = n_list;
-            for (int w = 0; w < warp; ++w) base += wcount[w];
-            if (has) {
-                const int slot = base + __popc(bal & lt_mask);
-                scan_list[slot] = (unsigned short)s; scan_beg[slot] = ob; scan_end[slot] = oe;
+            for (int s1 = s0; s1 < min(s0 + kOccList, a.chunk_scans); s1 += kOccNT) {
+                const int s = s1 + tid;
+                unsigned ob = 0, oe = 0;
+                if (s < min(s0 + kOccList, a.chunk_scans)) { ob = off[s]; oe = off[s + 1]; }
+                const bool has = oe > ob;
+                const unsigned bal = __ballot_sync(0xffffffffu, has);
+                if (lane == 0) wcount[warp] = __popc(bal);
+                __syncthreads();
+                int base = n_list;
+                for (int w = 0; w < warp; ++w) base += wcount[w];
+                if (has) {
+                    const int slot = base + __popc(bal & lt_mask);
+                    lst_scan[slot] = s; lst_beg[slot] = ob; lst_end[slot] = oe;
+                }
+                __syncthreads();
+                if (tid == 0) { int tot = 0; for (int w = 0; w < kOccNT / 32; ++w) tot += wcount[w]; n_list += tot; }
+                __syncthreads();
             }
-            __syncthreads();
-            if (tid == 0) { int tot = 0; for (int w = 0; w < kOccNT / 32; ++w) tot += wcount[w]; n_list += tot; }
-            __syncthreads();
-        }
-        const int n_scans_here = n_list;
-        if (n_scans_here > 0) occ_count_scan(a, scan_beg[0], scan_end[0], cnt0, warp, lane);
-        __syncthreads();
-        for (int li = 0; li < n_scans_here; ++li) {
-            unsigned* cur = (li & 1) ? cnt1 : cnt0;
-            unsigned* nxt = (li & 1) ? cnt0 : cnt1;
-            if (li + 1 < n_scans_here) occ_count_scan(a, scan_beg[li + 1], scan_end[li + 1], nxt, warp, lane);
-            occ_apply_scan(a, tile, cur, (int)scan_list[li] >= a.virgin_after, tid);
-            __syncthreads();
+            const int n_lst = n_list;
+            scans_done += n_lst;
+            for (int b0 = 0; b0 < n_lst; b0 += kOccBatch) {
+                const int nb = min(kOccBatch, n_lst - b0);
+                // ---- count: the batch's runs are one contiguous range; 32 runs per warp task
+                const unsigned rb = lst_beg[b0], re = lst_end[b0 + nb - 1];
+                for (unsigned e0 = rb + warp * 32u; e0 < re; e0 += kOccNT)
+                    occ_count_task(a, e0 + lane, re, lst_end + b0, nb - 1, cnt, lane);
+                __syncthreads();
+                // ---- apply: four cells per thread, scans in order
+                for (int c0 = tid * 4; c0 < TCELLS; c0 += kOccNT * 4) {
+                    float4 x4 = *reinterpret_cast<float4*>(&tile[c0]);
+                    float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+                    bool dirty = false;
+                    for (int b = 0; b < nb; ++b) {
+                        unsigned* plane = cnt + b * TCELLS;
+                        const uint4 c4 = *reinterpret_cast<const uint4*>(&plane[c0]);
+                        if ((c4.x | c4.y | c4.z | c4.w) == 0u) continue;
+                        *reinterpret_cast<uint4*>(&plane[c0]) = make_uint4(0u, 0u, 0u, 0u);
+                        const unsigned cv[4] = {c4.x, c4.y, c4.z, c4.w};
+                        const bool virgin_fix = lst_scan[b0 + b] >= a.virgin_after;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (cv[k]) {
+                                float x = xv[k];
+                                if (virgin_fix && x == 0.0f) x = a.clamp0;
+                                xv[k] = chain(x, cv[k] >> 20, cv[k] & kMissMask, a.l_hit, a.l_miss, a.lo, a.hi);
+                            }
+                        }
+                        dirty = true;
+                    }
+                    if (dirty) *reinterpret_cast<float4*>(&tile[c0]) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+                }
+                __syncthreads();
+            }
         }
         for (int c = tid; c < TCELLS; c += kOccNT) {
             const int x = tx0 + (c & (TS - 1)), y = ty0 + (c / TS);
@@ -500,7 +509,7 @@ __global__ void __launch_bounds__(kOccNT) occ_tile_apply(const ApplyArgs a) {
         }
         if (a.tile_prof && tid == 0) {
             long long* rec = a.tile_prof + 4ll * t;
-            rec[0] = t; rec[1] = n_scans_here;
+            rec[0] = t; rec[1] = scans_done;
             rec[2] = (long long)(off[a.chunk_scans] - off[0]);
             rec[3] = clock64() - t_start;
         }

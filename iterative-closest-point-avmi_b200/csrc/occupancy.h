@@ -6,9 +6,9 @@
 
 namespace icpb {
 
-constexpr int kOccTile = 64;                       // cells per tile edge (power of two)
+constexpr int kOccTile = 32;                       // cells per tile edge (power of two)
 constexpr int kOccMaxChunkScans = 2048;            // scans replayed per tile pass
-constexpr long long kOccMaxMatrix = 16LL << 20;    // (tile, scan) counters per pass
+constexpr long long kOccMaxMatrix = 64LL << 20;    // (tile, scan) counters per pass
 
 struct OccGrid {
     int nx = 0, ny = 0, tiles_x = 0, tiles_y = 0;
@@ -26,7 +26,7 @@ struct OccGrid {
     DevBuf origins, hits, hit_off;                 // staging for the host-buffer entry point
     DevBuf origin_cell, ray_cell, ray_scan;
     DevBuf counts, offsets, sums, runs, order, small, tile_prof;
-    int split = 4;                                 // lock-step windows per 32-run chunk (tuning knob)
+    int split = 1;                                 // lock-step windows per 32-run chunk (tuning knob)
     bool profile_tiles = false;                    // icpb200_grid_tile_profile() requested per-tile timings
     void release_all();
 };

@@ -20,7 +20,8 @@ lib.icpb200_grid_tile_profile(grid._dev._h, None, 0)
 for _ in range(2):
     grid.reset()
     grid._dev.update(origins, flat, off)
-n_tiles = 64 * 64
+from icp_b200.dist import TILE  # noqa: E402
+n_tiles = ((grid.nx + TILE - 1) // TILE) * ((grid.ny + TILE - 1) // TILE)
 full = np.zeros((2 * n_tiles, 4), dtype=np.int64)
 n = lib.icpb200_grid_tile_profile(grid._dev._h, full.ctypes.data_as(_lib.c_int64_p), 2 * n_tiles)
 buf, ph = full[:n_tiles], full[n_tiles:]

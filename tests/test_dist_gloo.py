@@ -51,13 +51,14 @@ def _worker(rank, size, port, tmp):
             assert np.array_equal(got[key], want[key]), key
         # ---- occupancy: each rank keeps only its tiles of the replay; the sum is the whole map
         gkw = dict(resolution=0.05, p_hit=0.85, p_miss=0.42, log_odds_min=-8.0, log_odds_max=8.0)
-        full = occupancy_oracle.GridOracleC(-12.8, 12.8, -9.6, 9.6, **gkw)      # 512 x 384 cells = 8 x 6 tiles
+        full = occupancy_oracle.GridOracleC(-12.8, 12.8, -9.6, 9.6, **gkw)      # 512 x 384 cells
         for s in range(6):
             full.update_scan(poses[s, :2] * 0.4, synth.to_world_frame(scans[s], poses[s]) * 0.4)
         mask = icpd.owned_tile_mask(full.nx, full.ny, rank, size)
         other = icpd.owned_tile_mask(full.nx, full.ny, 1 - rank, size)
         assert not (mask & other).any() and (mask | other).all()
-        assert mask[:64, :64].all() == (rank == 0) and mask[:64, 64:128].all() == (rank == 1)
+        T = icpd.TILE
+        assert mask[:T, :T].all() == (rank == 0) and mask[:T, T:2 * T].all() == (rank == 1)
         partial = np.where(mask, full.log_odds, np.float32(0))
         total = icpd.grid_allreduce_host(partial)
         assert total.dtype == np.float32 and total.tobytes() == full.log_odds.tobytes()
