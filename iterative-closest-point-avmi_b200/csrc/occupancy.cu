@@ -33,7 +33,7 @@ namespace icpb {
 
 constexpr int TS = kOccTile;                 // tile edge in cells
 constexpr int TCELLS = TS * TS;
-constexpr int kOccNT = 256;
+constexpr int kOccNT = 512;
 constexpr unsigned kHitUnit = 1u << 20;      // counter word: hits << 20 | misses
 constexpr unsigned kMissMask = kHitUnit - 1u;
 
@@ -476,20 +476,32 @@ __global__ void __launch_bounds__(kOccNT) occ_tile_apply(const ApplyArgs a) {
                 for (unsigned e0 = rb + warp * 32u; e0 < re; e0 += kOccNT)
                     occ_count_task(a, e0 + lane, re, lst_end + b0, nb - 1, cnt, lane);
                 __syncthreads();
-                // ---- apply: four cells per thread, scans in order
-                for (int c0 = tid * 4; c0 < TCELLS; c0 += kOccNT * 4) {
-                    float4 x4 = *reinterpret_cast<float4*>(&tile[c0]);
-                    float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+                // ---- apply: kCpt cells per thread kept in registers, scans in order
+                constexpr int kCpt = TCELLS / kOccNT >= 4 ? 4 : 2;
+                for (int c0 = tid * kCpt; c0 < TCELLS; c0 += kOccNT * kCpt) {
+                    float xv[kCpt];
+#pragma unroll
+                    for (int k = 0; k < kCpt; ++k) xv[k] = tile[c0 + k];
                     bool dirty = false;
                     for (int b = 0; b < nb; ++b) {
                         unsigned* plane = cnt + b * TCELLS;
-                        const uint4 c4 = *reinterpret_cast<const uint4*>(&plane[c0]);
-                        if ((c4.x | c4.y | c4.z | c4.w) == 0u) continue;
-                        *reinterpret_cast<uint4*>(&plane[c0]) = make_uint4(0u, 0u, 0u, 0u);
-                        const unsigned cv[4] = {c4.x, c4.y, c4.z, c4.w};
+                        unsigned cv[kCpt];
+                        if (kCpt == 4) {
+                            const uint4 c4 = *reinterpret_cast<const uint4*>(&plane[c0]);
+                            cv[0] = c4.x; cv[1] = c4.y; cv[kCpt - 2] = c4.z; cv[kCpt - 1] = c4.w;
+                        } else {
+                            const uint2 c2 = *reinterpret_cast<const uint2*>(&plane[c0]);
+                            cv[0] = c2.x; cv[1] = c2.y;
+                        }
+                        unsigned any = 0u;
+#pragma unroll
+                        for (int k = 0; k < kCpt; ++k) any |= cv[k];
+                        if (any == 0u) continue;
+#pragma unroll
+                        for (int k = 0; k < kCpt; ++k) plane[c0 + k] = 0u;
                         const bool virgin_fix = lst_scan[b0 + b] >= a.virgin_after;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
+                        for (int k = 0; k < kCpt; ++k) {
                             if (cv[k]) {
                                 float x = xv[k];
                                 if (virgin_fix && x == 0.0f) x = a.clamp0;
@@ -498,7 +510,10 @@ __global__ void __launch_bounds__(kOccNT) occ_tile_apply(const ApplyArgs a) {
                         }
                         dirty = true;
                     }
-                    if (dirty) *reinterpret_cast<float4*>(&tile[c0]) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+                    if (dirty) {
+#pragma unroll
+                        for (int k = 0; k < kCpt; ++k) tile[c0 + k] = xv[k];
+                    }
                 }
                 __syncthreads();
             }
