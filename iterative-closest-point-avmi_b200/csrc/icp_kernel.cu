@@ -62,8 +62,10 @@ size_t icp_pair_smem_bytes(int dim, int cap_s, int cap_t) {
 }
 size_t icp_voxel_smem_bytes(int sort_pad) { return align16(sizeof(CtaShared)) + (size_t)sort_pad * 12; }
 size_t icp_normals_smem_bytes(int cap_t) {
+    const size_t grid_path = sizeof(int) * (kGridCells + 1) + 4 + sizeof(unsigned short) * 4 * (size_t)cap_t + 16;
+    const size_t sweep_path = (sizeof(float2) + 2 * sizeof(float) + sizeof(unsigned short)) * (size_t)cap_t + 16;
     return align16(sizeof(CtaShared)) + align16(sizeof(double) * 2 * (size_t)(cap_t + cap_t / 32)) +
-           sizeof(int) * (kGridCells + 1) + 4 + sizeof(unsigned short) * 4 * (size_t)cap_t + 16;
+           (grid_path > sweep_path ? grid_path : sweep_path);
 }
 
 // ---- K0: which clouds are referenced / are point-to-line targets -------------
@@ -335,6 +337,227 @@ __device__ void knn_normals_fast(const double* tx, const double* ty, int n_t, in
     }
 }
 
+// ---- K2 fast path: lock-step slab sweep ---------------------------------------------
+// voxel_downsample emits its rows ordered by voxel column (icp.py:121-127), so a
+// cloud is sorted by x up to one voxel.  A warp takes 32 consecutive queries (one
+// per lane) and walks the cloud outwards from them, down and up in turns; every
+// lane evaluates the SAME candidate at the same step, so the candidate is one
+// broadcast shared-memory load and the lanes never diverge.  A direction stops
+// once the prefix maximum (suffix minimum) of x over the unvisited part puts it
+// farther from every lane's query than that lane's current K-th distance; the
+// rule needs no sortedness to be correct, only to be fast.
+//
+// Candidates are ranked by a 32-bit key: fp32 distance^2 on box-centred
+// coordinates with the low mantissa bits replaced by the point index, kept in a
+// 16-slot min/max network that runs only when some lane improves its list.  The
+// keys only pre-select: the survivors are re-evaluated in fp64, membership of the
+// K nearest is repaired by exact swaps, and the set is accepted only when it is
+// provably separated from everything the keys rejected or the sweep skipped
+// (truncation, fp32 rounding and recentring slack included).  Anything else goes
+// to the exact fp64 pass below.  The normal always comes from fp64 coordinates.
+__device__ __forceinline__ void pca_normal_masked(const double* tx, const double* ty, const unsigned (&key)[kKnnReg],
+                                                  unsigned idx_mask, unsigned in_mask, int K, double* out2) {
+    double mx = 0.0, my = 0.0;
+#pragma unroll
+    for (int m = 0; m < kKnnReg; ++m)
+        if ((in_mask >> m) & 1u) {
+            const int j = (int)(key[m] & idx_mask);
+            mx += tx[pad_index(j)]; my += ty[pad_index(j)];
+        }
+    mx /= (double)K; my /= (double)K;
+    double sxx = 0.0, sxy = 0.0, syy = 0.0;
+#pragma unroll
+    for (int m = 0; m < kKnnReg; ++m)
+        if ((in_mask >> m) & 1u) {
+            const int j = (int)(key[m] & idx_mask);
+            const double dx = tx[pad_index(j)] - mx, dy = ty[pad_index(j)] - my;
+            sxx += dx * dx; sxy += dx * dy; syy += dy * dy;
+        }
+    sym2_min_eigvec(sxx, sxy, syy, out2);
+}
+
+__device__ void cta_normals_sweep(const double* tx, const double* ty, int n, int K, double* __restrict__ normals_out,
+                                  float2* pf, float* pmax, float* smin, unsigned short* redo, CtaShared& sh) {
+    __shared__ float wtot[2][kNW];
+    const unsigned full = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double cx = 0.5 * (sh.lo_t[0] + sh.hi_t[0]), cy = 0.5 * (sh.lo_t[1] + sh.hi_t[1]);
+    const double half = 0.5 * fmax(sh.hi_t[0] - sh.lo_t[0], sh.hi_t[1] - sh.lo_t[1]);
+    for (int j = tid; j < n; j += kNT)
+        pf[j] = make_float2((float)(tx[pad_index(j)] - cx), (float)(ty[pad_index(j)] - cy));
+    if (tid == 0) sh.bcast_i[1] = 0;
+    __syncthreads();
+    {   // prefix maximum / suffix minimum of the fp32 x coordinate
+        const int per = (n + kNT - 1) / kNT;
+        const int beg = tid * per, end = min(beg + per, n);
+        float mx = -INFINITY, mn = INFINITY;               // mx over [beg, end), mn over the mirrored range
+        for (int j = beg; j < end; ++j) {
+            mx = fmaxf(mx, pf[j].x);
+            mn = fminf(mn, pf[n - 1 - j].x);
+        }
+        float imx = mx, imn = mn;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float a = __shfl_up_sync(full, imx, o), b = __shfl_up_sync(full, imn, o);
+            if (lane >= o) { imx = fmaxf(imx, a); imn = fminf(imn, b); }
+        }
+        if (lane == 31) { wtot[0][warp] = imx; wtot[1][warp] = imn; }
+        float emx = __shfl_up_sync(full, imx, 1), emn = __shfl_up_sync(full, imn, 1);
+        if (lane == 0) { emx = -INFINITY; emn = INFINITY; }
+        __syncthreads();
+        for (int w = 0; w < warp; ++w) { emx = fmaxf(emx, wtot[0][w]); emn = fminf(emn, wtot[1][w]); }
+        for (int j = beg; j < end; ++j) {
+            emx = fmaxf(emx, pf[j].x);          pmax[j] = emx;
+            emn = fminf(emn, pf[n - 1 - j].x);  smin[n - 1 - j] = emn;
+        }
+    }
+    __syncthreads();
+
+    const unsigned idx_mask = n <= 1024 ? 0x3ffu : 0xfffu;
+    const double eps_abs = 2.5e-7 * half;                   // |fp32-world distance - true distance|
+    for (int base = warp * 32; base < n; base += kNT) {
+        const int i = min(base + lane, n - 1);
+        const bool valid = base + lane < n;
+        const float2 q = pf[i];
+        unsigned key[kKnnReg];
+#pragma unroll
+        for (int m = 0; m < kKnnReg; ++m) key[m] = 0xffffffffu;
+        auto offer = [&](int j) {
+            const float2 t = pf[j];
+            const float dx = q.x - t.x, dy = q.y - t.y;
+            unsigned kk = (__float_as_uint(fmaf(dy, dy, dx * dx)) & ~idx_mask) | (unsigned)j;
+            if (__any_sync(full, kk < key[kKnnReg - 1])) {
+#pragma unroll
+                for (int m = 0; m < kKnnReg; ++m) {
+                    const unsigned lo_ = min(key[m], kk);
+                    kk = max(key[m], kk);
+                    key[m] = lo_;
+                }
+            }
+        };
+        auto kth_ub = [&]() {                               // >= fp32 distance^2 of the K-th candidate (NaN if none)
+            unsigned kth = 0xffffffffu;
+#pragma unroll
+            for (int m = 0; m < kKnnReg; ++m) kth = (m == K - 1) ? key[m] : kth;
+            return __uint_as_float(kth | idx_mask) * 1.02f;
+        };
+        int dn = min(base + 31, n - 1), up = base + 32;
+        bool ddone = false, udone = up >= n;
+        float gdn = INFINITY, gup = INFINITY;               // |dx| lower bound to the unvisited part, per lane
+        while (!ddone || !udone) {
+            if (!ddone) {
+                const int stop = max(dn - 7, 0);
+                for (int j = dn; j >= stop; --j) offer(j);
+                dn = stop - 1;
+                if (dn < 0) ddone = true;
+                else {
+                    const float g = q.x - pmax[dn];
+                    if (__all_sync(full, g > 0.f && g * g > kth_ub())) { ddone = true; gdn = g; }
+                }
+            }
+            if (!udone) {
+                const int stop = min(up + 7, n - 1);
+                for (int j = up; j <= stop; ++j) offer(j);
+                up = stop + 1;
+                if (up >= n) udone = true;
+                else {
+                    const float g = smin[up] - q.x;
+                    if (__all_sync(full, g > 0.f && g * g > kth_ub())) { udone = true; gup = g; }
+                }
+            }
+        }
+        // exact membership of the K nearest among the survivors (lexicographic (d, j) order)
+        const double px = tx[pad_index(i)], py = ty[pad_index(i)];
+        unsigned in_mask = (1u << K) - 1u;
+        double e_in = 0.0;
+        bool ok;
+        {
+            unsigned kthk = 0xffffffffu;
+#pragma unroll
+            for (int m = 0; m < kKnnReg; ++m) kthk = (m == K - 1) ? key[m] : kthk;
+            ok = kthk != 0xffffffffu;
+        }
+        for (int pass = 0; pass < 6; ++pass) {
+            double din = -1.0, dout = INFINITY;
+            int jin = -1, jout = 0x7fffffff, min_ = 0, mout = 0;
+#pragma unroll
+            for (int m = 0; m < kKnnReg; ++m) {
+                if (key[m] == 0xffffffffu) continue;
+                const int j = (int)(key[m] & idx_mask);
+                const double ex = px - tx[pad_index(j)], ey = py - ty[pad_index(j)];
+                const double d = ex * ex + ey * ey;
+                if ((in_mask >> m) & 1u) {
+                    if (d > din || (d == din && j > jin)) { din = d; jin = j; min_ = m; }
+                } else {
+                    if (d < dout || (d == dout && j < jout)) { dout = d; jout = j; mout = m; }
+                }
+            }
+            e_in = din;
+            const bool sorted = din < dout || (din == dout && jin < jout);
+            if (!sorted && ok) in_mask ^= (1u << min_) | (1u << mout);
+            if (pass == 5 && !sorted) ok = false;
+            if (!__any_sync(full, !sorted && ok)) break;
+        }
+        // everything outside the survivor list: rejected by key (>= truncated 16th key) or skipped by the sweep
+        float lbf = fminf(gdn, gup);
+        if (key[kKnnReg - 1] != 0xffffffffu)
+            lbf = fminf(lbf, sqrtf(__uint_as_float(key[kKnnReg - 1] & ~idx_mask)) * (1.0f - 1e-6f));
+        const double lb = (double)lbf * (1.0 - 1e-6) - eps_abs;
+        ok = ok && lb > 0.0 && e_in < lb * lb;
+        if (valid) {
+            if (ok) {
+                double nrm[2];
+                pca_normal_masked(tx, ty, key, idx_mask, in_mask, K, nrm);
+                normals_out[2 * i] = nrm[0];
+                normals_out[2 * i + 1] = nrm[1];
+            } else {
+                redo[atomicAdd(&sh.bcast_i[1], 1)] = (unsigned short)i;
+            }
+        }
+    }
+    __syncthreads();
+    // exact fp64 pass for the undecided points: same outward walk, one thread per point
+    const int n_redo = sh.bcast_i[1];
+    const double slack = 4.0e-7 * half;                     // fp32 recentring of both x coordinates, and then some
+    for (int r = tid; r < n_redo; r += kNT) {
+        const int i = redo[r];
+        const double px = tx[pad_index(i)], py = ty[pad_index(i)];
+        const double qx = (double)pf[i].x;
+        BestK<true> best;
+        best.init();
+        for (int j = i; j >= 0; --j) {
+            const double dx = px - tx[pad_index(j)], dy = py - ty[pad_index(j)];
+            best.offer(dx * dx + dy * dy, j, K);
+            if (j > 0) {
+                const double g = qx - (double)pmax[j - 1] - slack;
+                if (g > 0.0 && g * g > best.kth(K)) break;
+            }
+        }
+        for (int j = i + 1; j < n; ++j) {
+            const double g = (double)smin[j] - qx - slack;
+            if (g > 0.0 && g * g > best.kth(K)) break;
+            const double dx = px - tx[pad_index(j)], dy = py - ty[pad_index(j)];
+            best.offer(dx * dx + dy * dy, j, K);
+        }
+        double mx = 0.0, my = 0.0;
+#pragma unroll
+        for (int m = 0; m < kKnnReg; ++m)
+            if (m < K) { mx += tx[pad_index(best.j[m])]; my += ty[pad_index(best.j[m])]; }
+        mx /= (double)K; my /= (double)K;
+        double sxx = 0.0, sxy = 0.0, syy = 0.0;
+#pragma unroll
+        for (int m = 0; m < kKnnReg; ++m)
+            if (m < K) {
+                const double dx = tx[pad_index(best.j[m])] - mx, dy = ty[pad_index(best.j[m])] - my;
+                sxx += dx * dx; sxy += dx * dy; syy += dy * dy;
+            }
+        double nrm[2];
+        sym2_min_eigvec(sxx, sxy, syy, nrm);
+        normals_out[2 * i] = nrm[0];
+        normals_out[2 * i + 1] = nrm[1];
+    }
+}
+
 // ---- K2: normals: exact (k+1)-NN on a shared-memory uniform grid + 2x2 PCA -------
 // Restates utilities/icp.py:51-76.  All distances fp64; the neighbour set is
 // the exact (k+1)-NN (ties broken by lower index).  np.cov's 1/(K-1) scale is
@@ -432,6 +655,35 @@ __global__ void __launch_bounds__(kNT) normals_kernel(const CloudSet cs, int nor
     }
     __syncthreads();
     cta_normals_2d(tx, ty, n, normal_k, voxel, cs.nrm + beg * 2, cell_start, items, item_cell, redo, sh);
+}
+
+// K2 fast kernel: normal_k + 1 <= 16 and every cloud <= 4096 points (host-checked).
+__global__ void __launch_bounds__(kNT, 4) normals_sweep_kernel(const CloudSet cs, int normal_k, int cap_t) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    CtaShared& sh = *reinterpret_cast<CtaShared*>(smem);
+    const int c = blockIdx.x;
+    if (!cs.is_tgt[c]) return;
+    const int n = cs.ds_n[c];
+    if (n <= 0) return;
+    const int tstride = cap_t + cap_t / 32;
+    double* tx = reinterpret_cast<double*>(smem + align16(sizeof(CtaShared)));
+    double* ty = tx + tstride;
+    unsigned char* rest = smem + align16(sizeof(CtaShared)) + align16(sizeof(double) * 2 * (size_t)tstride);
+    float2* pf = reinterpret_cast<float2*>(rest);
+    float* pmax = reinterpret_cast<float*>(pf + cap_t);
+    float* smin = pmax + cap_t;
+    unsigned short* redo = reinterpret_cast<unsigned short*>(smin + cap_t);
+    const long long beg = cs.off[c];
+    const double* ds = cs.ds + beg * 2;
+    for (int j = threadIdx.x; j < n; j += kNT) {
+        tx[pad_index(j)] = ds[2 * j];
+        ty[pad_index(j)] = ds[2 * j + 1];
+    }
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 3; ++k) { sh.lo_t[k] = cs.box[(size_t)c * 6 + k]; sh.hi_t[k] = cs.box[(size_t)c * 6 + 3 + k]; }
+    }
+    __syncthreads();
+    cta_normals_sweep(tx, ty, n, min(normal_k, n - 1) + 1, cs.nrm + beg * 2, pf, pmax, smin, redo, sh);
 }
 
 // ---- K3: fp32 sweep --------------------------------------------------------------
@@ -1230,6 +1482,12 @@ int launch_voxel_clouds(const CloudSet& cs, int dim, double voxel, int sort_pad,
 
 int launch_normals(const CloudSet& cs, int cap_t, int normal_k, double voxel, cudaStream_t stream) {
     const size_t smem = icp_normals_smem_bytes(cap_t);
+    if (normal_k + 1 <= kKnnReg && cap_t <= 4096) {
+        ICPB_CUDA(cudaFuncSetAttribute(normals_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        normals_sweep_kernel<<<cs.n_clouds, kNT, smem, stream>>>(cs, normal_k, cap_t);
+        ICPB_LAUNCH_CHECK();
+        return ICPB200_OK;
+    }
     ICPB_CUDA(cudaFuncSetAttribute(normals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     normals_kernel<<<cs.n_clouds, kNT, smem, stream>>>(cs, normal_k, cap_t, voxel);
     ICPB_LAUNCH_CHECK();
