@@ -665,7 +665,8 @@ int icpb200_voxel_downsample(const double* pts, int64_t n, int dim, double voxel
 
 void OccGrid::release_all() {
     DevBuf* bufs[] = {&grid, &origins, &hits, &hit_off, &origin_cell, &ray_cell, &ray_scan,
-                      &counts, &offsets, &sums, &runs, &order, &small, &tile_prof};
+                      &counts, &offsets, &sums, &runs, &order, &small, &tile_prof,
+                      &slotmap, &slot_cell, &ord, &tile_count, &hit_off_shift};
     for (DevBuf* b : bufs) b->release();
 }
 
@@ -686,6 +687,8 @@ void* icpb200_grid_create(int nx, int ny, double min_x, double min_y, double res
     g->l_hit = l_hit; g->l_miss = l_miss; g->lo_min = lo_min; g->lo_max = lo_max;
     g->zero_outside_clamp = ((float)lo_min > 0.f) || ((float)lo_max < 0.f);
     g->apply_ctas = occ_apply_ctas(g_ctx.sm_count);
+    g->fast_ctas = occ_fast_ctas(g_ctx.sm_count);
+    if (const char* e = getenv("ICPB200_OCC_PATH")) g->use_fast = strcmp(e, "ordered") != 0;
     if (const char* e = getenv("ICPB200_OCC_SPLIT")) g->split = std::max(1, std::min(8, atoi(e)));
     if (g->grid.reserve(sizeof(float) * (size_t)nx * ny) ||
         cudaMemsetAsync(g->grid.p, 0, sizeof(float) * (size_t)nx * ny, g_ctx.stream) != cudaSuccess ||

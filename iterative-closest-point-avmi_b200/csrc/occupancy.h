@@ -9,6 +9,7 @@ namespace icpb {
 constexpr int kOccTile = 32;                       // cells per tile edge (power of two)
 constexpr int kOccMaxChunkScans = 2048;            // scans replayed per tile pass
 constexpr long long kOccMaxMatrix = 64LL << 20;    // (tile, scan) counters per pass
+constexpr size_t kOccOrdBudget = 1ull << 30;       // order-free path: (hit cell, scan) counters per chunk (4 GiB)
 
 struct OccGrid {
     int nx = 0, ny = 0, tiles_x = 0, tiles_y = 0;
@@ -26,6 +27,10 @@ struct OccGrid {
     DevBuf origins, hits, hit_off;                 // staging for the host-buffer entry point
     DevBuf origin_cell, ray_cell, ray_scan;
     DevBuf counts, offsets, sums, runs, order, small, tile_prof;
+    // order-free path (occupancy_fast.cu)
+    DevBuf slotmap, slot_cell, ord, tile_count, hit_off_shift;
+    int fast_ctas = 0;
+    bool use_fast = true;                          // ICPB200_OCC_PATH=ordered forces the ordered tile replay
     int split = 1;                                 // lock-step windows per 32-run chunk (tuning knob)
     bool profile_tiles = false;                    // icpb200_grid_tile_profile() requested per-tile timings
     void release_all();
@@ -36,6 +41,11 @@ struct OccGrid {
 // small readback per scan chunk.
 int occ_update_device(OccGrid& g, int n_scans, const double* d_origins, const double* d_hits,
                       const long long* d_hit_off, const long long* h_hit_off, cudaStream_t st);
+int occ_update_ordered(OccGrid& g, int n_scans, const double* d_origins, const double* d_hits,
+                       const long long* d_hit_off, const long long* h_hit_off, cudaStream_t st);
+int occ_update_fast(OccGrid& g, int n_scans, const double* d_origins, const double* d_hits,
+                    const long long* d_hit_off, const long long* h_hit_off, cudaStream_t st);
 int occ_apply_ctas(int sm_count);
+int occ_fast_ctas(int sm_count);
 
 }  // namespace icpb

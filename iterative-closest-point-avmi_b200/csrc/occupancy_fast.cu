@@ -1,0 +1,610 @@
+// Occupancy-grid log-odds raycast, order-free formulation (sm_100a) -- the
+// default path behind icpb200_grid_update for
+// /root/reference/utilities/mapping.py:103-141 applied to a batch of scans.
+//
+// The update is x = f32(f64(x) + c) per event with one clip per scan
+// (mapping.py:129, 139, 141), so in general the value of a cell depends on the
+// ORDER of the scans that touch it.  But a cell that receives NO hit in the
+// batch only ever sees adds of l_miss: the chain is monotone, the clip can only
+// pin it at the bound it is moving towards, and
+//
+//        final = clip(chain_N(x0))        N = total misses on the cell
+//
+// whatever way the N misses are spread over the scans (proof in DESIGN.md 3.4).
+// So only the cells that are some ray's endpoint ("hit cells", the walls: 0.2 %
+// of the touched cells on the C4 workload, 0.5 % of the ray-cell events) need an
+// ordered replay.  The pipeline per chunk of <= 2048 scans:
+//
+//   1. occ_fast_count   per ray: world -> cell (fp64, exact), claim a slot for the
+//                       endpoint's cell, count the ray's tile crossings per tile
+//   2. occ_tile_scan    exclusive scan of the per-tile run counts, active tiles
+//                       ordered heaviest first
+//   3. occ_fast_fill    per ray: hit -> ord[slot][scan] (global atomic), tile runs
+//                       (16-byte self-contained records) grouped by tile
+//   4. occ_fast_tiles   one CTA per tile: every run is walked, in any order, by
+//                       one lane; misses on ordinary cells are counted in shared
+//                       memory, misses on hit cells go to ord[slot][scan]; then
+//                       x = clip(chain_N(x)) on the counted cells
+//   5. occ_fast_replay  one warp per hit cell: its row of ord is replayed scan by
+//                       scan (m hits, k misses, clip) and cleared
+//
+// No barrier per scan, no (tile x scan) matrix, nothing sequential but the
+// per-hit-cell chains.  Clamp intervals that exclude 0 (every untouched cell
+// moves on the first scan) and hit-cell tables beyond kOrdBudget take the
+// ordered tile replay in occupancy.cu instead.
+#include "icp_b200.h"
+#include "bres.cuh"
+#include "common.cuh"
+#include "occupancy.h"
+
+#include <algorithm>
+#include <vector>
+
+namespace icpb {
+
+namespace {
+
+constexpr int TS = kOccTile;
+constexpr int TCELLS = TS * TS;
+constexpr unsigned kNone = 0xffffffffu;      // slot map: not a hit cell
+constexpr unsigned kClaimed = 0xfffffffeu;   // slot map: being assigned
+constexpr unsigned kHitUnit = 1u << 20;      // ord word: hits << 20 | misses
+constexpr unsigned kMissMask = kHitUnit - 1u;
+constexpr int kTileNT = 256;
+
+// 16-byte run record: everything the tile kernel needs to walk the run.
+//   w0 = local cell of the first step (10) | x-major (1) | major + (1) | minor + (1) | len-1 (5) | chunk-local scan (11)
+//   w1 = Bresenham error term at the first step   w2 = dmaj   w3 = dmin
+constexpr int kRunXMajor = 1 << 10, kRunMajPos = 1 << 11, kRunMinPos = 1 << 12;
+
+struct FastArgs {
+    // rays
+    const double2* hits;
+    const long long* hit_off;                 // whole call, n_scans + 1
+    const double* origins;
+    long long ray_begin, ray_end;             // rays of this chunk (absolute)
+    int scan_begin, chunk_scans, n_scans;
+    double min_x, min_y, res;
+    int nx, ny, tiles_x, n_tiles;
+    int rank, world;
+    int2* ray_cell;                           // chunk-relative
+    int* ray_scan;
+    int2* origin_cell;                        // absolute scan index
+    // hit cells
+    unsigned* slotmap;                        // ny * nx
+    unsigned* slot_cell;                      // slot -> cell
+    unsigned* ord;                            // [slot][chunk_scans]
+    // binning
+    unsigned* tile_count;                     // count pass: += 1 ; fill pass: cursor
+    const unsigned* tile_off;
+    uint4* runs;
+    // small: [0] total runs [1] n_active [2] queue [3] error flag [4] n_slots ; stats (u64 x 4) at +64 bytes
+    unsigned* small;
+    unsigned long long* stats;
+};
+
+__device__ __forceinline__ int swz(int idx) { return idx ^ ((idx / TS) & 31); }
+
+// Tile crossings of one ray with the divisions done in 32 bits whenever the ray
+// is short enough (always, for endpoints inside a <= 16k-cell grid); same runs
+// in the same order as TileRunIter<TS>.
+struct FastTileIter {
+    RayGeom g;
+    int n, nb;
+    bool small;
+    int tiles_x;
+    __device__ __forceinline__ void init_empty() { n = 0; nb = 0; small = true; }
+    __device__ __forceinline__ void init(const RayGeom& geom, int nx, int ny, int tiles_x_) {
+        g = geom; tiles_x = tiles_x_;
+        int64_t a = 0, b = 0;
+        if (g.dmaj != 0) clip_to_grid(g, nx, ny, a, b);
+        n = (int)a; nb = (int)b;
+        small = g.dmaj < (1 << 14) && nb < (1 << 14);          // 2*n*dmin + dmaj < 2^30
+    }
+    __device__ __forceinline__ int minor_at(int nn) const {
+        if (small) return (int)((2u * (unsigned)nn * (unsigned)g.dmin + (unsigned)g.dmaj - 1u) / (2u * (unsigned)g.dmaj));
+        return minor_steps(g, nn);
+    }
+    __device__ __forceinline__ long long reach(int j) const {
+        if (small && j < (1 << 14)) {
+            const unsigned num = 2u * (unsigned)g.dmaj * (unsigned)j - (unsigned)g.dmaj + 1u, den = 2u * (unsigned)g.dmin;
+            return (long long)((num + den - 1u) / den);
+        }
+        return first_step_reaching(g, j);
+    }
+    __device__ __forceinline__ bool next(TileRun& r) {
+        if (n >= nb) return false;
+        const int j = minor_at(n);
+        int x, y;
+        cell_at(g, n, j, x, y);
+        const int cmaj = g.xmajor ? x : y, cmin = g.xmajor ? y : x;
+        const int inmaj = cmaj & (TS - 1);
+        long long end = (long long)n + (g.smaj > 0 ? (TS - inmaj) : (inmaj + 1));
+        if (g.dmin != 0) {
+            const int inmin = cmin & (TS - 1);
+            const int jleave = j + (g.smin > 0 ? (TS - inmin) : (inmin + 1));
+            const long long nleave = reach(jleave);
+            if (nleave < end) end = nleave;
+        }
+        if (end > nb) end = nb;
+        r.tile = (y / TS) * tiles_x + (x / TS);
+        r.n0 = n; r.j0 = j; r.len = (int)(end - n);
+        n = (int)end;
+        return true;
+    }
+};
+
+// ---- 1./3. per-ray passes --------------------------------------------------------
+__global__ void occ_fast_origins(const double* __restrict__ origins, int n_scans, double min_x, double min_y,
+                                 double res, int2* __restrict__ origin_cell) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_scans) return;
+    // mapping.py:57-60: floor((w - min) / resolution)
+    origin_cell[s] = make_int2(sat_cell(floor((origins[2 * s] - min_x) / res)),
+                               sat_cell(floor((origins[2 * s + 1] - min_y) / res)));
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) occ_fast_rays(const FastArgs a) {
+    const long long rl = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // chunk-relative ray
+    const long long r = a.ray_begin + rl;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned long long cells = 0, nhits = 0, nruns = 0;
+    FastTileIter it;
+    it.init_empty();
+    int sl = 0;
+    if (r < a.ray_end) {
+        int2 h;
+        int s;
+        if (!FILL) {
+            const double2 p = a.hits[r];
+            // mapping.py:94-98
+            h = make_int2(sat_cell(floor((p.x - a.min_x) / a.res)), sat_cell(floor((p.y - a.min_y) / a.res)));
+            int lo = a.scan_begin, hi = a.scan_begin + a.chunk_scans;      // largest s with hit_off[s] <= r
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (a.hit_off[mid] <= r) lo = mid; else hi = mid;
+            }
+            s = lo;
+            a.ray_cell[rl] = h;
+            a.ray_scan[rl] = s;
+        } else {
+            h = a.ray_cell[rl];
+            s = a.ray_scan[rl];
+        }
+        sl = s - a.scan_begin;
+        const int2 o = a.origin_cell[s];
+        it.init(make_ray(o.x, o.y, h.x, h.y), a.nx, a.ny, a.tiles_x);
+        if (h.x >= 0 && h.x < a.nx && h.y >= 0 && h.y < a.ny) {                 // mapping.py:124-127
+            const int tile = (h.y / TS) * a.tiles_x + (h.x / TS);
+            if (tile % a.world == a.rank) {
+                const size_t cell = (size_t)h.y * a.nx + h.x;
+                if (!FILL) {
+                    ++nhits;
+                    if (atomicCAS(&a.slotmap[cell], kNone, kClaimed) == kNone) {
+                        const unsigned slot = atomicAdd(&a.small[4], 1u);
+                        a.slot_cell[slot] = (unsigned)cell;
+                        a.slotmap[cell] = slot;                                  // read by later kernels only
+                    }
+                } else {
+                    const unsigned slot = a.slotmap[cell];
+                    const unsigned old = atomicAdd(&a.ord[(size_t)slot * a.chunk_scans + sl], kHitUnit);
+                    if ((old >> 20) == 4095u) a.small[3] = 1u;
+                }
+            }
+        }
+    }
+    // All lanes walk their rays' tile runs in lock step; runs of the warp that fall
+    // into the same tile take one atomic and consecutive slots.
+    for (;;) {
+        TileRun t;
+        const bool has = it.next(t);
+        if (!__any_sync(0xffffffffu, has)) break;
+        const bool owned = has && (t.tile % a.world == a.rank);
+        const unsigned peers = __match_any_sync(0xffffffffu, owned ? t.tile : -1 - lane);
+        const int leader = __ffs(peers) - 1;
+        unsigned base = 0;
+        if (owned && lane == leader) base = atomicAdd(&a.tile_count[t.tile], (unsigned)__popc(peers));
+        if (FILL) {
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (owned) {
+                int x, y;
+                cell_at(it.g, t.n0, t.j0, x, y);
+                uint4 run;
+                run.x = (unsigned)((y % TS) * TS + (x % TS)) | (it.g.xmajor ? kRunXMajor : 0) |
+                        (it.g.smaj > 0 ? kRunMajPos : 0) | (it.g.smin > 0 ? kRunMinPos : 0) |
+                        ((unsigned)(t.len - 1) << 13) | ((unsigned)sl << 18);
+                // RunWalker::start: (2n+2)*dmin - 2*dmaj*j - dmaj, bounded by 2*dmaj + 2*dmin
+                run.y = (unsigned)(int)((2ll * t.n0 + 2) * it.g.dmin - 2ll * it.g.dmaj * t.j0 - it.g.dmaj);
+                run.z = (unsigned)it.g.dmaj;
+                run.w = (unsigned)it.g.dmin;
+                a.runs[a.tile_off[t.tile] + base + __popc(peers & lt_mask)] = run;
+            }
+        } else if (owned) {
+            cells += t.len;
+            ++nruns;
+        }
+    }
+    if (!FILL) {
+        __shared__ unsigned long long part[3][8];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cells += __shfl_xor_sync(0xffffffffu, cells, o);
+            nhits += __shfl_xor_sync(0xffffffffu, nhits, o);
+            nruns += __shfl_xor_sync(0xffffffffu, nruns, o);
+        }
+        const int w = threadIdx.x >> 5;
+        if (lane == 0) { part[0][w] = cells; part[1][w] = nhits; part[2][w] = nruns; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long c = 0, h = 0, n = 0;
+            for (int k = 0; k < 8; ++k) { c += part[0][k]; h += part[1][k]; n += part[2][k]; }
+            if (c) atomicAdd(&a.stats[1], c);
+            if (h) atomicAdd(&a.stats[2], h);
+            if (n) atomicAdd(&a.stats[3], n);
+        }
+    }
+}
+
+// ---- 2. scan of the per-tile run counts + active tiles, heaviest first ---------------
+__global__ void __launch_bounds__(1024) occ_tile_scan(const unsigned* __restrict__ counts, int n_tiles,
+                                                      unsigned* __restrict__ offsets /* n_tiles + 1 */,
+                                                      int* __restrict__ order, unsigned* __restrict__ small) {
+    __shared__ unsigned wsum[32];
+    __shared__ unsigned carry;
+    __shared__ int hist[33], start[33];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    if (tid < 33) hist[tid] = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < n_tiles; b0 += 1024) {
+        const int t = b0 + tid;
+        const unsigned v = t < n_tiles ? counts[t] : 0u;
+        if (v) atomicAdd(&hist[32 - __clz(v)], 1);
+        unsigned inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        unsigned base = carry;
+        for (int w = 0; w < warp; ++w) base += wsum[w];
+        if (t < n_tiles) offsets[t] = base + inc - v;
+        __syncthreads();
+        if (tid == 1023) carry = base + inc;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        offsets[n_tiles] = carry;
+        small[0] = carry;
+        int run = 0;
+        for (int b = 32; b >= 1; --b) { start[b] = run; run += hist[b]; }
+        small[1] = (unsigned)run;
+    }
+    __syncthreads();
+    for (int t = tid; t < n_tiles; t += 1024) {
+        const unsigned v = counts[t];
+        if (v) order[atomicAdd(&start[32 - __clz(v)], 1)] = t;
+    }
+}
+
+// ---- the add chain (mapping.py:129, 139, 141) ------------------------------------------
+__device__ __forceinline__ float fast_chain(float x, unsigned m, unsigned k, double l_hit, double l_miss,
+                                            float lo, float hi) {
+    if (m == 0u) {                            // already pinned where the misses push it
+        if (l_miss < 0.0 && x <= lo) return lo;
+        if (l_miss > 0.0 && x >= hi) return hi;
+    }
+    for (unsigned i = 0; i < m; ++i) {        // mapping.py:129 -- m hits, each x = f32(f64(x) + l_hit)
+        const float y = (float)((double)x + l_hit);
+        if (y == x) break;                    // absorbed: every further add is too
+        x = y;
+        if (k == 0 && ((l_hit > 0.0 && x >= hi) || (l_hit < 0.0 && x <= lo))) break;   // the clip decides
+    }
+    // mapping.py:139 -- k misses.  Each add moves x by l_miss up to one float rounding (< 1e-6 for
+    // |x| <= 16), so k adds certainly cross the bound when k * (|l_miss| - 1e-6) covers the gap.
+    if (k > 4 && fabsf(x) <= 16.f && lo >= -16.f && hi <= 16.f) {
+        if (l_miss < -1e-5 && (double)x + (double)k * (l_miss + 1e-6) <= (double)lo) return lo;
+        if (l_miss > 1e-5 && (double)x + (double)k * (l_miss - 1e-6) >= (double)hi) return hi;
+    }
+    for (unsigned i = 0; i < k; ++i) {
+        const float y = (float)((double)x + l_miss);
+        if (y == x) break;
+        x = y;
+        if ((l_miss < 0.0 && x <= lo) || (l_miss > 0.0 && x >= hi)) break;
+    }
+    return fminf(fmaxf(x, lo), hi);           // mapping.py:141
+}
+
+// ---- 4. tiles ----------------------------------------------------------------------------
+struct TileArgs {
+    float* grid;
+    int nx, ny, tiles_x;
+    const unsigned* tile_off;
+    const uint4* runs;
+    const int* order;
+    unsigned* small;                          // [1] n_active [2] queue
+    const unsigned* slotmap;
+    unsigned* ord;
+    int chunk_scans;
+    double l_hit, l_miss;
+    float lo, hi;
+};
+
+template <bool HITS>
+__device__ __forceinline__ void walk_runs(const TileArgs& a, unsigned beg, unsigned end, unsigned* cnt,
+                                          const unsigned* slot, int warp, int lane) {
+    for (unsigned e0 = beg + warp * 32u; e0 < end; e0 += kTileNT) {
+        const unsigned e = e0 + lane;
+        int len = 0, idx = 0, d = 0, inc = 0, dec = 0, step_maj = 0, step_both = 0, sl = 0;
+        if (e < end) {
+            const uint4 r = __ldg(a.runs + e);
+            idx = (int)(r.x & 1023u);
+            len = (int)((r.x >> 13) & 31u) + 1;
+            sl = (int)(r.x >> 18);
+            const int maj = (r.x & kRunXMajor) ? ((r.x & kRunMajPos) ? 1 : -1) : ((r.x & kRunMajPos) ? TS : -TS);
+            const int mnr = (r.x & kRunXMajor) ? ((r.x & kRunMinPos) ? TS : -TS) : ((r.x & kRunMinPos) ? 1 : -1);
+            step_maj = maj; step_both = maj + mnr;
+            d = (int)r.y; dec = 2 * (int)r.z; inc = 2 * (int)r.w;
+        }
+        const int maxlen = (int)__reduce_max_sync(0xffffffffu, (unsigned)len);
+        for (int k = 0; k < maxlen; ++k) {
+            if (k < len) {
+                const int c = swz(idx);
+                if (HITS) {
+                    const unsigned s = slot[c];
+                    if (s != kNone) atomicAdd(&a.ord[(size_t)s * a.chunk_scans + sl], 1u);
+                    else atomicAdd(&cnt[c], 1u);
+                } else {
+                    atomicAdd(&cnt[c], 1u);
+                }
+                const bool m = d > 0;
+                idx += m ? step_both : step_maj;
+                d += inc - (m ? dec : 0);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kTileNT) occ_fast_tiles(const TileArgs a) {
+    __shared__ unsigned cnt[TCELLS];
+    __shared__ unsigned slot[TCELLS];
+    __shared__ int cur_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned n_active = a.small[1];
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned q = atomicAdd(&a.small[2], 1u);
+            cur_tile = q < n_active ? a.order[q] : -1;
+        }
+        __syncthreads();
+        const int t = cur_tile;
+        if (t < 0) break;
+        const int tx0 = (t % a.tiles_x) * TS, ty0 = (t / a.tiles_x) * TS;
+        bool any = false;
+        for (int c = tid; c < TCELLS; c += kTileNT) {
+            const int x = tx0 + (c & (TS - 1)), y = ty0 + (c / TS);
+            const unsigned s = (x < a.nx && y < a.ny) ? a.slotmap[(size_t)y * a.nx + x] : kNone;
+            slot[swz(c)] = s;
+            cnt[c] = 0u;
+            any |= s != kNone;
+        }
+        const int has_hits = __syncthreads_or(any);
+        const unsigned beg = a.tile_off[t], end = a.tile_off[t + 1];
+        if (has_hits) walk_runs<true>(a, beg, end, cnt, slot, warp, lane);
+        else          walk_runs<false>(a, beg, end, cnt, slot, warp, lane);
+        __syncthreads();
+        for (int c = tid; c < TCELLS; c += kTileNT) {
+            const unsigned n = cnt[swz(c)];
+            if (n) {
+                const int x = tx0 + (c & (TS - 1)), y = ty0 + (c / TS);
+                float* g = a.grid + (size_t)y * a.nx + x;
+                *g = fast_chain(*g, 0u, n, a.l_hit, a.l_miss, a.lo, a.hi);
+            }
+        }
+    }
+}
+
+// ---- 5. ordered replay of the hit cells ---------------------------------------------------
+__global__ void __launch_bounds__(256) occ_fast_replay(float* __restrict__ grid, unsigned* __restrict__ slotmap,
+                                                       const unsigned* __restrict__ slot_cell, unsigned* __restrict__ ord,
+                                                       const unsigned* __restrict__ small, int chunk_scans,
+                                                       double l_hit, double l_miss, float lo, float hi) {
+    const unsigned n_slots = small[4];
+    const unsigned slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (slot >= n_slots) return;
+    const unsigned cell = slot_cell[slot];
+    unsigned* row = ord + (size_t)slot * chunk_scans;
+    float x = grid[cell];
+    for (int s0 = 0; s0 < chunk_scans; s0 += 128) {
+        unsigned v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int s = s0 + u * 32 + lane;
+            v[u] = s < chunk_scans ? row[s] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            unsigned nz = __ballot_sync(0xffffffffu, v[u] != 0u);
+            if (v[u]) row[s0 + u * 32 + lane] = 0u;                 // leave the table clean for the next chunk
+            while (nz) {
+                const int l = __ffs(nz) - 1;
+                nz &= nz - 1;
+                const unsigned w = __shfl_sync(0xffffffffu, v[u], l);
+                x = fast_chain(x, w >> 20, w & kMissMask, l_hit, l_miss, lo, hi);
+            }
+        }
+    }
+    if (lane == 0) {
+        grid[cell] = x;
+        slotmap[cell] = kNone;
+    }
+}
+
+}  // namespace
+
+// Returns ICPB200_OK, an error, or 1 when this chunk must take the ordered path instead.
+static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_origins, const double* d_hits,
+                      const long long* d_hit_off, const long long* h_hit_off, cudaStream_t st) {
+    const long long rb = h_hit_off[s0], re = h_hit_off[s0 + cs];
+    const long long nr = re - rb;
+    if (nr == 0) return ICPB200_OK;
+    const int n_tiles = g.tiles_x * g.tiles_y;
+    if (g.tile_count.reserve(sizeof(unsigned) * (size_t)n_tiles) || g.offsets.reserve(sizeof(unsigned) * ((size_t)n_tiles + 1)) ||
+        g.slot_cell.reserve(sizeof(unsigned) * (size_t)nr))
+        return ICPB200_ERR_CUDA;
+    unsigned* d_small = g.small.as<unsigned>();
+    unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(g.small.as<unsigned char>() + 64);
+    ICPB_CUDA(cudaMemsetAsync(d_small, 0, 64, st));
+    ICPB_CUDA(cudaMemsetAsync(g.tile_count.p, 0, sizeof(unsigned) * (size_t)n_tiles, st));
+
+    FastArgs a;
+    a.hits = reinterpret_cast<const double2*>(d_hits);
+    a.hit_off = d_hit_off; a.origins = d_origins;
+    a.ray_begin = rb; a.ray_end = re;
+    a.scan_begin = s0; a.chunk_scans = cs; a.n_scans = n_scans;
+    a.min_x = g.min_x; a.min_y = g.min_y; a.res = g.res;
+    a.nx = g.nx; a.ny = g.ny; a.tiles_x = g.tiles_x; a.n_tiles = n_tiles;
+    a.rank = g.rank; a.world = g.world;
+    a.ray_cell = g.ray_cell.as<int2>();
+    a.ray_scan = g.ray_scan.as<int>();
+    a.origin_cell = g.origin_cell.as<int2>();
+    a.slotmap = g.slotmap.as<unsigned>();
+    a.slot_cell = g.slot_cell.as<unsigned>();
+    a.ord = nullptr;
+    a.tile_count = g.tile_count.as<unsigned>();
+    a.tile_off = nullptr; a.runs = nullptr;
+    a.small = d_small; a.stats = d_stats;
+    const unsigned nblk = (unsigned)((nr + 255) / 256);
+    occ_fast_rays<false><<<nblk, 256, 0, st>>>(a);
+    ICPB_LAUNCH_CHECK();
+    occ_tile_scan<<<1, 1024, 0, st>>>(g.tile_count.as<unsigned>(), n_tiles, g.offsets.as<unsigned>(), g.order.as<int>(), d_small);
+    ICPB_LAUNCH_CHECK();
+    unsigned h_small[8];
+    ICPB_CUDA(cudaMemcpyAsync(h_small, d_small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
+    ICPB_CUDA(cudaStreamSynchronize(st));
+    const unsigned total_runs = h_small[0], n_slots = h_small[4];
+    const size_t ord_words = (size_t)n_slots * cs;
+    if (ord_words > kOccOrdBudget) {
+        // too many hit cells for the dense table: undo the claims, the ordered path takes the chunk
+        if (n_slots) {
+            occ_fast_replay<<<(n_slots * 32u + 255u) / 256u, 256, 0, st>>>(g.grid.as<float>(), g.slotmap.as<unsigned>(),
+                                                                           g.slot_cell.as<unsigned>(), nullptr, d_small, 0, g.l_hit,
+                                                                           g.l_miss, (float)g.lo_min, (float)g.lo_max);
+            ICPB_LAUNCH_CHECK();
+        }
+        return 1;
+    }
+    {
+        void* before = g.ord.p;
+        const size_t cap_before = g.ord.cap;
+        if (g.ord.reserve(sizeof(unsigned) * std::max<size_t>(ord_words, 1))) return ICPB200_ERR_CUDA;
+        if (g.ord.p != before || g.ord.cap != cap_before) ICPB_CUDA(cudaMemsetAsync(g.ord.p, 0, g.ord.cap, st));
+    }
+    if (g.runs.reserve(sizeof(uint4) * ((size_t)total_runs + 64))) return ICPB200_ERR_CUDA;
+    ICPB_CUDA(cudaMemsetAsync(g.tile_count.p, 0, sizeof(unsigned) * (size_t)n_tiles, st));
+    a.ord = g.ord.as<unsigned>();
+    a.tile_off = g.offsets.as<unsigned>();
+    a.runs = g.runs.as<uint4>();
+    occ_fast_rays<true><<<nblk, 256, 0, st>>>(a);
+    ICPB_LAUNCH_CHECK();
+    const float lo = (float)g.lo_min, hi = (float)g.lo_max;
+    if (total_runs) {
+        TileArgs t;
+        t.grid = g.grid.as<float>();
+        t.nx = g.nx; t.ny = g.ny; t.tiles_x = g.tiles_x;
+        t.tile_off = g.offsets.as<unsigned>();
+        t.runs = g.runs.as<uint4>();
+        t.order = g.order.as<int>();
+        t.small = d_small;
+        t.slotmap = g.slotmap.as<unsigned>();
+        t.ord = g.ord.as<unsigned>();
+        t.chunk_scans = cs;
+        t.l_hit = g.l_hit; t.l_miss = g.l_miss; t.lo = lo; t.hi = hi;
+        const unsigned n_active = h_small[1];
+        const unsigned ctas = std::min<unsigned>(n_active, (unsigned)g.fast_ctas);
+        occ_fast_tiles<<<ctas, kTileNT, 0, st>>>(t);
+        ICPB_LAUNCH_CHECK();
+    }
+    if (n_slots) {
+        occ_fast_replay<<<(n_slots * 32u + 255u) / 256u, 256, 0, st>>>(g.grid.as<float>(), g.slotmap.as<unsigned>(),
+                                                                       g.slot_cell.as<unsigned>(), g.ord.as<unsigned>(), d_small, cs,
+                                                                       g.l_hit, g.l_miss, lo, hi);
+        ICPB_LAUNCH_CHECK();
+    }
+    return ICPB200_OK;
+}
+
+int occ_fast_ctas(int sm_count) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, occ_fast_tiles, kTileNT, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return sm_count * per_sm;
+}
+
+int occ_update_fast(OccGrid& g, int n_scans, const double* d_origins, const double* d_hits,
+                    const long long* d_hit_off, const long long* h_hit_off, cudaStream_t st) {
+    const long long n_rays = h_hit_off[n_scans] - h_hit_off[0];
+    g.stats[0] = n_rays; g.stats[1] = g.stats[2] = g.stats[3] = 0;
+    if (n_rays <= 0) return ICPB200_OK;                                   // mapping.py:113-114
+    const int n_tiles = g.tiles_x * g.tiles_y;
+    const size_t n_cells = (size_t)g.nx * g.ny;
+    const long long max_chunk_rays = [&] {
+        long long m = 0;
+        for (int s0 = 0; s0 < n_scans; s0 += kOccMaxChunkScans)
+            m = std::max(m, h_hit_off[std::min(n_scans, s0 + kOccMaxChunkScans)] - h_hit_off[s0]);
+        return m;
+    }();
+    if (g.origin_cell.reserve(sizeof(int2) * (size_t)n_scans) || g.ray_cell.reserve(sizeof(int2) * (size_t)max_chunk_rays) ||
+        g.ray_scan.reserve(sizeof(int) * (size_t)max_chunk_rays) || g.order.reserve(sizeof(int) * (size_t)n_tiles) ||
+        g.small.reserve(256))
+        return ICPB200_ERR_CUDA;
+    if (!g.slotmap.p) {
+        if (g.slotmap.reserve(sizeof(unsigned) * n_cells)) return ICPB200_ERR_CUDA;
+        ICPB_CUDA(cudaMemsetAsync(g.slotmap.p, 0xff, sizeof(unsigned) * n_cells, st));
+    }
+    ICPB_CUDA(cudaMemsetAsync(g.small.p, 0, 256, st));
+    occ_fast_origins<<<(n_scans + 255) / 256, 256, 0, st>>>(d_origins, n_scans, g.min_x, g.min_y, g.res, g.origin_cell.as<int2>());
+    ICPB_LAUNCH_CHECK();
+    long long tot[4] = {0, 0, 0, 0};
+    for (int s0 = 0; s0 < n_scans; s0 += kOccMaxChunkScans) {
+        const int cs = std::min(kOccMaxChunkScans, n_scans - s0);
+        int rc = fast_chunk(g, n_scans, s0, cs, d_origins, d_hits, d_hit_off, h_hit_off, st);
+        if (rc == 1) {
+            long long keep[4] = {g.stats[0], g.stats[1], g.stats[2], g.stats[3]};
+            std::vector<long long> off((size_t)cs + 1);
+            for (int k = 0; k <= cs; ++k) off[k] = h_hit_off[s0 + k] - h_hit_off[s0];
+            // the ordered path wants offsets that start at 0: shift the device copies as well
+            if (g.hit_off_shift.reserve(sizeof(long long) * off.size())) return ICPB200_ERR_CUDA;
+            ICPB_CUDA(cudaMemcpyAsync(g.hit_off_shift.p, off.data(), sizeof(long long) * off.size(), cudaMemcpyHostToDevice, st));
+            ICPB_CUDA(cudaStreamSynchronize(st));
+            rc = occ_update_ordered(g, cs, d_origins + 2 * (size_t)s0, d_hits + 2 * (size_t)h_hit_off[s0],
+                                    g.hit_off_shift.as<long long>(), off.data(), st);
+            if (rc) return rc;
+            for (int k = 1; k < 4; ++k) tot[k] += g.stats[k];
+            for (int k = 0; k < 4; ++k) g.stats[k] = keep[k];
+            continue;
+        }
+        if (rc) return rc;
+        unsigned char host_small[256];
+        ICPB_CUDA(cudaMemcpyAsync(host_small, g.small.p, 256, cudaMemcpyDeviceToHost, st));
+        ICPB_CUDA(cudaStreamSynchronize(st));
+        const unsigned long long* hs = reinterpret_cast<const unsigned long long*>(host_small + 64);
+        for (int k = 1; k < 4; ++k) tot[k] += (long long)hs[k];
+        ICPB_CUDA(cudaMemsetAsync(g.small.as<unsigned char>() + 64, 0, 64, st));
+        if (reinterpret_cast<const unsigned*>(host_small)[3]) {
+            set_error("grid_update: more than 4095 hits landed in one cell within one scan (unsupported)");
+            return ICPB200_ERR_LIMIT;
+        }
+    }
+    g.stats[0] = n_rays;
+    for (int k = 1; k < 4; ++k) g.stats[k] = tot[k];
+    g.seen_nonempty_scan = true;
+    return ICPB200_OK;
+}
+
+}  // namespace icpb

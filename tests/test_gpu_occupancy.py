@@ -13,6 +13,14 @@ pytestmark = pytest.mark.gpu
 GKW = dict(resolution=0.05, p_hit=0.85, p_miss=0.42, log_odds_min=-8.0, log_odds_max=8.0)
 
 
+@pytest.fixture(params=["fast", "ordered"], autouse=True)
+def occ_path(request, monkeypatch):
+    """Every test runs on both device paths: the order-free pipeline (default)
+    and the ordered tile replay (read by icpb200_grid_create)."""
+    monkeypatch.setenv("ICPB200_OCC_PATH", request.param)
+    return request.param
+
+
 def make_pair(bounds, **kw):
     from utilities import OccupancyGrid2D
     return OccupancyGrid2D(*bounds, **kw), oo.GridOracleC(*bounds, **kw)
@@ -158,3 +166,19 @@ def test_empty_inputs_and_limits():
     assert np.isfinite(grid.log_odds).all()
     with pytest.raises(RuntimeError):
         grid._dev.update(np.zeros((1, 2)), np.zeros((3, 2)), np.array([1, 3]))   # hit_off[0] != 0
+
+
+def test_many_scans_cross_the_chunk_boundary_and_neutral_miss():
+    """2300 small scans in one call (the device path works in chunks of 2048
+    scans) and p_miss = 0.5 (l_miss == 0: free cells must not move)."""
+    rng = np.random.default_rng(5)
+    bounds = (-6.4, 6.4, -6.4, 6.4)
+    n = 2300
+    origins = rng.uniform(-5, 5, size=(n, 2))
+    clouds = [o + rng.normal(scale=2.5, size=(int(rng.integers(0, 6)), 2)) for o in origins]
+    flat, off = synth.pack_ragged(clouds)
+    for kw in (GKW, dict(GKW, p_miss=0.5), dict(GKW, p_miss=0.49999)):
+        gpu, ref = make_pair(bounds, **kw)
+        gpu._dev.update(origins, flat, off)
+        ref.update_many(origins, flat, off, fast=True)
+        assert_same(gpu, ref, str(kw))
