@@ -21,7 +21,7 @@
 // Tiles are independent, so there is no grid-wide synchronisation per scan;
 // HBM sees each active tile once in and once out per batch, the runs once,
 // the endpoints twice.  Multi-GPU: a rank owns the tiles t with
-// t % world == rank and skips all others in step 2.
+// occ_owner(tile) == rank and skips all others in step 2.
 #include "icp_b200.h"
 #include "bres.cuh"
 #include "common.cuh"
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) occ_bin(const BinArgs a) {
             t.tile = hit_tile; t.n0 = hit_cell; t.j0 = 0; t.len = 0;
         }
         if (!__any_sync(0xffffffffu, has)) break;
-        const bool owned = has && (t.tile % a.world == a.rank);
+        const bool owned = has && occ_owner((t.tile % a.tiles_x) * TS, (t.tile / a.tiles_x) * TS, a.nx, a.world) == a.rank;
         const unsigned long long gi = owned ? (unsigned long long)t.tile * a.chunk_scans + sl : ~0ull;
         const unsigned peers = __match_any_sync(0xffffffffu, gi);
         const int leader = __ffs(peers) - 1;
@@ -538,7 +538,8 @@ __global__ void occ_finalize_virgin(float* grid, int nx, int ny, int tiles_x, in
     if (i >= (size_t)nx * ny) return;
     const int x = (int)(i % nx), y = (int)(i / nx);
     const int tile = (y / TS) * tiles_x + (x / TS);
-    if (tile % world != rank) return;
+    (void)tile;
+    if (occ_owner(x, y, nx, world) != rank) return;
     if (grid[i] == 0.0f) grid[i] = clamp0;
 }
 
@@ -561,7 +562,7 @@ int occ_update_device(OccGrid& g, int n_scans, const double* d_origins, const do
                       const long long* d_hit_off, const long long* h_hit_off, cudaStream_t st) {
     if (g.use_fast && !g.zero_outside_clamp) {
         const int rc = occ_update_fast(g, n_scans, d_origins, d_hits, d_hit_off, h_hit_off, st);
-        if (rc < 0) { g.slotmap.release(); g.ord.release(); }      // claims may be left behind: start clean next time
+        if (rc < 0) { g.slotmap.release(); g.ord.release(); g.ncount.release(); }      // claims may be left behind: start clean next time
         return rc;
     }
     return occ_update_ordered(g, n_scans, d_origins, d_hits, d_hit_off, h_hit_off, st);

@@ -7,9 +7,17 @@
 namespace icpb {
 
 constexpr int kOccTile = 32;                       // cells per tile edge (power of two)
+constexpr int kOccOwnTile = 64;                    // multi-GPU ownership granularity (cells); see occ_owner
 constexpr int kOccMaxChunkScans = 2048;            // scans replayed per tile pass
 constexpr long long kOccMaxMatrix = 64LL << 20;    // (tile, scan) counters per pass
 constexpr size_t kOccOrdBudget = 1ull << 30;       // order-free path: (hit cell, scan) counters per chunk (4 GiB)
+
+// Spatial sharding: the grid is cut into kOccOwnTile-cell blocks dealt round-robin to the ranks.
+// Both device paths (32-cell tiles of the ordered replay, 64-cell tiles of the order-free path)
+// use this one rule, so a cell never changes owner between calls.
+__host__ __device__ inline int occ_owner(int x, int y, int nx, int world) {
+    return (int)(((long long)(y / kOccOwnTile) * ((nx + kOccOwnTile - 1) / kOccOwnTile) + (x / kOccOwnTile)) % world);
+}
 
 struct OccGrid {
     int nx = 0, ny = 0, tiles_x = 0, tiles_y = 0;
@@ -28,7 +36,7 @@ struct OccGrid {
     DevBuf origin_cell, ray_cell, ray_scan;
     DevBuf counts, offsets, sums, runs, order, small, tile_prof;
     // order-free path (occupancy_fast.cu)
-    DevBuf slotmap, slot_cell, ord, tile_count, hit_off_shift;
+    DevBuf slotmap, slot_cell, ord, tile_count, hit_off_shift, items, multi, ncount, ev, ev_count;
     int fast_ctas = 0;
     bool use_fast = true;                          // ICPB200_OCC_PATH=ordered forces the ordered tile replay
     int split = 1;                                 // lock-step windows per 32-run chunk (tuning knob)

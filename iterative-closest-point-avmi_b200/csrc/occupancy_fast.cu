@@ -44,7 +44,7 @@ namespace icpb {
 
 namespace {
 
-constexpr int TS = kOccTile;
+constexpr int TS = kOccOwnTile;               // 64-cell tiles: an owned block is exactly one tile
 constexpr int TCELLS = TS * TS;
 constexpr unsigned kNone = 0xffffffffu;      // slot map: not a hit cell
 constexpr unsigned kClaimed = 0xfffffffeu;   // slot map: being assigned
@@ -53,9 +53,10 @@ constexpr unsigned kMissMask = kHitUnit - 1u;
 constexpr int kTileNT = 256;
 
 // 16-byte run record: everything the tile kernel needs to walk the run.
-//   w0 = local cell of the first step (10) | x-major (1) | major + (1) | minor + (1) | len-1 (5) | chunk-local scan (11)
+//   w0 = local cell of the first step (12) | x-major (1) | major + (1) | minor + (1) | len-1 (6) | chunk-local scan (11)
 //   w1 = Bresenham error term at the first step   w2 = dmaj   w3 = dmin
-constexpr int kRunXMajor = 1 << 10, kRunMajPos = 1 << 11, kRunMinPos = 1 << 12;
+constexpr int kRunXMajor = 1 << 12, kRunMajPos = 1 << 13, kRunMinPos = 1 << 14;
+static_assert(TS == 64 && kOccMaxChunkScans <= 2048, "run record bit layout");
 
 struct FastArgs {
     // rays
@@ -73,7 +74,8 @@ struct FastArgs {
     // hit cells
     unsigned* slotmap;                        // ny * nx
     unsigned* slot_cell;                      // slot -> cell
-    unsigned* ord;                            // [slot][chunk_scans]
+    unsigned* ord;                            // [slot][ord_stride]
+    int ord_stride;
     // binning
     unsigned* tile_count;                     // count pass: += 1 ; fill pass: cursor
     const unsigned* tile_off;
@@ -83,7 +85,7 @@ struct FastArgs {
     unsigned long long* stats;
 };
 
-__device__ __forceinline__ int swz(int idx) { return idx ^ ((idx / TS) & 31); }
+__device__ __forceinline__ int swz(int idx) { return idx ^ ((idx / TS) & 31); }   // bank = (x ^ y) & 31
 
 // Tile crossings of one ray with the divisions done in 32 bits whenever the ray
 // is short enough (always, for endpoints inside a <= 16k-cell grid); same runs
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(256) occ_fast_rays(const FastArgs a) {
                     }
                 } else {
                     const unsigned slot = a.slotmap[cell];
-                    const unsigned old = atomicAdd(&a.ord[(size_t)slot * a.chunk_scans + sl], kHitUnit);
+                    const unsigned old = atomicAdd(&a.ord[(size_t)slot * a.ord_stride + sl], kHitUnit);
                     if ((old >> 20) == 4095u) a.small[3] = 1u;
                 }
             }
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(256) occ_fast_rays(const FastArgs a) {
                 uint4 run;
                 run.x = (unsigned)((y % TS) * TS + (x % TS)) | (it.g.xmajor ? kRunXMajor : 0) |
                         (it.g.smaj > 0 ? kRunMajPos : 0) | (it.g.smin > 0 ? kRunMinPos : 0) |
-                        ((unsigned)(t.len - 1) << 13) | ((unsigned)sl << 18);
+                        ((unsigned)(t.len - 1) << 15) | ((unsigned)sl << 21);
                 // RunWalker::start: (2n+2)*dmin - 2*dmaj*j - dmaj, bounded by 2*dmaj + 2*dmin
                 run.y = (unsigned)(int)((2ll * t.n0 + 2) * it.g.dmin - 2ll * it.g.dmaj * t.j0 - it.g.dmaj);
                 run.z = (unsigned)it.g.dmaj;
@@ -248,20 +250,27 @@ __global__ void __launch_bounds__(256) occ_fast_rays(const FastArgs a) {
 }
 
 // ---- 2. scan of the per-tile run counts + active tiles, heaviest first ---------------
+// Work items: a tile's runs are cut into pieces of at most kItemRuns, so that the busiest
+// tiles (tens of thousands of runs) do not set the length of the tile kernel.  Tiles with
+// several items combine their partial counts in a global per-cell counter (`multi` lists them).
+constexpr unsigned kItemRuns = 2048;
+
 __global__ void __launch_bounds__(1024) occ_tile_scan(const unsigned* __restrict__ counts, int n_tiles,
                                                       unsigned* __restrict__ offsets /* n_tiles + 1 */,
-                                                      int* __restrict__ order, unsigned* __restrict__ small) {
+                                                      uint2* __restrict__ items, int* __restrict__ multi,
+                                                      unsigned* __restrict__ small) {
     __shared__ unsigned wsum[32];
     __shared__ unsigned carry;
     __shared__ int hist[33], start[33];
+    __shared__ unsigned n_multi;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry = 0;
+    if (tid == 0) { carry = 0; n_multi = 0; }
     if (tid < 33) hist[tid] = 0;
     __syncthreads();
     for (int b0 = 0; b0 < n_tiles; b0 += 1024) {
         const int t = b0 + tid;
         const unsigned v = t < n_tiles ? counts[t] : 0u;
-        if (v) atomicAdd(&hist[32 - __clz(v)], 1);
+        if (v) atomicAdd(&hist[32 - __clz(v)], (int)((v + kItemRuns - 1) / kItemRuns));
         unsigned inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -281,22 +290,37 @@ __global__ void __launch_bounds__(1024) occ_tile_scan(const unsigned* __restrict
         offsets[n_tiles] = carry;
         small[0] = carry;
         int run = 0;
-        for (int b = 32; b >= 1; --b) { start[b] = run; run += hist[b]; }
-        small[1] = (unsigned)run;
+        for (int b = 32; b >= 1; --b) { start[b] = run; run += hist[b]; }      // heaviest tiles first
+        small[1] = (unsigned)run;                                               // number of items
     }
     __syncthreads();
     for (int t = tid; t < n_tiles; t += 1024) {
         const unsigned v = counts[t];
-        if (v) order[atomicAdd(&start[32 - __clz(v)], 1)] = t;
+        if (v) {
+            const int n_it = (int)((v + kItemRuns - 1) / kItemRuns);
+            const int base = atomicAdd(&start[32 - __clz(v)], n_it);
+            for (int i = 0; i < n_it; ++i) items[base + i] = make_uint2((unsigned)t, (unsigned)i);
+            if (n_it > 1) multi[atomicAdd(&n_multi, 1u)] = t;
+        }
     }
+    __syncthreads();
+    if (tid == 0) small[5] = n_multi;
 }
 
 // ---- the add chain (mapping.py:129, 139, 141) ------------------------------------------
 __device__ __forceinline__ float fast_chain(float x, unsigned m, unsigned k, double l_hit, double l_miss,
                                             float lo, float hi) {
-    if (m == 0u) {                            // already pinned where the misses push it
-        if (l_miss < 0.0 && x <= lo) return lo;
-        if (l_miss > 0.0 && x >= hi) return hi;
+    // Nothing is clipped inside a scan, so the value before the clip is x + m*l_hit + k*l_miss up to
+    // the float rounding of each add (<= 2^-24 of the running magnitude, itself <= mag).  When that
+    // cannot bring it back inside the clamp interval the clip alone decides -- the steady state of
+    // free space (pinned low, misses only) and of walls (pinned high, hits outweigh the misses).
+    {
+        const double dm = (double)m, dk = (double)k;
+        const double t = (double)x + dm * l_hit + dk * l_miss;
+        const double mag = fabs((double)x) + dm * fabs(l_hit) + dk * fabs(l_miss);
+        const double err = (dm + dk) * mag * 1.2e-7;
+        if (t - err >= (double)hi) return hi;
+        if (t + err <= (double)lo) return lo;
     }
     for (unsigned i = 0; i < m; ++i) {        // mapping.py:129 -- m hits, each x = f32(f64(x) + l_hit)
         const float y = (float)((double)x + l_hit);
@@ -325,11 +349,13 @@ struct TileArgs {
     int nx, ny, tiles_x;
     const unsigned* tile_off;
     const uint4* runs;
-    const int* order;
-    unsigned* small;                          // [1] n_active [2] queue
+    const uint2* items;                       // (tile, piece)
+    const int* multi;                         // tiles cut into several items
+    unsigned* small;                          // [1] n_items [2] queue [5] n_multi
+    unsigned* ncount;                         // ny * nx partial miss counts of multi-item tiles (kept zero)
     const unsigned* slotmap;
     unsigned* ord;
-    int chunk_scans;
+    int ord_stride;
     double l_hit, l_miss;
     float lo, hi;
 };
@@ -342,9 +368,9 @@ __device__ __forceinline__ void walk_runs(const TileArgs& a, unsigned beg, unsig
         int len = 0, idx = 0, d = 0, inc = 0, dec = 0, step_maj = 0, step_both = 0, sl = 0;
         if (e < end) {
             const uint4 r = __ldg(a.runs + e);
-            idx = (int)(r.x & 1023u);
-            len = (int)((r.x >> 13) & 31u) + 1;
-            sl = (int)(r.x >> 18);
+            idx = (int)(r.x & 4095u);
+            len = (int)((r.x >> 15) & 63u) + 1;
+            sl = (int)(r.x >> 21);
             const int maj = (r.x & kRunXMajor) ? ((r.x & kRunMajPos) ? 1 : -1) : ((r.x & kRunMajPos) ? TS : -TS);
             const int mnr = (r.x & kRunXMajor) ? ((r.x & kRunMinPos) ? TS : -TS) : ((r.x & kRunMinPos) ? 1 : -1);
             step_maj = maj; step_both = maj + mnr;
@@ -356,7 +382,7 @@ __device__ __forceinline__ void walk_runs(const TileArgs& a, unsigned beg, unsig
                 const int c = swz(idx);
                 if (HITS) {
                     const unsigned s = slot[c];
-                    if (s != kNone) atomicAdd(&a.ord[(size_t)s * a.chunk_scans + sl], 1u);
+                    if (s != kNone) atomicAdd(&a.ord[(size_t)s * a.ord_stride + sl], 1u);
                     else atomicAdd(&cnt[c], 1u);
                 } else {
                     atomicAdd(&cnt[c], 1u);
@@ -372,18 +398,18 @@ __device__ __forceinline__ void walk_runs(const TileArgs& a, unsigned beg, unsig
 __global__ void __launch_bounds__(kTileNT) occ_fast_tiles(const TileArgs a) {
     __shared__ unsigned cnt[TCELLS];
     __shared__ unsigned slot[TCELLS];
-    __shared__ int cur_tile;
+    __shared__ uint2 cur_item;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned n_active = a.small[1];
+    const unsigned n_items = a.small[1];
     for (;;) {
         __syncthreads();
         if (tid == 0) {
             const unsigned q = atomicAdd(&a.small[2], 1u);
-            cur_tile = q < n_active ? a.order[q] : -1;
+            cur_item = q < n_items ? a.items[q] : make_uint2(kNone, 0u);
         }
         __syncthreads();
-        const int t = cur_tile;
-        if (t < 0) break;
+        if (cur_item.x == kNone) break;
+        const int t = (int)cur_item.x;
         const int tx0 = (t % a.tiles_x) * TS, ty0 = (t / a.tiles_x) * TS;
         bool any = false;
         for (int c = tid; c < TCELLS; c += kTileNT) {
@@ -394,53 +420,104 @@ __global__ void __launch_bounds__(kTileNT) occ_fast_tiles(const TileArgs a) {
             any |= s != kNone;
         }
         const int has_hits = __syncthreads_or(any);
-        const unsigned beg = a.tile_off[t], end = a.tile_off[t + 1];
+        const unsigned t_beg = a.tile_off[t], t_end = a.tile_off[t + 1];
+        const unsigned beg = t_beg + cur_item.y * kItemRuns, end = min(beg + kItemRuns, t_end);
         if (has_hits) walk_runs<true>(a, beg, end, cnt, slot, warp, lane);
         else          walk_runs<false>(a, beg, end, cnt, slot, warp, lane);
         __syncthreads();
+        const bool whole = t_end - t_beg <= kItemRuns;
         for (int c = tid; c < TCELLS; c += kTileNT) {
             const unsigned n = cnt[swz(c)];
             if (n) {
                 const int x = tx0 + (c & (TS - 1)), y = ty0 + (c / TS);
-                float* g = a.grid + (size_t)y * a.nx + x;
-                *g = fast_chain(*g, 0u, n, a.l_hit, a.l_miss, a.lo, a.hi);
+                const size_t cell = (size_t)y * a.nx + x;
+                if (whole) a.grid[cell] = fast_chain(a.grid[cell], 0u, n, a.l_hit, a.l_miss, a.lo, a.hi);
+                else atomicAdd(&a.ncount[cell], n);
             }
         }
     }
 }
 
+// tiles that were cut into several items: total misses per cell -> one chain
+__global__ void __launch_bounds__(256) occ_fast_apply_multi(const TileArgs a) {
+    const int t = a.multi[blockIdx.x];
+    const int tx0 = (t % a.tiles_x) * TS, ty0 = (t / a.tiles_x) * TS;
+    for (int c = threadIdx.x; c < TCELLS; c += 256) {
+        const int x = tx0 + (c & (TS - 1)), y = ty0 + (c / TS);
+        if (x >= a.nx || y >= a.ny) continue;
+        const size_t cell = (size_t)y * a.nx + x;
+        const unsigned n = a.ncount[cell];
+        if (n) {
+            a.ncount[cell] = 0u;
+            a.grid[cell] = fast_chain(a.grid[cell], 0u, n, a.l_hit, a.l_miss, a.lo, a.hi);
+        }
+    }
+}
+
 // ---- 5. ordered replay of the hit cells ---------------------------------------------------
-__global__ void __launch_bounds__(256) occ_fast_replay(float* __restrict__ grid, unsigned* __restrict__ slotmap,
-                                                       const unsigned* __restrict__ slot_cell, unsigned* __restrict__ ord,
-                                                       const unsigned* __restrict__ small, int chunk_scans,
-                                                       double l_hit, double l_miss, float lo, float hi) {
+// The rows of `ord` are sparse (a wall cell is seen by ~7 % of the scans), so a lane that
+// walked its own row would idle most of the time, and a warp that walked one row would run
+// the chain 32 times redundantly.  Two kernels instead:
+//   occ_fast_compact  one warp per hit cell, coalesced: the non-zero words of its row are
+//                     moved, in scan order, to the front of the matching row of `ev`
+//                     (and cleared in `ord`, which is thereby left clean for the next chunk)
+//   occ_fast_chain    one lane per hit cell: runs the add chain over its event list --
+//                     in scan order, which is all the reference's semantics need.
+__global__ void __launch_bounds__(256) occ_fast_compact(unsigned* __restrict__ ord, unsigned* __restrict__ ev,
+                                                        unsigned* __restrict__ ev_count, const unsigned* __restrict__ small,
+                                                        int chunk_scans, int stride) {
     const unsigned n_slots = small[4];
     const unsigned slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (slot >= n_slots) return;
-    const unsigned cell = slot_cell[slot];
-    unsigned* row = ord + (size_t)slot * chunk_scans;
-    float x = grid[cell];
-    for (int s0 = 0; s0 < chunk_scans; s0 += 128) {
-        unsigned v[4];
+    unsigned* row = ord + (size_t)slot * stride;
+    unsigned* out = ev + (size_t)slot * stride;
+    const unsigned lt = (1u << lane) - 1u;
+    int pos = 0;
+    for (int s0 = 0; s0 < chunk_scans; s0 += 256) {
+        unsigned v[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
             const int s = s0 + u * 32 + lane;
-            v[u] = s < chunk_scans ? row[s] : 0u;
+            v[u] = s < chunk_scans ? __ldcs(row + s) : 0u;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            unsigned nz = __ballot_sync(0xffffffffu, v[u] != 0u);
-            if (v[u]) row[s0 + u * 32 + lane] = 0u;                 // leave the table clean for the next chunk
-            while (nz) {
-                const int l = __ffs(nz) - 1;
-                nz &= nz - 1;
-                const unsigned w = __shfl_sync(0xffffffffu, v[u], l);
-                x = fast_chain(x, w >> 20, w & kMissMask, l_hit, l_miss, lo, hi);
+        for (int u = 0; u < 8; ++u) {
+            const unsigned nz = __ballot_sync(0xffffffffu, v[u] != 0u);
+            if (v[u]) {
+                row[s0 + u * 32 + lane] = 0u;
+                out[pos + __popc(nz & lt)] = v[u];
             }
+            pos += __popc(nz);
         }
     }
-    if (lane == 0) {
+    if (lane == 0) ev_count[slot] = (unsigned)pos;
+}
+
+__global__ void __launch_bounds__(128) occ_fast_chain(float* __restrict__ grid, unsigned* __restrict__ slotmap,
+                                                      const unsigned* __restrict__ slot_cell, const unsigned* __restrict__ ev,
+                                                      const unsigned* __restrict__ ev_count, const unsigned* __restrict__ small,
+                                                      int stride, double l_hit, double l_miss, float lo, float hi) {
+    const unsigned n_slots = small[4];
+    const unsigned slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = slot < n_slots;
+    const unsigned cell = valid ? slot_cell[slot] : 0u;
+    const int n = valid ? (int)ev_count[slot] : 0;
+    float x = valid ? grid[cell] : 0.f;
+    const uint4* row = reinterpret_cast<const uint4*>(ev + (size_t)slot * stride);      // stride is a multiple of 4
+    const int maxn = (int)__reduce_max_sync(0xffffffffu, (unsigned)n);
+    uint4 w_next = n > 0 ? __ldcs(row) : make_uint4(0u, 0u, 0u, 0u);
+    for (int p = 0; p < maxn; p += 4) {
+        if (p < n) {
+            const uint4 w = w_next;
+            if (p + 4 < n) w_next = __ldcs(row + (p >> 2) + 1);          // fetched while this group is replayed
+            x = fast_chain(x, w.x >> 20, w.x & kMissMask, l_hit, l_miss, lo, hi);
+            if (p + 1 < n) x = fast_chain(x, w.y >> 20, w.y & kMissMask, l_hit, l_miss, lo, hi);
+            if (p + 2 < n) x = fast_chain(x, w.z >> 20, w.z & kMissMask, l_hit, l_miss, lo, hi);
+            if (p + 3 < n) x = fast_chain(x, w.w >> 20, w.w & kMissMask, l_hit, l_miss, lo, hi);
+        }
+    }
+    if (valid) {
         grid[cell] = x;
         slotmap[cell] = kNone;
     }
@@ -454,9 +531,13 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
     const long long rb = h_hit_off[s0], re = h_hit_off[s0 + cs];
     const long long nr = re - rb;
     if (nr == 0) return ICPB200_OK;
-    const int n_tiles = g.tiles_x * g.tiles_y;
+    const int tiles_x = (g.nx + TS - 1) / TS, tiles_y = (g.ny + TS - 1) / TS;
+    const int n_tiles = tiles_x * tiles_y;
+    // a ray crosses at most tiles_x + tiles_y + 1 tiles, which bounds the number of work items
+    const size_t max_items = (size_t)n_tiles + (size_t)(((unsigned long long)nr * (tiles_x + tiles_y + 1)) / kItemRuns) + 1;
     if (g.tile_count.reserve(sizeof(unsigned) * (size_t)n_tiles) || g.offsets.reserve(sizeof(unsigned) * ((size_t)n_tiles + 1)) ||
-        g.slot_cell.reserve(sizeof(unsigned) * (size_t)nr))
+        g.slot_cell.reserve(sizeof(unsigned) * (size_t)nr) || g.items.reserve(sizeof(uint2) * max_items) ||
+        g.multi.reserve(sizeof(int) * (size_t)n_tiles))
         return ICPB200_ERR_CUDA;
     unsigned* d_small = g.small.as<unsigned>();
     unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(g.small.as<unsigned char>() + 64);
@@ -469,33 +550,36 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
     a.ray_begin = rb; a.ray_end = re;
     a.scan_begin = s0; a.chunk_scans = cs; a.n_scans = n_scans;
     a.min_x = g.min_x; a.min_y = g.min_y; a.res = g.res;
-    a.nx = g.nx; a.ny = g.ny; a.tiles_x = g.tiles_x; a.n_tiles = n_tiles;
+    a.nx = g.nx; a.ny = g.ny; a.tiles_x = tiles_x; a.n_tiles = n_tiles;
     a.rank = g.rank; a.world = g.world;
     a.ray_cell = g.ray_cell.as<int2>();
     a.ray_scan = g.ray_scan.as<int>();
     a.origin_cell = g.origin_cell.as<int2>();
     a.slotmap = g.slotmap.as<unsigned>();
     a.slot_cell = g.slot_cell.as<unsigned>();
-    a.ord = nullptr;
+    a.ord = nullptr; a.ord_stride = 0;
     a.tile_count = g.tile_count.as<unsigned>();
     a.tile_off = nullptr; a.runs = nullptr;
     a.small = d_small; a.stats = d_stats;
     const unsigned nblk = (unsigned)((nr + 255) / 256);
     occ_fast_rays<false><<<nblk, 256, 0, st>>>(a);
     ICPB_LAUNCH_CHECK();
-    occ_tile_scan<<<1, 1024, 0, st>>>(g.tile_count.as<unsigned>(), n_tiles, g.offsets.as<unsigned>(), g.order.as<int>(), d_small);
+    occ_tile_scan<<<1, 1024, 0, st>>>(g.tile_count.as<unsigned>(), n_tiles, g.offsets.as<unsigned>(), g.items.as<uint2>(), g.multi.as<int>(), d_small);
     ICPB_LAUNCH_CHECK();
     unsigned h_small[8];
     ICPB_CUDA(cudaMemcpyAsync(h_small, d_small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
     ICPB_CUDA(cudaStreamSynchronize(st));
     const unsigned total_runs = h_small[0], n_slots = h_small[4];
-    const size_t ord_words = (size_t)n_slots * cs;
+    const int stride = (cs + 3) & ~3;
+    const size_t ord_words = (size_t)n_slots * stride;
     if (ord_words > kOccOrdBudget) {
         // too many hit cells for the dense table: undo the claims, the ordered path takes the chunk
         if (n_slots) {
-            occ_fast_replay<<<(n_slots * 32u + 255u) / 256u, 256, 0, st>>>(g.grid.as<float>(), g.slotmap.as<unsigned>(),
-                                                                           g.slot_cell.as<unsigned>(), nullptr, d_small, 0, g.l_hit,
-                                                                           g.l_miss, (float)g.lo_min, (float)g.lo_max);
+            if (g.ev_count.reserve(sizeof(unsigned) * (size_t)n_slots)) return ICPB200_ERR_CUDA;
+            ICPB_CUDA(cudaMemsetAsync(g.ev_count.p, 0, sizeof(unsigned) * (size_t)n_slots, st));
+            occ_fast_chain<<<(n_slots + 127u) / 128u, 128, 0, st>>>(g.grid.as<float>(), g.slotmap.as<unsigned>(),
+                                                                    g.slot_cell.as<unsigned>(), nullptr, g.ev_count.as<unsigned>(), d_small,
+                                                                    0, g.l_hit, g.l_miss, (float)g.lo_min, (float)g.lo_max);
             ICPB_LAUNCH_CHECK();
         }
         return 1;
@@ -505,10 +589,13 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
         const size_t cap_before = g.ord.cap;
         if (g.ord.reserve(sizeof(unsigned) * std::max<size_t>(ord_words, 1))) return ICPB200_ERR_CUDA;
         if (g.ord.p != before || g.ord.cap != cap_before) ICPB_CUDA(cudaMemsetAsync(g.ord.p, 0, g.ord.cap, st));
+        if (g.ev.reserve(sizeof(unsigned) * std::max<size_t>(ord_words, 1)) ||
+            g.ev_count.reserve(sizeof(unsigned) * std::max<size_t>(n_slots, 1)))
+            return ICPB200_ERR_CUDA;
     }
     if (g.runs.reserve(sizeof(uint4) * ((size_t)total_runs + 64))) return ICPB200_ERR_CUDA;
     ICPB_CUDA(cudaMemsetAsync(g.tile_count.p, 0, sizeof(unsigned) * (size_t)n_tiles, st));
-    a.ord = g.ord.as<unsigned>();
+    a.ord = g.ord.as<unsigned>(); a.ord_stride = stride;
     a.tile_off = g.offsets.as<unsigned>();
     a.runs = g.runs.as<uint4>();
     occ_fast_rays<true><<<nblk, 256, 0, st>>>(a);
@@ -517,24 +604,33 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
     if (total_runs) {
         TileArgs t;
         t.grid = g.grid.as<float>();
-        t.nx = g.nx; t.ny = g.ny; t.tiles_x = g.tiles_x;
+        t.nx = g.nx; t.ny = g.ny; t.tiles_x = tiles_x;
         t.tile_off = g.offsets.as<unsigned>();
         t.runs = g.runs.as<uint4>();
-        t.order = g.order.as<int>();
+        t.items = g.items.as<uint2>();
+        t.multi = g.multi.as<int>();
         t.small = d_small;
+        t.ncount = g.ncount.as<unsigned>();
         t.slotmap = g.slotmap.as<unsigned>();
         t.ord = g.ord.as<unsigned>();
-        t.chunk_scans = cs;
+        t.ord_stride = stride;
         t.l_hit = g.l_hit; t.l_miss = g.l_miss; t.lo = lo; t.hi = hi;
-        const unsigned n_active = h_small[1];
-        const unsigned ctas = std::min<unsigned>(n_active, (unsigned)g.fast_ctas);
+        const unsigned n_items = h_small[1], n_multi = h_small[5];
+        const unsigned ctas = std::min<unsigned>(n_items, (unsigned)g.fast_ctas);
         occ_fast_tiles<<<ctas, kTileNT, 0, st>>>(t);
         ICPB_LAUNCH_CHECK();
+        if (n_multi) {
+            occ_fast_apply_multi<<<n_multi, 256, 0, st>>>(t);
+            ICPB_LAUNCH_CHECK();
+        }
     }
     if (n_slots) {
-        occ_fast_replay<<<(n_slots * 32u + 255u) / 256u, 256, 0, st>>>(g.grid.as<float>(), g.slotmap.as<unsigned>(),
-                                                                       g.slot_cell.as<unsigned>(), g.ord.as<unsigned>(), d_small, cs,
-                                                                       g.l_hit, g.l_miss, lo, hi);
+        occ_fast_compact<<<(n_slots * 32u + 255u) / 256u, 256, 0, st>>>(g.ord.as<unsigned>(), g.ev.as<unsigned>(), g.ev_count.as<unsigned>(),
+                                                                        d_small, cs, stride);
+        ICPB_LAUNCH_CHECK();
+        occ_fast_chain<<<(n_slots + 127u) / 128u, 128, 0, st>>>(g.grid.as<float>(), g.slotmap.as<unsigned>(), g.slot_cell.as<unsigned>(),
+                                                                g.ev.as<unsigned>(), g.ev_count.as<unsigned>(), d_small, stride,
+                                                                g.l_hit, g.l_miss, lo, hi);
         ICPB_LAUNCH_CHECK();
     }
     return ICPB200_OK;
@@ -551,7 +647,7 @@ int occ_update_fast(OccGrid& g, int n_scans, const double* d_origins, const doub
     const long long n_rays = h_hit_off[n_scans] - h_hit_off[0];
     g.stats[0] = n_rays; g.stats[1] = g.stats[2] = g.stats[3] = 0;
     if (n_rays <= 0) return ICPB200_OK;                                   // mapping.py:113-114
-    const int n_tiles = g.tiles_x * g.tiles_y;
+    const int n_tiles = ((g.nx + TS - 1) / TS) * ((g.ny + TS - 1) / TS);
     const size_t n_cells = (size_t)g.nx * g.ny;
     const long long max_chunk_rays = [&] {
         long long m = 0;
@@ -566,6 +662,10 @@ int occ_update_fast(OccGrid& g, int n_scans, const double* d_origins, const doub
     if (!g.slotmap.p) {
         if (g.slotmap.reserve(sizeof(unsigned) * n_cells)) return ICPB200_ERR_CUDA;
         ICPB_CUDA(cudaMemsetAsync(g.slotmap.p, 0xff, sizeof(unsigned) * n_cells, st));
+    }
+    if (!g.ncount.p) {
+        if (g.ncount.reserve(sizeof(unsigned) * n_cells)) return ICPB200_ERR_CUDA;
+        ICPB_CUDA(cudaMemsetAsync(g.ncount.p, 0, sizeof(unsigned) * n_cells, st));
     }
     ICPB_CUDA(cudaMemsetAsync(g.small.p, 0, 256, st));
     occ_fast_origins<<<(n_scans + 255) / 256, 256, 0, st>>>(d_origins, n_scans, g.min_x, g.min_y, g.res, g.origin_cell.as<int2>());

@@ -3,8 +3,8 @@
 * registrations: pairs are independent, so rank r registers a contiguous block
   of the pair list with no data-path collective; one all_gather returns every
   rank's (R, t, error, iters, status) to all ranks.
-* occupancy replay: the grid is cut into 32 x 32-cell tiles owned block-cyclically
-  (tile % world == rank, the rule libicp_b200 applies in icpb200_grid_set_shard);
+* occupancy replay: the grid is cut into 64 x 64-cell blocks owned block-cyclically
+  (block % world == rank, the rule libicp_b200 applies in icpb200_grid_set_shard);
   every rank replays every scan clipped to its own tiles, in scan order, so the
   clamp order matches the reference.  Cells a rank does not own stay exactly 0,
   hence one all_reduce(SUM) reassembles the map bit-exactly.
@@ -17,7 +17,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-TILE = 32          # must equal kOccTile in csrc/occupancy.h
+TILE = 64          # must equal kOccOwnTile in csrc/occupancy.h
 
 
 def world():
