@@ -85,7 +85,6 @@ struct FastArgs {
     unsigned long long* stats;
 };
 
-__device__ __forceinline__ int swz(int idx) { return idx ^ ((idx / TS) & 31); }   // bank = (x ^ y) & 31
 
 // Tile crossings of one ray with the divisions done in 32 bits whenever the ray
 // is short enough (always, for endpoints inside a <= 16k-cell grid); same runs
@@ -360,44 +359,81 @@ struct TileArgs {
     float lo, hi;
 };
 
+// shared-memory accesses by 32-bit shared address (no generic -> shared conversion per step)
+__device__ __forceinline__ void red_shared_inc(unsigned addr) {
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ unsigned ld_shared_u32(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int imad(int a, int b, int c) {      // a * b + c on the FMA pipe
+    int r;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+// Every lane walks one run; a task is 32 consecutive runs of the item.  The counters live in a
+// padded layout (row stride TS + 1 words): lanes of a fan sit in the same column at different
+// rows, which would all be one bank; the cell index is kept in padded space, so the padding
+// costs nothing per step.  The Bresenham error term is kept negated (e = -d): "the minor axis
+// steps too" is then its sign bit and both updates are multiply-adds by that bit (FMA pipe)
+// instead of compare + select chains (the ALU pipe is the busy one).  A lane whose run is over
+// keeps stepping a stale index but counts into a private dummy word: one select, no branch.
+constexpr int TSP = TS + 1;
+constexpr int kPadCells = TS * TSP;
+constexpr int kStepsPerRound = 4;
+
+__device__ __forceinline__ int pad_cell(int idx) { return idx + (idx >> 6); }
+
 template <bool HITS>
-__device__ __forceinline__ void walk_runs(const TileArgs& a, unsigned beg, unsigned end, unsigned* cnt,
-                                          const unsigned* slot, int warp, int lane) {
-    for (unsigned e0 = beg + warp * 32u; e0 < end; e0 += kTileNT) {
-        const unsigned e = e0 + lane;
-        int len = 0, idx = 0, d = 0, inc = 0, dec = 0, step_maj = 0, step_both = 0, sl = 0;
-        if (e < end) {
-            const uint4 r = __ldg(a.runs + e);
-            idx = (int)(r.x & 4095u);
-            len = (int)((r.x >> 15) & 63u) + 1;
-            sl = (int)(r.x >> 21);
-            const int maj = (r.x & kRunXMajor) ? ((r.x & kRunMajPos) ? 1 : -1) : ((r.x & kRunMajPos) ? TS : -TS);
-            const int mnr = (r.x & kRunXMajor) ? ((r.x & kRunMinPos) ? TS : -TS) : ((r.x & kRunMinPos) ? 1 : -1);
-            step_maj = maj; step_both = maj + mnr;
-            d = (int)r.y; dec = 2 * (int)r.z; inc = 2 * (int)r.w;
-        }
-        const int maxlen = (int)__reduce_max_sync(0xffffffffu, (unsigned)len);
-        for (int k = 0; k < maxlen; ++k) {
-            if (k < len) {
-                const int c = swz(idx);
+__device__ __forceinline__ void walk_runs(const TileArgs& a, unsigned beg, unsigned end, unsigned cnt_base,
+                                          unsigned slot_base, unsigned dummy_addr, int warp, int lane) {
+    const unsigned full = 0xffffffffu;
+    unsigned e0 = beg + (unsigned)warp * 32u;
+    if (e0 >= end) return;
+    uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+    if (e0 + lane < end) nxt = __ldg(a.runs + e0 + lane);
+    for (; e0 < end; e0 += kTileNT) {
+        const uint4 w = nxt;
+        const bool have = e0 + lane < end;
+        if (e0 + kTileNT + lane < end) nxt = __ldg(a.runs + e0 + kTileNT + lane);       // next task's record, in flight
+        int idx = pad_cell((int)(w.x & 4095u));
+        int rem = have ? (int)((w.x >> 15) & 63u) + 1 : 0;
+        const unsigned sl = w.x >> 21;
+        const int step_maj = (w.x & kRunXMajor) ? ((w.x & kRunMajPos) ? 1 : -1) : ((w.x & kRunMajPos) ? TSP : -TSP);
+        const int nmnr = (w.x & kRunXMajor) ? ((w.x & kRunMinPos) ? -TSP : TSP) : ((w.x & kRunMinPos) ? -1 : 1);
+        int e = -(int)w.y;
+        const int ndec = -2 * (int)w.z, ninc = -2 * (int)w.w;
+        const int maxlen = (int)__reduce_max_sync(full, (unsigned)rem);
+        for (int k = 0; k < maxlen; k += kStepsPerRound) {
+#pragma unroll
+            for (int u = 0; u < kStepsPerRound; ++u) {
+                const bool act = rem > 0;
+                bool count_here = act;
                 if (HITS) {
-                    const unsigned s = slot[c];
-                    if (s != kNone) atomicAdd(&a.ord[(size_t)s * a.ord_stride + sl], 1u);
-                    else atomicAdd(&cnt[c], 1u);
-                } else {
-                    atomicAdd(&cnt[c], 1u);
+                    const unsigned sidx = ld_shared_u32(act ? (unsigned)imad(idx, 4, (int)slot_base) : slot_base);
+                    const bool on_hit = act && sidx != kNone;
+                    if (__any_sync(full, on_hit)) {
+                        if (on_hit) atomicAdd(&a.ord[(size_t)sidx * a.ord_stride + sl], 1u);
+                        count_here = act && !on_hit;
+                    }
                 }
-                const bool m = d > 0;
-                idx += m ? step_both : step_maj;
-                d += inc - (m ? dec : 0);
+                red_shared_inc(count_here ? (unsigned)imad(idx, 4, (int)cnt_base) : dummy_addr);
+                const int mneg = e >> 31;                                        // -1 iff the minor axis steps too
+                idx = imad(mneg, nmnr, idx + step_maj);
+                e = imad(mneg, ndec, e + ninc);
+                --rem;
             }
         }
     }
 }
 
 __global__ void __launch_bounds__(kTileNT) occ_fast_tiles(const TileArgs a) {
-    __shared__ unsigned cnt[TCELLS];
-    __shared__ unsigned slot[TCELLS];
+    __shared__ unsigned cnt[kPadCells];
+    __shared__ unsigned slot[kPadCells];
+    __shared__ unsigned dummy[kTileNT];           // where idle lanes count
     __shared__ uint2 cur_item;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned n_items = a.small[1];
@@ -415,19 +451,22 @@ __global__ void __launch_bounds__(kTileNT) occ_fast_tiles(const TileArgs a) {
         for (int c = tid; c < TCELLS; c += kTileNT) {
             const int x = tx0 + (c & (TS - 1)), y = ty0 + (c / TS);
             const unsigned s = (x < a.nx && y < a.ny) ? a.slotmap[(size_t)y * a.nx + x] : kNone;
-            slot[swz(c)] = s;
-            cnt[c] = 0u;
+            slot[pad_cell(c)] = s;
+            cnt[pad_cell(c)] = 0u;
             any |= s != kNone;
         }
         const int has_hits = __syncthreads_or(any);
         const unsigned t_beg = a.tile_off[t], t_end = a.tile_off[t + 1];
         const unsigned beg = t_beg + cur_item.y * kItemRuns, end = min(beg + kItemRuns, t_end);
-        if (has_hits) walk_runs<true>(a, beg, end, cnt, slot, warp, lane);
-        else          walk_runs<false>(a, beg, end, cnt, slot, warp, lane);
+        unsigned cnt_base = (unsigned)__cvta_generic_to_shared(cnt), slot_base = (unsigned)__cvta_generic_to_shared(slot);
+        unsigned dummy_addr = (unsigned)__cvta_generic_to_shared(&dummy[tid]);
+        asm volatile("" : "+r"(cnt_base), "+r"(slot_base), "+r"(dummy_addr));     // keep them in registers: no re-derivation per step
+        if (has_hits) walk_runs<true>(a, beg, end, cnt_base, slot_base, dummy_addr, warp, lane);
+        else          walk_runs<false>(a, beg, end, cnt_base, slot_base, dummy_addr, warp, lane);
         __syncthreads();
         const bool whole = t_end - t_beg <= kItemRuns;
         for (int c = tid; c < TCELLS; c += kTileNT) {
-            const unsigned n = cnt[swz(c)];
+            const unsigned n = cnt[pad_cell(c)];
             if (n) {
                 const int x = tx0 + (c & (TS - 1)), y = ty0 + (c / TS);
                 const size_t cell = (size_t)y * a.nx + x;
