@@ -51,12 +51,14 @@ constexpr unsigned kClaimed = 0xfffffffeu;   // slot map: being assigned
 constexpr unsigned kHitUnit = 1u << 20;      // ord word: hits << 20 | misses
 constexpr unsigned kMissMask = kHitUnit - 1u;
 constexpr int kTileNT = 256;
+constexpr int kLenShift = 4, kLenClasses = TS >> kLenShift;      // runs are grouped by length: 1-16, 17-32, 33-48, 49-64
 
 // 16-byte run record: everything the tile kernel needs to walk the run.
 //   w0 = local cell of the first step (12) | x-major (1) | major + (1) | minor + (1) | len-1 (6) | chunk-local scan (11)
 //   w1 = Bresenham error term at the first step   w2 = dmaj   w3 = dmin
 constexpr int kRunXMajor = 1 << 12, kRunMajPos = 1 << 13, kRunMinPos = 1 << 14;
 static_assert(TS == 64 && kOccMaxChunkScans <= 2048, "run record bit layout");
+static_assert(kLenClasses == 4, "occ_tile_scan reads the class counters as uint4");
 
 struct FastArgs {
     // rays
@@ -78,7 +80,7 @@ struct FastArgs {
     int ord_stride;
     // binning
     unsigned* tile_count;                     // count pass: += 1 ; fill pass: cursor
-    const unsigned* tile_off;
+    const unsigned* tile_off;                 // fill pass: start of every (tile, length class) segment
     uint4* runs;
     // small: [0] total runs [1] n_active [2] queue [3] error flag [4] n_slots ; stats (u64 x 4) at +64 bytes
     unsigned* small;
@@ -155,6 +157,7 @@ __global__ void __launch_bounds__(256) occ_fast_rays(const FastArgs a) {
     FastTileIter it;
     it.init_empty();
     int sl = 0;
+    unsigned hit_old_plus1 = 0u;
     if (r < a.ray_end) {
         int2 h;
         int s;
@@ -190,43 +193,56 @@ __global__ void __launch_bounds__(256) occ_fast_rays(const FastArgs a) {
                     }
                 } else {
                     const unsigned slot = a.slotmap[cell];
-                    const unsigned old = atomicAdd(&a.ord[(size_t)slot * a.ord_stride + sl], kHitUnit);
-                    if ((old >> 20) == 4095u) a.small[3] = 1u;
+                    hit_old_plus1 = atomicAdd(&a.ord[(size_t)slot * a.ord_stride + sl], kHitUnit) + 1u;   // checked after the walk
                 }
             }
         }
     }
-    // All lanes walk their rays' tile runs in lock step; runs of the warp that fall
-    // into the same tile take one atomic and consecutive slots.
+    // All lanes walk their rays' tile runs in lock step; runs of the warp that fall into the same
+    // (tile, length class) take one atomic and consecutive slots.  Inside a tile the runs are laid
+    // out by length class, so the 32 runs of a tile-kernel task have similar lengths.  The fill
+    // pass stores a run one iteration late: its slot comes back from the atomic while the next
+    // tile crossing is being computed.
+    bool p_valid = false;
+    unsigned p_base = 0, p_off = 0, p_rank = 0;
+    int p_leader = 0;
+    uint4 p_run = make_uint4(0u, 0u, 0u, 0u);
     for (;;) {
         TileRun t;
         const bool has = it.next(t);
-        if (!__any_sync(0xffffffffu, has)) break;
+        const bool more = __any_sync(0xffffffffu, has);
         const bool owned = has && (t.tile % a.world == a.rank);
-        const unsigned peers = __match_any_sync(0xffffffffu, owned ? t.tile : -1 - lane);
-        const int leader = __ffs(peers) - 1;
-        unsigned base = 0;
-        if (owned && lane == leader) base = atomicAdd(&a.tile_count[t.tile], (unsigned)__popc(peers));
+        const int seg = owned ? t.tile * kLenClasses + ((t.len - 1) >> kLenShift) : -1 - lane;
+        unsigned base = 0, off = 0, peers = 0;
+        int leader = 0;
+        if (more) {
+            peers = __match_any_sync(0xffffffffu, seg);
+            leader = __ffs(peers) - 1;
+            if (owned && lane == leader) base = atomicAdd(&a.tile_count[seg], (unsigned)__popc(peers));
+            if (FILL && owned) off = a.tile_off[seg];
+        }
         if (FILL) {
-            base = __shfl_sync(0xffffffffu, base, leader);
+            const unsigned b = __shfl_sync(0xffffffffu, p_base, p_leader);
+            if (p_valid) a.runs[p_off + b + p_rank] = p_run;
+            p_valid = owned; p_base = base; p_leader = leader; p_off = off; p_rank = (unsigned)__popc(peers & lt_mask);
             if (owned) {
                 int x, y;
                 cell_at(it.g, t.n0, t.j0, x, y);
-                uint4 run;
-                run.x = (unsigned)((y % TS) * TS + (x % TS)) | (it.g.xmajor ? kRunXMajor : 0) |
-                        (it.g.smaj > 0 ? kRunMajPos : 0) | (it.g.smin > 0 ? kRunMinPos : 0) |
-                        ((unsigned)(t.len - 1) << 15) | ((unsigned)sl << 21);
+                p_run.x = (unsigned)((y % TS) * TS + (x % TS)) | (it.g.xmajor ? kRunXMajor : 0) |
+                          (it.g.smaj > 0 ? kRunMajPos : 0) | (it.g.smin > 0 ? kRunMinPos : 0) |
+                          ((unsigned)(t.len - 1) << 15) | ((unsigned)sl << 21);
                 // RunWalker::start: (2n+2)*dmin - 2*dmaj*j - dmaj, bounded by 2*dmaj + 2*dmin
-                run.y = (unsigned)(int)((2ll * t.n0 + 2) * it.g.dmin - 2ll * it.g.dmaj * t.j0 - it.g.dmaj);
-                run.z = (unsigned)it.g.dmaj;
-                run.w = (unsigned)it.g.dmin;
-                a.runs[a.tile_off[t.tile] + base + __popc(peers & lt_mask)] = run;
+                p_run.y = (unsigned)(int)((2ll * t.n0 + 2) * it.g.dmin - 2ll * it.g.dmaj * t.j0 - it.g.dmaj);
+                p_run.z = (unsigned)it.g.dmaj;
+                p_run.w = (unsigned)it.g.dmin;
             }
         } else if (owned) {
             cells += t.len;
             ++nruns;
         }
+        if (!more) break;
     }
+    if (FILL && hit_old_plus1 != 0u && ((hit_old_plus1 - 1u) >> 20) == 4095u) a.small[3] = 1u;
     if (!FILL) {
         __shared__ unsigned long long part[3][8];
 #pragma unroll
@@ -256,6 +272,7 @@ constexpr unsigned kItemRuns = 2048;
 
 __global__ void __launch_bounds__(1024) occ_tile_scan(const unsigned* __restrict__ counts, int n_tiles,
                                                       unsigned* __restrict__ offsets /* n_tiles + 1 */,
+                                                      unsigned* __restrict__ class_off /* [tile][class] */,
                                                       uint2* __restrict__ items, int* __restrict__ multi,
                                                       unsigned* __restrict__ small) {
     __shared__ unsigned wsum[32];
@@ -268,7 +285,9 @@ __global__ void __launch_bounds__(1024) occ_tile_scan(const unsigned* __restrict
     __syncthreads();
     for (int b0 = 0; b0 < n_tiles; b0 += 1024) {
         const int t = b0 + tid;
-        const unsigned v = t < n_tiles ? counts[t] : 0u;
+        uint4 cc = make_uint4(0u, 0u, 0u, 0u);
+        if (t < n_tiles) cc = reinterpret_cast<const uint4*>(counts)[t];
+        const unsigned v = cc.x + cc.y + cc.z + cc.w;
         if (v) atomicAdd(&hist[32 - __clz(v)], (int)((v + kItemRuns - 1) / kItemRuns));
         unsigned inc = v;
 #pragma unroll
@@ -280,7 +299,11 @@ __global__ void __launch_bounds__(1024) occ_tile_scan(const unsigned* __restrict
         __syncthreads();
         unsigned base = carry;
         for (int w = 0; w < warp; ++w) base += wsum[w];
-        if (t < n_tiles) offsets[t] = base + inc - v;
+        if (t < n_tiles) {
+            const unsigned o = base + inc - v;
+            offsets[t] = o;
+            reinterpret_cast<uint4*>(class_off)[t] = make_uint4(o, o + cc.x, o + cc.x + cc.y, o + cc.x + cc.y + cc.z);
+        }
         __syncthreads();
         if (tid == 1023) carry = base + inc;
         __syncthreads();
@@ -294,7 +317,8 @@ __global__ void __launch_bounds__(1024) occ_tile_scan(const unsigned* __restrict
     }
     __syncthreads();
     for (int t = tid; t < n_tiles; t += 1024) {
-        const unsigned v = counts[t];
+        const uint4 cc = reinterpret_cast<const uint4*>(counts)[t];
+        const unsigned v = cc.x + cc.y + cc.z + cc.w;
         if (v) {
             const int n_it = (int)((v + kItemRuns - 1) / kItemRuns);
             const int base = atomicAdd(&start[32 - __clz(v)], n_it);
@@ -574,14 +598,15 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
     const int n_tiles = tiles_x * tiles_y;
     // a ray crosses at most tiles_x + tiles_y + 1 tiles, which bounds the number of work items
     const size_t max_items = (size_t)n_tiles + (size_t)(((unsigned long long)nr * (tiles_x + tiles_y + 1)) / kItemRuns) + 1;
-    if (g.tile_count.reserve(sizeof(unsigned) * (size_t)n_tiles) || g.offsets.reserve(sizeof(unsigned) * ((size_t)n_tiles + 1)) ||
+    if (g.tile_count.reserve(sizeof(unsigned) * kLenClasses * (size_t)n_tiles) || g.offsets.reserve(sizeof(unsigned) * ((size_t)n_tiles + 1)) ||
+        g.class_off.reserve(sizeof(unsigned) * kLenClasses * (size_t)n_tiles) ||
         g.slot_cell.reserve(sizeof(unsigned) * (size_t)nr) || g.items.reserve(sizeof(uint2) * max_items) ||
         g.multi.reserve(sizeof(int) * (size_t)n_tiles))
         return ICPB200_ERR_CUDA;
     unsigned* d_small = g.small.as<unsigned>();
     unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(g.small.as<unsigned char>() + 64);
     ICPB_CUDA(cudaMemsetAsync(d_small, 0, 64, st));
-    ICPB_CUDA(cudaMemsetAsync(g.tile_count.p, 0, sizeof(unsigned) * (size_t)n_tiles, st));
+    ICPB_CUDA(cudaMemsetAsync(g.tile_count.p, 0, sizeof(unsigned) * kLenClasses * (size_t)n_tiles, st));
 
     FastArgs a;
     a.hits = reinterpret_cast<const double2*>(d_hits);
@@ -603,7 +628,7 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
     const unsigned nblk = (unsigned)((nr + 255) / 256);
     occ_fast_rays<false><<<nblk, 256, 0, st>>>(a);
     ICPB_LAUNCH_CHECK();
-    occ_tile_scan<<<1, 1024, 0, st>>>(g.tile_count.as<unsigned>(), n_tiles, g.offsets.as<unsigned>(), g.items.as<uint2>(), g.multi.as<int>(), d_small);
+    occ_tile_scan<<<1, 1024, 0, st>>>(g.tile_count.as<unsigned>(), n_tiles, g.offsets.as<unsigned>(), g.class_off.as<unsigned>(), g.items.as<uint2>(), g.multi.as<int>(), d_small);
     ICPB_LAUNCH_CHECK();
     unsigned h_small[8];
     ICPB_CUDA(cudaMemcpyAsync(h_small, d_small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
@@ -633,9 +658,9 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
             return ICPB200_ERR_CUDA;
     }
     if (g.runs.reserve(sizeof(uint4) * ((size_t)total_runs + 64))) return ICPB200_ERR_CUDA;
-    ICPB_CUDA(cudaMemsetAsync(g.tile_count.p, 0, sizeof(unsigned) * (size_t)n_tiles, st));
+    ICPB_CUDA(cudaMemsetAsync(g.tile_count.p, 0, sizeof(unsigned) * kLenClasses * (size_t)n_tiles, st));
     a.ord = g.ord.as<unsigned>(); a.ord_stride = stride;
-    a.tile_off = g.offsets.as<unsigned>();
+    a.tile_off = g.class_off.as<unsigned>();
     a.runs = g.runs.as<uint4>();
     occ_fast_rays<true><<<nblk, 256, 0, st>>>(a);
     ICPB_LAUNCH_CHECK();
