@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256) occ_fast_rays(const FastArgs a) {
     FastTileIter it;
     it.init_empty();
     int sl = 0;
-    unsigned hit_old_plus1 = 0u;
+    unsigned hit_old = 0u;
     if (r < a.ray_end) {
         int2 h;
         int s;
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(256) occ_fast_rays(const FastArgs a) {
                     }
                 } else {
                     const unsigned slot = a.slotmap[cell];
-                    hit_old_plus1 = atomicAdd(&a.ord[(size_t)slot * a.ord_stride + sl], kHitUnit) + 1u;   // checked after the walk
+                    hit_old = atomicAdd(&a.ord[(size_t)slot * a.ord_stride + sl], kHitUnit);   // looked at after the walk
                 }
             }
         }
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256) occ_fast_rays(const FastArgs a) {
         }
         if (!more) break;
     }
-    if (FILL && hit_old_plus1 != 0u && ((hit_old_plus1 - 1u) >> 20) == 4095u) a.small[3] = 1u;
+    if (FILL && (hit_old >> 20) == 4095u) a.small[3] = 1u;
     if (!FILL) {
         __shared__ unsigned long long part[3][8];
 #pragma unroll
@@ -364,6 +364,16 @@ __device__ __forceinline__ float fast_chain(float x, unsigned m, unsigned k, dou
         if ((l_miss < 0.0 && x <= lo) || (l_miss > 0.0 && x >= hi)) break;
     }
     return fminf(fmaxf(x, lo), hi);           // mapping.py:141
+}
+
+// The same chain written literally, for the ordered replay where m + k is a handful: no early
+// exits to evaluate, three dependent instructions per add.
+__device__ __forceinline__ float lean_chain(float x, unsigned m, unsigned k, double l_hit, double l_miss,
+                                            float lo, float hi) {
+    if (m + k > 8u) return fast_chain(x, m, k, l_hit, l_miss, lo, hi);
+    for (unsigned i = 0; i < m; ++i) x = (float)((double)x + l_hit);      // mapping.py:129
+    for (unsigned i = 0; i < k; ++i) x = (float)((double)x + l_miss);     // mapping.py:139
+    return fminf(fmaxf(x, lo), hi);                                       // mapping.py:141
 }
 
 // ---- 4. tiles ----------------------------------------------------------------------------
@@ -501,20 +511,25 @@ __global__ void __launch_bounds__(kTileNT) occ_fast_tiles(const TileArgs a) {
     }
 }
 
-// tiles that were cut into several items: total misses per cell -> one chain
+// tiles that were cut into several items: total misses per cell -> one chain (a CTA per quarter tile)
 __global__ void __launch_bounds__(256) occ_fast_apply_multi(const TileArgs a) {
-    const int t = a.multi[blockIdx.x];
-    const int tx0 = (t % a.tiles_x) * TS, ty0 = (t / a.tiles_x) * TS;
-    for (int c = threadIdx.x; c < TCELLS; c += 256) {
+    const int t = a.multi[blockIdx.x >> 2];
+    const int tx0 = (t % a.tiles_x) * TS, ty0 = (t / a.tiles_x) * TS + (blockIdx.x & 3) * (TS / 4);
+    unsigned n[4];
+    size_t cell[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int c = threadIdx.x + u * 256;
         const int x = tx0 + (c & (TS - 1)), y = ty0 + (c / TS);
-        if (x >= a.nx || y >= a.ny) continue;
-        const size_t cell = (size_t)y * a.nx + x;
-        const unsigned n = a.ncount[cell];
-        if (n) {
-            a.ncount[cell] = 0u;
-            a.grid[cell] = fast_chain(a.grid[cell], 0u, n, a.l_hit, a.l_miss, a.lo, a.hi);
-        }
+        cell[u] = (size_t)y * a.nx + x;
+        n[u] = (x < a.nx && y < a.ny) ? a.ncount[cell[u]] : 0u;
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        if (n[u]) {
+            a.ncount[cell[u]] = 0u;
+            a.grid[cell[u]] = fast_chain(a.grid[cell[u]], 0u, n[u], a.l_hit, a.l_miss, a.lo, a.hi);
+        }
 }
 
 // ---- 5. ordered replay of the hit cells ---------------------------------------------------
@@ -574,10 +589,10 @@ __global__ void __launch_bounds__(128) occ_fast_chain(float* __restrict__ grid, 
         if (p < n) {
             const uint4 w = w_next;
             if (p + 4 < n) w_next = __ldcs(row + (p >> 2) + 1);          // fetched while this group is replayed
-            x = fast_chain(x, w.x >> 20, w.x & kMissMask, l_hit, l_miss, lo, hi);
-            if (p + 1 < n) x = fast_chain(x, w.y >> 20, w.y & kMissMask, l_hit, l_miss, lo, hi);
-            if (p + 2 < n) x = fast_chain(x, w.z >> 20, w.z & kMissMask, l_hit, l_miss, lo, hi);
-            if (p + 3 < n) x = fast_chain(x, w.w >> 20, w.w & kMissMask, l_hit, l_miss, lo, hi);
+            x = lean_chain(x, w.x >> 20, w.x & kMissMask, l_hit, l_miss, lo, hi);
+            if (p + 1 < n) x = lean_chain(x, w.y >> 20, w.y & kMissMask, l_hit, l_miss, lo, hi);
+            if (p + 2 < n) x = lean_chain(x, w.z >> 20, w.z & kMissMask, l_hit, l_miss, lo, hi);
+            if (p + 3 < n) x = lean_chain(x, w.w >> 20, w.w & kMissMask, l_hit, l_miss, lo, hi);
         }
     }
     if (valid) {
@@ -684,7 +699,7 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
         occ_fast_tiles<<<ctas, kTileNT, 0, st>>>(t);
         ICPB_LAUNCH_CHECK();
         if (n_multi) {
-            occ_fast_apply_multi<<<n_multi, 256, 0, st>>>(t);
+            occ_fast_apply_multi<<<n_multi * 4u, 256, 0, st>>>(t);
             ICPB_LAUNCH_CHECK();
         }
     }
