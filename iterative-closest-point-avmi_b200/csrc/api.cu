@@ -666,7 +666,7 @@ int icpb200_voxel_downsample(const double* pts, int64_t n, int dim, double voxel
 void OccGrid::release_all() {
     DevBuf* bufs[] = {&grid, &origins, &hits, &hit_off, &origin_cell, &ray_cell, &ray_scan,
                       &counts, &offsets, &sums, &runs, &order, &small, &tile_prof,
-                      &slotmap, &slot_cell, &ord, &tile_count, &hit_off_shift, &items, &multi, &ncount, &ev, &ev_count, &class_off};
+                      &slotmap, &slot_cell, &ord, &tile_count, &hit_off_shift, &items, &multi, &ncount, &ev, &ev_count, &class_off, &tile_flag};
     for (DevBuf* b : bufs) b->release();
 }
 

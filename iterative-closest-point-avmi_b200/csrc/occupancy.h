@@ -36,7 +36,7 @@ struct OccGrid {
     DevBuf origin_cell, ray_cell, ray_scan;
     DevBuf counts, offsets, sums, runs, order, small, tile_prof;
     // order-free path (occupancy_fast.cu)
-    DevBuf slotmap, slot_cell, ord, tile_count, hit_off_shift, items, multi, ncount, ev, ev_count, class_off;
+    DevBuf slotmap, slot_cell, ord, tile_count, hit_off_shift, items, multi, ncount, ev, ev_count, class_off, tile_flag;
     int fast_ctas = 0;
     bool use_fast = true;                          // ICPB200_OCC_PATH=ordered forces the ordered tile replay
     int split = 1;                                 // lock-step windows per 32-run chunk (tuning knob)

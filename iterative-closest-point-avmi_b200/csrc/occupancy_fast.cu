@@ -37,6 +37,8 @@
 #include "common.cuh"
 #include "occupancy.h"
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -80,9 +82,11 @@ struct FastArgs {
     int ord_stride;
     // binning
     unsigned* tile_count;                     // count pass: += 1 ; fill pass: cursor
+    unsigned* tile_flag;                      // count pass: 1 = the tile holds a hit cell
     const unsigned* tile_off;                 // fill pass: start of every (tile, length class) segment
     uint4* runs;
-    // small: [0] total runs [1] n_active [2] queue [3] error flag [4] n_slots ; stats (u64 x 4) at +64 bytes
+    // small: [0] total runs [1] items [2] queue A [3] error flag [4] n_slots [5] multi-item tiles
+    //        [6] items of tiles with hit cells (they come first) [7] queue B ; stats (u64 x 4) at +64 bytes
     unsigned* small;
     unsigned long long* stats;
 };
@@ -148,7 +152,7 @@ __global__ void occ_fast_origins(const double* __restrict__ origins, int n_scans
 }
 
 template <bool FILL>
-__global__ void __launch_bounds__(256) occ_fast_rays(const FastArgs a) {
+__global__ void __launch_bounds__(256, 8) occ_fast_rays(const FastArgs a) {
     const long long rl = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // chunk-relative ray
     const long long r = a.ray_begin + rl;
     const int lane = threadIdx.x & 31;
@@ -190,6 +194,7 @@ __global__ void __launch_bounds__(256) occ_fast_rays(const FastArgs a) {
                         const unsigned slot = atomicAdd(&a.small[4], 1u);
                         a.slot_cell[slot] = (unsigned)cell;
                         a.slotmap[cell] = slot;                                  // read by later kernels only
+                        a.tile_flag[tile] = 1u;
                     }
                 } else {
                     const unsigned slot = a.slotmap[cell];
@@ -273,22 +278,22 @@ constexpr unsigned kItemRuns = 2048;
 __global__ void __launch_bounds__(1024) occ_tile_scan(const unsigned* __restrict__ counts, int n_tiles,
                                                       unsigned* __restrict__ offsets /* n_tiles + 1 */,
                                                       unsigned* __restrict__ class_off /* [tile][class] */,
-                                                      uint2* __restrict__ items, int* __restrict__ multi,
+                                                      const unsigned* __restrict__ tile_flag, uint2* __restrict__ items, int* __restrict__ multi,
                                                       unsigned* __restrict__ small) {
     __shared__ unsigned wsum[32];
     __shared__ unsigned carry;
-    __shared__ int hist[33], start[33];
+    __shared__ int hist[2][33], start[2][33];      // [0] tiles with hit cells, [1] the others
     __shared__ unsigned n_multi;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) { carry = 0; n_multi = 0; }
-    if (tid < 33) hist[tid] = 0;
+    if (tid < 66) hist[tid / 33][tid % 33] = 0;
     __syncthreads();
     for (int b0 = 0; b0 < n_tiles; b0 += 1024) {
         const int t = b0 + tid;
         uint4 cc = make_uint4(0u, 0u, 0u, 0u);
         if (t < n_tiles) cc = reinterpret_cast<const uint4*>(counts)[t];
         const unsigned v = cc.x + cc.y + cc.z + cc.w;
-        if (v) atomicAdd(&hist[32 - __clz(v)], (int)((v + kItemRuns - 1) / kItemRuns));
+        if (v) atomicAdd(&hist[tile_flag[t] ? 0 : 1][32 - __clz(v)], (int)((v + kItemRuns - 1) / kItemRuns));
         unsigned inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -312,7 +317,10 @@ __global__ void __launch_bounds__(1024) occ_tile_scan(const unsigned* __restrict
         offsets[n_tiles] = carry;
         small[0] = carry;
         int run = 0;
-        for (int b = 32; b >= 1; --b) { start[b] = run; run += hist[b]; }      // heaviest tiles first
+        for (int g = 0; g < 2; ++g) {
+            for (int b = 32; b >= 1; --b) { start[g][b] = run; run += hist[g][b]; }   // heaviest tiles first
+            if (g == 0) small[6] = (unsigned)run;
+        }
         small[1] = (unsigned)run;                                               // number of items
     }
     __syncthreads();
@@ -321,7 +329,7 @@ __global__ void __launch_bounds__(1024) occ_tile_scan(const unsigned* __restrict
         const unsigned v = cc.x + cc.y + cc.z + cc.w;
         if (v) {
             const int n_it = (int)((v + kItemRuns - 1) / kItemRuns);
-            const int base = atomicAdd(&start[32 - __clz(v)], n_it);
+            const int base = atomicAdd(&start[tile_flag[t] ? 0 : 1][32 - __clz(v)], n_it);
             for (int i = 0; i < n_it; ++i) items[base + i] = make_uint2((unsigned)t, (unsigned)i);
             if (n_it > 1) multi[atomicAdd(&n_multi, 1u)] = t;
         }
@@ -382,7 +390,8 @@ struct TileArgs {
     int nx, ny, tiles_x;
     const unsigned* tile_off;
     const uint4* runs;
-    const uint2* items;                       // (tile, piece)
+    const uint2* items;                       // (tile, piece); tiles with hit cells first
+    unsigned n_items, n_hit_items;
     const int* multi;                         // tiles cut into several items
     unsigned* small;                          // [1] n_items [2] queue [5] n_multi
     unsigned* ncount;                         // ny * nx partial miss counts of multi-item tiles (kept zero)
@@ -469,34 +478,35 @@ __global__ void __launch_bounds__(kTileNT) occ_fast_tiles(const TileArgs a) {
     __shared__ unsigned slot[kPadCells];
     __shared__ unsigned dummy[kTileNT];           // where idle lanes count
     __shared__ uint2 cur_item;
+    __shared__ unsigned cur_q;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned n_items = a.small[1];
     for (;;) {
         __syncthreads();
         if (tid == 0) {
             const unsigned q = atomicAdd(&a.small[2], 1u);
-            cur_item = q < n_items ? a.items[q] : make_uint2(kNone, 0u);
+            cur_q = q;
+            cur_item = q < a.n_items ? a.items[q] : make_uint2(kNone, 0u);
         }
         __syncthreads();
         if (cur_item.x == kNone) break;
         const int t = (int)cur_item.x;
+        const bool HITS = cur_q < a.n_hit_items;          // items of tiles that hold hit cells come first
         const int tx0 = (t % a.tiles_x) * TS, ty0 = (t / a.tiles_x) * TS;
-        bool any = false;
         for (int c = tid; c < TCELLS; c += kTileNT) {
-            const int x = tx0 + (c & (TS - 1)), y = ty0 + (c / TS);
-            const unsigned s = (x < a.nx && y < a.ny) ? a.slotmap[(size_t)y * a.nx + x] : kNone;
-            slot[pad_cell(c)] = s;
+            if (HITS) {
+                const int x = tx0 + (c & (TS - 1)), y = ty0 + (c / TS);
+                slot[pad_cell(c)] = (x < a.nx && y < a.ny) ? a.slotmap[(size_t)y * a.nx + x] : kNone;
+            }
             cnt[pad_cell(c)] = 0u;
-            any |= s != kNone;
         }
-        const int has_hits = __syncthreads_or(any);
+        __syncthreads();
         const unsigned t_beg = a.tile_off[t], t_end = a.tile_off[t + 1];
         const unsigned beg = t_beg + cur_item.y * kItemRuns, end = min(beg + kItemRuns, t_end);
         unsigned cnt_base = (unsigned)__cvta_generic_to_shared(cnt), slot_base = (unsigned)__cvta_generic_to_shared(slot);
         unsigned dummy_addr = (unsigned)__cvta_generic_to_shared(&dummy[tid]);
         asm volatile("" : "+r"(cnt_base), "+r"(slot_base), "+r"(dummy_addr));     // keep them in registers: no re-derivation per step
-        if (has_hits) walk_runs<true>(a, beg, end, cnt_base, slot_base, dummy_addr, warp, lane);
-        else          walk_runs<false>(a, beg, end, cnt_base, slot_base, dummy_addr, warp, lane);
+        if (HITS) walk_runs<true>(a, beg, end, cnt_base, slot_base, dummy_addr, warp, lane);
+        else      walk_runs<false>(a, beg, end, cnt_base, slot_base, dummy_addr, warp, lane);
         __syncthreads();
         const bool whole = t_end - t_beg <= kItemRuns;
         for (int c = tid; c < TCELLS; c += kTileNT) {
@@ -603,6 +613,40 @@ __global__ void __launch_bounds__(128) occ_fast_chain(float* __restrict__ grid, 
 
 }  // namespace
 
+// Optional stage timing (ICPB200_OCC_TIMING=1): events on the main stream at the stage boundaries,
+// printed to stderr after the chunk.  A profiling aid; never on in the timed runs.
+struct StageTimer {
+    bool on = false;
+    cudaEvent_t ev[12];
+    const char* name[12];
+    int n = 0;
+    cudaStream_t st = nullptr;
+    void init(cudaStream_t s) {
+        static const bool want = getenv("ICPB200_OCC_TIMING") != nullptr;
+        on = want; st = s;
+    }
+    void mark(const char* what) {
+        if (!on || n >= 12) return;
+        cudaEventCreate(&ev[n]);
+        cudaEventRecord(ev[n], st);
+        name[n++] = what;
+    }
+    void report() {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        for (int i = 1; i < n; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            fprintf(stderr, "[occ stage] %-12s %8.1f us\n", name[i], ms * 1e3f);
+        }
+        float tot = 0.f;
+        if (n > 1) cudaEventElapsedTime(&tot, ev[0], ev[n - 1]);
+        fprintf(stderr, "[occ stage] %-12s %8.1f us\n", "total", tot * 1e3f);
+        for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]);
+        n = 0;
+    }
+};
+
 // Returns ICPB200_OK, an error, or 1 when this chunk must take the ordered path instead.
 static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_origins, const double* d_hits,
                       const long long* d_hit_off, const long long* h_hit_off, cudaStream_t st) {
@@ -616,12 +660,16 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
     if (g.tile_count.reserve(sizeof(unsigned) * kLenClasses * (size_t)n_tiles) || g.offsets.reserve(sizeof(unsigned) * ((size_t)n_tiles + 1)) ||
         g.class_off.reserve(sizeof(unsigned) * kLenClasses * (size_t)n_tiles) ||
         g.slot_cell.reserve(sizeof(unsigned) * (size_t)nr) || g.items.reserve(sizeof(uint2) * max_items) ||
-        g.multi.reserve(sizeof(int) * (size_t)n_tiles))
+        g.multi.reserve(sizeof(int) * (size_t)n_tiles) || g.tile_flag.reserve(sizeof(unsigned) * (size_t)n_tiles))
         return ICPB200_ERR_CUDA;
     unsigned* d_small = g.small.as<unsigned>();
     unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(g.small.as<unsigned char>() + 64);
+    StageTimer tm;
+    tm.init(st);
+    tm.mark("begin");
     ICPB_CUDA(cudaMemsetAsync(d_small, 0, 64, st));
     ICPB_CUDA(cudaMemsetAsync(g.tile_count.p, 0, sizeof(unsigned) * kLenClasses * (size_t)n_tiles, st));
+    ICPB_CUDA(cudaMemsetAsync(g.tile_flag.p, 0, sizeof(unsigned) * (size_t)n_tiles, st));
 
     FastArgs a;
     a.hits = reinterpret_cast<const double2*>(d_hits);
@@ -638,14 +686,17 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
     a.slot_cell = g.slot_cell.as<unsigned>();
     a.ord = nullptr; a.ord_stride = 0;
     a.tile_count = g.tile_count.as<unsigned>();
+    a.tile_flag = g.tile_flag.as<unsigned>();
     a.tile_off = nullptr; a.runs = nullptr;
     a.small = d_small; a.stats = d_stats;
     const unsigned nblk = (unsigned)((nr + 255) / 256);
     occ_fast_rays<false><<<nblk, 256, 0, st>>>(a);
     ICPB_LAUNCH_CHECK();
-    occ_tile_scan<<<1, 1024, 0, st>>>(g.tile_count.as<unsigned>(), n_tiles, g.offsets.as<unsigned>(), g.class_off.as<unsigned>(), g.items.as<uint2>(), g.multi.as<int>(), d_small);
+    tm.mark("count");
+    occ_tile_scan<<<1, 1024, 0, st>>>(g.tile_count.as<unsigned>(), n_tiles, g.offsets.as<unsigned>(), g.class_off.as<unsigned>(), g.tile_flag.as<unsigned>(), g.items.as<uint2>(), g.multi.as<int>(), d_small);
     ICPB_LAUNCH_CHECK();
     unsigned h_small[8];
+    tm.mark("scan");
     ICPB_CUDA(cudaMemcpyAsync(h_small, d_small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
     ICPB_CUDA(cudaStreamSynchronize(st));
     const unsigned total_runs = h_small[0], n_slots = h_small[4];
@@ -677,8 +728,10 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
     a.ord = g.ord.as<unsigned>(); a.ord_stride = stride;
     a.tile_off = g.class_off.as<unsigned>();
     a.runs = g.runs.as<uint4>();
+    tm.mark("host gap");
     occ_fast_rays<true><<<nblk, 256, 0, st>>>(a);
     ICPB_LAUNCH_CHECK();
+    tm.mark("fill");
     const float lo = (float)g.lo_min, hi = (float)g.lo_max;
     if (total_runs) {
         TileArgs t;
@@ -694,24 +747,30 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
         t.ord = g.ord.as<unsigned>();
         t.ord_stride = stride;
         t.l_hit = g.l_hit; t.l_miss = g.l_miss; t.lo = lo; t.hi = hi;
-        const unsigned n_items = h_small[1], n_multi = h_small[5];
-        const unsigned ctas = std::min<unsigned>(n_items, (unsigned)g.fast_ctas);
-        occ_fast_tiles<<<ctas, kTileNT, 0, st>>>(t);
+        t.n_items = h_small[1]; t.n_hit_items = h_small[6];
+        const unsigned n_multi = h_small[5];
+        occ_fast_tiles<<<std::min<unsigned>(t.n_items, (unsigned)g.fast_ctas), kTileNT, 0, st>>>(t);
         ICPB_LAUNCH_CHECK();
+        tm.mark("tiles");
         if (n_multi) {
             occ_fast_apply_multi<<<n_multi * 4u, 256, 0, st>>>(t);
             ICPB_LAUNCH_CHECK();
         }
+        tm.mark("apply multi");
     }
     if (n_slots) {
-        occ_fast_compact<<<(n_slots * 32u + 255u) / 256u, 256, 0, st>>>(g.ord.as<unsigned>(), g.ev.as<unsigned>(), g.ev_count.as<unsigned>(),
-                                                                        d_small, cs, stride);
+        occ_fast_compact<<<(n_slots * 32u + 255u) / 256u, 256, 0, st>>>(g.ord.as<unsigned>(), g.ev.as<unsigned>(),
+                                                                        g.ev_count.as<unsigned>(), d_small, cs, stride);
         ICPB_LAUNCH_CHECK();
-        occ_fast_chain<<<(n_slots + 127u) / 128u, 128, 0, st>>>(g.grid.as<float>(), g.slotmap.as<unsigned>(), g.slot_cell.as<unsigned>(),
-                                                                g.ev.as<unsigned>(), g.ev_count.as<unsigned>(), d_small, stride,
-                                                                g.l_hit, g.l_miss, lo, hi);
+        tm.mark("compact");
+        occ_fast_chain<<<(n_slots + 127u) / 128u, 128, 0, st>>>(g.grid.as<float>(), g.slotmap.as<unsigned>(),
+                                                                g.slot_cell.as<unsigned>(), g.ev.as<unsigned>(),
+                                                                g.ev_count.as<unsigned>(), d_small, stride, g.l_hit, g.l_miss, lo, hi);
         ICPB_LAUNCH_CHECK();
+        tm.mark("chain");
     }
+    tm.mark("end");
+    tm.report();
     return ICPB200_OK;
 }
 
