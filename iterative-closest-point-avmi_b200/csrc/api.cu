@@ -218,7 +218,7 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
     if (two_phase) {
         const size_t np_ = (size_t)n_pairs, cs_ = (size_t)a.cap_s;
         if (c.cont_cur.reserve(sizeof(double) * k.dim * cs_ * np_) || c.cont_match.reserve(sizeof(int) * cs_ * np_) ||
-            c.cont_d2lb.reserve(sizeof(float) * cs_ * np_) || c.cont_moved.reserve(sizeof(float) * cs_ * np_) ||
+            c.cont_d2lb.reserve(sizeof(float) * cs_ * np_) || c.cont_moved.reserve(sizeof(float) * k.dim * cs_ * np_) ||
             c.cont_scalar.reserve(sizeof(double) * 16 * np_) || c.cont_list.reserve(sizeof(int) * np_))
             return ICPB200_ERR_CUDA;
         a.cont_count = a.queue + 2;
@@ -292,8 +292,11 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
         IcpArgs b = a;
         b.resume = 1;
         b.queue = a.queue + 1;
-        const size_t smem2 = std::max(smem, (size_t)c.max_smem_optin / 2 + 1024);
-        if ((rc = launch_icp_pairs(b, k.dim, grid, c.sm_count, std::min(smem2, (size_t)c.max_smem_optin), st))) return rc;
+        static const int p2_per_sm = getenv("ICPB200_P2_PER_SM") ? std::max(1, std::min(3, atoi(getenv("ICPB200_P2_PER_SM")))) : 1;
+        size_t smem2 = smem;
+        if (p2_per_sm == 1) smem2 = std::max(smem, (size_t)c.max_smem_optin / 2 + 1024);
+        else if (p2_per_sm == 2) smem2 = std::max(smem, (size_t)c.max_smem_optin / 3 + 1024);
+        if ((rc = launch_icp_pairs(b, k.dim, grid, c.sm_count * p2_per_sm, std::min(smem2, (size_t)c.max_smem_optin), st))) return rc;
     }
     ICPB_CUDA(cudaEventRecord(c.ev[3], st));
     return ICPB200_OK;

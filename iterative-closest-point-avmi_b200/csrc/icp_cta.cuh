@@ -27,8 +27,8 @@ struct CtaShared {
     int n_s, n_t;
     int amb_n;
     // split-sweep partials (K3): [warp][lane]
-    float part_b1[kNW][32], part_b2[kNW][32];
-    int part_bt[kNW][32];
+    float part_b1[kNW][32], part_b2[kNW][32], part_b3[kNW][32];
+    int part_bt[kNW][32], part_bt2[kNW][32];
 };
 
 struct SumOp { __device__ static double f(double a, double b) { return a + b; } };

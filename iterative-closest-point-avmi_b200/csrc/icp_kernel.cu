@@ -56,7 +56,7 @@ size_t icp_pair_smem_bytes(int dim, int cap_s, int cap_t) {
     b += sizeof(float) * (dim == 2 ? 2 : 4) * (size_t)cap_t;           // tgt32
     b += sizeof(double) * dim * (size_t)cap_s;                         // cur64 SoA
     b += sizeof(int) * (size_t)cap_s;                                  // match
-    b += sizeof(float) * 2 * (size_t)cap_s;                            // d2lb, moved
+    b += sizeof(float) * (1 + dim) * (size_t)cap_s;                    // d2lb, decision position (fp32, recentred)
     b += sizeof(unsigned short) * 2 * (size_t)cap_s;                   // todo, ambiguous
     return align16(b);
 }
@@ -763,7 +763,9 @@ struct Loop {
     float4* t32;
     int* match;
     float* d2lb;             // lower bound on the distance to every non-match target at decision time
-    float* moved;            // upper bound on the movement since that decision
+    float* p0;               // position at that decision (fp32, recentred; SoA with stride cap): the bound holds
+                             // as long as the NET displacement since then leaves room, however long the path
+    int cap;
     unsigned short* todo;    // points that need a sweep this iteration
     unsigned short* amb;     // points that need the full fp64 scan
     int n_s, n_t, n_tiles;
@@ -799,6 +801,23 @@ __device__ __forceinline__ double dist2_64(const Loop<DIM>& L, double px, double
 
 __device__ __forceinline__ float f32_down(double v) { return __double2float_rd(v); }
 
+// remember where point i stood when its correspondence was decided
+template <int DIM>
+__device__ __forceinline__ void stamp_p0(const Loop<DIM>& L, int i) {
+    L.p0[i] = (float)(L.cx[i] - L.c0);
+    L.p0[L.cap + i] = (float)(L.cy[i] - L.c1);
+    if (DIM == 3) L.p0[2 * L.cap + i] = (float)(L.cz[i] - L.c2);
+}
+
+// Correspondence word.  Brute mode (targets <= 4096 points) packs two candidates: the match in
+// the low half and, in the high half, alt + 1 -- the one other target that may overtake it
+// (0 = none).  d2lb then bounds the distance to every target OTHER THAN THESE TWO, so a point
+// that flips between two near-equidistant targets (the reference's limit cycles) is re-decided
+// from two exact distances instead of a sweep.  Grid mode stores the plain index.
+template <bool GRID> __device__ __forceinline__ int m_idx(int w) { return GRID ? w : (w & 0xffff); }
+template <bool GRID> __device__ __forceinline__ int m_alt(int w) { return GRID ? -1 : ((w >> 16) - 1); }
+__device__ __forceinline__ int m_pack(int j, int alt) { return j | ((alt + 1) << 16); }
+
 // Decide the correspondence of source point i from its sweep result: re-evaluate
 // the winning tile in fp64, bound everything else by the runner-up tile minimum.
 template <int DIM>
@@ -807,13 +826,15 @@ __device__ __forceinline__ void decide(const Loop<DIM>& L, CtaShared& sh, int i,
     const double px = L.cx[i], py = L.cy[i], pz = DIM == 3 ? L.cz[i] : 0.0;
     const int j0 = btv * 32;
     const int j1 = min(j0 + 32, L.n_t);
-    double best = INFINITY, second = INFINITY;
-    int bj = j0;
+    double best = INFINITY, second = INFINITY, third = INFINITY;
+    int bj = j0, j2 = -1;
     for (int j = j0; j < j1; ++j) {
         const double d = dist2_64<DIM>(L, px, py, pz, j);
-        if (d < best) { second = best; best = d; bj = j; }
-        else if (d < second) second = d;
+        if (d < best) { third = second; second = best; j2 = bj; best = d; bj = j; }
+        else if (d < second) { third = second; second = d; j2 = j; }
+        else if (d < third) third = d;
     }
+    if (!(second < INFINITY)) j2 = -1;
     // Can a target outside the winning tile be closer?  fp32 coordinate
     // rounding moves a distance by at most eps32 * (|s| + |t|) summed over
     // axes; 3x safety on the 2^-24 unit roundoff, and the sweep's own four
@@ -825,9 +846,9 @@ __device__ __forceinline__ void decide(const Loop<DIM>& L, CtaShared& sh, int i,
     if (!(other > d1)) {
         L.amb[atomicAdd(&sh.amb_n, 1)] = (unsigned short)i;
     } else {
-        L.match[i] = bj;
-        L.d2lb[i] = f32_down(fmin(other, sqrt(second) * (1.0 - 1e-12)));
-        L.moved[i] = 0.f;
+        L.match[i] = m_pack(bj, j2);
+        L.d2lb[i] = f32_down(fmin(other, sqrt(third) * (1.0 - 1e-12)));       // everything but bj and j2
+        stamp_p0<DIM>(L, i);
     }
 }
 
@@ -875,53 +896,73 @@ __device__ __forceinline__ void nn_split(const Loop<DIM>& L, CtaShared& sh, int 
         sy = pt >= 0 ? (float)(L.cy[i] - L.c1) : 0.f;
         sz = (DIM == 3 && pt >= 0) ? (float)(L.cz[i] - L.c2) : 0.f;
         const int j0 = (int)((long long)part * L.n_tiles / F) * 32, j1 = (int)((long long)(part + 1) * L.n_tiles / F) * 32;
-        float b1 = INFINITY, b2 = INFINITY;
-        int bj = j0;
+        float b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
+        int bj = j0, bj2 = j0;
+        auto offer = [&](float d, int j) {
+            const bool lt1 = d < b1, lt2 = d < b2;
+            b3 = lt2 ? b2 : fminf(b3, d);
+            b2 = lt1 ? b1 : (lt2 ? d : b2);
+            bj2 = lt1 ? bj : (lt2 ? j : bj2);
+            b1 = lt1 ? d : b1;
+            bj = lt1 ? j : bj;
+        };
         if (DIM == 2) {
             const float2* t = reinterpret_cast<const float2*>(L.t32);
 #pragma unroll 8
             for (int j = j0; j < j1; ++j) {
                 const float2 q2 = t[j];
                 const float dx = sx - q2.x, dy = sy - q2.y;
-                const float d = fmaf(dy, dy, dx * dx);
-                const bool lt = d < b1;
-                b2 = lt ? b1 : fminf(b2, d);
-                bj = lt ? j : bj;
-                b1 = fminf(b1, d);
+                offer(fmaf(dy, dy, dx * dx), j);
             }
         } else {
 #pragma unroll 8
             for (int j = j0; j < j1; ++j) {
                 const float4 q4 = L.t32[j];
                 const float dx = sx - q4.x, dy = sy - q4.y, dz = sz - q4.z;
-                const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                const bool lt = d < b1;
-                b2 = lt ? b1 : fminf(b2, d);
-                bj = lt ? j : bj;
-                b1 = fminf(b1, d);
+                offer(fmaf(dz, dz, fmaf(dy, dy, dx * dx)), j);
             }
         }
-        sh.part_b1[w][lane] = b1; sh.part_b2[w][lane] = b2; sh.part_bt[w][lane] = bj;
+        sh.part_b1[w][lane] = b1; sh.part_b2[w][lane] = b2; sh.part_b3[w][lane] = b3;
+        sh.part_bt[w][lane] = bj; sh.part_bt2[w][lane] = bj2;
     }
     __syncthreads();
     if (live && part == 0 && pt >= 0) {
-        float m1 = INFINITY, m2 = INFINITY;
-        int mj = 0;
+        // merge the F partial top-3 lists (fp32 ranking), then decide between the two front
+        // runners with exact distances; the third bounds every other target
+        float m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
+        int mj = 0, mj2 = 0;
+        auto offer = [&](float d, int j) {
+            const bool lt1 = d < m1, lt2 = d < m2;
+            m3 = lt2 ? m2 : fminf(m3, d);
+            m2 = lt1 ? m1 : (lt2 ? d : m2);
+            mj2 = lt1 ? mj : (lt2 ? j : mj2);
+            m1 = lt1 ? d : m1;
+            mj = lt1 ? j : mj;
+        };
         for (int f = 0; f < F; ++f) {
-            const float p1 = sh.part_b1[w + f][lane], p2 = sh.part_b2[w + f][lane];
-            if (p1 < m1) { m2 = fminf(m1, p2); m1 = p1; mj = sh.part_bt[w + f][lane]; }
-            else m2 = fminf(m2, p1);
+            offer(sh.part_b1[w + f][lane], sh.part_bt[w + f][lane]);
+            offer(sh.part_b2[w + f][lane], sh.part_bt2[w + f][lane]);
+            m3 = fminf(m3, sh.part_b3[w + f][lane]);
         }
         mj = min(mj, L.n_t - 1);                       // padding targets can only win if n_t == 0
-        const double d1 = sqrt(dist2_64<DIM>(L, L.cx[pt], L.cy[pt], DIM == 3 ? L.cz[pt] : 0.0, mj));
+        const bool two = mj2 < L.n_t && mj2 != mj && m2 < 1.0e30f;
+        const double px = L.cx[pt], py = L.cy[pt], pz = DIM == 3 ? L.cz[pt] : 0.0;
+        double e1 = dist2_64<DIM>(L, px, py, pz, mj);
+        int j1 = mj, j2 = -1;
+        if (two) {
+            const double e2 = dist2_64<DIM>(L, px, py, pz, mj2);
+            j2 = mj2;
+            if (e2 < e1 || (e2 == e1 && mj2 < mj)) { j1 = mj2; j2 = mj; e1 = e2; }
+        }
+        const double d1 = sqrt(e1);
         const float mag = fabsf(sx) + fabsf(sy) + (DIM == 3 ? fabsf(sz) : 0.f) + L.ta;
-        const double other = sqrt((double)m2) * (1.0 - 1.0e-6) - 1.8e-7 * (double)mag;
+        const double other = sqrt((double)(two ? m3 : m2)) * (1.0 - 1.0e-6) - 1.8e-7 * (double)mag;
         if (!(other > d1)) {
             L.amb[atomicAdd(&sh.amb_n, 1)] = (unsigned short)pt;
         } else {
-            L.match[pt] = mj;
+            L.match[pt] = m_pack(j1, j2);
             L.d2lb[pt] = f32_down(other);
-            L.moved[pt] = 0.f;
+            stamp_p0<DIM>(L, pt);
         }
     }
 }
@@ -958,29 +999,29 @@ __device__ __forceinline__ void resolve_ambiguous(const Loop<DIM>& L, const CtaS
     for (int a = w; a < n_amb; a += kNW) {
         const int i = L.amb[a];
         const double px = L.cx[i], py = L.cy[i], pz = DIM == 3 ? L.cz[i] : 0.0;
-        double best = INFINITY, second = INFINITY;
-        int bj = 0x7fffffff;
-        for (int j = l; j < L.n_t; j += 32) {
-            const double d = dist2_64<DIM>(L, px, py, pz, j);
-            if (d < best) { second = best; best = d; bj = j; }
-            else if (d < second) second = d;
-        }
+        double best = INFINITY, second = INFINITY, third = INFINITY;
+        int bj = 0x7fffffff, j2 = 0x7fffffff;
+        auto offer = [&](double d, int j) {                     // (d, j) lexicographic: lowest index wins exact ties
+            if (d < best || (d == best && j < bj)) { third = second; second = best; j2 = bj; best = d; bj = j; }
+            else if (d < second || (d == second && j < j2)) { third = second; second = d; j2 = j; }
+            else if (d < third) third = d;
+        };
+        for (int j = l; j < L.n_t; j += 32) offer(dist2_64<DIM>(L, px, py, pz, j), j);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const double od = __shfl_xor_sync(0xffffffffu, best, o);
             const double os = __shfl_xor_sync(0xffffffffu, second, o);
+            const double ot = __shfl_xor_sync(0xffffffffu, third, o);
             const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
-            if (od < best || (od == best && oj < bj)) {
-                second = fmin(best, os);
-                best = od; bj = oj;
-            } else {
-                second = fmin(second, od);
-            }
+            const int oj2 = __shfl_xor_sync(0xffffffffu, j2, o);
+            if (oj != 0x7fffffff) offer(od, oj);
+            if (oj2 != 0x7fffffff) offer(os, oj2);
+            third = fmin(third, ot);
         }
         if (l == 0) {
-            L.match[i] = bj;
-            L.d2lb[i] = f32_down(sqrt(second) * (1.0 - 1e-12));
-            L.moved[i] = 0.f;
+            L.match[i] = m_pack(bj, j2 == 0x7fffffff ? -1 : j2);
+            L.d2lb[i] = f32_down(sqrt(third) * (1.0 - 1e-12));
+            stamp_p0<DIM>(L, i);
         }
     }
 }
@@ -1046,7 +1087,7 @@ __device__ __forceinline__ void grid_nn(const Loop<DIM>& L, int n_todo) {
         }
         L.match[i] = bj;
         L.d2lb[i] = f32_down(fmin(sqrt(second), bound) * (1.0 - 1e-12));
-        L.moved[i] = 0.f;
+        stamp_p0<DIM>(L, i);
     }
 }
 
@@ -1070,7 +1111,8 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
         L.cz = reinterpret_cast<double*>(q);           if (DIM == 3) q += sizeof(double) * (size_t)a.cap_s;
         L.match = reinterpret_cast<int*>(q);           q += sizeof(int) * (size_t)a.cap_s;
         L.d2lb = reinterpret_cast<float*>(q);          q += sizeof(float) * (size_t)a.cap_s;
-        L.moved = reinterpret_cast<float*>(q);         q += sizeof(float) * (size_t)a.cap_s;
+        L.p0 = reinterpret_cast<float*>(q);            q += sizeof(float) * DIM * (size_t)a.cap_s;
+        L.cap = a.cap_s;
         L.todo = reinterpret_cast<unsigned short*>(q); q += sizeof(unsigned short) * (size_t)a.cap_s;
         L.amb = reinterpret_cast<unsigned short*>(q);
     }
@@ -1184,7 +1226,6 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
                     L.cz[i] = x * r[6] + y * r[7] + z * r[8] + t[2];
                 }
                 L.d2lb[i] = -1.f;                  // no decision yet: forces a sweep
-                L.moved[i] = 0.f;
                 L.match[i] = 0;
             }
         }
@@ -1198,7 +1239,7 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
                 if (DIM == 3) L.cz[i] = cc[2 * (size_t)a.cap_s + i];
                 L.match[i] = a.cont_match[so + i];
                 L.d2lb[i] = a.cont_d2lb[so + i];
-                L.moved[i] = a.cont_moved[so + i];
+                for (int k = 0; k < DIM; ++k) L.p0[k * L.cap + i] = a.cont_moved[so * DIM + (size_t)k * a.cap_s + i];
             }
             const double* sc = a.cont_scalar + (size_t)slot_in * 16;
             prev = sc[12]; err = sc[13]; iters = (int)sc[14];
@@ -1230,7 +1271,7 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
                     if (DIM == 3) cc[2 * (size_t)a.cap_s + i] = L.cz[i];
                     a.cont_match[so + i] = L.match[i];
                     a.cont_d2lb[so + i] = L.d2lb[i];
-                    a.cont_moved[so + i] = L.moved[i];
+                    for (int k = 0; k < DIM; ++k) a.cont_moved[so * DIM + (size_t)k * a.cap_s + i] = L.p0[k * L.cap + i];
                 }
                 if (tid == 0) {
                     double* sc = a.cont_scalar + (size_t)slot * 16;
@@ -1249,9 +1290,22 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
                 bool keep = false;
                 const float lb = L.d2lb[i];
                 if (lb >= 0.f) {
-                    // dist(p, match) < D2 - moved, compared on squares (no fp64 sqrt), with rounding slack
-                    const double room = (double)lb - (double)L.moved[i] - 1e-12;
-                    const double d2 = dist2_64<DIM, GRID>(L, L.cx[i], L.cy[i], DIM == 3 ? L.cz[i] : 0.0, L.match[i]);
+                    // dist(p, match) < D2 - moved, compared on squares (no fp64 sqrt), with rounding slack;
+                    // moved = net displacement since the decision, rounded up (the stamped position is
+                    // fp32: 2^-24 relative per axis, covered by the 1.2e-7 * magnitude term)
+                    const int mw = L.match[i], j = m_idx<GRID>(mw), alt = m_alt<GRID>(mw);
+                    const double px = L.cx[i], py = L.cy[i], pz = DIM == 3 ? L.cz[i] : 0.0;
+                    const float x0 = L.p0[i], y0 = L.p0[L.cap + i], z0 = DIM == 3 ? L.p0[2 * L.cap + i] : 0.f;
+                    const float ux = (float)(px - L.c0) - x0, uy = (float)(py - L.c1) - y0;
+                    const float uz = DIM == 3 ? (float)(pz - L.c2) - z0 : 0.f;
+                    const float moved = __fmaf_ru(__fsqrt_ru(__fmaf_ru(uz, uz, __fmaf_ru(uy, uy, __fmul_ru(ux, ux)))), 1.000001f,
+                                                  2.4e-7f * (fabsf(x0) + fabsf(y0) + fabsf(z0) + fabsf(ux) + fabsf(uy) + fabsf(uz)));
+                    const double room = (double)lb - (double)moved - 1e-12;
+                    double d2 = dist2_64<DIM, GRID>(L, px, py, pz, j);
+                    if (alt >= 0) {                    // the one rival: exact comparison, lowest index on ties
+                        const double da = dist2_64<DIM, GRID>(L, px, py, pz, alt);
+                        if (da < d2 || (da == d2 && alt < j)) { d2 = da; L.match[i] = m_pack(alt, j); }
+                    }
                     keep = room > 0.0 && d2 * (1.0 + 4e-9) < room * room;
                 }
                 if (!keep) L.todo[atomicAdd(&sh.bcast_i[0], 1)] = (unsigned short)i;
@@ -1277,7 +1331,7 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
             if (prof) { const long long c = clock64(); ph[1] += c - ph_t; ph_t = c; }
             if (tid == 0) { st_amb += sh.amb_n; sh.amb_n = 0; sh.bcast_i[0] = 0; }
             if (a.trace_match && p == 0 && it < a.trace_iters)
-                for (int i = tid; i < n_s; i += kNT) a.trace_match[(size_t)it * a.trace_stride + i] = L.match[i];
+                for (int i = tid; i < n_s; i += kNT) a.trace_match[(size_t)it * a.trace_stride + i] = m_idx<GRID>(L.match[i]);
 
             double rr[9], tt[3];
             if (p2l) {
@@ -1291,7 +1345,7 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {                     // the normals live in global memory (L2)
                         const int i = i0 + u * kNT;
-                        jj[u] = i < n_s ? L.match[i] : 0;
+                        jj[u] = i < n_s ? m_idx<GRID>(L.match[i]) : 0;
                         nn[u] = __ldg(reinterpret_cast<const double2*>(normals) + jj[u]);
                     }
 #pragma unroll
@@ -1340,7 +1394,7 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
                 for (int i = tid; i < n_s; i += kNT) {
                     const double px = L.cx[i], py = L.cy[i], pz = DIM == 3 ? L.cz[i] : 0.0;
                     double qx, qy, qz;
-                    tgt_at<DIM, GRID>(L, L.match[i], qx, qy, qz);
+                    tgt_at<DIM, GRID>(L, m_idx<GRID>(L.match[i]), qx, qy, qz);
                     if (gated) {
                         const double dx = px - qx, dy = py - qy, dz = pz - qz;
                         const double nd = sqrt(dx * dx + dy * dy + dz * dz);
@@ -1362,7 +1416,7 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
                 for (int i = tid; i < n_s; i += kNT) {
                     double ps[3] = {L.cx[i], L.cy[i], DIM == 3 ? L.cz[i] : 0.0};
                     double qs[3];
-                    tgt_at<DIM, GRID>(L, L.match[i], qs[0], qs[1], qs[2]);
+                    tgt_at<DIM, GRID>(L, m_idx<GRID>(L.match[i]), qs[0], qs[1], qs[2]);
                     if (gated) {
                         const double dx = ps[0] - qs[0], dy = ps[1] - qs[1], dz = ps[2] - qs[2];
                         const double nd = sqrt(dx * dx + dy * dy + dz * dz);
@@ -1407,7 +1461,7 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
             double e[1] = {0.0};
             for (int i = tid; i < n_s; i += kNT) {
                 double qx, qy, qz;
-                tgt_at<DIM, GRID>(L, L.match[i], qx, qy, qz);
+                tgt_at<DIM, GRID>(L, m_idx<GRID>(L.match[i]), qx, qy, qz);
                 const double x = L.cx[i], y = L.cy[i];
                 double nx_, ny_, nz_ = 0.0, mv;
                 if (DIM == 2) {
@@ -1423,8 +1477,6 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
                     mv = (nx_ - x) * (nx_ - x) + (ny_ - y) * (ny_ - y) + (nz_ - z) * (nz_ - z);
                 }
                 L.cx[i] = nx_; L.cy[i] = ny_;
-                // movement since the last decision, rounded up
-                L.moved[i] = __fadd_ru(L.moved[i], __fmul_ru(__fsqrt_ru(__double2float_ru(mv)), 1.000001f));
                 const double dx = qx - nx_, dy = qy - ny_;
                 double d = dx * dx + dy * dy;
                 if (DIM == 3) { const double dz = qz - nz_; d += dz * dz; }

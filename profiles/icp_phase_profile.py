@@ -24,3 +24,4 @@ print("iterations >= 8:", it, " total iterations:", st["iterations"])
 for name, v in zip(("classify", "nearest-nb", "accumulate", "solve", "apply+err"), ph[:5]):
     print(f"  {name:12s} {v / it:9.0f} cycles/iteration")
 print("  sum          %9.0f cycles/iteration" % (ph[:5].sum() / it))
+print("stats:", {k: st[k] for k in st if k not in ("voxel_kernel_ns", "normals_kernel_ns", "pair_kernel_ns")})
