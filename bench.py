@@ -298,7 +298,8 @@ def run_ours(args, rank, world, local_rank):
     iters = d_it.cpu().numpy().astype(np.int64)
     status = d_st.cpu().numpy()
 
-    # ---- e2e: host buffers through the C ABI (H2D + kernel + D2H per step)
+    # ---- e2e: host buffers through the C ABI (H2D from page-locked memory + kernels + D2H per step)
+    pin = api.pinned(flat, off, si, ti)
     e2e_t = []
     for k in range(2 + args.steps):
         barrier()
@@ -310,6 +311,7 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
         if k >= 2:
             e2e_t.append(time.perf_counter() - t0)
+    pin.release()
     h2d = flat.nbytes + off.nbytes + si.nbytes + ti.nbytes
     d2h = sum(out[k].nbytes for k in ("R", "t", "error", "prev_error", "iters", "status"))
     assert np.array_equal(out["iters"], iters.astype(np.int32)), "host-buffer and device-resident paths disagree"
@@ -425,6 +427,7 @@ def bench_raycast(args, lib, api, dev, local_rank, pk, rank=0, world=1):
     sec = float(np.mean(ms)) / 1e3
     e2e_t = []
     host_out = np.empty((grid.ny, grid.nx), dtype=np.float32)
+    pin = api.pinned(host_out, flat, origins, off)
     for k in range(1 + steps):
         grid.reset()
         if world > 1:
@@ -437,6 +440,7 @@ def bench_raycast(args, lib, api, dev, local_rank, pk, rank=0, world=1):
         if k >= 1:
             e2e_t.append(time.perf_counter() - t0)
     e2e_s = float(np.mean(e2e_t))
+    pin.release()
     cells, hits_in = float(st["traversed"]), float(st["hits"])
     if world > 1:
         red = torch.tensor([sec, e2e_s], dtype=torch.float64, device=dev)

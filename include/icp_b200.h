@@ -33,6 +33,7 @@
 #ifndef ICP_B200_H
 #define ICP_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -213,6 +214,16 @@ int icpb200_grid_last_stats(void *grid, int64_t *stats4);
  * {tile, scans replayed, runs, SM cycles spent on the tile} of the last scan
  * chunk (zeros for idle tiles) and returns the number of tiles written. */
 int icpb200_grid_tile_profile(void *grid, int64_t *out, int64_t cap_tiles);
+
+/* ---- host buffers ----------------------------------------------------------
+ * The host-buffer entry points above accept any host pointer.  Buffers that
+ * are reused from call to call (a scan history, the caller's copy of the map)
+ * transfer at full PCIe rate once they are page-locked; these two calls do
+ * that for memory the CALLER owns (cudaHostRegister / cudaHostUnregister).
+ * The caller keeps ownership and must unpin before freeing.  The reference
+ * has no counterpart (numpy arrays in one address space, mapping.py:47). */
+int icpb200_pin_host(void *ptr, size_t bytes);
+int icpb200_unpin_host(void *ptr);
 
 #ifdef __cplusplus
 }

@@ -808,6 +808,23 @@ int icpb200_grid_tile_profile(void* grid, int64_t* out, int64_t cap_tiles) {
     return (int)n;
 }
 
+int icpb200_pin_host(void* ptr, size_t bytes) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!ptr || bytes == 0) { set_error("icpb200_pin_host: null pointer or empty range"); return ICPB200_ERR_ARG; }
+    int rc = init_locked(-1);
+    if (rc) return rc;
+    ICPB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return ICPB200_OK;
+}
+
+int icpb200_unpin_host(void* ptr) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!ptr) { set_error("icpb200_unpin_host: null pointer"); return ICPB200_ERR_ARG; }
+    if (!g_ctx.ready) return ICPB200_OK;
+    ICPB_CUDA(cudaHostUnregister(ptr));
+    return ICPB200_OK;
+}
+
 int icpb200_grid_last_stats(void* grid, int64_t* stats4) {
     if (!grid || !stats4) { set_error("icpb200_grid_last_stats: null pointer"); return ICPB200_ERR_ARG; }
     OccGrid* g = static_cast<OccGrid*>(grid);

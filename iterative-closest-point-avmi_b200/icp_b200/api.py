@@ -139,6 +139,39 @@ def voxel_downsample(points, voxel_size):
     return out[:int(n_out.value)].copy()
 
 
+class pinned:
+    """Page-lock numpy arrays the caller reuses from call to call (full-rate PCIe copies).
+
+    ``with pinned(flat, out): ...`` or keep the object and call ``release()``; the arrays must stay
+    alive and must not be resized while pinned."""
+
+    def __init__(self, *arrays):
+        self._lib = _lib.load()
+        self._ptrs = []
+        for a in arrays:
+            if not isinstance(a, np.ndarray) or not a.flags["C_CONTIGUOUS"] or a.nbytes == 0:
+                continue
+            check(self._lib.icpb200_pin_host(ctypes.c_void_p(a.ctypes.data), a.nbytes), "icpb200_pin_host")
+            self._ptrs.append(a.ctypes.data)
+
+    def release(self):
+        for p in self._ptrs:
+            self._lib.icpb200_unpin_host(ctypes.c_void_p(p))
+        self._ptrs = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.release()
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
 class DeviceGrid:
     """Owner of one device-resident occupancy grid handle."""
 

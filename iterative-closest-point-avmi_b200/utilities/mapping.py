@@ -42,12 +42,17 @@ class OccupancyGrid2D:
         self._dev = _api.DeviceGrid(self.nx, self.ny, self.min_x, self.min_y, self.resolution,
                                     self.l_hit, self.l_miss, self.log_odds_min, self.log_odds_max)
         self._host = None
+        self._mirror = None               # page-locked host copy, reused by every read-back
+        self._mirror_pin = None
 
     # ---- device <-> host -------------------------------------------------
     @property
     def log_odds(self):
         if self._host is None:
-            self._host = self._dev.read()
+            if self._mirror is None:
+                self._mirror = np.empty((self.ny, self.nx), dtype=np.float32)
+                self._mirror_pin = _api.pinned(self._mirror)
+            self._host = self._dev.read(self._mirror)
         return self._host
 
     # ---- update ----------------------------------------------------------
