@@ -151,7 +151,9 @@ __global__ void occ_fast_origins(const double* __restrict__ origins, int n_scans
                                sat_cell(floor((origins[2 * s + 1] - min_y) / res)));
 }
 
-template <bool FILL>
+// CHECK: some scan has more than 4095 rays, so a cell could collect more hits in one scan than
+// the 12-bit field holds; only then the hit atomic needs its return value.
+template <bool FILL, bool CHECK>
 __global__ void __launch_bounds__(256, 8) occ_fast_rays(const FastArgs a) {
     const long long rl = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // chunk-relative ray
     const long long r = a.ray_begin + rl;
@@ -198,7 +200,8 @@ __global__ void __launch_bounds__(256, 8) occ_fast_rays(const FastArgs a) {
                     }
                 } else {
                     const unsigned slot = a.slotmap[cell];
-                    hit_old = atomicAdd(&a.ord[(size_t)slot * a.ord_stride + sl], kHitUnit);   // looked at after the walk
+                    if (CHECK) hit_old = atomicAdd(&a.ord[(size_t)slot * a.ord_stride + sl], kHitUnit);   // looked at after the walk
+                    else atomicAdd(&a.ord[(size_t)slot * a.ord_stride + sl], kHitUnit);
                 }
             }
         }
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(256, 8) occ_fast_rays(const FastArgs a) {
         }
         if (!more) break;
     }
-    if (FILL && (hit_old >> 20) == 4095u) a.small[3] = 1u;
+    if (FILL && CHECK && (hit_old >> 20) == 4095u) a.small[3] = 1u;
     if (!FILL) {
         __shared__ unsigned long long part[3][8];
 #pragma unroll
@@ -690,7 +693,7 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
     a.tile_off = nullptr; a.runs = nullptr;
     a.small = d_small; a.stats = d_stats;
     const unsigned nblk = (unsigned)((nr + 255) / 256);
-    occ_fast_rays<false><<<nblk, 256, 0, st>>>(a);
+    occ_fast_rays<false, false><<<nblk, 256, 0, st>>>(a);
     ICPB_LAUNCH_CHECK();
     tm.mark("count");
     occ_tile_scan<<<1, 1024, 0, st>>>(g.tile_count.as<unsigned>(), n_tiles, g.offsets.as<unsigned>(), g.class_off.as<unsigned>(), g.tile_flag.as<unsigned>(), g.items.as<uint2>(), g.multi.as<int>(), d_small);
@@ -729,7 +732,10 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
     a.tile_off = g.class_off.as<unsigned>();
     a.runs = g.runs.as<uint4>();
     tm.mark("host gap");
-    occ_fast_rays<true><<<nblk, 256, 0, st>>>(a);
+    bool big_scan = false;
+    for (int s = s0; s < s0 + cs && !big_scan; ++s) big_scan = h_hit_off[s + 1] - h_hit_off[s] > 4095;
+    if (big_scan) occ_fast_rays<true, true><<<nblk, 256, 0, st>>>(a);
+    else occ_fast_rays<true, false><<<nblk, 256, 0, st>>>(a);
     ICPB_LAUNCH_CHECK();
     tm.mark("fill");
     const float lo = (float)g.lo_min, hi = (float)g.lo_max;

@@ -182,3 +182,18 @@ def test_many_scans_cross_the_chunk_boundary_and_neutral_miss():
         gpu._dev.update(origins, flat, off)
         ref.update_many(origins, flat, off, fast=True)
         assert_same(gpu, ref, str(kw))
+
+
+def test_hit_field_overflow_is_reported_and_the_handle_survives():
+    """More than 4095 endpoints of ONE scan in ONE cell exceed the packed hit counter: both device
+    paths must refuse loudly (no silent wrap), and the grid must keep working afterwards."""
+    bounds = (-3.2, 3.2, -3.2, 3.2)
+    gpu, ref = make_pair(bounds, **GKW)
+    pts = np.tile([[1.011, 0.512]], (5000, 1))
+    with pytest.raises(RuntimeError, match="4095"):
+        gpu.update_scan(np.zeros(2), pts)
+    gpu.reset()
+    ok = np.tile([[1.011, 0.512]], (4095, 1))
+    gpu.update_scan(np.zeros(2), ok)
+    ref.update_scan(np.zeros(2), ok, fast=True)
+    assert_same(gpu, ref, "after the refused call")
