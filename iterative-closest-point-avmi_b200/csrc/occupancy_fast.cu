@@ -53,14 +53,14 @@ constexpr unsigned kClaimed = 0xfffffffeu;   // slot map: being assigned
 constexpr unsigned kHitUnit = 1u << 20;      // ord word: hits << 20 | misses
 constexpr unsigned kMissMask = kHitUnit - 1u;
 constexpr int kTileNT = 256;
-constexpr int kLenShift = 4, kLenClasses = TS >> kLenShift;      // runs are grouped by length: 1-16, 17-32, 33-48, 49-64
+constexpr int kLenShift = 3, kLenClasses = TS >> kLenShift;      // runs are grouped by length: 1-8, 9-16, ... 57-64
 
 // 16-byte run record: everything the tile kernel needs to walk the run.
 //   w0 = local cell of the first step (12) | x-major (1) | major + (1) | minor + (1) | len-1 (6) | chunk-local scan (11)
 //   w1 = Bresenham error term at the first step   w2 = dmaj   w3 = dmin
 constexpr int kRunXMajor = 1 << 12, kRunMajPos = 1 << 13, kRunMinPos = 1 << 14;
 static_assert(TS == 64 && kOccMaxChunkScans <= 2048, "run record bit layout");
-static_assert(kLenClasses == 4, "occ_tile_scan reads the class counters as uint4");
+static_assert(kLenClasses == 8, "occ_tile_scan reads the class counters as two uint4");
 
 struct FastArgs {
     // rays
@@ -293,9 +293,9 @@ __global__ void __launch_bounds__(1024) occ_tile_scan(const unsigned* __restrict
     __syncthreads();
     for (int b0 = 0; b0 < n_tiles; b0 += 1024) {
         const int t = b0 + tid;
-        uint4 cc = make_uint4(0u, 0u, 0u, 0u);
-        if (t < n_tiles) cc = reinterpret_cast<const uint4*>(counts)[t];
-        const unsigned v = cc.x + cc.y + cc.z + cc.w;
+        uint4 cc = make_uint4(0u, 0u, 0u, 0u), cd = cc;
+        if (t < n_tiles) { cc = reinterpret_cast<const uint4*>(counts)[2 * t]; cd = reinterpret_cast<const uint4*>(counts)[2 * t + 1]; }
+        const unsigned v = cc.x + cc.y + cc.z + cc.w + cd.x + cd.y + cd.z + cd.w;
         if (v) atomicAdd(&hist[tile_flag[t] ? 0 : 1][32 - __clz(v)], (int)((v + kItemRuns - 1) / kItemRuns));
         unsigned inc = v;
 #pragma unroll
@@ -310,7 +310,9 @@ __global__ void __launch_bounds__(1024) occ_tile_scan(const unsigned* __restrict
         if (t < n_tiles) {
             const unsigned o = base + inc - v;
             offsets[t] = o;
-            reinterpret_cast<uint4*>(class_off)[t] = make_uint4(o, o + cc.x, o + cc.x + cc.y, o + cc.x + cc.y + cc.z);
+            const unsigned o4 = o + cc.x + cc.y + cc.z + cc.w;
+            reinterpret_cast<uint4*>(class_off)[2 * t] = make_uint4(o, o + cc.x, o + cc.x + cc.y, o + cc.x + cc.y + cc.z);
+            reinterpret_cast<uint4*>(class_off)[2 * t + 1] = make_uint4(o4, o4 + cd.x, o4 + cd.x + cd.y, o4 + cd.x + cd.y + cd.z);
         }
         __syncthreads();
         if (tid == 1023) carry = base + inc;
@@ -328,8 +330,8 @@ __global__ void __launch_bounds__(1024) occ_tile_scan(const unsigned* __restrict
     }
     __syncthreads();
     for (int t = tid; t < n_tiles; t += 1024) {
-        const uint4 cc = reinterpret_cast<const uint4*>(counts)[t];
-        const unsigned v = cc.x + cc.y + cc.z + cc.w;
+        const uint4 cc = reinterpret_cast<const uint4*>(counts)[2 * t], cd = reinterpret_cast<const uint4*>(counts)[2 * t + 1];
+        const unsigned v = cc.x + cc.y + cc.z + cc.w + cd.x + cd.y + cd.z + cd.w;
         if (v) {
             const int n_it = (int)((v + kItemRuns - 1) / kItemRuns);
             const int base = atomicAdd(&start[tile_flag[t] ? 0 : 1][32 - __clz(v)], n_it);
