@@ -671,6 +671,9 @@ void OccGrid::release_all() {
                       &counts, &offsets, &sums, &runs, &order, &small, &tile_prof,
                       &slotmap, &slot_cell, &ord, &tile_count, &hit_off_shift, &items, &multi, &ncount, &ev, &ev_count, &class_off, &tile_flag};
     for (DevBuf* b : bufs) b->release();
+    if (aux_stream) { cudaStreamDestroy(aux_stream); aux_stream = nullptr; }
+    if (ev_fork) { cudaEventDestroy(ev_fork); ev_fork = nullptr; }
+    if (ev_join) { cudaEventDestroy(ev_join); ev_join = nullptr; }
 }
 
 void* icpb200_grid_create(int nx, int ny, double min_x, double min_y, double resolution, double l_hit,

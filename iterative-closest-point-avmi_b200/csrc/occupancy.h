@@ -37,6 +37,8 @@ struct OccGrid {
     DevBuf counts, offsets, sums, runs, order, small, tile_prof;
     // order-free path (occupancy_fast.cu)
     DevBuf slotmap, slot_cell, ord, tile_count, hit_off_shift, items, multi, ncount, ev, ev_count, class_off, tile_flag;
+    cudaStream_t aux_stream = nullptr;             // the hit cells' replay runs here, under the remaining tiles
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int fast_ctas = 0;
     bool use_fast = true;                          // ICPB200_OCC_PATH=ordered forces the ordered tile replay
     int split = 1;                                 // lock-step windows per 32-run chunk (tuning knob)

@@ -396,7 +396,8 @@ struct TileArgs {
     const unsigned* tile_off;
     const uint4* runs;
     const uint2* items;                       // (tile, piece); tiles with hit cells first
-    unsigned n_items, n_hit_items;
+    unsigned n_hit_items, item_first, item_end;
+    int persistent;
     const int* multi;                         // tiles cut into several items
     unsigned* small;                          // [1] n_items [2] queue [5] n_multi
     unsigned* ncount;                         // ny * nx partial miss counts of multi-item tiles (kept zero)
@@ -485,12 +486,17 @@ __global__ void __launch_bounds__(kTileNT) occ_fast_tiles(const TileArgs a) {
     __shared__ uint2 cur_item;
     __shared__ unsigned cur_q;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (;;) {
+    // Two launch shapes over the item range [item_first, item_end): persistent CTAs pulling from a
+    // queue (the hit tiles, heaviest first), or one item per CTA (the rest: CTAs retire all the
+    // time, so the hit cells' replay on the second stream finds SM slots while this runs).
+    for (bool first = true;; first = false) {
         __syncthreads();
         if (tid == 0) {
-            const unsigned q = atomicAdd(&a.small[2], 1u);
+            unsigned q;
+            if (a.persistent) q = a.item_first + atomicAdd(&a.small[2], 1u);
+            else q = first ? a.item_first + blockIdx.x : a.item_end;
             cur_q = q;
-            cur_item = q < a.n_items ? a.items[q] : make_uint2(kNone, 0u);
+            cur_item = q < a.item_end ? a.items[q] : make_uint2(kNone, 0u);
         }
         __syncthreads();
         if (cur_item.x == kNone) break;
@@ -667,6 +673,13 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
         g.slot_cell.reserve(sizeof(unsigned) * (size_t)nr) || g.items.reserve(sizeof(uint2) * max_items) ||
         g.multi.reserve(sizeof(int) * (size_t)n_tiles) || g.tile_flag.reserve(sizeof(unsigned) * (size_t)n_tiles))
         return ICPB200_ERR_CUDA;
+    if (!g.aux_stream) {
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        ICPB_CUDA(cudaStreamCreateWithPriority(&g.aux_stream, cudaStreamNonBlocking, prio_hi));
+        ICPB_CUDA(cudaEventCreateWithFlags(&g.ev_fork, cudaEventDisableTiming));
+        ICPB_CUDA(cudaEventCreateWithFlags(&g.ev_join, cudaEventDisableTiming));
+    }
     unsigned* d_small = g.small.as<unsigned>();
     unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(g.small.as<unsigned char>() + 64);
     StageTimer tm;
@@ -741,6 +754,7 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
     ICPB_LAUNCH_CHECK();
     tm.mark("fill");
     const float lo = (float)g.lo_min, hi = (float)g.lo_max;
+    bool replayed = false;
     if (total_runs) {
         TileArgs t;
         t.grid = g.grid.as<float>();
@@ -755,27 +769,49 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
         t.ord = g.ord.as<unsigned>();
         t.ord_stride = stride;
         t.l_hit = g.l_hit; t.l_miss = g.l_miss; t.lo = lo; t.hi = hi;
-        t.n_items = h_small[1]; t.n_hit_items = h_small[6];
-        const unsigned n_multi = h_small[5];
-        occ_fast_tiles<<<std::min<unsigned>(t.n_items, (unsigned)g.fast_ctas), kTileNT, 0, st>>>(t);
-        ICPB_LAUNCH_CHECK();
-        tm.mark("tiles");
+        const unsigned n_items = h_small[1], n_multi = h_small[5];
+        t.n_hit_items = h_small[6];
+        if (t.n_hit_items) {
+            t.item_first = 0u; t.item_end = t.n_hit_items; t.persistent = 1;
+            occ_fast_tiles<<<std::min<unsigned>(t.n_hit_items, (unsigned)g.fast_ctas), kTileNT, 0, st>>>(t);
+            ICPB_LAUNCH_CHECK();
+        }
+        tm.mark("tiles hit");
+        if (n_slots) {
+            // the hit cells' tables are complete: replay them on the second stream, under the remaining tiles
+            ICPB_CUDA(cudaEventRecord(g.ev_fork, st));
+            ICPB_CUDA(cudaStreamWaitEvent(g.aux_stream, g.ev_fork, 0));
+            occ_fast_compact<<<(n_slots * 32u + 255u) / 256u, 256, 0, g.aux_stream>>>(g.ord.as<unsigned>(), g.ev.as<unsigned>(),
+                                                                                      g.ev_count.as<unsigned>(), d_small, cs, stride);
+            ICPB_LAUNCH_CHECK();
+            occ_fast_chain<<<(n_slots + 127u) / 128u, 128, 0, g.aux_stream>>>(g.grid.as<float>(), g.slotmap.as<unsigned>(),
+                                                                             g.slot_cell.as<unsigned>(), g.ev.as<unsigned>(),
+                                                                             g.ev_count.as<unsigned>(), d_small, stride, g.l_hit, g.l_miss, lo, hi);
+            ICPB_LAUNCH_CHECK();
+            ICPB_CUDA(cudaEventRecord(g.ev_join, g.aux_stream));
+            replayed = true;
+        }
+        if (n_items > t.n_hit_items) {
+            t.item_first = t.n_hit_items; t.item_end = n_items; t.persistent = 0;
+            occ_fast_tiles<<<n_items - t.n_hit_items, kTileNT, 0, st>>>(t);
+            ICPB_LAUNCH_CHECK();
+        }
         if (n_multi) {
             occ_fast_apply_multi<<<n_multi * 4u, 256, 0, st>>>(t);
             ICPB_LAUNCH_CHECK();
         }
-        tm.mark("apply multi");
+        tm.mark("tiles rest");
+        if (replayed) ICPB_CUDA(cudaStreamWaitEvent(st, g.ev_join, 0));
+        tm.mark("join replay");
     }
-    if (n_slots) {
+    if (n_slots && !replayed) {                       // no tile runs at all: hits only
         occ_fast_compact<<<(n_slots * 32u + 255u) / 256u, 256, 0, st>>>(g.ord.as<unsigned>(), g.ev.as<unsigned>(),
                                                                         g.ev_count.as<unsigned>(), d_small, cs, stride);
         ICPB_LAUNCH_CHECK();
-        tm.mark("compact");
         occ_fast_chain<<<(n_slots + 127u) / 128u, 128, 0, st>>>(g.grid.as<float>(), g.slotmap.as<unsigned>(),
                                                                 g.slot_cell.as<unsigned>(), g.ev.as<unsigned>(),
                                                                 g.ev_count.as<unsigned>(), d_small, stride, g.l_hit, g.l_miss, lo, hi);
         ICPB_LAUNCH_CHECK();
-        tm.mark("chain");
     }
     tm.mark("end");
     tm.report();
