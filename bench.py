@@ -536,6 +536,32 @@ def bench_extras(args, api):
                                     pair_kernel_ms=ks["pair_kernel_ns"] / 1e6,
                                     note="the 52k-point target is re-downsampled and re-gridded inside every call, "
                                          "as ICP() does (icp.py:150-151)")
+    # F1: rotation-search pre-alignment, the reference's config values
+    # (config.yaml:37-39: voxel 0.15, coarse 1.5 deg = 240 angles, fine 0.1 deg = 30 angles)
+    from utilities import rotation_search
+    import contextlib
+    import io
+    scans, _ = synth.make_sequence(258, world="room", seed=0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        rotation_search(scans[0], scans[1], voxel_size=0.15, angle_step_coarse=1.5, angle_step_fine=0.1)     # warm
+        t0 = time.perf_counter()
+        for k in range(20):
+            rotation_search(scans[k], scans[k + 1], voxel_size=0.15, angle_step_coarse=1.5, angle_step_fine=0.1)
+        call_ms = (time.perf_counter() - t0) / 20 * 1e3
+    n = 256
+    ds = [api.voxel_downsample(scans[k], 0.15) for k in range(n + 1)]
+    srcs = [d - d.mean(axis=0) for d in ds[:n]]
+    tgts = ds[1:n + 1]
+    angles = np.deg2rad(np.arange(-180, 180, 1.5))
+    api.rotation_scores(srcs[:8], tgts[:8], [angles] * 8, [t.mean(axis=0) for t in tgts[:8]])
+    t0 = time.perf_counter()
+    sc = api.rotation_scores(srcs, tgts, [angles] * n, [t.mean(axis=0) for t in tgts])
+    dt = time.perf_counter() - t0
+    evals = float(sum(len(a) * len(b) for a, b in zip(srcs, tgts))) * len(angles)
+    out["F1_rotation_search"] = dict(single_call_ms=call_ms, angles_per_call=270, batch_problems=n,
+                                     batch_coarse_sweeps_per_s=n / dt, batch_pair_evals_per_s=evals / dt,
+                                     points_after_voxel=float(np.mean([len(d) for d in ds])),
+                                     best_angles_deg=[float(np.degrees(angles[int(np.argmin(s))])) for s in sc[:4]])
     return out
 
 

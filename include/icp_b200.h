@@ -215,6 +215,23 @@ int icpb200_grid_last_stats(void *grid, int64_t *stats4);
  * chunk (zeros for idle tiles) and returns the number of tiles written. */
 int icpb200_grid_tile_profile(void *grid, int64_t *out, int64_t cap_tiles);
 
+/* ---- rotation-search scoring -------------------------------------------------
+ * The pre-alignment sweeps in front of every ICP call:
+ *   utilities/features.py:165-242  rotation_search  (score every angle of a coarse, then a fine sweep)
+ *   slam.py:111-183                _submap_rotation_search (the same around a predicted pose, plus one
+ *                                  nearest-neighbour translation step, slam.py:166-181)
+ * Both evaluate  score(angle) = mean_i min_j |R(angle) s_i + shift - t_j|^2  (features.py:205-211,
+ * slam.py:138-143: KDTree distance, squared again, np.mean).  Problems are independent and packed like
+ * the clouds of icpb200_icp_pairs: src (sum n_s, 2), tgt (sum n_t, 2), angles (radians) and one shift
+ * (2 doubles) per problem; scores_out receives one value per angle in the order given.  With
+ * nn_dist_out / nn_idx_out (both or neither; exactly one angle per problem) the exact nearest target
+ * index and distance of every source point are returned as tgt_tree.query would (slam.py:168).
+ * Limits: 2-D, targets <= 8192 points (they live in shared memory). */
+int icpb200_rotation_scores(int n_problems, const double *src, const int64_t *src_off,
+                            const double *tgt, const int64_t *tgt_off, const double *angles,
+                            const int64_t *ang_off, const double *shift, double *scores_out,
+                            double *nn_dist_out, int32_t *nn_idx_out);
+
 /* ---- host buffers ----------------------------------------------------------
  * The host-buffer entry points above accept any host pointer.  Buffers that
  * are reused from call to call (a scan history, the caller's copy of the map)

@@ -371,7 +371,7 @@ void icpb200_shutdown(void) {
                       &c.aux_ds[0], &c.aux_ds[1], &c.aux_n[0], &c.aux_n[1], &c.aux_box[0], &c.aux_box[1],
                       &c.aux_nrm[0], &c.aux_nrm[1], &c.aux_flags[0], &c.aux_flags[1], &c.vox_in, &c.vox_out,
                       &c.big_keys, &c.big_idx, &c.grid_start, &c.grid_items, &c.grid_cell, &c.grid_desc, &c.grid_off,
-                      &c.grid_buckets, &c.cont_cur, &c.cont_match, &c.cont_d2lb, &c.cont_moved, &c.cont_scalar, &c.cont_list};
+                      &c.grid_buckets, &c.rot_src, &c.rot_tgt, &c.rot_ang, &c.rot_off, &c.rot_out, &c.cont_cur, &c.cont_match, &c.cont_d2lb, &c.cont_moved, &c.cont_scalar, &c.cont_list};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 4; ++i) if (c.ev[i]) { cudaEventDestroy(c.ev[i]); c.ev[i] = nullptr; }
     cudaStreamDestroy(c.stream);
@@ -661,6 +661,74 @@ int icpb200_voxel_downsample(const double* pts, int64_t n, int dim, double voxel
     }
     ICPB_CUDA(cudaMemcpy(out, c.vox_out.p, sizeof(double) * dim * (size_t)m, cudaMemcpyDeviceToHost));
     *n_out = m;
+    return ICPB200_OK;
+}
+
+// ---- rotation-search scoring (features.py:165-242, slam.py:111-183) ---------------------------------
+int icpb200_rotation_scores(int n_problems, const double* src, const int64_t* src_off, const double* tgt,
+                            const int64_t* tgt_off, const double* angles, const int64_t* ang_off, const double* shift,
+                            double* scores_out, double* nn_dist_out, int32_t* nn_idx_out) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (n_problems <= 0 || !src || !src_off || !tgt || !tgt_off || !angles || !ang_off || !shift || !scores_out ||
+        ((nn_dist_out == nullptr) != (nn_idx_out == nullptr))) {
+        set_error("icpb200_rotation_scores: null pointer or n_problems <= 0");
+        return ICPB200_ERR_ARG;
+    }
+    if (src_off[0] != 0 || tgt_off[0] != 0 || ang_off[0] != 0) { set_error("icpb200_rotation_scores: offsets must start at 0"); return ICPB200_ERR_ARG; }
+    long long max_t = 0, max_a = 0;
+    for (int p = 0; p < n_problems; ++p) {
+        if (src_off[p + 1] < src_off[p] || tgt_off[p + 1] < tgt_off[p] || ang_off[p + 1] < ang_off[p]) {
+            set_error("icpb200_rotation_scores: offsets decrease at problem %d", p);
+            return ICPB200_ERR_ARG;
+        }
+        max_t = std::max<long long>(max_t, tgt_off[p + 1] - tgt_off[p]);
+        max_a = std::max<long long>(max_a, ang_off[p + 1] - ang_off[p]);
+        if (nn_idx_out && ang_off[p + 1] - ang_off[p] != 1) {
+            set_error("icpb200_rotation_scores: nearest-neighbour output needs exactly one angle per problem");
+            return ICPB200_ERR_ARG;
+        }
+    }
+    const long long n_src = src_off[n_problems], n_tgt = tgt_off[n_problems], n_ang = ang_off[n_problems];
+    if (n_ang == 0) return ICPB200_OK;
+    if (max_t > 8192 || n_problems > 65535) {
+        set_error("icpb200_rotation_scores: targets are limited to 8192 points (got %lld) and 65535 problems per call", max_t);
+        return ICPB200_ERR_LIMIT;
+    }
+    int rc = init_locked(-1);
+    if (rc) return rc;
+    Context& c = g_ctx;
+    cudaStream_t st = c.stream;
+    const size_t np = (size_t)n_problems;
+    const size_t b_src = sizeof(double) * 2 * (size_t)n_src, b_tgt = sizeof(double) * 2 * (size_t)n_tgt;
+    const size_t b_ang = sizeof(double) * (size_t)n_ang, b_off = sizeof(int64_t) * (np + 1);
+    if (c.rot_src.reserve(b_src + 16) || c.rot_tgt.reserve(b_tgt + 16) || c.rot_ang.reserve(b_ang + sizeof(double) * 2 * np) ||
+        c.rot_off.reserve(3 * b_off) || c.rot_out.reserve(b_ang + (sizeof(double) + sizeof(int)) * (size_t)std::max<long long>(n_src, 1)))
+        return ICPB200_ERR_CUDA;
+    unsigned char* d_off = c.rot_off.as<unsigned char>();
+    ICPB_CUDA(cudaMemcpyAsync(c.rot_src.p, src, b_src, cudaMemcpyHostToDevice, st));
+    ICPB_CUDA(cudaMemcpyAsync(c.rot_tgt.p, tgt, b_tgt, cudaMemcpyHostToDevice, st));
+    ICPB_CUDA(cudaMemcpyAsync(c.rot_ang.p, angles, b_ang, cudaMemcpyHostToDevice, st));
+    ICPB_CUDA(cudaMemcpyAsync(c.rot_ang.as<unsigned char>() + b_ang, shift, sizeof(double) * 2 * np, cudaMemcpyHostToDevice, st));
+    ICPB_CUDA(cudaMemcpyAsync(d_off, src_off, b_off, cudaMemcpyHostToDevice, st));
+    ICPB_CUDA(cudaMemcpyAsync(d_off + b_off, tgt_off, b_off, cudaMemcpyHostToDevice, st));
+    ICPB_CUDA(cudaMemcpyAsync(d_off + 2 * b_off, ang_off, b_off, cudaMemcpyHostToDevice, st));
+    RotArgs a;
+    a.src = c.rot_src.as<double>(); a.src_off = reinterpret_cast<const long long*>(d_off);
+    a.tgt = c.rot_tgt.as<double>(); a.tgt_off = reinterpret_cast<const long long*>(d_off + b_off);
+    a.angles = c.rot_ang.as<double>(); a.ang_off = reinterpret_cast<const long long*>(d_off + 2 * b_off);
+    a.shift = reinterpret_cast<const double*>(c.rot_ang.as<unsigned char>() + b_ang);
+    a.scores = c.rot_out.as<double>();
+    a.nn_dist = nn_dist_out ? reinterpret_cast<double*>(c.rot_out.as<unsigned char>() + b_ang) : nullptr;
+    a.nn_idx = nn_idx_out ? reinterpret_cast<int*>(c.rot_out.as<unsigned char>() + b_ang + sizeof(double) * (size_t)n_src) : nullptr;
+    a.cap_t = round_up((int)std::max<long long>(max_t, 32), 32);
+    if (rot_smem_bytes(a.cap_t) > (size_t)c.max_smem_optin) { set_error("icpb200_rotation_scores: target too large for shared memory"); return ICPB200_ERR_LIMIT; }
+    if ((rc = launch_rot_scores(a, n_problems, (int)max_a, c.sm_count, st))) return rc;
+    ICPB_CUDA(cudaMemcpyAsync(scores_out, a.scores, b_ang, cudaMemcpyDeviceToHost, st));
+    if (nn_dist_out) {
+        ICPB_CUDA(cudaMemcpyAsync(nn_dist_out, a.nn_dist, sizeof(double) * (size_t)n_src, cudaMemcpyDeviceToHost, st));
+        ICPB_CUDA(cudaMemcpyAsync(nn_idx_out, a.nn_idx, sizeof(int) * (size_t)n_src, cudaMemcpyDeviceToHost, st));
+    }
+    ICPB_CUDA(cudaStreamSynchronize(st));
     return ICPB200_OK;
 }
 

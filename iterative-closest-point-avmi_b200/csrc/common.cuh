@@ -58,6 +58,8 @@ struct Context {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // K1 start | K2 start | K3 start | K3 end
     // voxel_downsample entry point
     DevBuf vox_in, vox_out;
+    // rotation-search scoring
+    DevBuf rot_src, rot_tgt, rot_ang, rot_off, rot_out;
 };
 
 Context& ctx();

@@ -1511,6 +1511,165 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
     }
 }
 
+// ---- K8: rotation-search scoring (features.py:165-242, slam.py:111-183) ---------------------------
+// score(angle) = mean over the source of the squared distance to the nearest target after
+// p' = R(angle) p + shift.  One CTA per (problem, angle): the target sits in shared memory (fp64
+// tile-padded SoA + fp32 recentred, exactly as K3 stages it), the source is rotated on the fly in
+// fp64, the same fp32 tile sweep finds the winning tile and the same fp64 re-evaluation + bound
+// (or a full fp64 scan when the bound cannot exclude another tile) makes the distance exact.
+// With want_nn the per-point nearest index and distance are written instead (one angle).
+struct RotProblem {
+    const double* tx; const double* ty;            // shared-memory target
+    const float4* t32;
+    int n_t, n_tiles;
+    double c0, c1;
+    float ta;
+};
+
+__device__ __forceinline__ void rot_exact(const RotProblem& P, double px, double py, float sxv, float syv, float b2v, int btv,
+                                          double& d2_out, int& j_out) {
+    const int j0 = btv * 32, j1 = min(j0 + 32, P.n_t);
+    double best = INFINITY;
+    int bj = j0;
+    for (int j = j0; j < j1; ++j) {
+        const int jp = pad_index(j);
+        const double dx = px - P.tx[jp], dy = py - P.ty[jp];
+        const double d = dx * dx + dy * dy;
+        if (d < best) { best = d; bj = j; }
+    }
+    const float mag = fabsf(sxv) + fabsf(syv) + P.ta;
+    const double other = sqrt((double)b2v) * (1.0 - 1.0e-6) - 1.8e-7 * (double)mag;
+    if (!(other > sqrt(best))) {                   // another tile may hold a closer point: exact scan
+        best = INFINITY; bj = 0;
+        for (int j = 0; j < P.n_t; ++j) {
+            const int jp = pad_index(j);
+            const double dx = px - P.tx[jp], dy = py - P.ty[jp];
+            const double d = dx * dx + dy * dy;
+            if (d < best) { best = d; bj = j; }
+        }
+    }
+    d2_out = best; j_out = bj;
+}
+
+template <int S>
+__device__ __forceinline__ double rot_round(const RotProblem& P, const double* __restrict__ src, int n_s, int first_chunk,
+                                            double ca, double sa, double ox, double oy, double* nn_d, int* nn_idx) {
+    const int lane = threadIdx.x & 31;
+    float sx[S], sy[S], b1[S], b2[S];
+    double px[S], py[S];
+    int bt[S], pt[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const int i = (first_chunk + s * kNW) * 32 + lane;
+        pt[s] = i < n_s ? i : -1;
+        const double x = pt[s] >= 0 ? src[2 * (size_t)i] : 0.0, y = pt[s] >= 0 ? src[2 * (size_t)i + 1] : 0.0;
+        px[s] = x * ca + y * (-sa) + ox;           // src @ R.T + shift (features.py:208-209)
+        py[s] = x * sa + y * ca + oy;
+        sx[s] = (float)(px[s] - P.c0);
+        sy[s] = (float)(py[s] - P.c1);
+    }
+    sweep2d<S>(P.t32, 0, P.n_tiles, sx, sy, b1, b2, bt);
+    double acc = 0.0;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        if (pt[s] < 0) continue;
+        double d2;
+        int j;
+        rot_exact(P, px[s], py[s], sx[s], sy[s], b2[s], bt[s], d2, j);
+        const double d = sqrt(d2);                 // KDTree returns the distance; the callers square it again
+        acc += d * d;
+        if (nn_d) { nn_d[pt[s]] = d; nn_idx[pt[s]] = j; }
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(kNT) rot_scores_kernel(const RotArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    CtaShared& sh = *reinterpret_cast<CtaShared*>(smem);
+    const int p = blockIdx.y, k0 = blockIdx.x * a.angles_per_cta, tid = threadIdx.x, w = tid >> 5;
+    const long long ab = a.ang_off[p];
+    const int n_ang = (int)(a.ang_off[p + 1] - ab);
+    if (k0 >= n_ang) return;
+    const double* src = a.src + 2 * a.src_off[p];
+    const double* tgt = a.tgt + 2 * a.tgt_off[p];
+    const int n_s = (int)(a.src_off[p + 1] - a.src_off[p]), n_t = (int)(a.tgt_off[p + 1] - a.tgt_off[p]);
+    const int k1 = min(k0 + a.angles_per_cta, n_ang);
+    if (n_s <= 0 || n_t <= 0) {
+        for (int k = k0 + tid; k < k1; k += kNT) a.scores[ab + k] = INFINITY;
+        return;
+    }
+    const int tstride = a.cap_t + a.cap_t / 32;
+    double* tx = reinterpret_cast<double*>(smem + align16(sizeof(CtaShared)));
+    double* ty = tx + tstride;
+    float* f = reinterpret_cast<float*>(smem + align16(sizeof(CtaShared)) + align16(sizeof(double) * 2 * (size_t)tstride));
+    int phase = 0;
+    // bounding box -> recentring offset
+    double b[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+    for (int j = tid; j < n_t; j += kNT) {
+        const double x = tgt[2 * (size_t)j], y = tgt[2 * (size_t)j + 1];
+        b[0] = fmin(b[0], x); b[1] = fmin(b[1], y); b[2] = fmin(b[2], -x); b[3] = fmin(b[3], -y);
+    }
+    block_reduce<4, MinOp>(b, sh, phase);
+    RotProblem P;
+    P.tx = tx; P.ty = ty; P.t32 = reinterpret_cast<const float4*>(f);
+    P.n_t = n_t; P.n_tiles = (n_t + 31) / 32;
+    P.c0 = 0.5 * (b[0] - b[2]); P.c1 = 0.5 * (b[1] - b[3]);
+    P.ta = (float)((0.5 * (-b[2] - b[0]) + 0.5 * (-b[3] - b[1])) * 1.0000002);
+    for (int j = tid; j < P.n_tiles * 32; j += kNT) {
+        if (j < n_t) {
+            const double x = tgt[2 * (size_t)j], y = tgt[2 * (size_t)j + 1];
+            tx[pad_index(j)] = x; ty[pad_index(j)] = y;
+            f[2 * j] = (float)(x - P.c0); f[2 * j + 1] = (float)(y - P.c1);
+        } else {
+            f[2 * j] = kFar; f[2 * j + 1] = kFar;
+        }
+    }
+    __syncthreads();
+    const int n_chunks = (n_s + 31) >> 5;
+    // the staged target serves every angle of this CTA's group
+    for (int k = k0; k < k1; ++k) {
+    const double ang = a.angles[ab + k];
+    double sa, ca;
+    sincos(ang, &sa, &ca);                         // np.cos / np.sin of the same double
+    const double ox = a.shift[2 * p], oy = a.shift[2 * p + 1];
+    double* nn_d = a.nn_dist ? a.nn_dist + a.src_off[p] : nullptr;
+    int* nn_i = a.nn_idx ? a.nn_idx + a.src_off[p] : nullptr;
+    double acc[1] = {0.0};
+    constexpr int kRotS = 4;                       // chunks per warp per round (register budget: two CTAs per SM)
+    for (int base = 0; base < n_chunks; base += kRotS * kNW) {
+        const int first = base + w;
+        const int mine = first < n_chunks ? min(kRotS, (n_chunks - first + kNW - 1) / kNW) : 0;   // warp-uniform
+        switch (mine) {
+            case 0: break;
+            case 1: acc[0] += rot_round<1>(P, src, n_s, first, ca, sa, ox, oy, nn_d, nn_i); break;
+            case 2: acc[0] += rot_round<2>(P, src, n_s, first, ca, sa, ox, oy, nn_d, nn_i); break;
+            case 3: acc[0] += rot_round<3>(P, src, n_s, first, ca, sa, ox, oy, nn_d, nn_i); break;
+            default: acc[0] += rot_round<4>(P, src, n_s, first, ca, sa, ox, oy, nn_d, nn_i); break;
+        }
+    }
+    block_reduce<1, SumOp>(acc, sh, phase);
+    if (tid == 0) a.scores[ab + k] = acc[0] / (double)n_s;         // np.mean(dists ** 2)
+    }
+}
+
+size_t rot_smem_bytes(int cap_t) {
+    return align16(sizeof(CtaShared)) + align16(sizeof(double) * 2 * (size_t)(cap_t + cap_t / 32)) + sizeof(float) * 2 * (size_t)cap_t + 16;
+}
+
+int launch_rot_scores(const RotArgs& a_in, int n_problems, int max_angles, int sm_count, cudaStream_t stream) {
+    RotArgs a = a_in;
+    // one angle per CTA while that still leaves SMs idle, groups of up to 8 once the launch fills the machine
+    a.angles_per_cta = 1;
+    while (a.angles_per_cta < 8 && (long long)n_problems * ((max_angles + 2 * a.angles_per_cta - 1) / (2 * a.angles_per_cta)) >= 4LL * sm_count)
+        a.angles_per_cta *= 2;
+    max_angles = (max_angles + a.angles_per_cta - 1) / a.angles_per_cta;
+    const size_t smem = rot_smem_bytes(a.cap_t);
+    ICPB_CUDA(cudaFuncSetAttribute(rot_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rot_scores_kernel<<<dim3((unsigned)max_angles, (unsigned)n_problems), kNT, smem, stream>>>(a);
+    ICPB_LAUNCH_CHECK();
+    return ICPB200_OK;
+}
+
 // ---- host-side launchers -------------------------------------------------------------
 int launch_mark_used(const IcpArgs& a, bool p2l, cudaStream_t stream) {
     mark_used_kernel<<<(a.n_pairs + 255) / 256, 256, 0, stream>>>(a.n_pairs, a.src_idx, a.tgt_idx, a.s.used, a.t.used,

@@ -86,6 +86,20 @@ struct IcpArgs {
     int trace_stride;
 };
 
+// K8: rotation-search scoring.  Problems are independent (source, target, angle list, shift).
+struct RotArgs {
+    const double* src; const long long* src_off;       // (sum n_s, 2), n_problems + 1
+    const double* tgt; const long long* tgt_off;
+    const double* angles; const long long* ang_off;    // radians
+    const double* shift;                               // 2 per problem: added after the rotation
+    double* scores;                                    // one per angle
+    double* nn_dist; int* nn_idx;                      // optional, per source point (single-angle queries)
+    int cap_t;                                         // multiple of 32 >= the largest target
+    int angles_per_cta;                                // set by the launcher
+};
+size_t rot_smem_bytes(int cap_t);
+int launch_rot_scores(const RotArgs& a, int n_problems, int max_angles, int sm_count, cudaStream_t stream);
+
 size_t icp_pair_smem_bytes(int dim, int cap_s, int cap_t);
 size_t icp_voxel_smem_bytes(int sort_pad);
 size_t icp_normals_smem_bytes(int cap_t);

@@ -60,6 +60,8 @@ PROTOTYPES = {
     "icpb200_grid_device_ptr": (ctypes.c_void_p, [ctypes.c_void_p]),
     "icpb200_grid_tile_profile": (ctypes.c_int, [ctypes.c_void_p, c_int64_p, ctypes.c_int64]),
     "icpb200_grid_last_stats": (ctypes.c_int, [ctypes.c_void_p, c_int64_p]),
+    "icpb200_rotation_scores": (ctypes.c_int, [ctypes.c_int, c_double_p, c_int64_p, c_double_p, c_int64_p, c_double_p,
+                                               c_int64_p, c_double_p, c_double_p, c_double_p, c_int32_p]),
     "icpb200_pin_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),
     "icpb200_unpin_host": (ctypes.c_int, [ctypes.c_void_p]),
 }

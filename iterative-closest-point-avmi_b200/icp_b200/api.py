@@ -139,6 +139,35 @@ def voxel_downsample(points, voxel_size):
     return out[:int(n_out.value)].copy()
 
 
+def rotation_scores(sources, targets, angle_lists, shifts, want_nn=False):
+    """score(angle) = mean_i min_j |R(angle) s_i + shift - t_j|^2 for every angle of every problem
+    (features.py:205-211, slam.py:138-143); one launch for all problems and angles.
+
+    Returns a list of score arrays, plus (dist, idx) lists when ``want_nn`` (one angle per problem)."""
+    from .synth import pack_ragged
+    src, so = pack_ragged([_f64(s).reshape(-1, 2) for s in sources])
+    tgt, to = pack_ragged([_f64(t).reshape(-1, 2) for t in targets])
+    angs = [np.ascontiguousarray(a, dtype=np.float64).reshape(-1) for a in angle_lists]
+    ao = np.zeros(len(angs) + 1, dtype=np.int64)
+    ao[1:] = np.cumsum([len(a) for a in angs])
+    ang = np.concatenate(angs) if angs else np.zeros(0)
+    sh = _f64(shifts).reshape(-1, 2)
+    if not (len(sources) == len(targets) == len(angs) == len(sh)):
+        raise ValueError("rotation_scores: one target, angle list and shift per source")
+    scores = np.empty(int(ao[-1]), dtype=np.float64)
+    nn_d = np.empty(int(so[-1]), dtype=np.float64) if want_nn else None
+    nn_i = np.empty(int(so[-1]), dtype=np.int32) if want_nn else None
+    check(_lib.load().icpb200_rotation_scores(len(angs), _ptr(src, c_double_p), _ptr(so, c_int64_p), _ptr(tgt, c_double_p),
+                                              _ptr(to, c_int64_p), _ptr(ang, c_double_p), _ptr(ao, c_int64_p),
+                                              _ptr(sh, c_double_p), _ptr(scores, c_double_p),
+                                              _ptr(nn_d, c_double_p) if want_nn else None,
+                                              _ptr(nn_i, c_int32_p) if want_nn else None), "icpb200_rotation_scores")
+    out = [scores[ao[k]:ao[k + 1]] for k in range(len(angs))]
+    if not want_nn:
+        return out
+    return out, [nn_d[so[k]:so[k + 1]] for k in range(len(angs))], [nn_i[so[k]:so[k + 1]] for k in range(len(angs))]
+
+
 class pinned:
     """Page-lock numpy arrays the caller reuses from call to call (full-rate PCIe copies).
 

@@ -8,5 +8,6 @@ by these names (slam.py:8-10, demos/teapot_icp_demo.py:23).
 """
 from .icp import ICP, voxel_downsample
 from .mapping import OccupancyGrid2D
+from .features import rotation_search, submap_rotation_search
 
-__all__ = ["ICP", "voxel_downsample", "OccupancyGrid2D"]
+__all__ = ["ICP", "voxel_downsample", "OccupancyGrid2D", "rotation_search", "submap_rotation_search"]

@@ -112,3 +112,20 @@ def test_submap_fixture():
             g[f"{tag}/src"], g["submap"], 1e-10, 150, 0.04, R_init=g[f"{tag}/R_init"], t_init=g[f"{tag}/t_init"],
             method="point_to_point", max_corr_dist=1.5)
         assert same_bits(R, g[f"{tag}/R"]) and same_bits(t, g[f"{tag}/t"]) and iters == int(g[f"{tag}/iters"])
+
+
+def test_rotation_search_oracle_reproduces_the_reference():
+    """tests/golden/rotation.npz holds the live reference's outputs (oracle/pin_rotation.py)."""
+    from oracle import features_oracle as fo
+    g = load_golden("rotation.npz")
+    for name in ("cfg", "defaults", "turned", "tiny"):
+        v, c, f = g[f"rs_{name}_kw"]
+        R, t, score = fo.rotation_search(g[f"rs_{name}_src"], g[f"rs_{name}_tgt"], voxel_size=v, angle_step_coarse=c,
+                                         angle_step_fine=f)[:3]
+        assert R.tobytes() == g[f"rs_{name}_R"].tobytes() and t.tobytes() == g[f"rs_{name}_t"].tobytes()
+        assert np.float64(score).tobytes() == g[f"rs_{name}_score"].tobytes()
+    for name in ("cfg", "defaults"):
+        ar, st, fs, v = g[f"sub_{name}_kw"]
+        R, t = fo.submap_rotation_search(g[f"sub_{name}_src"], g[f"sub_{name}_map"], g[f"sub_{name}_pose"], angle_range=ar,
+                                         angle_step=st, fine_step=fs, voxel_size=v)
+        assert R.tobytes() == g[f"sub_{name}_R"].tobytes() and t.tobytes() == g[f"sub_{name}_t"].tobytes()
