@@ -211,7 +211,7 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
     if (c.queue.reserve(4 * sizeof(unsigned)) || c.stats.reserve(16 * sizeof(unsigned long long))) return ICPB200_ERR_CUDA;
     a.queue = c.queue.as<unsigned>();
     // two-phase schedule (see icp_kernel.h): worthwhile once the batch fills the machine
-    const int kPhaseCap = 12;
+    static const int kPhaseCap = getenv("ICPB200_PHASE_CAP") ? std::max(2, atoi(getenv("ICPB200_PHASE_CAP"))) : 12;
     const bool two_phase = n_pairs >= 2 * c.sm_count && k.max_iterations > 2 * kPhaseCap;
     a.phase_cap = two_phase ? kPhaseCap : 0;
     a.resume = 0;

@@ -6,6 +6,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace icpb {
 
 constexpr int kNT = 256;               // threads per CTA
@@ -108,6 +110,75 @@ __device__ __forceinline__ void bitonic_sort_pairs(unsigned long long* keys, uns
     }
 }
 
+// Register/shuffle bitonic sort for n_pad = kNT * E elements in a blocked layout (thread t holds
+// elements t*E .. t*E+E-1): compare-exchange distances below E stay in registers, distances
+// below 32*E go through warp shuffles, only the larger ones through shared memory (6 of the 66
+// passes for 2048 elements).  Same order as bitonic_sort_pairs: ascending (key, idx).
+template <int E>
+__device__ __forceinline__ void bitonic_sort_blocked(unsigned long long (&key)[E], unsigned int (&idx)[E],
+                                                     unsigned long long* skeys, unsigned int* sidx) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    constexpr int n_pad = kNT * E;
+    auto greater = [](unsigned long long ka, unsigned ia, unsigned long long kb, unsigned ib) {
+        return ka > kb || (ka == kb && ia > ib);
+    };
+    for (int k = 2; k <= n_pad; k <<= 1) {
+        for (int j = k >> 1; j >= E; j >>= 1) {
+            if (false) {
+            } else if (j < 32 * E) {                       // partner lane in this warp
+                const int lj = j / E;
+                const bool lower = (lane & lj) == 0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key[e], lj);
+                    const unsigned oi = __shfl_xor_sync(0xffffffffu, idx[e], lj);
+                    const bool asc = (((tid * E + e) & k) == 0);
+                    // the lower element of the pair keeps the minimum when ascending
+                    const bool mine_greater = greater(key[e], idx[e], ok, oi);
+                    const bool take = (lower == asc) ? mine_greater : !mine_greater;
+                    if (take) { key[e] = ok; idx[e] = oi; }
+                }
+            } else {                                       // partner in another warp: through shared memory
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < E; ++e) { skeys[tid * E + e] = key[e]; sidx[tid * E + e] = idx[e]; }
+                __syncthreads();
+                const int pt = tid ^ (j / E);
+                const bool lower = (tid & (j / E)) == 0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const unsigned long long ok = skeys[pt * E + e];
+                    const unsigned oi = sidx[pt * E + e];
+                    const bool asc = (((tid * E + e) & k) == 0);
+                    const bool mine_greater = greater(key[e], idx[e], ok, oi);
+                    const bool take = (lower == asc) ? mine_greater : !mine_greater;
+                    if (take) { key[e] = ok; idx[e] = oi; }
+                }
+            }
+        }
+        // distances below E: partner in this thread's registers (all indices compile-time)
+#pragma unroll
+        for (int jj = E / 2; jj > 0; jj >>= 1) {
+            if (jj >= k) continue;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int pe = e ^ jj;
+                if (pe > e) {
+                    const bool asc = (((tid * E + e) & k) == 0);
+                    if (greater(key[e], idx[e], key[pe], idx[pe]) == asc) {
+                        const unsigned long long tk = key[e]; key[e] = key[pe]; key[pe] = tk;
+                        const unsigned ti = idx[e]; idx[e] = idx[pe]; idx[pe] = ti;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < E; ++e) { skeys[tid * E + e] = key[e]; sidx[tid * E + e] = idx[e]; }
+    __syncthreads();
+}
+
 // Voxel-grid mean of one cloud, executed by the whole CTA.
 //   raw : n rows of DIM float64 (global)        out : rows of DIM float64 (global)
 //   keys/idx : shared scratch for n_pad entries (n_pad = power of two >= n, >= kNT)
@@ -147,9 +218,8 @@ __device__ int cta_voxel_means(const double* __restrict__ raw, int n, double vox
     }
     if (!(span < 4.0e18)) return -1;
 
-    for (int i = threadIdx.x; i < n_pad; i += kNT) {
-        unsigned long long key = ~0ull;
-        unsigned int id = ~0u;
+    auto make_key = [&](int i, unsigned long long& key, unsigned int& id) {
+        key = ~0ull; id = ~0u;
         if (i < n) {
             key = 0ull;
 #pragma unroll
@@ -159,11 +229,25 @@ __device__ int cta_voxel_means(const double* __restrict__ raw, int n, double vox
             }
             id = (unsigned int)i;
         }
-        keys[i] = key;
-        idx[i] = id;
+    };
+    auto sort_blocked = [&](auto e_tag) {
+        constexpr int E = decltype(e_tag)::value;
+        unsigned long long k[E];
+        unsigned int id[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) make_key(threadIdx.x * E + e, k[e], id[e]);
+        bitonic_sort_blocked<E>(k, id, keys, idx);
+    };
+    switch (n_pad / kNT) {
+        case 1: sort_blocked(std::integral_constant<int, 1>{}); break;
+        case 2: sort_blocked(std::integral_constant<int, 2>{}); break;
+        case 4: sort_blocked(std::integral_constant<int, 4>{}); break;
+        case 8: sort_blocked(std::integral_constant<int, 8>{}); break;
+        default:
+            for (int i = threadIdx.x; i < n_pad; i += kNT) make_key(i, keys[i], idx[i]);
+            __syncthreads();
+            bitonic_sort_pairs(keys, idx, n_pad);
     }
-    __syncthreads();
-    bitonic_sort_pairs(keys, idx, n_pad);
 
     // run heads -> output rows
     const int chunk = n_pad / kNT;
