@@ -179,6 +179,53 @@ __device__ __forceinline__ void bitonic_sort_blocked(unsigned long long (&key)[E
     __syncthreads();
 }
 
+// The same network on single 32-bit words (cell key and input index packed into one word, see
+// cta_voxel_means): a compare-exchange is one min and one max.
+template <int E>
+__device__ __forceinline__ void bitonic_sort_blocked_u32(unsigned int (&key)[E], unsigned int* skeys) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    constexpr int n_pad = kNT * E;
+    for (int k = 2; k <= n_pad; k <<= 1) {
+        for (int j = k >> 1; j >= E; j >>= 1) {
+            const int tj = j / E;
+            const bool keep_min = (((tid & tj) == 0) == (((tid * E) & k) == 0));    // k >= 2E here: the direction is per thread
+            if (j < 32 * E) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const unsigned o = __shfl_xor_sync(0xffffffffu, key[e], tj);
+                    key[e] = keep_min ? min(key[e], o) : max(key[e], o);
+                }
+            } else {
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < E; ++e) skeys[e * kNT + tid] = key[e];             // [e][tid]: conflict-free
+                __syncthreads();
+                const int pt = tid ^ tj;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const unsigned o = skeys[e * kNT + pt];
+                    key[e] = keep_min ? min(key[e], o) : max(key[e], o);
+                }
+            }
+        }
+#pragma unroll
+        for (int jj = E / 2; jj > 0; jj >>= 1) {
+            if (jj >= k) continue;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int pe = e ^ jj;
+                if (pe > e) {
+                    const bool asc = (((tid * E + e) & k) == 0);
+                    const unsigned lo_ = min(key[e], key[pe]), hi_ = max(key[e], key[pe]);
+                    key[e] = asc ? lo_ : hi_;
+                    key[pe] = asc ? hi_ : lo_;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
 // Voxel-grid mean of one cloud, executed by the whole CTA.
 //   raw : n rows of DIM float64 (global)        out : rows of DIM float64 (global)
 //   keys/idx : shared scratch for n_pad entries (n_pad = power of two >= n, >= kNT)
@@ -238,7 +285,38 @@ __device__ int cta_voxel_means(const double* __restrict__ raw, int n, double vox
         for (int e = 0; e < E; ++e) make_key(threadIdx.x * E + e, k[e], id[e]);
         bitonic_sort_blocked<E>(k, id, keys, idx);
     };
-    switch (n_pad / kNT) {
+    // Cell key and input index fit one 32-bit word together (always for lidar scans: ~600k cells x 2048
+    // points): sort plain words.  Padding sorts last (all ones) in both forms.
+    int idx_bits = 0;
+    while ((1 << idx_bits) < n_pad) ++idx_bits;
+    const bool pack32 = span * (double)n_pad < 4.0e9 && n_pad <= 8 * kNT;
+    auto sort_packed = [&](auto e_tag) {
+        constexpr int E = decltype(e_tag)::value;
+        unsigned int k[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            unsigned long long key;
+            unsigned int id;
+            make_key(threadIdx.x * E + e, key, id);
+            k[e] = id == ~0u ? ~0u : (unsigned int)((key << idx_bits) | id);
+        }
+        bitonic_sort_blocked_u32<E>(k, idx);               // idx[] doubles as the exchange buffer
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const bool pad = k[e] == ~0u;
+            keys[threadIdx.x * E + e] = pad ? ~0ull : (unsigned long long)(k[e] >> idx_bits);
+        }
+        __syncthreads();                                   // idx[] is free again
+#pragma unroll
+        for (int e = 0; e < E; ++e) idx[threadIdx.x * E + e] = k[e] == ~0u ? ~0u : (k[e] & ((1u << idx_bits) - 1u));
+        __syncthreads();
+    };
+    const int epl = n_pad / kNT;
+    if (pack32 && epl == 1) sort_packed(std::integral_constant<int, 1>{});
+    else if (pack32 && epl == 2) sort_packed(std::integral_constant<int, 2>{});
+    else if (pack32 && epl == 4) sort_packed(std::integral_constant<int, 4>{});
+    else if (pack32 && epl == 8) sort_packed(std::integral_constant<int, 8>{});
+    else switch (epl) {
         case 1: sort_blocked(std::integral_constant<int, 1>{}); break;
         case 2: sort_blocked(std::integral_constant<int, 2>{}); break;
         case 4: sort_blocked(std::integral_constant<int, 4>{}); break;
