@@ -376,16 +376,19 @@ __device__ __forceinline__ void pca_normal_masked(const double* tx, const double
     sym2_min_eigvec(sxx, sxy, syy, out2);
 }
 
-__device__ void cta_normals_sweep(const double* tx, const double* ty, int n, int K, double* __restrict__ normals_out,
+template <int KT>
+__device__ void cta_normals_sweep(const double* tx, const double* ty, int n, int K_rt, double* __restrict__ normals_out,
                                   float2* pf, float* pmax, float* smin, unsigned short* redo, CtaShared& sh) {
     __shared__ float wtot[2][kNW];
+    __shared__ int next_block;                              // query blocks are handed out dynamically
+    const int K = KT > 0 ? KT : K_rt;                       // compile-time for the usual neighbourhood sizes
     const unsigned full = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double cx = 0.5 * (sh.lo_t[0] + sh.hi_t[0]), cy = 0.5 * (sh.lo_t[1] + sh.hi_t[1]);
     const double half = 0.5 * fmax(sh.hi_t[0] - sh.lo_t[0], sh.hi_t[1] - sh.lo_t[1]);
     for (int j = tid; j < n; j += kNT)
         pf[j] = make_float2((float)(tx[pad_index(j)] - cx), (float)(ty[pad_index(j)] - cy));
-    if (tid == 0) sh.bcast_i[1] = 0;
+    if (tid == 0) { sh.bcast_i[1] = 0; next_block = kNW; }
     __syncthreads();
     {   // prefix maximum / suffix minimum of the fp32 x coordinate
         const int per = (n + kNT - 1) / kNT;
@@ -415,7 +418,8 @@ __device__ void cta_normals_sweep(const double* tx, const double* ty, int n, int
 
     const unsigned idx_mask = n <= 1024 ? 0x3ffu : 0xfffu;
     const double eps_abs = 2.5e-7 * half;                   // |fp32-world distance - true distance|
-    for (int base = warp * 32; base < n; base += kNT) {
+    for (int blk = warp; blk * 32 < n; blk = __shfl_sync(full, lane == 0 ? atomicAdd(&next_block, 1) : 0, 0)) {
+        const int base = blk * 32;
         const int i = min(base + lane, n - 1);
         const bool valid = base + lane < n;
         const float2 q = pf[i];
@@ -683,7 +687,10 @@ __global__ void __launch_bounds__(kNT, 4) normals_sweep_kernel(const CloudSet cs
         for (int k = 0; k < 3; ++k) { sh.lo_t[k] = cs.box[(size_t)c * 6 + k]; sh.hi_t[k] = cs.box[(size_t)c * 6 + 3 + k]; }
     }
     __syncthreads();
-    cta_normals_sweep(tx, ty, n, min(normal_k, n - 1) + 1, cs.nrm + beg * 2, pf, pmax, smin, redo, sh);
+    const int K = min(normal_k, n - 1) + 1;
+    if (K == 13) cta_normals_sweep<13>(tx, ty, n, K, cs.nrm + beg * 2, pf, pmax, smin, redo, sh);          // normal_k = 12 (config.yaml)
+    else if (K == 11) cta_normals_sweep<11>(tx, ty, n, K, cs.nrm + beg * 2, pf, pmax, smin, redo, sh);     // normal_k = 10 (ICP default)
+    else cta_normals_sweep<0>(tx, ty, n, K, cs.nrm + beg * 2, pf, pmax, smin, redo, sh);
 }
 
 // ---- K3: fp32 sweep --------------------------------------------------------------
