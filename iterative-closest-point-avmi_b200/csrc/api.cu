@@ -214,6 +214,8 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
     static const int kPhaseCap = getenv("ICPB200_PHASE_CAP") ? std::max(2, atoi(getenv("ICPB200_PHASE_CAP"))) : 12;
     const bool two_phase = n_pairs >= 2 * c.sm_count && k.max_iterations > 2 * kPhaseCap;
     a.phase_cap = two_phase ? kPhaseCap : 0;
+    static const bool no_slab = getenv("ICPB200_NO_SLAB") != nullptr;      // A/B switch: tile sweep for every decision
+    a.brute_slab = (!grid && k.voxel_size > 0.0 && !no_slab) ? 1 : 0;
     a.resume = 0;
     if (two_phase) {
         const size_t np_ = (size_t)n_pairs, cs_ = (size_t)a.cap_s;

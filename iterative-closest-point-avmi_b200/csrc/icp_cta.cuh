@@ -28,6 +28,7 @@ struct CtaShared {
     int grid_nx, grid_ny;
     int n_s, n_t;
     int amb_n;
+    unsigned int slab_evals;           // fp32 evaluations of the slab sweeps of this iteration (statistics)
     // split-sweep partials (K3): [warp][lane]
     float part_b1[kNW][32], part_b2[kNW][32], part_b3[kNW][32];
     int part_bt[kNW][32], part_bt2[kNW][32];

@@ -974,12 +974,106 @@ __device__ __forceinline__ void nn_split(const Loop<DIM>& L, CtaShared& sh, int 
     }
 }
 
+// Bulk sweeps (many points to decide): K1 emits every cloud ordered by voxel column, so both the
+// target and the todo list (ascending source index) are sorted by x up to one voxel.  A warp takes
+// 32 consecutive todo points and walks the target outwards from their position, down and up in
+// turns; all lanes evaluate the SAME candidate (one broadcast load), tracking their three best in
+// fp32.  A direction stops once the x-gap to the unvisited part (whose x is bounded through the
+// voxel-column order) exceeds every lane's third-best distance.  The decision is nn_split's: the two
+// front runners are compared in fp64, everything else -- visited or not -- is bounded by
+// min(third best, gaps) minus the fp32 slack; otherwise the full fp64 scan decides.  On C2 a chunk
+// visits ~60 of the 800 targets instead of all of them, and the 32-target fp64 re-evaluation of
+// the tile sweep is gone.
 template <int DIM>
-__device__ __forceinline__ void nn_dispatch(const Loop<DIM>& L, CtaShared& sh, int n_todo) {
+__device__ __forceinline__ void nn_slab(const Loop<DIM>& L, CtaShared& sh, int n_todo, float vox) {
+    const unsigned full = 0xffffffffu;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_chunks = (n_todo + 31) >> 5;
+    const float* tf = reinterpret_cast<const float*>(L.t32);
+    constexpr int kStride = DIM == 2 ? 2 : 4;                 // floats per target in t32
+    for (int chunk = w; chunk < n_chunks; chunk += kNW) {
+        const int q = chunk * 32 + lane;
+        const int pt = q < n_todo ? (int)L.todo[q] : -1;
+        const int i = pt >= 0 ? pt : (int)L.todo[chunk * 32];   // idle lanes shadow the chunk's first point
+        const float sx = (float)(L.cx[i] - L.c0), sy = (float)(L.cy[i] - L.c1);
+        const float sz = DIM == 3 ? (float)(L.cz[i] - L.c2) : 0.f;
+        float b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
+        int bj = 0, bj2 = -1;
+        auto offer = [&](int j) {
+            const float dx = sx - tf[j * kStride], dy = sy - tf[j * kStride + 1];
+            float d = fmaf(dy, dy, dx * dx);
+            if (DIM == 3) { const float dz = sz - tf[j * kStride + 2]; d = fmaf(dz, dz, d); }
+            const bool lt1 = d < b1, lt2 = d < b2;
+            b3 = lt2 ? b2 : fminf(b3, d);
+            b2 = lt1 ? b1 : (lt2 ? d : b2);
+            bj2 = lt1 ? bj : (lt2 ? j : bj2);
+            b1 = lt1 ? d : b1;
+            bj = lt1 ? j : bj;
+        };
+        // start where lane 0's point would be inserted (any start is correct, this one is short)
+        const float x0 = __shfl_sync(full, sx, 0);
+        int lo = 0, hi = L.n_t;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (tf[mid * kStride] < x0) lo = mid + 1; else hi = mid;
+        }
+        int dn = lo - 1, up = lo;
+        bool ddone = dn < 0, udone = up >= L.n_t;
+        float gdn = INFINITY, gup = INFINITY;                 // x-gap to the unvisited part, per lane
+        while (!ddone || !udone) {
+            if (!ddone) {
+                const int stop = max(dn - 7, 0);
+                for (int j = dn; j >= stop; --j) offer(j);
+                dn = stop - 1;
+                if (dn < 0) ddone = true;
+                else {
+                    const float g = sx - (tf[dn * kStride] + vox);      // every j' <= dn has x < x[dn] + voxel
+                    if (__all_sync(full, g > 0.f && g * g > b3 * 1.0001f)) { ddone = true; gdn = g; }
+                }
+            }
+            if (!udone) {
+                const int stop = min(up + 7, L.n_t - 1);
+                for (int j = up; j <= stop; ++j) offer(j);
+                up = stop + 1;
+                if (up >= L.n_t) udone = true;
+                else {
+                    const float g = (tf[up * kStride] - vox) - sx;      // every j' >= up has x > x[up] - voxel
+                    if (__all_sync(full, g > 0.f && g * g > b3 * 1.0001f)) { udone = true; gup = g; }
+                }
+            }
+        }
+        if (lane == 0) atomicAdd(&sh.slab_evals, (unsigned)((lo - 1 - dn) + (up - lo)) * 32u);      // statistics only
+        if (pt < 0) continue;
+        const bool two = bj2 >= 0 && bj2 != bj;
+        const double px = L.cx[pt], py = L.cy[pt], pz = DIM == 3 ? L.cz[pt] : 0.0;
+        double e1 = dist2_64<DIM>(L, px, py, pz, bj);
+        int j1 = bj, j2 = -1;
+        if (two) {
+            const double e2 = dist2_64<DIM>(L, px, py, pz, bj2);
+            j2 = bj2;
+            if (e2 < e1 || (e2 == e1 && bj2 < bj)) { j1 = bj2; j2 = bj; e1 = e2; }
+        }
+        const double d1 = sqrt(e1);
+        const float mag = fabsf(sx) + fabsf(sy) + (DIM == 3 ? fabsf(sz) : 0.f) + L.ta + vox;
+        const double rest = fmin(sqrt((double)(two ? b3 : b2)) * (1.0 - 1.0e-6), (double)fminf(gdn, gup) * (1.0 - 1.0e-6));
+        const double other = rest - 1.8e-7 * (double)mag;
+        if (!(other > d1)) {
+            L.amb[atomicAdd(&sh.amb_n, 1)] = (unsigned short)pt;
+        } else {
+            L.match[pt] = m_pack(j1, j2);
+            L.d2lb[pt] = f32_down(other);
+            stamp_p0<DIM>(L, pt);
+        }
+    }
+}
+
+template <int DIM>
+__device__ __forceinline__ void nn_dispatch(const Loop<DIM>& L, CtaShared& sh, int n_todo, float vox) {
     const int w = threadIdx.x >> 5;
     const int n_chunks = (n_todo + 31) >> 5;
     const int F = n_chunks > 0 ? kNW / n_chunks : 1;
     if (F >= 2) { nn_split<DIM>(L, sh, n_todo, n_chunks, F); return; }
+    if (vox > 0.f) { nn_slab<DIM>(L, sh, n_todo, vox); return; }
     for (int base = 0; base < n_chunks; base += kSMax * kNW) {
         const int first = base + w;
         const int mine = first < n_chunks ? min(kSMax, (n_chunks - first + kNW - 1) / kNW) : 0;   // warp-uniform
@@ -1176,6 +1270,7 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
                 sh.r_tot[k] = init ? a.R_init[(size_t)p * DIM * DIM + k] : ((k % (DIM + 1) == 0) ? 1.0 : 0.0);
             for (int k = 0; k < DIM; ++k) sh.t_tot[k] = init ? a.t_init[(size_t)p * DIM + k] : 0.0;
             sh.amb_n = 0;
+            sh.slab_evals = 0u;
             sh.bcast_i[0] = 0;                     // todo counter
         }
         // ---- stage the target: fp64 (tile-padded SoA) and recentred fp32
@@ -1265,6 +1360,8 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
         const int min_inl = max(3, n_s / 10);                         // icp.py:186
         int status = ICPB200_MAX_ITER;
         bool handed_over = false;
+        // clouds come out of K1 ordered by voxel column: x is sorted up to one voxel (plus fp32 rounding)
+        const float slab_vox = a.brute_slab ? __double2float_ru(a.voxel * 1.000001) + 1e-6f * L.ta : 0.f;
         for (int it = iters; it < a.max_iter; ++it) {
             if (!a.resume && a.phase_cap > 0 && it == a.phase_cap) {
                 // not converged within the bulk budget: park the state, a dedicated launch finishes it
@@ -1324,14 +1421,19 @@ __global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
                 if (GRID) {
                     grid_nn<DIM>(L, n_todo);
                 } else {
-                    nn_dispatch<DIM>(L, sh, n_todo);
+                    nn_dispatch<DIM>(L, sh, n_todo, slab_vox);
                     __syncthreads();
                     if (sh.amb_n > 0) resolve_ambiguous<DIM>(L, sh);
                 }
             }
             if (tid == 0) {
                 const int n_chunks = (n_todo + 31) >> 5;
-                if (!GRID) st_evals += (unsigned long long)n_chunks * 32ull * (unsigned long long)L.n_tiles * 32ull;
+                if (!GRID) {
+                    const bool slab = slab_vox > 0.f && n_chunks > kNW / 2;      // nn_dispatch's choice
+                    st_evals += slab ? (unsigned long long)sh.slab_evals
+                                     : (unsigned long long)n_chunks * 32ull * (unsigned long long)L.n_tiles * 32ull;
+                    sh.slab_evals = 0u;
+                }
                 st_swept += n_todo; st_kept += n_s - n_todo; st_iters += 1;
             }
             __syncthreads();

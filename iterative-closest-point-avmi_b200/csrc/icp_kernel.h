@@ -54,6 +54,7 @@ struct IcpArgs {
     double err_thr;
     int max_iter;
     double voxel;
+    int brute_slab;            // brute mode: sweep the voxel-ordered target outwards from the query (nn_slab)
     int method;
     int normal_k;
     double max_corr;           // < 0: no gate
