@@ -18,6 +18,7 @@ constexpr int kRedMax = 12;            // widest block reduction (values)
 // kernel that uses these helpers.
 struct CtaShared {
     double red[2][kNW][kRedMax];       // double-buffered warp partials
+    double red_tot[2][kRedMax];        // ... and block totals
     int scan_tot[kNW + 1];
     int bcast_i[4];
     unsigned int pair;
@@ -34,33 +35,66 @@ struct CtaShared {
     int part_bt[kNW][32], part_bt2[kNW][32];
 };
 
-struct SumOp { __device__ static double f(double a, double b) { return a + b; } };
-struct MinOp { __device__ static double f(double a, double b) { return fmin(a, b); } };
+struct SumOp {
+    __device__ static double f(double a, double b) { return a + b; }
+    __device__ static double id() { return 0.0; }
+};
+struct MinOp {
+    __device__ static double f(double a, double b) { return fmin(a, b); }
+    __device__ static double id() { return INFINITY; }
+};
 
-// All-threads block reduction of NV doubles.  Fixed butterfly + fixed warp
-// order => bitwise deterministic, and every thread returns the same value.
-// `phase` alternates the scratch buffer so one barrier per reduction suffices.
+// All-threads block reduction of NV doubles.  Fixed tree + fixed warp order => bitwise
+// deterministic, and every thread returns the same values.
+//   warp    recursive halving: at each of the first log2(NVP) shuffle distances a lane hands half of
+//           its values to its partner and keeps the other half (which half is the lane's bit), so
+//           NVP values cost NVP - 1 shuffles per lane instead of 5 * NVP; the remaining distances
+//           are a plain butterfly.  Lane bits then spell the index of the one value a lane holds.
+//   block   threads 0 .. NV-1 each add one value over the warps (in warp order), everybody reads
+//           the NV totals back: NV + kNW shared loads per thread instead of NV * kNW.
+// `phase` alternates the scratch buffer so a reduction may start while another is still read.
 template <int NV, class Op>
 __device__ __forceinline__ void block_reduce(double (&v)[NV], CtaShared& sh, int& phase) {
     static_assert(NV <= kRedMax, "reduction too wide");
-#pragma unroll
-    for (int k = 0; k < NV; ++k)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v[k] = Op::f(v[k], __shfl_xor_sync(0xffffffffu, v[k], o));
+    constexpr int NVP = NV <= 1 ? 1 : NV <= 2 ? 2 : NV <= 4 ? 4 : NV <= 8 ? 8 : 16;
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    double(*buf)[kRedMax] = sh.red[phase & 1];
-    if (l == 0) {
+    double x[NVP];
 #pragma unroll
-        for (int k = 0; k < NV; ++k) buf[w][k] = v[k];
+    for (int k = 0; k < NVP; ++k) x[k] = k < NV ? v[k] : Op::id();
+    int held = 0;                                  // index of x[0] once the halving is over
+    int c = NVP;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        if (c > 1) {
+            const bool upper = (l & o) != 0;
+            const int h = c / 2;
+#pragma unroll
+            for (int k = 0; k < NVP / 2; ++k) {
+                if (k < h) {
+                    const double send = upper ? x[k] : x[k + h];
+                    const double keep = upper ? x[k + h] : x[k];
+                    x[k] = Op::f(keep, __shfl_xor_sync(0xffffffffu, send, o));
+                }
+            }
+            held += upper ? h : 0;
+            c = h;
+        } else {
+            x[0] = Op::f(x[0], __shfl_xor_sync(0xffffffffu, x[0], o));
+        }
+    }
+    double(*buf)[kRedMax] = sh.red[phase & 1];
+    constexpr int kDup = 32 / NVP;                 // lanes that hold the same value after the butterfly tail
+    if ((l & (kDup - 1)) == 0 && held < NV) buf[w][held] = x[0];
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = buf[0][threadIdx.x];
+#pragma unroll
+        for (int ww = 1; ww < kNW; ++ww) s = Op::f(s, buf[ww][threadIdx.x]);
+        sh.red_tot[phase & 1][threadIdx.x] = s;
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        double s = buf[0][k];
-#pragma unroll
-        for (int ww = 1; ww < kNW; ++ww) s = Op::f(s, buf[ww][k]);
-        v[k] = s;
-    }
+    for (int k = 0; k < NV; ++k) v[k] = sh.red_tot[phase & 1][k];
     ++phase;
 }
 
