@@ -337,19 +337,24 @@ def run_ours(args, rank, world, local_rank):
     clk_mhz = clocks["sm_mhz"] or pk["sm_max_mhz"]
     sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
     peak_evals = sm_count * FMA_LANES_PER_SM * clk_mhz * 1e6 / FMA_INSTR_PER_PAIR_EVAL_2D
-    achieved_tf = exe_evals * FLOP_PER_PAIR_EVAL_2D / kernel_s / 1e12
+    # The contract's `achieved` is ALGORITHMIC work / kernel time (brute-force pair evaluations x 5 flop).
+    # The kernel does not execute that work -- carried-over correspondences are not searched again and the
+    # voxel-ordered slab sweep visits ~150 of the ~800 targets -- so the figure may exceed the FMA-pipe ceiling;
+    # what the kernel really issued is reported next to it (executed_*).
+    achieved_tf = alg_evals * FLOP_PER_PAIR_EVAL_2D / kernel_s / 1e12
+    executed_tf = exe_evals * FLOP_PER_PAIR_EVAL_2D / kernel_s / 1e12
     peak_tf = peak_evals * FLOP_PER_PAIR_EVAL_2D / 1e12
     roofline = dict(bound="fp32_fma", achieved=achieved_tf, peak=peak_tf, unit="TFLOP/s", frac=achieved_tf / peak_tf,
                     traffic=None, kernel="icp_pairs_kernel<2>", kernel_ms=kernel_s * 1e3,
                     kernel_share_of_step=kernel_s * 1e3 / float(np.mean(ms_steps)),
                     voxel_kernel_ms=kstats["voxel_kernel_ns"] / 1e6, normals_kernel_ms=kstats["normals_kernel_ns"] / 1e6,
-                    executed_pair_evals_per_launch=exe_evals, algorithmic_pair_evals_per_launch=alg_evals,
-                    algorithmic_equivalent_frac=alg_evals / kernel_s / peak_evals,
+                    algorithmic_pair_evals_per_launch=alg_evals, executed_pair_evals_per_launch=exe_evals,
+                    executed_tflops=executed_tf, executed_frac=executed_tf / peak_tf,
                     points_swept=kstats["points_swept"], points_carried=kstats["points_carried"],
                     fp64_rescans=kstats["fp64_rescans"],
-                    note="achieved counts the fp32 sweep evaluations actually executed; correspondences carried over "
-                         "by the exact movement bound are not swept, so the brute-force count of BASELINE.md section 4 "
-                         "is reported separately as algorithmic_*",
+                    note="achieved = algorithmic (brute-force) pair evaluations of BASELINE.md section 4 x 5 flop / kernel "
+                         "time; the kernel reaches the same exact nearest neighbours with far fewer evaluations "
+                         "(executed_*): it is bound by the latency of its per-iteration phases, not by the FMA pipe",
                     peak_basis=f"{sm_count} SMs x {FMA_LANES_PER_SM} FP32 lanes x {clk_mhz:.0f} MHz (median SM clock "
                                f"sampled during the timed region) / {FMA_INSTR_PER_PAIR_EVAL_2D} FMA-pipe instr per 2-D "
                                f"pair evaluation x {FLOP_PER_PAIR_EVAL_2D} flop (BASELINE.md section 4)")
