@@ -85,6 +85,13 @@ static int init_locked(int device) {
     c.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     ICPB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) ICPB_CUDA(cudaEventCreate(&c.ev[i]));
+    ICPB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < kUploadChunks; ++i) {
+        ICPB_CUDA(cudaEventCreateWithFlags(&c.chunk_ev[i], cudaEventDisableTiming));
+        ICPB_CUDA(cudaEventCreateWithFlags(&c.chunk_done[i], cudaEventDisableTiming));
+        ICPB_CUDA(cudaStreamCreateWithFlags(&c.chunk_stream[i], cudaStreamNonBlocking));
+    }
+    ICPB_CUDA(cudaEventCreateWithFlags(&c.fork_ev, cudaEventDisableTiming));
     c.ready = true;
     return ICPB200_OK;
 }
@@ -153,6 +160,13 @@ static int make_cloud_set(Context& c, int slot, const DevClouds& d, int dim, boo
 
 // voxel-grid means of a whole set: shared-memory kernel for scan-sized clouds,
 // global-memory radix-sort kernel when any cloud of the set exceeds one CTA
+// The host-buffer entry point uploads the clouds in a few chunks on a second stream; K1 (and K2) of a chunk start as
+// soon as that chunk has arrived, under the copy of the next one.
+struct UploadPlan {
+    int n_chunks;
+    int first[kUploadChunks + 1];              // cloud ranges
+};
+
 static int voxel_set(Context& c, const CloudSet& cs, const DevClouds& d, int dim, double voxel, cudaStream_t st) {
     if (d.set_max <= ICPB200_BRUTE_MAX_POINTS)
         return launch_voxel_clouds(cs, dim, voxel, next_pow2((int)std::max<long long>(d.set_max, 256)), st);
@@ -169,7 +183,7 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
                        const int* d_src_idx, const int* d_tgt_idx,
                        const double* d_R_init, const double* d_t_init, double* d_R, double* d_t,
                        double* d_err, double* d_prev, int* d_iters, int* d_status, cudaStream_t st,
-                       const IcpTrace& tr, IcpArgs* args_out) {
+                       const IcpTrace& tr, IcpArgs* args_out, const UploadPlan* plan = nullptr) {
     Context& c = g_ctx;
     if (n_pairs == 0) return ICPB200_OK;
     const bool grid = k.nn_mode == ICPB200_NN_GRID ||
@@ -240,48 +254,70 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
     a.grids = nullptr;
     if ((rc = launch_mark_used(a, p2l || grid, st))) return rc;
     ICPB_CUDA(cudaEventRecord(c.ev[0], st));
-    if ((rc = voxel_set(c, a.s, s, k.dim, k.voxel_size, st))) return rc;
-    if (!same_set && (rc = voxel_set(c, a.t, t, k.dim, k.voxel_size, st))) return rc;
-    ICPB_CUDA(cudaEventRecord(c.ev[1], st));
-    if (grid) {
-        // one hash grid per target cloud; bucket counts from the raw sizes (host side)
-        std::vector<int64_t> fetched;
-        const int64_t* h_off = t.h_off;
-        if (!h_off) {
-            fetched.resize((size_t)t.n_clouds + 1);
-            ICPB_CUDA(cudaMemcpyAsync(fetched.data(), t.off, sizeof(int64_t) * fetched.size(), cudaMemcpyDeviceToHost, st));
-            ICPB_CUDA(cudaStreamSynchronize(st));
-            h_off = fetched.data();
+    const bool chunked = plan && same_set && !grid && s.set_max <= ICPB200_BRUTE_MAX_POINTS;
+    if (plan && !chunked)
+        for (int ch = 0; ch < plan->n_chunks; ++ch) ICPB_CUDA(cudaStreamWaitEvent(st, c.chunk_ev[ch], 0));
+    if (chunked) {
+        // K1 (and K2) of an upload chunk run under the copy of the next chunk
+        const int sort_pad = next_pow2((int)std::max<long long>(s.set_max, 256));
+        // each chunk's kernels go to their own stream: a quarter of the clouds does not fill the GPU, so the
+        // chunks' kernels must be able to run side by side (and under the copies still in flight)
+        ICPB_CUDA(cudaEventRecord(c.fork_ev, st));                 // flags from mark_used
+        for (int ch = 0; ch < plan->n_chunks; ++ch) {
+            const int first = plan->first[ch], count = plan->first[ch + 1] - first;
+            cudaStream_t cs_ = c.chunk_stream[ch];
+            ICPB_CUDA(cudaStreamWaitEvent(cs_, c.fork_ev, 0));
+            ICPB_CUDA(cudaStreamWaitEvent(cs_, c.chunk_ev[ch], 0));
+            if ((rc = launch_voxel_clouds(a.s, k.dim, k.voxel_size, sort_pad, cs_, first, count))) return rc;
+            if (p2l && (rc = launch_normals(a.t, a.cap_t, k.normal_k, k.voxel_size, cs_, first, count))) return rc;
+            ICPB_CUDA(cudaEventRecord(c.chunk_done[ch], cs_));
+            ICPB_CUDA(cudaStreamWaitEvent(st, c.chunk_done[ch], 0));
         }
-        std::vector<long long> goff((size_t)t.n_clouds);
-        std::vector<int> gbuckets((size_t)t.n_clouds);
-        long long total_start = 0;
-        for (int i = 0; i < t.n_clouds; ++i) {
-            const long long n = h_off[i + 1] - h_off[i];
-            int b = 1024;
-            while (b < 2 * n && b < (1 << 24)) b <<= 1;
-            gbuckets[i] = b;
-            goff[i] = total_start;
-            total_start += b + 1;
+        ICPB_CUDA(cudaEventRecord(c.ev[1], st));
+    } else {
+        if ((rc = voxel_set(c, a.s, s, k.dim, k.voxel_size, st))) return rc;
+        if (!same_set && (rc = voxel_set(c, a.t, t, k.dim, k.voxel_size, st))) return rc;
+        ICPB_CUDA(cudaEventRecord(c.ev[1], st));
+        if (grid) {
+            // one hash grid per target cloud; bucket counts from the raw sizes (host side)
+            std::vector<int64_t> fetched;
+            const int64_t* h_off = t.h_off;
+            if (!h_off) {
+                fetched.resize((size_t)t.n_clouds + 1);
+                ICPB_CUDA(cudaMemcpyAsync(fetched.data(), t.off, sizeof(int64_t) * fetched.size(), cudaMemcpyDeviceToHost, st));
+                ICPB_CUDA(cudaStreamSynchronize(st));
+                h_off = fetched.data();
+            }
+            std::vector<long long> goff((size_t)t.n_clouds);
+            std::vector<int> gbuckets((size_t)t.n_clouds);
+            long long total_start = 0;
+            for (int i = 0; i < t.n_clouds; ++i) {
+                const long long n = h_off[i + 1] - h_off[i];
+                int b = 1024;
+                while (b < 2 * n && b < (1 << 24)) b <<= 1;
+                gbuckets[i] = b;
+                goff[i] = total_start;
+                total_start += b + 1;
+            }
+            const size_t np = (size_t)t.total_points, nc = (size_t)t.n_clouds;
+            if (c.grid_start.reserve(sizeof(int) * (size_t)total_start) || c.grid_items.reserve(sizeof(int) * np) ||
+                c.grid_cell.reserve(sizeof(int2) * np) || c.grid_desc.reserve(sizeof(BigGrid) * nc) ||
+                c.grid_off.reserve(sizeof(long long) * nc) || c.grid_buckets.reserve(sizeof(int) * nc))
+                return ICPB200_ERR_CUDA;
+            ICPB_CUDA(cudaMemcpyAsync(c.grid_off.p, goff.data(), sizeof(long long) * nc, cudaMemcpyHostToDevice, st));
+            ICPB_CUDA(cudaMemcpyAsync(c.grid_buckets.p, gbuckets.data(), sizeof(int) * nc, cudaMemcpyHostToDevice, st));
+            ICPB_CUDA(cudaStreamSynchronize(st));          // goff / gbuckets are stack-owned
+            ICPB_CUDA(cudaMemsetAsync(c.grid_desc.p, 0, sizeof(BigGrid) * nc, st));
+            // cell edge: 8 voxels (a 3x3 block of cells holds a few dozen wall points)
+            if ((rc = launch_big_grid(a.t, 8.0 * k.voxel_size, c.grid_off.as<long long>(), c.grid_buckets.as<int>(),
+                                      c.grid_start.as<int>(), c.grid_items.as<int>(), c.grid_cell.as<int2>(),
+                                      c.grid_desc.as<BigGrid>(), st)))
+                return rc;
+            a.grids = c.grid_desc.as<BigGrid>();
+            if (p2l && (rc = launch_big_normals(a.t, a.grids, k.normal_k, t.role_max, st))) return rc;
+        } else if (p2l) {
+            if ((rc = launch_normals(a.t, a.cap_t, k.normal_k, k.voxel_size, st))) return rc;
         }
-        const size_t np = (size_t)t.total_points, nc = (size_t)t.n_clouds;
-        if (c.grid_start.reserve(sizeof(int) * (size_t)total_start) || c.grid_items.reserve(sizeof(int) * np) ||
-            c.grid_cell.reserve(sizeof(int2) * np) || c.grid_desc.reserve(sizeof(BigGrid) * nc) ||
-            c.grid_off.reserve(sizeof(long long) * nc) || c.grid_buckets.reserve(sizeof(int) * nc))
-            return ICPB200_ERR_CUDA;
-        ICPB_CUDA(cudaMemcpyAsync(c.grid_off.p, goff.data(), sizeof(long long) * nc, cudaMemcpyHostToDevice, st));
-        ICPB_CUDA(cudaMemcpyAsync(c.grid_buckets.p, gbuckets.data(), sizeof(int) * nc, cudaMemcpyHostToDevice, st));
-        ICPB_CUDA(cudaStreamSynchronize(st));          // goff / gbuckets are stack-owned
-        ICPB_CUDA(cudaMemsetAsync(c.grid_desc.p, 0, sizeof(BigGrid) * nc, st));
-        // cell edge: 8 voxels (a 3x3 block of cells holds a few dozen wall points)
-        if ((rc = launch_big_grid(a.t, 8.0 * k.voxel_size, c.grid_off.as<long long>(), c.grid_buckets.as<int>(),
-                                  c.grid_start.as<int>(), c.grid_items.as<int>(), c.grid_cell.as<int2>(),
-                                  c.grid_desc.as<BigGrid>(), st)))
-            return rc;
-        a.grids = c.grid_desc.as<BigGrid>();
-        if (p2l && (rc = launch_big_normals(a.t, a.grids, k.normal_k, t.role_max, st))) return rc;
-    } else if (p2l) {
-        if ((rc = launch_normals(a.t, a.cap_t, k.normal_k, k.voxel_size, st))) return rc;
     }
     ICPB_CUDA(cudaEventRecord(c.ev[2], st));
     const int per_sm = icp_max_ctas_per_sm(k.dim, grid, smem);
@@ -376,6 +412,13 @@ void icpb200_shutdown(void) {
                       &c.grid_buckets, &c.rot_src, &c.rot_tgt, &c.rot_ang, &c.rot_off, &c.rot_out, &c.cont_cur, &c.cont_match, &c.cont_d2lb, &c.cont_moved, &c.cont_scalar, &c.cont_list};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 4; ++i) if (c.ev[i]) { cudaEventDestroy(c.ev[i]); c.ev[i] = nullptr; }
+    for (int i = 0; i < kUploadChunks; ++i) {
+        if (c.chunk_ev[i]) { cudaEventDestroy(c.chunk_ev[i]); c.chunk_ev[i] = nullptr; }
+        if (c.chunk_done[i]) { cudaEventDestroy(c.chunk_done[i]); c.chunk_done[i] = nullptr; }
+        if (c.chunk_stream[i]) { cudaStreamDestroy(c.chunk_stream[i]); c.chunk_stream[i] = nullptr; }
+    }
+    if (c.fork_ev) { cudaEventDestroy(c.fork_ev); c.fork_ev = nullptr; }
+    if (c.copy_stream) { cudaStreamDestroy(c.copy_stream); c.copy_stream = nullptr; }
     cudaStreamDestroy(c.stream);
     c.stream = nullptr;
     c.ready = false;
@@ -453,10 +496,23 @@ int icpb200_icp_pairs(int n_clouds, int dim, const double* pts, const int64_t* c
         c.idx_a.reserve(sizeof(int32_t) * (size_t)n_pairs) || c.idx_b.reserve(sizeof(int32_t) * (size_t)n_pairs))
         return ICPB200_ERR_CUDA;
     if ((rc = reserve_outputs(c, n_pairs, dim))) return rc;
-    ICPB_CUDA(cudaMemcpyAsync(c.pts_a.p, pts, sizeof(double) * dim * np, cudaMemcpyHostToDevice, c.stream));
     ICPB_CUDA(cudaMemcpyAsync(c.off_a.p, cloud_off, sizeof(int64_t) * (n_clouds + 1), cudaMemcpyHostToDevice, c.stream));
     ICPB_CUDA(cudaMemcpyAsync(c.idx_a.p, src_idx, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyHostToDevice, c.stream));
     ICPB_CUDA(cudaMemcpyAsync(c.idx_b.p, tgt_idx, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyHostToDevice, c.stream));
+    // the clouds go up in a few chunks on the copy stream; the per-cloud kernels of a chunk start when it has landed
+    static const bool e2e_timing = getenv("ICPB200_E2E_TIMING") != nullptr;
+    static const bool no_chunk = getenv("ICPB200_NO_CHUNK") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    UploadPlan plan;
+    plan.n_chunks = (int)std::max<size_t>(1, std::min<size_t>(kUploadChunks, np * dim * sizeof(double) / (4u << 20)));
+    if (no_chunk) plan.n_chunks = 1;
+    plan.n_chunks = std::min(plan.n_chunks, n_clouds);
+    for (int ch = 0; ch <= plan.n_chunks; ++ch) plan.first[ch] = (int)((long long)n_clouds * ch / plan.n_chunks);
+    for (int ch = 0; ch < plan.n_chunks; ++ch) {
+        const size_t b0 = (size_t)cloud_off[plan.first[ch]] * dim, b1 = (size_t)cloud_off[plan.first[ch + 1]] * dim;
+        ICPB_CUDA(cudaMemcpyAsync(c.pts_a.as<double>() + b0, pts + b0, sizeof(double) * (b1 - b0), cudaMemcpyHostToDevice, c.copy_stream));
+        ICPB_CUDA(cudaEventRecord(c.chunk_ev[ch], c.copy_stream));
+    }
     const double *d_Ri, *d_ti;
     if ((rc = upload_init(c, n_pairs, dim, R_init, t_init, &d_Ri, &d_ti))) return rc;
     long long max_src = 0, max_tgt = 0;
@@ -468,8 +524,20 @@ int icpb200_icp_pairs(int n_clouds, int dim, const double* pts, const int64_t* c
     const DevClouds t{c.pts_a.as<double>(), c.off_a.as<long long>(), cloud_off, n_clouds, max_tgt, max_pts, (long long)np};
     rc = icp_enqueue(k, n_pairs, s, t, true, c.idx_a.as<int>(), c.idx_b.as<int>(), d_Ri, d_ti, c.out_r.as<double>(),
                      c.out_t.as<double>(), c.out_err.as<double>(), c.out_prev.as<double>(), c.out_iters.as<int>(),
-                     c.out_status.as<int>(), c.stream, IcpTrace{}, nullptr);
-    if (rc) return rc;
+                     c.out_status.as<int>(), c.stream, IcpTrace{}, nullptr, &plan);
+    if (rc) { cudaStreamSynchronize(c.copy_stream); return rc; }
+    if (e2e_timing) {
+        const auto t_enq = std::chrono::steady_clock::now();
+        cudaStreamSynchronize(c.copy_stream);
+        const auto t_copy = std::chrono::steady_clock::now();
+        cudaStreamSynchronize(c.stream);
+        const auto t_done = std::chrono::steady_clock::now();
+        auto us = [](auto a_, auto b_) { return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(b_ - a_).count() / 1e3; };
+        fprintf(stderr, "[icp e2e] enqueue %.0f us, copies done at %.0f us, kernels done at %.0f us (%d chunks)\n",
+                us(t_begin, t_enq), us(t_begin, t_copy), us(t_begin, t_done), plan.n_chunks);
+    }
+    // paths that did not consume the chunk events (grid mode, big clouds) still need the data before their kernels:
+    // icp_enqueue waited for every chunk in that case (see below), so nothing is pending here
     return fetch_outputs(c, n_pairs, dim, IcpOutputs{R_out, t_out, err_out, prev_err_out, iters_out, status_out});
 }
 

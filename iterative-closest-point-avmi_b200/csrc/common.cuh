@@ -40,12 +40,17 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+constexpr int kUploadChunks = 4;
+
 struct Context {
     bool ready = false;
     int device = -1;
     int sm_count = 0;
     int max_smem_optin = 0;
     cudaStream_t stream = nullptr;     // library-owned stream for the host-buffer entry points
+    cudaStream_t copy_stream = nullptr;                        // chunked cloud uploads of icpb200_icp_pairs
+    cudaEvent_t chunk_ev[kUploadChunks] = {}, chunk_done[kUploadChunks] = {}, fork_ev = nullptr;
+    cudaStream_t chunk_stream[kUploadChunks] = {};              // K1/K2 of upload chunk k
     // ICP staging (host-buffer entry points)
     DevBuf pts_a, pts_b, off_a, off_b, idx_a, idx_b, rinit, tinit;
     DevBuf out_r, out_t, out_err, out_prev, out_iters, out_status, queue, trace, stats;

@@ -81,10 +81,10 @@ __global__ void mark_used_kernel(int n_pairs, const int* __restrict__ src_idx, c
 
 // ---- K1: voxel-grid means, one CTA per cloud -----------------------------------
 template <int DIM>
-__global__ void __launch_bounds__(kNT) voxel_clouds_kernel(const CloudSet cs, double voxel, int sort_pad) {
+__global__ void __launch_bounds__(kNT) voxel_clouds_kernel(const CloudSet cs, double voxel, int sort_pad, int first) {
     extern __shared__ __align__(16) unsigned char smem[];
     CtaShared& sh = *reinterpret_cast<CtaShared*>(smem);
-    const int c = blockIdx.x;
+    const int c = first + blockIdx.x;
     if (cs.used && !cs.used[c]) return;
     const long long beg = cs.off[c];
     const long long n = cs.off[c + 1] - beg;
@@ -633,10 +633,10 @@ __device__ void cta_normals_2d(const double* tx, const double* ty, int n_t, int 
     }
 }
 
-__global__ void __launch_bounds__(kNT) normals_kernel(const CloudSet cs, int normal_k, int cap_t, double voxel) {
+__global__ void __launch_bounds__(kNT) normals_kernel(const CloudSet cs, int normal_k, int cap_t, double voxel, int first) {
     extern __shared__ __align__(16) unsigned char smem[];
     CtaShared& sh = *reinterpret_cast<CtaShared*>(smem);
-    const int c = blockIdx.x;
+    const int c = first + blockIdx.x;
     if (!cs.is_tgt[c]) return;
     const int n = cs.ds_n[c];
     if (n <= 0) return;
@@ -662,10 +662,10 @@ __global__ void __launch_bounds__(kNT) normals_kernel(const CloudSet cs, int nor
 }
 
 // K2 fast kernel: normal_k + 1 <= 16 and every cloud <= 4096 points (host-checked).
-__global__ void __launch_bounds__(kNT, 4) normals_sweep_kernel(const CloudSet cs, int normal_k, int cap_t) {
+__global__ void __launch_bounds__(kNT, 4) normals_sweep_kernel(const CloudSet cs, int normal_k, int cap_t, int first) {
     extern __shared__ __align__(16) unsigned char smem[];
     CtaShared& sh = *reinterpret_cast<CtaShared*>(smem);
-    const int c = blockIdx.x;
+    const int c = first + blockIdx.x;
     if (!cs.is_tgt[c]) return;
     const int n = cs.ds_n[c];
     if (n <= 0) return;
@@ -1787,29 +1787,33 @@ int launch_mark_used(const IcpArgs& a, bool p2l, cudaStream_t stream) {
     return ICPB200_OK;
 }
 
-int launch_voxel_clouds(const CloudSet& cs, int dim, double voxel, int sort_pad, cudaStream_t stream) {
+int launch_voxel_clouds(const CloudSet& cs, int dim, double voxel, int sort_pad, cudaStream_t stream, int first, int count) {
+    if (count < 0) count = cs.n_clouds - first;
+    if (count == 0) return ICPB200_OK;
     const size_t smem = icp_voxel_smem_bytes(sort_pad);
     if (dim == 2) {
         ICPB_CUDA(cudaFuncSetAttribute(voxel_clouds_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        voxel_clouds_kernel<2><<<cs.n_clouds, kNT, smem, stream>>>(cs, voxel, sort_pad);
+        voxel_clouds_kernel<2><<<count, kNT, smem, stream>>>(cs, voxel, sort_pad, first);
     } else {
         ICPB_CUDA(cudaFuncSetAttribute(voxel_clouds_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        voxel_clouds_kernel<3><<<cs.n_clouds, kNT, smem, stream>>>(cs, voxel, sort_pad);
+        voxel_clouds_kernel<3><<<count, kNT, smem, stream>>>(cs, voxel, sort_pad, first);
     }
     ICPB_LAUNCH_CHECK();
     return ICPB200_OK;
 }
 
-int launch_normals(const CloudSet& cs, int cap_t, int normal_k, double voxel, cudaStream_t stream) {
+int launch_normals(const CloudSet& cs, int cap_t, int normal_k, double voxel, cudaStream_t stream, int first, int count) {
+    if (count < 0) count = cs.n_clouds - first;
+    if (count == 0) return ICPB200_OK;
     const size_t smem = icp_normals_smem_bytes(cap_t);
     if (normal_k + 1 <= kKnnReg && cap_t <= 4096) {
         ICPB_CUDA(cudaFuncSetAttribute(normals_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        normals_sweep_kernel<<<cs.n_clouds, kNT, smem, stream>>>(cs, normal_k, cap_t);
+        normals_sweep_kernel<<<count, kNT, smem, stream>>>(cs, normal_k, cap_t, first);
         ICPB_LAUNCH_CHECK();
         return ICPB200_OK;
     }
     ICPB_CUDA(cudaFuncSetAttribute(normals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    normals_kernel<<<cs.n_clouds, kNT, smem, stream>>>(cs, normal_k, cap_t, voxel);
+    normals_kernel<<<count, kNT, smem, stream>>>(cs, normal_k, cap_t, voxel, first);
     ICPB_LAUNCH_CHECK();
     return ICPB200_OK;
 }

@@ -108,8 +108,8 @@ int icp_max_ctas_per_sm(int dim, bool grid, size_t smem);
 
 // used[c] = 1 for every referenced cloud, is_tgt[c] = 1 for p2l targets (device-side, from the idx arrays)
 int launch_mark_used(const IcpArgs& a, bool p2l, cudaStream_t stream);
-int launch_voxel_clouds(const CloudSet& cs, int dim, double voxel, int sort_pad, cudaStream_t stream);
-int launch_normals(const CloudSet& cs, int cap_t, int normal_k, double voxel, cudaStream_t stream);
+int launch_voxel_clouds(const CloudSet& cs, int dim, double voxel, int sort_pad, cudaStream_t stream, int first = 0, int count = -1);
+int launch_normals(const CloudSet& cs, int cap_t, int normal_k, double voxel, cudaStream_t stream, int first = 0, int count = -1);
 int launch_icp_pairs(const IcpArgs& a, int dim, bool grid, int n_ctas, size_t smem, cudaStream_t stream);
 
 // big-cloud kernels (icp_big.cu)
