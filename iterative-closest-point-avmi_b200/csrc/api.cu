@@ -225,7 +225,7 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
     if (c.queue.reserve(4 * sizeof(unsigned)) || c.stats.reserve(16 * sizeof(unsigned long long))) return ICPB200_ERR_CUDA;
     a.queue = c.queue.as<unsigned>();
     // two-phase schedule (see icp_kernel.h): worthwhile once the batch fills the machine
-    static const int kPhaseCap = getenv("ICPB200_PHASE_CAP") ? std::max(2, atoi(getenv("ICPB200_PHASE_CAP"))) : 12;
+    const int kPhaseCap = 12;                                    // flat between 8 and 16 on C2 (profiles/README.md)
     const bool two_phase = n_pairs >= 2 * c.sm_count && k.max_iterations > 2 * kPhaseCap;
     a.phase_cap = two_phase ? kPhaseCap : 0;
     static const bool no_slab = getenv("ICPB200_NO_SLAB") != nullptr;      // A/B switch: tile sweep for every decision
@@ -330,11 +330,9 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
         IcpArgs b = a;
         b.resume = 1;
         b.queue = a.queue + 1;
-        static const int p2_per_sm = getenv("ICPB200_P2_PER_SM") ? std::max(1, std::min(3, atoi(getenv("ICPB200_P2_PER_SM")))) : 1;
-        size_t smem2 = smem;
-        if (p2_per_sm == 1) smem2 = std::max(smem, (size_t)c.max_smem_optin / 2 + 1024);
-        else if (p2_per_sm == 2) smem2 = std::max(smem, (size_t)c.max_smem_optin / 3 + 1024);
-        if ((rc = launch_icp_pairs(b, k.dim, grid, c.sm_count * p2_per_sm, std::min(smem2, (size_t)c.max_smem_optin), st))) return rc;
+        // (two or three CTAs per SM were measured slower: the hand-over pairs are latency-bound and want the SM alone)
+        const size_t smem2 = std::max(smem, (size_t)c.max_smem_optin / 2 + 1024);
+        if ((rc = launch_icp_pairs(b, k.dim, grid, c.sm_count, std::min(smem2, (size_t)c.max_smem_optin), st))) return rc;
     }
     ICPB_CUDA(cudaEventRecord(c.ev[3], st));
     return ICPB200_OK;
