@@ -831,7 +831,6 @@ void* icpb200_grid_create(int nx, int ny, double min_x, double min_y, double res
     g->apply_ctas = occ_apply_ctas(g_ctx.sm_count);
     g->fast_ctas = occ_fast_ctas(g_ctx.sm_count);
     if (const char* e = getenv("ICPB200_OCC_PATH")) g->use_fast = strcmp(e, "ordered") != 0;
-    if (const char* e = getenv("ICPB200_OCC_SPLIT")) g->split = std::max(1, std::min(8, atoi(e)));
     if (g->grid.reserve(sizeof(float) * (size_t)nx * ny) ||
         cudaMemsetAsync(g->grid.p, 0, sizeof(float) * (size_t)nx * ny, g_ctx.stream) != cudaSuccess ||
         cudaStreamSynchronize(g_ctx.stream) != cudaSuccess) {

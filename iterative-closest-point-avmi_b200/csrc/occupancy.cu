@@ -293,7 +293,6 @@ struct ApplyArgs {
     float clamp0;
     int* error_flag;
     long long* tile_prof;                     // optional: per queue slot {tile, scans, runs, cycles}
-    int split;                                // lock-step windows per 32-run chunk
 };
 
 __device__ __forceinline__ float chain(float x, unsigned m, unsigned k, double l_hit, double l_miss,
@@ -664,7 +663,6 @@ int occ_update_ordered(OccGrid& g, int n_scans, const double* d_origins, const d
         }
         ap.error_flag = reinterpret_cast<int*>(d_small + 3);
         ap.tile_prof = nullptr;
-        ap.split = g.split;
         if (g.profile_tiles) {
             if (g.tile_prof.reserve(sizeof(long long) * 4 * (size_t)n_tiles)) return ICPB200_ERR_CUDA;
             ICPB_CUDA(cudaMemsetAsync(g.tile_prof.p, 0, sizeof(long long) * 4 * (size_t)n_tiles, st));

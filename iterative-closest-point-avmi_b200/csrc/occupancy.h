@@ -41,7 +41,6 @@ struct OccGrid {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int fast_ctas = 0;
     bool use_fast = true;                          // ICPB200_OCC_PATH=ordered forces the ordered tile replay
-    int split = 1;                                 // lock-step windows per 32-run chunk (tuning knob)
     bool profile_tiles = false;                    // icpb200_grid_tile_profile() requested per-tile timings
     void release_all();
 };
