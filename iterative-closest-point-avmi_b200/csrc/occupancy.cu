@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) occ_bin(const BinArgs a) {
             t.tile = hit_tile; t.n0 = hit_cell; t.j0 = 0; t.len = 0;
         }
         if (!__any_sync(0xffffffffu, has)) break;
-        const bool owned = has && occ_owner((t.tile % a.tiles_x) * TS, (t.tile / a.tiles_x) * TS, a.nx, a.world) == a.rank;
+        const bool owned = has && occ_owner((t.tile % a.tiles_x) * TS, (t.tile / a.tiles_x) * TS, a.nx, a.ny, a.world) == a.rank;
         const unsigned long long gi = owned ? (unsigned long long)t.tile * a.chunk_scans + sl : ~0ull;
         const unsigned peers = __match_any_sync(0xffffffffu, gi);
         const int leader = __ffs(peers) - 1;
@@ -538,7 +538,7 @@ __global__ void occ_finalize_virgin(float* grid, int nx, int ny, int tiles_x, in
     const int x = (int)(i % nx), y = (int)(i / nx);
     const int tile = (y / TS) * tiles_x + (x / TS);
     (void)tile;
-    if (occ_owner(x, y, nx, world) != rank) return;
+    if (occ_owner(x, y, nx, ny, world) != rank) return;
     if (grid[i] == 0.0f) grid[i] = clamp0;
 }
 

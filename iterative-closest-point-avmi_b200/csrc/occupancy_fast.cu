@@ -71,7 +71,7 @@ struct FastArgs {
     int scan_begin, chunk_scans, n_scans;
     double min_x, min_y, res;
     int nx, ny, tiles_x, n_tiles;
-    int rank, world;
+    int ya, yb;                               // this rank's rows (occ_strip_begin)
     int2* ray_cell;                           // chunk-relative
     int* ray_scan;
     int2* origin_cell;                        // absolute scan index
@@ -99,12 +99,15 @@ struct FastTileIter {
     RayGeom g;
     int n, nb;
     bool small;
-    int tiles_x;
-    __device__ __forceinline__ void init_empty() { n = 0; nb = 0; small = true; }
-    __device__ __forceinline__ void init(const RayGeom& geom, int nx, int ny, int tiles_x_) {
+    int tiles_x, tile_row0;
+    __device__ __forceinline__ void init_empty() { n = 0; nb = 0; small = true; tile_row0 = 0; }
+    // rows [ya, yb) are this rank's strip (the whole grid on one GPU): the ray is clipped to it in closed form
+    __device__ __forceinline__ void init(const RayGeom& geom, int nx, int ya, int yb, int tiles_x_) {
         g = geom; tiles_x = tiles_x_;
+        g.oy -= ya;                                            // strip coordinates; ya is a multiple of TS
+        tile_row0 = ya / TS;
         int64_t a = 0, b = 0;
-        if (g.dmaj != 0) clip_to_grid(g, nx, ny, a, b);
+        if (g.dmaj != 0) clip_to_grid(g, nx, yb - ya, a, b);
         n = (int)a; nb = (int)b;
         small = g.dmaj < (1 << 14) && nb < (1 << 14);          // 2*n*dmin + dmaj < 2^30
     }
@@ -134,7 +137,7 @@ struct FastTileIter {
             if (nleave < end) end = nleave;
         }
         if (end > nb) end = nb;
-        r.tile = (y / TS) * tiles_x + (x / TS);
+        r.tile = (y / TS + tile_row0) * tiles_x + (x / TS);
         r.n0 = n; r.j0 = j; r.len = (int)(end - n);
         n = (int)end;
         return true;
@@ -185,10 +188,10 @@ __global__ void __launch_bounds__(256, 8) occ_fast_rays(const FastArgs a) {
         }
         sl = s - a.scan_begin;
         const int2 o = a.origin_cell[s];
-        it.init(make_ray(o.x, o.y, h.x, h.y), a.nx, a.ny, a.tiles_x);
+        it.init(make_ray(o.x, o.y, h.x, h.y), a.nx, a.ya, a.yb, a.tiles_x);
         if (h.x >= 0 && h.x < a.nx && h.y >= 0 && h.y < a.ny) {                 // mapping.py:124-127
             const int tile = (h.y / TS) * a.tiles_x + (h.x / TS);
-            if (tile % a.world == a.rank) {
+            if (h.y >= a.ya && h.y < a.yb) {
                 const size_t cell = (size_t)h.y * a.nx + h.x;
                 if (!FILL) {
                     ++nhits;
@@ -219,7 +222,7 @@ __global__ void __launch_bounds__(256, 8) occ_fast_rays(const FastArgs a) {
         TileRun t;
         const bool has = it.next(t);
         const bool more = __any_sync(0xffffffffu, has);
-        const bool owned = has && (t.tile % a.world == a.rank);
+        const bool owned = has;                                // the walk is already clipped to the rank's strip
         const int seg = owned ? t.tile * kLenClasses + ((t.len - 1) >> kLenShift) : -1 - lane;
         unsigned base = 0, off = 0, peers = 0;
         int leader = 0;
@@ -696,7 +699,7 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
     a.scan_begin = s0; a.chunk_scans = cs; a.n_scans = n_scans;
     a.min_x = g.min_x; a.min_y = g.min_y; a.res = g.res;
     a.nx = g.nx; a.ny = g.ny; a.tiles_x = tiles_x; a.n_tiles = n_tiles;
-    a.rank = g.rank; a.world = g.world;
+    a.ya = occ_strip_begin(g.rank, g.ny, g.world); a.yb = occ_strip_begin(g.rank + 1, g.ny, g.world);
     a.ray_cell = g.ray_cell.as<int2>();
     a.ray_scan = g.ray_scan.as<int>();
     a.origin_cell = g.origin_cell.as<int2>();

@@ -3,11 +3,12 @@
 * registrations: pairs are independent, so rank r registers a contiguous block
   of the pair list with no data-path collective; one all_gather returns every
   rank's (R, t, error, iters, status) to all ranks.
-* occupancy replay: the grid is cut into 64 x 64-cell blocks owned block-cyclically
-  (block % world == rank, the rule libicp_b200 applies in icpb200_grid_set_shard);
-  every rank replays every scan clipped to its own tiles, in scan order, so the
-  clamp order matches the reference.  Cells a rank does not own stay exactly 0,
-  hence one all_reduce(SUM) reassembles the map bit-exactly.
+* occupancy replay: rank r owns a horizontal strip of the grid -- the 64-cell tile
+  rows [r*T/world, (r+1)*T/world) (the rule libicp_b200 applies in
+  icpb200_grid_set_shard); every rank replays every scan clipped to its own strip,
+  in scan order, so the clamp order matches the reference.  Cells a rank does not
+  own stay exactly 0: one all_gather of the strips (equally tall strips) or one
+  all_reduce(SUM) reassembles the map bit-exactly.
 
 NCCL (GPU tensors) on the B200 box, gloo (CPU tensors) in the CPU tests.
 """
@@ -72,14 +73,19 @@ def icp_pairs_sharded(points, cloud_off, src_idx, tgt_idx, *args, compute=None, 
                 status=full[:, dd + dim + 3].astype(np.int32))
 
 
+def strip_rows(ny, rank, size):
+    """Rows [lo, hi) of the grid owned by `rank` (occ_strip_begin in csrc/occupancy.h)."""
+    tiles_y = (ny + TILE - 1) // TILE
+    lo = min((tiles_y * rank // size) * TILE, ny)
+    hi = min((tiles_y * (rank + 1) // size) * TILE, ny)
+    return lo, hi
+
+
 def owned_tile_mask(nx, ny, rank, size):
-    """(ny, nx) bool mask of the cells whose tile this rank owns (tile % size == rank)."""
-    tiles_x = (nx + TILE - 1) // TILE
-    ty, tx = np.divmod(np.arange(((ny + TILE - 1) // TILE) * tiles_x), tiles_x)
-    own = (np.arange(len(tx)) % size) == rank
+    """(ny, nx) bool mask of the cells this rank owns."""
+    lo, hi = strip_rows(ny, rank, size)
     mask = np.zeros((ny, nx), dtype=bool)
-    for t in np.nonzero(own)[0]:
-        mask[ty[t] * TILE:(ty[t] + 1) * TILE, tx[t] * TILE:(tx[t] + 1) * TILE] = True
+    mask[lo:hi] = True
     return mask
 
 
@@ -107,10 +113,17 @@ def grid_device_tensor(device_grid):
 
 
 def grid_allreduce_device(device_grid):
-    """In-place NCCL all_reduce(SUM) of the sharded grid on the device (B200 box)."""
+    """Reassemble the sharded grid on every rank, in place on the device (NCCL, B200 box): an all_gather of the
+    strips when they are equally tall (each rank sends only its own rows), else an all_reduce(SUM)."""
     rank, size = world()
     if size > 1:
         t = grid_device_tensor(device_grid)
+        ny = t.shape[0]
+        rows = [strip_rows(ny, r, size) for r in range(size)]
         torch.cuda.synchronize()
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        if len({hi - lo for lo, hi in rows}) == 1 and rows[-1][1] == ny:
+            lo, hi = rows[rank]
+            dist.all_gather_into_tensor(t, t[lo:hi])
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
         torch.cuda.synchronize()

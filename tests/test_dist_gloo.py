@@ -57,8 +57,9 @@ def _worker(rank, size, port, tmp):
         mask = icpd.owned_tile_mask(full.nx, full.ny, rank, size)
         other = icpd.owned_tile_mask(full.nx, full.ny, 1 - rank, size)
         assert not (mask & other).any() and (mask | other).all()
-        T = icpd.TILE
-        assert mask[:T, :T].all() == (rank == 0) and mask[:T, T:2 * T].all() == (rank == 1)
+        lo, hi = icpd.strip_rows(full.ny, rank, size)              # horizontal strips of whole tile rows
+        assert lo % icpd.TILE == 0 and mask[lo:hi].all() and mask.sum() == (hi - lo) * full.nx
+        assert (lo, hi) == ((0, 192) if rank == 0 else (192, 384))
         partial = np.where(mask, full.log_odds, np.float32(0))
         total = icpd.grid_allreduce_host(partial)
         assert total.dtype == np.float32 and total.tobytes() == full.log_odds.tobytes()
