@@ -181,9 +181,11 @@ void *icpb200_grid_create(int nx, int ny, double min_x, double min_y, double res
                           double l_hit, double l_miss, double lo_min, double lo_max);
 void icpb200_grid_destroy(void *grid);
 
-/* Multi-GPU spatial sharding: this process updates only the tiles t with
- * t % world == rank (block-cyclic over 32x32-cell tiles); all other cells
- * stay 0, so an element-wise sum over ranks reassembles the map. */
+/* Multi-GPU spatial sharding: this process updates only its horizontal strip
+ * of the grid -- the rows of the 64-cell tile rows [rank*T/world,
+ * (rank+1)*T/world), T = ceil(ny/64); all other cells stay 0, so a gather of
+ * the strips (or an element-wise sum over ranks) reassembles the map.  Call
+ * before the first update of the grid. */
 int icpb200_grid_set_shard(void *grid, int rank, int world);
 
 /* mapping.py:103-141 for n_scans scans applied in array order (n_scans = 1 is
