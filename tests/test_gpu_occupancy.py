@@ -197,3 +197,36 @@ def test_hit_field_overflow_is_reported_and_the_handle_survives():
     gpu.update_scan(np.zeros(2), ok)
     ref.update_scan(np.zeros(2), ok, fast=True)
     assert_same(gpu, ref, "after the refused call")
+
+
+def test_randomised_configurations_match_the_oracle():
+    """Twelve random grids (sizes that are no multiple of the tile, origins inside and outside, endpoints far out,
+    p_hit / p_miss on both sides of 0.5, lop-sided clamps that still contain 0, duplicate endpoints, empty scans):
+    the device map must equal the oracle's bit for bit on both device paths."""
+    rng = np.random.default_rng(20261018)
+    for case in range(12):
+        w, h = rng.uniform(3.0, 14.0, size=2)
+        res = float(rng.choice([0.05, 0.07, 0.1]))
+        bounds = (-w / 2, w / 2, -h / 3, 2 * h / 3)
+        kw = dict(resolution=res, p_hit=float(rng.uniform(0.08, 0.95)), p_miss=float(rng.uniform(0.08, 0.95)),
+                  log_odds_min=-float(rng.uniform(0.3, 9.0)), log_odds_max=float(rng.uniform(0.3, 9.0)))
+        n_scans = int(rng.integers(1, 90))
+        origins = rng.uniform(-0.7 * max(w, h), 0.7 * max(w, h), size=(n_scans, 2))
+        clouds = []
+        for o in origins:
+            n = int(rng.integers(0, 120))
+            pts = o + rng.normal(scale=rng.choice([0.2, 2.0, 30.0]), size=(n, 2))
+            if n > 4:
+                pts[1] = pts[0]                           # duplicate endpoint
+                pts[2] = o                                # zero-length ray
+            clouds.append(pts)
+        flat, off = synth.pack_ragged(clouds)
+        gpu, ref = make_pair(bounds, **kw)
+        gpu._dev.update(origins, flat, off)
+        ref.update_many(origins, flat, off, fast=True)
+        assert_same(gpu, ref, f"case {case}: {kw} bounds {bounds} scans {n_scans}")
+        # ... and scan by scan on top of the batch (state carried between calls)
+        for s in range(min(n_scans, 5)):
+            gpu.update_scan(origins[s], clouds[s])
+            ref.update_scan(origins[s], clouds[s], fast=True)
+        assert_same(gpu, ref, f"case {case} after single scans")
