@@ -180,3 +180,24 @@ def test_two_phase_schedule_is_bitwise_identical():
         part = api.icp_pairs(flat, off, si[lo:lo + 128], ti[lo:lo + 128], **CFG)
         for key in ("R", "t", "error", "prev_error", "iters", "status"):
             assert part[key].tobytes() == big[key][lo:lo + 128].tobytes(), (key, lo)
+
+
+def test_c2_batch_sweep_against_the_oracle():
+    """A slice of the headline batch (400 consecutive scans, the reference's config.yaml parameters) through the
+    batch entry point against the oracle on every 6th pair plus every pair that hits the iteration limit: same
+    iteration counts and exit status, poses within the north-star tolerance.  This is the regime the pair kernel's
+    shortcuts live in (slab sweep, two-candidate words, net-displacement bound, hand-over launch)."""
+    from oracle import icp_oracle
+    scans, _ = synth.make_sequence(400, world="room", seed=0)
+    cfg = dict(error_threshold=1e-10, max_iterations=150, voxel_size=0.04, method="point_to_line", normal_k=12)
+    flat, off = synth.pack_ragged(scans)
+    si = np.arange(len(scans) - 1, dtype=np.int32)
+    out = api.icp_pairs(flat, off, si, si + 1, **cfg)
+    assert out["iters"].max() == 150 and (out["status"] == 1).sum() >= 5        # the batch does contain limit cycles
+    sel = np.unique(np.concatenate([np.arange(0, len(si), 6), np.nonzero(out["iters"] >= 150)[0]]))
+    for i in sel:
+        R, t, err, iters, status = icp_oracle.register(scans[i], scans[i + 1], **cfg)
+        assert int(out["iters"][i]) == iters and int(out["status"][i]) == status, f"pair {i}"
+        assert np.abs(out["t"][i] - t).max() <= 1e-4
+        dth = np.arctan2(out["R"][i][1, 0], out["R"][i][0, 0]) - np.arctan2(R[1, 0], R[0, 0])
+        assert abs(dth) <= 1e-5
