@@ -378,7 +378,8 @@ __device__ __forceinline__ void pca_normal_masked(const double* tx, const double
 
 template <int KT>
 __device__ void cta_normals_sweep(const double* tx, const double* ty, int n, int K_rt, double* __restrict__ normals_out,
-                                  float2* pf, float* pmax, float* smin, unsigned short* redo, CtaShared& sh) {
+                                  float2* pf, float* pmax, float* smin, unsigned short* redo, CtaShared& sh,
+                                  int part, int split) {
     __shared__ float wtot[2][kNW];
     __shared__ int next_block;                              // query blocks are handed out dynamically
     const int K = KT > 0 ? KT : K_rt;                       // compile-time for the usual neighbourhood sizes
@@ -418,8 +419,9 @@ __device__ void cta_normals_sweep(const double* tx, const double* ty, int n, int
 
     const unsigned idx_mask = n <= 1024 ? 0x3ffu : 0xfffu;
     const double eps_abs = 2.5e-7 * half;                   // |fp32-world distance - true distance|
-    for (int blk = warp; blk * 32 < n; blk = __shfl_sync(full, lane == 0 ? atomicAdd(&next_block, 1) : 0, 0)) {
-        const int base = blk * 32;
+    // (a cloud may be shared by `split` CTAs when the launch is small: this one takes blocks part, part + split, ...)
+    for (int m = warp; (part + m * split) * 32 < n; m = __shfl_sync(full, lane == 0 ? atomicAdd(&next_block, 1) : 0, 0)) {
+        const int base = (part + m * split) * 32;
         const int i = min(base + lane, n - 1);
         const bool valid = base + lane < n;
         const float2 q = pf[i];
@@ -662,10 +664,10 @@ __global__ void __launch_bounds__(kNT) normals_kernel(const CloudSet cs, int nor
 }
 
 // K2 fast kernel: normal_k + 1 <= 16 and every cloud <= 4096 points (host-checked).
-__global__ void __launch_bounds__(kNT, 4) normals_sweep_kernel(const CloudSet cs, int normal_k, int cap_t, int first) {
+__global__ void __launch_bounds__(kNT, 4) normals_sweep_kernel(const CloudSet cs, int normal_k, int cap_t, int first, int split) {
     extern __shared__ __align__(16) unsigned char smem[];
     CtaShared& sh = *reinterpret_cast<CtaShared*>(smem);
-    const int c = first + blockIdx.x;
+    const int c = first + blockIdx.x / split, part = blockIdx.x % split;
     if (!cs.is_tgt[c]) return;
     const int n = cs.ds_n[c];
     if (n <= 0) return;
@@ -688,9 +690,9 @@ __global__ void __launch_bounds__(kNT, 4) normals_sweep_kernel(const CloudSet cs
     }
     __syncthreads();
     const int K = min(normal_k, n - 1) + 1;
-    if (K == 13) cta_normals_sweep<13>(tx, ty, n, K, cs.nrm + beg * 2, pf, pmax, smin, redo, sh);          // normal_k = 12 (config.yaml)
-    else if (K == 11) cta_normals_sweep<11>(tx, ty, n, K, cs.nrm + beg * 2, pf, pmax, smin, redo, sh);     // normal_k = 10 (ICP default)
-    else cta_normals_sweep<0>(tx, ty, n, K, cs.nrm + beg * 2, pf, pmax, smin, redo, sh);
+    if (K == 13) cta_normals_sweep<13>(tx, ty, n, K, cs.nrm + beg * 2, pf, pmax, smin, redo, sh, part, split);          // normal_k = 12 (config.yaml)
+    else if (K == 11) cta_normals_sweep<11>(tx, ty, n, K, cs.nrm + beg * 2, pf, pmax, smin, redo, sh, part, split);     // normal_k = 10 (ICP default)
+    else cta_normals_sweep<0>(tx, ty, n, K, cs.nrm + beg * 2, pf, pmax, smin, redo, sh, part, split);
 }
 
 // ---- K3: fp32 sweep --------------------------------------------------------------
@@ -1808,7 +1810,12 @@ int launch_normals(const CloudSet& cs, int cap_t, int normal_k, double voxel, cu
     const size_t smem = icp_normals_smem_bytes(cap_t);
     if (normal_k + 1 <= kKnnReg && cap_t <= 4096) {
         ICPB_CUDA(cudaFuncSetAttribute(normals_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        normals_sweep_kernel<<<count, kNT, smem, stream>>>(cs, normal_k, cap_t, first);
+        // few clouds (the online loop registers one pair per call): several CTAs share a cloud's query blocks
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int split = std::max(1, std::min(8, sms / std::max(count, 1)));
+        normals_sweep_kernel<<<count * split, kNT, smem, stream>>>(cs, normal_k, cap_t, first, split);
         ICPB_LAUNCH_CHECK();
         return ICPB200_OK;
     }
