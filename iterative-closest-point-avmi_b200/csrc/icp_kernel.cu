@@ -1025,7 +1025,12 @@ __device__ __forceinline__ void nn_slab(const Loop<DIM>& L, CtaShared& sh, int n
         while (!ddone || !udone) {
             if (!ddone) {
                 const int stop = max(dn - 7, 0);
-                for (int j = dn; j >= stop; --j) offer(j);
+                if (dn >= 7) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) offer(dn - u);
+                } else {
+                    for (int j = dn; j >= stop; --j) offer(j);
+                }
                 dn = stop - 1;
                 if (dn < 0) ddone = true;
                 else {
@@ -1035,7 +1040,12 @@ __device__ __forceinline__ void nn_slab(const Loop<DIM>& L, CtaShared& sh, int n
             }
             if (!udone) {
                 const int stop = min(up + 7, L.n_t - 1);
-                for (int j = up; j <= stop; ++j) offer(j);
+                if (up + 7 < L.n_t) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) offer(up + u);
+                } else {
+                    for (int j = up; j <= stop; ++j) offer(j);
+                }
                 up = stop + 1;
                 if (up >= L.n_t) udone = true;
                 else {
