@@ -85,6 +85,8 @@ struct FastArgs {
     unsigned* tile_flag;                      // count pass: 1 = the tile holds a hit cell
     const unsigned* tile_off;                 // fill pass: start of every (tile, length class) segment
     uint4* runs;
+    unsigned long long runs_cap, ord_cap;     // capacities (records / words): a fill launched before the host knows the
+                                              // totals leaves without a write when they do not fit
     // small: [0] total runs [1] items [2] queue A [3] error flag [4] n_slots [5] multi-item tiles
     //        [6] items of tiles with hit cells (they come first) [7] queue B ; stats (u64 x 4) at +64 bytes
     unsigned* small;
@@ -158,6 +160,9 @@ __global__ void occ_fast_origins(const double* __restrict__ origins, int n_scans
 // the 12-bit field holds; only then the hit atomic needs its return value.
 template <bool FILL, bool CHECK>
 __global__ void __launch_bounds__(256, 8) occ_fast_rays(const FastArgs a) {
+    if (FILL && ((unsigned long long)a.small[0] + 64ull > a.runs_cap ||
+                 (unsigned long long)a.small[4] * (unsigned long long)a.ord_stride > a.ord_cap))
+        return;                                               // speculative launch, buffers too small: the host repeats it
     const long long rl = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // chunk-relative ray
     const long long r = a.ray_begin + rl;
     const int lane = threadIdx.x & 31;
@@ -709,6 +714,7 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
     a.tile_count = g.tile_count.as<unsigned>();
     a.tile_flag = g.tile_flag.as<unsigned>();
     a.tile_off = nullptr; a.runs = nullptr;
+    a.runs_cap = 0; a.ord_cap = 0;
     a.small = d_small; a.stats = d_stats;
     const unsigned nblk = (unsigned)((nr + 255) / 256);
     occ_fast_rays<false, false><<<nblk, 256, 0, st>>>(a);
@@ -718,11 +724,34 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
     ICPB_LAUNCH_CHECK();
     unsigned h_small[8];
     tm.mark("scan");
+    const int stride = (cs + 3) & ~3;
+    bool big_scan = false;
+    for (int s = s0; s < s0 + cs && !big_scan; ++s) big_scan = h_hit_off[s + 1] - h_hit_off[s] > 4095;
+    auto launch_fill = [&]() -> int {
+        ICPB_CUDA(cudaMemsetAsync(g.tile_count.p, 0, sizeof(unsigned) * kLenClasses * (size_t)n_tiles, st));
+        a.ord = g.ord.as<unsigned>(); a.ord_stride = stride;
+        a.tile_off = g.class_off.as<unsigned>();
+        a.runs = g.runs.as<uint4>();
+        a.runs_cap = g.runs.cap / sizeof(uint4);
+        a.ord_cap = g.ord.cap / sizeof(unsigned);
+        if (big_scan) occ_fast_rays<true, true><<<nblk, 256, 0, st>>>(a);
+        else occ_fast_rays<true, false><<<nblk, 256, 0, st>>>(a);
+        ICPB_LAUNCH_CHECK();
+        return ICPB200_OK;
+    };
+    // The fill pass needs buffers sized by totals the host does not know yet.  From the second call on the buffers of
+    // the previous call are almost always large enough: launch the fill first (it checks the totals on the device and
+    // leaves without a write if they do not fit), read the totals back underneath it, repeat it only if it had to leave.
+    const bool speculative = g.runs.cap > 0 && g.ord.cap > 0;
+    if (speculative) {
+        int rc = launch_fill();
+        if (rc) return rc;
+    }
     ICPB_CUDA(cudaMemcpyAsync(h_small, d_small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
     ICPB_CUDA(cudaStreamSynchronize(st));
     const unsigned total_runs = h_small[0], n_slots = h_small[4];
-    const int stride = (cs + 3) & ~3;
     const size_t ord_words = (size_t)n_slots * stride;
+    const bool filled = speculative && (size_t)total_runs + 64 <= g.runs.cap / sizeof(uint4) && ord_words <= g.ord.cap / sizeof(unsigned);
     if (ord_words > kOccOrdBudget) {
         // too many hit cells for the dense table: undo the claims, the ordered path takes the chunk
         if (n_slots) {
@@ -735,26 +764,20 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
         }
         return 1;
     }
-    {
+    if (!filled) {
         void* before = g.ord.p;
         const size_t cap_before = g.ord.cap;
         if (g.ord.reserve(sizeof(unsigned) * std::max<size_t>(ord_words, 1))) return ICPB200_ERR_CUDA;
         if (g.ord.p != before || g.ord.cap != cap_before) ICPB_CUDA(cudaMemsetAsync(g.ord.p, 0, g.ord.cap, st));
-        if (g.ev.reserve(sizeof(unsigned) * std::max<size_t>(ord_words, 1)) ||
-            g.ev_count.reserve(sizeof(unsigned) * std::max<size_t>(n_slots, 1)))
-            return ICPB200_ERR_CUDA;
+        if (g.runs.reserve(sizeof(uint4) * ((size_t)total_runs + 64))) return ICPB200_ERR_CUDA;
     }
-    if (g.runs.reserve(sizeof(uint4) * ((size_t)total_runs + 64))) return ICPB200_ERR_CUDA;
-    ICPB_CUDA(cudaMemsetAsync(g.tile_count.p, 0, sizeof(unsigned) * kLenClasses * (size_t)n_tiles, st));
-    a.ord = g.ord.as<unsigned>(); a.ord_stride = stride;
-    a.tile_off = g.class_off.as<unsigned>();
-    a.runs = g.runs.as<uint4>();
+    if (g.ev.reserve(std::max<size_t>(g.ord.cap, sizeof(unsigned))) || g.ev_count.reserve(sizeof(unsigned) * std::max<size_t>(n_slots, 1)))
+        return ICPB200_ERR_CUDA;
     tm.mark("host gap");
-    bool big_scan = false;
-    for (int s = s0; s < s0 + cs && !big_scan; ++s) big_scan = h_hit_off[s + 1] - h_hit_off[s] > 4095;
-    if (big_scan) occ_fast_rays<true, true><<<nblk, 256, 0, st>>>(a);
-    else occ_fast_rays<true, false><<<nblk, 256, 0, st>>>(a);
-    ICPB_LAUNCH_CHECK();
+    if (!filled) {
+        int rc = launch_fill();
+        if (rc) return rc;
+    }
     tm.mark("fill");
     const float lo = (float)g.lo_min, hi = (float)g.lo_max;
     bool replayed = false;
