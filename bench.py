@@ -192,6 +192,12 @@ def cpu_raycast_baseline(origins, flat, off, n_sample):
                        f"update_scan measured 2.8k rays/s/core in BASELINE.md")
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, from the round's `ncu --set full` captures of this command
+# (profiles/r01_ncu_icp_final.txt, profiles/r01_ncu_occ_final.txt); the occupancy figure is the sum over the update's kernels
+NCU_DRAM_BYTES = dict(icp_pairs_kernel=55.2e6 + 7.3e6, occupancy_update=651e6,
+                      source="ncu --set full, profiles/r01_ncu_icp_final.txt / r01_ncu_occ_final.txt (C2 / C4, round 1)")
+
+
 # --------------------------------------------------------------------------- reference arm
 def run_reference(args, rank, world):
     if rank != 0:
@@ -372,7 +378,8 @@ def run_ours(args, rank, world, local_rank):
     executed_tf = exe_evals * FLOP_PER_PAIR_EVAL_2D / kernel_s / 1e12
     peak_tf = peak_evals * FLOP_PER_PAIR_EVAL_2D / 1e12
     roofline = dict(bound="fp32_fma", achieved=achieved_tf, peak=peak_tf, unit="TFLOP/s", frac=achieved_tf / peak_tf,
-                    traffic=None, kernel="icp_pairs_kernel<2>", kernel_ms=kernel_s * 1e3,
+                    traffic=NCU_DRAM_BYTES["icp_pairs_kernel"], traffic_source=NCU_DRAM_BYTES["source"],
+                    kernel="icp_pairs_kernel<2>", kernel_ms=kernel_s * 1e3,
                     kernel_share_of_step=kernel_s * 1e3 / float(np.mean(ms_steps)),
                     voxel_kernel_ms=kstats["voxel_kernel_ns"] / 1e6, normals_kernel_ms=kstats["normals_kernel_ns"] / 1e6,
                     algorithmic_pair_evals_per_launch=alg_evals, executed_pair_evals_per_launch=exe_evals,
@@ -495,8 +502,8 @@ def bench_raycast(args, lib, api, dev, local_rank, pk, rank=0, world=1):
                          d2h_bytes_per_step=int(host_out.nbytes), api="icpb200_grid_update + icpb200_grid_read"),
                 gpu_launches=int(launches),
                 roofline=dict(bound="hbm", achieved=alg_bytes / sec / 1e9 / world, peak=pk["hbm_gbs"], unit="GB/s",
-                              frac=alg_bytes / sec / 1e9 / world / pk["hbm_gbs"], traffic=None,
-                              kernel="occ_tile_apply (+ binning passes; whole update timed); per GPU",
+                              frac=alg_bytes / sec / 1e9 / world / pk["hbm_gbs"], traffic=NCU_DRAM_BYTES["occupancy_update"], traffic_source=NCU_DRAM_BYTES["source"],
+                              kernel="occ_fast_tiles + binning passes + hit-cell replay (the whole update is timed); per GPU",
                               algorithmic_bytes=alg_bytes, peak_basis=f"{pk['source']} HBM copy bandwidth"),
                 cpu_baseline=cpu, clocks=clk.summary())
 
