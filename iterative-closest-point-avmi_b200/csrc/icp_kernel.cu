@@ -355,6 +355,40 @@ __device__ void knn_normals_fast(const double* tx, const double* ty, int n_t, in
 // provably separated from everything the keys rejected or the sweep skipped
 // (truncation, fp32 rounding and recentring slack included).  Anything else goes
 // to the exact fp64 pass below.  The normal always comes from fp64 coordinates.
+// Sorting networks on registers (every index is a compile-time constant after unrolling).
+template <int N>
+__device__ __forceinline__ void bitonic_sort_regs(unsigned (&v)[N]) {
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1)
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const unsigned lo_ = min(v[i], v[p]), hi_ = max(v[i], v[p]);
+                    const bool asc = (i & k) == 0;
+                    v[i] = asc ? lo_ : hi_;
+                    v[p] = asc ? hi_ : lo_;
+                }
+            }
+}
+// v is bitonic on entry, ascending on exit
+template <int N>
+__device__ __forceinline__ void bitonic_merge_regs(unsigned (&v)[N]) {
+#pragma unroll
+    for (int j = N >> 1; j > 0; j >>= 1)
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const int p = i ^ j;
+            if (p > i) {
+                const unsigned lo_ = min(v[i], v[p]), hi_ = max(v[i], v[p]);
+                v[i] = lo_;
+                v[p] = hi_;
+            }
+        }
+}
+
 __device__ __forceinline__ void pca_normal_masked(const double* tx, const double* ty, const unsigned (&key)[kKnnReg],
                                                   unsigned idx_mask, unsigned in_mask, int K, double* out2) {
     double mx = 0.0, my = 0.0;
@@ -428,18 +462,13 @@ __device__ void cta_normals_sweep(const double* tx, const double* ty, int n, int
         unsigned key[kKnnReg];
 #pragma unroll
         for (int m = 0; m < kKnnReg; ++m) key[m] = 0xffffffffu;
-        auto offer = [&](int j) {
+        // Candidates are taken sixteen at a time (eight below, eight above), sorted in registers and merged into the
+        // list: min(list[i], batch[15 - i]) keeps the sixteen smallest of the union as a bitonic sequence, one merge
+        // network sorts it -- 240 min/max per batch instead of 32 per candidate for an insertion network.
+        auto make_key = [&](int j) {
             const float2 t = pf[j];
             const float dx = q.x - t.x, dy = q.y - t.y;
-            unsigned kk = (__float_as_uint(fmaf(dy, dy, dx * dx)) & ~idx_mask) | (unsigned)j;
-            if (__any_sync(full, kk < key[kKnnReg - 1])) {
-#pragma unroll
-                for (int m = 0; m < kKnnReg; ++m) {
-                    const unsigned lo_ = min(key[m], kk);
-                    kk = max(key[m], kk);
-                    key[m] = lo_;
-                }
-            }
+            return (__float_as_uint(fmaf(dy, dy, dx * dx)) & ~idx_mask) | (unsigned)j;
         };
         auto kth_ub = [&]() {                               // >= fp32 distance^2 of the K-th candidate (NaN if none)
             unsigned kth = 0xffffffffu;
@@ -451,10 +480,24 @@ __device__ void cta_normals_sweep(const double* tx, const double* ty, int n, int
         bool ddone = false, udone = up >= n;
         float gdn = INFINITY, gup = INFINITY;               // |dx| lower bound to the unvisited part, per lane
         while (!ddone || !udone) {
+            unsigned batch[kKnnReg];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int jd = dn - u, ju = up + u;
+                batch[u] = (!ddone && jd >= 0) ? make_key(jd) : 0xffffffffu;
+                batch[8 + u] = (!udone && ju < n) ? make_key(ju) : 0xffffffffu;
+            }
+            unsigned bmin = batch[0];
+#pragma unroll
+            for (int u = 1; u < kKnnReg; ++u) bmin = min(bmin, batch[u]);
+            if (__any_sync(full, bmin < key[kKnnReg - 1])) {
+                bitonic_sort_regs<kKnnReg>(batch);
+#pragma unroll
+                for (int m = 0; m < kKnnReg; ++m) key[m] = min(key[m], batch[kKnnReg - 1 - m]);
+                bitonic_merge_regs<kKnnReg>(key);
+            }
             if (!ddone) {
-                const int stop = max(dn - 7, 0);
-                for (int j = dn; j >= stop; --j) offer(j);
-                dn = stop - 1;
+                dn -= 8;
                 if (dn < 0) ddone = true;
                 else {
                     const float g = q.x - pmax[dn];
@@ -462,9 +505,7 @@ __device__ void cta_normals_sweep(const double* tx, const double* ty, int n, int
                 }
             }
             if (!udone) {
-                const int stop = min(up + 7, n - 1);
-                for (int j = up; j <= stop; ++j) offer(j);
-                up = stop + 1;
+                up += 8;
                 if (up >= n) udone = true;
                 else {
                     const float g = smin[up] - q.x;
