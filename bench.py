@@ -68,8 +68,35 @@ def peaks():
     return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
 
 
-class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+class _SamplerBase:
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, r[3:7]):
+                if str(flag).lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx or None,
+                    reasons=sorted(reasons), samples=len(sm), source=self.SOURCE)
+
+
+class SmiSpawnSampler(_SamplerBase):
+    """One nvidia-smi process per sample (0.2 s apart).  Kept as the fallback when NVML cannot be loaded and for
+    profiles/scale_probe.py: a process that attaches to every GPU of the box while the timed region runs is not free."""
+    SOURCE = "nvidia-smi"
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -92,28 +119,58 @@ class ClockSampler:
                 pass
             self._stop.wait(0.2)
 
-    def __enter__(self):
-        self._t.start()
-        return self
 
-    def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+class NvmlSampler(_SamplerBase):
+    """Samples SM clock, power and the clock-event (throttle) reasons of this rank's GPU during the timed region.
 
-    def summary(self):
-        sm, mx, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+    The same NVML counters nvidia-smi prints (clocks.sm, clocks.max.sm, power.draw, clocks_event_reasons.*), read
+    in-process every 5 ms by a thread that was attached to the device BEFORE the timed region starts: the region is
+    a few milliseconds long, so a `nvidia-smi -lms 200` loop would rarely land a sample inside it, and starting one
+    nvidia-smi process per rank at the start of the region (what this class did before) attaches to every GPU of the
+    box while the kernels are being launched."""
+    SOURCE = "nvml"
+    PERIOD_S = 0.005
+
+    def __init__(self, index):
+        import pynvml as nv
+        self.nv = nv
+        nv.nvmlInit()
+        self.h = None
+        try:                                        # CUDA index -> NVML handle through the UUID (CUDA_VISIBLE_DEVICES)
+            import torch
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            self.h = nv.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        except Exception:
+            self.h = nv.nvmlDeviceGetHandleByIndex(index)
+        self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv, h = self.nv, self.h
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = (0x8, 0x40, 0x20, 0x4)               # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+        while not self._stop.is_set():
             try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-            except ValueError:
-                continue
-            for name, flag in zip(names, r[3:7]):
-                if flag.lower().startswith("active"):
-                    reasons.add(name)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx or None,
-                    reasons=sorted(reasons), samples=len(sm))
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mask = int(get_reasons(h))
+                try:
+                    power = nv.nvmlDeviceGetPowerUsage(h) / 1e3
+                except Exception:
+                    power = float("nan")
+                self.rows.append([sm, self.max_sm, power] + ["Active" if mask & b else "Not Active" for b in bits])
+            except Exception:
+                pass
+            self._stop.wait(self.PERIOD_S)
+
+
+def ClockSampler(index):
+    """NVML in-process when it loads, one nvidia-smi process per sample otherwise."""
+    try:
+        return NvmlSampler(index)
+    except Exception:
+        return SmiSpawnSampler(index)
 
 
 def voxel_count(cloud, voxel):

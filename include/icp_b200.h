@@ -195,7 +195,15 @@ int icpb200_grid_set_shard(void *grid, int rank, int world);
 int icpb200_grid_update(void *grid, int n_scans, const double *origins,
                         const double *hits, const int64_t *hit_off);
 /* Device-resident inputs, stream-ordered on `stream` (NULL = library stream).
- * total_hits = hit_off[n_scans] must be supplied by the caller. */
+ * total_hits = hit_off[n_scans] must be supplied by the caller.  For up to
+ * 2048 scans per call the offsets are checked on the device and the call
+ * returns with the update enqueued (the host waits once, for the binning
+ * totals, while the fill pass runs): the grid is valid in stream order, the
+ * statistics and a hit-field overflow (more than 4095 endpoints of one scan in
+ * one cell) are collected -- and the overflow reported -- by the next call
+ * that names this grid (update, read, reset, last_stats), each of which waits
+ * for the update to finish first.  Readers of icpb200_grid_device_ptr() must
+ * order themselves after `stream`. */
 int icpb200_grid_update_dev(void *grid, int n_scans, const double *d_origins,
                             const double *d_hits, const int64_t *d_hit_off,
                             int64_t total_hits, void *stream);

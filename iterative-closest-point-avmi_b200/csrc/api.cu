@@ -810,6 +810,10 @@ void OccGrid::release_all() {
     if (aux_stream) { cudaStreamDestroy(aux_stream); aux_stream = nullptr; }
     if (ev_fork) { cudaEventDestroy(ev_fork); ev_fork = nullptr; }
     if (ev_join) { cudaEventDestroy(ev_join); ev_join = nullptr; }
+    if (ev_hit) { cudaEventDestroy(ev_hit); ev_hit = nullptr; }
+    if (ev_stats) { cudaEventDestroy(ev_stats); ev_stats = nullptr; }
+    if (pending_host) { cudaFreeHost(pending_host); pending_host = nullptr; }
+    stats_pending = false;
 }
 
 void* icpb200_grid_create(int nx, int ny, double min_x, double min_y, double resolution, double l_hit,
@@ -846,7 +850,7 @@ void icpb200_grid_destroy(void* grid) {
     std::lock_guard<std::mutex> lk(g_api_mutex);
     if (!grid) return;
     OccGrid* g = static_cast<OccGrid*>(grid);
-    if (g_ctx.ready) cudaStreamSynchronize(g_ctx.stream);
+    if (g_ctx.ready) { occ_collect(*g); cudaDeviceSynchronize(); }    // updates may have run on a caller's stream
     g->release_all();
     delete g;
 }
@@ -872,6 +876,7 @@ int icpb200_grid_update(void* grid, int n_scans, const double* origins, const do
     if (rc) return rc;
     OccGrid* g = static_cast<OccGrid*>(grid);
     cudaStream_t st = g_ctx.stream;
+    if ((rc = occ_collect(*g))) return rc;
     if (n_rays == 0) { g->stats[0] = g->stats[1] = g->stats[2] = g->stats[3] = 0; return ICPB200_OK; }
     if (g->origins.reserve(sizeof(double) * 2 * (size_t)n_scans) || g->hits.reserve(sizeof(double) * 2 * (size_t)n_rays) ||
         g->hit_off.reserve(sizeof(int64_t) * ((size_t)n_scans + 1)))
@@ -895,11 +900,23 @@ int icpb200_grid_update_dev(void* grid, int n_scans, const double* d_origins, co
     if (rc) return rc;
     OccGrid* g = static_cast<OccGrid*>(grid);
     cudaStream_t st = stream ? (cudaStream_t)stream : g_ctx.stream;
+    if ((rc = occ_collect(*g))) return rc;
+    if (g->use_fast && !g->zero_outside_clamp && n_scans <= kOccMaxChunkScans) {
+        // One chunk of the order-free path: the offsets are checked on the device, the host waits once (for the
+        // binning totals, underneath the fill pass) and returns with the rest of the update enqueued.  The hit-overflow
+        // flag and the statistics are collected by the next call on this grid.
+        rc = occ_update_fast(*g, n_scans, d_origins, d_hits, reinterpret_cast<const long long*>(d_hit_off), nullptr,
+                             (long long)total_hits, true, st);
+        if (rc < 0) { g->slotmap.release(); g->ord.release(); g->ncount.release(); }
+        return rc;
+    }
     std::vector<long long> h_off((size_t)n_scans + 1);
     ICPB_CUDA(cudaMemcpyAsync(h_off.data(), d_hit_off, sizeof(long long) * h_off.size(), cudaMemcpyDeviceToHost, st));
     ICPB_CUDA(cudaStreamSynchronize(st));
-    if (h_off[0] != 0 || h_off[n_scans] != total_hits) {
-        set_error("icpb200_grid_update_dev: hit_off[0] must be 0 and hit_off[n_scans] must equal total_hits");
+    bool monotone = true;
+    for (int s = 0; s < n_scans && monotone; ++s) monotone = h_off[s + 1] >= h_off[s];
+    if (h_off[0] != 0 || h_off[n_scans] != total_hits || !monotone) {
+        set_error("icpb200_grid_update_dev: hit_off[0] must be 0, hit_off must not decrease and hit_off[n_scans] must equal total_hits");
         return ICPB200_ERR_ARG;
     }
     return occ_update_device(*g, n_scans, d_origins, d_hits, reinterpret_cast<const long long*>(d_hit_off), h_off.data(), st);
@@ -911,6 +928,7 @@ int icpb200_grid_read(void* grid, float* out) {
     int rc = init_locked(-1);
     if (rc) return rc;
     OccGrid* g = static_cast<OccGrid*>(grid);
+    if ((rc = occ_collect(*g))) return rc;
     ICPB_CUDA(cudaMemcpyAsync(out, g->grid.p, sizeof(float) * (size_t)g->nx * g->ny, cudaMemcpyDeviceToHost, g_ctx.stream));
     ICPB_CUDA(cudaStreamSynchronize(g_ctx.stream));
     return ICPB200_OK;
@@ -922,6 +940,7 @@ int icpb200_grid_reset(void* grid) {
     int rc = init_locked(-1);
     if (rc) return rc;
     OccGrid* g = static_cast<OccGrid*>(grid);
+    if ((rc = occ_collect(*g))) return rc;
     ICPB_CUDA(cudaMemsetAsync(g->grid.p, 0, sizeof(float) * (size_t)g->nx * g->ny, g_ctx.stream));   // mapping.py:143-145
     ICPB_CUDA(cudaStreamSynchronize(g_ctx.stream));
     g->seen_nonempty_scan = false;
@@ -966,6 +985,11 @@ int icpb200_unpin_host(void* ptr) {
 int icpb200_grid_last_stats(void* grid, int64_t* stats4) {
     if (!grid || !stats4) { set_error("icpb200_grid_last_stats: null pointer"); return ICPB200_ERR_ARG; }
     OccGrid* g = static_cast<OccGrid*>(grid);
+    {
+        std::lock_guard<std::mutex> lk(g_api_mutex);
+        const int rc = occ_collect(*g);
+        if (rc) return rc;
+    }
     for (int i = 0; i < 4; ++i) stats4[i] = g->stats[i];
     return ICPB200_OK;
 }

@@ -1246,8 +1246,10 @@ __device__ __forceinline__ void grid_nn(const Loop<DIM>& L, int n_todo) {
 }
 
 // ---- K3: the kernel ----------------------------------------------------------------
-template <int DIM, bool GRID>
-__global__ void __launch_bounds__(kNT, 3) icp_pairs_kernel(const IcpArgs a) {
+// MINB = CTAs per SM the register allocation must allow: 3 for the bulk launch, 1 for the hand-over launch (one CTA
+// per SM anyway), which then keeps everything in registers instead of spilling.
+template <int DIM, bool GRID, int MINB>
+__global__ void __launch_bounds__(kNT, MINB) icp_pairs_kernel(const IcpArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     CtaShared& sh = *reinterpret_cast<CtaShared*>(smem);
     const int tid = threadIdx.x;
@@ -1876,31 +1878,32 @@ int launch_normals(const CloudSet& cs, int cap_t, int normal_k, double voxel, cu
     return ICPB200_OK;
 }
 
-template <int DIM, bool GRID>
+template <int DIM, bool GRID, int MINB>
 static int launch_pairs_t(const IcpArgs& a, int n_ctas, size_t smem, cudaStream_t stream) {
-    ICPB_CUDA(cudaFuncSetAttribute(icp_pairs_kernel<DIM, GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    icp_pairs_kernel<DIM, GRID><<<n_ctas, kNT, smem, stream>>>(a);
+    ICPB_CUDA(cudaFuncSetAttribute(icp_pairs_kernel<DIM, GRID, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    icp_pairs_kernel<DIM, GRID, MINB><<<n_ctas, kNT, smem, stream>>>(a);
     ICPB_LAUNCH_CHECK();
     return ICPB200_OK;
 }
 
 int launch_icp_pairs(const IcpArgs& a, int dim, bool grid, int n_ctas, size_t smem, cudaStream_t stream) {
-    if (grid) return launch_pairs_t<2, true>(a, n_ctas, smem, stream);        // grid mode is 2-D only
-    return dim == 2 ? launch_pairs_t<2, false>(a, n_ctas, smem, stream) : launch_pairs_t<3, false>(a, n_ctas, smem, stream);
+    if (grid) return launch_pairs_t<2, true, 3>(a, n_ctas, smem, stream);        // grid mode is 2-D only
+    if (dim == 2 && a.resume) return launch_pairs_t<2, false, 1>(a, n_ctas, smem, stream);
+    return dim == 2 ? launch_pairs_t<2, false, 3>(a, n_ctas, smem, stream) : launch_pairs_t<3, false, 3>(a, n_ctas, smem, stream);
 }
 
 int icp_max_ctas_per_sm(int dim, bool grid, size_t smem) {
     int n = 0;
     cudaError_t e;
     if (grid) {
-        cudaFuncSetAttribute(icp_pairs_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, icp_pairs_kernel<2, true>, kNT, smem);
+        cudaFuncSetAttribute(icp_pairs_kernel<2, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, icp_pairs_kernel<2, true, 3>, kNT, smem);
     } else if (dim == 2) {
-        cudaFuncSetAttribute(icp_pairs_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, icp_pairs_kernel<2, false>, kNT, smem);
+        cudaFuncSetAttribute(icp_pairs_kernel<2, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, icp_pairs_kernel<2, false, 3>, kNT, smem);
     } else {
-        cudaFuncSetAttribute(icp_pairs_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, icp_pairs_kernel<3, false>, kNT, smem);
+        cudaFuncSetAttribute(icp_pairs_kernel<3, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, icp_pairs_kernel<3, false, 3>, kNT, smem);
     }
     if (e != cudaSuccess || n < 1) n = 1;
     return n;

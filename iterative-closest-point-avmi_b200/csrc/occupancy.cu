@@ -560,7 +560,8 @@ static int exclusive_scan_u32(const unsigned* d_in, size_t n, unsigned* d_out, D
 int occ_update_device(OccGrid& g, int n_scans, const double* d_origins, const double* d_hits,
                       const long long* d_hit_off, const long long* h_hit_off, cudaStream_t st) {
     if (g.use_fast && !g.zero_outside_clamp) {
-        const int rc = occ_update_fast(g, n_scans, d_origins, d_hits, d_hit_off, h_hit_off, st);
+        const int rc = occ_update_fast(g, n_scans, d_origins, d_hits, d_hit_off, h_hit_off, h_hit_off[n_scans] - h_hit_off[0],
+                                       false, st);
         if (rc < 0) { g.slotmap.release(); g.ord.release(); g.ncount.release(); }      // claims may be left behind: start clean next time
         return rc;
     }

@@ -53,7 +53,13 @@ struct OccGrid {
     // order-free path (occupancy_fast.cu)
     DevBuf slotmap, slot_cell, ord, tile_count, hit_off_shift, items, multi, ncount, ev, ev_count, class_off, tile_flag;
     cudaStream_t aux_stream = nullptr;             // the hit cells' replay runs here, under the remaining tiles
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_hit = nullptr;
+    // Deferred read-back of the device-resident entry point (occ_update_fast with defer = true): the statistics and
+    // the hit-overflow flag of the last update land in `pending_host` (page-locked) behind `ev_stats`; occ_collect()
+    // folds them into `stats` and reports the flag.  Every entry point that touches the grid collects first.
+    unsigned char* pending_host = nullptr;
+    cudaEvent_t ev_stats = nullptr;
+    bool stats_pending = false;
     int fast_ctas = 0;
     bool use_fast = true;                          // ICPB200_OCC_PATH=ordered forces the ordered tile replay
     bool profile_tiles = false;                    // icpb200_grid_tile_profile() requested per-tile timings
@@ -67,8 +73,13 @@ int occ_update_device(OccGrid& g, int n_scans, const double* d_origins, const do
                       const long long* d_hit_off, const long long* h_hit_off, cudaStream_t st);
 int occ_update_ordered(OccGrid& g, int n_scans, const double* d_origins, const double* d_hits,
                        const long long* d_hit_off, const long long* h_hit_off, cudaStream_t st);
+// h_hit_off may be null when n_scans <= kOccMaxChunkScans: the offsets are then validated on the device and the host
+// never waits for them.  defer = true leaves the final statistics / overflow read-back to occ_collect().
 int occ_update_fast(OccGrid& g, int n_scans, const double* d_origins, const double* d_hits,
-                    const long long* d_hit_off, const long long* h_hit_off, cudaStream_t st);
+                    const long long* d_hit_off, const long long* h_hit_off, long long total_hits, bool defer,
+                    cudaStream_t st);
+// Waits for a deferred read-back (if any); returns ICPB200_ERR_LIMIT when the update it belongs to overflowed.
+int occ_collect(OccGrid& g);
 int occ_apply_ctas(int sm_count);
 int occ_fast_ctas(int sm_count);
 

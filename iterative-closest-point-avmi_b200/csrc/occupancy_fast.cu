@@ -53,6 +53,8 @@ constexpr unsigned kClaimed = 0xfffffffeu;   // slot map: being assigned
 constexpr unsigned kHitUnit = 1u << 20;      // ord word: hits << 20 | misses
 constexpr unsigned kMissMask = kHitUnit - 1u;
 constexpr int kTileNT = 256;
+// words of `small` beyond the per-chunk part: written by occ_fast_origins when the host has not seen the offsets
+constexpr int kFlagBigScan = 32, kFlagBadOffsets = 33;
 constexpr int kLenShift = 3, kLenClasses = TS >> kLenShift;      // runs are grouped by length: 1-8, 9-16, ... 57-64
 
 // 16-byte run record: everything the tile kernel needs to walk the run.
@@ -148,21 +150,32 @@ struct FastTileIter {
 
 // ---- 1./3. per-ray passes --------------------------------------------------------
 __global__ void occ_fast_origins(const double* __restrict__ origins, int n_scans, double min_x, double min_y,
-                                 double res, int2* __restrict__ origin_cell) {
+                                 double res, int2* __restrict__ origin_cell, const long long* __restrict__ hit_off,
+                                 long long total_hits, unsigned* __restrict__ flags) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_scans) return;
     // mapping.py:57-60: floor((w - min) / resolution)
     origin_cell[s] = make_int2(sat_cell(floor((origins[2 * s] - min_x) / res)),
                                sat_cell(floor((origins[2 * s + 1] - min_y) / res)));
+    if (flags) {
+        // the host has not seen the offsets (device-resident entry point): check them here.
+        // flags[0] = some scan has more than 4095 rays (the fill pass then needs the hit atomic's return value)
+        // flags[1] = offsets inconsistent (hit_off[0] != 0, decreasing, or hit_off[n_scans] != total_hits)
+        const long long b = hit_off[s], e = hit_off[s + 1];
+        if (e - b > 4095) flags[0] = 1u;
+        if (e < b || (s == 0 && b != 0) || (s == n_scans - 1 && e != total_hits)) flags[1] = 1u;
+    }
 }
 
 // CHECK: some scan has more than 4095 rays, so a cell could collect more hits in one scan than
 // the 12-bit field holds; only then the hit atomic needs its return value.
 template <bool FILL, bool CHECK>
 __global__ void __launch_bounds__(256, 8) occ_fast_rays(const FastArgs a) {
+    if (a.small[kFlagBadOffsets]) return;                     // offsets checked on the device: the host reports the error
     if (FILL && ((unsigned long long)a.small[0] + 64ull > a.runs_cap ||
-                 (unsigned long long)a.small[4] * (unsigned long long)a.ord_stride > a.ord_cap))
-        return;                                               // speculative launch, buffers too small: the host repeats it
+                 (unsigned long long)a.small[4] * (unsigned long long)a.ord_stride > a.ord_cap ||
+                 (!CHECK && a.small[kFlagBigScan])))
+        return;                                               // speculative launch, buffers too small (or the CHECK variant is needed): the host repeats it
     const long long rl = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // chunk-relative ray
     const long long r = a.ray_begin + rl;
     const int lane = threadIdx.x & 31;
@@ -667,9 +680,12 @@ struct StageTimer {
 };
 
 // Returns ICPB200_OK, an error, or 1 when this chunk must take the ordered path instead.
+// [rb, re) are the chunk's rays; big_scan: 1 = some scan of the chunk has more than 4095 rays, 0 = none has,
+// -1 = the host does not know (the device flag kFlagBigScan decides; comes back with the totals).
+// *bad_offsets is set when the device-side check of the offsets failed (nothing was written then).
 static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_origins, const double* d_hits,
-                      const long long* d_hit_off, const long long* h_hit_off, cudaStream_t st) {
-    const long long rb = h_hit_off[s0], re = h_hit_off[s0 + cs];
+                      const long long* d_hit_off, long long rb, long long re, int big_scan_in, bool* bad_offsets,
+                      cudaStream_t st) {
     const long long nr = re - rb;
     if (nr == 0) return ICPB200_OK;
     const int tiles_x = (g.nx + TS - 1) / TS, tiles_y = (g.ny + TS - 1) / TS;
@@ -687,6 +703,7 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
         ICPB_CUDA(cudaStreamCreateWithPriority(&g.aux_stream, cudaStreamNonBlocking, prio_hi));
         ICPB_CUDA(cudaEventCreateWithFlags(&g.ev_fork, cudaEventDisableTiming));
         ICPB_CUDA(cudaEventCreateWithFlags(&g.ev_join, cudaEventDisableTiming));
+        ICPB_CUDA(cudaEventCreateWithFlags(&g.ev_hit, cudaEventDisableTiming));
     }
     unsigned* d_small = g.small.as<unsigned>();
     unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(g.small.as<unsigned char>() + 64);
@@ -722,11 +739,10 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
     tm.mark("count");
     occ_tile_scan<<<1, 1024, 0, st>>>(g.tile_count.as<unsigned>(), n_tiles, g.offsets.as<unsigned>(), g.class_off.as<unsigned>(), g.tile_flag.as<unsigned>(), g.items.as<uint2>(), g.multi.as<int>(), d_small);
     ICPB_LAUNCH_CHECK();
-    unsigned h_small[8];
+    unsigned h_small[40];
     tm.mark("scan");
     const int stride = (cs + 3) & ~3;
-    bool big_scan = false;
-    for (int s = s0; s < s0 + cs && !big_scan; ++s) big_scan = h_hit_off[s + 1] - h_hit_off[s] > 4095;
+    bool big_scan = big_scan_in > 0;
     auto launch_fill = [&]() -> int {
         ICPB_CUDA(cudaMemsetAsync(g.tile_count.p, 0, sizeof(unsigned) * kLenClasses * (size_t)n_tiles, st));
         a.ord = g.ord.as<unsigned>(); a.ord_stride = stride;
@@ -749,9 +765,13 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
     }
     ICPB_CUDA(cudaMemcpyAsync(h_small, d_small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
     ICPB_CUDA(cudaStreamSynchronize(st));
+    if (h_small[kFlagBadOffsets]) { *bad_offsets = true; return ICPB200_OK; }
+    const bool wrong_variant = big_scan_in < 0 && h_small[kFlagBigScan] != 0;      // the speculative fill left: it needs CHECK
+    if (wrong_variant) big_scan = true;
     const unsigned total_runs = h_small[0], n_slots = h_small[4];
     const size_t ord_words = (size_t)n_slots * stride;
-    const bool filled = speculative && (size_t)total_runs + 64 <= g.runs.cap / sizeof(uint4) && ord_words <= g.ord.cap / sizeof(unsigned);
+    const bool filled = speculative && !wrong_variant && (size_t)total_runs + 64 <= g.runs.cap / sizeof(uint4) &&
+                        ord_words <= g.ord.cap / sizeof(unsigned);
     if (ord_words > kOccOrdBudget) {
         // too many hit cells for the dense table: undo the claims, the ordered path takes the chunk
         if (n_slots) {
@@ -797,16 +817,23 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
         t.l_hit = g.l_hit; t.l_miss = g.l_miss; t.lo = lo; t.hi = hi;
         const unsigned n_items = h_small[1], n_multi = h_small[5];
         t.n_hit_items = h_small[6];
-        if (t.n_hit_items) {
-            t.item_first = 0u; t.item_end = t.n_hit_items; t.persistent = 1;
-            occ_fast_tiles<<<std::min<unsigned>(t.n_hit_items, (unsigned)g.fast_ctas), kTileNT, 0, st>>>(t);
-            ICPB_LAUNCH_CHECK();
-        }
-        tm.mark("tiles hit");
-        if (n_slots) {
-            // the hit cells' tables are complete: replay them on the second stream, under the remaining tiles
+        // Two launches side by side.  The tiles that hold hit cells go to the priority stream (persistent CTAs pulling
+        // from a queue, heaviest first) followed by the hit cells' replay; the other tiles go to the main stream, one
+        // item per CTA, and fill every SM slot the first launch leaves free -- its tail and the replay run underneath.
+        bool forked = false;
+        if (t.n_hit_items || n_slots) {
             ICPB_CUDA(cudaEventRecord(g.ev_fork, st));
             ICPB_CUDA(cudaStreamWaitEvent(g.aux_stream, g.ev_fork, 0));
+            forked = true;
+        }
+        if (t.n_hit_items) {
+            t.item_first = 0u; t.item_end = t.n_hit_items; t.persistent = 1;
+            occ_fast_tiles<<<std::min<unsigned>(t.n_hit_items, (unsigned)g.fast_ctas), kTileNT, 0, g.aux_stream>>>(t);
+            ICPB_LAUNCH_CHECK();
+            ICPB_CUDA(cudaEventRecord(g.ev_hit, g.aux_stream));
+        }
+        if (n_slots) {
+            // the hit cells' tables are complete once the hit tiles are done
             occ_fast_compact<<<(n_slots * 32u + 255u) / 256u, 256, 0, g.aux_stream>>>(g.ord.as<unsigned>(), g.ev.as<unsigned>(),
                                                                                       g.ev_count.as<unsigned>(), d_small, cs, stride);
             ICPB_LAUNCH_CHECK();
@@ -814,20 +841,22 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
                                                                              g.slot_cell.as<unsigned>(), g.ev.as<unsigned>(),
                                                                              g.ev_count.as<unsigned>(), d_small, stride, g.l_hit, g.l_miss, lo, hi);
             ICPB_LAUNCH_CHECK();
-            ICPB_CUDA(cudaEventRecord(g.ev_join, g.aux_stream));
             replayed = true;
         }
+        if (forked) ICPB_CUDA(cudaEventRecord(g.ev_join, g.aux_stream));
         if (n_items > t.n_hit_items) {
             t.item_first = t.n_hit_items; t.item_end = n_items; t.persistent = 0;
             occ_fast_tiles<<<n_items - t.n_hit_items, kTileNT, 0, st>>>(t);
             ICPB_LAUNCH_CHECK();
         }
+        tm.mark("tiles rest");
         if (n_multi) {
+            if (t.n_hit_items) ICPB_CUDA(cudaStreamWaitEvent(st, g.ev_hit, 0));       // pieces of a tile may sit in both launches
             occ_fast_apply_multi<<<n_multi * 4u, 256, 0, st>>>(t);
             ICPB_LAUNCH_CHECK();
         }
-        tm.mark("tiles rest");
-        if (replayed) ICPB_CUDA(cudaStreamWaitEvent(st, g.ev_join, 0));
+        tm.mark("apply multi");
+        if (forked) ICPB_CUDA(cudaStreamWaitEvent(st, g.ev_join, 0));
         tm.mark("join replay");
     }
     if (n_slots && !replayed) {                       // no tile runs at all: hits only
@@ -850,14 +879,30 @@ int occ_fast_ctas(int sm_count) {
     return sm_count * per_sm;
 }
 
+int occ_collect(OccGrid& g) {
+    if (!g.stats_pending) return ICPB200_OK;
+    g.stats_pending = false;
+    ICPB_CUDA(cudaEventSynchronize(g.ev_stats));
+    const unsigned long long* hs = reinterpret_cast<const unsigned long long*>(g.pending_host + 64);
+    for (int k = 1; k < 4; ++k) g.stats[k] = (long long)hs[k];
+    if (reinterpret_cast<const unsigned*>(g.pending_host)[3]) {
+        set_error("grid_update: more than 4095 hits landed in one cell within one scan of the previous update (unsupported)");
+        return ICPB200_ERR_LIMIT;
+    }
+    return ICPB200_OK;
+}
+
 int occ_update_fast(OccGrid& g, int n_scans, const double* d_origins, const double* d_hits,
-                    const long long* d_hit_off, const long long* h_hit_off, cudaStream_t st) {
-    const long long n_rays = h_hit_off[n_scans] - h_hit_off[0];
+                    const long long* d_hit_off, const long long* h_hit_off, long long total_hits, bool defer,
+                    cudaStream_t st) {
+    const long long n_rays = total_hits;
     g.stats[0] = n_rays; g.stats[1] = g.stats[2] = g.stats[3] = 0;
     if (n_rays <= 0) return ICPB200_OK;                                   // mapping.py:113-114
+    if (!h_hit_off && n_scans > kOccMaxChunkScans) { set_error("grid_update: host offsets needed for more than one chunk"); return ICPB200_ERR_ARG; }
     const int n_tiles = ((g.nx + TS - 1) / TS) * ((g.ny + TS - 1) / TS);
     const size_t n_cells = (size_t)g.nx * g.ny;
     const long long max_chunk_rays = [&] {
+        if (!h_hit_off) return n_rays;
         long long m = 0;
         for (int s0 = 0; s0 < n_scans; s0 += kOccMaxChunkScans)
             m = std::max(m, h_hit_off[std::min(n_scans, s0 + kOccMaxChunkScans)] - h_hit_off[s0]);
@@ -875,14 +920,41 @@ int occ_update_fast(OccGrid& g, int n_scans, const double* d_origins, const doub
         if (g.ncount.reserve(sizeof(unsigned) * n_cells)) return ICPB200_ERR_CUDA;
         ICPB_CUDA(cudaMemsetAsync(g.ncount.p, 0, sizeof(unsigned) * n_cells, st));
     }
+    if (defer && !g.pending_host) {
+        ICPB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g.pending_host), 256, cudaHostAllocDefault));
+        ICPB_CUDA(cudaEventCreateWithFlags(&g.ev_stats, cudaEventDisableTiming));
+    }
     ICPB_CUDA(cudaMemsetAsync(g.small.p, 0, 256, st));
-    occ_fast_origins<<<(n_scans + 255) / 256, 256, 0, st>>>(d_origins, n_scans, g.min_x, g.min_y, g.res, g.origin_cell.as<int2>());
+    occ_fast_origins<<<(n_scans + 255) / 256, 256, 0, st>>>(d_origins, n_scans, g.min_x, g.min_y, g.res, g.origin_cell.as<int2>(),
+                                                            d_hit_off, total_hits,
+                                                            h_hit_off ? nullptr : g.small.as<unsigned>() + kFlagBigScan);
     ICPB_LAUNCH_CHECK();
+    std::vector<long long> fetched;                                        // host copy of the offsets, if it is needed after all
     long long tot[4] = {0, 0, 0, 0};
+    bool all_fast = true;
     for (int s0 = 0; s0 < n_scans; s0 += kOccMaxChunkScans) {
         const int cs = std::min(kOccMaxChunkScans, n_scans - s0);
-        int rc = fast_chunk(g, n_scans, s0, cs, d_origins, d_hits, d_hit_off, h_hit_off, st);
+        long long rb = 0, re = n_rays;
+        int big = -1;
+        if (h_hit_off) {
+            rb = h_hit_off[s0]; re = h_hit_off[s0 + cs];
+            big = 0;
+            for (int s = s0; s < s0 + cs && !big; ++s) big = h_hit_off[s + 1] - h_hit_off[s] > 4095 ? 1 : 0;
+        }
+        bool bad_offsets = false;
+        int rc = fast_chunk(g, n_scans, s0, cs, d_origins, d_hits, d_hit_off, rb, re, big, &bad_offsets, st);
+        if (bad_offsets) {
+            set_error("grid_update: hit_off[0] must be 0, hit_off must not decrease and hit_off[n_scans] must equal total_hits");
+            return ICPB200_ERR_ARG;
+        }
         if (rc == 1) {
+            all_fast = false;
+            if (!h_hit_off) {                                              // single chunk, offsets checked on the device
+                fetched.resize((size_t)n_scans + 1);
+                ICPB_CUDA(cudaMemcpyAsync(fetched.data(), d_hit_off, sizeof(long long) * fetched.size(), cudaMemcpyDeviceToHost, st));
+                ICPB_CUDA(cudaStreamSynchronize(st));
+                h_hit_off = fetched.data();
+            }
             long long keep[4] = {g.stats[0], g.stats[1], g.stats[2], g.stats[3]};
             std::vector<long long> off((size_t)cs + 1);
             for (int k = 0; k <= cs; ++k) off[k] = h_hit_off[s0 + k] - h_hit_off[s0];
@@ -898,6 +970,14 @@ int occ_update_fast(OccGrid& g, int n_scans, const double* d_origins, const doub
             continue;
         }
         if (rc) return rc;
+        if (defer && all_fast && n_scans <= kOccMaxChunkScans) {
+            // the only chunk: statistics and the overflow flag are collected later (occ_collect)
+            ICPB_CUDA(cudaMemcpyAsync(g.pending_host, g.small.p, 256, cudaMemcpyDeviceToHost, st));
+            ICPB_CUDA(cudaEventRecord(g.ev_stats, st));
+            g.stats_pending = true;
+            g.seen_nonempty_scan = true;
+            return ICPB200_OK;
+        }
         unsigned char host_small[256];
         ICPB_CUDA(cudaMemcpyAsync(host_small, g.small.p, 256, cudaMemcpyDeviceToHost, st));
         ICPB_CUDA(cudaStreamSynchronize(st));

@@ -230,3 +230,66 @@ def test_randomised_configurations_match_the_oracle():
             gpu.update_scan(origins[s], clouds[s])
             ref.update_scan(origins[s], clouds[s], fast=True)
         assert_same(gpu, ref, f"case {case} after single scans")
+
+
+def test_device_resident_entry_point_is_stream_ordered_and_reports_late():
+    """icpb200_grid_update_dev (device pointers, caller's stream): same map as the oracle, statistics available after
+    the call, offsets that do not add up refused with nothing written, and the hit-field overflow -- detected on the
+    device after the call has returned -- reported by the next call on the grid."""
+    import torch
+    dev = torch.device("cuda", 0)
+    scans, poses = synth.make_sequence(120, world="campus", seed=3)
+    hits = [synth.to_world_frame(s, p) for s, p in zip(scans, poses)]
+    bounds = (poses[:, 0].mean() - 25.6, poses[:, 0].mean() + 25.6, poses[:, 1].mean() - 25.6, poses[:, 1].mean() + 25.6)
+    gpu, ref = make_pair(bounds, **GKW)
+    flat, off = synth.pack_ragged(hits)
+    org = poses[:, :2].copy()
+    d_org, d_hits, d_off = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (org, flat, off))
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+
+    class _Dev:                                       # the shim caches its host mirror: drop it after every device update
+        def update_dev(self, *a):
+            gpu._host = None
+            gpu._dev.update_dev(*a)
+    dev_entry = _Dev()
+    for rep in range(2):                              # the second call takes the speculative fill (buffers already sized)
+        dev_entry.update_dev(len(off) - 1, d_org.data_ptr(), d_hits.data_ptr(), d_off.data_ptr(), int(off[-1]), stream.cuda_stream)
+        cells = ref.update_many(org, flat, off, fast=True)
+        assert gpu._dev.last_stats()["traversed"] == cells
+        assert_same(gpu, ref, f"device-resident update {rep}")
+    # offsets that do not add up: refused, map untouched
+    bad = off.copy()
+    bad[5] = bad[4] - 1
+    d_bad = torch.from_numpy(bad).to(dev)
+    with pytest.raises(RuntimeError, match="hit_off"):
+        dev_entry.update_dev(len(off) - 1, d_org.data_ptr(), d_hits.data_ptr(), d_bad.data_ptr(), int(off[-1]), stream.cuda_stream)
+    with pytest.raises(RuntimeError, match="hit_off"):
+        dev_entry.update_dev(len(off) - 1, d_org.data_ptr(), d_hits.data_ptr(), d_off.data_ptr(), int(off[-1]) - 1, stream.cuda_stream)
+    assert_same(gpu, ref, "after the refused calls")
+    dev_entry.update_dev(len(off) - 1, d_org.data_ptr(), d_hits.data_ptr(), d_off.data_ptr(), int(off[-1]), stream.cuda_stream)
+    ref.update_many(org, flat, off, fast=True)
+    assert_same(gpu, ref, "the handle works after the refused calls")
+    # a scan with more than 4095 rays: the fill pass needs its checking variant (decided on the device)
+    big = np.column_stack([np.linspace(bounds[0] + 1, bounds[1] - 1, 6000), np.full(6000, bounds[2] + 2.0)])
+    o1 = np.array([[poses[0, 0], poses[0, 1]]])
+    boff = np.array([0, 6000], dtype=np.int64)
+    d_o1, d_big, d_boff = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (o1, big, boff))
+    dev_entry.update_dev(1, d_o1.data_ptr(), d_big.data_ptr(), d_boff.data_ptr(), 6000, stream.cuda_stream)
+    ref.update_many(o1, big, boff, fast=True)
+    assert_same(gpu, ref, "6000-ray scan")
+    # 5000 endpoints of one scan in one cell: reported late (by the next call), then the handle works again
+    pts = np.tile([[poses[0, 0] + 1.011, poses[0, 1] + 0.512]], (5000, 1))
+    d_pts = torch.from_numpy(pts).to(dev)
+    d_poff = torch.from_numpy(np.array([0, 5000], dtype=np.int64)).to(dev)
+    try:
+        dev_entry.update_dev(1, d_o1.data_ptr(), d_pts.data_ptr(), d_poff.data_ptr(), 5000, stream.cuda_stream)
+        with pytest.raises(RuntimeError, match="4095"):
+            gpu._dev.last_stats()
+    except RuntimeError as e:                         # the ordered path reports it at once
+        assert "4095" in str(e)
+    gpu.reset()
+    gpu.update_scan(o1[0], pts[:4095])
+    ref2 = oo.GridOracleC(*bounds, **GKW)
+    ref2.update_scan(o1[0], pts[:4095], fast=True)
+    assert_same(gpu, ref2, "after the overflow report")
