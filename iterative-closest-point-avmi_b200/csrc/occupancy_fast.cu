@@ -614,33 +614,120 @@ __global__ void __launch_bounds__(256) occ_fast_compact(unsigned* __restrict__ o
     if (lane == 0) ev_count[slot] = (unsigned)pos;
 }
 
-__global__ void __launch_bounds__(128) occ_fast_chain(float* __restrict__ grid, unsigned* __restrict__ slotmap,
-                                                      const unsigned* __restrict__ slot_cell, const unsigned* __restrict__ ev,
-                                                      const unsigned* __restrict__ ev_count, const unsigned* __restrict__ small,
-                                                      int stride, double l_hit, double l_miss, float lo, float hi) {
+// A hit cell that sits on a clamp bound usually stays there: walls are pinned high, each event adds more hits than
+// misses.  For an event of at most 8 adds starting AT a bound, the literal chain ends at x + m*l_hit + k*l_miss up to
+// the float rounding of each add (<= 8 * 2^-24 * (|bound| + 8 * max|l|)), so when that sum leaves the interval by more
+// than `margin` (4e-6 * (|bound| + 8 * max|l|), which also covers the float evaluation of the sum below) the clip
+// returns the bound again and the three-instruction-deep fp64 adds are skipped.  The longest event lists belong to
+// exactly such cells, and the longest list is the critical path of the whole replay.
+__device__ __forceinline__ float chain_event(float x, unsigned w, double l_hit, double l_miss, float lhf, float lmf,
+                                             float margin, float lo, float hi) {
+    const unsigned m = w >> 20, k = w & kMissMask;
+    if (m + k <= 8u) {
+        const float t = fmaf((float)m, lhf, (float)k * lmf);
+        if ((x == hi && t > margin) || (x == lo && t < -margin)) return x;
+    }
+    return lean_chain(x, m, k, l_hit, l_miss, lo, hi);
+}
+
+// One GROUP of kChainG lanes per hit cell.  The event list of a cell is cut into kChainG consecutive segments, one per
+// lane.  Lane 0 runs its segment from the cell's value; every other lane does not know its input yet and runs its
+// segment from BOTH ends of the clamp interval.  Every event is a monotone map of [lo, hi] into itself (a rounded add
+// never reorders two values, neither does the clip), so a segment is one too: when its two trajectories meet, its output
+// is that value whatever the input was -- and for wall and free cells they meet within a dozen events.  The group then
+// takes the output of its last such segment and replays only the segments behind it (usually none, or empty ones) in
+// order.  Exact (the literal adds are still what produces every value); the longest dependent chain of the replay drops
+// from the longest list (373 events on C4) to an eighth of it plus the unresolved tail.
+constexpr int kChainG = 8;
+static_assert(128 % kChainG == 0 && 32 % kChainG == 0, "groups must not straddle warps");
+
+__device__ __forceinline__ float chain_segment(float x, const uint4* __restrict__ row, int gb, int ge, int n, double l_hit,
+                                               double l_miss, float lhf, float lmf, float margin, float lo, float hi) {
+    for (int q = gb; q < ge; ++q) {
+        const uint4 w = __ldcs(row + q);
+        const int p = 4 * q;
+        x = chain_event(x, w.x, l_hit, l_miss, lhf, lmf, margin, lo, hi);
+        if (p + 1 < n) x = chain_event(x, w.y, l_hit, l_miss, lhf, lmf, margin, lo, hi);
+        if (p + 2 < n) x = chain_event(x, w.z, l_hit, l_miss, lhf, lmf, margin, lo, hi);
+        if (p + 3 < n) x = chain_event(x, w.w, l_hit, l_miss, lhf, lmf, margin, lo, hi);
+    }
+    return x;
+}
+
+__global__ void __launch_bounds__(128, 4) occ_fast_chain(float* __restrict__ grid, unsigned* __restrict__ slotmap,
+                                                         const unsigned* __restrict__ slot_cell, const unsigned* __restrict__ ev,
+                                                         const unsigned* __restrict__ ev_count, const unsigned* __restrict__ small,
+                                                         int stride, double l_hit, double l_miss, float lo, float hi) {
+    const unsigned full = 0xffffffffu;
     const unsigned n_slots = small[4];
-    const unsigned slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned slot = (blockIdx.x * blockDim.x + threadIdx.x) / kChainG;
+    const int lane = threadIdx.x & 31, j = lane % kChainG, base = lane - j;
     const bool valid = slot < n_slots;
     const unsigned cell = valid ? slot_cell[slot] : 0u;
     const int n = valid ? (int)ev_count[slot] : 0;
-    float x = valid ? grid[cell] : 0.f;
+    const float x0 = valid ? grid[cell] : 0.f;
+    const float lhf = (float)l_hit, lmf = (float)l_miss;
+    const float margin = 4e-6f * (fmaxf(fabsf(lo), fabsf(hi)) + 8.f * fmaxf(fabsf(lhf), fabsf(lmf))) * 1.0001f;
     const uint4* row = reinterpret_cast<const uint4*>(ev + (size_t)slot * stride);      // stride is a multiple of 4
-    const int maxn = (int)__reduce_max_sync(0xffffffffu, (unsigned)n);
-    uint4 w_next = n > 0 ? __ldcs(row) : make_uint4(0u, 0u, 0u, 0u);
-    for (int p = 0; p < maxn; p += 4) {
-        if (p < n) {
-            const uint4 w = w_next;
-            if (p + 4 < n) w_next = __ldcs(row + (p >> 2) + 1);          // fetched while this group is replayed
-            x = lean_chain(x, w.x >> 20, w.x & kMissMask, l_hit, l_miss, lo, hi);
-            if (p + 1 < n) x = lean_chain(x, w.y >> 20, w.y & kMissMask, l_hit, l_miss, lo, hi);
-            if (p + 2 < n) x = lean_chain(x, w.z >> 20, w.z & kMissMask, l_hit, l_miss, lo, hi);
-            if (p + 3 < n) x = lean_chain(x, w.w >> 20, w.w & kMissMask, l_hit, l_miss, lo, hi);
+    // segments in units of four events (one 16-byte load); short lists stay with lane 0
+    const int quads = (n + 3) >> 2;
+    const int per = quads <= 4 ? quads : (quads + kChainG - 1) / kChainG;
+    const int gb = min(j * per, quads), ge = min(gb + per, quads);
+    // x0 must lie inside the clamp interval for the two-ended argument (it does: the interval contains 0 on this path
+    // and every earlier update ended with the clip); a value outside is replayed by lane 0 alone
+    const bool solo = !(x0 >= lo && x0 <= hi);
+    float a = j == 0 ? x0 : lo, b = j == 0 ? x0 : hi;
+    const int my_gb = solo ? (j == 0 ? 0 : quads) : gb, my_ge = solo ? quads : ge;
+    const int steps = (int)__reduce_max_sync(full, (unsigned)(my_ge - my_gb));
+    uint4 w_next = my_gb < my_ge ? __ldcs(row + my_gb) : make_uint4(0u, 0u, 0u, 0u);
+    for (int q = 0; q < steps; ++q) {
+        const int g4 = my_gb + q;
+        const bool act = g4 < my_ge;
+        const uint4 w = w_next;
+        if (g4 + 1 < my_ge) w_next = __ldcs(row + g4 + 1);                       // fetched while this group is replayed
+        const int p = 4 * g4;
+        const bool two = act && __float_as_uint(a) != __float_as_uint(b);
+        const bool any_two = __any_sync(full, two);
+        if (act) {
+            a = chain_event(a, w.x, l_hit, l_miss, lhf, lmf, margin, lo, hi);
+            if (p + 1 < n) a = chain_event(a, w.y, l_hit, l_miss, lhf, lmf, margin, lo, hi);
+            if (p + 2 < n) a = chain_event(a, w.z, l_hit, l_miss, lhf, lmf, margin, lo, hi);
+            if (p + 3 < n) a = chain_event(a, w.w, l_hit, l_miss, lhf, lmf, margin, lo, hi);
+        }
+        if (any_two) {
+            if (two) {
+                b = chain_event(b, w.x, l_hit, l_miss, lhf, lmf, margin, lo, hi);
+                if (p + 1 < n) b = chain_event(b, w.y, l_hit, l_miss, lhf, lmf, margin, lo, hi);
+                if (p + 2 < n) b = chain_event(b, w.z, l_hit, l_miss, lhf, lmf, margin, lo, hi);
+                if (p + 3 < n) b = chain_event(b, w.w, l_hit, l_miss, lhf, lmf, margin, lo, hi);
+            } else if (act) {
+                b = a;
+            }
+        } else if (act) {
+            b = a;
         }
     }
-    if (valid) {
+    // the last segment whose output does not depend on its input (lane 0 always qualifies: it knew its input)
+    const bool met = __float_as_uint(a) == __float_as_uint(b);
+    const unsigned met_mask = (__ballot_sync(full, met) >> base) & ((1u << kChainG) - 1u);
+    const int last = 31 - __clz((int)(met_mask | 1u));
+    float x = __shfl_sync(full, a, base + last);
+#pragma unroll 1
+    for (int jj = 1; jj < kChainG; ++jj) {
+        // segments behind `last` are replayed in order from the value that reaches them
+        if (j == jj && jj > last && my_gb < my_ge)
+            a = chain_segment(x, row, my_gb, my_ge, n, l_hit, l_miss, lhf, lmf, margin, lo, hi);
+        const float y = __shfl_sync(full, a, base + jj);
+        if (jj > last && __shfl_sync(full, (int)(my_gb < my_ge), base + jj)) x = y;
+    }
+    if (valid && j == 0) {
         grid[cell] = x;
         slotmap[cell] = kNone;
     }
+}
+
+static inline unsigned chain_blocks(unsigned n_slots) {
+    return (unsigned)(((unsigned long long)n_slots * kChainG + 127ull) / 128ull);
 }
 
 }  // namespace
@@ -657,6 +744,16 @@ struct StageTimer {
         static const bool want = getenv("ICPB200_OCC_TIMING") != nullptr;
         on = want; st = s;
     }
+    // events on the second stream, reported relative to the main stream's mark `ref` ("fill")
+    cudaEvent_t aux_ev[4];
+    const char* aux_name[4];
+    int n_aux = 0, ref = 0;
+    void mark_aux(const char* what, cudaStream_t aux) {
+        if (!on || n_aux >= 4) return;
+        cudaEventCreate(&aux_ev[n_aux]);
+        cudaEventRecord(aux_ev[n_aux], aux);
+        aux_name[n_aux++] = what;
+    }
     void mark(const char* what) {
         if (!on || n >= 12) return;
         cudaEventCreate(&ev[n]);
@@ -671,6 +768,14 @@ struct StageTimer {
             cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
             fprintf(stderr, "[occ stage] %-12s %8.1f us\n", name[i], ms * 1e3f);
         }
+        for (int i = 0; i < n_aux; ++i) {
+            float ms = 0.f;
+            cudaEventSynchronize(aux_ev[i]);
+            cudaEventElapsedTime(&ms, ev[ref], aux_ev[i]);
+            fprintf(stderr, "[occ stage]   second stream: %-12s done %8.1f us after %s\n", aux_name[i], ms * 1e3f, name[ref]);
+            cudaEventDestroy(aux_ev[i]);
+        }
+        n_aux = 0;
         float tot = 0.f;
         if (n > 1) cudaEventElapsedTime(&tot, ev[0], ev[n - 1]);
         fprintf(stderr, "[occ stage] %-12s %8.1f us\n", "total", tot * 1e3f);
@@ -777,7 +882,7 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
         if (n_slots) {
             if (g.ev_count.reserve(sizeof(unsigned) * (size_t)n_slots)) return ICPB200_ERR_CUDA;
             ICPB_CUDA(cudaMemsetAsync(g.ev_count.p, 0, sizeof(unsigned) * (size_t)n_slots, st));
-            occ_fast_chain<<<(n_slots + 127u) / 128u, 128, 0, st>>>(g.grid.as<float>(), g.slotmap.as<unsigned>(),
+            occ_fast_chain<<<chain_blocks(n_slots), 128, 0, st>>>(g.grid.as<float>(), g.slotmap.as<unsigned>(),
                                                                     g.slot_cell.as<unsigned>(), nullptr, g.ev_count.as<unsigned>(), d_small,
                                                                     0, g.l_hit, g.l_miss, (float)g.lo_min, (float)g.lo_max);
             ICPB_LAUNCH_CHECK();
@@ -799,6 +904,7 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
         if (rc) return rc;
     }
     tm.mark("fill");
+    tm.ref = tm.n - 1;
     const float lo = (float)g.lo_min, hi = (float)g.lo_max;
     bool replayed = false;
     if (total_runs) {
@@ -831,16 +937,19 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
             occ_fast_tiles<<<std::min<unsigned>(t.n_hit_items, (unsigned)g.fast_ctas), kTileNT, 0, g.aux_stream>>>(t);
             ICPB_LAUNCH_CHECK();
             ICPB_CUDA(cudaEventRecord(g.ev_hit, g.aux_stream));
+            tm.mark_aux("hit tiles", g.aux_stream);
         }
         if (n_slots) {
             // the hit cells' tables are complete once the hit tiles are done
             occ_fast_compact<<<(n_slots * 32u + 255u) / 256u, 256, 0, g.aux_stream>>>(g.ord.as<unsigned>(), g.ev.as<unsigned>(),
                                                                                       g.ev_count.as<unsigned>(), d_small, cs, stride);
             ICPB_LAUNCH_CHECK();
-            occ_fast_chain<<<(n_slots + 127u) / 128u, 128, 0, g.aux_stream>>>(g.grid.as<float>(), g.slotmap.as<unsigned>(),
+            tm.mark_aux("compact", g.aux_stream);
+            occ_fast_chain<<<chain_blocks(n_slots), 128, 0, g.aux_stream>>>(g.grid.as<float>(), g.slotmap.as<unsigned>(),
                                                                              g.slot_cell.as<unsigned>(), g.ev.as<unsigned>(),
                                                                              g.ev_count.as<unsigned>(), d_small, stride, g.l_hit, g.l_miss, lo, hi);
             ICPB_LAUNCH_CHECK();
+            tm.mark_aux("chain", g.aux_stream);
             replayed = true;
         }
         if (forked) ICPB_CUDA(cudaEventRecord(g.ev_join, g.aux_stream));
@@ -863,7 +972,7 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
         occ_fast_compact<<<(n_slots * 32u + 255u) / 256u, 256, 0, st>>>(g.ord.as<unsigned>(), g.ev.as<unsigned>(),
                                                                         g.ev_count.as<unsigned>(), d_small, cs, stride);
         ICPB_LAUNCH_CHECK();
-        occ_fast_chain<<<(n_slots + 127u) / 128u, 128, 0, st>>>(g.grid.as<float>(), g.slotmap.as<unsigned>(),
+        occ_fast_chain<<<chain_blocks(n_slots), 128, 0, st>>>(g.grid.as<float>(), g.slotmap.as<unsigned>(),
                                                                 g.slot_cell.as<unsigned>(), g.ev.as<unsigned>(),
                                                                 g.ev_count.as<unsigned>(), d_small, stride, g.l_hit, g.l_miss, lo, hi);
         ICPB_LAUNCH_CHECK();
