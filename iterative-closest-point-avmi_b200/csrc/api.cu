@@ -89,6 +89,7 @@ static int init_locked(int device) {
     for (int i = 0; i < kUploadChunks; ++i) {
         ICPB_CUDA(cudaEventCreateWithFlags(&c.chunk_ev[i], cudaEventDisableTiming));
         ICPB_CUDA(cudaEventCreateWithFlags(&c.chunk_done[i], cudaEventDisableTiming));
+        ICPB_CUDA(cudaEventCreateWithFlags(&c.group_done[i], cudaEventDisableTiming));
         ICPB_CUDA(cudaStreamCreateWithFlags(&c.chunk_stream[i], cudaStreamNonBlocking));
     }
     ICPB_CUDA(cudaEventCreateWithFlags(&c.fork_ev, cudaEventDisableTiming));
@@ -165,6 +166,10 @@ static int make_cloud_set(Context& c, int slot, const DevClouds& d, int dim, boo
 struct UploadPlan {
     int n_chunks;
     int first[kUploadChunks + 1];              // cloud ranges
+    // pairs grouped by the last chunk they need (group g: both clouds have arrived once chunk g has): the bulk launch of
+    // group g runs on chunk g's stream right after its K1 / K2, under the uploads and per-cloud kernels of later chunks
+    int group_first[kUploadChunks + 1];        // ranges of the ordered pair list
+    const int* d_order;                        // device: ordered pair list, nullptr = the pairs are grouped as they come
 };
 
 static int voxel_set(Context& c, const CloudSet& cs, const DevClouds& d, int dim, double voxel, cudaStream_t st) {
@@ -222,7 +227,7 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
         set_error("icp: %zu bytes of shared memory needed, device allows %d", smem, c.max_smem_optin);
         return ICPB200_ERR_LIMIT;
     }
-    if (c.queue.reserve(4 * sizeof(unsigned)) || c.stats.reserve(16 * sizeof(unsigned long long))) return ICPB200_ERR_CUDA;
+    if (c.queue.reserve(16 * sizeof(unsigned)) || c.stats.reserve(16 * sizeof(unsigned long long))) return ICPB200_ERR_CUDA;
     a.queue = c.queue.as<unsigned>();
     // two-phase schedule (see icp_kernel.h): worthwhile once the batch fills the machine
     const int kPhaseCap = 12;                                    // flat between 8 and 16 on C2 (profiles/README.md)
@@ -247,7 +252,7 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
     }
     a.stats = c.stats.as<unsigned long long>();
     a.trace_match = tr.match; a.trace_iters = tr.iters; a.trace_stride = tr.stride;
-    ICPB_CUDA(cudaMemsetAsync(a.queue, 0, 4 * sizeof(unsigned), st));
+    ICPB_CUDA(cudaMemsetAsync(a.queue, 0, 16 * sizeof(unsigned), st));
     ICPB_CUDA(cudaMemsetAsync(a.stats, 0, 16 * sizeof(unsigned long long), st));
     ICPB_CUDA(cudaMemsetAsync(a.s.used, 0, 2 * (size_t)s.n_clouds, st));
     if (!same_set) ICPB_CUDA(cudaMemsetAsync(a.t.used, 0, 2 * (size_t)t.n_clouds, st));
@@ -255,6 +260,7 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
     if ((rc = launch_mark_used(a, p2l || grid, st))) return rc;
     ICPB_CUDA(cudaEventRecord(c.ev[0], st));
     const bool chunked = plan && same_set && !grid && s.set_max <= ICPB200_BRUTE_MAX_POINTS;
+    bool bulk_done = false;                        // chunked: the bulk launches went out per upload chunk
     if (plan && !chunked)
         for (int ch = 0; ch < plan->n_chunks; ++ch) ICPB_CUDA(cudaStreamWaitEvent(st, c.chunk_ev[ch], 0));
     if (chunked) {
@@ -263,6 +269,7 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
         // each chunk's kernels go to their own stream: a quarter of the clouds does not fill the GPU, so the
         // chunks' kernels must be able to run side by side (and under the copies still in flight)
         ICPB_CUDA(cudaEventRecord(c.fork_ev, st));                 // flags from mark_used
+        const int per_sm_g = icp_max_ctas_per_sm(k.dim, grid, smem);
         for (int ch = 0; ch < plan->n_chunks; ++ch) {
             const int first = plan->first[ch], count = plan->first[ch + 1] - first;
             cudaStream_t cs_ = c.chunk_stream[ch];
@@ -271,8 +278,21 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
             if ((rc = launch_voxel_clouds(a.s, k.dim, k.voxel_size, sort_pad, cs_, first, count))) return rc;
             if (p2l && (rc = launch_normals(a.t, a.cap_t, k.normal_k, k.voxel_size, cs_, first, count))) return rc;
             ICPB_CUDA(cudaEventRecord(c.chunk_done[ch], cs_));
-            ICPB_CUDA(cudaStreamWaitEvent(st, c.chunk_done[ch], 0));
+            // the pairs whose clouds are complete with this chunk: bulk launch on the chunk's stream
+            const int g_pairs = plan->group_first[ch + 1] - plan->group_first[ch];
+            if (g_pairs > 0) {
+                for (int prev = 0; prev < ch; ++prev) ICPB_CUDA(cudaStreamWaitEvent(cs_, c.chunk_done[prev], 0));
+                IcpArgs ga = a;
+                ga.n_pairs = g_pairs;
+                ga.pair_first = plan->group_first[ch];
+                ga.pair_order = plan->d_order;
+                ga.queue = a.queue + 4 + ch;
+                if ((rc = launch_icp_pairs(ga, k.dim, grid, std::min(g_pairs, c.sm_count * per_sm_g), smem, cs_))) return rc;
+            }
+            ICPB_CUDA(cudaEventRecord(c.group_done[ch], cs_));
+            ICPB_CUDA(cudaStreamWaitEvent(st, c.group_done[ch], 0));
         }
+        bulk_done = true;
         ICPB_CUDA(cudaEventRecord(c.ev[1], st));
     } else {
         if ((rc = voxel_set(c, a.s, s, k.dim, k.voxel_size, st))) return rc;
@@ -324,7 +344,7 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
     const int n_ctas = std::min(n_pairs, c.sm_count * per_sm);
     c.last_icp_stream = st;
     if (args_out) *args_out = a;
-    if ((rc = launch_icp_pairs(a, k.dim, grid, n_ctas, smem, st))) return rc;
+    if (!bulk_done && (rc = launch_icp_pairs(a, k.dim, grid, n_ctas, smem, st))) return rc;
     if (two_phase) {
         // the handed-over pairs: one CTA per SM (shared memory request above half an SM forces it)
         IcpArgs b = a;
@@ -402,7 +422,7 @@ void icpb200_shutdown(void) {
     if (!c.ready) return;
     cudaSetDevice(c.device);
     cudaStreamSynchronize(c.stream);
-    DevBuf* bufs[] = {&c.pts_a, &c.pts_b, &c.off_a, &c.off_b, &c.idx_a, &c.idx_b, &c.rinit, &c.tinit, &c.out_r,
+    DevBuf* bufs[] = {&c.pts_a, &c.pts_b, &c.off_a, &c.off_b, &c.idx_a, &c.idx_b, &c.idx_order, &c.rinit, &c.tinit, &c.out_r,
                       &c.out_t, &c.out_err, &c.out_prev, &c.out_iters, &c.out_status, &c.queue, &c.trace, &c.stats,
                       &c.aux_ds[0], &c.aux_ds[1], &c.aux_n[0], &c.aux_n[1], &c.aux_box[0], &c.aux_box[1],
                       &c.aux_nrm[0], &c.aux_nrm[1], &c.aux_flags[0], &c.aux_flags[1], &c.vox_in, &c.vox_out,
@@ -413,6 +433,7 @@ void icpb200_shutdown(void) {
     for (int i = 0; i < kUploadChunks; ++i) {
         if (c.chunk_ev[i]) { cudaEventDestroy(c.chunk_ev[i]); c.chunk_ev[i] = nullptr; }
         if (c.chunk_done[i]) { cudaEventDestroy(c.chunk_done[i]); c.chunk_done[i] = nullptr; }
+        if (c.group_done[i]) { cudaEventDestroy(c.group_done[i]); c.group_done[i] = nullptr; }
         if (c.chunk_stream[i]) { cudaStreamDestroy(c.chunk_stream[i]); c.chunk_stream[i] = nullptr; }
     }
     if (c.fork_ev) { cudaEventDestroy(c.fork_ev); c.fork_ev = nullptr; }
@@ -514,9 +535,33 @@ int icpb200_icp_pairs(int n_clouds, int dim, const double* pts, const int64_t* c
     const double *d_Ri, *d_ti;
     if ((rc = upload_init(c, n_pairs, dim, R_init, t_init, &d_Ri, &d_ti))) return rc;
     long long max_src = 0, max_tgt = 0;
+    // pairs by the last upload chunk they need (see UploadPlan)
+    std::vector<int> group((size_t)n_pairs);
+    int count[kUploadChunks + 1] = {};
+    bool grouped = true;
     for (int p = 0; p < n_pairs; ++p) {
         max_src = std::max<long long>(max_src, cloud_off[src_idx[p] + 1] - cloud_off[src_idx[p]]);
         max_tgt = std::max<long long>(max_tgt, cloud_off[tgt_idx[p] + 1] - cloud_off[tgt_idx[p]]);
+        const int last = std::max(src_idx[p], tgt_idx[p]);
+        int g = 0;
+        while (g + 1 < plan.n_chunks && last >= plan.first[g + 1]) ++g;
+        group[(size_t)p] = g;
+        ++count[g + 1];
+        if (p > 0 && g < group[(size_t)p - 1]) grouped = false;
+    }
+    plan.group_first[0] = 0;
+    for (int g = 0; g < kUploadChunks; ++g) plan.group_first[g + 1] = plan.group_first[g] + count[g + 1];
+    plan.d_order = nullptr;
+    std::vector<int> order;
+    if (!grouped) {
+        order.resize((size_t)n_pairs);
+        int cursor[kUploadChunks];
+        for (int g = 0; g < kUploadChunks; ++g) cursor[g] = plan.group_first[g];
+        for (int p = 0; p < n_pairs; ++p) order[(size_t)cursor[group[(size_t)p]]++] = p;
+        if (c.idx_order.reserve(sizeof(int) * (size_t)n_pairs)) return ICPB200_ERR_CUDA;
+        // pageable source: the copy is staged before the call returns, `order` may go out of scope afterwards
+        ICPB_CUDA(cudaMemcpyAsync(c.idx_order.p, order.data(), sizeof(int) * (size_t)n_pairs, cudaMemcpyHostToDevice, c.stream));
+        plan.d_order = c.idx_order.as<int>();
     }
     const DevClouds s{c.pts_a.as<double>(), c.off_a.as<long long>(), cloud_off, n_clouds, max_src, max_pts, (long long)np};
     const DevClouds t{c.pts_a.as<double>(), c.off_a.as<long long>(), cloud_off, n_clouds, max_tgt, max_pts, (long long)np};

@@ -49,10 +49,10 @@ struct Context {
     int max_smem_optin = 0;
     cudaStream_t stream = nullptr;     // library-owned stream for the host-buffer entry points
     cudaStream_t copy_stream = nullptr;                        // chunked cloud uploads of icpb200_icp_pairs
-    cudaEvent_t chunk_ev[kUploadChunks] = {}, chunk_done[kUploadChunks] = {}, fork_ev = nullptr;
+    cudaEvent_t chunk_ev[kUploadChunks] = {}, chunk_done[kUploadChunks] = {}, group_done[kUploadChunks] = {}, fork_ev = nullptr;
     cudaStream_t chunk_stream[kUploadChunks] = {};              // K1/K2 of upload chunk k
     // ICP staging (host-buffer entry points)
-    DevBuf pts_a, pts_b, off_a, off_b, idx_a, idx_b, rinit, tinit;
+    DevBuf pts_a, pts_b, off_a, off_b, idx_a, idx_b, idx_order, rinit, tinit;
     DevBuf out_r, out_t, out_err, out_prev, out_iters, out_status, queue, trace, stats;
     // preprocessed form of cloud sets A and B (see CloudSet in icp_kernel.h)
     DevBuf aux_ds[2], aux_n[2], aux_box[2], aux_nrm[2], aux_flags[2];

@@ -1287,7 +1287,9 @@ __global__ void __launch_bounds__(kNT, MINB) icp_pairs_kernel(const IcpArgs a) {
         if (tid == 0) {
             const unsigned q = atomicAdd(a.queue, 1u);
             const unsigned limit = a.resume ? *a.cont_count : (unsigned)a.n_pairs;
-            sh.pair = q < limit ? (a.resume ? (unsigned)a.cont_list[q] : q) : 0xffffffffu;
+            sh.pair = q < limit ? (a.resume ? (unsigned)a.cont_list[q]
+                                            : (a.pair_order ? (unsigned)a.pair_order[a.pair_first + q] : (unsigned)a.pair_first + q))
+                                : 0xffffffffu;
             sh.bcast_i[2] = (int)q;                 // continuation slot when resuming
         }
         __syncthreads();

@@ -67,6 +67,10 @@ struct IcpArgs {
     int cap_s, cap_t;          // multiples of 32, >= largest raw cloud of each set
     int sort_pad;              // power of two >= largest raw cloud, >= 256
     unsigned int* queue;       // zeroed before launch
+    // a launch may cover only the pairs order[pair_first .. pair_first + n_pairs) (order == nullptr: the identity):
+    // the host-buffer entry point registers the pairs of an upload chunk while the next chunk is still on its way
+    int pair_first;
+    const int* pair_order;
     unsigned long long* stats; // [0] fp32 sweep pair evaluations executed, [1] points re-decided by the
                                // full fp64 scan, [2] iterations, [3] source points swept, [4] source points
                                // whose correspondence was carried over by the movement bound; may be nullptr
