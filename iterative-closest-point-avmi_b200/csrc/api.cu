@@ -373,13 +373,28 @@ static int check_offsets(const int64_t* off, int n, const char* what, long long*
 struct IcpOutputs { double* R; double* t; double* err; double* prev; int32_t* iters; int32_t* status; };
 
 static int fetch_outputs(Context& c, int n_pairs, int dim, const IcpOutputs& o) {
-    ICPB_CUDA(cudaMemcpyAsync(o.R, c.out_r.p, sizeof(double) * dim * dim * (size_t)n_pairs, cudaMemcpyDeviceToHost, c.stream));
-    ICPB_CUDA(cudaMemcpyAsync(o.t, c.out_t.p, sizeof(double) * dim * (size_t)n_pairs, cudaMemcpyDeviceToHost, c.stream));
-    ICPB_CUDA(cudaMemcpyAsync(o.err, c.out_err.p, sizeof(double) * (size_t)n_pairs, cudaMemcpyDeviceToHost, c.stream));
-    if (o.prev) ICPB_CUDA(cudaMemcpyAsync(o.prev, c.out_prev.p, sizeof(double) * (size_t)n_pairs, cudaMemcpyDeviceToHost, c.stream));
-    ICPB_CUDA(cudaMemcpyAsync(o.iters, c.out_iters.p, sizeof(int) * (size_t)n_pairs, cudaMemcpyDeviceToHost, c.stream));
-    ICPB_CUDA(cudaMemcpyAsync(o.status, c.out_status.p, sizeof(int) * (size_t)n_pairs, cudaMemcpyDeviceToHost, c.stream));
+    // The caller's arrays are pageable: six device-to-pageable copies would each go through the driver's bounce buffer
+    // and block.  The results land in one page-locked staging block instead (asynchronous, one wait) and are copied
+    // out by the host.
+    const size_t np = (size_t)n_pairs;
+    const size_t bytes[6] = {sizeof(double) * dim * dim * np, sizeof(double) * dim * np, sizeof(double) * np,
+                             o.prev ? sizeof(double) * np : 0, sizeof(int) * np, sizeof(int) * np};
+    const void* src[6] = {c.out_r.p, c.out_t.p, c.out_err.p, c.out_prev.p, c.out_iters.p, c.out_status.p};
+    void* dst[6] = {o.R, o.t, o.err, o.prev, o.iters, o.status};
+    size_t at[6], total = 0;
+    for (int k = 0; k < 6; ++k) { at[k] = total; total += (bytes[k] + 63) & ~(size_t)63; }
+    if (total > c.h_stage_cap) {
+        if (c.h_stage) { cudaFreeHost(c.h_stage); c.h_stage = nullptr; c.h_stage_cap = 0; }
+        const size_t cap = std::max<size_t>(total + total / 2, 1u << 16);
+        ICPB_CUDA(cudaHostAlloc(&c.h_stage, cap, cudaHostAllocDefault));
+        c.h_stage_cap = cap;
+    }
+    unsigned char* stage = static_cast<unsigned char*>(c.h_stage);
+    for (int k = 0; k < 6; ++k)
+        if (bytes[k]) ICPB_CUDA(cudaMemcpyAsync(stage + at[k], src[k], bytes[k], cudaMemcpyDeviceToHost, c.stream));
     ICPB_CUDA(cudaStreamSynchronize(c.stream));
+    for (int k = 0; k < 6; ++k)
+        if (bytes[k]) memcpy(dst[k], stage + at[k], bytes[k]);
     return ICPB200_OK;
 }
 
@@ -437,6 +452,7 @@ void icpb200_shutdown(void) {
         if (c.chunk_stream[i]) { cudaStreamDestroy(c.chunk_stream[i]); c.chunk_stream[i] = nullptr; }
     }
     if (c.fork_ev) { cudaEventDestroy(c.fork_ev); c.fork_ev = nullptr; }
+    if (c.h_stage) { cudaFreeHost(c.h_stage); c.h_stage = nullptr; c.h_stage_cap = 0; }
     if (c.copy_stream) { cudaStreamDestroy(c.copy_stream); c.copy_stream = nullptr; }
     cudaStreamDestroy(c.stream);
     c.stream = nullptr;

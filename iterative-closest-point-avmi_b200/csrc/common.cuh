@@ -59,6 +59,8 @@ struct Context {
     // big-cloud path: radix-sort scratch and hash grids
     DevBuf big_keys, big_idx, grid_start, grid_items, grid_cell, grid_desc, grid_off, grid_buckets;
     DevBuf cont_cur, cont_match, cont_d2lb, cont_moved, cont_scalar, cont_list;
+    void* h_stage = nullptr;           // page-locked staging for the result read-back (one wait, then host copies)
+    size_t h_stage_cap = 0;
     cudaStream_t last_icp_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // K1 start | K2 start | K3 start | K3 end
     // voxel_downsample entry point

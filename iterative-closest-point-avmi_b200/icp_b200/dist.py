@@ -112,18 +112,23 @@ def grid_device_tensor(device_grid):
                            device=torch.device("cuda", torch.cuda.current_device()))
 
 
-def grid_allreduce_device(device_grid):
+def grid_allreduce_device(device_grid, sync=True):
     """Reassemble the sharded grid on every rank, in place on the device (NCCL, B200 box): an all_gather of the
-    strips when they are equally tall (each rank sends only its own rows), else an all_reduce(SUM)."""
+    strips when they are equally tall (each rank sends only its own rows), else an all_reduce(SUM).
+
+    sync=False leaves everything stream-ordered on torch's current stream (the caller ran the update on that
+    stream -- icpb200_grid_update_dev -- and reads the result on it): no host wait on either side."""
     rank, size = world()
     if size > 1:
         t = grid_device_tensor(device_grid)
         ny = t.shape[0]
         rows = [strip_rows(ny, r, size) for r in range(size)]
-        torch.cuda.synchronize()
+        if sync:
+            torch.cuda.synchronize()
         if len({hi - lo for lo, hi in rows}) == 1 and rows[-1][1] == ny:
             lo, hi = rows[rank]
             dist.all_gather_into_tensor(t, t[lo:hi])
         else:
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        torch.cuda.synchronize()
+        if sync:
+            torch.cuda.synchronize()
