@@ -251,7 +251,7 @@ def cpu_raycast_baseline(origins, flat, off, n_sample):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the round's `ncu --set full` captures of this command
 # (profiles/r01_ncu_icp_final.txt, profiles/r01_ncu_occ_final.txt); the occupancy figure is the sum over the update's kernels
-NCU_DRAM_BYTES = dict(icp_pairs_kernel=55.2e6 + 7.3e6, occupancy_update=651e6,
+NCU_DRAM_BYTES = dict(icp_pairs_kernel=52.4e6 + 7.3e6, occupancy_update=645e6,
                       source="ncu --set full, profiles/r01_ncu_icp_final.txt / r01_ncu_occ_final.txt (C2 / C4, round 1)")
 
 
@@ -653,7 +653,7 @@ def bench_extras(args, api):
     srcs = [d - d.mean(axis=0) for d in ds[:n]]
     tgts = ds[1:n + 1]
     angles = np.deg2rad(np.arange(-180, 180, 1.5))
-    api.rotation_scores(srcs[:8], tgts[:8], [angles] * 8, [t.mean(axis=0) for t in tgts[:8]])
+    api.rotation_scores(srcs, tgts, [angles] * n, [t.mean(axis=0) for t in tgts])     # warm: buffers grow to the batch's size
     t0 = time.perf_counter()
     sc = api.rotation_scores(srcs, tgts, [angles] * n, [t.mean(axis=0) for t in tgts])
     dt = time.perf_counter() - t0
