@@ -638,8 +638,6 @@ __device__ __forceinline__ float chain_event(float x, unsigned w, double l_hit, 
 // takes the output of its last such segment and replays only the segments behind it (usually none, or empty ones) in
 // order.  Exact (the literal adds are still what produces every value); the longest dependent chain of the replay drops
 // from the longest list (373 events on C4) to an eighth of it plus the unresolved tail.
-constexpr int kChainG = 8;
-static_assert(128 % kChainG == 0 && 32 % kChainG == 0, "groups must not straddle warps");
 
 __device__ __forceinline__ float chain_segment(float x, const uint4* __restrict__ row, int gb, int ge, int n, double l_hit,
                                                double l_miss, float lhf, float lmf, float margin, float lo, float hi) {
@@ -654,10 +652,12 @@ __device__ __forceinline__ float chain_segment(float x, const uint4* __restrict_
     return x;
 }
 
+template <int kChainG>
 __global__ void __launch_bounds__(128, 4) occ_fast_chain(float* __restrict__ grid, unsigned* __restrict__ slotmap,
                                                          const unsigned* __restrict__ slot_cell, const unsigned* __restrict__ ev,
                                                          const unsigned* __restrict__ ev_count, const unsigned* __restrict__ small,
                                                          int stride, double l_hit, double l_miss, float lo, float hi) {
+    static_assert(128 % kChainG == 0 && 32 % kChainG == 0, "groups must not straddle warps");
     const unsigned full = 0xffffffffu;
     const unsigned n_slots = small[4];
     const unsigned slot = (blockIdx.x * blockDim.x + threadIdx.x) / kChainG;
@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(128, 4) occ_fast_chain(float* __restrict__ gri
     }
     // the last segment whose output does not depend on its input (lane 0 always qualifies: it knew its input)
     const bool met = __float_as_uint(a) == __float_as_uint(b);
-    const unsigned met_mask = (__ballot_sync(full, met) >> base) & ((1u << kChainG) - 1u);
+    const unsigned met_mask = (__ballot_sync(full, met) >> base) & (kChainG == 32 ? 0xffffffffu : ((1u << (kChainG & 31)) - 1u));
     const int last = 31 - __clz((int)(met_mask | 1u));
     float x = __shfl_sync(full, a, base + last);
 #pragma unroll 1
@@ -726,8 +726,15 @@ __global__ void __launch_bounds__(128, 4) occ_fast_chain(float* __restrict__ gri
     }
 }
 
-static inline unsigned chain_blocks(unsigned n_slots) {
-    return (unsigned)(((unsigned long long)n_slots * kChainG + 127ull) / 128ull);
+// group size: 4 and 8 lanes per cell measure the same on C4 (696 us per update), 16 and 32 are slower (721 / 754 us: more
+// lanes replay their segment twice); one lane per cell was 0.71 ms
+constexpr int kChainLanes = 8;
+
+static void launch_chain(unsigned n_slots, cudaStream_t st, float* grid, unsigned* slotmap, const unsigned* slot_cell,
+                         const unsigned* ev, const unsigned* ev_count, const unsigned* small, int stride, double l_hit,
+                         double l_miss, float lo, float hi) {
+    const unsigned blocks = (unsigned)(((unsigned long long)n_slots * kChainLanes + 127ull) / 128ull);
+    occ_fast_chain<kChainLanes><<<blocks, 128, 0, st>>>(grid, slotmap, slot_cell, ev, ev_count, small, stride, l_hit, l_miss, lo, hi);
 }
 
 }  // namespace
@@ -882,7 +889,7 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
         if (n_slots) {
             if (g.ev_count.reserve(sizeof(unsigned) * (size_t)n_slots)) return ICPB200_ERR_CUDA;
             ICPB_CUDA(cudaMemsetAsync(g.ev_count.p, 0, sizeof(unsigned) * (size_t)n_slots, st));
-            occ_fast_chain<<<chain_blocks(n_slots), 128, 0, st>>>(g.grid.as<float>(), g.slotmap.as<unsigned>(),
+            launch_chain(n_slots, st, g.grid.as<float>(), g.slotmap.as<unsigned>(),
                                                                     g.slot_cell.as<unsigned>(), nullptr, g.ev_count.as<unsigned>(), d_small,
                                                                     0, g.l_hit, g.l_miss, (float)g.lo_min, (float)g.lo_max);
             ICPB_LAUNCH_CHECK();
@@ -945,7 +952,7 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
                                                                                       g.ev_count.as<unsigned>(), d_small, cs, stride);
             ICPB_LAUNCH_CHECK();
             tm.mark_aux("compact", g.aux_stream);
-            occ_fast_chain<<<chain_blocks(n_slots), 128, 0, g.aux_stream>>>(g.grid.as<float>(), g.slotmap.as<unsigned>(),
+            launch_chain(n_slots, g.aux_stream, g.grid.as<float>(), g.slotmap.as<unsigned>(),
                                                                              g.slot_cell.as<unsigned>(), g.ev.as<unsigned>(),
                                                                              g.ev_count.as<unsigned>(), d_small, stride, g.l_hit, g.l_miss, lo, hi);
             ICPB_LAUNCH_CHECK();
@@ -972,7 +979,7 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
         occ_fast_compact<<<(n_slots * 32u + 255u) / 256u, 256, 0, st>>>(g.ord.as<unsigned>(), g.ev.as<unsigned>(),
                                                                         g.ev_count.as<unsigned>(), d_small, cs, stride);
         ICPB_LAUNCH_CHECK();
-        occ_fast_chain<<<chain_blocks(n_slots), 128, 0, st>>>(g.grid.as<float>(), g.slotmap.as<unsigned>(),
+        launch_chain(n_slots, st, g.grid.as<float>(), g.slotmap.as<unsigned>(),
                                                                 g.slot_cell.as<unsigned>(), g.ev.as<unsigned>(),
                                                                 g.ev_count.as<unsigned>(), d_small, stride, g.l_hit, g.l_miss, lo, hi);
         ICPB_LAUNCH_CHECK();
