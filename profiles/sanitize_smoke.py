@@ -23,4 +23,19 @@ teapot = np.random.default_rng(0).normal(size=(400, 3))
 api.icp_batch([teapot + 0.01], [teapot], 1e-12, 30, 0.05)                       # 3-D Kabsch
 g = OccupancyGrid2D(-25.6, 25.6, -25.6, 25.6, resolution=0.05, p_hit=0.85, p_miss=0.42, log_odds_min=-8, log_odds_max=8)
 g.update_scans([p[:2] for p in poses], [synth.to_world_frame(s, p) for s, p in zip(scans, poses)])
+# device-resident entry point (offsets checked on the device, deferred statistics, eight-lane replay)
+import torch  # noqa: E402
+hits = [synth.to_world_frame(s, p) for s, p in zip(scans, poses)]
+flat, off = synth.pack_ragged(hits)
+d_org, d_hits, d_off = (torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (poses[:, :2].copy(), flat, off))
+torch.cuda.synchronize()
+for _ in range(2):
+    g._dev.update_dev(len(off) - 1, d_org.data_ptr(), d_hits.data_ptr(), d_off.data_ptr(), int(off[-1]), 0)
+g._host = None
+st = g._dev.last_stats()
+# pairs out of order through the host-buffer entry point (pair grouping by upload chunk)
+cl, co = synth.pack_ragged(list(scans))
+si = np.array([4, 0, 2, 1, 3], dtype=np.int32)
+out3 = api.icp_pairs(cl, co, si, si + 1, **cfg)
+assert np.array_equal(out3["iters"], out["iters"][si])
 print("sanitize smoke ok", out["iters"].tolist(), len(ds), float(g.log_odds.min()), float(g.log_odds.max()))
