@@ -1889,28 +1889,45 @@ static int launch_pairs_t(const IcpArgs& a, int n_ctas, size_t smem, cudaStream_
     return ICPB200_OK;
 }
 
+// CTAs per SM the bulk launches are compiled for (profiles/kernel_ab.py, grid_batch_ab.py): 2-D brute 2 (128 registers,
+// no spills: 1.22 against 1.26 ms on C2), grid mode 2 (4.56 against 4.75 ms for 592 scan->submap pairs), 3-D 3 (2 measured
+// the same on the teapot batch)
+static constexpr int bulk_minb(int dim, bool grid) { return grid ? 2 : (dim == 2 ? 2 : 3); }
+
 int launch_icp_pairs(const IcpArgs& a, int dim, bool grid, int n_ctas, size_t smem, cudaStream_t stream) {
-    if (grid) return launch_pairs_t<2, true, 3>(a, n_ctas, smem, stream);        // grid mode is 2-D only
-    if (dim == 2 && a.resume) return launch_pairs_t<2, false, 1>(a, n_ctas, smem, stream);
-    // 2-D bulk launch: two CTAs per SM with 128 registers (no spills) beat three with 80 (1.22 against 1.26 ms on C2)
-    return dim == 2 ? launch_pairs_t<2, false, 2>(a, n_ctas, smem, stream) : launch_pairs_t<3, false, 3>(a, n_ctas, smem, stream);
+    static const int sms = [] {
+        int dev = 0, n = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        return n;
+    }();
+    // a launch of at most one CTA per SM (the hand-over launch, single calls, small batches) takes the variant that is
+    // allowed every register: nothing spills (64 scan->submap pairs: 3.50 -> 1.93 ms)
+    const bool roomy = a.resume || n_ctas <= sms;
+    if (grid) {                                                                // grid mode is 2-D only
+        if (roomy) return launch_pairs_t<2, true, 1>(a, n_ctas, smem, stream);
+        return launch_pairs_t<2, true, bulk_minb(2, true)>(a, n_ctas, smem, stream);
+    }
+    if (dim == 2) {
+        if (roomy) return launch_pairs_t<2, false, 1>(a, n_ctas, smem, stream);
+        return launch_pairs_t<2, false, bulk_minb(2, false)>(a, n_ctas, smem, stream);
+    }
+    if (roomy) return launch_pairs_t<3, false, 1>(a, n_ctas, smem, stream);
+    return launch_pairs_t<3, false, bulk_minb(3, false)>(a, n_ctas, smem, stream);
+}
+
+template <int DIM, bool GRID, int MINB>
+static int max_ctas_t(size_t smem) {
+    int n = 0;
+    cudaFuncSetAttribute(icp_pairs_kernel<DIM, GRID, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, icp_pairs_kernel<DIM, GRID, MINB>, kNT, smem) != cudaSuccess || n < 1) n = 1;
+    return n;
 }
 
 int icp_max_ctas_per_sm(int dim, bool grid, size_t smem) {
-    int n = 0;
-    cudaError_t e;
-    if (grid) {
-        cudaFuncSetAttribute(icp_pairs_kernel<2, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, icp_pairs_kernel<2, true, 3>, kNT, smem);
-    } else if (dim == 2) {
-        cudaFuncSetAttribute(icp_pairs_kernel<2, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, icp_pairs_kernel<2, false, 2>, kNT, smem);
-    } else {
-        cudaFuncSetAttribute(icp_pairs_kernel<3, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, icp_pairs_kernel<3, false, 3>, kNT, smem);
-    }
-    if (e != cudaSuccess || n < 1) n = 1;
-    return n;
+    if (grid) return max_ctas_t<2, true, bulk_minb(2, true)>(smem);
+    if (dim == 2) return max_ctas_t<2, false, bulk_minb(2, false)>(smem);
+    return max_ctas_t<3, false, bulk_minb(3, false)>(smem);
 }
 
 }  // namespace icpb

@@ -201,3 +201,31 @@ def test_c2_batch_sweep_against_the_oracle():
         assert np.abs(out["t"][i] - t).max() <= 1e-4
         dth = np.arctan2(out["R"][i][1, 0], out["R"][i][0, 0]) - np.arctan2(R[1, 0], R[0, 0])
         assert abs(dth) <= 1e-5
+
+
+def test_chunked_upload_with_pairs_in_any_order_is_bitwise_identical():
+    """icpb200_icp_pairs uploads a large cloud set in four chunks and registers a pair as soon as the chunks of both
+    its clouds have landed (pairs grouped by the last chunk they need, an order list on the device).  The results must be
+    the ones of the plain batch entry point, bit for bit, in the caller's order -- for pairs that arrive in time order,
+    shuffled, reversed, and with initial guesses."""
+    scans, poses = synth.make_sequence(1100, world="room", seed=5)        # 18 MB of points: four upload chunks
+    flat, off = synth.pack_ragged(scans)
+    assert flat.nbytes >= 16 << 20
+    rng = np.random.default_rng(11)
+    src = rng.integers(0, 1099, size=700).astype(np.int32)
+    tgt = np.clip(src + rng.integers(-2, 3, size=700), 0, 1099).astype(np.int32)
+    tgt[src == tgt] = src[src == tgt] + 1
+    ref = api.icp_batch([scans[i] for i in src], [scans[j] for j in tgt], **CFG)
+    assert (ref["status"] == 0).sum() > 500
+    for name, perm in (("shuffled", np.arange(700)), ("sorted", np.argsort(np.maximum(src, tgt), kind="stable")),
+                       ("reversed", np.argsort(-np.maximum(src, tgt), kind="stable"))):
+        out = api.icp_pairs(flat, off, src[perm], tgt[perm], **CFG)
+        for key in ("R", "t", "error", "iters", "status"):
+            assert out[key].tobytes() == ref[key][perm].tobytes(), (name, key)
+    th = rng.normal(0.0, 0.01, size=700)
+    R0 = np.stack([[[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]] for a in th])
+    t0 = rng.normal(0.0, 0.02, size=(700, 2))
+    a = api.icp_batch([scans[i] for i in src], [scans[j] for j in tgt], R_init=R0, t_init=t0, **CFG)
+    b = api.icp_pairs(flat, off, src, tgt, R_init=R0, t_init=t0, **CFG)
+    for key in ("R", "t", "error", "iters", "status"):
+        assert a[key].tobytes() == b[key].tobytes(), ("init", key)
