@@ -451,7 +451,8 @@ def run_ours(args, rank, world, local_rank):
                                f"pair evaluation x {FLOP_PER_PAIR_EVAL_2D} flop (BASELINE.md section 4)")
 
     cores = os.cpu_count() or 1
-    cpu = cpu_icp_baseline(scans, si, ti, min(n_pairs, max(4 * cores, 256)), cores) if not args.no_cpu else None
+    # the CPU leg runs at N = 1 only (measurement contract): at N > 1 the other ranks would sit in a barrier behind it
+    cpu = cpu_icp_baseline(scans, si, ti, min(n_pairs, max(4 * cores, 256)), cores) if not args.no_cpu and world == 1 else None
 
     line = dict(metric="icp_registrations_per_s", value=world * n_pairs * args.steps / t_max, unit="registrations/s",
                 n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=1e3 * t_max / args.steps,
@@ -552,7 +553,7 @@ def bench_raycast(args, lib, api, dev, local_rank, pk, rank=0, world=1):
         return None
     # algorithmic bytes: 16 B endpoint + 8 B per traversed cell + 8 B hit-cell RMW
     alg_bytes = 16.0 * n_rays + 8.0 * cells + 8.0 * hits_in
-    cpu = cpu_raycast_baseline(origins, flat, off, min(len(off) - 1, 60)) if not args.no_cpu else None
+    cpu = cpu_raycast_baseline(origins, flat, off, min(len(off) - 1, 60)) if not args.no_cpu and world == 1 else None
     return dict(metric="occupancy_rays_per_s", value=n_rays / sec, unit="rays/s", ms_per_step=sec * 1e3,
                 n_gpus=world, scaling="strong", update_only_ms=sec_update * 1e3,
                 config=dict(workload=f"C4 occupancy log-odds raycast: {len(off) - 1} scans, {n_rays} rays, "
