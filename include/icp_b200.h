@@ -207,6 +207,14 @@ int icpb200_grid_update(void *grid, int n_scans, const double *origins,
 int icpb200_grid_update_dev(void *grid, int n_scans, const double *d_origins,
                             const double *d_hits, const int64_t *d_hit_off,
                             int64_t total_hits, void *stream);
+/* slam.py:271-277 `_rebuild_map` with slam.py:46-50 `transform_points_2d` fused in:
+ * clear the grid, then replay n_scans scans given in their LOCAL frames with their
+ * current 3x3 homogeneous poses (row major, n_scans*9): world = local @ R.T + t
+ * evaluated on the device as fma(p1, r_1, p0*r_0) + t -- the roundings of numpy's
+ * matmul followed by the broadcast add -- origin = the pose's translation.
+ * local_pts: rows of 2 float64; scan s owns rows off[s] .. off[s+1]. */
+int icpb200_grid_rebuild(void *grid, int n_scans, const double *poses,
+                         const double *local_pts, const int64_t *off);
 /* Copy the (ny, nx) float32 log-odds array, row major [iy][ix], to `out`. */
 int icpb200_grid_read(void *grid, float *out);
 /* mapping.py:143-145 */

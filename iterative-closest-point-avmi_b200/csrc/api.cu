@@ -864,7 +864,7 @@ int icpb200_rotation_scores(int n_problems, const double* src, const int64_t* sr
 // ---- occupancy grid --------------------------------------------------------------
 
 void OccGrid::release_all() {
-    DevBuf* bufs[] = {&grid, &origins, &hits, &hit_off, &origin_cell, &ray_cell, &ray_scan,
+    DevBuf* bufs[] = {&grid, &origins, &hits, &hit_off, &local_pts, &poses, &origin_cell, &ray_cell, &ray_scan,
                       &counts, &offsets, &sums, &runs, &order, &small, &tile_prof,
                       &slotmap, &slot_cell, &ord, &tile_count, &hit_off_shift, &items, &multi, &ncount, &ev, &ev_count, &class_off, &tile_flag};
     for (DevBuf* b : bufs) b->release();
@@ -947,6 +947,40 @@ int icpb200_grid_update(void* grid, int n_scans, const double* origins, const do
     ICPB_CUDA(cudaMemcpyAsync(g->hit_off.p, hit_off, sizeof(int64_t) * ((size_t)n_scans + 1), cudaMemcpyHostToDevice, st));
     return occ_update_device(*g, n_scans, g->origins.as<double>(), g->hits.as<double>(), g->hit_off.as<long long>(),
                              reinterpret_cast<const long long*>(hit_off), st);
+}
+
+int icpb200_grid_rebuild(void* grid, int n_scans, const double* poses, const double* local_pts, const int64_t* off) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!grid || n_scans < 0 || (n_scans > 0 && (!poses || !off))) { set_error("icpb200_grid_rebuild: null pointer"); return ICPB200_ERR_ARG; }
+    if (n_scans > 0) {
+        if (off[0] != 0) { set_error("icpb200_grid_rebuild: off[0] must be 0"); return ICPB200_ERR_ARG; }
+        for (int s = 0; s < n_scans; ++s)
+            if (off[s + 1] < off[s]) { set_error("icpb200_grid_rebuild: off decreases at scan %d", s); return ICPB200_ERR_ARG; }
+        if (off[n_scans] > 0 && !local_pts) { set_error("icpb200_grid_rebuild: local_pts is null"); return ICPB200_ERR_ARG; }
+    }
+    int rc = init_locked(-1);
+    if (rc) return rc;
+    OccGrid* g = static_cast<OccGrid*>(grid);
+    cudaStream_t st = g_ctx.stream;
+    if ((rc = occ_collect(*g))) return rc;
+    ICPB_CUDA(cudaMemsetAsync(g->grid.p, 0, sizeof(float) * (size_t)g->nx * g->ny, st));      // slam.py:273, mapping.py:143-145
+    g->seen_nonempty_scan = false;
+    g->virgin_finalised = false;
+    g->stats[0] = g->stats[1] = g->stats[2] = g->stats[3] = 0;
+    const long long n_pts = n_scans > 0 ? (long long)off[n_scans] : 0;
+    if (n_pts == 0) { ICPB_CUDA(cudaStreamSynchronize(st)); return ICPB200_OK; }
+    if (g->origins.reserve(sizeof(double) * 2 * (size_t)n_scans) || g->hits.reserve(sizeof(double) * 2 * (size_t)n_pts) ||
+        g->hit_off.reserve(sizeof(int64_t) * ((size_t)n_scans + 1)) || g->local_pts.reserve(sizeof(double) * 2 * (size_t)n_pts) ||
+        g->poses.reserve(sizeof(double) * 9 * (size_t)n_scans))
+        return ICPB200_ERR_CUDA;
+    ICPB_CUDA(cudaMemcpyAsync(g->poses.p, poses, sizeof(double) * 9 * (size_t)n_scans, cudaMemcpyHostToDevice, st));
+    ICPB_CUDA(cudaMemcpyAsync(g->hit_off.p, off, sizeof(int64_t) * ((size_t)n_scans + 1), cudaMemcpyHostToDevice, st));
+    ICPB_CUDA(cudaMemcpyAsync(g->local_pts.p, local_pts, sizeof(double) * 2 * (size_t)n_pts, cudaMemcpyHostToDevice, st));
+    if ((rc = occ_transform_history(n_scans, n_pts, g->poses.as<double>(), g->local_pts.as<double>(), g->hit_off.as<long long>(),
+                                    g->hits.as<double>(), g->origins.as<double>(), st)))
+        return rc;
+    return occ_update_device(*g, n_scans, g->origins.as<double>(), g->hits.as<double>(), g->hit_off.as<long long>(),
+                             reinterpret_cast<const long long*>(off), st);
 }
 
 int icpb200_grid_update_dev(void* grid, int n_scans, const double* d_origins, const double* d_hits,

@@ -557,6 +557,42 @@ static int exclusive_scan_u32(const unsigned* d_in, size_t n, unsigned* d_out, D
     return ICPB200_OK;
 }
 
+// slam.py:46-50 `transform_points_2d`: points_2d @ R.T + t.  numpy evaluates the 2-term dot product of the matmul as
+// fma(p1, r1, rn(p0 * r0)) (OpenBLAS dgemm on FMA hardware; checked against exact rational arithmetic in the build
+// container, oracle/pin_rebuild.py pins the result against the reference) and then adds t: the same three roundings here.
+__global__ void occ_transform_kernel(int n_scans, long long n_points, const double* __restrict__ poses,
+                                     const double2* __restrict__ local, const long long* __restrict__ off,
+                                     double2* __restrict__ world, double* __restrict__ origins) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_scans) {                                   // slam.py:275: origin = pose[:2, 2]
+        origins[2 * i] = poses[9 * i + 2];
+        origins[2 * i + 1] = poses[9 * i + 5];
+    }
+    if (i >= n_points) return;
+    int lo = 0, hi = n_scans;                            // largest s with off[s] <= i
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (off[mid] <= i) lo = mid; else hi = mid;
+    }
+    const double* P = poses + 9 * (size_t)lo;
+    const double2 p = local[i];
+    double2 w;
+    w.x = __dadd_rn(__fma_rn(p.y, P[1], __dmul_rn(p.x, P[0])), P[2]);
+    w.y = __dadd_rn(__fma_rn(p.y, P[4], __dmul_rn(p.x, P[3])), P[5]);
+    world[i] = w;
+}
+
+int occ_transform_history(int n_scans, long long n_points, const double* d_poses, const double* d_local,
+                          const long long* d_off, double* d_world, double* d_origins, cudaStream_t st) {
+    const long long n = std::max<long long>(n_points, n_scans);
+    if (n <= 0) return ICPB200_OK;
+    occ_transform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n_scans, n_points, d_poses,
+                                                                      reinterpret_cast<const double2*>(d_local), d_off,
+                                                                      reinterpret_cast<double2*>(d_world), d_origins);
+    ICPB_LAUNCH_CHECK();
+    return ICPB200_OK;
+}
+
 int occ_update_device(OccGrid& g, int n_scans, const double* d_origins, const double* d_hits,
                       const long long* d_hit_off, const long long* h_hit_off, cudaStream_t st) {
     if (g.use_fast && !g.zero_outside_clamp) {

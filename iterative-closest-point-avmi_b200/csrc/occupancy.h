@@ -48,6 +48,7 @@ struct OccGrid {
     long long stats[4] = {0, 0, 0, 0};
     DevBuf grid;                                   // ny * nx float32, row major
     DevBuf origins, hits, hit_off;                 // staging for the host-buffer entry point
+    DevBuf local_pts, poses;                       // icpb200_grid_rebuild: scans in their local frames + 3x3 poses
     DevBuf origin_cell, ray_cell, ray_scan;
     DevBuf counts, offsets, sums, runs, order, small, tile_prof;
     // order-free path (occupancy_fast.cu)
@@ -80,6 +81,9 @@ int occ_update_fast(OccGrid& g, int n_scans, const double* d_origins, const doub
                     cudaStream_t st);
 // Waits for a deferred read-back (if any); returns ICPB200_ERR_LIMIT when the update it belongs to overflowed.
 int occ_collect(OccGrid& g);
+// slam.py:46-50 for every scan of a history: world = local @ R.T + t, origin = t (device pointers)
+int occ_transform_history(int n_scans, long long n_points, const double* d_poses, const double* d_local,
+                          const long long* d_off, double* d_world, double* d_origins, cudaStream_t st);
 int occ_apply_ctas(int sm_count);
 int occ_fast_ctas(int sm_count);
 

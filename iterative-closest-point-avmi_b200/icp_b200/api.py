@@ -233,6 +233,16 @@ class DeviceGrid:
         check(self._lib.icpb200_grid_update(self._h, len(off) - 1, _ptr(org, c_double_p), _ptr(pts, c_double_p),
                                             _ptr(off, c_int64_p)), "icpb200_grid_update")
 
+    def rebuild(self, poses, local_points, off):
+        """slam.py:271-277 in one call: clear, then replay scans given in their local frames with 3x3 poses."""
+        P = _f64(poses).reshape(-1, 9)
+        pts = _f64(local_points).reshape(-1, 2)
+        o = np.ascontiguousarray(off, dtype=np.int64)
+        if len(o) - 1 != len(P):
+            raise ValueError("rebuild: one pose per scan")
+        check(self._lib.icpb200_grid_rebuild(self._h, len(P), _ptr(P, c_double_p), _ptr(pts, c_double_p), _ptr(o, c_int64_p)),
+              "icpb200_grid_rebuild")
+
     def update_dev(self, n_scans, d_origins, d_hits, d_hit_off, total_hits, stream=0):
         check(self._lib.icpb200_grid_update_dev(self._h, int(n_scans), d_origins, d_hits, d_hit_off, int(total_hits),
                                                 stream), "icpb200_grid_update_dev")

@@ -72,6 +72,21 @@ class OccupancyGrid2D:
         self._dev.update(np.asarray(origins, dtype=np.float64), flat, off)
         self._host = None
 
+    def rebuild(self, scan_history):
+        """The reference's `_rebuild_map(mapper, scan_history)` (slam.py:271-277) as one device call: clear the grid and
+        replay every `(local_points (N, 2), pose (3, 3))` of the history in order; `transform_points_2d` (slam.py:46-50)
+        runs on the device with numpy's roundings.  Same map as `reset()` + `update_scan(pose[:2, 2], pts @ R.T + t)` per
+        scan."""
+        from icp_b200.synth import pack_ragged
+        scans = [np.asarray(pts, dtype=np.float64).reshape(-1, 2) for pts, _ in scan_history]
+        poses = np.asarray([np.asarray(pose, dtype=np.float64) for _, pose in scan_history], dtype=np.float64).reshape(-1, 3, 3)
+        if len(scans) == 0:
+            self.reset()
+            return
+        flat, off = pack_ragged(scans)
+        self._dev.rebuild(poses, flat, off)
+        self._host = None
+
     def reset(self):
         """Back to unexplored (all zeros)."""
         self._dev.reset()

@@ -168,3 +168,22 @@ def line_cells_c(x0, y0, x1, y1):
         x0, y0, x1, y1, buf.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), len(buf))
     assert got == n
     return buf[:n]
+
+
+# ---- map rebuild: /root/reference/slam.py:46-50 and 271-277 ----------------
+def transform_points_2d(points_2d, pose):
+    """slam.py:46-50 -- `points_2d @ R.T + t` with R, t taken from a 3x3 homogeneous pose, written as the reference
+    writes it (numpy matmul, then the broadcast add)."""
+    R = pose[:2, :2]
+    t = pose[:2, 2]
+    return points_2d @ R.T + t
+
+
+def rebuild_map(grid, scan_history):
+    """slam.py:271-277 `_rebuild_map`: clear the grid, replay every (local points, pose) of the history in order,
+    origin = the pose's translation.  `grid` is any of the oracle grids above."""
+    grid.reset()
+    for pts, pose in scan_history:
+        origin = pose[:2, 2]
+        grid.update_scan(origin, transform_points_2d(pts, pose))
+    return grid

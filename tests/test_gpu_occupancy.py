@@ -293,3 +293,34 @@ def test_device_resident_entry_point_is_stream_ordered_and_reports_late():
     ref2 = oo.GridOracleC(*bounds, **GKW)
     ref2.update_scan(o1[0], pts[:4095], fast=True)
     assert_same(gpu, ref2, "after the overflow report")
+
+
+def test_rebuild_map_in_one_call_matches_the_reference_and_the_oracle():
+    """`_rebuild_map` (slam.py:271-277) with `transform_points_2d` (slam.py:46-50) fused in --
+    OccupancyGrid2D.rebuild(scan_history) / icpb200_grid_rebuild.  Bit-exact against the reference's own maps
+    (tests/golden/rebuild.npz) and, on a larger random history, against the oracle's scan-by-scan rebuild."""
+    from utilities import OccupancyGrid2D
+    g = load_golden("rebuild.npz")
+    off = g["scan_off"]
+    grid = OccupancyGrid2D(*g["bounds"], **GKW)
+    assert grid.log_odds.shape == tuple(g["grid_shape"])
+    grid.update_scan(np.zeros(2), g["scans"][off[0]:off[1]])           # something to clear
+    for variant in (0, 1, 0):
+        history = [(g["scans"][off[s]:off[s + 1]], g[f"poses_{variant}"][s]) for s in range(len(off) - 1)]
+        grid.rebuild(history)
+        want = np.zeros(grid.log_odds.size, dtype=np.float32)
+        want[g[f"nz_index_{variant}"]] = g[f"nz_value_{variant}"]
+        assert grid.log_odds.ravel().tobytes() == want.tobytes(), variant
+    grid.rebuild([])
+    assert not grid.log_odds.any()
+    # 150 scans of the campus world with perturbed poses
+    scans, poses = synth.make_sequence(150, world="campus", seed=9)
+    rng = np.random.default_rng(4)
+    poses = poses + rng.normal(0, [0.1, 0.1, 0.02], size=poses.shape)
+    mats = [np.array([[np.cos(t), -np.sin(t), x], [np.sin(t), np.cos(t), y], [0.0, 0.0, 1.0]]) for x, y, t in poses]
+    bounds = (poses[:, 0].mean() - 51.2, poses[:, 0].mean() + 51.2, poses[:, 1].mean() - 51.2, poses[:, 1].mean() + 51.2)
+    gpu, ref = make_pair(bounds, **GKW)
+    history = list(zip(scans, mats))
+    gpu.rebuild(history)
+    oo.rebuild_map(ref, history)
+    assert_same(gpu, ref, "150-scan rebuild")

@@ -129,3 +129,23 @@ def test_rotation_search_oracle_reproduces_the_reference():
         R, t = fo.submap_rotation_search(g[f"sub_{name}_src"], g[f"sub_{name}_map"], g[f"sub_{name}_pose"], angle_range=ar,
                                          angle_step=st, fine_step=fs, voxel_size=v)
         assert R.tobytes() == g[f"sub_{name}_R"].tobytes() and t.tobytes() == g[f"sub_{name}_t"].tobytes()
+
+
+def _rebuild_history(g, variant):
+    off = g["scan_off"]
+    return [(g["scans"][off[s]:off[s + 1]], g[f"poses_{variant}"][s]) for s in range(len(off) - 1)]
+
+
+def test_rebuild_map_oracle_reproduces_the_reference():
+    """slam.py:271-277 `_rebuild_map` + slam.py:46-50 `transform_points_2d`: the reference's own maps for a 14-scan
+    history (an empty scan, endpoints beyond the grid), before and after its poses were corrected
+    (tests/golden/rebuild.npz, written by oracle/pin_rebuild.py from the live reference)."""
+    g = load_golden("rebuild.npz")
+    kw = dict(resolution=0.05, p_hit=0.85, p_miss=0.42, log_odds_min=-8.0, log_odds_max=8.0)
+    grid = occupancy_oracle.GridOracleC(*g["bounds"], **kw)
+    assert grid.log_odds.shape == tuple(g["grid_shape"])
+    for variant in (0, 1, 0):                      # a rebuild starts from a cleared grid whatever was in it
+        occupancy_oracle.rebuild_map(grid, _rebuild_history(g, variant))
+        want = np.zeros(grid.log_odds.size, dtype=np.float32)
+        want[g[f"nz_index_{variant}"]] = g[f"nz_value_{variant}"]
+        assert same_bits(grid.log_odds.ravel(), want), variant
