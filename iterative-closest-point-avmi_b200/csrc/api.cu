@@ -864,7 +864,7 @@ int icpb200_rotation_scores(int n_problems, const double* src, const int64_t* sr
 // ---- occupancy grid --------------------------------------------------------------
 
 void OccGrid::release_all() {
-    DevBuf* bufs[] = {&grid, &origins, &hits, &hit_off, &local_pts, &poses, &origin_cell, &ray_cell, &ray_scan,
+    DevBuf* bufs[] = {&grid, &origins, &hits, &hit_off, &local_pts, &poses, &in_pack, &origin_cell, &ray_cell, &ray_scan,
                       &counts, &offsets, &sums, &runs, &order, &small, &tile_prof,
                       &slotmap, &slot_cell, &ord, &tile_count, &hit_off_shift, &items, &multi, &ncount, &ev, &ev_count, &class_off, &tile_flag};
     for (DevBuf* b : bufs) b->release();
@@ -874,6 +874,7 @@ void OccGrid::release_all() {
     if (ev_hit) { cudaEventDestroy(ev_hit); ev_hit = nullptr; }
     if (ev_stats) { cudaEventDestroy(ev_stats); ev_stats = nullptr; }
     if (pending_host) { cudaFreeHost(pending_host); pending_host = nullptr; }
+    if (h_in_pack) { cudaFreeHost(h_in_pack); h_in_pack = nullptr; h_in_cap = 0; }
     stats_pending = false;
 }
 
@@ -939,12 +940,33 @@ int icpb200_grid_update(void* grid, int n_scans, const double* origins, const do
     cudaStream_t st = g_ctx.stream;
     if ((rc = occ_collect(*g))) return rc;
     if (n_rays == 0) { g->stats[0] = g->stats[1] = g->stats[2] = g->stats[3] = 0; return ICPB200_OK; }
-    if (g->origins.reserve(sizeof(double) * 2 * (size_t)n_scans) || g->hits.reserve(sizeof(double) * 2 * (size_t)n_rays) ||
-        g->hit_off.reserve(sizeof(int64_t) * ((size_t)n_scans + 1)))
-        return ICPB200_ERR_CUDA;
-    ICPB_CUDA(cudaMemcpyAsync(g->origins.p, origins, sizeof(double) * 2 * (size_t)n_scans, cudaMemcpyHostToDevice, st));
-    ICPB_CUDA(cudaMemcpyAsync(g->hits.p, hits, sizeof(double) * 2 * (size_t)n_rays, cudaMemcpyHostToDevice, st));
-    ICPB_CUDA(cudaMemcpyAsync(g->hit_off.p, hit_off, sizeof(int64_t) * ((size_t)n_scans + 1), cudaMemcpyHostToDevice, st));
+    const size_t b_org = sizeof(double) * 2 * (size_t)n_scans, b_off = sizeof(int64_t) * ((size_t)n_scans + 1),
+                 b_hits = sizeof(double) * 2 * (size_t)n_rays;
+    if (b_org + b_off + b_hits <= (256u << 10)) {
+        // update_scan and other small updates (the online loop, slam.py:408, 557): three copies from pageable memory
+        // would each go through the driver's bounce buffer and block; one block, one copy instead
+        const size_t at_off = (b_org + 15) & ~(size_t)15, at_hits = (at_off + b_off + 15) & ~(size_t)15, total = at_hits + b_hits;
+        if (total > g->h_in_cap) {
+            if (g->h_in_pack) { cudaFreeHost(g->h_in_pack); g->h_in_pack = nullptr; g->h_in_cap = 0; }
+            ICPB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g->h_in_pack), 256u << 10, cudaHostAllocDefault));
+            g->h_in_cap = 256u << 10;
+        }
+        if (g->in_pack.reserve(256u << 10)) return ICPB200_ERR_CUDA;
+        memcpy(g->h_in_pack, origins, b_org);
+        memcpy(g->h_in_pack + at_off, hit_off, b_off);
+        memcpy(g->h_in_pack + at_hits, hits, b_hits);
+        ICPB_CUDA(cudaMemcpyAsync(g->in_pack.p, g->h_in_pack, total, cudaMemcpyHostToDevice, st));
+        unsigned char* d = g->in_pack.as<unsigned char>();
+        // the host block is reused by the next call: occ_update_device ends with a wait on `st`, the copy is done by then
+        rc = occ_update_device(*g, n_scans, reinterpret_cast<const double*>(d), reinterpret_cast<const double*>(d + at_hits),
+                               reinterpret_cast<const long long*>(d + at_off), reinterpret_cast<const long long*>(hit_off), st);
+        if (rc) cudaStreamSynchronize(st);         // an early error return may leave the copy in flight
+        return rc;
+    }
+    if (g->origins.reserve(b_org) || g->hits.reserve(b_hits) || g->hit_off.reserve(b_off)) return ICPB200_ERR_CUDA;
+    ICPB_CUDA(cudaMemcpyAsync(g->origins.p, origins, b_org, cudaMemcpyHostToDevice, st));
+    ICPB_CUDA(cudaMemcpyAsync(g->hits.p, hits, b_hits, cudaMemcpyHostToDevice, st));
+    ICPB_CUDA(cudaMemcpyAsync(g->hit_off.p, hit_off, b_off, cudaMemcpyHostToDevice, st));
     return occ_update_device(*g, n_scans, g->origins.as<double>(), g->hits.as<double>(), g->hit_off.as<long long>(),
                              reinterpret_cast<const long long*>(hit_off), st);
 }

@@ -49,6 +49,9 @@ struct OccGrid {
     DevBuf grid;                                   // ny * nx float32, row major
     DevBuf origins, hits, hit_off;                 // staging for the host-buffer entry point
     DevBuf local_pts, poses;                       // icpb200_grid_rebuild: scans in their local frames + 3x3 poses
+    DevBuf in_pack;                                // small updates: origins | hit_off | hits in one block ...
+    unsigned char* h_in_pack = nullptr;            // ... uploaded from one page-locked block with one copy
+    size_t h_in_cap = 0;
     DevBuf origin_cell, ray_cell, ray_scan;
     DevBuf counts, offsets, sums, runs, order, small, tile_prof;
     // order-free path (occupancy_fast.cu)
