@@ -2,32 +2,31 @@
 """Benchmark of the B200-native ICP registration + occupancy raycast hot path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload c2|c5|teapot] [--scans 2000]
 
-Headline workload (BASELINE.json configs[1], "C2"): 2000 synthetic 1080-beam
-2-D scans -> 1999 consecutive scan-to-scan point_to_line registrations with
-the reference's config.yaml parameters.  One "step" = one pass of the hot path
-over that whole batch.  Prints ONE JSON line (rank 0):
+One GPU (the BENCH line): the headline workload is BASELINE.json configs[1] ("C2"): 2000 synthetic 1080-beam 2-D
+scans -> 1999 consecutive scan-to-scan point_to_line registrations with the reference's config.yaml parameters.  One
+"step" = one pass of the hot path over that whole batch.  The line also carries `c5` (configs[4], the 8192-pair
+loop-closure batch on this one GPU: the N = 1 point of the strong-scaling curve), `occupancy` (configs[3], C4),
+`online` (single calls through the drop-in shim), `verify` (the timed outputs against the oracle) and `extras`
+(C1 teapot, C3 scan -> submap, rotation search, map rebuild).
 
-  value      registrations/s with the clouds already resident in HBM, timed with
-             CUDA events on the launching stream, max over ranks
-  e2e        the same batch through the host-buffer C ABI call
-             (icpb200_icp_pairs): H2D of the clouds and D2H of the poses inside
-             the timed region
-  roofline   FP32-FMA-pipe roofline of the per-pair ICP kernel (BASELINE.md
-             section 4: pair evaluations x 5 flop vs SMs x 128 lanes x clock / 4)
-  cpu_baseline  the oracle port of the reference (numpy/scipy, same arithmetic
-             and library calls as /root/reference/utilities/icp.py) timed on
-             this box's host cores on a bounded sample of the same pairs
-  occupancy  the second metric of BASELINE.json (configs[3], "C4"): rays/s of the
-             occupancy raycast, 4096x4096 grid @ 5 cm, with its own value / e2e /
-             roofline (HBM) / cpu_baseline
+Several GPUs (torchrun, the SCALE lines): the headline is configs[4] ("C5"): ONE batch of 8192 loop-closure
+candidate pairs partitioned across the ranks (strong scaling; icp_b200.dist: locality-sorted chunks dealt round-robin,
+every rank uploads and preprocesses only the clouds its pairs reference, one NCCL all_gather of packed result blocks).
+`c2_weak` keeps round 1's weak-scaling figure (every rank registers the whole C2 batch) as an extra.
 
---impl reference times the reference's CPU implementation (the oracle port:
-the reference is pure Python and /root/reference does not exist on the GPU
-box) on all host cores.  Multi-GPU (torchrun): every rank registers its own
-1999-pair batch (weak scaling); poses are gathered with one NCCL all_gather
-inside the timed region.
+Keys of a line (rank 0 prints ONE JSON line):
+  value      registrations/s with the clouds already resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e        the same batch through the host-buffer call (icpb200_icp_pairs / dist.icp_pairs_sharded): H2D of the clouds
+             and D2H of the poses inside the timed region; `unpinned` = the same from pageable memory
+  roofline   FP32-FMA pipe: EXECUTED fp32 pair evaluations (a device counter) x 5 flop / kernel time against
+             SMs x 128 lanes x clock / 4; `algorithmic_equivalent` (the brute-force count of BASELINE.md section 4,
+             which the kernel does not execute) and `latency_model` are reported next to it, clearly named
+  cpu_baseline  the reference's CPU path timed on this box's host cores on a bounded sample of the same pairs:
+             the UNMODIFIED reference from oracle/_ref (kind "reference") when the archive is present, else the
+             oracle port (kind "port")
+
+--impl reference times that CPU implementation alone on all host cores.
 """
 from __future__ import annotations
 
@@ -203,20 +202,44 @@ def build_c4(n_scans, seed):
     return poses[:, :2].copy(), flat, off
 
 
-# --------------------------------------------------------------------------- CPU baseline (oracle port)
+# --------------------------------------------------------------------------- CPU baseline (reference or oracle port)
+def _reference_kind():
+    """("reference", description) when oracle/_ref holds the packed, unmodified reference, else ("port", ...)."""
+    from oracle import ref_loader
+    if ref_loader.reference_root() is not None:
+        return "reference", "the UNMODIFIED reference utilities/icp.py::ICP from oracle/_ref (numpy + scipy KDTree)"
+    return "port", "oracle/icp_oracle.py (numpy + scipy KDTree restatement, same calls as the reference)"
+
+
+_REF_ICP = None
+
+
 def _cpu_icp_one(args):
+    """One registration on one core: (seconds, R, t, error, iters or -1, status or -1)."""
+    global _REF_ICP
     os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    src, tgt, kind = args
+    if kind == "reference":
+        if _REF_ICP is None:
+            from oracle import ref_loader
+            _REF_ICP = ref_loader.import_reference("utilities.icp").ICP
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            t0 = time.perf_counter()
+            R, t, err = _REF_ICP(src, tgt, ICP_CFG["error_threshold"], ICP_CFG["max_iterations"], ICP_CFG["voxel_size"],
+                                 method=ICP_CFG["method"], normal_k=ICP_CFG["normal_k"])
+            dt = time.perf_counter() - t0
+        return dt, R, t, float(err), -1, -1
     from oracle import icp_oracle
-    src, tgt = args
     t0 = time.perf_counter()
-    out = icp_oracle.register(src, tgt, **ICP_CFG)
-    return time.perf_counter() - t0, int(out[3])
+    R, t, err, iters, status = icp_oracle.register(src, tgt, **ICP_CFG)
+    return time.perf_counter() - t0, R, t, float(err), int(iters), int(status)
 
 
-def cpu_icp_baseline(scans, src_idx, tgt_idx, n_sample, cores):
-    """Oracle port timed on `cores` processes over n_sample disjoint pairs."""
-    sel = np.linspace(0, len(src_idx) - 1, n_sample).astype(int)
-    jobs = [(scans[src_idx[i]], scans[tgt_idx[i]]) for i in sel]
+def cpu_icp_run(scans, src_idx, tgt_idx, sel, cores, kind):
+    """Register the pairs `sel` on `cores` processes; returns (wall seconds of the map alone, list of results)."""
+    jobs = [(scans[src_idx[i]], scans[tgt_idx[i]], kind) for i in sel]
     os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = "1"     # inherited by the workers
     if cores > 1:
         # spawn: the parent may hold a CUDA context, which must not be forked
@@ -229,11 +252,19 @@ def cpu_icp_baseline(scans, src_idx, tgt_idx, n_sample, cores):
         t0 = time.perf_counter()
         res = [_cpu_icp_one(j) for j in jobs]
         wall = time.perf_counter() - t0
+    return wall, res
+
+
+def cpu_icp_baseline(scans, src_idx, tgt_idx, n_sample, cores):
+    """The reference's CPU registration timed on `cores` processes over n_sample pairs spread over the batch."""
+    kind, what = _reference_kind()
+    sel = np.linspace(0, len(src_idx) - 1, n_sample).astype(int)
+    wall, res = cpu_icp_run(scans, src_idx, tgt_idx, sel, cores, kind)
     per_call = float(np.mean([r[0] for r in res]))
-    return dict(value=n_sample / wall, unit="registrations/s", cores=cores, kind="port",
-                sample=f"{n_sample} of {len(src_idx)} pairs, oracle/icp_oracle.py (numpy+scipy KDTree), "
-                       f"{cores} processes x 1 thread; mean {per_call * 1e3:.1f} ms/registration/core",
-                one_core_value=1.0 / per_call, mean_iters=float(np.mean([r[1] for r in res])))
+    return dict(value=n_sample / wall, unit="registrations/s", cores=cores, kind=kind,
+                sample=f"{n_sample} of {len(src_idx)} pairs, {what}, {cores} processes x 1 thread; "
+                       f"mean {per_call * 1e3:.1f} ms/registration/core",
+                one_core_value=1.0 / per_call)
 
 
 def cpu_raycast_baseline(origins, flat, off, n_sample):
@@ -249,10 +280,62 @@ def cpu_raycast_baseline(origins, flat, off, n_sample):
                        f"update_scan measured 2.8k rays/s/core in BASELINE.md")
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch, from the round's `ncu --set full` captures of this command
-# (profiles/r01_ncu_icp_final.txt, profiles/r01_ncu_occ_final.txt); the occupancy figure is the sum over the update's kernels
-NCU_DRAM_BYTES = dict(icp_pairs_kernel=52.4e6 + 7.3e6, occupancy_update=645e6,
-                      source="ncu --set full, profiles/r01_ncu_icp_final.txt / r01_ncu_occ_final.txt (C2 / C4, round 1)")
+# --------------------------------------------------------------------------- verification of the timed outputs
+def verify_icp(scans, si, ti, res, n_spread, max_slow, cores):
+    """Compare the registrations the bench timed with the oracle port (bit-pinned against the live reference,
+    oracle/pin_against_reference.py) on a sample: n_spread pairs spread over the batch plus up to max_slow pairs that
+    hit the iteration limit.  Poses within north_star's 1e-4 m / 1e-5 rad, iteration counts and exit status equal."""
+    n = len(si)
+    sel = set(np.linspace(0, n - 1, min(n_spread, n)).astype(int).tolist())
+    slow = np.flatnonzero(res["status"] == 1)
+    sel |= set(slow[:max_slow].tolist())
+    sel = np.array(sorted(sel))
+    wall, ref = cpu_icp_run(scans, si, ti, sel, cores, "port")
+    dt = dr = de = 0.0
+    it_bad = st_bad = 0
+    for k, i in enumerate(sel):
+        _, R, t, err, iters, status = ref[k]
+        dt = max(dt, float(np.max(np.abs(res["t"][i] - t))))
+        rel = res["R"][i] @ R.T
+        dr = max(dr, abs(float(np.arctan2(rel[1, 0], rel[0, 0]))))
+        if np.isfinite(err) or np.isfinite(res["error"][i]):
+            de = max(de, abs(float(res["error"][i]) - err))
+        it_bad += int(res["iters"][i] != iters)
+        st_bad += int(res["status"][i] != status)
+    ok = dt < 1e-4 and dr < 1e-5 and st_bad == 0
+    out = dict(pairs_checked=int(len(sel)), iteration_limit_pairs_checked=int(min(len(slow), max_slow)),
+               max_translation_diff_m=dt, max_rotation_diff_rad=dr, max_error_diff=de,
+               iteration_count_mismatches=it_bad, status_mismatches=st_bad, ok=bool(ok),
+               checker="oracle/icp_oracle.py on the host cores, outside every timed region", seconds=wall)
+    if not ok:
+        raise SystemExit(f"bench.py: timed ICP outputs differ from the oracle: {out}")
+    return out
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch come from profiles/r02_ncu_traffic.json, written by
+# profiles/ncu_traffic.py from an `ncu --set full` capture of this command and keyed by a hash of the kernel sources: a
+# figure measured on other sources is reported as null, not silently reused.
+def source_hash():
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(PKG, "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            with open(os.path.join(d, name), "rb") as f:
+                h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(kernel):
+    path = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    if not os.path.exists(path):
+        return None, "no ncu capture committed for this round yet"
+    with open(path) as f:
+        d = json.load(f)
+    if d.get("source_hash") != source_hash():
+        return None, f"profiles/r02_ncu_traffic.json was captured on other kernel sources ({d.get('source_hash')}): stale, not reported"
+    v = d.get("dram_bytes_per_launch", {}).get(kernel)
+    return v, f"ncu --set full, profiles/r02_ncu_traffic.json ({d.get('command', '')})"
 
 
 # --------------------------------------------------------------------------- reference arm
@@ -260,7 +343,13 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    scans, poses, flat, off, si, ti = build_c2(args.scans, seed=0)
+    kind, what = _reference_kind()
+    if args.gpus > 1:
+        scans, poses, flat, off, si, ti = build_c5(args.scans, args.pairs, seed=0)
+        wl = f"C5 loop-closure candidate batch ({len(si)} pairs; bounded sample per step)"
+    else:
+        scans, poses, flat, off, si, ti = build_c2(args.scans, seed=0)
+        wl = "C2 scan-to-scan point_to_line ICP, 1080-beam 2-D scans (bounded sample per step)"
     n_sample = min(len(si), max(cores * 4, 128))
     for _ in range(max(args.warmup, 0)):
         cpu_icp_baseline(scans, si, ti, min(cores, 8), cores)
@@ -271,11 +360,10 @@ def run_reference(args, rank, world):
     value = n_sample * args.steps / sum(t_all)
     line = dict(metric="icp_registrations_per_s", value=value, unit="registrations/s", n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * float(np.mean(t_all)),
-                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-                impl="reference",
-                config=dict(workload="C2 scan-to-scan point_to_line ICP, 1080-beam 2-D scans (bounded sample per step)",
-                            pairs_per_step=n_sample, **{k: v for k, v in ICP_CFG.items()}),
-                cpu_baseline=dict(value=value, unit="registrations/s", cores=cores, kind="port", sample=last["sample"]),
+                higher_is_better=True, scaling="strong" if args.gpus > 1 else "weak", vs_baseline=None, dtype="f64",
+                data="synthetic", impl="reference",
+                config=dict(workload=wl, pairs_per_step=n_sample, **{k: v for k, v in ICP_CFG.items()}),
+                cpu_baseline=dict(value=value, unit="registrations/s", cores=cores, kind=kind, sample=last["sample"]),
                 e2e=dict(value=value, unit="registrations/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     _REAL_STDOUT.write(json.dumps(line) + "\n")
@@ -283,192 +371,249 @@ def run_reference(args, rank, world):
 
 
 # --------------------------------------------------------------------------- our arm
+class Env:
+    """What every leg needs: rank / world, device, streams, the library."""
+
+    def __init__(self, args, rank, world, local_rank):
+        import torch
+        from icp_b200 import _lib, api
+        self.args, self.rank, self.world, self.local_rank = args, rank, world, local_rank
+        self.torch, self.api, self.lib = torch, api, _lib.load()
+        self.dev = torch.device("cuda", local_rank)
+        self.pk = peaks()
+        self.stream = torch.cuda.Stream(device=self.dev)          # explicit stream: the library launches on it too
+        torch.cuda.set_stream(self.stream)
+        self.flush = torch.empty(512 << 20, dtype=torch.uint8, device=self.dev)        # > 126 MB L2
+        self.sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        if self.world == 1:
+            return list(vals)
+        import torch.distributed as dist
+        red = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        return [float(v) for v in red]
+
+
+def bench_icp(env, name, data, mode, steps, warmup, want_cpu, want_unpinned, verify):
+    """One ICP workload.  mode: "single" (one GPU), "strong" (one batch partitioned over the ranks) or "weak"
+    (every rank registers the whole batch).  Returns the result object (rank 0) or None."""
+    import torch
+    from icp_b200 import dist as icpd
+    api = env.api
+    scans, poses, flat, off, si, ti = data
+    n_pairs = len(si)
+    shard = icpd.DevicePairShard(flat, off, si, ti, env.dev, replicated=(mode != "strong"))
+    kw = {k: v for k, v in ICP_CFG.items()}
+
+    def step():
+        shard.enqueue(env.stream, **kw, gather=env.world > 1 or mode == "single")
+
+    for _ in range(max(warmup, 3)):
+        step()
+    env.barrier()
+    launches0 = api.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    with ClockSampler(env.local_rank) as clk:
+        env.barrier()
+        wall0 = time.perf_counter()
+        for a, b in ev:
+            env.flush.zero_()                   # evict L2 between timed iterations (outside the events)
+            a.record(env.stream)
+            step()
+            b.record(env.stream)
+        env.barrier()
+        wall = time.perf_counter() - wall0
+    launches = api.launch_count() - launches0
+    kstats = api.icp_last_stats()
+    phase = api.icp_phase_profile()
+    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    t_local = sum(ms_steps) / 1e3
+    clocks = clk.summary()
+    res = shard.results()                       # every pair of the batch, the caller's order (all ranks hold it)
+
+    # ---- e2e: host buffers through the public call (H2D from page-locked memory + kernels + D2H per step)
+    def e2e_call():
+        if mode == "strong" and env.world > 1:
+            return icpd.icp_pairs_sharded(flat, off, si, ti, **kw)
+        out = api.icp_pairs(flat, off, si, ti, **kw)
+        if mode == "weak" and env.world > 1:       # the path's only exchange: every rank's poses to every rank
+            icpd.gather_result_blocks(out, 2)
+        return out
+
+    def e2e_time(reps):
+        ts = []
+        for k in range(2 + reps):
+            env.barrier()
+            t0 = time.perf_counter()
+            out = e2e_call()
+            if k >= 2:
+                ts.append(time.perf_counter() - t0)
+        return float(np.mean(ts)), out
+
+    e2e_unpinned = None
+    if want_unpinned:
+        e2e_unpinned, _ = e2e_time(max(2, steps // 2))
+    pin = api.pinned(flat, off, si, ti)
+    e2e_s, out = e2e_time(steps)
+    pin.release()
+    assert np.array_equal(out["iters"], res["iters"]) and np.array_equal(out["status"], res["status"]), \
+        "host-buffer and device-resident paths disagree"
+    h2d = shard.h2d_bytes if mode == "strong" else flat.nbytes + off.nbytes + si.nbytes + ti.nbytes
+    d2h = sum(out[k].nbytes for k in ("R", "t", "error", "prev_error", "iters", "status"))
+    t_max, e2e_max, unp_max = env.max_over_ranks(t_local, e2e_s, e2e_unpinned or 0.0)
+    checked = None
+    if verify and env.rank == 0:
+        checked = verify_icp(scans, si, ti, res, *verify, os.cpu_count() or 1)
+    if env.rank != 0:
+        return None
+
+    # ---- roofline of the per-pair kernel K3 (this rank's share, last timed step)
+    iters, status = res["iters"].astype(np.int64), res["status"]
+    n_ds = np.array([voxel_count(s, ICP_CFG["voxel_size"]) for s in scans], dtype=np.int64)
+    mine = shard.plan[env.rank] if mode == "strong" else np.arange(n_pairs)
+    ns, nt = n_ds[si[mine]], n_ds[ti[mine]]
+    alg_evals = float(np.sum(iters[mine] * ns * nt + nt * nt))     # BASELINE.md section 4: brute force, + Mt^2 for the normals
+    exe_evals = float(kstats["sweep_pair_evals"])                   # fp32 evaluations the kernel really issued (device counter)
+    kernel_s = max(kstats["pair_kernel_ns"], 1) / 1e9               # K3 alone, CUDA events on its stream
+    clk_mhz = clocks["sm_mhz"] or env.pk["sm_max_mhz"]
+    peak_evals = env.sm_count * FMA_LANES_PER_SM * clk_mhz * 1e6 / FMA_INSTR_PER_PAIR_EVAL_2D
+    peak_tf = peak_evals * FLOP_PER_PAIR_EVAL_2D / 1e12
+    executed_tf = exe_evals * FLOP_PER_PAIR_EVAL_2D / kernel_s / 1e12
+    traffic, traffic_src = ncu_traffic("icp_pairs_kernel")
+    # latency model: a registration is a chain of dependent iterations; the kernel cannot finish before the busiest
+    # CTA slot has run its share of them, nor before the longest single chain has run
+    it_cycles = phase["cycles_per_iteration"]
+    slots = env.sm_count * 2
+    it_s = it_cycles / (clk_mhz * 1e6) if it_cycles else 0.0
+    lb_throughput = float(iters[mine].sum()) * it_s / slots
+    lb_chain = float(iters[mine].max()) * it_s if len(mine) else 0.0
+    roofline = dict(
+        bound="fp32_fma", achieved=executed_tf, peak=peak_tf, unit="TFLOP/s", frac=executed_tf / peak_tf,
+        traffic=traffic, traffic_source=traffic_src, kernel="icp_pairs_kernel<2> (bulk + hand-over launches)",
+        kernel_ms=kernel_s * 1e3, kernel_share_of_step=kernel_s * 1e3 / float(np.mean(ms_steps)),
+        voxel_kernel_ms=kstats["voxel_kernel_ns"] / 1e6, normals_kernel_ms=kstats["normals_kernel_ns"] / 1e6,
+        executed_pair_evals_per_launch=exe_evals, points_swept=kstats["points_swept"],
+        points_carried=kstats["points_carried"], fp64_rescans=kstats["fp64_rescans"],
+        note="achieved = fp32 pair evaluations the kernel EXECUTED (device counter) x 5 flop / kernel time: exact carry-over "
+             "and the voxel-ordered slab sweep leave a few percent of the brute-force evaluations, so the FMA pipe is not "
+             "what bounds this kernel -- the latency of its dependent per-iteration phases is (latency_model)",
+        algorithmic_equivalent=dict(
+            pair_evals_per_launch=alg_evals, tflops=alg_evals * FLOP_PER_PAIR_EVAL_2D / kernel_s / 1e12,
+            times_fma_ceiling=alg_evals * FLOP_PER_PAIR_EVAL_2D / kernel_s / 1e12 / peak_tf,
+            note="brute-force count of BASELINE.md section 4 (sum iters*Ns*Mt + Mt^2) the kernel would have to execute "
+                 "without pruning; NOT a roofline fraction (the work is not executed)"),
+        latency_model=dict(
+            cycles_per_converged_iteration=it_cycles, phase_cycles=phase["phases"], iterations=int(iters[mine].sum()),
+            longest_chain_iterations=int(iters[mine].max()) if len(mine) else 0, cta_slots=slots,
+            lower_bound_ms=1e3 * max(lb_throughput, lb_chain), frac_of_kernel_time=max(lb_throughput, lb_chain) / kernel_s,
+            note="lower bound = max(sum of iterations x measured converged-iteration time / CTA slots, longest chain x "
+                 "that time); early iterations (full sweeps) cost more, so the fraction stays below 1"),
+        peak_basis=f"{env.sm_count} SMs x {FMA_LANES_PER_SM} FP32 lanes x {clk_mhz:.0f} MHz (median SM clock sampled "
+                   f"during the timed region) / {FMA_INSTR_PER_PAIR_EVAL_2D} FMA-pipe instr per 2-D pair evaluation x "
+                   f"{FLOP_PER_PAIR_EVAL_2D} flop (BASELINE.md section 4)")
+    cores = os.cpu_count() or 1
+    cpu = cpu_icp_baseline(scans, si, ti, min(n_pairs, max(4 * cores, 256)), cores) if want_cpu else None
+    total = n_pairs * (env.world if mode == "weak" else 1)
+    sharding = {"single": "one GPU",
+                "strong": "ONE batch partitioned over the ranks (strong scaling): pairs sorted by their lower cloud index, cut "
+                          "into 4 chunks per rank dealt round-robin; a rank uploads / preprocesses only the clouds its pairs "
+                          "reference; no data-path collective; one NCCL all_gather of packed result blocks inside the timed region",
+                "weak": "every rank registers the whole batch (weak scaling, per-GPU work fixed); one NCCL all_gather of "
+                        "result blocks per step inside the timed region"}[mode]
+    return dict(metric="icp_registrations_per_s", value=total * steps / t_max, unit="registrations/s",
+                n_gpus=env.world, steps=steps, warmup=max(warmup, 3), ms_per_step=1e3 * t_max / steps,
+                higher_is_better=True, scaling="weak" if mode == "weak" else "strong", vs_baseline=None, dtype="f64",
+                data="synthetic",
+                config=dict(workload=name, pairs=n_pairs, pairs_this_rank=int(len(mine)), clouds_this_rank=int(shard.n_clouds),
+                            points_per_cloud_after_voxel=float(n_ds.mean()), mean_iterations=float(iters.mean()),
+                            converged=int((status == 0).sum()), max_iter_pairs=int((status == 1).sum()),
+                            l2="flushed between timed steps (512 MiB memset)", sharding=sharding, **ICP_CFG),
+                e2e=dict(value=total / e2e_max, unit="registrations/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                         api="icp_b200.dist.icp_pairs_sharded -> icpb200_icp_pairs (host buffers, blocking)" if mode == "strong"
+                             else "icpb200_icp_pairs (host buffers, blocking)",
+                         host_buffers="page-locked by the caller once (icpb200_pin_host), outside the timed region",
+                         unpinned=dict(value=total / unp_max, unit="registrations/s",
+                                       host_buffers="pageable numpy arrays") if want_unpinned else None),
+                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, clocks=clocks, verify=checked,
+                wall_s_timed_region=wall, peaks_source=env.pk["source"])
+
+
+def bench_online(env, scans):
+    """the slam.py main loop calls ICP() and update_scan() one at a time (slam.py:471-483, 557)."""
+    import contextlib
+    import io
+    from utilities import ICP, OccupancyGrid2D
+    from icp_b200 import synth
+    n = min(len(scans) - 1, 200)
+    lat = []
+    with contextlib.redirect_stdout(io.StringIO()):
+        for k in range(5):
+            ICP(scans[k], scans[k + 1], **ICP_CFG)
+        for k in range(n):
+            t0 = time.perf_counter()
+            ICP(scans[k], scans[k + 1], **ICP_CFG)
+            lat.append(time.perf_counter() - t0)
+    c4_scans, c4_poses = synth.make_sequence(120, world="campus", seed=0)
+    grid = OccupancyGrid2D(*GRID_BOUNDS, **GRID_CFG)
+    up = []
+    for k in range(120):
+        hits = synth.to_world_frame(c4_scans[k], c4_poses[k])
+        t0 = time.perf_counter()
+        grid.update_scan(c4_poses[k, :2], hits)
+        if k >= 20:
+            up.append(time.perf_counter() - t0)
+    grid._dev.close()
+    lat, up = np.array(lat) * 1e3, np.array(up) * 1e3
+    return dict(icp_call_ms=dict(median=float(np.median(lat)), p90=float(np.percentile(lat, 90)), calls=int(n)),
+                icp_calls_per_s=float(1e3 / np.mean(lat)),
+                update_scan_ms=dict(median=float(np.median(up)), p90=float(np.percentile(up, 90)), calls=int(len(up))),
+                note="sequential single calls through the drop-in shim (utilities.ICP / OccupancyGrid2D.update_scan), "
+                     "host numpy arrays in and out, wall clock per call")
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
-    import torch.distributed as dist
-    from icp_b200 import _lib, api
+    from icp_b200 import api
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; libicp_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     api.init(local_rank)
-    lib = _lib.load()
-    dev = torch.device("cuda", local_rank)
-    pk = peaks()
-
-    if args.workload == "c5":
-        scans, poses, flat, off, si, ti = build_c5(args.scans, args.pairs, seed=0)
-        wl = f"C5 loop-closure candidate batch: {len(si)} scan-pair point_to_line registrations from {args.scans} scans"
+    env = Env(args, rank, world, local_rank)
+    cpu_ok = not args.no_cpu and world == 1        # the CPU legs run at N = 1 only (measurement contract)
+    c2 = build_c2(args.scans, seed=0)
+    c2_name = f"C2 scan-to-scan point_to_line ICP: {len(c2[4])} consecutive pairs of {args.scans} synthetic 1080-beam 2-D scans"
+    c5 = c5_name = None
+    if not args.no_c5 or world > 1:
+        c5 = build_c5(args.scans, args.pairs, seed=0)
+        c5_name = (f"C5 loop-closure candidate batch: {len(c5[4])} scan-pair point_to_line registrations "
+                   f"(pairs within 3 m) from {args.scans} scans")
+    v = not args.no_verify and not args.no_cpu
+    if world == 1:
+        line = bench_icp(env, c2_name, c2, "single", args.steps, args.warmup, cpu_ok, True, (200, 128) if v else None)
+        if c5 is not None:
+            line["c5"] = bench_icp(env, c5_name, c5, "single", max(3, args.steps // 2), 3, False, False, (256, 128) if v else None)
     else:
-        scans, poses, flat, off, si, ti = build_c2(args.scans, seed=0)
-        wl = f"C2 scan-to-scan point_to_line ICP: {len(si)} consecutive pairs of {args.scans} synthetic 1080-beam 2-D scans"
-    n_pairs, dim = len(si), 2
-    max_pts = int(np.max(np.diff(off)))
-
-    # ---- device-resident inputs / outputs (torch owns the memory; the library gets raw pointers)
-    d_pts = torch.from_numpy(flat).to(dev)
-    d_off = torch.from_numpy(off).to(dev)
-    d_si, d_ti = torch.from_numpy(si).to(dev), torch.from_numpy(ti).to(dev)
-    d_R = torch.empty((n_pairs, 2, 2), dtype=torch.float64, device=dev)
-    d_t = torch.empty((n_pairs, 2), dtype=torch.float64, device=dev)
-    d_err = torch.empty(n_pairs, dtype=torch.float64, device=dev)
-    d_prev = torch.empty(n_pairs, dtype=torch.float64, device=dev)
-    d_it = torch.empty(n_pairs, dtype=torch.int32, device=dev)
-    d_st = torch.empty(n_pairs, dtype=torch.int32, device=dev)
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2
-    # pose exchange (world > 1): double-buffered and asynchronous -- the all_gather of step k runs on a side
-    # stream under the kernels of step k + 1; the tail of the last one is inside the timed region (see below)
-    gather_buf = [[torch.empty((n_pairs, 3), dtype=torch.float64, device=dev) for _ in range(world)] for _ in range(2)] \
-        if world > 1 else None
-    mine_buf = [torch.empty((n_pairs, 3), dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else None
-    pending = [None, None]
-    step_no = [0]
-    stream = torch.cuda.Stream(device=dev)          # explicit stream: the library launches on it too
-    comm_stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-
-    def step_resident():
-        rc = lib.icpb200_icp_pairs_dev(
-            len(off) - 1, dim, d_pts.data_ptr(), d_off.data_ptr(), max_pts, n_pairs, d_si.data_ptr(), d_ti.data_ptr(),
-            None, None, ICP_CFG["error_threshold"], ICP_CFG["max_iterations"], ICP_CFG["voxel_size"],
-            _lib.POINT_TO_LINE, ICP_CFG["normal_k"], -1.0, _lib.NN_AUTO,
-            d_R.data_ptr(), d_t.data_ptr(), d_err.data_ptr(), d_prev.data_ptr(), d_it.data_ptr(), d_st.data_ptr(),
-            stream.cuda_stream)
-        _lib.check(rc, "icpb200_icp_pairs_dev")
-        if world > 1:   # pose results (theta, tx, ty) to every rank: the path's only exchange
-            k = step_no[0] & 1
-            step_no[0] += 1
-            if pending[k] is not None:
-                pending[k].wait()                       # the gather that used these buffers two steps ago
-            mine = mine_buf[k]
-            torch.atan2(d_R[:, 1, 0], d_R[:, 0, 0], out=mine[:, 0])
-            mine[:, 1:].copy_(d_t)
-            comm_stream.wait_stream(stream)
-            with torch.cuda.stream(comm_stream):
-                pending[k] = dist.all_gather(gather_buf[k], mine, async_op=True)
-
-    def drain():
-        for k in (0, 1):
-            if pending[k] is not None:
-                pending[k].wait()
-                pending[k] = None
-        stream.wait_stream(comm_stream)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    drain()
-    barrier()
-    launches0 = api.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local_rank) as clk:
-        barrier()
-        wall0 = time.perf_counter()
-        for a, b in ev:
-            flush.zero_()                       # evict L2 between timed iterations (outside the events)
-            a.record(stream)
-            step_resident()
-            b.record(stream)
-        tail_a, tail_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tail_a.record(stream)
-        drain()                                 # whatever is left of the pose exchange counts
-        tail_b.record(stream)
-        barrier()
-        wall = time.perf_counter() - wall0
-    launches = api.launch_count() - launches0
-    kstats = api.icp_last_stats()
-    ms_steps = [a.elapsed_time(b) for a, b in ev]
-    t_local = (sum(ms_steps) + tail_a.elapsed_time(tail_b)) / 1e3
-    clocks = clk.summary()
-    iters = d_it.cpu().numpy().astype(np.int64)
-    status = d_st.cpu().numpy()
-
-    # ---- e2e: host buffers through the C ABI (H2D from page-locked memory + kernels + D2H per step)
-    pin = api.pinned(flat, off, si, ti)
-    e2e_t = []
-    for k in range(2 + args.steps):
-        barrier()
-        t0 = time.perf_counter()
-        out = api.icp_pairs(flat, off, si, ti, **ICP_CFG)
-        if world > 1:
-            mine = torch.from_numpy(np.column_stack([np.arctan2(out["R"][:, 1, 0], out["R"][:, 0, 0]), out["t"]])).to(dev)
-            dist.all_gather(gather_buf[0], mine)
-            torch.cuda.synchronize()
-        if k >= 2:
-            e2e_t.append(time.perf_counter() - t0)
-    pin.release()
-    h2d = flat.nbytes + off.nbytes + si.nbytes + ti.nbytes
-    d2h = sum(out[k].nbytes for k in ("R", "t", "error", "prev_error", "iters", "status"))
-    assert np.array_equal(out["iters"], iters.astype(np.int32)), "host-buffer and device-resident paths disagree"
-
-    # ---- max over ranks
-    t_max, e2e_max = t_local, float(np.mean(e2e_t))
-    if world > 1:
-        red = torch.tensor([t_local, e2e_max], dtype=torch.float64, device=dev)
-        dist.all_reduce(red, op=dist.ReduceOp.MAX)
-        t_max, e2e_max = float(red[0]), float(red[1])
-
+        line = bench_icp(env, c5_name, c5, "strong", args.steps, args.warmup, False, False, (128, 64) if v else None)
+        weak = bench_icp(env, c2_name, c2, "weak", max(3, args.steps // 2), 3, False, False, None)
+        if rank == 0:
+            line["c2_weak"] = weak
     occ = None
     if not args.no_raycast:
-        occ = bench_raycast(args, lib, api, dev, local_rank, pk, rank, world)      # all ranks take part
+        occ = bench_raycast(args, env.lib, api, env.dev, local_rank, env.pk, rank, world, verify=v)      # all ranks take part
     if rank != 0:
         return
-    # ---- roofline of the per-pair kernel K3 (rank 0's batch, last timed step)
-    n_ds = np.array([voxel_count(s, ICP_CFG["voxel_size"]) for s in scans], dtype=np.int64)
-    ns, nt = n_ds[si], n_ds[ti]
-    # brute-force pair evaluations = sum iters*Ns*Mt (+ Mt^2 once for the p2l normals)
-    alg_evals = float(np.sum(iters * ns * nt + nt * nt))
-    exe_evals = float(kstats["sweep_pair_evals"])              # fp32 sweep evaluations the kernel really issued
-    kernel_s = kstats["pair_kernel_ns"] / 1e9                  # K3 alone, CUDA events on its stream
-    clk_mhz = clocks["sm_mhz"] or pk["sm_max_mhz"]
-    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
-    peak_evals = sm_count * FMA_LANES_PER_SM * clk_mhz * 1e6 / FMA_INSTR_PER_PAIR_EVAL_2D
-    # The contract's `achieved` is ALGORITHMIC work / kernel time (brute-force pair evaluations x 5 flop).
-    # The kernel does not execute that work -- carried-over correspondences are not searched again and the
-    # voxel-ordered slab sweep visits ~150 of the ~800 targets -- so the figure may exceed the FMA-pipe ceiling;
-    # what the kernel really issued is reported next to it (executed_*).
-    achieved_tf = alg_evals * FLOP_PER_PAIR_EVAL_2D / kernel_s / 1e12
-    executed_tf = exe_evals * FLOP_PER_PAIR_EVAL_2D / kernel_s / 1e12
-    peak_tf = peak_evals * FLOP_PER_PAIR_EVAL_2D / 1e12
-    roofline = dict(bound="fp32_fma", achieved=achieved_tf, peak=peak_tf, unit="TFLOP/s", frac=achieved_tf / peak_tf,
-                    traffic=NCU_DRAM_BYTES["icp_pairs_kernel"], traffic_source=NCU_DRAM_BYTES["source"],
-                    kernel="icp_pairs_kernel<2>", kernel_ms=kernel_s * 1e3,
-                    kernel_share_of_step=kernel_s * 1e3 / float(np.mean(ms_steps)),
-                    voxel_kernel_ms=kstats["voxel_kernel_ns"] / 1e6, normals_kernel_ms=kstats["normals_kernel_ns"] / 1e6,
-                    algorithmic_pair_evals_per_launch=alg_evals, executed_pair_evals_per_launch=exe_evals,
-                    executed_tflops=executed_tf, executed_frac=executed_tf / peak_tf,
-                    points_swept=kstats["points_swept"], points_carried=kstats["points_carried"],
-                    fp64_rescans=kstats["fp64_rescans"],
-                    note="achieved = algorithmic (brute-force) pair evaluations of BASELINE.md section 4 x 5 flop / kernel "
-                         "time; the kernel reaches the same exact nearest neighbours with far fewer evaluations "
-                         "(executed_*): it is bound by the latency of its per-iteration phases, not by the FMA pipe",
-                    peak_basis=f"{sm_count} SMs x {FMA_LANES_PER_SM} FP32 lanes x {clk_mhz:.0f} MHz (median SM clock "
-                               f"sampled during the timed region) / {FMA_INSTR_PER_PAIR_EVAL_2D} FMA-pipe instr per 2-D "
-                               f"pair evaluation x {FLOP_PER_PAIR_EVAL_2D} flop (BASELINE.md section 4)")
-
-    cores = os.cpu_count() or 1
-    # the CPU leg runs at N = 1 only (measurement contract): at N > 1 the other ranks would sit in a barrier behind it
-    cpu = cpu_icp_baseline(scans, si, ti, min(n_pairs, max(4 * cores, 256)), cores) if not args.no_cpu and world == 1 else None
-
-    line = dict(metric="icp_registrations_per_s", value=world * n_pairs * args.steps / t_max, unit="registrations/s",
-                n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=1e3 * t_max / args.steps,
-                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-                config=dict(workload=wl, pairs_per_gpu=n_pairs, points_per_cloud_after_voxel=float(n_ds.mean()),
-                            mean_iterations=float(iters.mean()), converged=int((status == 0).sum()),
-                            max_iter_pairs=int((status == 1).sum()), l2="flushed between timed steps (512 MiB memset)",
-                            sharding="pairs partitioned by rank (weak scaling: every rank registers the same 1999-pair batch, so the per-GPU work is fixed), no data-path collective; one asynchronous NCCL all_gather of poses per step",
-                            **ICP_CFG),
-                e2e=dict(value=world * n_pairs / e2e_max, unit="registrations/s", h2d_bytes_per_step=int(h2d),
-                         d2h_bytes_per_step=int(d2h), api="icpb200_icp_pairs (host buffers, blocking)"),
-                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, clocks=clocks,
-                wall_s_timed_region=wall, peaks_source=pk["source"])
     if occ is not None:
         line["occupancy"] = occ
-    if not args.no_extras:
+    if world == 1 and not args.no_extras:
+        line["online"] = bench_online(env, c2[0])
         line["extras"] = bench_extras(args, api)
     if args.no_icp_line:
         line = line["occupancy"]
@@ -476,7 +621,7 @@ def run_ours(args, rank, world, local_rank):
     _REAL_STDOUT.flush()
 
 
-def bench_raycast(args, lib, api, dev, local_rank, pk, rank=0, world=1):
+def bench_raycast(args, lib, api, dev, local_rank, pk, rank=0, world=1, verify=False):
     """C4: 2000 scans x 1080 rays into a 4096 x 4096 grid @ 5 cm.
 
     Multi-GPU: the grid is cut into horizontal strips of 64-cell tile rows, one per rank;
@@ -541,6 +686,21 @@ def bench_raycast(args, lib, api, dev, local_rank, pk, rank=0, world=1):
             e2e_t.append(time.perf_counter() - t0)
     e2e_s = float(np.mean(e2e_t))
     pin.release()
+    checked = None
+    if verify and rank == 0:
+        # the map the e2e leg just read back (reassembled from every rank's share at N > 1) against the C oracle of
+        # mapping.py:103-141 run over the SAME 2000-scan batch: bit for bit
+        from oracle import occupancy_oracle
+        t0 = time.perf_counter()
+        ref = occupancy_oracle.GridOracleC(*GRID_BOUNDS, **GRID_CFG)
+        ref.update_many(origins, flat, off, fast=True)
+        same = host_out.tobytes() == ref.log_odds.tobytes()
+        checked = dict(bit_exact=bool(same), cells=int(host_out.size), nonzero_cells=int(np.count_nonzero(ref.log_odds)),
+                       differing_cells=int(np.count_nonzero(host_out != ref.log_odds)), scans=int(len(off) - 1),
+                       checker="oracle/occupancy_oracle.c over the whole batch, outside every timed region",
+                       seconds=time.perf_counter() - t0)
+        if not same:
+            raise SystemExit(f"bench.py: the timed occupancy map differs from the oracle: {checked}")
     cells, hits_in = float(st["traversed"]), float(st["hits"])
     if world > 1:
         red = torch.tensor([sec, e2e_s, sec_update], dtype=torch.float64, device=dev)
@@ -564,8 +724,9 @@ def bench_raycast(args, lib, api, dev, local_rank, pk, rank=0, world=1):
                          h2d_bytes_per_step=int(origins.nbytes + flat.nbytes + off.nbytes),
                          d2h_bytes_per_step=int(host_out.nbytes), api="icpb200_grid_update + icpb200_grid_read"),
                 gpu_launches=int(launches),
+                verify=checked,
                 roofline=dict(bound="hbm", achieved=alg_bytes / sec / 1e9 / world, peak=pk["hbm_gbs"], unit="GB/s",
-                              frac=alg_bytes / sec / 1e9 / world / pk["hbm_gbs"], traffic=NCU_DRAM_BYTES["occupancy_update"], traffic_source=NCU_DRAM_BYTES["source"],
+                              frac=alg_bytes / sec / 1e9 / world / pk["hbm_gbs"], traffic=ncu_traffic("occupancy_update")[0], traffic_source=ncu_traffic("occupancy_update")[1],
                               kernel="occ_fast_tiles + binning passes + hit-cell replay (the whole update is timed); per GPU",
                               algorithmic_bytes=alg_bytes, peak_basis=f"{pk['source']} HBM copy bandwidth"),
                 cpu_baseline=cpu, clocks=clk.summary())
@@ -690,13 +851,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c5"])
     ap.add_argument("--scans", type=int, default=2000)
     ap.add_argument("--pairs", type=int, default=8192)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-raycast", action="store_true", help="skip the occupancy (C4) leg")
     ap.add_argument("--no-icp-line", action="store_true", help="print only the occupancy object (profiling aid)")
-    ap.add_argument("--no-extras", action="store_true", help="skip the C1 / C3 extras")
+    ap.add_argument("--no-extras", action="store_true", help="skip the online / C1 / C3 extras")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 object of the one-GPU line")
+    ap.add_argument("--no-verify", action="store_true", help="skip the comparison of the timed outputs with the oracle")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

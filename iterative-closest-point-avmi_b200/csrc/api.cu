@@ -538,18 +538,49 @@ int icpb200_icp_pairs(int n_clouds, int dim, const double* pts, const int64_t* c
     static const bool e2e_timing = getenv("ICPB200_E2E_TIMING") != nullptr;
     static const bool no_chunk = getenv("ICPB200_NO_CHUNK") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
+    // Only the clouds some pair references cross PCIe (a loop-closure batch names a few scans of a long history,
+    // slam.py:575-579; a rank of a sharded batch names its own block's): runs of referenced clouds are copied, gaps of
+    // up to 64 KB are bridged rather than paid for with another copy call.  Chunk boundaries balance the bytes copied.
+    std::vector<unsigned char> used((size_t)n_clouds, 0);
+    for (int p = 0; p < n_pairs; ++p) used[(size_t)src_idx[p]] = used[(size_t)tgt_idx[p]] = 1;
+    size_t used_rows = 0;
+    for (int i = 0; i < n_clouds; ++i) if (used[(size_t)i]) used_rows += (size_t)(cloud_off[i + 1] - cloud_off[i]);
     UploadPlan plan;
-    plan.n_chunks = (int)std::max<size_t>(1, std::min<size_t>(kUploadChunks, np * dim * sizeof(double) / (4u << 20)));
+    plan.n_chunks = (int)std::max<size_t>(1, std::min<size_t>(kUploadChunks, used_rows * dim * sizeof(double) / (4u << 20)));
     if (no_chunk) plan.n_chunks = 1;
     plan.n_chunks = std::min(plan.n_chunks, n_clouds);
-    for (int ch = 0; ch <= plan.n_chunks; ++ch) plan.first[ch] = (int)((long long)n_clouds * ch / plan.n_chunks);
+    {
+        plan.first[0] = 0;
+        size_t seen = 0;
+        int ch = 1;
+        for (int i = 0; i < n_clouds && ch < plan.n_chunks; ++i) {
+            if (used[(size_t)i]) seen += (size_t)(cloud_off[i + 1] - cloud_off[i]);
+            if (seen * (size_t)plan.n_chunks >= used_rows * (size_t)ch) plan.first[ch++] = i + 1;
+        }
+        for (; ch <= plan.n_chunks; ++ch) plan.first[ch] = n_clouds;
+    }
+    const long long bridge_rows = (64 << 10) / (long long)(sizeof(double) * dim);
     for (int ch = 0; ch < plan.n_chunks; ++ch) {
-        const size_t b0 = (size_t)cloud_off[plan.first[ch]] * dim, b1 = (size_t)cloud_off[plan.first[ch + 1]] * dim;
-        ICPB_CUDA(cudaMemcpyAsync(c.pts_a.as<double>() + b0, pts + b0, sizeof(double) * (b1 - b0), cudaMemcpyHostToDevice, c.copy_stream));
+        int i = plan.first[ch];
+        const int end = plan.first[ch + 1];
+        while (i < end) {
+            while (i < end && !used[(size_t)i]) ++i;
+            if (i >= end) break;
+            int j = i + 1, last_used = i;                     // extend the run over small gaps
+            while (j < end) {
+                if (used[(size_t)j]) last_used = j;
+                else if (cloud_off[j + 1] - cloud_off[last_used + 1] > bridge_rows) break;
+                ++j;
+            }
+            const size_t b0 = (size_t)cloud_off[i] * dim, b1 = (size_t)cloud_off[last_used + 1] * dim;
+            ICPB_CUDA(cudaMemcpyAsync(c.pts_a.as<double>() + b0, pts + b0, sizeof(double) * (b1 - b0), cudaMemcpyHostToDevice, c.copy_stream));
+            i = last_used + 1;
+        }
         ICPB_CUDA(cudaEventRecord(c.chunk_ev[ch], c.copy_stream));
     }
     const double *d_Ri, *d_ti;
-    if ((rc = upload_init(c, n_pairs, dim, R_init, t_init, &d_Ri, &d_ti))) return rc;
+    // from here on the caller's (possibly page-locked) buffer is being read by the copy stream: every error return waits for it
+    if ((rc = upload_init(c, n_pairs, dim, R_init, t_init, &d_Ri, &d_ti))) { cudaStreamSynchronize(c.copy_stream); cudaStreamSynchronize(c.stream); return rc; }
     long long max_src = 0, max_tgt = 0;
     // pairs by the last upload chunk they need (see UploadPlan)
     std::vector<int> group((size_t)n_pairs);
@@ -574,7 +605,7 @@ int icpb200_icp_pairs(int n_clouds, int dim, const double* pts, const int64_t* c
         int cursor[kUploadChunks];
         for (int g = 0; g < kUploadChunks; ++g) cursor[g] = plan.group_first[g];
         for (int p = 0; p < n_pairs; ++p) order[(size_t)cursor[group[(size_t)p]]++] = p;
-        if (c.idx_order.reserve(sizeof(int) * (size_t)n_pairs)) return ICPB200_ERR_CUDA;
+        if (c.idx_order.reserve(sizeof(int) * (size_t)n_pairs)) { cudaStreamSynchronize(c.copy_stream); cudaStreamSynchronize(c.stream); return ICPB200_ERR_CUDA; }
         // pageable source: the copy is staged before the call returns, `order` may go out of scope afterwards
         ICPB_CUDA(cudaMemcpyAsync(c.idx_order.p, order.data(), sizeof(int) * (size_t)n_pairs, cudaMemcpyHostToDevice, c.stream));
         plan.d_order = c.idx_order.as<int>();
@@ -584,7 +615,7 @@ int icpb200_icp_pairs(int n_clouds, int dim, const double* pts, const int64_t* c
     rc = icp_enqueue(k, n_pairs, s, t, true, c.idx_a.as<int>(), c.idx_b.as<int>(), d_Ri, d_ti, c.out_r.as<double>(),
                      c.out_t.as<double>(), c.out_err.as<double>(), c.out_prev.as<double>(), c.out_iters.as<int>(),
                      c.out_status.as<int>(), c.stream, IcpTrace{}, nullptr, &plan);
-    if (rc) { cudaStreamSynchronize(c.copy_stream); return rc; }
+    if (rc) { cudaStreamSynchronize(c.copy_stream); cudaStreamSynchronize(c.stream); return rc; }
     if (e2e_timing) {
         const auto t_enq = std::chrono::steady_clock::now();
         cudaStreamSynchronize(c.copy_stream);

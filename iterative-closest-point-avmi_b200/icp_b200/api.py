@@ -129,6 +129,16 @@ def icp_last_stats():
                 pair_kernel_ns=int(st[7]))
 
 
+def icp_phase_profile():
+    """Thread 0's SM cycles per phase of a pair-kernel iteration, averaged over iterations >= 8 of the last call."""
+    st = np.zeros(8, dtype=np.int64)
+    check(_lib.load().icpb200_icp_phase_profile(_ptr(st, c_int64_p)), "icpb200_icp_phase_profile")
+    n = max(int(st[5]), 1)
+    names = ("classify", "nearest_neighbour", "accumulate", "solve", "apply_error")
+    phases = {k: float(st[i]) / n for i, k in enumerate(names)}
+    return dict(phases=phases, iterations_profiled=int(st[5]), cycles_per_iteration=float(sum(phases.values())) if st[5] else 0.0)
+
+
 def voxel_downsample(points, voxel_size):
     pts = _f64(points)
     out = np.empty_like(pts)

@@ -1,8 +1,10 @@
 """One-process-per-GPU sharding of the two batch seams (torch.distributed).
 
-* registrations: pairs are independent, so rank r registers a contiguous block
-  of the pair list with no data-path collective; one all_gather returns every
-  rank's (R, t, error, iters, status) to all ranks.
+* registrations: pairs are independent, so every rank registers its share of the
+  pair list (plan_pair_shards: locality-sorted chunks dealt round-robin) with no
+  data-path collective and uploads only the clouds its pairs reference; one
+  all_gather of packed result blocks returns (R, t, error, iters, status) of
+  every pair to all ranks.
 * occupancy replay: rank r owns a horizontal strip of the grid -- the 64-cell tile
   rows [r*T/world, (r+1)*T/world) (the rule libicp_b200 applies in
   icpb200_grid_set_shard); every rank replays every scan clipped to its own strip,
@@ -38,39 +40,178 @@ def _comm_device():
     return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
 
 
-def icp_pairs_sharded(points, cloud_off, src_idx, tgt_idx, *args, compute=None, R_init=None, t_init=None, **kw):
-    """Register all pairs, each rank doing its block; every rank returns the full result dict.
+def plan_pair_shards(src_idx, tgt_idx, size, chunks_per_rank=4):
+    """Which pairs each of ``size`` ranks registers: a list of index arrays into the pair list.
 
-    ``compute`` defaults to :func:`icp_b200.api.icp_pairs` (tests inject a CPU stand-in)."""
+    Pairs are sorted by the lower of their two cloud indices and cut into ``size * chunks_per_rank`` contiguous
+    chunks that are dealt round-robin.  A rank's pairs then name a few contiguous ranges of the scan history, so
+    the upload and the per-cloud kernels (voxel means, normals) shard with the pairs instead of being repeated on
+    every rank, while a stretch of slow pairs (the reference's limit cycles) is spread over all ranks.
+    Every rank computes the same plan from the same arguments -- nothing is exchanged."""
+    src_idx = np.asarray(src_idx)
+    tgt_idx = np.asarray(tgt_idx)
+    n = len(src_idx)
+    order = np.argsort(np.minimum(src_idx, tgt_idx), kind="stable")
+    n_chunks = max(1, size * chunks_per_rank)
+    bounds = (np.arange(n_chunks + 1, dtype=np.int64) * n) // n_chunks
+    plan = []
+    for r in range(size):
+        parts = [order[bounds[c]:bounds[c + 1]] for c in range(r, n_chunks, size)]
+        plan.append(np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64))
+    return plan
+
+
+_FIELDS = (("R", np.float64, lambda d: d * d), ("t", np.float64, lambda d: d), ("error", np.float64, lambda d: 1),
+           ("prev_error", np.float64, lambda d: 1), ("iters", np.int32, lambda d: 1), ("status", np.int32, lambda d: 1))
+
+
+def result_layout(n_max, dim):
+    """Byte layout of one rank's result block (every field padded to n_max pairs): {name: (offset, dtype, width)}, total."""
+    at, out = 0, {}
+    for name, dt, width in _FIELDS:
+        out[name] = (at, dt, width(dim))
+        at += (n_max * width(dim) * np.dtype(dt).itemsize + 63) // 64 * 64
+    return out, at
+
+
+def _unpack_results(blocks, plan, dim):
+    """blocks: (size, bytes) uint8 array of the gathered result blocks -> full result dict in the caller's pair order."""
+    n = sum(len(p) for p in plan)
+    n_max = max(len(p) for p in plan)
+    layout, _ = result_layout(n_max, dim)
+    full = dict(R=np.empty((n, dim, dim)), t=np.empty((n, dim)), error=np.empty(n), prev_error=np.empty(n),
+                iters=np.empty(n, dtype=np.int32), status=np.empty(n, dtype=np.int32))
+    for r, mine in enumerate(plan):
+        for name, (at, dt, width) in layout.items():
+            vals = np.frombuffer(blocks[r], dtype=dt, count=len(mine) * width, offset=at)
+            full[name][mine] = vals.reshape((len(mine),) + full[name].shape[1:])
+    return full
+
+
+def icp_pairs_sharded(points, cloud_off, src_idx, tgt_idx, *args, compute=None, R_init=None, t_init=None,
+                      chunks_per_rank=4, **kw):
+    """Register all pairs, each rank doing its share (:func:`plan_pair_shards`); every rank returns the full result
+    dict in the caller's pair order.  Host buffers in, host arrays out: the batch seam of slam.py:575-579.
+
+    A rank hands the library the whole scan history and its own pairs; ``icpb200_icp_pairs`` uploads only the clouds
+    those pairs reference.  One all_gather of the packed result blocks is the only exchange.
+    ``compute`` defaults to :func:`icp_b200.api.icp_pairs` (the gloo tests inject a CPU stand-in)."""
     if compute is None:
         from .api import icp_pairs as compute
     rank, size = world()
-    src_idx = np.asarray(src_idx, dtype=np.int32)
-    tgt_idx = np.asarray(tgt_idx, dtype=np.int32)
-    n = len(src_idx)
-    lo, hi = shard_range(n, rank, size)
-    if R_init is not None and t_init is not None:
-        kw = dict(kw, R_init=np.asarray(R_init)[lo:hi], t_init=np.asarray(t_init)[lo:hi])
-    part = compute(points, cloud_off, src_idx[lo:hi], tgt_idx[lo:hi], *args, **kw) if hi > lo else None
+    src_idx = np.ascontiguousarray(src_idx, dtype=np.int32)
+    tgt_idx = np.ascontiguousarray(tgt_idx, dtype=np.int32)
     if size == 1:
-        return part
+        if R_init is not None and t_init is not None:
+            kw = dict(kw, R_init=R_init, t_init=t_init)
+        return compute(points, cloud_off, src_idx, tgt_idx, *args, **kw)
+    plan = plan_pair_shards(src_idx, tgt_idx, size, chunks_per_rank)
+    mine = plan[rank]
+    if R_init is not None and t_init is not None:
+        kw = dict(kw, R_init=np.asarray(R_init)[mine], t_init=np.asarray(t_init)[mine])
+    part = compute(points, cloud_off, src_idx[mine], tgt_idx[mine], *args, **kw) if len(mine) else None
     dim = int(np.asarray(points).shape[1])
-    width = dim * dim + dim + 2 + 2                       # R | t | error, prev_error | iters, status
-    counts = [shard_range(n, r, size)[1] - shard_range(n, r, size)[0] for r in range(size)]
-    dev = _comm_device()
-    mine = torch.zeros((max(counts), width), dtype=torch.float64, device=dev)
+    layout, nbytes = result_layout(max(len(p) for p in plan), dim)
+    block = np.zeros(nbytes, dtype=np.uint8)
     if part is not None:
-        packed = np.concatenate([part["R"].reshape(hi - lo, -1), part["t"], part["error"][:, None],
-                                 part["prev_error"][:, None], part["iters"][:, None].astype(np.float64),
-                                 part["status"][:, None].astype(np.float64)], axis=1)
-        mine[:hi - lo] = torch.from_numpy(packed).to(dev)
-    bufs = [torch.empty_like(mine) for _ in range(size)]
-    dist.all_gather(bufs, mine)
-    full = np.concatenate([b[:c].cpu().numpy() for b, c in zip(bufs, counts)], axis=0)
-    dd = dim * dim
-    return dict(R=full[:, :dd].reshape(n, dim, dim), t=full[:, dd:dd + dim], error=full[:, dd + dim],
-                prev_error=full[:, dd + dim + 1], iters=full[:, dd + dim + 2].astype(np.int32),
-                status=full[:, dd + dim + 3].astype(np.int32))
+        for name, (at, dt, width) in layout.items():
+            vals = np.ascontiguousarray(part[name], dtype=dt).reshape(-1)
+            block[at:at + vals.nbytes] = vals.view(np.uint8)
+    dev = _comm_device()
+    send = torch.from_numpy(block).to(dev)
+    if dist.get_backend() == "nccl":
+        recv = torch.empty((size, nbytes), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(recv, send)
+        blocks = recv.cpu().numpy()
+    else:
+        bufs = [torch.empty_like(send) for _ in range(size)]
+        dist.all_gather(bufs, send)
+        blocks = np.stack([b.cpu().numpy() for b in bufs])
+    return _unpack_results(blocks, plan, dim)
+
+
+def gather_result_blocks(part, dim):
+    """all_gather of one rank's result dict (host arrays) as a packed block; returns the (size, bytes) uint8 array."""
+    rank, size = world()
+    n = len(part["iters"])
+    layout, nbytes = result_layout(n, dim)
+    block = np.zeros(nbytes, dtype=np.uint8)
+    for name, (at, dt, width) in layout.items():
+        vals = np.ascontiguousarray(part[name], dtype=dt).reshape(-1)
+        block[at:at + vals.nbytes] = vals.view(np.uint8)
+    if size == 1:
+        return block[None]
+    dev = _comm_device()
+    send = torch.from_numpy(block).to(dev)
+    bufs = [torch.empty_like(send) for _ in range(size)]
+    dist.all_gather(bufs, send)
+    return np.stack([b.cpu().numpy() for b in bufs])
+
+
+class DevicePairShard:
+    """This rank's share of a pair batch, resident in HBM: the clouds its pairs reference (compacted), its pair
+    lists and one packed result block.  ``enqueue()`` runs the registration stream-ordered (icpb200_icp_pairs_dev)
+    and gathers every rank's result block with one NCCL all_gather; ``results()`` unpacks them on the host."""
+
+    def __init__(self, points, cloud_off, src_idx, tgt_idx, device, chunks_per_rank=4, replicated=False):
+        """replicated = True: every rank registers the WHOLE batch (weak scaling); the gather then moves every
+        rank's full result block."""
+        from . import _lib
+        self._lib_mod = _lib
+        self.lib = _lib.load()
+        self.rank, self.size = world()
+        points = np.asarray(points, dtype=np.float64)
+        off = np.asarray(cloud_off, dtype=np.int64)
+        src_idx = np.asarray(src_idx, dtype=np.int32)
+        tgt_idx = np.asarray(tgt_idx, dtype=np.int32)
+        self.dim = int(points.shape[1])
+        self.replicated = bool(replicated) or self.size == 1
+        if self.replicated:
+            self.plan = [np.arange(len(src_idx), dtype=np.int64)] * self.size
+        else:
+            self.plan = plan_pair_shards(src_idx, tgt_idx, self.size, chunks_per_rank)
+        mine = self.plan[self.rank]
+        self.n_mine = len(mine)
+        used = np.unique(np.concatenate([src_idx[mine], tgt_idx[mine]])) if self.n_mine else np.zeros(0, dtype=np.int64)
+        remap = np.full(len(off) - 1, -1, dtype=np.int32)
+        remap[used] = np.arange(len(used), dtype=np.int32)
+        lens = off[used + 1] - off[used]
+        new_off = np.zeros(len(used) + 1, dtype=np.int64)
+        new_off[1:] = np.cumsum(lens)
+        flat = np.concatenate([points[off[c]:off[c + 1]] for c in used]) if len(used) else np.zeros((0, self.dim))
+        self.n_clouds, self.max_pts = len(used), int(lens.max()) if len(used) else 0
+        self.h2d_bytes = flat.nbytes + new_off.nbytes + 2 * 4 * self.n_mine
+        self.d_pts = torch.from_numpy(flat).to(device)
+        self.d_off = torch.from_numpy(new_off).to(device)
+        self.d_si = torch.from_numpy(remap[src_idx[mine]]).to(device)
+        self.d_ti = torch.from_numpy(remap[tgt_idx[mine]]).to(device)
+        self.layout, self.nbytes = result_layout(max(len(p) for p in self.plan), self.dim)
+        self.block = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+        self.gathered = torch.zeros((self.size, self.nbytes), dtype=torch.uint8, device=device)
+        self._ptr = {name: self.block.data_ptr() + at for name, (at, _, _) in self.layout.items()}
+
+    def enqueue(self, stream, error_threshold, max_iterations, voxel_size, method="point_to_point", normal_k=10,
+                max_corr_dist=None, gather=True):
+        """Stream-ordered on ``stream`` (a torch.cuda.Stream that is also torch's current stream)."""
+        L = self._lib_mod
+        if self.n_mine:
+            rc = self.lib.icpb200_icp_pairs_dev(
+                self.n_clouds, self.dim, self.d_pts.data_ptr(), self.d_off.data_ptr(), self.max_pts, self.n_mine,
+                self.d_si.data_ptr(), self.d_ti.data_ptr(), None, None, float(error_threshold), int(max_iterations),
+                float(voxel_size), L.POINT_TO_LINE if method == "point_to_line" else L.POINT_TO_POINT, int(normal_k),
+                -1.0 if max_corr_dist is None else float(max_corr_dist), L.NN_AUTO,
+                self._ptr["R"], self._ptr["t"], self._ptr["error"], self._ptr["prev_error"], self._ptr["iters"],
+                self._ptr["status"], stream.cuda_stream)
+            L.check(rc, "icpb200_icp_pairs_dev")
+        if gather and self.size > 1:
+            dist.all_gather_into_tensor(self.gathered, self.block)
+
+    def results(self):
+        """Full result dict in the caller's pair order (host arrays); call after a gathered enqueue()."""
+        torch.cuda.synchronize()
+        if self.replicated:
+            return _unpack_results(self.block.cpu().numpy()[None], self.plan[:1], self.dim)
+        return _unpack_results(self.gathered.cpu().numpy(), self.plan, self.dim)
 
 
 def strip_rows(ny, rank, size):

@@ -8,8 +8,11 @@ so using it means replacing that one function -- see INTEGRATION.md section 3).
 Both run every angle of a sweep in ONE launch of libicp_b200's rotation-score
 kernel: the angle lists, the argmin and the output transform are computed on
 the host exactly as the reference computes them.  The rest of
-``utilities/features.py`` (curvature key points, RANSAC) is outside the
-accelerated path and stays the reference's.
+``utilities/features.py`` (curvature key points, descriptors, RANSAC behind
+``feature_based_alignment``, features.py:22-160, 247-315) is outside the
+accelerated path and stays the reference's: when this package shadows the
+reference's ``utilities`` (second option) those names are
+adopted from the reference's own ``features.py`` found through the package path.
 """
 import os
 import sys
@@ -87,3 +90,33 @@ def submap_rotation_search(source_local, submap_global, predicted_pose, angle_ra
     else:
         refined_t = pred_t
     return R_best, refined_t
+
+
+# ---- the rest of the reference's module, unchanged (fall-through) -----------------------------------
+def _adopt_reference_features():
+    """Load the reference's own utilities/features.py (the next one on the package path) as a private submodule and
+    re-export every public name this file does not replace.  Its `from .icp import voxel_downsample`
+    (features.py:198, 276) then resolves to this package's GPU `voxel_downsample`."""
+    import importlib.util
+    pkg = sys.modules.get(__package__)
+    for d in list(getattr(pkg, "__path__", []))[1:]:
+        path = os.path.join(d, "features.py")
+        if not os.path.isfile(path):
+            continue
+        spec = importlib.util.spec_from_file_location(__package__ + "._reference_features", path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[spec.name] = mod
+        spec.loader.exec_module(mod)
+        for name in dir(mod):
+            if not name.startswith("__") and name not in globals():
+                globals()[name] = getattr(mod, name)
+        return True
+    return False
+
+
+if not _adopt_reference_features():
+    def feature_based_alignment(*args, **kwargs):
+        """features.py:247-315 is not part of the accelerated path; it is the reference's own function whenever the
+        reference is importable (see the module docstring)."""
+        raise ImportError("utilities.features.feature_based_alignment is the reference's own function: put the reference "
+                          "root on sys.path behind this package (INTEGRATION.md section 1)")

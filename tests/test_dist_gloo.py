@@ -44,8 +44,8 @@ def _worker(rank, size, port, tmp):
         t0 = np.tile([0.01, -0.01], (7, 1))
         cfg = dict(error_threshold=1e-7, max_iterations=20, voxel_size=0.3, method="point_to_point")
         got = icpd.icp_pairs_sharded(flat, off, si, ti, compute=_icp_oracle_pairs, R_init=R0, t_init=t0, **cfg)
-        lo, hi = icpd.shard_range(7, rank, size)
-        assert (lo, hi) == ((0, 4) if rank == 0 else (4, 7))
+        plan = icpd.plan_pair_shards(si, ti, size)
+        assert sorted(np.concatenate(plan).tolist()) == list(range(7)) and abs(len(plan[0]) - len(plan[1])) <= 1
         want = _icp_oracle_pairs(flat, off, si, ti, R_init=R0, t_init=t0, **cfg)
         for key in ("R", "t", "error", "iters", "status"):
             assert np.array_equal(got[key], want[key]), key
@@ -83,3 +83,41 @@ def test_shard_ranges_cover_everything():
             assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
             lens = [b - a for a, b in blocks]
             assert max(lens) - min(lens) <= 1
+
+
+def test_pair_shard_plan_is_a_partition_with_locality():
+    """Every pair lands on exactly one rank, shares differ by a few pairs, and a rank's pairs name a small part of the
+    scan history (so the upload and the per-cloud kernels shard with the pairs)."""
+    from icp_b200 import dist as icpd, synth
+    poses = synth.room_trajectory(2000)
+    pairs = synth.loop_closure_pairs(poses, 8192, seed=0, max_dist=3.0)
+    si, ti = pairs[:, 0], pairs[:, 1]
+    for size in (1, 2, 3, 8):
+        plan = icpd.plan_pair_shards(si, ti, size)
+        allp = np.concatenate(plan)
+        assert len(allp) == 8192 and np.array_equal(np.sort(allp), np.arange(8192))
+        lens = [len(p) for p in plan]
+        assert max(lens) - min(lens) <= 4 * size
+        if size == 8:
+            for p in plan:
+                used = np.unique(np.concatenate([si[p], ti[p]]))
+                assert len(used) < 0.45 * 2000, len(used)
+
+
+def test_result_block_round_trip():
+    from icp_b200 import dist as icpd
+    rng = np.random.default_rng(0)
+    n, dim, size = 37, 2, 3
+    si = rng.integers(0, 50, n); ti = rng.integers(0, 50, n)
+    plan = icpd.plan_pair_shards(si, ti, size)
+    want = dict(R=rng.normal(size=(n, 2, 2)), t=rng.normal(size=(n, 2)), error=rng.normal(size=n), prev_error=rng.normal(size=n),
+                iters=rng.integers(0, 150, n).astype(np.int32), status=rng.integers(0, 3, n).astype(np.int32))
+    layout, nbytes = icpd.result_layout(max(len(p) for p in plan), dim)
+    blocks = np.zeros((size, nbytes), dtype=np.uint8)
+    for r, mine in enumerate(plan):
+        for name, (at, dt, width) in layout.items():
+            vals = np.ascontiguousarray(want[name][mine], dtype=dt).reshape(-1)
+            blocks[r, at:at + vals.nbytes] = vals.view(np.uint8)
+    got = icpd._unpack_results(blocks, plan, dim)
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k

@@ -1,0 +1,138 @@
+"""GPU parity at the sizes bench.py times (BASELINE.json configs[1], [2], [3], [4]) -- through the C ABI, against the
+oracle on the host cores.  The oracle legs run on a process pool (the box has >= 16 cores) so that the file stays
+within a couple of minutes:
+
+* C4: the exact 2000-scan / 4096 x 4096 batch of the bench, bit for bit against the C oracle;
+* C2: the exact 1999-pair batch; every 8th pair plus EVERY pair that hits the iteration limit against the oracle;
+* C5: the exact 8192-pair loop-closure batch; 256 pairs spread over it plus every iteration-limit pair among the first
+  2048, and the sharded plan (plan_pair_shards, 8 ranks simulated one after the other on this GPU) reassembling to the
+  same bits as the single call;
+* C3: 64 scans against the 52k-point submap (hash-grid nearest neighbour, gate 1.5 m) against the oracle.
+
+Tolerances: north_star's 1e-4 m / 1e-5 rad on poses; iteration counts and exit status equal; grids bit-exact."""
+import multiprocessing as mp
+import os
+
+import numpy as np
+import pytest
+
+from conftest import pose_delta
+from icp_b200 import api, synth
+from icp_b200 import dist as icpd
+
+pytestmark = pytest.mark.gpu
+
+CFG = dict(error_threshold=1e-10, max_iterations=150, voxel_size=0.04, method="point_to_line", normal_k=12)
+GRID_CFG = dict(resolution=0.05, p_hit=0.85, p_miss=0.42, log_odds_min=-8.0, log_odds_max=8.0)
+
+
+def _oracle_one(job):
+    os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    from oracle import icp_oracle
+    src, tgt, kw = job
+    R, t, err, iters, status = icp_oracle.register(src, tgt, **kw)
+    return R, t, float(err), int(iters), int(status)
+
+
+def _oracle_many(jobs):
+    os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    with mp.get_context("spawn").Pool(min(os.cpu_count() or 1, 32)) as pool:
+        return pool.map(_oracle_one, jobs, chunksize=1)
+
+
+def _compare(out, sel, refs, what):
+    worst_t = worst_r = 0.0
+    for i, (R, t, err, iters, status) in zip(sel, refs):
+        assert int(out["iters"][i]) == iters and int(out["status"][i]) == status, \
+            f"{what} pair {i}: iters {int(out['iters'][i])} vs {iters}, status {int(out['status'][i])} vs {status}"
+        dt, dr = pose_delta(out["R"][i], out["t"][i], R, t)
+        worst_t, worst_r = max(worst_t, dt), max(worst_r, dr)
+        assert dt < 1e-4 and dr < 1e-5, f"{what} pair {i}: dt={dt:.3e} dr={dr:.3e}"
+        if np.isfinite(err):
+            assert abs(float(out["error"][i]) - err) < 1e-9, f"{what} pair {i}"
+    return worst_t, worst_r
+
+
+@pytest.fixture(scope="module")
+def room2000():
+    scans, poses = synth.make_sequence(2000, world="room", seed=0)
+    flat, off = synth.pack_ragged(scans)
+    return scans, poses, flat, off
+
+
+def test_c4_full_batch_bit_exact():
+    from oracle import occupancy_oracle
+    from utilities import OccupancyGrid2D
+    scans, poses = synth.make_sequence(2000, world="campus", seed=0)
+    hits = [synth.to_world_frame(s, p) for s, p in zip(scans, poses)]
+    flat, off = synth.pack_ragged(hits)
+    grid = OccupancyGrid2D(-102.4, 102.4, -102.4, 102.4, **GRID_CFG)
+    assert (grid.ny, grid.nx) == (4096, 4096)
+    grid._dev.update(poses[:, :2].copy(), flat, off)
+    ref = occupancy_oracle.GridOracleC(-102.4, 102.4, -102.4, 102.4, **GRID_CFG)
+    ref.update_many(poses[:, :2].copy(), flat, off, fast=True)
+    got = grid.log_odds
+    assert np.count_nonzero(ref.log_odds) > 1_000_000
+    assert got.tobytes() == ref.log_odds.tobytes(), f"{np.count_nonzero(got != ref.log_odds)} cells differ"
+    # the dirty-tile read-out returns the same map
+    if hasattr(grid._dev, "read_dirty"):
+        mirror = np.zeros_like(got)
+        grid._dev.read_dirty(mirror)
+        assert mirror.tobytes() == ref.log_odds.tobytes()
+
+
+def test_c2_full_batch_against_the_oracle(room2000):
+    scans, poses, flat, off = room2000
+    si = np.arange(1999, dtype=np.int32)
+    out = api.icp_pairs(flat, off, si, si + 1, **CFG)
+    slow = np.flatnonzero(out["status"] == 1)
+    assert len(slow) >= 50                                  # the reference's limit cycles are in the batch
+    sel = np.unique(np.concatenate([np.arange(0, 1999, 8), slow]))
+    refs = _oracle_many([(scans[i], scans[i + 1], CFG) for i in sel])
+    _compare(out, sel, refs, "C2")
+
+
+def test_c5_full_batch_against_the_oracle_and_sharded_plan(room2000):
+    scans, poses, flat, off = room2000
+    pairs = synth.loop_closure_pairs(poses, 8192, seed=0, max_dist=3.0).astype(np.int32)
+    si, ti = pairs[:, 0].copy(), pairs[:, 1].copy()
+    out = api.icp_pairs(flat, off, si, ti, **CFG)
+    slow = np.flatnonzero(out["status"][:2048] == 1)
+    sel = np.unique(np.concatenate([np.linspace(0, 8191, 256).astype(int), slow]))
+    assert len(sel) >= 200
+    refs = _oracle_many([(scans[si[i]], scans[ti[i]], CFG) for i in sel])
+    _compare(out, sel, refs, "C5")
+    # eight ranks' shares, one after the other: each call names the whole history but only its own pairs
+    plan = icpd.plan_pair_shards(si, ti, 8)
+    merged = {k: np.empty_like(v) for k, v in out.items()}
+    for mine in plan:
+        part = api.icp_pairs(flat, off, si[mine], ti[mine], **CFG)
+        for k in merged:
+            merged[k][mine] = part[k]
+    for k in ("R", "t", "error", "prev_error", "iters", "status"):
+        assert merged[k].tobytes() == out[k].tobytes(), k
+
+
+def test_c3_64_sources_against_the_oracle():
+    target = synth.submap_cloud(n_raw=52000, seed=3)
+    rng = np.random.default_rng(103)
+    clouds, R0, t0s = [target], [], []
+    while len(clouds) < 1 + 64:
+        c = target[rng.integers(len(target))]
+        near = target[np.hypot(*(target - c).T) < 12.0]
+        if len(near) < 1500:
+            continue
+        pts = near[rng.choice(len(near), 1080, replace=False)] + rng.normal(0, 0.01, size=(1080, 2))
+        th = rng.uniform(-0.3, 0.3)
+        rot = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        shift = rng.uniform(-5, 5, size=2)
+        clouds.append((pts - shift) @ rot)
+        a = th + 0.01
+        R0.append([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+        t0s.append(shift + [0.05, -0.04])
+    flat, off = synth.pack_ragged(clouds)
+    kw = dict(error_threshold=1e-10, max_iterations=150, voxel_size=0.04, method="point_to_point", max_corr_dist=1.5)
+    R0, t0s = np.asarray(R0), np.asarray(t0s)
+    out = api.icp_pairs(flat, off, np.arange(1, 65, dtype=np.int32), np.zeros(64, dtype=np.int32), R_init=R0, t_init=t0s, **kw)
+    refs = _oracle_many([(clouds[1 + p], target, dict(kw, R_init=R0[p], t_init=t0s[p])) for p in range(64)])
+    _compare(out, np.arange(64), refs, "C3")
