@@ -167,6 +167,13 @@ int icpb200_icp_last_stats(int64_t *stats8);
  * call; out8[5] is the number of such iterations. */
 int icpb200_icp_phase_profile(int64_t *out8);
 
+/* Profiling aid: the first call switches per-pair counters on; after the next
+ * registration call, a call with a buffer of 4*cap_pairs int64 receives, per
+ * pair of that call, {SM cycles spent on the pair (both launches), source
+ * points swept, points re-decided by the fp64 fallback, iterations} and
+ * returns the number of pairs written. */
+int icpb200_icp_pair_profile(int64_t *out, int64_t cap_pairs);
+
 /* Voxel-grid mean downsample (replaces utilities/icp.py:117-129).  `out`
  * needs n*dim doubles; *n_out receives the number of occupied voxels; rows
  * are in lexicographic voxel-index order like np.unique(axis=0). */

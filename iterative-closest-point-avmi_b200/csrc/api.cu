@@ -221,8 +221,8 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
     a.cap_s = round_up((int)std::max<long long>(s.role_max, 32), 32);
     a.cap_t = grid ? 32 : round_up((int)std::max<long long>(t.role_max, 32), 32);
     a.sort_pad = next_pow2((int)std::max<long long>(std::min<long long>(std::max(s.set_max, t.set_max), ICPB200_BRUTE_MAX_POINTS), 256));
-    const size_t smem = icp_pair_smem_bytes(k.dim, a.cap_s, a.cap_t);
-    if (smem > (size_t)c.max_smem_optin || (!grid && p2l && icp_normals_smem_bytes(a.cap_t) > (size_t)c.max_smem_optin) ||
+    const size_t smem = icp_pair_smem_bytes(k.dim, a.cap_s, a.cap_t);               // bulk variant; the launcher adds what the roomy one needs
+    if (icp_pair_smem_bytes(k.dim, a.cap_s, a.cap_t, 512) > (size_t)c.max_smem_optin || (!grid && p2l && icp_normals_smem_bytes(a.cap_t) > (size_t)c.max_smem_optin) ||
         icp_voxel_smem_bytes(a.sort_pad) > (size_t)c.max_smem_optin) {
         set_error("icp: %zu bytes of shared memory needed, device allows %d", smem, c.max_smem_optin);
         return ICPB200_ERR_LIMIT;
@@ -252,6 +252,13 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
     }
     a.stats = c.stats.as<unsigned long long>();
     a.trace_match = tr.match; a.trace_iters = tr.iters; a.trace_stride = tr.stride;
+    a.pair_prof = nullptr;
+    if (c.pair_prof_on) {                                          // icpb200_icp_pair_profile() asked for per-pair counters
+        if (c.pair_prof.reserve(sizeof(unsigned long long) * 4 * (size_t)n_pairs)) return ICPB200_ERR_CUDA;
+        ICPB_CUDA(cudaMemsetAsync(c.pair_prof.p, 0, sizeof(unsigned long long) * 4 * (size_t)n_pairs, st));
+        a.pair_prof = c.pair_prof.as<unsigned long long>();
+        c.pair_prof_n = n_pairs;
+    }
     ICPB_CUDA(cudaMemsetAsync(a.queue, 0, 16 * sizeof(unsigned), st));
     ICPB_CUDA(cudaMemsetAsync(a.stats, 0, 16 * sizeof(unsigned long long), st));
     ICPB_CUDA(cudaMemsetAsync(a.s.used, 0, 2 * (size_t)s.n_clouds, st));
@@ -442,7 +449,7 @@ void icpb200_shutdown(void) {
                       &c.aux_ds[0], &c.aux_ds[1], &c.aux_n[0], &c.aux_n[1], &c.aux_box[0], &c.aux_box[1],
                       &c.aux_nrm[0], &c.aux_nrm[1], &c.aux_flags[0], &c.aux_flags[1], &c.vox_in, &c.vox_out,
                       &c.big_keys, &c.big_idx, &c.grid_start, &c.grid_items, &c.grid_cell, &c.grid_desc, &c.grid_off,
-                      &c.grid_buckets, &c.rot_src, &c.rot_tgt, &c.rot_ang, &c.rot_off, &c.rot_out, &c.cont_cur, &c.cont_match, &c.cont_d2lb, &c.cont_moved, &c.cont_scalar, &c.cont_list};
+                      &c.grid_buckets, &c.rot_src, &c.rot_tgt, &c.rot_ang, &c.rot_off, &c.rot_out, &c.cont_cur, &c.cont_match, &c.cont_d2lb, &c.cont_moved, &c.cont_scalar, &c.cont_list, &c.pair_prof};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 4; ++i) if (c.ev[i]) { cudaEventDestroy(c.ev[i]); c.ev[i] = nullptr; }
     for (int i = 0; i < kUploadChunks; ++i) {
@@ -773,6 +780,20 @@ int icpb200_icp_phase_profile(int64_t* out8) {
     ICPB_CUDA(cudaMemcpyAsync(out8, c.stats.as<int64_t>() + 8, 8 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     ICPB_CUDA(cudaStreamSynchronize(st));
     return ICPB200_OK;
+}
+
+int icpb200_icp_pair_profile(int64_t* out, int64_t cap_pairs) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    int rc = init_locked(-1);
+    if (rc) return rc;
+    Context& c = g_ctx;
+    c.pair_prof_on = true;                         // takes effect from the next registration call
+    if (!out || cap_pairs <= 0 || !c.pair_prof.p || c.pair_prof_n <= 0) return 0;
+    cudaStream_t st = c.last_icp_stream ? c.last_icp_stream : c.stream;
+    const int64_t n = std::min<int64_t>(cap_pairs, c.pair_prof_n);
+    ICPB_CUDA(cudaMemcpyAsync(out, c.pair_prof.p, sizeof(int64_t) * 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    ICPB_CUDA(cudaStreamSynchronize(st));
+    return (int)n;
 }
 
 int icpb200_voxel_downsample(const double* pts, int64_t n, int dim, double voxel_size, double* out, int64_t* n_out) {

@@ -16,10 +16,12 @@ constexpr int kRedMax = 12;            // widest block reduction (values)
 
 // Shared-memory header: lives at the start of dynamic shared memory in every
 // kernel that uses these helpers.
-struct CtaShared {
-    double red[2][kNW][kRedMax];       // double-buffered warp partials
+template <int NW_>
+struct CtaSharedT {
+    static constexpr int kWarps = NW_;
+    double red[2][NW_][kRedMax];       // double-buffered warp partials
     double red_tot[2][kRedMax];        // ... and block totals
-    int scan_tot[kNW + 1];
+    int scan_tot[NW_ + 1];
     int bcast_i[4];
     unsigned int pair;
     // registration state (ICP kernel only)
@@ -31,9 +33,12 @@ struct CtaShared {
     int amb_n;
     unsigned int slab_evals;           // fp32 evaluations of the slab sweeps of this iteration (statistics)
     // split-sweep partials (K3): [warp][lane]
-    float part_b1[kNW][32], part_b2[kNW][32], part_b3[kNW][32];
-    int part_bt[kNW][32], part_bt2[kNW][32];
+    float part_b1[NW_][32], part_b2[NW_][32], part_b3[NW_][32];
+    int part_bt[NW_][32], part_bt2[NW_][32];
+    int bins[65];                      // x-bins of the points to decide (K3: todo list ordered for the slab sweep)
+    int front_n;                       // K3 far-field front set size
 };
+using CtaShared = CtaSharedT<kNW>;     // the 256-thread kernels (K1, K2, K8, bulk K3)
 
 struct SumOp {
     __device__ static double f(double a, double b) { return a + b; }
@@ -53,8 +58,9 @@ struct MinOp {
 //   block   threads 0 .. NV-1 each add one value over the warps (in warp order), everybody reads
 //           the NV totals back: NV + kNW shared loads per thread instead of NV * kNW.
 // `phase` alternates the scratch buffer so a reduction may start while another is still read.
-template <int NV, class Op>
-__device__ __forceinline__ void block_reduce(double (&v)[NV], CtaShared& sh, int& phase) {
+template <int NV, class Op, class SH>
+__device__ __forceinline__ void block_reduce(double (&v)[NV], SH& sh, int& phase) {
+    constexpr int NWB = SH::kWarps;
     static_assert(NV <= kRedMax, "reduction too wide");
     constexpr int NVP = NV <= 1 ? 1 : NV <= 2 ? 2 : NV <= 4 ? 4 : NV <= 8 ? 8 : 16;
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -89,7 +95,7 @@ __device__ __forceinline__ void block_reduce(double (&v)[NV], CtaShared& sh, int
     if (threadIdx.x < NV) {
         double s = buf[0][threadIdx.x];
 #pragma unroll
-        for (int ww = 1; ww < kNW; ++ww) s = Op::f(s, buf[ww][threadIdx.x]);
+        for (int ww = 1; ww < NWB; ++ww) s = Op::f(s, buf[ww][threadIdx.x]);
         sh.red_tot[phase & 1][threadIdx.x] = s;
     }
     __syncthreads();

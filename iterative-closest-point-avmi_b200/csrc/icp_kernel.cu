@@ -49,15 +49,15 @@ __host__ __device__ inline int pad_index(int j) { return j + (j >> 5); }   // 33
 __host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~size_t(15); }
 
 // ---- shared-memory sizes (must match the carve-up in the kernels) -----------
-size_t icp_pair_smem_bytes(int dim, int cap_s, int cap_t) {
-    size_t b = align16(sizeof(CtaShared));
+size_t icp_pair_smem_bytes(int dim, int cap_s, int cap_t, int nt) {
+    size_t b = align16(nt == 512 ? sizeof(CtaSharedT<16>) : sizeof(CtaShared));
     b += sizeof(double) * dim * (size_t)(cap_t + cap_t / 32);          // tgt64, tile-padded SoA
     b = align16(b);
     b += sizeof(float) * (dim == 2 ? 2 : 4) * (size_t)cap_t;           // tgt32
     b += sizeof(double) * dim * (size_t)cap_s;                         // cur64 SoA
     b += sizeof(int) * (size_t)cap_s;                                  // match
     b += sizeof(float) * (1 + dim) * (size_t)cap_s;                    // d2lb, decision position (fp32, recentred)
-    b += sizeof(unsigned short) * 2 * (size_t)cap_s;                   // todo, ambiguous
+    b += sizeof(unsigned short) * 3 * (size_t)cap_s;                   // todo, todo ordered by x, ambiguous
     return align16(b);
 }
 size_t icp_voxel_smem_bytes(int sort_pad) { return align16(sizeof(CtaShared)) + (size_t)sort_pad * 12; }
@@ -805,6 +805,12 @@ __device__ __forceinline__ void sweep3d(const float4* __restrict__ t32, int tile
     }
 }
 
+// Relative slack of an fp32 swept distance against the exact one.  dx = sx - tx, dx * dx and the fma each round once:
+// d^2 is off by at most 3 * 2^-24 = 1.8e-7 relative, the distance by 0.9e-7; the coordinates' own rounding is covered
+// separately by the absolute term 1.8e-7 * (|s| + |t|).  3e-7 leaves a factor three (it was 1e-6: far-away points,
+// whose candidates differ by less than that, went to the fp64 fallback for nothing).
+constexpr double kRel32 = 3.0e-7;
+
 template <int DIM>
 struct Loop {
     // views into shared memory, valid during the iteration loop
@@ -816,8 +822,10 @@ struct Loop {
     float* p0;               // position at that decision (fp32, recentred; SoA with stride cap): the bound holds
                              // as long as the NET displacement since then leaves room, however long the path
     int cap;
-    unsigned short* todo;    // points that need a sweep this iteration
-    unsigned short* amb;     // points that need the full fp64 scan
+    unsigned short* todo;    // points that need a sweep this iteration (in the order the classify pass found them)
+    unsigned short* todo2;   // the same points ordered by their current x (bins of the target's x range), for the slab sweep
+    const unsigned short* list;   // what the sweeps read: todo or todo2
+    unsigned short* amb;     // points whose fp32 ranking could not be separated: decided in fp64
     int n_s, n_t, n_tiles;
     double c0, c1, c2;       // recentring offset
     float ta;                // sum over axes of max |target - centre|
@@ -870,8 +878,8 @@ __device__ __forceinline__ int m_pack(int j, int alt) { return j | ((alt + 1) <<
 
 // Decide the correspondence of source point i from its sweep result: re-evaluate
 // the winning tile in fp64, bound everything else by the runner-up tile minimum.
-template <int DIM>
-__device__ __forceinline__ void decide(const Loop<DIM>& L, CtaShared& sh, int i, float sxv, float syv, float szv,
+template <int DIM, class SH>
+__device__ __forceinline__ void decide(const Loop<DIM>& L, SH& sh, int i, float sxv, float syv, float szv,
                                        float b2v, int btv) {
     const double px = L.cx[i], py = L.cy[i], pz = DIM == 3 ? L.cz[i] : 0.0;
     const int j0 = btv * 32;
@@ -891,9 +899,10 @@ __device__ __forceinline__ void decide(const Loop<DIM>& L, CtaShared& sh, int i,
     // roundings folded into the relative factor.
     const float mag = fabsf(sxv) + fabsf(syv) + (DIM == 3 ? fabsf(szv) : 0.f) + L.ta;
     const double slack = 1.8e-7 * (double)mag;
-    const double other = sqrt((double)b2v) * (1.0 - 1.0e-6) - slack;
+    const double other = sqrt((double)b2v) * (1.0 - kRel32) - slack;
     const double d1 = sqrt(best);
     if (!(other > d1)) {
+        L.match[i] = m_pack(bj, -1);                   // the best known candidate: the fp64 fallback starts from it
         L.amb[atomicAdd(&sh.amb_n, 1)] = (unsigned short)i;
     } else {
         L.match[i] = m_pack(bj, j2);
@@ -902,17 +911,17 @@ __device__ __forceinline__ void decide(const Loop<DIM>& L, CtaShared& sh, int i,
     }
 }
 
-// One sweep round for this warp: chunks first_chunk + s * kNW, s < S, of the todo list.
-template <int DIM, int S>
-__device__ __forceinline__ void nn_round(const Loop<DIM>& L, CtaShared& sh, int first_chunk, int n_todo) {
+// One sweep round for this warp: chunks first_chunk + s * (NT / 32), s < S, of the todo list.
+template <int DIM, int S, int NT, class SH>
+__device__ __forceinline__ void nn_round(const Loop<DIM>& L, SH& sh, int first_chunk, int n_todo) {
     const int lane = threadIdx.x & 31;
     float sx[S], sy[S], sz[S];
     float b1[S], b2[S];
     int bt[S], pt[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-        const int q = (first_chunk + s * kNW) * 32 + lane;
-        pt[s] = q < n_todo ? (int)L.todo[q] : -1;
+        const int q = (first_chunk + s * (NT / 32)) * 32 + lane;
+        pt[s] = q < n_todo ? (int)L.list[q] : -1;
         const int i = max(pt[s], 0);
         sx[s] = pt[s] >= 0 ? (float)(L.cx[i] - L.c0) : 0.f;
         sy[s] = pt[s] >= 0 ? (float)(L.cy[i] - L.c1) : 0.f;
@@ -931,8 +940,8 @@ __device__ __forceinline__ void nn_round(const Loop<DIM>& L, CtaShared& sh, int 
 // pair), so the decision needs a single fp64 evaluation instead of a 32-point
 // tile scan: accept j1 when the fp32 runner-up, shrunk by the rounding slack, is
 // still farther than the exact distance to j1; otherwise the full fp64 scan decides.
-template <int DIM>
-__device__ __forceinline__ void nn_split(const Loop<DIM>& L, CtaShared& sh, int n_todo, int n_chunks, int F) {
+template <int DIM, int NT, class SH>
+__device__ __forceinline__ void nn_split(const Loop<DIM>& L, SH& sh, int n_todo, int n_chunks, int F) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunk = w / F, part = w % F;
     const bool live = chunk < n_chunks;
@@ -940,7 +949,7 @@ __device__ __forceinline__ void nn_split(const Loop<DIM>& L, CtaShared& sh, int 
     int pt = -1;
     if (live) {
         const int q = chunk * 32 + lane;
-        pt = q < n_todo ? (int)L.todo[q] : -1;
+        pt = q < n_todo ? (int)L.list[q] : -1;
         const int i = max(pt, 0);
         sx = pt >= 0 ? (float)(L.cx[i] - L.c0) : 0.f;
         sy = pt >= 0 ? (float)(L.cy[i] - L.c1) : 0.f;
@@ -1006,8 +1015,9 @@ __device__ __forceinline__ void nn_split(const Loop<DIM>& L, CtaShared& sh, int 
         }
         const double d1 = sqrt(e1);
         const float mag = fabsf(sx) + fabsf(sy) + (DIM == 3 ? fabsf(sz) : 0.f) + L.ta;
-        const double other = sqrt((double)(two ? m3 : m2)) * (1.0 - 1.0e-6) - 1.8e-7 * (double)mag;
+        const double other = sqrt((double)(two ? m3 : m2)) * (1.0 - kRel32) - 1.8e-7 * (double)mag;
         if (!(other > d1)) {
+            L.match[pt] = m_pack(j1, -1);
             L.amb[atomicAdd(&sh.amb_n, 1)] = (unsigned short)pt;
         } else {
             L.match[pt] = m_pack(j1, j2);
@@ -1027,31 +1037,48 @@ __device__ __forceinline__ void nn_split(const Loop<DIM>& L, CtaShared& sh, int 
 // min(third best, gaps) minus the fp32 slack; otherwise the full fp64 scan decides.  On C2 a chunk
 // visits ~60 of the 800 targets instead of all of them, and the 32-target fp64 re-evaluation of
 // the tile sweep is gone.
-template <int DIM>
-__device__ __forceinline__ void nn_slab(const Loop<DIM>& L, CtaShared& sh, int n_todo, float vox) {
+template <int DIM, int NT, class SH>
+__device__ __forceinline__ void nn_slab(const Loop<DIM>& L, SH& sh, int n_todo, float vox) {
     const unsigned full = 0xffffffffu;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_chunks = (n_todo + 31) >> 5;
     const float* tf = reinterpret_cast<const float*>(L.t32);
     constexpr int kStride = DIM == 2 ? 2 : 4;                 // floats per target in t32
-    for (int chunk = w; chunk < n_chunks; chunk += kNW) {
+    for (int chunk = w; chunk < n_chunks; chunk += (NT / 32)) {
         const int q = chunk * 32 + lane;
-        const int pt = q < n_todo ? (int)L.todo[q] : -1;
-        const int i = pt >= 0 ? pt : (int)L.todo[chunk * 32];   // idle lanes shadow the chunk's first point
+        const int pt = q < n_todo ? (int)L.list[q] : -1;
+        const int i = pt >= 0 ? pt : (int)L.list[chunk * 32];   // idle lanes shadow the chunk's first point
         const float sx = (float)(L.cx[i] - L.c0), sy = (float)(L.cy[i] - L.c1);
         const float sz = DIM == 3 ? (float)(L.cz[i] - L.c2) : 0.f;
         float b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
         int bj = 0, bj2 = -1;
-        auto offer = [&](int j) {
+        auto dist = [&](int j) {
             const float dx = sx - tf[j * kStride], dy = sy - tf[j * kStride + 1];
             float d = fmaf(dy, dy, dx * dx);
             if (DIM == 3) { const float dz = sz - tf[j * kStride + 2]; d = fmaf(dz, dz, d); }
+            return d;
+        };
+        auto offer_d = [&](float d, int j) {
             const bool lt1 = d < b1, lt2 = d < b2;
             b3 = lt2 ? b2 : fminf(b3, d);
             b2 = lt1 ? b1 : (lt2 ? d : b2);
             bj2 = lt1 ? bj : (lt2 ? j : bj2);
             b1 = lt1 ? d : b1;
             bj = lt1 ? j : bj;
+        };
+        auto offer = [&](int j) { offer_d(dist(j), j); };
+        // eight candidates at a time: their distances are independent (the three-best update is a dependent chain of
+        // compares and selects), and once the lists have warmed up a block rarely holds anything closer than some
+        // lane's third best -- then it costs eight evaluations and a vote instead of eight chained updates
+        auto offer8 = [&](int j0, int step) {
+            float d[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) d[u] = dist(j0 + u * step);
+            const float m = fminf(fminf(fminf(d[0], d[1]), fminf(d[2], d[3])), fminf(fminf(d[4], d[5]), fminf(d[6], d[7])));
+            if (__any_sync(full, m < b3)) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) offer_d(d[u], j0 + u * step);
+            }
         };
         // start where lane 0's point would be inserted (any start is correct, this one is short)
         const float x0 = __shfl_sync(full, sx, 0);
@@ -1067,8 +1094,7 @@ __device__ __forceinline__ void nn_slab(const Loop<DIM>& L, CtaShared& sh, int n
             if (!ddone) {
                 const int stop = max(dn - 7, 0);
                 if (dn >= 7) {
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) offer(dn - u);
+                    offer8(dn, -1);
                 } else {
                     for (int j = dn; j >= stop; --j) offer(j);
                 }
@@ -1082,8 +1108,7 @@ __device__ __forceinline__ void nn_slab(const Loop<DIM>& L, CtaShared& sh, int n
             if (!udone) {
                 const int stop = min(up + 7, L.n_t - 1);
                 if (up + 7 < L.n_t) {
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) offer(up + u);
+                    offer8(up, 1);
                 } else {
                     for (int j = up; j <= stop; ++j) offer(j);
                 }
@@ -1108,9 +1133,10 @@ __device__ __forceinline__ void nn_slab(const Loop<DIM>& L, CtaShared& sh, int n
         }
         const double d1 = sqrt(e1);
         const float mag = fabsf(sx) + fabsf(sy) + (DIM == 3 ? fabsf(sz) : 0.f) + L.ta + vox;
-        const double rest = fmin(sqrt((double)(two ? b3 : b2)) * (1.0 - 1.0e-6), (double)fminf(gdn, gup) * (1.0 - 1.0e-6));
+        const double rest = fmin(sqrt((double)(two ? b3 : b2)) * (1.0 - kRel32), (double)fminf(gdn, gup) * (1.0 - kRel32));
         const double other = rest - 1.8e-7 * (double)mag;
         if (!(other > d1)) {
+            L.match[pt] = m_pack(j1, -1);
             L.amb[atomicAdd(&sh.amb_n, 1)] = (unsigned short)pt;
         } else {
             L.match[pt] = m_pack(j1, j2);
@@ -1120,37 +1146,37 @@ __device__ __forceinline__ void nn_slab(const Loop<DIM>& L, CtaShared& sh, int n
     }
 }
 
-template <int DIM>
-__device__ __forceinline__ void nn_dispatch(const Loop<DIM>& L, CtaShared& sh, int n_todo, float vox) {
+template <int DIM, int NT, class SH>
+__device__ __forceinline__ void nn_dispatch(const Loop<DIM>& L, SH& sh, int n_todo, float vox) {
     const int w = threadIdx.x >> 5;
     const int n_chunks = (n_todo + 31) >> 5;
-    const int F = n_chunks > 0 ? kNW / n_chunks : 1;
-    if (F >= 2) { nn_split<DIM>(L, sh, n_todo, n_chunks, F); return; }
-    if (vox > 0.f) { nn_slab<DIM>(L, sh, n_todo, vox); return; }
-    for (int base = 0; base < n_chunks; base += kSMax * kNW) {
+    const int F = n_chunks > 0 ? (NT / 32) / n_chunks : 1;
+    if (F >= 2) { nn_split<DIM, NT>(L, sh, n_todo, n_chunks, F); return; }
+    if (vox > 0.f) { nn_slab<DIM, NT>(L, sh, n_todo, vox); return; }
+    for (int base = 0; base < n_chunks; base += kSMax * (NT / 32)) {
         const int first = base + w;
-        const int mine = first < n_chunks ? min(kSMax, (n_chunks - first + kNW - 1) / kNW) : 0;   // warp-uniform
+        const int mine = first < n_chunks ? min(kSMax, (n_chunks - first + (NT / 32) - 1) / (NT / 32)) : 0;   // warp-uniform
         switch (mine) {
             case 0: break;
-            case 1: nn_round<DIM, 1>(L, sh, first, n_todo); break;
-            case 2: nn_round<DIM, 2>(L, sh, first, n_todo); break;
-            case 3: nn_round<DIM, 3>(L, sh, first, n_todo); break;
-            case 4: nn_round<DIM, 4>(L, sh, first, n_todo); break;
-            case 5: nn_round<DIM, 5>(L, sh, first, n_todo); break;
-            case 6: nn_round<DIM, 6>(L, sh, first, n_todo); break;
-            case 7: nn_round<DIM, 7>(L, sh, first, n_todo); break;
-            default: nn_round<DIM, 8>(L, sh, first, n_todo); break;
+            case 1: nn_round<DIM, 1, NT>(L, sh, first, n_todo); break;
+            case 2: nn_round<DIM, 2, NT>(L, sh, first, n_todo); break;
+            case 3: nn_round<DIM, 3, NT>(L, sh, first, n_todo); break;
+            case 4: nn_round<DIM, 4, NT>(L, sh, first, n_todo); break;
+            case 5: nn_round<DIM, 5, NT>(L, sh, first, n_todo); break;
+            case 6: nn_round<DIM, 6, NT>(L, sh, first, n_todo); break;
+            case 7: nn_round<DIM, 7, NT>(L, sh, first, n_todo); break;
+            default: nn_round<DIM, 8, NT>(L, sh, first, n_todo); break;
         }
     }
 }
 
 // Points whose runner-up bound was inconclusive: one warp per point scans the
 // whole target in fp64 (lowest index wins exact ties) and keeps the two best.
-template <int DIM>
-__device__ __forceinline__ void resolve_ambiguous(const Loop<DIM>& L, const CtaShared& sh) {
+template <int DIM, int NT, class SH>
+__device__ __forceinline__ void resolve_ambiguous(const Loop<DIM>& L, const SH& sh) {
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     const int n_amb = sh.amb_n;
-    for (int a = w; a < n_amb; a += kNW) {
+    for (int a = w; a < n_amb; a += (NT / 32)) {
         const int i = L.amb[a];
         const double px = L.cx[i], py = L.cy[i], pz = DIM == 3 ? L.cz[i] : 0.0;
         double best = INFINITY, second = INFINITY, third = INFINITY;
@@ -1180,6 +1206,163 @@ __device__ __forceinline__ void resolve_ambiguous(const Loop<DIM>& L, const CtaS
     }
 }
 
+// Many points at once whose fp32 ranking could not be separated (a source that sits metres or kilometres away from the
+// target -- a registration that is diverging, SURVEY H1's cousins in the loop-closure batch -- has whole walls of
+// near-equidistant candidates): one warp per point scanning the whole target in fp64 serialises them.  Instead a LANE
+// takes a point and the warp walks the tiles in lock step: the fp32 tile minimum (one broadcast load per target, the
+// sweep's arithmetic) filters, and only tiles that may hold a target as close as the best one known -- U, the exact
+// distance to the fp32 argmin the failed decision left in match[] -- are evaluated in fp64.  A target in a skipped tile
+// has fp32 d^2 > Tf = ((U + slack)(1 + kRel32))^2, so its exact distance exceeds U: it is neither the match nor the
+// rival, and sqrt(Tf)(1 - kRel32) - slack bounds it from below for the carry-over test.
+template <int DIM, int NT, class SH>
+__device__ __forceinline__ void resolve_ambiguous_lockstep(const Loop<DIM>& L, const SH& sh) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_amb = sh.amb_n, n_chunks = (n_amb + 31) >> 5;
+    const float* tf = reinterpret_cast<const float*>(L.t32);
+    constexpr int kStride = DIM == 2 ? 2 : 4;
+    for (int chunk = w; chunk < n_chunks; chunk += NT / 32) {
+        const int q = chunk * 32 + lane;
+        const bool live = q < n_amb;
+        const int i = L.amb[live ? q : chunk * 32];               // idle lanes shadow the chunk's first point
+        const double px = L.cx[i], py = L.cy[i], pz = DIM == 3 ? L.cz[i] : 0.0;
+        const float sx = (float)(px - L.c0), sy = (float)(py - L.c1), sz = DIM == 3 ? (float)(pz - L.c2) : 0.f;
+        const int j0 = m_idx<false>(L.match[i]);
+        double best = dist2_64<DIM>(L, px, py, pz, j0), second = INFINITY, third = INFINITY;
+        int bj = j0, j2 = 0x7fffffff;
+        const double slack = 1.8e-7 * (double)(fabsf(sx) + fabsf(sy) + (DIM == 3 ? fabsf(sz) : 0.f) + L.ta);
+        const double reach = (sqrt(best) + slack) * (1.0 + kRel32);
+        const float Tf = __double2float_ru(reach * reach);
+        auto offer = [&](double d, int j) {                     // (d, j) lexicographic: lowest index wins exact ties
+            if (d < best || (d == best && j < bj)) { third = second; second = best; j2 = bj; best = d; bj = j; }
+            else if (d < second || (d == second && j < j2)) { third = second; second = d; j2 = j; }
+            else if (d < third) third = d;
+        };
+        for (int tile = 0; tile < L.n_tiles; ++tile) {
+            float tm = INFINITY;
+            const float* p = tf + (size_t)tile * 32 * kStride;
+#pragma unroll 8
+            for (int u = 0; u < 32; ++u) {
+                const float dx = sx - p[u * kStride], dy = sy - p[u * kStride + 1];
+                float d = fmaf(dy, dy, dx * dx);
+                if (DIM == 3) { const float dz = sz - p[u * kStride + 2]; d = fmaf(dz, dz, d); }
+                tm = fminf(tm, d);
+            }
+            if (tm <= Tf) {
+                const int je = min(tile * 32 + 32, L.n_t);
+                for (int j = tile * 32; j < je; ++j)
+                    if (j != j0) offer(dist2_64<DIM>(L, px, py, pz, j), j);
+            }
+        }
+        if (live) {
+            const double skipped = sqrt((double)Tf) * (1.0 - kRel32) - slack;          // every target in a tile that was skipped
+            L.match[i] = m_pack(bj, j2 == 0x7fffffff ? -1 : j2);
+            L.d2lb[i] = f32_down(fmin(sqrt(third) * (1.0 - 1e-12), skipped));
+            stamp_p0<DIM>(L, i);
+        }
+    }
+}
+
+// Far field.  When the source has left the target's neighbourhood altogether -- a diverged registration keeps iterating to
+// max_iterations in the reference, icp.py:177-223, with every point hundreds or millions of metres from every target --
+// fp32 cannot rank the candidates at all, and nothing is pruned.  But then almost no target can be anybody's nearest
+// neighbour: with q0 = source point 0, D = q0 - c (c the target's box centre), u = q - q0, v = t - c,
+//        |q - t|^2 = |D|^2 + 2 D.u + |u - v|^2 - 2 D.v ,
+// so for two targets a, b and ANY source point q:  d^2(q,a) - d^2(q,b) = (w_a - w_b) + (|u - v_a|^2 - |u - v_b|^2) with
+// w = -2 D.v and the bracket inside [-(S + T)^2, (S + T)^2] (S = max |u|, T >= max |v|).  A target whose w exceeds the
+// minimum by more than (S + T)^2 is therefore never a nearest neighbour: only the "front" of the target facing the
+// source survives -- a handful of points -- and every source point is decided among them by exact fp64 distances
+// (lowest index on exact ties).  Returns false (nothing written) when the source is not that far or the front is large.
+constexpr int kFrontMax = 128;
+
+template <int DIM, int NT, class SH>
+__device__ __forceinline__ bool far_field_matches(const Loop<DIM>& L, SH& sh, int& phase) {
+    const int tid = threadIdx.x;
+    const double q0x = L.cx[0], q0y = L.cy[0], q0z = DIM == 3 ? L.cz[0] : 0.0;
+    const double Dx = q0x - L.c0, Dy = q0y - L.c1, Dz = DIM == 3 ? q0z - L.c2 : 0.0;
+    const double Dn2 = Dx * Dx + Dy * Dy + Dz * Dz;
+    const double T = (double)L.ta;                              // sum over axes of max |v|: >= max |v|
+    if (!(Dn2 > 4096.0 * T * T) || !(Dn2 < 1e300)) return false;                  // uniform: every thread reads the same words
+    double m[1] = {0.0};
+    for (int i = tid; i < L.n_s; i += NT) {
+        const double ux = L.cx[i] - q0x, uy = L.cy[i] - q0y, uz = DIM == 3 ? L.cz[i] - q0z : 0.0;
+        m[0] = fmin(m[0], -(ux * ux + uy * uy + uz * uz));
+    }
+    block_reduce<1, MinOp>(m, sh, phase);
+    const double S = sqrt(-m[0]);
+    const double Dn = sqrt(Dn2);
+    if (!(Dn > 64.0 * (S + T))) return false;
+    // (S + T)^2, plus what the fp64 roundings of w and of the distances themselves (|d^2| <= (Dn + S + T)^2) can move
+    const double E2 = (S + T) * (S + T) * (1.0 + 1e-9) + 2e-15 * (Dn + S + T) * (Dn + S + T);
+    auto w_of = [&](int j) {
+        double x, y, z;
+        tgt_at<DIM, false>(L, j, x, y, z);
+        return -2.0 * (Dx * (x - L.c0) + Dy * (y - L.c1) + (DIM == 3 ? Dz * (z - L.c2) : 0.0));
+    };
+    double wm[1] = {INFINITY};
+    for (int j = tid; j < L.n_t; j += NT) wm[0] = fmin(wm[0], w_of(j));
+    if (tid == 0) sh.front_n = 0;
+    block_reduce<1, MinOp>(wm, sh, phase);                      // its barriers also publish front_n = 0
+    for (int j = tid; j < L.n_t; j += NT)
+        if (w_of(j) <= wm[0] + E2) {
+            const int k = atomicAdd(&sh.front_n, 1);
+            if (k < kFrontMax) L.amb[k] = (unsigned short)j;   // the ambiguity list is idle between iterations
+        }
+    __syncthreads();
+    const int nf = sh.front_n;
+    if (nf > kFrontMax || nf > L.cap) return false;
+    for (int i = tid; i < L.n_s; i += NT) {
+        const double px = L.cx[i], py = L.cy[i], pz = DIM == 3 ? L.cz[i] : 0.0;
+        double best = INFINITY;
+        int bj = 0x7fffffff;
+        for (int k = 0; k < nf; ++k) {
+            const int j = L.amb[k];
+            const double d = dist2_64<DIM>(L, px, py, pz, j);
+            if (d < best || (d == best && j < bj)) { best = d; bj = j; }
+        }
+        L.match[i] = m_pack(bj, -1);
+        L.d2lb[i] = -1.f;                                       // decided afresh in every iteration spent out here
+    }
+    __syncthreads();
+    return true;
+}
+
+// The points to decide, ordered by their CURRENT x for the slab sweep.  The classify pass lists them by source index,
+// i.e. by x in the source's own frame; once the registration has rotated the source -- loop-closure candidates start
+// up to half a radian apart -- 32 consecutive ones spread over metres of x and a warp's walk covers most of the target.
+// A counting sort into 64 bins of the target's x range (two passes over the list, one 64-entry scan) restores the
+// locality; the order inside a bin is whatever the atomics gave, which is irrelevant to an exact search.
+template <int DIM, int NT, class SH>
+__device__ __forceinline__ void order_todo_by_x(Loop<DIM>& L, SH& sh, int n_todo, double xlo, double xhi) {
+    const int tid = threadIdx.x;
+    if (tid < 65) sh.bins[tid] = 0;
+    __syncthreads();
+    const double scale = xhi > xlo ? 64.0 / (xhi - xlo) : 0.0;
+    auto bin_of = [&](int i) {
+        const double b = (L.cx[i] - xlo) * scale;
+        return b > 0.0 ? (b < 63.0 ? (int)b : 63) : 0;          // NaN -> 0
+    };
+    for (int q = tid; q < n_todo; q += NT) atomicAdd(&sh.bins[bin_of(L.todo[q])], 1);
+    __syncthreads();
+    if (tid < 32) {                                            // exclusive scan of 64 counts by one warp
+        const int a0 = sh.bins[2 * tid], a1 = sh.bins[2 * tid + 1];
+        int inc = a0 + a1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (tid >= o) inc += t;
+        }
+        sh.bins[2 * tid] = inc - a0 - a1;
+        sh.bins[2 * tid + 1] = inc - a1;
+    }
+    __syncthreads();
+    for (int q = tid; q < n_todo; q += NT) {
+        const int i = L.todo[q];
+        L.todo2[atomicAdd(&sh.bins[bin_of(i)], 1)] = (unsigned short)i;
+    }
+    __syncthreads();
+    L.list = L.todo2;
+}
+
 // ---- grid-mode nearest neighbour (big targets): exact fp64 ring search ------------------
 // One thread per source point that needs a decision.  Cells are visited ring by
 // ring around the query's cell; after ring r every unvisited target lies outside
@@ -1189,10 +1372,10 @@ __device__ __forceinline__ void resolve_ambiguous(const Loop<DIM>& L, const CtaS
 // more than kGridMaxRing rings fall back to a scan of the whole target.
 constexpr int kGridMaxRing = 24;
 
-template <int DIM>
+template <int DIM, int NT>
 __device__ __forceinline__ void grid_nn(const Loop<DIM>& L, int n_todo) {
     const BigGrid& G = L.grid;
-    for (int q = threadIdx.x; q < n_todo; q += kNT) {
+    for (int q = threadIdx.x; q < n_todo; q += NT) {
         const int i = L.todo[q];
         const double px = L.cx[i], py = L.cy[i];
         // the query may lie outside the target's bounding box: clamp its cell, keep exact bounds
@@ -1248,15 +1431,16 @@ __device__ __forceinline__ void grid_nn(const Loop<DIM>& L, int n_todo) {
 // ---- K3: the kernel ----------------------------------------------------------------
 // MINB = CTAs per SM the register allocation must allow: 2 for the 2-D bulk launch (3 for 3-D and grid mode), 1 for the
 // hand-over launch (one CTA per SM anyway); at 1 and 2 everything stays in registers instead of spilling.
-template <int DIM, bool GRID, int MINB>
-__global__ void __launch_bounds__(kNT, MINB) icp_pairs_kernel(const IcpArgs a) {
+template <int DIM, bool GRID, int MINB, int NT>
+__global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    CtaShared& sh = *reinterpret_cast<CtaShared*>(smem);
+    using SH = CtaSharedT<NT / 32>;
+    SH& sh = *reinterpret_cast<SH*>(smem);
     const int tid = threadIdx.x;
     const int tstride = a.cap_t + a.cap_t / 32;
     Loop<DIM> L;
     {
-        unsigned char* q = smem + align16(sizeof(CtaShared));
+        unsigned char* q = smem + align16(sizeof(SH));
         double* tgt64 = reinterpret_cast<double*>(q);
         L.tx = tgt64; L.ty = tgt64 + tstride; L.tz = tgt64 + 2 * (size_t)tstride;
         q += sizeof(double) * DIM * (size_t)tstride;
@@ -1270,13 +1454,15 @@ __global__ void __launch_bounds__(kNT, MINB) icp_pairs_kernel(const IcpArgs a) {
         L.p0 = reinterpret_cast<float*>(q);            q += sizeof(float) * DIM * (size_t)a.cap_s;
         L.cap = a.cap_s;
         L.todo = reinterpret_cast<unsigned short*>(q); q += sizeof(unsigned short) * (size_t)a.cap_s;
+        L.todo2 = reinterpret_cast<unsigned short*>(q); q += sizeof(unsigned short) * (size_t)a.cap_s;
         L.amb = reinterpret_cast<unsigned short*>(q);
+        L.list = L.todo;
     }
     double* tx = const_cast<double*>(L.tx);
     double* ty = const_cast<double*>(L.ty);
     double* tz = const_cast<double*>(L.tz);
     int phase = 0;
-    unsigned long long st_evals = 0, st_amb = 0, st_iters = 0, st_swept = 0, st_kept = 0;   // thread 0 only
+    unsigned long long st_evals = 0, st_amb = 0, st_iters = 0, st_swept = 0, st_kept = 0, st_far = 0;   // thread 0 only
     // thread 0's cycles per phase over iterations >= 8 (the nearly-converged regime): profiling aid
     long long ph[6] = {0, 0, 0, 0, 0, 0}, ph_t = 0;
     unsigned long long ph_iters = 0;
@@ -1296,6 +1482,8 @@ __global__ void __launch_bounds__(kNT, MINB) icp_pairs_kernel(const IcpArgs a) {
         if (sh.pair == 0xffffffffu) break;
         const int p = (int)sh.pair;
         const int slot_in = sh.bcast_i[2];
+        const long long pair_t0 = (tid == 0 && a.pair_prof) ? clock64() : 0;
+        const unsigned long long pp_swept0 = st_swept, pp_amb0 = st_amb, pp_it0 = st_iters;
 
         const int cs = a.src_idx ? a.src_idx[p] : p;
         const int ct = a.tgt_idx ? a.tgt_idx[p] : p;
@@ -1315,6 +1503,7 @@ __global__ void __launch_bounds__(kNT, MINB) icp_pairs_kernel(const IcpArgs a) {
         const double* tgt_ds = a.t.ds + a.t.off[ct] * DIM;
         const double* normals = a.t.nrm ? a.t.nrm + a.t.off[ct] * 2 : nullptr;
         const double* box = a.t.box + (size_t)ct * 6;
+        const double tgt_xlo = box[0], tgt_xhi = box[3];
         L.n_s = n_s; L.n_t = n_t; L.n_tiles = (n_t + 31) / 32;
         L.c0 = 0.5 * (box[0] + box[3]); L.c1 = 0.5 * (box[1] + box[4]); L.c2 = 0.5 * (box[2] + box[5]);
         L.tg = tgt_ds;
@@ -1340,7 +1529,7 @@ __global__ void __launch_bounds__(kNT, MINB) icp_pairs_kernel(const IcpArgs a) {
             double ext[DIM];
 #pragma unroll
             for (int k = 0; k < DIM; ++k) ext[k] = 0.0;
-            for (int j = tid; j < L.n_tiles * 32; j += kNT) {
+            for (int j = tid; j < L.n_tiles * 32; j += NT) {
                 if (j < n_t) {
                     const int jp = pad_index(j);
                     const double x = tgt_ds[(size_t)j * DIM], y = tgt_ds[(size_t)j * DIM + 1];
@@ -1373,7 +1562,7 @@ __global__ void __launch_bounds__(kNT, MINB) icp_pairs_kernel(const IcpArgs a) {
             double r[9], t[3];
             for (int k = 0; k < DIM * DIM; ++k) r[k] = sh.r_tot[k];
             for (int k = 0; k < DIM; ++k) t[k] = sh.t_tot[k];
-            for (int i = tid; i < n_s; i += kNT) {
+            for (int i = tid; i < n_s; i += NT) {
                 const double x = src_ds[(size_t)i * DIM], y = src_ds[(size_t)i * DIM + 1];
                 if (DIM == 2) {
                     L.cx[i] = x * r[0] + y * r[1] + t[0];
@@ -1393,7 +1582,7 @@ __global__ void __launch_bounds__(kNT, MINB) icp_pairs_kernel(const IcpArgs a) {
         if (a.resume) {                            // continue where phase 1 stopped
             const size_t so = (size_t)slot_in * a.cap_s;
             const double* cc = a.cont_cur + so * DIM;
-            for (int i = tid; i < n_s; i += kNT) {
+            for (int i = tid; i < n_s; i += NT) {
                 L.cx[i] = cc[i]; L.cy[i] = cc[(size_t)a.cap_s + i];
                 if (DIM == 3) L.cz[i] = cc[2 * (size_t)a.cap_s + i];
                 L.match[i] = a.cont_match[so + i];
@@ -1427,7 +1616,7 @@ __global__ void __launch_bounds__(kNT, MINB) icp_pairs_kernel(const IcpArgs a) {
                 const int slot = sh.bcast_i[3];
                 const size_t so = (size_t)slot * a.cap_s;
                 double* cc = a.cont_cur + so * DIM;
-                for (int i = tid; i < n_s; i += kNT) {
+                for (int i = tid; i < n_s; i += NT) {
                     cc[i] = L.cx[i]; cc[(size_t)a.cap_s + i] = L.cy[i];
                     if (DIM == 3) cc[2 * (size_t)a.cap_s + i] = L.cz[i];
                     a.cont_match[so + i] = L.match[i];
@@ -1446,8 +1635,12 @@ __global__ void __launch_bounds__(kNT, MINB) icp_pairs_kernel(const IcpArgs a) {
             }
             const bool prof = tid == 0 && it >= 8;
             if (prof) ph_t = clock64();
-            // ---- correspondences (icp.py:179): carry over where the movement bound allows
-            for (int i = tid; i < n_s; i += kNT) {
+            // ---- correspondences (icp.py:179).  A source that has left the target's neighbourhood altogether is decided
+            // against the target's front set; otherwise carry over where the movement bound allows and sweep the rest
+            bool far = false;
+            if (!GRID) far = far_field_matches<DIM, NT>(L, sh, phase);
+            if (far && tid == 0) ++st_far;
+            for (int i = tid; i < (far ? 0 : n_s); i += NT) {
                 bool keep = false;
                 const float lb = L.d2lb[i];
                 if (lb >= 0.f) {
@@ -1474,19 +1667,24 @@ __global__ void __launch_bounds__(kNT, MINB) icp_pairs_kernel(const IcpArgs a) {
             __syncthreads();
             if (prof) { const long long c = clock64(); ph[0] += c - ph_t; ph_t = c; }
             const int n_todo = sh.bcast_i[0];
+            L.list = L.todo;
             if (n_todo > 0) {
                 if (GRID) {
-                    grid_nn<DIM>(L, n_todo);
+                    grid_nn<DIM, NT>(L, n_todo);
                 } else {
-                    nn_dispatch<DIM>(L, sh, n_todo, slab_vox);
+                    if (slab_vox > 0.f && ((n_todo + 31) >> 5) > (NT / 32) / 2)          // the slab sweep will run
+                        order_todo_by_x<DIM, NT>(L, sh, n_todo, tgt_xlo, tgt_xhi);
+                    nn_dispatch<DIM, NT>(L, sh, n_todo, slab_vox);
                     __syncthreads();
-                    if (sh.amb_n > 0) resolve_ambiguous<DIM>(L, sh);
+                    // a few undecided points: one warp each scans the target; many: a lane each, tiles filtered in fp32
+                    if (sh.amb_n > NT / 32) resolve_ambiguous_lockstep<DIM, NT>(L, sh);
+                    else if (sh.amb_n > 0) resolve_ambiguous<DIM, NT>(L, sh);
                 }
             }
             if (tid == 0) {
                 const int n_chunks = (n_todo + 31) >> 5;
                 if (!GRID) {
-                    const bool slab = slab_vox > 0.f && n_chunks > kNW / 2;      // nn_dispatch's choice
+                    const bool slab = slab_vox > 0.f && n_chunks > (NT / 32) / 2;      // nn_dispatch's choice
                     st_evals += slab ? (unsigned long long)sh.slab_evals
                                      : (unsigned long long)n_chunks * 32ull * (unsigned long long)L.n_tiles * 32ull;
                     sh.slab_evals = 0u;
@@ -1497,7 +1695,7 @@ __global__ void __launch_bounds__(kNT, MINB) icp_pairs_kernel(const IcpArgs a) {
             if (prof) { const long long c = clock64(); ph[1] += c - ph_t; ph_t = c; }
             if (tid == 0) { st_amb += sh.amb_n; sh.amb_n = 0; sh.bcast_i[0] = 0; }
             if (a.trace_match && p == 0 && it < a.trace_iters)
-                for (int i = tid; i < n_s; i += kNT) a.trace_match[(size_t)it * a.trace_stride + i] = m_idx<GRID>(L.match[i]);
+                for (int i = tid; i < n_s; i += NT) a.trace_match[(size_t)it * a.trace_stride + i] = m_idx<GRID>(L.match[i]);
 
             double rr[9], tt[3];
             if (p2l) {
@@ -1505,18 +1703,18 @@ __global__ void __launch_bounds__(kNT, MINB) icp_pairs_kernel(const IcpArgs a) {
                 double acc[10];
 #pragma unroll
                 for (int k = 0; k < 10; ++k) acc[k] = 0.0;
-                for (int i0 = tid; i0 < n_s; i0 += 4 * kNT) {
+                for (int i0 = tid; i0 < n_s; i0 += 4 * NT) {
                     int jj[4];
                     double2 nn[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {                     // the normals live in global memory (L2)
-                        const int i = i0 + u * kNT;
+                        const int i = i0 + u * NT;
                         jj[u] = i < n_s ? m_idx<GRID>(L.match[i]) : 0;
                         nn[u] = __ldg(reinterpret_cast<const double2*>(normals) + jj[u]);
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const int i = i0 + u * kNT;
+                        const int i = i0 + u * NT;
                         if (i >= n_s) continue;
                         const double px = L.cx[i], py = L.cy[i];
                         double qx_, qy_, qz_;
@@ -1542,7 +1740,7 @@ __global__ void __launch_bounds__(kNT, MINB) icp_pairs_kernel(const IcpArgs a) {
                     const double ata[9] = {acc[0], acc[1], acc[2], acc[1], acc[3], acc[4], acc[2], acc[4], acc[5]};
                     const double atb[3] = {acc[6], acc[7], acc[8]};
                     double x[3];
-                    if (solve3_lu(ata, atb, x) == 0) {
+                    if (solve3_lu_rcp(ata, atb, x) == 0) {
                         double ct_, st_;
                         sincos(x[0], &st_, &ct_);                             // icp.py:110-114
                         sh.r[0] = ct_; sh.r[1] = -st_; sh.r[2] = st_; sh.r[3] = ct_;
@@ -1557,7 +1755,7 @@ __global__ void __launch_bounds__(kNT, MINB) icp_pairs_kernel(const IcpArgs a) {
                 double m[2 * DIM + 1];
 #pragma unroll
                 for (int k = 0; k < 2 * DIM + 1; ++k) m[k] = 0.0;
-                for (int i = tid; i < n_s; i += kNT) {
+                for (int i = tid; i < n_s; i += NT) {
                     const double px = L.cx[i], py = L.cy[i], pz = DIM == 3 ? L.cz[i] : 0.0;
                     double qx, qy, qz;
                     tgt_at<DIM, GRID>(L, m_idx<GRID>(L.match[i]), qx, qy, qz);
@@ -1579,7 +1777,7 @@ __global__ void __launch_bounds__(kNT, MINB) icp_pairs_kernel(const IcpArgs a) {
                 double w[DIM * DIM];
 #pragma unroll
                 for (int k = 0; k < DIM * DIM; ++k) w[k] = 0.0;
-                for (int i = tid; i < n_s; i += kNT) {
+                for (int i = tid; i < n_s; i += NT) {
                     double ps[3] = {L.cx[i], L.cy[i], DIM == 3 ? L.cz[i] : 0.0};
                     double qs[3];
                     tgt_at<DIM, GRID>(L, m_idx<GRID>(L.match[i]), qs[0], qs[1], qs[2]);
@@ -1603,8 +1801,12 @@ __global__ void __launch_bounds__(kNT, MINB) icp_pairs_kernel(const IcpArgs a) {
                     }
                 }
             }
-            if (tid == 0) {
-                // icp.py:210-211: r_total = r r_total ; t_total = r t_total + t
+            if (prof) { const long long c = clock64(); ph[3] += c - ph_t; ph_t = c; }
+            __syncthreads();
+            if (tid == NT - 1) {
+                // icp.py:210-211: r_total = r r_total ; t_total = r t_total + t -- off the critical path: nothing in the
+                // next iteration needs the totals, so the last thread (it has the fewest points to move) updates them
+                // while the others already apply the step
                 double nr[9], nt[3];
                 for (int u = 0; u < DIM; ++u) {
                     for (int v = 0; v < DIM; ++v) {
@@ -1619,13 +1821,11 @@ __global__ void __launch_bounds__(kNT, MINB) icp_pairs_kernel(const IcpArgs a) {
                 for (int k = 0; k < DIM * DIM; ++k) sh.r_tot[k] = nr[k];
                 for (int k = 0; k < DIM; ++k) sh.t_tot[k] = nt[k];
             }
-            if (prof) { const long long c = clock64(); ph[3] += c - ph_t; ph_t = c; }
-            __syncthreads();
             for (int k = 0; k < DIM * DIM; ++k) rr[k] = sh.r[k];
             for (int k = 0; k < DIM; ++k) tt[k] = sh.t[k];
             // icp.py:212 apply to ALL points; icp.py:215 error vs the OLD matches
             double e[1] = {0.0};
-            for (int i = tid; i < n_s; i += kNT) {
+            for (int i = tid; i < n_s; i += NT) {
                 double qx, qy, qz;
                 tgt_at<DIM, GRID>(L, m_idx<GRID>(L.match[i]), qx, qy, qz);
                 const double x = L.cx[i], y = L.cy[i];
@@ -1657,6 +1857,15 @@ __global__ void __launch_bounds__(kNT, MINB) icp_pairs_kernel(const IcpArgs a) {
             prev = err;
         }
         __syncthreads();
+        if (tid == 0 && a.pair_prof) {
+            st_amb += sh.amb_n;                    // (a break may leave the last iteration's count uncollected; profiling only)
+            unsigned long long* pp = a.pair_prof + 4 * (size_t)p;
+            atomicAdd(&pp[0], (unsigned long long)(clock64() - pair_t0));
+            atomicAdd(&pp[1], st_swept - pp_swept0);
+            atomicAdd(&pp[2], st_amb - pp_amb0);
+            atomicAdd(&pp[3], st_iters - pp_it0);
+            st_amb -= sh.amb_n;
+        }
         if (tid == 0 && !handed_over) {
             for (int k = 0; k < DIM * DIM; ++k) a.R_out[(size_t)p * DIM * DIM + k] = sh.r_tot[k];
             for (int k = 0; k < DIM; ++k) a.t_out[(size_t)p * DIM + k] = sh.t_tot[k];
@@ -1672,6 +1881,7 @@ __global__ void __launch_bounds__(kNT, MINB) icp_pairs_kernel(const IcpArgs a) {
         atomicAdd(&a.stats[2], st_iters);
         atomicAdd(&a.stats[3], st_swept);
         atomicAdd(&a.stats[4], st_kept);
+        atomicAdd(&a.stats[14], st_far);
         for (int k = 0; k < 5; ++k) atomicAdd(&a.stats[8 + k], (unsigned long long)ph[k]);
         atomicAdd(&a.stats[13], ph_iters);
     }
@@ -1881,10 +2091,10 @@ int launch_normals(const CloudSet& cs, int cap_t, int normal_k, double voxel, cu
     return ICPB200_OK;
 }
 
-template <int DIM, bool GRID, int MINB>
+template <int DIM, bool GRID, int MINB, int NT>
 static int launch_pairs_t(const IcpArgs& a, int n_ctas, size_t smem, cudaStream_t stream) {
-    ICPB_CUDA(cudaFuncSetAttribute(icp_pairs_kernel<DIM, GRID, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    icp_pairs_kernel<DIM, GRID, MINB><<<n_ctas, kNT, smem, stream>>>(a);
+    ICPB_CUDA(cudaFuncSetAttribute(icp_pairs_kernel<DIM, GRID, MINB, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    icp_pairs_kernel<DIM, GRID, MINB, NT><<<n_ctas, NT, smem, stream>>>(a);
     ICPB_LAUNCH_CHECK();
     return ICPB200_OK;
 }
@@ -1893,34 +2103,37 @@ static int launch_pairs_t(const IcpArgs& a, int n_ctas, size_t smem, cudaStream_
 // no spills: 1.22 against 1.26 ms on C2), grid mode 2 (4.56 against 4.75 ms for 592 scan->submap pairs), 3-D 3 (2 measured
 // the same on the teapot batch)
 static constexpr int bulk_minb(int dim, bool grid) { return grid ? 2 : (dim == 2 ? 2 : 3); }
+// Launches of at most one CTA per SM (the hand-over launch, single calls, small batches) are latency-bound -- a
+// registration is a chain of dependent iterations -- and take the 512-thread variant: two source points per thread instead
+// of four, sixteen warps to hide the shared-memory and fp64 latencies, every register the SM has (128 per thread).
+constexpr int kRoomyNT = 512;
 
-int launch_icp_pairs(const IcpArgs& a, int dim, bool grid, int n_ctas, size_t smem, cudaStream_t stream) {
+int launch_icp_pairs(const IcpArgs& a, int dim, bool grid, int n_ctas, size_t smem_min, cudaStream_t stream) {
     static const int sms = [] {
         int dev = 0, n = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         return n;
     }();
-    // a launch of at most one CTA per SM (the hand-over launch, single calls, small batches) takes the variant that is
-    // allowed every register: nothing spills (64 scan->submap pairs: 3.50 -> 1.93 ms)
     const bool roomy = a.resume || n_ctas <= sms;
+    const size_t smem = std::max(smem_min, icp_pair_smem_bytes(dim, a.cap_s, a.cap_t, roomy ? kRoomyNT : kNT));
     if (grid) {                                                                // grid mode is 2-D only
-        if (roomy) return launch_pairs_t<2, true, 1>(a, n_ctas, smem, stream);
-        return launch_pairs_t<2, true, bulk_minb(2, true)>(a, n_ctas, smem, stream);
+        if (roomy) return launch_pairs_t<2, true, 1, kRoomyNT>(a, n_ctas, smem, stream);
+        return launch_pairs_t<2, true, bulk_minb(2, true), kNT>(a, n_ctas, smem, stream);
     }
     if (dim == 2) {
-        if (roomy) return launch_pairs_t<2, false, 1>(a, n_ctas, smem, stream);
-        return launch_pairs_t<2, false, bulk_minb(2, false)>(a, n_ctas, smem, stream);
+        if (roomy) return launch_pairs_t<2, false, 1, kRoomyNT>(a, n_ctas, smem, stream);
+        return launch_pairs_t<2, false, bulk_minb(2, false), kNT>(a, n_ctas, smem, stream);
     }
-    if (roomy) return launch_pairs_t<3, false, 1>(a, n_ctas, smem, stream);
-    return launch_pairs_t<3, false, bulk_minb(3, false)>(a, n_ctas, smem, stream);
+    if (roomy) return launch_pairs_t<3, false, 1, kRoomyNT>(a, n_ctas, smem, stream);
+    return launch_pairs_t<3, false, bulk_minb(3, false), kNT>(a, n_ctas, smem, stream);
 }
 
 template <int DIM, bool GRID, int MINB>
 static int max_ctas_t(size_t smem) {
     int n = 0;
-    cudaFuncSetAttribute(icp_pairs_kernel<DIM, GRID, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, icp_pairs_kernel<DIM, GRID, MINB>, kNT, smem) != cudaSuccess || n < 1) n = 1;
+    cudaFuncSetAttribute(icp_pairs_kernel<DIM, GRID, MINB, kNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, icp_pairs_kernel<DIM, GRID, MINB, kNT>, kNT, smem) != cudaSuccess || n < 1) n = 1;
     return n;
 }
 

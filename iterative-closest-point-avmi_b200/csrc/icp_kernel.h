@@ -86,6 +86,7 @@ struct IcpArgs {
     float* cont_d2lb;
     float* cont_moved;
     double* cont_scalar;       // [slot][16]: r_tot(9) t_tot(3) prev err iters
+    unsigned long long* pair_prof; // optional [pair][4]: SM cycles, points swept, fp64 rescans, iterations (both launches add up)
     int* trace_match;          // optional: correspondences of the first trace_iters iterations (pair 0)
     int trace_iters;
     int trace_stride;
@@ -105,7 +106,7 @@ struct RotArgs {
 size_t rot_smem_bytes(int cap_t);
 int launch_rot_scores(const RotArgs& a, int n_problems, int max_angles, int sm_count, cudaStream_t stream);
 
-size_t icp_pair_smem_bytes(int dim, int cap_s, int cap_t);
+size_t icp_pair_smem_bytes(int dim, int cap_s, int cap_t, int nt = 256);      // nt: threads per CTA of the variant (256 bulk, 512 roomy)
 size_t icp_voxel_smem_bytes(int sort_pad);
 size_t icp_normals_smem_bytes(int cap_t);
 int icp_max_ctas_per_sm(int dim, bool grid, size_t smem);
@@ -114,7 +115,7 @@ int icp_max_ctas_per_sm(int dim, bool grid, size_t smem);
 int launch_mark_used(const IcpArgs& a, bool p2l, cudaStream_t stream);
 int launch_voxel_clouds(const CloudSet& cs, int dim, double voxel, int sort_pad, cudaStream_t stream, int first = 0, int count = -1);
 int launch_normals(const CloudSet& cs, int cap_t, int normal_k, double voxel, cudaStream_t stream, int first = 0, int count = -1);
-int launch_icp_pairs(const IcpArgs& a, int dim, bool grid, int n_ctas, size_t smem, cudaStream_t stream);
+int launch_icp_pairs(const IcpArgs& a, int dim, bool grid, int n_ctas, size_t smem_min, cudaStream_t stream);
 
 // big-cloud kernels (icp_big.cu)
 int launch_big_voxel(const CloudSet& cs, int dim, double voxel, unsigned long long* key_buf, unsigned* idx_buf,

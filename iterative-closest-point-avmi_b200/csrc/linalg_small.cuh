@@ -56,6 +56,42 @@ ICPB_HDL int solve3_lu(const double* a_in, const double* b_in, double* x) {
     return 0;
 }
 
+// The same elimination with one reciprocal per pivot (what LAPACK's dgetf2 does for pivots above the safe minimum)
+// instead of six divisions: the solve sits on the critical path of every iteration of the pair kernel.
+ICPB_HDL int solve3_lu_rcp(const double* a_in, const double* b_in, double* x) {
+    double a[3][3], b[3], inv[3];
+    for (int i = 0; i < 3; ++i) {
+        b[i] = b_in[i];
+        for (int j = 0; j < 3; ++j) a[i][j] = a_in[3 * i + j];
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 3; ++k) {
+        int p = k;
+        double best = fabs(a[k][k]);
+        for (int i = k + 1; i < 3; ++i) {
+            const double v = fabs(a[i][k]);
+            if (v > best) { best = v; p = i; }
+        }
+        if (!(best > 0.0)) return 1;                      // exactly singular (or NaN)
+        if (p != k) {
+            for (int j = 0; j < 3; ++j) { const double t = a[k][j]; a[k][j] = a[p][j]; a[p][j] = t; }
+            const double t = b[k]; b[k] = b[p]; b[p] = t;
+        }
+        inv[k] = 1.0 / a[k][k];
+        for (int i = k + 1; i < 3; ++i) {
+            const double f = a[i][k] * inv[k];
+            for (int j = k + 1; j < 3; ++j) a[i][j] -= f * a[k][j];
+            b[i] -= f * b[k];
+        }
+    }
+    x[2] = b[2] * inv[2];
+    x[1] = (b[1] - a[1][2] * x[2]) * inv[1];
+    x[0] = (b[0] - a[0][1] * x[1] - a[0][2] * x[2]) * inv[0];
+    return 0;
+}
+
 // 2-D Kabsch: w = S_c^T T_c (row-major 2x2, w[a][b] = sum s_a t_b).  The proper
 // rotation maximising trace(R w^T) is R(theta) with
 // theta = atan2(w01 - w10, w00 + w11); this equals V U^T with the reference's

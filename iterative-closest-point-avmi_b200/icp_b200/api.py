@@ -139,6 +139,16 @@ def icp_phase_profile():
     return dict(phases=phases, iterations_profiled=int(st[5]), cycles_per_iteration=float(sum(phases.values())) if st[5] else 0.0)
 
 
+def icp_pair_profile(n_pairs=0):
+    """Per-pair counters of the last registration call: (n, 4) int64 = cycles, points swept, fp64 fallbacks, iterations.
+    The first call only switches the counters on (returns an empty array)."""
+    out = np.zeros((max(int(n_pairs), 1), 4), dtype=np.int64)
+    n = _lib.load().icpb200_icp_pair_profile(_ptr(out, c_int64_p), int(n_pairs))
+    if n < 0:
+        check(n, "icpb200_icp_pair_profile")
+    return out[:n]
+
+
 def voxel_downsample(points, voxel_size):
     pts = _f64(points)
     out = np.empty_like(pts)
