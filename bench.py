@@ -624,8 +624,8 @@ def run_ours(args, rank, world, local_rank):
 def bench_raycast(args, lib, api, dev, local_rank, pk, rank=0, world=1, verify=False):
     """C4: 2000 scans x 1080 rays into a 4096 x 4096 grid @ 5 cm.
 
-    Multi-GPU: the grid is cut into horizontal strips of 64-cell tile rows, one per rank;
-    every rank replays every scan clipped to its own strip of tile rows, then one NCCL all_gather over
+    Multi-GPU: the grid is cut into bands of 64 rows dealt round-robin over the ranks;
+    every rank replays every scan clipped to its own bands, then one NCCL all_gather over
     the device grids reassembles the map (strong scaling: the job is fixed)."""
     import torch
     import torch.distributed as dist
@@ -659,7 +659,7 @@ def bench_raycast(args, lib, api, dev, local_rank, pk, rank=0, world=1, verify=F
                                  stream.cuda_stream)
             m.record(stream)
             if world > 1:
-                icpd.grid_allreduce_device(grid._dev, sync=False)      # stream-ordered behind the update
+                icpd.grid_gather_device(grid._dev, sync=False)      # stream-ordered behind the update
             b.record(stream)
             torch.cuda.synchronize()
             if k >= 3:
@@ -679,7 +679,7 @@ def bench_raycast(args, lib, api, dev, local_rank, pk, rank=0, world=1, verify=F
         t0 = time.perf_counter()
         grid._dev.update(origins, flat, off)
         if world > 1:
-            icpd.grid_allreduce_device(grid._dev)
+            icpd.grid_gather_device(grid._dev)
         if rank == 0:                                   # one consumer reads the reassembled map
             grid._dev.read(host_out)
         if k >= 1:
@@ -715,11 +715,11 @@ def bench_raycast(args, lib, api, dev, local_rank, pk, rank=0, world=1, verify=F
     alg_bytes = 16.0 * n_rays + 8.0 * cells + 8.0 * hits_in
     cpu = cpu_raycast_baseline(origins, flat, off, min(len(off) - 1, 60)) if not args.no_cpu and world == 1 else None
     return dict(metric="occupancy_rays_per_s", value=n_rays / sec, unit="rays/s", ms_per_step=sec * 1e3,
-                n_gpus=world, scaling="strong", update_only_ms=sec_update * 1e3,
+                n_gpus=world, scaling="strong", update_only_ms=sec_update * 1e3, gather_ms=(sec - sec_update) * 1e3,
                 config=dict(workload=f"C4 occupancy log-odds raycast: {len(off) - 1} scans, {n_rays} rays, "
                                      f"{grid.nx}x{grid.ny} grid @ 0.05 m, campus world", **GRID_CFG,
                             cells_per_ray=cells / n_rays, tile_runs=st["runs"],
-                            sharding="horizontal strips of 64-cell tile rows, one per GPU; every ray clipped to the strip; one NCCL all_gather of the strips inside the timed region (update_only_ms = the slowest rank's update without it); e2e: one rank reads the reassembled map"),
+                            sharding="bands of 64 rows dealt round-robin over the GPUs; every rank walks every ray clipped to its own bands, in scan order; one NCCL all_gather of the packed bands inside the timed region (update_only_ms = the slowest rank's update without it, gather_ms = the rest); e2e: one rank reads the reassembled map"),
                 e2e=dict(value=n_rays / e2e_s, unit="rays/s",
                          h2d_bytes_per_step=int(origins.nbytes + flat.nbytes + off.nbytes),
                          d2h_bytes_per_step=int(host_out.nbytes), api="icpb200_grid_update + icpb200_grid_read"),

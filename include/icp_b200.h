@@ -188,11 +188,11 @@ void *icpb200_grid_create(int nx, int ny, double min_x, double min_y, double res
                           double l_hit, double l_miss, double lo_min, double lo_max);
 void icpb200_grid_destroy(void *grid);
 
-/* Multi-GPU spatial sharding: this process updates only its horizontal strip
- * of the grid -- the rows of the 64-cell tile rows [rank*T/world,
- * (rank+1)*T/world), T = ceil(ny/64); all other cells stay 0, so a gather of
- * the strips (or an element-wise sum over ranks) reassembles the map.  Call
- * before the first update of the grid. */
+/* Multi-GPU spatial sharding: the grid is cut into bands of 64 rows (one row
+ * of 64 x 64-cell tiles) dealt round-robin; this process updates only the
+ * bands b with b % world == rank and never touches any other row, so a gather
+ * of every rank's bands reassembles the map (icp_b200.dist.grid_gather_device).
+ * Call before the first update of the grid. */
 int icpb200_grid_set_shard(void *grid, int rank, int world);
 
 /* mapping.py:103-141 for n_scans scans applied in array order (n_scans = 1 is

@@ -240,10 +240,12 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
         const size_t np_ = (size_t)n_pairs, cs_ = (size_t)a.cap_s;
         if (c.cont_cur.reserve(sizeof(double) * k.dim * cs_ * np_) || c.cont_match.reserve(sizeof(int) * cs_ * np_) ||
             c.cont_d2lb.reserve(sizeof(float) * cs_ * np_) || c.cont_moved.reserve(sizeof(float) * k.dim * cs_ * np_) ||
-            c.cont_scalar.reserve(sizeof(double) * 16 * np_) || c.cont_list.reserve(sizeof(int) * np_))
+            c.cont_scalar.reserve(sizeof(double) * 16 * np_) || c.cont_list.reserve(sizeof(int) * 4 * np_))
             return ICPB200_ERR_CUDA;
-        a.cont_count = a.queue + 2;
+        a.cont_count = a.queue + 8;                                   // [8] total, [9..11] per cost class
         a.cont_list = c.cont_list.as<int>();
+        a.cont_bucket = a.cont_list + np_;
+        a.cont_cap = n_pairs;
         a.cont_cur = c.cont_cur.as<double>();
         a.cont_match = c.cont_match.as<int>();
         a.cont_d2lb = c.cont_d2lb.as<float>();

@@ -37,6 +37,7 @@ struct CtaSharedT {
     int part_bt[NW_][32], part_bt2[NW_][32];
     int bins[65];                      // x-bins of the points to decide (K3: todo list ordered for the slab sweep)
     int front_n;                       // K3 far-field front set size
+    int slab_off;                      // K3: sweeps left before the slab sweep is tried again (it pruned too little last time)
 };
 using CtaShared = CtaSharedT<kNW>;     // the 256-thread kernels (K1, K2, K8, bulk K3)
 

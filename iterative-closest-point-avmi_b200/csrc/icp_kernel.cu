@@ -41,6 +41,7 @@
 namespace icpb {
 
 constexpr int kSMax = 8;               // chunks (of 32 source points) per warp per sweep round
+constexpr unsigned kContClasses = 3;   // cost classes of the handed-over pairs (IcpArgs::cont_bucket)
 constexpr int kKnnMax = 64;            // normal_k + 1 upper bound
 constexpr int kGridCells = 4096;       // shared-memory uniform grid for the normals kNN
 constexpr float kFar = 3.0e18f;        // padding target coordinate (distance^2 ~ 1.8e37, finite)
@@ -1472,11 +1473,19 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
         // phase 1 takes pairs in order; phase 2 (a.resume) takes the pairs phase 1 handed over
         if (tid == 0) {
             const unsigned q = atomicAdd(a.queue, 1u);
-            const unsigned limit = a.resume ? *a.cont_count : (unsigned)a.n_pairs;
-            sh.pair = q < limit ? (a.resume ? (unsigned)a.cont_list[q]
-                                            : (a.pair_order ? (unsigned)a.pair_order[a.pair_first + q] : (unsigned)a.pair_first + q))
-                                : 0xffffffffu;
-            sh.bcast_i[2] = (int)q;                 // continuation slot when resuming
+            if (a.resume) {
+                // the handed-over pairs, most expensive class first (longest processing time first: the last CTAs to
+                // finish should be running short pairs, not a 150-iteration chain of full sweeps)
+                unsigned rest = q, b = 0;
+                while (b < kContClasses && rest >= a.cont_count[1 + b]) { rest -= a.cont_count[1 + b]; ++b; }
+                const int slot = b < kContClasses ? a.cont_bucket[(size_t)b * a.cont_cap + rest] : -1;
+                sh.pair = slot >= 0 ? (unsigned)a.cont_list[slot] : 0xffffffffu;
+                sh.bcast_i[2] = slot;               // where the pair's state was parked
+            } else {
+                sh.pair = q < (unsigned)a.n_pairs ? (a.pair_order ? (unsigned)a.pair_order[a.pair_first + q] : (unsigned)a.pair_first + q)
+                                                  : 0xffffffffu;
+                sh.bcast_i[2] = (int)q;
+            }
         }
         __syncthreads();
         if (sh.pair == 0xffffffffu) break;
@@ -1518,6 +1527,7 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
             sh.amb_n = 0;
             sh.slab_evals = 0u;
             sh.bcast_i[0] = 0;                     // todo counter
+            sh.slab_off = 0;
         }
         // ---- stage the target: fp64 (tile-padded SoA) and recentred fp32
         if (GRID) {
@@ -1629,6 +1639,10 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
                     for (int k = 0; k < DIM; ++k) sc[9 + k] = sh.t_tot[k];
                     sc[12] = prev; sc[13] = err; sc[14] = (double)iters;
                     a.cont_list[slot] = p;
+                    // cost class from the points swept so far: a pair that kept re-deciding most of its points will go on doing so
+                    const unsigned long long per_it = (st_swept - pp_swept0) / (unsigned long long)max(iters, 1);
+                    const int cls = per_it * 4ull >= (unsigned long long)n_s ? 0 : per_it * 10ull >= (unsigned long long)n_s ? 1 : 2;
+                    a.cont_bucket[(size_t)cls * a.cont_cap + atomicAdd(&a.cont_count[1 + cls], 1u)] = slot;
                 }
                 handed_over = true;
                 break;
@@ -1668,13 +1682,18 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
             if (prof) { const long long c = clock64(); ph[0] += c - ph_t; ph_t = c; }
             const int n_todo = sh.bcast_i[0];
             L.list = L.todo;
+            bool use_slab = false;
             if (n_todo > 0) {
                 if (GRID) {
                     grid_nn<DIM, NT>(L, n_todo);
                 } else {
-                    if (slab_vox > 0.f && ((n_todo + 31) >> 5) > (NT / 32) / 2)          // the slab sweep will run
+                    // The slab sweep prunes by x alone: when the points sit metres from the target (a pair that does not
+                    // align) its walks cover most of the target, one candidate block after the other, and the register-
+                    // blocked tile sweep is the faster way to look at everything.  The sweep measures itself (slab_off).
+                    use_slab = slab_vox > 0.f && sh.slab_off == 0;
+                    if (use_slab && ((n_todo + 31) >> 5) > (NT / 32) / 2)                 // the slab sweep will run
                         order_todo_by_x<DIM, NT>(L, sh, n_todo, tgt_xlo, tgt_xhi);
-                    nn_dispatch<DIM, NT>(L, sh, n_todo, slab_vox);
+                    nn_dispatch<DIM, NT>(L, sh, n_todo, use_slab ? slab_vox : 0.f);
                     __syncthreads();
                     // a few undecided points: one warp each scans the target; many: a lane each, tiles filtered in fp32
                     if (sh.amb_n > NT / 32) resolve_ambiguous_lockstep<DIM, NT>(L, sh);
@@ -1684,9 +1703,12 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
             if (tid == 0) {
                 const int n_chunks = (n_todo + 31) >> 5;
                 if (!GRID) {
-                    const bool slab = slab_vox > 0.f && n_chunks > (NT / 32) / 2;      // nn_dispatch's choice
-                    st_evals += slab ? (unsigned long long)sh.slab_evals
-                                     : (unsigned long long)n_chunks * 32ull * (unsigned long long)L.n_tiles * 32ull;
+                    const bool bulk = n_chunks > (NT / 32) / 2;                      // nn_dispatch's choice: not the split sweep
+                    const bool slab = use_slab && bulk;
+                    const unsigned long long all = (unsigned long long)n_chunks * 32ull * (unsigned long long)L.n_tiles * 32ull;
+                    st_evals += slab ? (unsigned long long)sh.slab_evals : all;
+                    if (slab) { if ((unsigned long long)sh.slab_evals * 20ull > all * 9ull) sh.slab_off = 4; }   // walked > 45 % of the target
+                    else if (bulk && sh.slab_off > 0) --sh.slab_off;
                     sh.slab_evals = 0u;
                 }
                 st_swept += n_todo; st_kept += n_s - n_todo; st_iters += 1;

@@ -79,8 +79,10 @@ struct IcpArgs {
     // second launch (resume = 1) that runs one CTA per SM, so the long tail does not share its SM
     int phase_cap;             // <= 0: single launch
     int resume;
-    unsigned int* cont_count;  // pairs handed over
+    unsigned int* cont_count;  // [0] pairs handed over, [1..3] per cost class
     int* cont_list;            // [slot] -> pair
+    int* cont_bucket;          // [class][cont_cap] -> slot: the second launch takes the expensive classes first
+    int cont_cap;              // pairs of the whole call (row length of cont_bucket)
     double* cont_cur;          // [slot][dim][cap_s]
     int* cont_match;           // [slot][cap_s]
     float* cont_d2lb;

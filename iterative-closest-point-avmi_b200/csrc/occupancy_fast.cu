@@ -73,7 +73,7 @@ struct FastArgs {
     int scan_begin, chunk_scans, n_scans;
     double min_x, min_y, res;
     int nx, ny, tiles_x, n_tiles;
-    int ya, yb;                               // this rank's rows (occ_strip_begin)
+    int rank, world;                          // this rank walks the bands b with b % world == rank (occ_owner)
     int2* ray_cell;                           // chunk-relative
     int* ray_scan;
     int2* origin_cell;                        // absolute scan index
@@ -99,21 +99,42 @@ struct FastArgs {
 // Tile crossings of one ray with the divisions done in 32 bits whenever the ray
 // is short enough (always, for endpoints inside a <= 16k-cell grid); same runs
 // in the same order as TileRunIter<TS>.
+// SHARDED = false: one GPU, the band is the whole grid and none of the band state exists (the ray passes run at 32
+// registers per thread).
+template <bool SHARDED>
 struct FastTileIter {
-    RayGeom g;
+    RayGeom g0;                                 // the ray in grid coordinates (SHARDED only)
+    RayGeom g;                                  // ... in the coordinates of the band being walked
     int n, nb;
     bool small;
     int tiles_x, tile_row0;
-    __device__ __forceinline__ void init_empty() { n = 0; nb = 0; small = true; tile_row0 = 0; }
-    // rows [ya, yb) are this rank's strip (the whole grid on one GPU): the ray is clipped to it in closed form
-    __device__ __forceinline__ void init(const RayGeom& geom, int nx, int ya, int yb, int tiles_x_) {
-        g = geom; tiles_x = tiles_x_;
-        g.oy -= ya;                                            // strip coordinates; ya is a multiple of TS
+    int nx, ny, world;
+    int band, band_last;                        // owned bands (tile rows) still to visit: band, band + world, ... <= band_last
+    __device__ __forceinline__ void init_empty() { n = 0; nb = 0; small = true; tile_row0 = 0; band = 1; band_last = 0; world = 1; }
+    // rows [ya, yb) are one band (the whole grid on one GPU): the ray is clipped to it in closed form
+    __device__ __forceinline__ void init_band(int ya, int yb) {
+        if (SHARDED) g = g0;
+        g.oy -= ya;                                            // band coordinates; ya is a multiple of TS
         tile_row0 = ya / TS;
         int64_t a = 0, b = 0;
         if (g.dmaj != 0) clip_to_grid(g, nx, yb - ya, a, b);
         n = (int)a; nb = (int)b;
         small = g.dmaj < (1 << 14) && nb < (1 << 14);          // 2*n*dmin + dmaj < 2^30
+    }
+    // this rank walks the bands b with b % world == rank (occ_owner); one GPU: a single band, the whole grid
+    __device__ __forceinline__ void init(const RayGeom& geom, int nx_, int ny_, int rank, int world_, int tiles_x_) {
+        tiles_x = tiles_x_; nx = nx_; ny = ny_;
+        n = 0; nb = 0; small = true; tile_row0 = 0;
+        if (!SHARDED) { g = geom; init_band(0, ny); return; }
+        g0 = geom; world = world_;
+        // rows the ray can touch: between its origin and its endpoint (the endpoint itself is not walked, no matter)
+        const int y_end = g0.xmajor ? g0.oy + g0.smin * g0.dmin : g0.oy + g0.smaj * g0.dmaj;
+        int ylo = min(g0.oy, y_end), yhi = max(g0.oy, y_end);
+        if (yhi < 0 || ylo >= ny || g0.dmaj == 0) { band = 1; band_last = 0; return; }
+        ylo = max(ylo, 0); yhi = min(yhi, ny - 1);
+        const int blo = ylo / TS;
+        band_last = yhi / TS;
+        band = blo + ((rank - blo) % world + world) % world;      // first owned band at or after blo
     }
     __device__ __forceinline__ int minor_at(int nn) const {
         if (small) return (int)((2u * (unsigned)nn * (unsigned)g.dmin + (unsigned)g.dmaj - 1u) / (2u * (unsigned)g.dmaj));
@@ -127,7 +148,11 @@ struct FastTileIter {
         return first_step_reaching(g, j);
     }
     __device__ __forceinline__ bool next(TileRun& r) {
-        if (n >= nb) return false;
+        while (n >= nb) {                                      // this band is done: on to the next one this rank owns
+            if (!SHARDED || band > band_last) return false;
+            init_band(band * TS, min(band * TS + TS, ny));
+            band += world;
+        }
         const int j = minor_at(n);
         int x, y;
         cell_at(g, n, j, x, y);
@@ -169,7 +194,7 @@ __global__ void occ_fast_origins(const double* __restrict__ origins, int n_scans
 
 // CHECK: some scan has more than 4095 rays, so a cell could collect more hits in one scan than
 // the 12-bit field holds; only then the hit atomic needs its return value.
-template <bool FILL, bool CHECK>
+template <bool FILL, bool CHECK, bool SHARDED>
 __global__ void __launch_bounds__(256, 8) occ_fast_rays(const FastArgs a) {
     if (a.small[kFlagBadOffsets]) return;                     // offsets checked on the device: the host reports the error
     if (FILL && ((unsigned long long)a.small[0] + 64ull > a.runs_cap ||
@@ -181,7 +206,7 @@ __global__ void __launch_bounds__(256, 8) occ_fast_rays(const FastArgs a) {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned long long cells = 0, nhits = 0, nruns = 0;
-    FastTileIter it;
+    FastTileIter<SHARDED> it;
     it.init_empty();
     int sl = 0;
     unsigned hit_old = 0u;
@@ -206,10 +231,10 @@ __global__ void __launch_bounds__(256, 8) occ_fast_rays(const FastArgs a) {
         }
         sl = s - a.scan_begin;
         const int2 o = a.origin_cell[s];
-        it.init(make_ray(o.x, o.y, h.x, h.y), a.nx, a.ya, a.yb, a.tiles_x);
+        it.init(make_ray(o.x, o.y, h.x, h.y), a.nx, a.ny, a.rank, a.world, a.tiles_x);
         if (h.x >= 0 && h.x < a.nx && h.y >= 0 && h.y < a.ny) {                 // mapping.py:124-127
             const int tile = (h.y / TS) * a.tiles_x + (h.x / TS);
-            if (h.y >= a.ya && h.y < a.yb) {
+            if (occ_owner(h.x, h.y, a.nx, a.ny, a.world) == a.rank) {
                 const size_t cell = (size_t)h.y * a.nx + h.x;
                 if (!FILL) {
                     ++nhits;
@@ -240,7 +265,7 @@ __global__ void __launch_bounds__(256, 8) occ_fast_rays(const FastArgs a) {
         TileRun t;
         const bool has = it.next(t);
         const bool more = __any_sync(0xffffffffu, has);
-        const bool owned = has;                                // the walk is already clipped to the rank's strip
+        const bool owned = has;                                // the walk is already clipped to the rank's bands
         const int seg = owned ? t.tile * kLenClasses + ((t.len - 1) >> kLenShift) : -1 - lane;
         unsigned base = 0, off = 0, peers = 0;
         int leader = 0;
@@ -833,7 +858,7 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
     a.scan_begin = s0; a.chunk_scans = cs; a.n_scans = n_scans;
     a.min_x = g.min_x; a.min_y = g.min_y; a.res = g.res;
     a.nx = g.nx; a.ny = g.ny; a.tiles_x = tiles_x; a.n_tiles = n_tiles;
-    a.ya = occ_strip_begin(g.rank, g.ny, g.world); a.yb = occ_strip_begin(g.rank + 1, g.ny, g.world);
+    a.rank = g.rank; a.world = g.world;
     a.ray_cell = g.ray_cell.as<int2>();
     a.ray_scan = g.ray_scan.as<int>();
     a.origin_cell = g.origin_cell.as<int2>();
@@ -846,7 +871,9 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
     a.runs_cap = 0; a.ord_cap = 0;
     a.small = d_small; a.stats = d_stats;
     const unsigned nblk = (unsigned)((nr + 255) / 256);
-    occ_fast_rays<false, false><<<nblk, 256, 0, st>>>(a);
+    const bool sharded = g.world > 1;
+    if (sharded) occ_fast_rays<false, false, true><<<nblk, 256, 0, st>>>(a);
+    else occ_fast_rays<false, false, false><<<nblk, 256, 0, st>>>(a);
     ICPB_LAUNCH_CHECK();
     tm.mark("count");
     occ_tile_scan<<<1, 1024, 0, st>>>(g.tile_count.as<unsigned>(), n_tiles, g.offsets.as<unsigned>(), g.class_off.as<unsigned>(), g.tile_flag.as<unsigned>(), g.items.as<uint2>(), g.multi.as<int>(), d_small);
@@ -862,8 +889,13 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
         a.runs = g.runs.as<uint4>();
         a.runs_cap = g.runs.cap / sizeof(uint4);
         a.ord_cap = g.ord.cap / sizeof(unsigned);
-        if (big_scan) occ_fast_rays<true, true><<<nblk, 256, 0, st>>>(a);
-        else occ_fast_rays<true, false><<<nblk, 256, 0, st>>>(a);
+        if (sharded) {
+            if (big_scan) occ_fast_rays<true, true, true><<<nblk, 256, 0, st>>>(a);
+            else occ_fast_rays<true, false, true><<<nblk, 256, 0, st>>>(a);
+        } else {
+            if (big_scan) occ_fast_rays<true, true, false><<<nblk, 256, 0, st>>>(a);
+            else occ_fast_rays<true, false, false><<<nblk, 256, 0, st>>>(a);
+        }
         ICPB_LAUNCH_CHECK();
         return ICPB200_OK;
     };

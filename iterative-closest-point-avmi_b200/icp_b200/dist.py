@@ -5,12 +5,12 @@
   data-path collective and uploads only the clouds its pairs reference; one
   all_gather of packed result blocks returns (R, t, error, iters, status) of
   every pair to all ranks.
-* occupancy replay: rank r owns a horizontal strip of the grid -- the 64-cell tile
-  rows [r*T/world, (r+1)*T/world) (the rule libicp_b200 applies in
-  icpb200_grid_set_shard); every rank replays every scan clipped to its own strip,
-  in scan order, so the clamp order matches the reference.  Cells a rank does not
-  own stay exactly 0: one all_gather of the strips (equally tall strips) or one
-  all_reduce(SUM) reassembles the map bit-exactly.
+* occupancy replay: the grid is cut into bands of 64 rows dealt round-robin -- rank
+  r owns the bands b with b % world == r (the rule libicp_b200 applies in
+  icpb200_grid_set_shard); every rank replays every scan clipped to its own bands,
+  in scan order, so the clamp order matches the reference.  One all_gather of the
+  packed bands reassembles the map bit-exactly (a gather, never a sum: rows a rank
+  does not own are overwritten).
 
 NCCL (GPU tensors) on the B200 box, gloo (CPU tensors) in the CPU tests.
 """
@@ -214,30 +214,34 @@ class DevicePairShard:
         return _unpack_results(self.gathered.cpu().numpy(), self.plan, self.dim)
 
 
-def strip_rows(ny, rank, size):
-    """Rows [lo, hi) of the grid owned by `rank` (occ_strip_begin in csrc/occupancy.h)."""
-    tiles_y = (ny + TILE - 1) // TILE
-    lo = min((tiles_y * rank // size) * TILE, ny)
-    hi = min((tiles_y * (rank + 1) // size) * TILE, ny)
-    return lo, hi
+def owned_rows(ny, rank, size):
+    """(ny,) bool: the grid rows `rank` owns -- bands of TILE rows dealt round-robin (occ_owner in csrc/occupancy.h)."""
+    return (np.arange(ny) // TILE) % size == rank
 
 
 def owned_tile_mask(nx, ny, rank, size):
     """(ny, nx) bool mask of the cells this rank owns."""
-    lo, hi = strip_rows(ny, rank, size)
-    mask = np.zeros((ny, nx), dtype=bool)
-    mask[lo:hi] = True
-    return mask
+    return np.repeat(owned_rows(ny, rank, size)[:, None], nx, axis=1)
 
 
-def grid_allreduce_host(log_odds):
-    """Sum the per-rank partial maps held as host arrays (gloo / tests)."""
+def grid_gather_host(log_odds):
+    """Reassemble the sharded map from per-rank host arrays (gloo / tests): every rank contributes the rows it owns.
+    A gather, not a sum: what a rank holds in rows it does not own (zeros, or a previously reassembled map) is ignored."""
     rank, size = world()
     if size == 1:
         return log_odds
-    t = torch.from_numpy(np.ascontiguousarray(log_odds)).to(_comm_device())
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return t.cpu().numpy()
+    ny, nx = log_odds.shape
+    mine = np.ascontiguousarray(log_odds[owned_rows(ny, rank, size)])
+    counts = [int(owned_rows(ny, r, size).sum()) for r in range(size)]
+    send = torch.zeros((max(counts), nx), dtype=torch.float32)
+    send[:len(mine)] = torch.from_numpy(mine)
+    send = send.to(_comm_device())
+    bufs = [torch.empty_like(send) for _ in range(size)]
+    dist.all_gather(bufs, send)
+    out = np.array(log_odds, copy=True)
+    for r in range(size):
+        out[owned_rows(ny, r, size)] = bufs[r][:counts[r]].cpu().numpy()
+    return out
 
 
 class _DevArray:
@@ -253,23 +257,38 @@ def grid_device_tensor(device_grid):
                            device=torch.device("cuda", torch.cuda.current_device()))
 
 
-def grid_allreduce_device(device_grid, sync=True):
-    """Reassemble the sharded grid on every rank, in place on the device (NCCL, B200 box): an all_gather of the
-    strips when they are equally tall (each rank sends only its own rows), else an all_reduce(SUM).
+def grid_gather_device(device_grid, sync=True):
+    """Reassemble the sharded grid on every rank, in place on the device (NCCL, B200 box).
 
-    sync=False leaves everything stream-ordered on torch's current stream (the caller ran the update on that
-    stream -- icpb200_grid_update_dev -- and reads the result on it): no host wait on either side."""
+    Rank r's bands (rows [64 b, 64 b + 64) with b % size == r) are packed into one contiguous block, one
+    all_gather_into_tensor moves every rank's block to every rank, and the blocks are scattered back to their rows.
+    A gather, never a sum: rows a rank does not own are overwritten, so update -> gather -> update -> gather works
+    without a reset in between.  sync=False leaves everything stream-ordered on torch's current stream (the caller ran
+    the update on that stream -- icpb200_grid_update_dev -- and reads the result on it): no host wait on either side."""
     rank, size = world()
-    if size > 1:
-        t = grid_device_tensor(device_grid)
-        ny = t.shape[0]
-        rows = [strip_rows(ny, r, size) for r in range(size)]
-        if sync:
-            torch.cuda.synchronize()
-        if len({hi - lo for lo, hi in rows}) == 1 and rows[-1][1] == ny:
-            lo, hi = rows[rank]
-            dist.all_gather_into_tensor(t, t[lo:hi])
-        else:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        if sync:
-            torch.cuda.synchronize()
+    if size == 1:
+        return
+    t = grid_device_tensor(device_grid)
+    ny, nx = t.shape
+    per = -(-ny // (TILE * size))                      # bands per rank, the last ones possibly short or missing
+    if sync:
+        torch.cuda.synchronize()
+    stage = getattr(device_grid, "_gather_stage", None)
+    if stage is None or stage[0].shape != (per, TILE, nx):
+        stage = (torch.empty((per, TILE, nx), dtype=torch.float32, device=t.device),
+                 torch.empty((size, per, TILE, nx), dtype=torch.float32, device=t.device),
+                 None if ny == per * size * TILE else torch.zeros((per * size * TILE, nx), dtype=torch.float32, device=t.device))
+        device_grid._gather_stage = stage
+    send, recv, padded = stage
+    full = t
+    if padded is not None:                            # ny is not a multiple of 64 * size: work on a padded copy
+        padded[:ny].copy_(t)
+        full = padded
+    bands = full.view(per, size, TILE, nx)
+    send.copy_(bands[:, rank])
+    dist.all_gather_into_tensor(recv, send)
+    bands.copy_(recv.permute(1, 0, 2, 3))
+    if padded is not None:
+        t.copy_(padded[:ny])
+    if sync:
+        torch.cuda.synchronize()

@@ -57,12 +57,24 @@ def _worker(rank, size, port, tmp):
         mask = icpd.owned_tile_mask(full.nx, full.ny, rank, size)
         other = icpd.owned_tile_mask(full.nx, full.ny, 1 - rank, size)
         assert not (mask & other).any() and (mask | other).all()
-        lo, hi = icpd.strip_rows(full.ny, rank, size)              # horizontal strips of whole tile rows
-        assert lo % icpd.TILE == 0 and mask[lo:hi].all() and mask.sum() == (hi - lo) * full.nx
-        assert (lo, hi) == ((0, 192) if rank == 0 else (192, 384))
+        rows = icpd.owned_rows(full.ny, rank, size)                # bands of 64 rows dealt round-robin
+        assert np.array_equal(rows, (np.arange(full.ny) // icpd.TILE) % 2 == rank) and mask.sum() == rows.sum() * full.nx
         partial = np.where(mask, full.log_odds, np.float32(0))
-        total = icpd.grid_allreduce_host(partial)
+        total = icpd.grid_gather_host(partial)
         assert total.dtype == np.float32 and total.tobytes() == full.log_odds.tobytes()
+        # a second round WITHOUT a reset: the rows a rank does not own now hold the previous map (not zeros); the
+        # reassembly is a gather, so they are simply overwritten (a sum over ranks would double them)
+        for s in range(6, 8):
+            full.update_scan(poses[s, :2] * 0.4, synth.to_world_frame(scans[s], poses[s]) * 0.4)
+        stale = total.copy()
+        stale[rows] = full.log_odds[rows]                           # this rank updated only its own rows
+        again = icpd.grid_gather_host(stale)
+        assert again.tobytes() == full.log_odds.tobytes()
+        # a grid whose bands do not divide by the ranks (5 bands over 2 ranks, the last one short)
+        odd = np.arange(300 * 7, dtype=np.float32).reshape(300, 7)
+        rows_odd = icpd.owned_rows(300, rank, size)
+        part = np.where(rows_odd[:, None], odd, np.float32(-1))
+        assert icpd.grid_gather_host(part).tobytes() == odd.tobytes()
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

@@ -133,25 +133,39 @@ def test_campus_replay_batched_vs_oracle():
 
 
 def test_spatial_shards_sum_to_whole_map():
-    """Multi-GPU seam emulated on one GPU: world=4 shards, each replaying all
-    scans clipped to its own tiles; the element-wise sum equals the unsharded map."""
+    """Multi-GPU seam emulated on one GPU: world = 4 and world = 3 shards (bands of 64 rows dealt round-robin, the rule
+    of icp_b200.dist.owned_rows), each replaying all scans clipped to its own bands.  Every shard writes only rows it
+    owns, bit-exactly the rows of the unsharded map, so the gather of the owned rows is the whole map -- also in a second
+    round without a reset, when the rows a shard does not own hold stale values."""
+    from icp_b200 import dist as icpd
     scans, poses = synth.make_sequence(40, world="room", seed=2)
     hits = [synth.to_world_frame(s, p) for s, p in zip(scans, poses)]
     flat, off = synth.pack_ragged(hits)
+    half = int(off[20])
     bounds = (-25.6, 25.6, -25.6, 25.6)
     whole, ref = make_pair(bounds, **GKW)
     whole._dev.update(poses[:, :2].copy(), flat, off)
     ref.update_many(poses[:, :2].copy(), flat, off)
     assert_same(whole, ref, "unsharded")
-    total = np.zeros_like(whole.log_odds)
-    for rank in range(4):
-        part, _ = make_pair(bounds, **GKW)
-        part._dev.set_shard(rank, 4)
-        part._dev.update(poses[:, :2].copy(), flat, off)
-        piece = part.log_odds
-        assert not np.any((piece != 0) & (total != 0))    # shards are disjoint
-        total += piece
-    assert total.tobytes() == whole.log_odds.tobytes()
+    first, _ = make_pair(bounds, **GKW)
+    first._dev.update(poses[:20, :2].copy(), flat[:half], off[:21])
+    first_map = first.log_odds.copy()
+    for world in (4, 3):
+        total = np.zeros_like(whole.log_odds)
+        for rank in range(world):
+            part, _ = make_pair(bounds, **GKW)
+            part._dev.set_shard(rank, world)
+            rows = icpd.owned_rows(part.ny, rank, world)
+            # round 1: the first 20 scans; round 2, no reset: the other 20 on top
+            part._dev.update(poses[:20, :2].copy(), flat[:half], off[:21])
+            piece = part._dev.read()                  # (the shim's log_odds property caches: read the device directly)
+            assert not piece[~rows].any(), f"world {world} rank {rank} wrote rows it does not own"
+            assert piece[rows].tobytes() == first_map[rows].tobytes()
+            part._dev.update(poses[20:, :2].copy(), flat[half:], off[20:] - off[20])
+            piece = part._dev.read()
+            assert not piece[~rows].any()
+            total[rows] = piece[rows]
+        assert total.tobytes() == whole.log_odds.tobytes(), world
 
 
 def test_empty_inputs_and_limits():
