@@ -235,6 +235,8 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
     a.phase_cap = two_phase ? kPhaseCap : 0;
     static const bool no_slab = getenv("ICPB200_NO_SLAB") != nullptr;      // A/B switch: tile sweep for every decision
     a.brute_slab = (!grid && k.voxel_size > 0.0 && !no_slab) ? 1 : 0;
+    static const bool no_tma = getenv("ICPB200_NO_TMA") != nullptr;       // A/B switch (profiles/README.md)
+    a.tma_normals = no_tma ? 0 : 1;
     a.resume = 0;
     if (two_phase) {
         const size_t np_ = (size_t)n_pairs, cs_ = (size_t)a.cap_s;

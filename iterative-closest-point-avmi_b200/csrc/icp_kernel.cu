@@ -32,6 +32,8 @@
 //
 // All reductions are fp64, fixed-order (warp butterfly, then warps in order):
 // no atomics in any sum, so results are bitwise reproducible run to run.
+#include <stdlib.h>
+
 #include "icp_b200.h"
 #include "common.cuh"
 #include "icp_cta.cuh"
@@ -59,6 +61,8 @@ size_t icp_pair_smem_bytes(int dim, int cap_s, int cap_t, int nt) {
     b += sizeof(int) * (size_t)cap_s;                                  // match
     b += sizeof(float) * (1 + dim) * (size_t)cap_s;                    // d2lb, decision position (fp32, recentred)
     b += sizeof(unsigned short) * 3 * (size_t)cap_s;                   // todo, todo ordered by x, ambiguous
+    b = align16(b);
+    if (nt == 512 && dim == 2) b += sizeof(double) * 2 * (size_t)cap_t + 16;   // target normals, brought in by a TMA bulk copy
     return align16(b);
 }
 size_t icp_voxel_smem_bytes(int sort_pad) { return align16(sizeof(CtaShared)) + (size_t)sort_pad * 12; }
@@ -806,6 +810,30 @@ __device__ __forceinline__ void sweep3d(const float4* __restrict__ t32, int tile
     }
 }
 
+// ---- TMA bulk copy (cp.async.bulk) global -> shared with an mbarrier: sm_90+/sm_100 data movement, one thread issues ------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem), b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(src_gmem), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(b), "r"(parity) : "memory");
+}
+
 // Relative slack of an fp32 swept distance against the exact one.  dx = sx - tx, dx * dx and the fma each round once:
 // d^2 is off by at most 3 * 2^-24 = 1.8e-7 relative, the distance by 0.9e-7; the coordinates' own rounding is covered
 // separately by the absolute term 1.8e-7 * (|s| + |t|).  3e-7 leaves a factor three (it was 1e-6: far-away points,
@@ -827,6 +855,7 @@ struct Loop {
     unsigned short* todo2;   // the same points ordered by their current x (bins of the target's x range), for the slab sweep
     const unsigned short* list;   // what the sweeps read: todo or todo2
     unsigned short* amb;     // points whose fp32 ranking could not be separated: decided in fp64
+    const double2* nrm_s;    // 512-thread variant: the target's normals in shared memory (nullptr: read them through L2)
     int n_s, n_t, n_tiles;
     double c0, c1, c2;       // recentring offset
     float ta;                // sum over axes of max |target - centre|
@@ -1456,8 +1485,10 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
         L.cap = a.cap_s;
         L.todo = reinterpret_cast<unsigned short*>(q); q += sizeof(unsigned short) * (size_t)a.cap_s;
         L.todo2 = reinterpret_cast<unsigned short*>(q); q += sizeof(unsigned short) * (size_t)a.cap_s;
-        L.amb = reinterpret_cast<unsigned short*>(q);
+        L.amb = reinterpret_cast<unsigned short*>(q);       q += sizeof(unsigned short) * (size_t)a.cap_s;
         L.list = L.todo;
+        L.nrm_s = nullptr;
+        if (NT == 512 && DIM == 2 && !GRID) L.nrm_s = reinterpret_cast<const double2*>(smem + align16((size_t)(q - smem)));
     }
     double* tx = const_cast<double*>(L.tx);
     double* ty = const_cast<double*>(L.ty);
@@ -1468,6 +1499,12 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
     long long ph[6] = {0, 0, 0, 0, 0, 0}, ph_t = 0;
     unsigned long long ph_iters = 0;
 
+    __shared__ __align__(8) unsigned long long nrm_bar;      // completion of the normals' bulk copy (512-thread variant)
+    unsigned nrm_parity = 0;
+    if (NT == 512 && DIM == 2 && !GRID) {
+        if (tid == 0) mbar_init(&nrm_bar, 1);
+        __syncthreads();
+    }
     for (;;) {
         __syncthreads();
         // phase 1 takes pairs in order; phase 2 (a.resume) takes the pairs phase 1 handed over
@@ -1513,6 +1550,17 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
         const double* normals = a.t.nrm ? a.t.nrm + a.t.off[ct] * 2 : nullptr;
         const double* box = a.t.box + (size_t)ct * 6;
         const double tgt_xlo = box[0], tgt_xhi = box[3];
+        // 512-thread variant: the target's normals come into shared memory by one TMA bulk copy issued now and awaited in
+        // front of the first accumulation -- it lands under the staging of the clouds and the first nearest-neighbour sweep
+        const bool nrm_tma = NT == 512 && DIM == 2 && !GRID && normals != nullptr && a.method == ICPB200_POINT_TO_LINE && a.tma_normals;
+        bool nrm_pending = false;
+        if (nrm_tma) {
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the last pair's reads of this buffer are done
+                tma_bulk_g2s(const_cast<double2*>(L.nrm_s), normals, (unsigned)n_t * 16u, &nrm_bar);
+            }
+            nrm_pending = true;
+        }
         L.n_s = n_s; L.n_t = n_t; L.n_tiles = (n_t + 31) / 32;
         L.c0 = 0.5 * (box[0] + box[3]); L.c1 = 0.5 * (box[1] + box[4]); L.c2 = 0.5 * (box[2] + box[5]);
         L.tg = tgt_ds;
@@ -1721,6 +1769,7 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
 
             double rr[9], tt[3];
             if (p2l) {
+                if (nrm_pending) { mbar_wait(&nrm_bar, nrm_parity); nrm_parity ^= 1u; nrm_pending = false; }
                 // icp.py:88-104 on the inliers
                 double acc[10];
 #pragma unroll
@@ -1732,7 +1781,7 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
                     for (int u = 0; u < 4; ++u) {                     // the normals live in global memory (L2)
                         const int i = i0 + u * NT;
                         jj[u] = i < n_s ? m_idx<GRID>(L.match[i]) : 0;
-                        nn[u] = __ldg(reinterpret_cast<const double2*>(normals) + jj[u]);
+                        nn[u] = nrm_tma ? L.nrm_s[jj[u]] : __ldg(reinterpret_cast<const double2*>(normals) + jj[u]);
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
@@ -1878,6 +1927,7 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
             if (delta < a.err_thr) { status = ICPB200_CONVERGED; break; }   // icp.py:217-219
             prev = err;
         }
+        if (nrm_pending) { mbar_wait(&nrm_bar, nrm_parity); nrm_parity ^= 1u; }      // never used (no iteration ran): still drain it
         __syncthreads();
         if (tid == 0 && a.pair_prof) {
             st_amb += sh.amb_n;                    // (a break may leave the last iteration's count uncollected; profiling only)
@@ -2137,17 +2187,25 @@ int launch_icp_pairs(const IcpArgs& a, int dim, bool grid, int n_ctas, size_t sm
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         return n;
     }();
+    static const int roomy_nt = [] {                  // A/B switch (profiles/README.md): ICPB200_ROOMY_NT=256
+        const char* e = getenv("ICPB200_ROOMY_NT");
+        return e && atoi(e) == 256 ? 256 : kRoomyNT;
+    }();
     const bool roomy = a.resume || n_ctas <= sms;
-    const size_t smem = std::max(smem_min, icp_pair_smem_bytes(dim, a.cap_s, a.cap_t, roomy ? kRoomyNT : kNT));
+    const int nt = roomy ? roomy_nt : kNT;
+    const size_t smem = std::max(smem_min, icp_pair_smem_bytes(dim, a.cap_s, a.cap_t, nt));
     if (grid) {                                                                // grid mode is 2-D only
-        if (roomy) return launch_pairs_t<2, true, 1, kRoomyNT>(a, n_ctas, smem, stream);
+        if (roomy && nt == 512) return launch_pairs_t<2, true, 1, kRoomyNT>(a, n_ctas, smem, stream);
+        if (roomy) return launch_pairs_t<2, true, 1, kNT>(a, n_ctas, smem, stream);
         return launch_pairs_t<2, true, bulk_minb(2, true), kNT>(a, n_ctas, smem, stream);
     }
     if (dim == 2) {
-        if (roomy) return launch_pairs_t<2, false, 1, kRoomyNT>(a, n_ctas, smem, stream);
+        if (roomy && nt == 512) return launch_pairs_t<2, false, 1, kRoomyNT>(a, n_ctas, smem, stream);
+        if (roomy) return launch_pairs_t<2, false, 1, kNT>(a, n_ctas, smem, stream);
         return launch_pairs_t<2, false, bulk_minb(2, false), kNT>(a, n_ctas, smem, stream);
     }
-    if (roomy) return launch_pairs_t<3, false, 1, kRoomyNT>(a, n_ctas, smem, stream);
+    if (roomy && nt == 512) return launch_pairs_t<3, false, 1, kRoomyNT>(a, n_ctas, smem, stream);
+    if (roomy) return launch_pairs_t<3, false, 1, kNT>(a, n_ctas, smem, stream);
     return launch_pairs_t<3, false, bulk_minb(3, false), kNT>(a, n_ctas, smem, stream);
 }
 

@@ -55,6 +55,7 @@ struct IcpArgs {
     int max_iter;
     double voxel;
     int brute_slab;            // brute mode: sweep the voxel-ordered target outwards from the query (nn_slab)
+    int tma_normals;           // 512-thread variant: stage the target's normals in shared memory with a TMA bulk copy
     int method;
     int normal_k;
     double max_corr;           // < 0: no gate
