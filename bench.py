@@ -680,8 +680,13 @@ def bench_raycast(args, lib, api, dev, local_rank, pk, rank=0, world=1, verify=F
         grid._dev.update(origins, flat, off)
         if world > 1:
             icpd.grid_gather_device(grid._dev)
-        if rank == 0:                                   # one consumer reads the reassembled map
-            grid._dev.read(host_out)
+        if rank == 0:                                   # one consumer reads the map: one GPU -> only the tiles the scans touched
+            if world > 1:
+                grid._dev.read(host_out)                # (reassembled from every rank's bands: the whole map)
+            else:
+                if k == 0:
+                    host_out[...] = 0.0                 # the caller's mirror; untouched tiles are never written again
+                grid._dev.read_dirty(host_out)
         if k >= 1:
             e2e_t.append(time.perf_counter() - t0)
     e2e_s = float(np.mean(e2e_t))
@@ -722,7 +727,10 @@ def bench_raycast(args, lib, api, dev, local_rank, pk, rank=0, world=1, verify=F
                             sharding="bands of 64 rows dealt round-robin over the GPUs; every rank walks every ray clipped to its own bands, in scan order; one NCCL all_gather of the packed bands inside the timed region (update_only_ms = the slowest rank's update without it, gather_ms = the rest); e2e: one rank reads the reassembled map"),
                 e2e=dict(value=n_rays / e2e_s, unit="rays/s",
                          h2d_bytes_per_step=int(origins.nbytes + flat.nbytes + off.nbytes),
-                         d2h_bytes_per_step=int(host_out.nbytes), api="icpb200_grid_update + icpb200_grid_read"),
+                         d2h_bytes_per_step=int(host_out.nbytes if world > 1 else grid._dev.last_tiles_copied * 64 * 64 * 4),
+                         api="icpb200_grid_update + icpb200_grid_read" if world > 1 else
+                             "icpb200_grid_update + icpb200_grid_read_view(log-odds, touched tiles only) into the caller's mirror",
+                         tiles_copied=None if world > 1 else int(grid._dev.last_tiles_copied)),
                 gpu_launches=int(launches),
                 verify=checked,
                 roofline=dict(bound="hbm", achieved=alg_bytes / sec / 1e9 / world, peak=pk["hbm_gbs"], unit="GB/s",

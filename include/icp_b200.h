@@ -224,6 +224,21 @@ int icpb200_grid_rebuild(void *grid, int n_scans, const double *poses,
                          const double *local_pts, const int64_t *off);
 /* Copy the (ny, nx) float32 log-odds array, row major [iy][ix], to `out`. */
 int icpb200_grid_read(void *grid, float *out);
+/* Read-out with the display transforms of mapping.py:150-160 evaluated on the
+ * device, and -- with dirty_only != 0 -- only of the 64 x 64-cell tiles some
+ * update has touched since the last reset (a map is mostly unexplored: the
+ * copy shrinks from ny*nx*4 bytes to the explored part).
+ *   view 0  log-odds                       (mapping.py:47)
+ *   view 1  1 / (1 + exp(-log_odds))       (to_probability, mapping.py:150-153)
+ *   view 2  1 - p, unexplored 1, free 0.85 (to_display, mapping.py:155-160)
+ * float32 arithmetic throughout, as numpy evaluates it; the device exp differs
+ * from numpy's float32 exp by at most 2 ulp (views 1 and 2 agree to 1e-6).
+ * With dirty_only the cells of untouched tiles are NOT written: `out` must
+ * already hold the view of an untouched cell there (0, 0.5 or 1 -- a mirror the
+ * caller keeps between calls; in a grid shared out with
+ * icpb200_grid_set_shard only this rank's tiles count as touched).
+ * tiles_copied (may be NULL) receives the number of tiles that crossed PCIe. */
+int icpb200_grid_read_view(void *grid, int view, int dirty_only, float *out, int32_t *tiles_copied);
 /* mapping.py:143-145 */
 int icpb200_grid_reset(void *grid);
 /* Raw device pointer of the ny*nx float32 grid (for NCCL reductions issued by

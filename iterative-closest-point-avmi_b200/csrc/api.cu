@@ -922,7 +922,8 @@ int icpb200_rotation_scores(int n_problems, const double* src, const int64_t* sr
 void OccGrid::release_all() {
     DevBuf* bufs[] = {&grid, &origins, &hits, &hit_off, &local_pts, &poses, &in_pack, &origin_cell, &ray_cell, &ray_scan,
                       &counts, &offsets, &sums, &runs, &order, &small, &tile_prof,
-                      &slotmap, &slot_cell, &ord, &tile_count, &hit_off_shift, &items, &multi, &ncount, &ev, &ev_count, &class_off, &tile_flag};
+                      &slotmap, &slot_cell, &ord, &tile_count, &hit_off_shift, &items, &multi, &ncount, &ev, &ev_count, &class_off, &tile_flag,
+                      &dirty, &pack, &pack_ids};
     for (DevBuf* b : bufs) b->release();
     if (aux_stream) { cudaStreamDestroy(aux_stream); aux_stream = nullptr; }
     if (ev_fork) { cudaEventDestroy(ev_fork); ev_fork = nullptr; }
@@ -931,6 +932,7 @@ void OccGrid::release_all() {
     if (ev_stats) { cudaEventDestroy(ev_stats); ev_stats = nullptr; }
     if (pending_host) { cudaFreeHost(pending_host); pending_host = nullptr; }
     if (h_in_pack) { cudaFreeHost(h_in_pack); h_in_pack = nullptr; h_in_cap = 0; }
+    if (h_pack) { cudaFreeHost(h_pack); h_pack = nullptr; h_pack_cap = 0; }
     stats_pending = false;
 }
 
@@ -1042,6 +1044,8 @@ int icpb200_grid_rebuild(void* grid, int n_scans, const double* poses, const dou
     cudaStream_t st = g_ctx.stream;
     if ((rc = occ_collect(*g))) return rc;
     ICPB_CUDA(cudaMemsetAsync(g->grid.p, 0, sizeof(float) * (size_t)g->nx * g->ny, st));      // slam.py:273, mapping.py:143-145
+    if (g->dirty.p) ICPB_CUDA(cudaMemsetAsync(g->dirty.p, 0, g->dirty.cap, st));
+    g->all_dirty = false;
     g->seen_nonempty_scan = false;
     g->virgin_finalised = false;
     g->stats[0] = g->stats[1] = g->stats[2] = g->stats[3] = 0;
@@ -1115,10 +1119,25 @@ int icpb200_grid_reset(void* grid) {
     OccGrid* g = static_cast<OccGrid*>(grid);
     if ((rc = occ_collect(*g))) return rc;
     ICPB_CUDA(cudaMemsetAsync(g->grid.p, 0, sizeof(float) * (size_t)g->nx * g->ny, g_ctx.stream));   // mapping.py:143-145
+    if (g->dirty.p) ICPB_CUDA(cudaMemsetAsync(g->dirty.p, 0, g->dirty.cap, g_ctx.stream));
+    g->all_dirty = false;
     ICPB_CUDA(cudaStreamSynchronize(g_ctx.stream));
     g->seen_nonempty_scan = false;
     g->virgin_finalised = false;
     return ICPB200_OK;
+}
+
+int icpb200_grid_read_view(void* grid, int view, int dirty_only, float* out, int32_t* tiles_copied) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!grid || !out || view < 0 || view > 2) { set_error("icpb200_grid_read_view: null pointer or unknown view %d", view); return ICPB200_ERR_ARG; }
+    int rc = init_locked(-1);
+    if (rc) return rc;
+    OccGrid* g = static_cast<OccGrid*>(grid);
+    if ((rc = occ_collect(*g))) return rc;
+    int n = 0;
+    rc = occ_read_view(*g, out, view, dirty_only != 0, &n, g_ctx.stream);
+    if (tiles_copied) *tiles_copied = n;
+    return rc;
 }
 
 void* icpb200_grid_device_ptr(void* grid) {

@@ -595,6 +595,7 @@ int occ_transform_history(int n_scans, long long n_points, const double* d_poses
 
 int occ_update_device(OccGrid& g, int n_scans, const double* d_origins, const double* d_hits,
                       const long long* d_hit_off, const long long* h_hit_off, cudaStream_t st) {
+    if (!(g.use_fast && !g.zero_outside_clamp)) g.all_dirty = true;       // the ordered replay does not track touched tiles
     if (g.use_fast && !g.zero_outside_clamp) {
         const int rc = occ_update_fast(g, n_scans, d_origins, d_hits, d_hit_off, h_hit_off, h_hit_off[n_scans] - h_hit_off[0],
                                        false, st);

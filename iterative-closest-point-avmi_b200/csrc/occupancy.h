@@ -44,6 +44,11 @@ struct OccGrid {
     DevBuf counts, offsets, sums, runs, order, small, tile_prof;
     // order-free path (occupancy_fast.cu)
     DevBuf slotmap, slot_cell, ord, tile_count, hit_off_shift, items, multi, ncount, ev, ev_count, class_off, tile_flag;
+    // read-out: tiles (64 x 64 cells) touched since the last reset; the ordered path does not track them (all_dirty)
+    DevBuf dirty, pack, pack_ids;
+    bool all_dirty = false;
+    unsigned char* h_pack = nullptr;               // page-locked staging of the packed tiles
+    size_t h_pack_cap = 0;
     cudaStream_t aux_stream = nullptr;             // the hit cells' replay runs here, under the remaining tiles
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_hit = nullptr;
     // Deferred read-back of the device-resident entry point (occ_update_fast with defer = true): the statistics and
@@ -72,6 +77,9 @@ int occ_update_fast(OccGrid& g, int n_scans, const double* d_origins, const doub
                     cudaStream_t st);
 // Waits for a deferred read-back (if any); returns ICPB200_ERR_LIMIT when the update it belongs to overflowed.
 int occ_collect(OccGrid& g);
+// Read-out as log-odds (view 0), probability (1) or display value (2), mapping.py:150-160; dirty_only copies just the tiles
+// touched since the last reset (occupancy_fast.cu).
+int occ_read_view(OccGrid& g, float* out, int view, bool dirty_only, int* tiles_out, cudaStream_t st);
 // slam.py:46-50 for every scan of a history: world = local @ R.T + t, origin = t (device pointers)
 int occ_transform_history(int n_scans, long long n_points, const double* d_poses, const double* d_local,
                           const long long* d_off, double* d_world, double* d_origins, cudaStream_t st);

@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(1024) occ_tile_scan(const unsigned* __restrict
                                                       unsigned* __restrict__ offsets /* n_tiles + 1 */,
                                                       unsigned* __restrict__ class_off /* [tile][class] */,
                                                       const unsigned* __restrict__ tile_flag, uint2* __restrict__ items, int* __restrict__ multi,
-                                                      unsigned* __restrict__ small) {
+                                                      unsigned* __restrict__ small, unsigned char* __restrict__ dirty) {
     __shared__ unsigned wsum[32];
     __shared__ unsigned carry;
     __shared__ int hist[2][33], start[2][33];      // [0] tiles with hit cells, [1] the others
@@ -342,6 +342,7 @@ __global__ void __launch_bounds__(1024) occ_tile_scan(const unsigned* __restrict
         uint4 cc = make_uint4(0u, 0u, 0u, 0u), cd = cc;
         if (t < n_tiles) { cc = reinterpret_cast<const uint4*>(counts)[2 * t]; cd = reinterpret_cast<const uint4*>(counts)[2 * t + 1]; }
         const unsigned v = cc.x + cc.y + cc.z + cc.w + cd.x + cd.y + cd.z + cd.w;
+        if (t < n_tiles && (v || tile_flag[t])) dirty[t] = 1;       // touched since the last reset (icpb200_grid_read_view copies only these)
         if (v) atomicAdd(&hist[tile_flag[t] ? 0 : 1][32 - __clz(v)], (int)((v + kItemRuns - 1) / kItemRuns));
         unsigned inc = v;
 #pragma unroll
@@ -876,7 +877,7 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
     else occ_fast_rays<false, false, false><<<nblk, 256, 0, st>>>(a);
     ICPB_LAUNCH_CHECK();
     tm.mark("count");
-    occ_tile_scan<<<1, 1024, 0, st>>>(g.tile_count.as<unsigned>(), n_tiles, g.offsets.as<unsigned>(), g.class_off.as<unsigned>(), g.tile_flag.as<unsigned>(), g.items.as<uint2>(), g.multi.as<int>(), d_small);
+    occ_tile_scan<<<1, 1024, 0, st>>>(g.tile_count.as<unsigned>(), n_tiles, g.offsets.as<unsigned>(), g.class_off.as<unsigned>(), g.tile_flag.as<unsigned>(), g.items.as<uint2>(), g.multi.as<int>(), d_small, g.dirty.as<unsigned char>());
     ICPB_LAUNCH_CHECK();
     unsigned h_small[40];
     tm.mark("scan");
@@ -1021,6 +1022,92 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
     return ICPB200_OK;
 }
 
+// ---- read-out of the touched tiles only ---------------------------------------------------------------------------
+// A map is mostly unexplored (C4: 510 of the 4096 tiles carry anything): the tiles touched since the last reset are packed
+// into one block and only that block crosses PCIe.  view: 0 log-odds, 1 probability, 2 display value (mapping.py:150-160),
+// evaluated in float32 throughout as numpy does; expf differs from numpy's float32 exp by at most 2 ulp.
+__device__ __forceinline__ float occ_view(float lo, int view) {
+    if (view == 0) return lo;
+    const float p = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-lo)));              // mapping.py:153
+    if (view == 1) return p;
+    return lo == 0.0f ? 1.0f : (lo < 0.0f ? 0.85f : __fsub_rn(1.0f, p));       // mapping.py:157-159
+}
+
+__global__ void __launch_bounds__(256) occ_pack_tiles(const float* __restrict__ grid, int nx, int ny, int tiles_x,
+                                                      const int* __restrict__ ids, float* __restrict__ pack, int view) {
+    const int t = ids[blockIdx.x];
+    const int tx0 = (t % tiles_x) * TS, ty0 = (t / tiles_x) * TS;
+    float* out = pack + (size_t)blockIdx.x * TCELLS;
+    for (int c = threadIdx.x; c < TCELLS; c += 256) {
+        const int x = tx0 + (c & (TS - 1)), y = ty0 + c / TS;
+        out[c] = (x < nx && y < ny) ? occ_view(grid[(size_t)y * nx + x], view) : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256) occ_view_all(const float* __restrict__ grid, float* __restrict__ out, size_t n, int view) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = occ_view(grid[i], view);
+}
+
+static int ensure_host_stage(OccGrid& g, size_t bytes) {
+    if (bytes <= g.h_pack_cap) return ICPB200_OK;
+    if (g.h_pack) { cudaFreeHost(g.h_pack); g.h_pack = nullptr; g.h_pack_cap = 0; }
+    const size_t cap = bytes + bytes / 4 + 4096;
+    ICPB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g.h_pack), cap, cudaHostAllocDefault));
+    g.h_pack_cap = cap;
+    return ICPB200_OK;
+}
+
+// dirty_only: write only the tiles touched since the last reset into `out` (the caller's array already holds the view of
+// an untouched cell everywhere else); otherwise the whole map.  *tiles_out = tiles copied.
+int occ_read_view(OccGrid& g, float* out, int view, bool dirty_only, int* tiles_out, cudaStream_t st) {
+    const int tiles_x = (g.nx + TS - 1) / TS, tiles_y = (g.ny + TS - 1) / TS, n_tiles = tiles_x * tiles_y;
+    const size_t n_cells = (size_t)g.nx * g.ny;
+    if (tiles_out) *tiles_out = n_tiles;
+    if (!dirty_only || g.all_dirty || !g.dirty.p) {
+        if (dirty_only && !g.all_dirty && !g.dirty.p) { if (tiles_out) *tiles_out = 0; return ICPB200_OK; }   // never updated
+        if (view == 0) {
+            ICPB_CUDA(cudaMemcpyAsync(out, g.grid.p, sizeof(float) * n_cells, cudaMemcpyDeviceToHost, st));
+        } else {
+            if (g.pack.reserve(sizeof(float) * n_cells)) return ICPB200_ERR_CUDA;
+            occ_view_all<<<2048, 256, 0, st>>>(g.grid.as<float>(), g.pack.as<float>(), n_cells, view);
+            ICPB_LAUNCH_CHECK();
+            ICPB_CUDA(cudaMemcpyAsync(out, g.pack.p, sizeof(float) * n_cells, cudaMemcpyDeviceToHost, st));
+        }
+        ICPB_CUDA(cudaStreamSynchronize(st));
+        return ICPB200_OK;
+    }
+    int rc = ensure_host_stage(g, (size_t)n_tiles * (1 + sizeof(int)));
+    if (rc) return rc;
+    unsigned char* h_dirty = g.h_pack;
+    ICPB_CUDA(cudaMemcpyAsync(h_dirty, g.dirty.p, (size_t)n_tiles, cudaMemcpyDeviceToHost, st));
+    ICPB_CUDA(cudaStreamSynchronize(st));
+    std::vector<int> ids;
+    ids.reserve(1024);
+    for (int t = 0; t < n_tiles; ++t) if (h_dirty[t]) ids.push_back(t);
+    const size_t n = ids.size();
+    if (tiles_out) *tiles_out = (int)n;
+    if (n == 0) return ICPB200_OK;
+    const size_t b_pack = sizeof(float) * TCELLS * n;
+    if (g.pack.reserve(b_pack) || g.pack_ids.reserve(sizeof(int) * (size_t)n_tiles)) return ICPB200_ERR_CUDA;
+    if ((rc = ensure_host_stage(g, b_pack + sizeof(int) * n))) return rc;
+    int* h_ids = reinterpret_cast<int*>(g.h_pack + b_pack);
+    memcpy(h_ids, ids.data(), sizeof(int) * n);
+    ICPB_CUDA(cudaMemcpyAsync(g.pack_ids.p, h_ids, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    occ_pack_tiles<<<(unsigned)n, 256, 0, st>>>(g.grid.as<float>(), g.nx, g.ny, tiles_x, g.pack_ids.as<int>(), g.pack.as<float>(), view);
+    ICPB_LAUNCH_CHECK();
+    ICPB_CUDA(cudaMemcpyAsync(g.h_pack, g.pack.p, b_pack, cudaMemcpyDeviceToHost, st));
+    ICPB_CUDA(cudaStreamSynchronize(st));
+    const float* src = reinterpret_cast<const float*>(g.h_pack);
+    for (size_t k = 0; k < n; ++k) {
+        const int t = ids[k], tx0 = (t % tiles_x) * TS, ty0 = (t / tiles_x) * TS;
+        const int w = std::min(TS, g.nx - tx0), hgt = std::min(TS, g.ny - ty0);
+        for (int r = 0; r < hgt; ++r)
+            memcpy(out + (size_t)(ty0 + r) * g.nx + tx0, src + k * TCELLS + (size_t)r * TS, sizeof(float) * (size_t)w);
+    }
+    return ICPB200_OK;
+}
+
 int occ_fast_ctas(int sm_count) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, occ_fast_tiles, kTileNT, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
@@ -1068,6 +1155,10 @@ int occ_update_fast(OccGrid& g, int n_scans, const double* d_origins, const doub
         if (g.ncount.reserve(sizeof(unsigned) * n_cells)) return ICPB200_ERR_CUDA;
         ICPB_CUDA(cudaMemsetAsync(g.ncount.p, 0, sizeof(unsigned) * n_cells, st));
     }
+    if (!g.dirty.p) {
+        if (g.dirty.reserve((size_t)n_tiles)) return ICPB200_ERR_CUDA;
+        ICPB_CUDA(cudaMemsetAsync(g.dirty.p, 0, (size_t)n_tiles, st));
+    }
     if (defer && !g.pending_host) {
         ICPB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g.pending_host), 256, cudaHostAllocDefault));
         ICPB_CUDA(cudaEventCreateWithFlags(&g.ev_stats, cudaEventDisableTiming));
@@ -1097,6 +1188,7 @@ int occ_update_fast(OccGrid& g, int n_scans, const double* d_origins, const doub
         }
         if (rc == 1) {
             all_fast = false;
+            g.all_dirty = true;
             if (!h_hit_off) {                                              // single chunk, offsets checked on the device
                 fetched.resize((size_t)n_scans + 1);
                 ICPB_CUDA(cudaMemcpyAsync(fetched.data(), d_hit_off, sizeof(long long) * fetched.size(), cudaMemcpyDeviceToHost, st));

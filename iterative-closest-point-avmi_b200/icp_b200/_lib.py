@@ -57,6 +57,7 @@ PROTOTYPES = {
     "icpb200_grid_update_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                                ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "icpb200_grid_read": (ctypes.c_int, [ctypes.c_void_p, c_float_p]),
+    "icpb200_grid_read_view": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_float_p, c_int32_p]),
     "icpb200_grid_reset": (ctypes.c_int, [ctypes.c_void_p]),
     "icpb200_grid_rebuild": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_double_p, c_double_p, c_int64_p]),
     "icpb200_grid_device_ptr": (ctypes.c_void_p, [ctypes.c_void_p]),

@@ -226,6 +226,8 @@ class DeviceGrid:
 
     def __init__(self, nx, ny, min_x, min_y, resolution, l_hit, l_miss, lo_min, lo_max):
         self.nx, self.ny = int(nx), int(ny)
+        self.sharded = False
+        self.last_tiles_copied = 0
         self._lib = _lib.load()
         self._h = self._lib.icpb200_grid_create(self.nx, self.ny, float(min_x), float(min_y), float(resolution),
                                                 float(l_hit), float(l_miss), float(lo_min), float(lo_max))
@@ -244,6 +246,7 @@ class DeviceGrid:
             pass
 
     def set_shard(self, rank, world):
+        self.sharded = int(world) > 1
         check(self._lib.icpb200_grid_set_shard(self._h, int(rank), int(world)), "icpb200_grid_set_shard")
 
     def update(self, origins, hits, hit_off):
@@ -272,6 +275,24 @@ class DeviceGrid:
             out = np.empty((self.ny, self.nx), dtype=np.float32)
         check(self._lib.icpb200_grid_read(self._h, _ptr(out, c_float_p)), "icpb200_grid_read")
         return out
+
+    VIEWS = {"log_odds": 0, "probability": 1, "display": 2}
+    UNTOUCHED = {"log_odds": 0.0, "probability": 0.5, "display": 1.0}      # the view of an unexplored cell
+
+    def read_view(self, view="log_odds", out=None, dirty_only=False):
+        """(ny, nx) float32 view of the map computed on the device (mapping.py:150-160).  With ``dirty_only`` only the
+        tiles touched since the last reset are copied into ``out``, which must hold ``UNTOUCHED[view]`` elsewhere."""
+        if out is None:
+            out = np.full((self.ny, self.nx), self.UNTOUCHED[view], dtype=np.float32)
+        n = ctypes.c_int32(0)
+        check(self._lib.icpb200_grid_read_view(self._h, self.VIEWS[view], 1 if dirty_only else 0, _ptr(out, c_float_p),
+                                               ctypes.byref(n)), "icpb200_grid_read_view")
+        self.last_tiles_copied = int(n.value)
+        return out
+
+    def read_dirty(self, out):
+        """Log-odds of the touched tiles into ``out`` (zeros elsewhere, kept by the caller)."""
+        return self.read_view("log_odds", out, dirty_only=True)
 
     def reset(self):
         check(self._lib.icpb200_grid_reset(self._h), "icpb200_grid_reset")

@@ -41,19 +41,35 @@ class OccupancyGrid2D:
         self.log_odds_max = float(log_odds_max)
         self._dev = _api.DeviceGrid(self.nx, self.ny, self.min_x, self.min_y, self.resolution,
                                     self.l_hit, self.l_miss, self.log_odds_min, self.log_odds_max)
-        self._host = None
-        self._mirror = None               # page-locked host copy, reused by every read-back
-        self._mirror_pin = None
+        self._views = {}                  # view name -> page-locked host mirror + its state
 
     # ---- device <-> host -------------------------------------------------
+    # One page-locked mirror per view (log-odds, probability, display value), kept between calls: a read-back copies only
+    # the 64 x 64-cell tiles some update has touched since the last reset() -- a map is mostly unexplored -- and everything
+    # else already holds the value of an untouched cell.
+    def _read(self, view):
+        entry = self._views.get(view)
+        fill = _api.DeviceGrid.UNTOUCHED[view]
+        if entry is None:
+            arr = np.full((self.ny, self.nx), fill, dtype=np.float32)
+            entry = dict(arr=arr, valid=False, refill=False, pin=_api.pinned(arr))
+            self._views[view] = entry
+        if not entry["valid"]:
+            if entry["refill"]:                       # a reset un-touched tiles this mirror still shows
+                entry["arr"][...] = fill
+                entry["refill"] = False
+            self._dev.read_view(view, entry["arr"], dirty_only=not self._dev.sharded)
+            entry["valid"] = True
+        return entry["arr"]
+
+    def _invalidate(self, reset=False):
+        for entry in self._views.values():
+            entry["valid"] = False
+            entry["refill"] = entry["refill"] or reset
+
     @property
     def log_odds(self):
-        if self._host is None:
-            if self._mirror is None:
-                self._mirror = np.empty((self.ny, self.nx), dtype=np.float32)
-                self._mirror_pin = _api.pinned(self._mirror)
-            self._host = self._dev.read(self._mirror)
-        return self._host
+        return self._read("log_odds")
 
     # ---- update ----------------------------------------------------------
     def update_scan(self, origin_xy, hit_points):
@@ -63,14 +79,14 @@ class OccupancyGrid2D:
             return
         org = np.ascontiguousarray(origin_xy, dtype=np.float64).reshape(1, 2)
         self._dev.update(org, pts.reshape(-1, 2), np.array([0, pts.shape[0]], dtype=np.int64))
-        self._host = None
+        self._invalidate()
 
     def update_scans(self, origins, hit_clouds):
         """Batch form (the _rebuild_map replay, slam.py:271-277): scans applied in order."""
         from icp_b200.synth import pack_ragged
         flat, off = pack_ragged([np.asarray(h, dtype=np.float64).reshape(-1, 2) for h in hit_clouds])
         self._dev.update(np.asarray(origins, dtype=np.float64), flat, off)
-        self._host = None
+        self._invalidate()
 
     def rebuild(self, scan_history):
         """The reference's `_rebuild_map(mapper, scan_history)` (slam.py:271-277) as one device call: clear the grid and
@@ -85,23 +101,22 @@ class OccupancyGrid2D:
             return
         flat, off = pack_ragged(scans)
         self._dev.rebuild(poses, flat, off)
-        self._host = None
+        self._invalidate(reset=True)
 
     def reset(self):
         """Back to unexplored (all zeros)."""
         self._dev.reset()
-        self._host = None
+        self._invalidate(reset=True)
 
     # ---- probability / display ---------------------------------------------
     def to_probability(self):
-        return 1.0 / (1.0 + np.exp(-self.log_odds))
+        """mapping.py:150-153 evaluated on the device in float32, as numpy evaluates it (the device exp differs from
+        numpy's float32 exp by at most 2 ulp: values agree to 1e-6).  A fresh array, as the reference returns."""
+        return self._read("probability").copy()
 
     def to_display(self):
-        lo = self.log_odds
-        shown = 1.0 - self.to_probability()
-        shown[lo == 0.0] = 1.0        # unexplored -> white
-        shown[lo < 0.0] = 0.85        # free -> light grey
-        return shown
+        """mapping.py:155-160 on the device: occupied 1 - p, unexplored 1 (white), free 0.85 (light grey)."""
+        return self._read("display").copy()
 
     def _flat_cell_data(self):
         return self.to_display().ravel(order="C")

@@ -31,7 +31,7 @@ d_org, d_hits, d_off = (torch.from_numpy(np.ascontiguousarray(x)).cuda() for x i
 torch.cuda.synchronize()
 for _ in range(2):
     g._dev.update_dev(len(off) - 1, d_org.data_ptr(), d_hits.data_ptr(), d_off.data_ptr(), int(off[-1]), 0)
-g._host = None
+g._invalidate()
 st = g._dev.last_stats()
 # pairs out of order through the host-buffer entry point (pair grouping by upload chunk)
 cl, co = synth.pack_ragged(list(scans))

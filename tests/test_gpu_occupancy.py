@@ -1,6 +1,8 @@
 """GPU parity: occupancy raycast through the C ABI vs the oracle / golden
 fixtures.  Bar: bit-exact float32 log-odds (north_star: Bresenham cell sets
 bit-exact, log-odds within 1e-9 abs -- i.e. identical float32 values)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -264,7 +266,7 @@ def test_device_resident_entry_point_is_stream_ordered_and_reports_late():
 
     class _Dev:                                       # the shim caches its host mirror: drop it after every device update
         def update_dev(self, *a):
-            gpu._host = None
+            gpu._invalidate()
             gpu._dev.update_dev(*a)
     dev_entry = _Dev()
     for rep in range(2):                              # the second call takes the speculative fill (buffers already sized)
@@ -338,3 +340,49 @@ def test_rebuild_map_in_one_call_matches_the_reference_and_the_oracle():
     gpu.rebuild(history)
     oo.rebuild_map(ref, history)
     assert_same(gpu, ref, "150-scan rebuild")
+
+
+def test_device_views_and_touched_tile_read_out():
+    """mapping.py:150-160 on the device and the read-out of touched tiles only: log-odds bit-exact (through the shim's
+    persistent mirror, across updates, a reset and a rebuild), probability / display within 1e-6 of numpy's float32
+    evaluation, and far fewer tiles copied than the grid has."""
+    scans, poses = synth.make_sequence(30, world="room", seed=9)
+    hits = [synth.to_world_frame(s, p) for s, p in zip(scans, poses)]
+    bounds = (-51.2, 51.2, -51.2, 51.2)                       # 2048 x 2048 cells, the room covers a corner of it
+    gpu, ref = make_pair(bounds, **GKW)
+    for k in range(10):
+        gpu.update_scan(poses[k, :2], hits[k]); ref.update_scan(poses[k, :2], hits[k])
+    assert_same(gpu, ref, "first read (mirror created)")
+    tiles_total = ((gpu.nx + 63) // 64) * ((gpu.ny + 63) // 64)
+    if os.environ.get("ICPB200_OCC_PATH") != "ordered":      # (the ordered replay does not track touched tiles: it reads everything)
+        assert 0 < gpu._dev.last_tiles_copied < tiles_total // 2, gpu._dev.last_tiles_copied
+    for k in range(10, 20):
+        gpu.update_scan(poses[k, :2], hits[k]); ref.update_scan(poses[k, :2], hits[k])
+    assert_same(gpu, ref, "second read (same mirror)")
+    lo = ref.log_odds
+    want_p = 1.0 / (1.0 + np.exp(-lo))                       # float32, as the reference computes it
+    got_p = gpu.to_probability()
+    assert got_p.dtype == np.float32 and got_p.shape == lo.shape and np.abs(got_p - want_p).max() < 1e-6
+    want_d = 1.0 - want_p
+    want_d[lo == 0.0] = 1.0
+    want_d[lo < 0.0] = 0.85
+    got_d = gpu.to_display()
+    assert got_d.dtype == np.float32 and np.abs(got_d - want_d).max() < 1e-6
+    assert np.array_equal(got_d == 1.0, want_d == 1.0) and np.array_equal(got_d == np.float32(0.85), want_d == np.float32(0.85))
+    got_d[:] = 7.0                                            # a caller may scribble on what it got (the reference returns a new array)
+    assert np.abs(gpu.to_display() - want_d).max() < 1e-6
+    # whole-map read-out of the views equals the touched-tile one
+    full = gpu._dev.read_view("probability")
+    assert np.array_equal(full, gpu.to_probability())
+    # reset: tiles that were touched must read as unexplored again, in every mirror
+    gpu.reset(); ref.reset()
+    gpu.update_scan(poses[25, :2] + 30.0, hits[25] + 30.0); ref.update_scan(poses[25, :2] + 30.0, hits[25] + 30.0)
+    assert_same(gpu, ref, "after reset")
+    assert np.abs(gpu.to_probability() - 1.0 / (1.0 + np.exp(-ref.log_odds))).max() < 1e-6
+    # rebuild (slam.py:271-277) clears the touched set as well
+    from oracle import occupancy_oracle
+    mats = [np.array([[np.cos(t), -np.sin(t), x], [np.sin(t), np.cos(t), y], [0.0, 0.0, 1.0]]) for x, y, t in poses[:6]]
+    history = [(scans[k], mats[k]) for k in range(6)]
+    gpu.rebuild(history)
+    occupancy_oracle.rebuild_map(ref, history)
+    assert_same(gpu, ref, "after rebuild")
