@@ -740,6 +740,51 @@ def bench_raycast(args, lib, api, dev, local_rank, pk, rank=0, world=1, verify=F
                 cpu_baseline=cpu, clocks=clk.summary())
 
 
+def c3_roofline(ks, ex, n_target_raw):
+    """SURVEY 8(d) grid-NN roofline: bytes per query = 8 (query xy) + 9 x 8 (cell ranges of the 3 x 3 block) + 8 x P
+    (candidate coordinates; P measured: target points evaluated per query) + 4 (index out); one grid build pass per
+    registration call, M_t x (8 read + 8 write + 4 key).  Against the measured HBM copy bandwidth; the 0.75 MB target
+    is L2-resident, so this is an L2-side figure (lts__t_bytes in profiles/)."""
+    pk = peaks()
+    q = max(ex["grid_queries"], 1)
+    p_mean = ex["grid_candidates"] / q
+    cells = ex["grid_cells"] / q
+    bytes_nn = q * (8.0 + 9 * 8.0 + 16.0 * p_mean + 4.0)         # fp64 xy per candidate here (16 B, not the survey's float2)
+    bytes_build = n_target_raw * 20.0
+    t = max(ks["pair_kernel_ns"], 1) / 1e9
+    return dict(bound="hbm", achieved=bytes_nn / t / 1e9, peak=pk["hbm_gbs"], unit="GB/s", frac=bytes_nn / t / 1e9 / pk["hbm_gbs"],
+                traffic=ncu_traffic("icp_pairs_kernel_grid")[0], traffic_source=ncu_traffic("icp_pairs_kernel_grid")[1],
+                kernel="icp_pairs_kernel<2, grid> (64 pairs, one CTA each)", queries=int(q), candidates_per_query=p_mean,
+                cells_visited_per_query=cells, algorithmic_bytes=bytes_nn, grid_build_bytes=bytes_build,
+                grid_build_ms=ks["normals_kernel_ns"] / 1e6, voxel_ms=ks["voxel_kernel_ns"] / 1e6,
+                note="64 CTAs on 148 SMs, each a dependent chain of ~20 iterations: latency-bound, far below the memory "
+                     "roofline; carried-over correspondences (most queries after the first iterations) issue no grid query")
+
+
+def build_c3(n_sources=64):
+    """C3 inputs (BASELINE.json configs[2]): one ~52k-point submap and n_sources 1080-point scans cut out of it, each with
+    an initial guess perturbed by (+0.05 m, -0.04 m, +0.01 rad)."""
+    from icp_b200 import synth
+    target = synth.submap_cloud(n_raw=52000, seed=3)
+    rng = np.random.default_rng(103)
+    clouds, R0, t0s = [target], [], []
+    while len(clouds) < 1 + n_sources:
+        c = target[rng.integers(len(target))]
+        near = target[np.hypot(*(target - c).T) < 12.0]
+        if len(near) < 1500:
+            continue
+        pts = near[rng.choice(len(near), 1080, replace=False)] + rng.normal(0, 0.01, size=(1080, 2))
+        th = rng.uniform(-0.3, 0.3)
+        rot = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        shift = rng.uniform(-5, 5, size=2)
+        clouds.append((pts - shift) @ rot)
+        a = th + 0.01
+        R0.append([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+        t0s.append(shift + [0.05, -0.04])
+    flat, off = synth.pack_ragged(clouds)
+    return target, flat, off, R0, t0s
+
+
 def bench_extras(args, api):
     """Smaller configs of BASELINE.json on one GPU (rank 0): C1 teapot, C3 scan -> 50k submap."""
     out = {}
@@ -769,25 +814,8 @@ def bench_extras(args, api):
                                        batch_pairs=n, batch_e2e_registrations_per_s=n / dt,
                                        batch_mean_iters=float(res["iters"].mean()))
     # C3: scans against one ~47k-voxel submap, p2p + max_corr_dist (slam.py:217-225)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
     from icp_b200 import synth
-    target = synth.submap_cloud(n_raw=52000, seed=3)
-    rng = np.random.default_rng(103)
-    clouds, R0, t0s = [target], [], []
-    while len(clouds) < 1 + 64:
-        c = target[rng.integers(len(target))]
-        near = target[np.hypot(*(target - c).T) < 12.0]
-        if len(near) < 1500:
-            continue
-        pts = near[rng.choice(len(near), 1080, replace=False)] + rng.normal(0, 0.01, size=(1080, 2))
-        th = rng.uniform(-0.3, 0.3)
-        rot = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
-        shift = rng.uniform(-5, 5, size=2)
-        clouds.append((pts - shift) @ rot)
-        a = th + 0.01
-        R0.append([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
-        t0s.append(shift + [0.05, -0.04])
-    flat, off = synth.pack_ragged(clouds)
+    target, flat, off, R0, t0s = build_c3()
     kw = dict(error_threshold=1e-10, max_iterations=150, voxel_size=0.04, method="point_to_point", max_corr_dist=1.5,
               R_init=np.asarray(R0), t_init=np.asarray(t0s))
     si, ti = np.arange(1, 65, dtype=np.int32), np.zeros(64, dtype=np.int32)
@@ -796,6 +824,7 @@ def bench_extras(args, api):
     res = api.icp_pairs(flat, off, si, ti, **kw)
     dt = time.perf_counter() - t0
     ks = api.icp_last_stats()
+    ex = api.icp_extra_stats()
     one_t = time.perf_counter()
     api.icp_pairs(flat, off, si[:1], ti[:1], error_threshold=1e-10, max_iterations=150, voxel_size=0.04,
                   method="point_to_point", max_corr_dist=1.5, R_init=np.asarray(R0)[:1], t_init=np.asarray(t0s)[:1])
@@ -804,6 +833,7 @@ def bench_extras(args, api):
                                     single_call_ms=one_t * 1e3, mean_iters=float(res["iters"].mean()),
                                     voxel_kernel_ms=ks["voxel_kernel_ns"] / 1e6, grid_kernel_ms=ks["normals_kernel_ns"] / 1e6,
                                     pair_kernel_ms=ks["pair_kernel_ns"] / 1e6,
+                                    roofline=c3_roofline(ks, ex, len(target)),
                                     note="the 52k-point target is re-downsampled and re-gridded inside every call, "
                                          "as ICP() does (icp.py:150-151)")
     # F3: _rebuild_map (slam.py:271-277) -- the C4 scans in their local frames + poses, one call

@@ -167,6 +167,12 @@ int icpb200_icp_last_stats(int64_t *stats8);
  * call; out8[5] is the number of such iterations. */
 int icpb200_icp_phase_profile(int64_t *out8);
 
+/* More counters of the most recent registration call: out8[0] iterations
+ * decided against the far-field front set (a diverged source), out8[1..3] grid
+ * mode: nearest-neighbour queries, target points evaluated, grid cells
+ * visited (bench.py: bytes per query of the hash-grid roofline). */
+int icpb200_icp_extra_stats(int64_t *out8);
+
 /* Profiling aid: the first call switches per-pair counters on; after the next
  * registration call, a call with a buffer of 4*cap_pairs int64 receives, per
  * pair of that call, {SM cycles spent on the pair (both launches), source

@@ -227,7 +227,7 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
         set_error("icp: %zu bytes of shared memory needed, device allows %d", smem, c.max_smem_optin);
         return ICPB200_ERR_LIMIT;
     }
-    if (c.queue.reserve(16 * sizeof(unsigned)) || c.stats.reserve(16 * sizeof(unsigned long long))) return ICPB200_ERR_CUDA;
+    if (c.queue.reserve(16 * sizeof(unsigned)) || c.stats.reserve(24 * sizeof(unsigned long long))) return ICPB200_ERR_CUDA;
     a.queue = c.queue.as<unsigned>();
     // two-phase schedule (see icp_kernel.h): worthwhile once the batch fills the machine
     const int kPhaseCap = 12;                                    // flat between 8 and 16 on C2 (profiles/README.md)
@@ -264,7 +264,7 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
         c.pair_prof_n = n_pairs;
     }
     ICPB_CUDA(cudaMemsetAsync(a.queue, 0, 16 * sizeof(unsigned), st));
-    ICPB_CUDA(cudaMemsetAsync(a.stats, 0, 16 * sizeof(unsigned long long), st));
+    ICPB_CUDA(cudaMemsetAsync(a.stats, 0, 24 * sizeof(unsigned long long), st));
     ICPB_CUDA(cudaMemsetAsync(a.s.used, 0, 2 * (size_t)s.n_clouds, st));
     if (!same_set) ICPB_CUDA(cudaMemsetAsync(a.t.used, 0, 2 * (size_t)t.n_clouds, st));
     a.grids = nullptr;
@@ -783,6 +783,23 @@ int icpb200_icp_phase_profile(int64_t* out8) {
     cudaStream_t st = c.last_icp_stream ? c.last_icp_stream : c.stream;
     ICPB_CUDA(cudaMemcpyAsync(out8, c.stats.as<int64_t>() + 8, 8 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     ICPB_CUDA(cudaStreamSynchronize(st));
+    return ICPB200_OK;
+}
+
+int icpb200_icp_extra_stats(int64_t* out8) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!out8) { set_error("icpb200_icp_extra_stats: null pointer"); return ICPB200_ERR_ARG; }
+    int rc = init_locked(-1);
+    if (rc) return rc;
+    Context& c = g_ctx;
+    for (int i = 0; i < 8; ++i) out8[i] = 0;
+    if (!c.stats.p || c.stats.cap < 24 * sizeof(unsigned long long)) return ICPB200_OK;
+    cudaStream_t st = c.last_icp_stream ? c.last_icp_stream : c.stream;
+    int64_t h[10];
+    ICPB_CUDA(cudaMemcpyAsync(h, c.stats.as<int64_t>() + 14, sizeof(h), cudaMemcpyDeviceToHost, st));
+    ICPB_CUDA(cudaStreamSynchronize(st));
+    out8[0] = h[0];                                // far-field iterations
+    out8[1] = h[2]; out8[2] = h[3]; out8[3] = h[4];   // grid mode: queries, candidates evaluated, cells visited
     return ICPB200_OK;
 }
 

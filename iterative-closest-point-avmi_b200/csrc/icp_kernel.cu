@@ -1403,7 +1403,7 @@ __device__ __forceinline__ void order_todo_by_x(Loop<DIM>& L, SH& sh, int n_todo
 constexpr int kGridMaxRing = 24;
 
 template <int DIM, int NT>
-__device__ __forceinline__ void grid_nn(const Loop<DIM>& L, int n_todo) {
+__device__ __forceinline__ void grid_nn(const Loop<DIM>& L, int n_todo, unsigned long long (&gst)[3]) {
     const BigGrid& G = L.grid;
     for (int q = threadIdx.x; q < n_todo; q += NT) {
         const int i = L.todo[q];
@@ -1425,10 +1425,12 @@ __device__ __forceinline__ void grid_nn(const Loop<DIM>& L, int n_todo) {
                     if (x < 0 || x >= G.nx) continue;
                     const unsigned b = big_cell_hash(x, y) & G.mask;
                     const int beg = b ? G.start[b - 1] : 0, end = G.start[b];
+                    ++gst[2];
                     for (int e = beg; e < end; ++e) {
                         const int2 cc = G.cell[e];
                         if (cc.x != x || cc.y != y) continue;          // another cell hashed to this bucket
                         const int j = G.items[e];
+                        ++gst[1];
                         const double d = dist2_64<DIM, true>(L, px, py, 0.0, j);
                         if (d < best || (d == best && j < bj)) { second = best; best = d; bj = j; }
                         else if (d < second) second = d;
@@ -1455,6 +1457,7 @@ __device__ __forceinline__ void grid_nn(const Loop<DIM>& L, int n_todo) {
         L.match[i] = bj;
         L.d2lb[i] = f32_down(fmin(sqrt(second), bound) * (1.0 - 1e-12));
         stamp_p0<DIM>(L, i);
+        ++gst[0];
     }
 }
 
@@ -1498,6 +1501,7 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
     // thread 0's cycles per phase over iterations >= 8 (the nearly-converged regime): profiling aid
     long long ph[6] = {0, 0, 0, 0, 0, 0}, ph_t = 0;
     unsigned long long ph_iters = 0;
+    unsigned long long gst[3] = {0, 0, 0};         // grid mode, per thread: queries, candidates evaluated, cells visited
 
     __shared__ __align__(8) unsigned long long nrm_bar;      // completion of the normals' bulk copy (512-thread variant)
     unsigned nrm_parity = 0;
@@ -1733,7 +1737,7 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
             bool use_slab = false;
             if (n_todo > 0) {
                 if (GRID) {
-                    grid_nn<DIM, NT>(L, n_todo);
+                    grid_nn<DIM, NT>(L, n_todo, gst);
                 } else {
                     // The slab sweep prunes by x alone: when the points sit metres from the target (a pair that does not
                     // align) its walks cover most of the target, one candidate block after the other, and the register-
@@ -1945,6 +1949,15 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
             if (a.prev_out) a.prev_out[p] = prev;
             a.iters_out[p] = iters;
             a.status_out[p] = status;
+        }
+    }
+    if (GRID && a.stats) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            unsigned long long v = gst[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((tid & 31) == 0 && v) atomicAdd(&a.stats[16 + k], v);
         }
     }
     if (tid == 0 && a.stats) {

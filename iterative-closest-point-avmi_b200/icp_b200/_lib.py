@@ -48,6 +48,7 @@ PROTOTYPES = {
     "icpb200_icp_last_stats": (ctypes.c_int, [c_int64_p]),
     "icpb200_icp_phase_profile": (ctypes.c_int, [c_int64_p]),
     "icpb200_icp_pair_profile": (ctypes.c_int, [c_int64_p, ctypes.c_int64]),
+    "icpb200_icp_extra_stats": (ctypes.c_int, [c_int64_p]),
     "icpb200_voxel_downsample": (ctypes.c_int, [c_double_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double,
                                                 c_double_p, c_int64_p]),
     "icpb200_grid_create": (ctypes.c_void_p, [ctypes.c_int, ctypes.c_int] + [ctypes.c_double] * 7),

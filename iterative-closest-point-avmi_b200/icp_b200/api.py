@@ -139,6 +139,12 @@ def icp_phase_profile():
     return dict(phases=phases, iterations_profiled=int(st[5]), cycles_per_iteration=float(sum(phases.values())) if st[5] else 0.0)
 
 
+def icp_extra_stats():
+    st = np.zeros(8, dtype=np.int64)
+    check(_lib.load().icpb200_icp_extra_stats(_ptr(st, c_int64_p)), "icpb200_icp_extra_stats")
+    return dict(far_field_iterations=int(st[0]), grid_queries=int(st[1]), grid_candidates=int(st[2]), grid_cells=int(st[3]))
+
+
 def icp_pair_profile(n_pairs=0):
     """Per-pair counters of the last registration call: (n, 4) int64 = cycles, points swept, fp64 fallbacks, iterations.
     The first call only switches the counters on (returns an empty array)."""
