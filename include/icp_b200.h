@@ -49,7 +49,8 @@ extern "C" {
 #define ICPB200_CONVERGED     0   /* |prev_error - error| < error_threshold   (icp.py:216-219) */
 #define ICPB200_MAX_ITER      1   /* loop exhausted                           (icp.py:222-223) */
 #define ICPB200_FEW_INLIERS   2   /* inliers < max(3, N/10): loop left early  (icp.py:186-187) */
-#define ICPB200_BAD_VOXELS    3   /* voxel index range does not fit 62 bits; pair not processed */
+#define ICPB200_BAD_VOXELS    3   /* pair not processed: voxel index range beyond 62 bits, or (device-resident
+                                     entry point) a cloud index outside the set */
 
 /* method (icp.py:133, 162) */
 #define ICPB200_POINT_TO_POINT 0
@@ -272,7 +273,8 @@ int icpb200_grid_tile_profile(void *grid, int64_t *out, int64_t cap_tiles);
  * (2 doubles) per problem; scores_out receives one value per angle in the order given.  With
  * nn_dist_out / nn_idx_out (both or neither; exactly one angle per problem) the exact nearest target
  * index and distance of every source point are returned as tgt_tree.query would (slam.py:168).
- * Limits: 2-D, targets <= 8192 points (they live in shared memory). */
+ * 2-D.  Targets of more than 8192 points are swept in slices of 8192 (one launch
+ * each; the running nearest neighbours of every angle live in HBM). */
 int icpb200_rotation_scores(int n_problems, const double *src, const int64_t *src_off,
                             const double *tgt, const int64_t *tgt_off, const double *angles,
                             const int64_t *ang_off, const double *shift, double *scores_out,

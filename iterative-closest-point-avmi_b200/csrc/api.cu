@@ -93,6 +93,7 @@ static int init_locked(int device) {
         ICPB_CUDA(cudaStreamCreateWithFlags(&c.chunk_stream[i], cudaStreamNonBlocking));
     }
     ICPB_CUDA(cudaEventCreateWithFlags(&c.fork_ev, cudaEventDisableTiming));
+    ICPB_CUDA(cudaEventCreateWithFlags(&c.icp_done, cudaEventDisableTiming));
     c.ready = true;
     return ICPB200_OK;
 }
@@ -191,6 +192,9 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
                        const IcpTrace& tr, IcpArgs* args_out, const UploadPlan* plan = nullptr) {
     Context& c = g_ctx;
     if (n_pairs == 0) return ICPB200_OK;
+    // The workspaces below (preprocessed clouds, queues, hand-over state) are per process: a call enqueued on another
+    // stream while the previous one is still running must not touch them, so every enqueue waits for the previous one.
+    if (c.icp_done_valid) ICPB_CUDA(cudaStreamWaitEvent(st, c.icp_done, 0));
     const bool grid = k.nn_mode == ICPB200_NN_GRID ||
                       (k.nn_mode == ICPB200_NN_AUTO && t.role_max > ICPB200_BRUTE_MAX_POINTS);
     if (!grid && t.role_max > ICPB200_BRUTE_MAX_POINTS) {
@@ -366,6 +370,8 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
         if ((rc = launch_icp_pairs(b, k.dim, grid, c.sm_count, std::min(smem2, (size_t)c.max_smem_optin), st))) return rc;
     }
     ICPB_CUDA(cudaEventRecord(c.ev[3], st));
+    ICPB_CUDA(cudaEventRecord(c.icp_done, st));
+    c.icp_done_valid = true;
     return ICPB200_OK;
 }
 
@@ -453,7 +459,7 @@ void icpb200_shutdown(void) {
                       &c.aux_ds[0], &c.aux_ds[1], &c.aux_n[0], &c.aux_n[1], &c.aux_box[0], &c.aux_box[1],
                       &c.aux_nrm[0], &c.aux_nrm[1], &c.aux_flags[0], &c.aux_flags[1], &c.vox_in, &c.vox_out,
                       &c.big_keys, &c.big_idx, &c.grid_start, &c.grid_items, &c.grid_cell, &c.grid_desc, &c.grid_off,
-                      &c.grid_buckets, &c.rot_src, &c.rot_tgt, &c.rot_ang, &c.rot_off, &c.rot_out, &c.cont_cur, &c.cont_match, &c.cont_d2lb, &c.cont_moved, &c.cont_scalar, &c.cont_list, &c.pair_prof};
+                      &c.grid_buckets, &c.rot_src, &c.rot_tgt, &c.rot_ang, &c.rot_off, &c.rot_out, &c.cont_cur, &c.cont_match, &c.cont_d2lb, &c.cont_moved, &c.cont_scalar, &c.cont_list, &c.pair_prof, &c.rot_part};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 4; ++i) if (c.ev[i]) { cudaEventDestroy(c.ev[i]); c.ev[i] = nullptr; }
     for (int i = 0; i < kUploadChunks; ++i) {
@@ -463,6 +469,7 @@ void icpb200_shutdown(void) {
         if (c.chunk_stream[i]) { cudaStreamDestroy(c.chunk_stream[i]); c.chunk_stream[i] = nullptr; }
     }
     if (c.fork_ev) { cudaEventDestroy(c.fork_ev); c.fork_ev = nullptr; }
+    if (c.icp_done) { cudaEventDestroy(c.icp_done); c.icp_done = nullptr; c.icp_done_valid = false; }
     if (c.h_stage) { cudaFreeHost(c.h_stage); c.h_stage = nullptr; c.h_stage_cap = 0; }
     if (c.copy_stream) { cudaStreamDestroy(c.copy_stream); c.copy_stream = nullptr; }
     cudaStreamDestroy(c.stream);
@@ -892,10 +899,16 @@ int icpb200_rotation_scores(int n_problems, const double* src, const int64_t* sr
     }
     const long long n_src = src_off[n_problems], n_tgt = tgt_off[n_problems], n_ang = ang_off[n_problems];
     if (n_ang == 0) return ICPB200_OK;
-    if (max_t > 8192 || n_problems > 65535) {
-        set_error("icpb200_rotation_scores: targets are limited to 8192 points (got %lld) and 65535 problems per call", max_t);
+    if (n_problems > 65535) {
+        set_error("icpb200_rotation_scores: at most 65535 problems per call (got %d)", n_problems);
         return ICPB200_ERR_LIMIT;
     }
+    // a target of more than kRotSlice points (the downsampled submap of slam.py:125-126 can be) does not fit shared memory:
+    // it is swept in slices, one launch each, with the running nearest neighbour of every (angle, source point) in HBM
+    constexpr long long kRotSlice = 8192;
+    const int n_slices = (int)std::max<long long>(1, (max_t + kRotSlice - 1) / kRotSlice);
+    long long max_s = 0;
+    for (int p = 0; p < n_problems; ++p) max_s = std::max<long long>(max_s, src_off[p + 1] - src_off[p]);
     int rc = init_locked(-1);
     if (rc) return rc;
     Context& c = g_ctx;
@@ -922,9 +935,25 @@ int icpb200_rotation_scores(int n_problems, const double* src, const int64_t* sr
     a.scores = c.rot_out.as<double>();
     a.nn_dist = nn_dist_out ? reinterpret_cast<double*>(c.rot_out.as<unsigned char>() + b_ang) : nullptr;
     a.nn_idx = nn_idx_out ? reinterpret_cast<int*>(c.rot_out.as<unsigned char>() + b_ang + sizeof(double) * (size_t)n_src) : nullptr;
-    a.cap_t = round_up((int)std::max<long long>(max_t, 32), 32);
+    a.cap_t = round_up((int)std::max<long long>(std::min<long long>(max_t, kRotSlice), 32), 32);
     if (rot_smem_bytes(a.cap_t) > (size_t)c.max_smem_optin) { set_error("icpb200_rotation_scores: target too large for shared memory"); return ICPB200_ERR_LIMIT; }
-    if ((rc = launch_rot_scores(a, n_problems, (int)max_a, c.sm_count, st))) return rc;
+    a.slice_len = 0; a.slice = 0; a.n_slices = 1; a.part_d2 = nullptr; a.part_j = nullptr; a.part_stride = 0;
+    if (n_slices > 1) {
+        const size_t rows = (size_t)n_ang, stride = (size_t)std::max<long long>(max_s, 1);
+        if (rows * stride * 12 > ((size_t)4 << 30)) {
+            set_error("icpb200_rotation_scores: %lld angles x %lld source points against a sliced target need more than 4 GiB of running minima", n_ang, max_s);
+            return ICPB200_ERR_LIMIT;
+        }
+        if (c.rot_part.reserve(rows * stride * 12)) return ICPB200_ERR_CUDA;
+        a.part_d2 = c.rot_part.as<double>();
+        a.part_j = reinterpret_cast<int*>(c.rot_part.as<unsigned char>() + rows * stride * 8);
+        a.part_stride = (long long)stride;
+        a.slice_len = (int)kRotSlice; a.n_slices = n_slices;
+    }
+    for (int s = 0; s < n_slices; ++s) {
+        a.slice = s;
+        if ((rc = launch_rot_scores(a, n_problems, (int)max_a, c.sm_count, st))) return rc;
+    }
     ICPB_CUDA(cudaMemcpyAsync(scores_out, a.scores, b_ang, cudaMemcpyDeviceToHost, st));
     if (nn_dist_out) {
         ICPB_CUDA(cudaMemcpyAsync(nn_dist_out, a.nn_dist, sizeof(double) * (size_t)n_src, cudaMemcpyDeviceToHost, st));
@@ -947,6 +976,7 @@ void OccGrid::release_all() {
     if (ev_join) { cudaEventDestroy(ev_join); ev_join = nullptr; }
     if (ev_hit) { cudaEventDestroy(ev_hit); ev_hit = nullptr; }
     if (ev_stats) { cudaEventDestroy(ev_stats); ev_stats = nullptr; }
+    if (ev_done) { cudaEventDestroy(ev_done); ev_done = nullptr; }
     if (pending_host) { cudaFreeHost(pending_host); pending_host = nullptr; }
     if (h_in_pack) { cudaFreeHost(h_in_pack); h_in_pack = nullptr; h_in_cap = 0; }
     if (h_pack) { cudaFreeHost(h_pack); h_pack = nullptr; h_pack_cap = 0; }
@@ -1095,6 +1125,10 @@ int icpb200_grid_update_dev(void* grid, int n_scans, const double* d_origins, co
     OccGrid* g = static_cast<OccGrid*>(grid);
     cudaStream_t st = stream ? (cudaStream_t)stream : g_ctx.stream;
     if ((rc = occ_collect(*g))) return rc;
+    // the grid's work buffers are shared by its updates: an update on another stream waits for the previous one
+    if (!g->ev_done) ICPB_CUDA(cudaEventCreateWithFlags(&g->ev_done, cudaEventDisableTiming));
+    else ICPB_CUDA(cudaStreamWaitEvent(st, g->ev_done, 0));
+    struct Mark { OccGrid* g; cudaStream_t st; ~Mark() { cudaEventRecord(g->ev_done, st); } } mark{g, st};
     if (g->use_fast && !g->zero_outside_clamp && n_scans <= kOccMaxChunkScans) {
         // One chunk of the order-free path: the offsets are checked on the device, the host waits once (for the
         // binning totals, underneath the fill pass) and returns with the rest of the update enqueued.  The hit-overflow

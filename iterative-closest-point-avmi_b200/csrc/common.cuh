@@ -65,11 +65,13 @@ struct Context {
     void* h_stage = nullptr;           // page-locked staging for the result read-back (one wait, then host copies)
     size_t h_stage_cap = 0;
     cudaStream_t last_icp_stream = nullptr;
+    cudaEvent_t icp_done = nullptr;    // end of the last registration enqueue: the next one (any stream) waits for it
+    bool icp_done_valid = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // K1 start | K2 start | K3 start | K3 end
     // voxel_downsample entry point
     DevBuf vox_in, vox_out;
     // rotation-search scoring
-    DevBuf rot_src, rot_tgt, rot_ang, rot_off, rot_out;
+    DevBuf rot_src, rot_tgt, rot_ang, rot_off, rot_out, rot_part;
 };
 
 Context& ctx();

@@ -75,10 +75,13 @@ size_t icp_normals_smem_bytes(int cap_t) {
 
 // ---- K0: which clouds are referenced / are point-to-line targets -------------
 __global__ void mark_used_kernel(int n_pairs, const int* __restrict__ src_idx, const int* __restrict__ tgt_idx,
-                                 unsigned char* used_s, unsigned char* used_t, unsigned char* is_tgt) {
+                                 unsigned char* used_s, unsigned char* used_t, unsigned char* is_tgt, int n_s, int n_t) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pairs) return;
     const int cs = src_idx ? src_idx[p] : p, ct = tgt_idx ? tgt_idx[p] : p;
+    // (the device-resident entry point cannot look at its index arrays on the host: a pair that names a cloud outside the
+    // set is skipped here and reported by the pair kernel with status ICPB200_BAD_VOXELS)
+    if (cs < 0 || cs >= n_s || ct < 0 || ct >= n_t) return;
     used_s[cs] = 1;
     used_t[ct] = 1;
     if (is_tgt) is_tgt[ct] = 1;
@@ -1537,7 +1540,8 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
 
         const int cs = a.src_idx ? a.src_idx[p] : p;
         const int ct = a.tgt_idx ? a.tgt_idx[p] : p;
-        const int n_s = a.s.ds_n[cs], n_t = a.t.ds_n[ct];
+        const bool named = cs >= 0 && cs < a.s.n_clouds && ct >= 0 && ct < a.t.n_clouds;
+        const int n_s = named ? a.s.ds_n[cs] : 0, n_t = named ? a.t.ds_n[ct] : 0;
         if (n_s <= 0 || n_t <= 0 || n_s > a.cap_s || (!GRID && n_t > a.cap_t)) {
             if (tid == 0) {
                 for (int k = 0; k < DIM * DIM; ++k) a.R_out[(size_t)p * DIM * DIM + k] = (k % (DIM + 1) == 0) ? 1.0 : 0.0;
@@ -2014,7 +2018,8 @@ __device__ __forceinline__ void rot_exact(const RotProblem& P, double px, double
 
 template <int S>
 __device__ __forceinline__ double rot_round(const RotProblem& P, const double* __restrict__ src, int n_s, int first_chunk,
-                                            double ca, double sa, double ox, double oy, double* nn_d, int* nn_idx) {
+                                            double ca, double sa, double ox, double oy, double* nn_d, int* nn_idx,
+                                            double* part_d2, int* part_j, int j_base, bool first_slice, bool last_slice) {
     const int lane = threadIdx.x & 31;
     float sx[S], sy[S], b1[S], b2[S];
     double px[S], py[S];
@@ -2037,6 +2042,15 @@ __device__ __forceinline__ double rot_round(const RotProblem& P, const double* _
         double d2;
         int j;
         rot_exact(P, px[s], py[s], sx[s], sy[s], b2[s], bt[s], d2, j);
+        j += j_base;
+        if (part_d2) {                             // the target comes in slices: keep the running minimum (lowest index on ties)
+            if (!first_slice) {
+                const double pd = part_d2[pt[s]];
+                const int pj = part_j[pt[s]];
+                if (pd < d2 || (pd == d2 && pj < j)) { d2 = pd; j = pj; }
+            }
+            if (!last_slice) { part_d2[pt[s]] = d2; part_j[pt[s]] = j; continue; }
+        }
         const double d = sqrt(d2);                 // KDTree returns the distance; the callers square it again
         acc += d * d;
         if (nn_d) { nn_d[pt[s]] = d; nn_idx[pt[s]] = j; }
@@ -2052,13 +2066,21 @@ __global__ void __launch_bounds__(kNT) rot_scores_kernel(const RotArgs a) {
     const int n_ang = (int)(a.ang_off[p + 1] - ab);
     if (k0 >= n_ang) return;
     const double* src = a.src + 2 * a.src_off[p];
-    const double* tgt = a.tgt + 2 * a.tgt_off[p];
-    const int n_s = (int)(a.src_off[p + 1] - a.src_off[p]), n_t = (int)(a.tgt_off[p + 1] - a.tgt_off[p]);
+    const int n_s = (int)(a.src_off[p + 1] - a.src_off[p]);
+    const int n_t_all = (int)(a.tgt_off[p + 1] - a.tgt_off[p]);
+    // targets beyond shared memory come in slices of slice_len points, one launch per slice: the running minima live in
+    // a.part_d2 / a.part_j, the last slice turns them into scores
+    const int j_base = a.slice_len > 0 ? a.slice * a.slice_len : 0;
+    const int n_t = a.slice_len > 0 ? max(0, min(a.slice_len, n_t_all - j_base)) : n_t_all;
+    const bool first_slice = a.slice_len <= 0 || a.slice == 0;
+    const bool last_slice = a.slice_len <= 0 || a.slice == a.n_slices - 1;
+    const double* tgt = a.tgt + 2 * (a.tgt_off[p] + j_base);
     const int k1 = min(k0 + a.angles_per_cta, n_ang);
-    if (n_s <= 0 || n_t <= 0) {
+    if (n_s <= 0 || n_t_all <= 0) {
         for (int k = k0 + tid; k < k1; k += kNT) a.scores[ab + k] = INFINITY;
         return;
     }
+    if (n_t <= 0 && !last_slice) return;           // this problem's target ended in an earlier slice
     const int tstride = a.cap_t + a.cap_t / 32;
     double* tx = reinterpret_cast<double*>(smem + align16(sizeof(CtaShared)));
     double* ty = tx + tstride;
@@ -2096,20 +2118,22 @@ __global__ void __launch_bounds__(kNT) rot_scores_kernel(const RotArgs a) {
     double* nn_d = a.nn_dist ? a.nn_dist + a.src_off[p] : nullptr;
     int* nn_i = a.nn_idx ? a.nn_idx + a.src_off[p] : nullptr;
     double acc[1] = {0.0};
+    double* pd2 = a.part_d2 ? a.part_d2 + (size_t)(ab + k) * a.part_stride : nullptr;
+    int* pj = a.part_j ? a.part_j + (size_t)(ab + k) * a.part_stride : nullptr;
     constexpr int kRotS = 4;                       // chunks per warp per round (register budget: two CTAs per SM)
     for (int base = 0; base < n_chunks; base += kRotS * kNW) {
         const int first = base + w;
         const int mine = first < n_chunks ? min(kRotS, (n_chunks - first + kNW - 1) / kNW) : 0;   // warp-uniform
         switch (mine) {
             case 0: break;
-            case 1: acc[0] += rot_round<1>(P, src, n_s, first, ca, sa, ox, oy, nn_d, nn_i); break;
-            case 2: acc[0] += rot_round<2>(P, src, n_s, first, ca, sa, ox, oy, nn_d, nn_i); break;
-            case 3: acc[0] += rot_round<3>(P, src, n_s, first, ca, sa, ox, oy, nn_d, nn_i); break;
-            default: acc[0] += rot_round<4>(P, src, n_s, first, ca, sa, ox, oy, nn_d, nn_i); break;
+            case 1: acc[0] += rot_round<1>(P, src, n_s, first, ca, sa, ox, oy, nn_d, nn_i, pd2, pj, j_base, first_slice, last_slice); break;
+            case 2: acc[0] += rot_round<2>(P, src, n_s, first, ca, sa, ox, oy, nn_d, nn_i, pd2, pj, j_base, first_slice, last_slice); break;
+            case 3: acc[0] += rot_round<3>(P, src, n_s, first, ca, sa, ox, oy, nn_d, nn_i, pd2, pj, j_base, first_slice, last_slice); break;
+            default: acc[0] += rot_round<4>(P, src, n_s, first, ca, sa, ox, oy, nn_d, nn_i, pd2, pj, j_base, first_slice, last_slice); break;
         }
     }
     block_reduce<1, SumOp>(acc, sh, phase);
-    if (tid == 0) a.scores[ab + k] = acc[0] / (double)n_s;         // np.mean(dists ** 2)
+    if (tid == 0 && last_slice) a.scores[ab + k] = acc[0] / (double)n_s;         // np.mean(dists ** 2)
     }
 }
 
@@ -2134,7 +2158,7 @@ int launch_rot_scores(const RotArgs& a_in, int n_problems, int max_angles, int s
 // ---- host-side launchers -------------------------------------------------------------
 int launch_mark_used(const IcpArgs& a, bool p2l, cudaStream_t stream) {
     mark_used_kernel<<<(a.n_pairs + 255) / 256, 256, 0, stream>>>(a.n_pairs, a.src_idx, a.tgt_idx, a.s.used, a.t.used,
-                                                                  p2l ? a.t.is_tgt : nullptr);
+                                                                  p2l ? a.t.is_tgt : nullptr, a.s.n_clouds, a.t.n_clouds);
     ICPB_LAUNCH_CHECK();
     return ICPB200_OK;
 }

@@ -103,8 +103,12 @@ struct RotArgs {
     const double* shift;                               // 2 per problem: added after the rotation
     double* scores;                                    // one per angle
     double* nn_dist; int* nn_idx;                      // optional, per source point (single-angle queries)
-    int cap_t;                                         // multiple of 32 >= the largest target
+    int cap_t;                                         // multiple of 32 >= the largest target (slice)
     int angles_per_cta;                                // set by the launcher
+    // targets beyond shared memory: slices of slice_len points, one launch per slice (slice_len 0: whole targets)
+    int slice_len, slice, n_slices;
+    double* part_d2; int* part_j;                      // running minimum per (angle, source point), rows of part_stride
+    long long part_stride;
 };
 size_t rot_smem_bytes(int cap_t);
 int launch_rot_scores(const RotArgs& a, int n_problems, int max_angles, int sm_count, cudaStream_t stream);

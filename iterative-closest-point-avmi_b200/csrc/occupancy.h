@@ -51,6 +51,7 @@ struct OccGrid {
     size_t h_pack_cap = 0;
     cudaStream_t aux_stream = nullptr;             // the hit cells' replay runs here, under the remaining tiles
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_hit = nullptr;
+    cudaEvent_t ev_done = nullptr;                 // end of the last stream-ordered update (icpb200_grid_update_dev)
     // Deferred read-back of the device-resident entry point (occ_update_fast with defer = true): the statistics and
     // the hit-overflow flag of the last update land in `pending_host` (page-locked) behind `ev_stats`; occ_collect()
     // folds them into `stats` and reports the flag.  Every entry point that touches the grid collects first.

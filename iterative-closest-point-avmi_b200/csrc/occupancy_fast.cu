@@ -188,7 +188,9 @@ __global__ void occ_fast_origins(const double* __restrict__ origins, int n_scans
         // flags[1] = offsets inconsistent (hit_off[0] != 0, decreasing, or hit_off[n_scans] != total_hits)
         const long long b = hit_off[s], e = hit_off[s + 1];
         if (e - b > 4095) flags[0] = 1u;
-        if (e < b || (s == 0 && b != 0) || (s == n_scans - 1 && e != total_hits)) flags[1] = 1u;
+        // (a scan of 2^20 rays or more does not fit the event word either: refused like inconsistent offsets -- the
+        // host-buffer entry point sends such a scan through the ordered replay instead)
+        if (e < b || (s == 0 && b != 0) || (s == n_scans - 1 && e != total_hits) || e - b >= (long long)kHitUnit) flags[1] = 1u;
     }
 }
 
@@ -1178,7 +1180,28 @@ int occ_update_fast(OccGrid& g, int n_scans, const double* d_origins, const doub
         if (h_hit_off) {
             rb = h_hit_off[s0]; re = h_hit_off[s0 + cs];
             big = 0;
-            for (int s = s0; s < s0 + cs && !big; ++s) big = h_hit_off[s + 1] - h_hit_off[s] > 4095 ? 1 : 0;
+            bool huge = false;
+            for (int s = s0; s < s0 + cs; ++s) {
+                const long long len = h_hit_off[s + 1] - h_hit_off[s];
+                if (len > 4095) big = 1;
+                if (len >= (long long)kHitUnit) huge = true;      // a cell could collect 2^20 misses of one scan: beyond the event word
+            }
+            if (huge) {
+                all_fast = false;
+                g.all_dirty = true;
+                std::vector<long long> off((size_t)cs + 1);
+                for (int k = 0; k <= cs; ++k) off[k] = h_hit_off[s0 + k] - h_hit_off[s0];
+                if (g.hit_off_shift.reserve(sizeof(long long) * off.size())) return ICPB200_ERR_CUDA;
+                ICPB_CUDA(cudaMemcpyAsync(g.hit_off_shift.p, off.data(), sizeof(long long) * off.size(), cudaMemcpyHostToDevice, st));
+                ICPB_CUDA(cudaStreamSynchronize(st));
+                long long keep[4] = {g.stats[0], g.stats[1], g.stats[2], g.stats[3]};
+                int rc2 = occ_update_ordered(g, cs, d_origins + 2 * (size_t)s0, d_hits + 2 * (size_t)h_hit_off[s0],
+                                             g.hit_off_shift.as<long long>(), off.data(), st);
+                if (rc2) return rc2;
+                for (int k = 1; k < 4; ++k) tot[k] += g.stats[k];
+                for (int k = 0; k < 4; ++k) g.stats[k] = keep[k];
+                continue;
+            }
         }
         bool bad_offsets = false;
         int rc = fast_chunk(g, n_scans, s0, cs, d_origins, d_hits, d_hit_off, rb, re, big, &bad_offsets, st);
