@@ -262,6 +262,35 @@ int icpb200_grid_last_stats(void *grid, int64_t *stats4);
  * chunk (zeros for idle tiles) and returns the number of tiles written. */
 int icpb200_grid_tile_profile(void *grid, int64_t *out, int64_t cap_tiles);
 
+/* ---- device-resident submap -------------------------------------------------
+ * The rolling window of global-frame scans the reference keeps as a Python list
+ * (slam.py:559-562 `submap_buffer.append / pop(0)`, rebuilt after a loop closure,
+ * slam.py:611-615) and everything it recomputes from the whole window in every
+ * scan: np.vstack + voxel_downsample (slam.py:103-108 `_build_submap`) and, inside
+ * ICP(scan, submap, ...) (slam.py:217-225), the second voxel_downsample of the
+ * target plus its KD-tree (icp.py:151, 173).  Here the window lives on the device:
+ * a push uploads ONE scan, the two downsamples and the hash grid are computed on
+ * the device from the resident window and cached until the window changes, so
+ * registrations against an unchanged window run the pair kernel only.
+ * Results are those of ICP(source, voxel_downsample(vstack(window), submap_voxel), ...). */
+void *icpb200_submap_create(int dim, int capacity_scans);
+void icpb200_submap_destroy(void *submap);
+/* append a scan (rows of dim float64, global frame); the oldest scan leaves once
+ * capacity_scans are held (slam.py:561-562) */
+int icpb200_submap_push(void *submap, const double *pts, int64_t n);
+int icpb200_submap_clear(void *submap);
+int icpb200_submap_size(void *submap, int64_t *n_scans, int64_t *n_points);
+/* slam.py:103-108: *n_out = rows of voxel_downsample(vstack(window), submap_voxel);
+ * `out` (may be NULL) receives them, bit-identical to the reference's array. */
+int icpb200_submap_build(void *submap, double submap_voxel, double *out, int64_t out_capacity_rows, int64_t *n_out);
+/* n_sources registrations against the window's submap (outputs as
+ * icpb200_icp_batch; every source is registered onto the same target). */
+int icpb200_submap_icp(void *submap, double submap_voxel, int n_sources, const double *src, const int64_t *src_off,
+                       const double *R_init, const double *t_init, double error_threshold, int max_iterations,
+                       double voxel_size, int method, int normal_k, double max_corr_dist, int nn_mode,
+                       double *R_out, double *t_out, double *err_out, double *prev_err_out,
+                       int32_t *iters_out, int32_t *status_out);
+
 /* ---- rotation-search scoring -------------------------------------------------
  * The pre-alignment sweeps in front of every ICP call:
  *   utilities/features.py:165-242  rotation_search  (score every angle of a coarse, then a fine sweep)

@@ -143,6 +143,24 @@ struct IcpTrace {                  // optional debug outputs of a single-pair ca
     int stride = 0;
 };
 
+// Preprocessed form of ONE target cloud that outlives a call: its voxel means, box, normals and hash grid live in buffers
+// of their own (a device-resident submap owns one, icpb200_submap_*), so registrations against the same target skip the
+// target's preprocessing altogether.
+struct PrepTarget {
+    DevBuf ds, n, box, nrm, flags, off;
+    DevBuf grid_start, grid_items, grid_cell, grid_desc, grid_off, grid_buckets;
+    bool ready = false;            // ds / box / (nrm) / (grid) hold the preprocessing for the parameters below
+    double voxel = 0.0;
+    int want_normals = 0, normal_k = 0, has_grid = 0;
+    void release() {
+        DevBuf* b[] = {&ds, &n, &box, &nrm, &flags, &off, &grid_start, &grid_items, &grid_cell, &grid_desc, &grid_off, &grid_buckets};
+        for (DevBuf* p : b) p->release();
+        ready = false;
+    }
+};
+
+static int make_prep_cloud_set(PrepTarget& pt, const struct DevClouds& d, int dim, bool want_normals, CloudSet* out);
+
 // Device buffers for the preprocessed form of cloud set `slot` (0 or 1).
 static int make_cloud_set(Context& c, int slot, const DevClouds& d, int dim, bool want_normals, CloudSet* out) {
     const size_t np = (size_t)d.total_points, nc = (size_t)d.n_clouds;
@@ -157,6 +175,21 @@ static int make_cloud_set(Context& c, int slot, const DevClouds& d, int dim, boo
     out->nrm = want_normals ? c.aux_nrm[slot].as<double>() : nullptr;
     out->used = c.aux_flags[slot].as<unsigned char>();
     out->is_tgt = out->used + nc;
+    return ICPB200_OK;
+}
+
+static int make_prep_cloud_set(PrepTarget& pt, const DevClouds& d, int dim, bool want_normals, CloudSet* out) {
+    const size_t np = (size_t)d.total_points;
+    if (pt.ds.reserve(sizeof(double) * dim * np) || pt.n.reserve(sizeof(int)) || pt.box.reserve(sizeof(double) * 6) ||
+        pt.flags.reserve(2) || (want_normals && pt.nrm.reserve(sizeof(double) * 2 * np)))
+        return ICPB200_ERR_CUDA;
+    out->raw = d.pts; out->off = d.off; out->n_clouds = 1;
+    out->ds = pt.ds.as<double>();
+    out->ds_n = pt.n.as<int>();
+    out->box = pt.box.as<double>();
+    out->nrm = want_normals ? pt.nrm.as<double>() : nullptr;
+    out->used = pt.flags.as<unsigned char>();
+    out->is_tgt = out->used + 1;
     return ICPB200_OK;
 }
 
@@ -189,7 +222,7 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
                        const int* d_src_idx, const int* d_tgt_idx,
                        const double* d_R_init, const double* d_t_init, double* d_R, double* d_t,
                        double* d_err, double* d_prev, int* d_iters, int* d_status, cudaStream_t st,
-                       const IcpTrace& tr, IcpArgs* args_out, const UploadPlan* plan = nullptr) {
+                       const IcpTrace& tr, IcpArgs* args_out, const UploadPlan* plan = nullptr, PrepTarget* prep = nullptr) {
     Context& c = g_ctx;
     if (n_pairs == 0) return ICPB200_OK;
     // The workspaces below (preprocessed clouds, queues, hand-over state) are per process: a call enqueued on another
@@ -214,7 +247,11 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
     memset(&a, 0, sizeof(a));
     int rc;
     if ((rc = make_cloud_set(c, 0, s, k.dim, p2l && same_set, &a.s))) return rc;
+    // a target that keeps its preprocessing between calls (prep): reuse it when it was made with the same parameters
+    const bool prep_hit = prep && prep->ready && prep->voxel == k.voxel_size && prep->want_normals == (p2l ? 1 : 0) &&
+                          (!p2l || prep->normal_k == k.normal_k) && prep->has_grid == (grid ? 1 : 0);
     if (same_set) a.t = a.s;
+    else if (prep) { if ((rc = make_prep_cloud_set(*prep, t, k.dim, p2l, &a.t))) return rc; }
     else if ((rc = make_cloud_set(c, 1, t, k.dim, p2l, &a.t))) return rc;
     a.n_pairs = n_pairs;
     a.src_idx = d_src_idx; a.tgt_idx = d_tgt_idx;
@@ -270,7 +307,7 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
     ICPB_CUDA(cudaMemsetAsync(a.queue, 0, 16 * sizeof(unsigned), st));
     ICPB_CUDA(cudaMemsetAsync(a.stats, 0, 24 * sizeof(unsigned long long), st));
     ICPB_CUDA(cudaMemsetAsync(a.s.used, 0, 2 * (size_t)s.n_clouds, st));
-    if (!same_set) ICPB_CUDA(cudaMemsetAsync(a.t.used, 0, 2 * (size_t)t.n_clouds, st));
+    if (!same_set && !prep_hit) ICPB_CUDA(cudaMemsetAsync(a.t.used, 0, 2 * (size_t)t.n_clouds, st));
     a.grids = nullptr;
     if ((rc = launch_mark_used(a, p2l || grid, st))) return rc;
     ICPB_CUDA(cudaEventRecord(c.ev[0], st));
@@ -311,9 +348,18 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
         ICPB_CUDA(cudaEventRecord(c.ev[1], st));
     } else {
         if ((rc = voxel_set(c, a.s, s, k.dim, k.voxel_size, st))) return rc;
-        if (!same_set && (rc = voxel_set(c, a.t, t, k.dim, k.voxel_size, st))) return rc;
+        if (!same_set && !prep_hit && (rc = voxel_set(c, a.t, t, k.dim, k.voxel_size, st))) return rc;
         ICPB_CUDA(cudaEventRecord(c.ev[1], st));
-        if (grid) {
+        // the hash grids live in the context's buffers, or in the prepared target's own
+        DevBuf& g_start = prep ? prep->grid_start : c.grid_start;
+        DevBuf& g_items = prep ? prep->grid_items : c.grid_items;
+        DevBuf& g_cell = prep ? prep->grid_cell : c.grid_cell;
+        DevBuf& g_desc = prep ? prep->grid_desc : c.grid_desc;
+        DevBuf& g_off = prep ? prep->grid_off : c.grid_off;
+        DevBuf& g_buckets = prep ? prep->grid_buckets : c.grid_buckets;
+        if (prep_hit) {
+            if (grid) a.grids = g_desc.as<BigGrid>();
+        } else if (grid) {
             // one hash grid per target cloud; bucket counts from the raw sizes (host side)
             std::vector<int64_t> fetched;
             const int64_t* h_off = t.h_off;
@@ -335,23 +381,27 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
                 total_start += b + 1;
             }
             const size_t np = (size_t)t.total_points, nc = (size_t)t.n_clouds;
-            if (c.grid_start.reserve(sizeof(int) * (size_t)total_start) || c.grid_items.reserve(sizeof(int) * np) ||
-                c.grid_cell.reserve(sizeof(int2) * np) || c.grid_desc.reserve(sizeof(BigGrid) * nc) ||
-                c.grid_off.reserve(sizeof(long long) * nc) || c.grid_buckets.reserve(sizeof(int) * nc))
+            if (g_start.reserve(sizeof(int) * (size_t)total_start) || g_items.reserve(sizeof(int) * np) ||
+                g_cell.reserve(sizeof(int2) * np) || g_desc.reserve(sizeof(BigGrid) * nc) ||
+                g_off.reserve(sizeof(long long) * nc) || g_buckets.reserve(sizeof(int) * nc))
                 return ICPB200_ERR_CUDA;
-            ICPB_CUDA(cudaMemcpyAsync(c.grid_off.p, goff.data(), sizeof(long long) * nc, cudaMemcpyHostToDevice, st));
-            ICPB_CUDA(cudaMemcpyAsync(c.grid_buckets.p, gbuckets.data(), sizeof(int) * nc, cudaMemcpyHostToDevice, st));
+            ICPB_CUDA(cudaMemcpyAsync(g_off.p, goff.data(), sizeof(long long) * nc, cudaMemcpyHostToDevice, st));
+            ICPB_CUDA(cudaMemcpyAsync(g_buckets.p, gbuckets.data(), sizeof(int) * nc, cudaMemcpyHostToDevice, st));
             ICPB_CUDA(cudaStreamSynchronize(st));          // goff / gbuckets are stack-owned
-            ICPB_CUDA(cudaMemsetAsync(c.grid_desc.p, 0, sizeof(BigGrid) * nc, st));
+            ICPB_CUDA(cudaMemsetAsync(g_desc.p, 0, sizeof(BigGrid) * nc, st));
             // cell edge: 8 voxels (a 3x3 block of cells holds a few dozen wall points)
-            if ((rc = launch_big_grid(a.t, 8.0 * k.voxel_size, c.grid_off.as<long long>(), c.grid_buckets.as<int>(),
-                                      c.grid_start.as<int>(), c.grid_items.as<int>(), c.grid_cell.as<int2>(),
-                                      c.grid_desc.as<BigGrid>(), st)))
+            if ((rc = launch_big_grid(a.t, 8.0 * k.voxel_size, g_off.as<long long>(), g_buckets.as<int>(),
+                                      g_start.as<int>(), g_items.as<int>(), g_cell.as<int2>(),
+                                      g_desc.as<BigGrid>(), st)))
                 return rc;
-            a.grids = c.grid_desc.as<BigGrid>();
+            a.grids = g_desc.as<BigGrid>();
             if (p2l && (rc = launch_big_normals(a.t, a.grids, k.normal_k, t.role_max, st))) return rc;
         } else if (p2l) {
             if ((rc = launch_normals(a.t, a.cap_t, k.normal_k, k.voxel_size, st))) return rc;
+        }
+        if (prep && !prep_hit) {
+            prep->ready = true; prep->voxel = k.voxel_size; prep->want_normals = p2l ? 1 : 0; prep->normal_k = k.normal_k;
+            prep->has_grid = grid ? 1 : 0;
         }
     }
     ICPB_CUDA(cudaEventRecord(c.ev[2], st));
@@ -434,6 +484,88 @@ static int upload_init(Context& c, int n_pairs, int dim, const double* R_init, c
         *d_R = c.rinit.as<double>();
         *d_t = c.tinit.as<double>();
     }
+    return ICPB200_OK;
+}
+
+// ---- device-resident submap (slam.py:103-108, 559-562, 611-615) ---------------------------------------------------------
+// The rolling window of global-frame scans the reference keeps as a Python list (`submap_buffer`): here the scans live in
+// fixed slots of one device arena, a push uploads ONE scan (17 KB), and everything the reference recomputes from the
+// whole window in every scan -- np.vstack, the first voxel_downsample (`_build_submap`), and inside ICP() the second
+// voxel_downsample of the target plus its KD-tree (here: hash grid) -- is computed on the device from the resident window
+// and cached until the window changes.
+struct SubmapSlot { int slot; long long n; };
+
+struct Submap {
+    int dim = 2, capacity = 0;
+    long long slot_points = 4096;                  // points per slot (grows when a larger scan arrives)
+    DevBuf arena;                                  // capacity x slot_points x dim doubles
+    std::vector<SubmapSlot> scans;                 // window, oldest first
+    std::vector<int> free_slots;
+    long long version = 0;                         // bumped by every push / clear
+    // np.vstack of the window (device), then voxel_downsample(.., submap_voxel): `built`
+    DevBuf cat, cat_desc, cat_off, built, built_n, built_box, built_off;
+    long long built_version = -1, built_points = 0;
+    double built_voxel = 0.0;
+    PrepTarget prep;                               // ICP()'s own preprocessing of that cloud (second downsample + grid)
+    long long prep_version = -1;
+    void release() {
+        DevBuf* b[] = {&arena, &cat, &cat_desc, &cat_off, &built, &built_n, &built_box, &built_off};
+        for (DevBuf* p : b) p->release();
+        prep.release();
+    }
+};
+
+__global__ void submap_concat_kernel(const double* __restrict__ arena, const long long* __restrict__ desc /* [scan] = {src row, dst row, rows} */,
+                                     int n_scans, int dim, double* __restrict__ out) {
+    const int s = blockIdx.y;
+    if (s >= n_scans) return;
+    const long long src = desc[3 * s] * dim, dst = desc[3 * s + 1] * dim, n = desc[3 * s + 2] * dim;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[dst + i] = arena[src + i];
+}
+
+// vstack + voxel_downsample(window, submap_voxel) on the device (slam.py:103-108); *n_out = rows of the result
+static int submap_build(Context& c, Submap& sm, double voxel, long long* n_out, cudaStream_t st) {
+    if (sm.built_version == sm.version && sm.built_voxel == voxel) { *n_out = sm.built_points; return ICPB200_OK; }
+    long long total = 0;
+    for (const SubmapSlot& s : sm.scans) total += s.n;
+    *n_out = 0;
+    sm.built_points = 0; sm.built_version = sm.version; sm.built_voxel = voxel;
+    sm.prep.ready = false;
+    if (total == 0) return ICPB200_OK;
+    const int ns = (int)sm.scans.size();
+    std::vector<long long> desc((size_t)3 * ns);
+    long long at = 0;
+    for (int i = 0; i < ns; ++i) {
+        desc[3 * i] = (long long)sm.scans[i].slot * sm.slot_points; desc[3 * i + 1] = at; desc[3 * i + 2] = sm.scans[i].n;
+        at += sm.scans[i].n;
+    }
+    const long long off[2] = {0, total};
+    if (sm.cat.reserve(sizeof(double) * sm.dim * (size_t)total) || sm.cat_desc.reserve(sizeof(long long) * desc.size()) ||
+        sm.cat_off.reserve(sizeof(off)) || sm.built.reserve(sizeof(double) * sm.dim * (size_t)total) ||
+        sm.built_n.reserve(sizeof(int)) || sm.built_box.reserve(sizeof(double) * 6) || sm.built_off.reserve(sizeof(off)) ||
+        c.big_keys.reserve(sizeof(unsigned long long) * 2 * (size_t)total) || c.big_idx.reserve(sizeof(unsigned) * 2 * (size_t)total))
+        return ICPB200_ERR_CUDA;
+    ICPB_CUDA(cudaMemcpyAsync(sm.cat_desc.p, desc.data(), sizeof(long long) * desc.size(), cudaMemcpyHostToDevice, st));
+    ICPB_CUDA(cudaMemcpyAsync(sm.cat_off.p, off, sizeof(off), cudaMemcpyHostToDevice, st));
+    ICPB_CUDA(cudaStreamSynchronize(st));              // desc / off are stack-owned
+    submap_concat_kernel<<<dim3(8, (unsigned)ns), 256, 0, st>>>(sm.arena.as<double>(), sm.cat_desc.as<long long>(), ns, sm.dim, sm.cat.as<double>());
+    ICPB_LAUNCH_CHECK();
+    CloudSet cs;
+    memset(&cs, 0, sizeof(cs));
+    cs.raw = sm.cat.as<double>(); cs.off = sm.cat_off.as<long long>(); cs.n_clouds = 1;
+    cs.ds = sm.built.as<double>(); cs.ds_n = sm.built_n.as<int>(); cs.box = sm.built_box.as<double>();
+    int rc = launch_big_voxel(cs, sm.dim, voxel, c.big_keys.as<unsigned long long>(), c.big_idx.as<unsigned>(), total, st);
+    if (rc) return rc;
+    int m = 0;
+    ICPB_CUDA(cudaMemcpyAsync(&m, cs.ds_n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ICPB_CUDA(cudaStreamSynchronize(st));
+    if (m < 0) { set_error("icpb200_submap: voxel index range does not fit 62 bits"); return ICPB200_ERR_LIMIT; }
+    const long long boff[2] = {0, m};
+    ICPB_CUDA(cudaMemcpyAsync(sm.built_off.p, boff, sizeof(boff), cudaMemcpyHostToDevice, st));
+    ICPB_CUDA(cudaStreamSynchronize(st));
+    sm.built_points = m;
+    *n_out = m;
     return ICPB200_OK;
 }
 
@@ -1223,6 +1355,145 @@ int icpb200_unpin_host(void* ptr) {
     if (!g_ctx.ready) return ICPB200_OK;
     ICPB_CUDA(cudaHostUnregister(ptr));
     return ICPB200_OK;
+}
+
+// ---- device-resident submap ----------------------------------------------------------------------------------------
+void* icpb200_submap_create(int dim, int capacity_scans) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if ((dim != 2 && dim != 3) || capacity_scans <= 0) { set_error("icpb200_submap_create: dim must be 2 or 3, capacity > 0"); return nullptr; }
+    if (init_locked(-1)) return nullptr;
+    Submap* sm = new Submap();
+    sm->dim = dim; sm->capacity = capacity_scans;
+    for (int i = capacity_scans - 1; i >= 0; --i) sm->free_slots.push_back(i);
+    return sm;
+}
+
+void icpb200_submap_destroy(void* submap) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!submap) return;
+    Submap* sm = static_cast<Submap*>(submap);
+    if (g_ctx.ready) cudaStreamSynchronize(g_ctx.stream);
+    sm->release();
+    delete sm;
+}
+
+int icpb200_submap_clear(void* submap) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!submap) { set_error("icpb200_submap_clear: null handle"); return ICPB200_ERR_ARG; }
+    Submap* sm = static_cast<Submap*>(submap);
+    for (const SubmapSlot& s : sm->scans) sm->free_slots.push_back(s.slot);
+    sm->scans.clear();
+    ++sm->version;
+    return ICPB200_OK;
+}
+
+int icpb200_submap_push(void* submap, const double* pts, int64_t n) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!submap || n < 0 || (n > 0 && !pts)) { set_error("icpb200_submap_push: null pointer or negative count"); return ICPB200_ERR_ARG; }
+    int rc = init_locked(-1);
+    if (rc) return rc;
+    Submap* sm = static_cast<Submap*>(submap);
+    Context& c = g_ctx;
+    if ((int)sm->scans.size() == sm->capacity) {                     // slam.py:561-562: pop(0)
+        sm->free_slots.push_back(sm->scans.front().slot);
+        sm->scans.erase(sm->scans.begin());
+    }
+    if (n > sm->slot_points || !sm->arena.p) {                        // (re)size the arena: slots of a power-of-two row count
+        long long want = sm->slot_points;
+        while (want < n) want *= 2;
+        DevBuf fresh;
+        if (fresh.reserve(sizeof(double) * sm->dim * (size_t)want * (size_t)sm->capacity)) return ICPB200_ERR_CUDA;
+        for (const SubmapSlot& s : sm->scans)
+            ICPB_CUDA(cudaMemcpyAsync(fresh.as<double>() + (size_t)s.slot * want * sm->dim,
+                                      sm->arena.as<double>() + (size_t)s.slot * sm->slot_points * sm->dim,
+                                      sizeof(double) * sm->dim * (size_t)s.n, cudaMemcpyDeviceToDevice, c.stream));
+        ICPB_CUDA(cudaStreamSynchronize(c.stream));
+        sm->arena.release();
+        sm->arena = fresh;
+        sm->slot_points = want;
+    }
+    const int slot = sm->free_slots.back();
+    sm->free_slots.pop_back();
+    if (n > 0) {
+        ICPB_CUDA(cudaMemcpyAsync(sm->arena.as<double>() + (size_t)slot * sm->slot_points * sm->dim, pts,
+                                  sizeof(double) * sm->dim * (size_t)n, cudaMemcpyHostToDevice, c.stream));
+        ICPB_CUDA(cudaStreamSynchronize(c.stream));                   // the caller's buffer is free on return
+    }
+    sm->scans.push_back(SubmapSlot{slot, (long long)n});
+    ++sm->version;
+    return ICPB200_OK;
+}
+
+int icpb200_submap_size(void* submap, int64_t* n_scans, int64_t* n_points) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!submap) { set_error("icpb200_submap_size: null handle"); return ICPB200_ERR_ARG; }
+    Submap* sm = static_cast<Submap*>(submap);
+    long long total = 0;
+    for (const SubmapSlot& s : sm->scans) total += s.n;
+    if (n_scans) *n_scans = (int64_t)sm->scans.size();
+    if (n_points) *n_points = total;
+    return ICPB200_OK;
+}
+
+int icpb200_submap_build(void* submap, double submap_voxel, double* out, int64_t out_capacity_rows, int64_t* n_out) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!submap || !(submap_voxel > 0.0) || !n_out) { set_error("icpb200_submap_build: null pointer or voxel <= 0"); return ICPB200_ERR_ARG; }
+    int rc = init_locked(-1);
+    if (rc) return rc;
+    Submap* sm = static_cast<Submap*>(submap);
+    long long m = 0;
+    if ((rc = submap_build(g_ctx, *sm, submap_voxel, &m, g_ctx.stream))) return rc;
+    *n_out = m;
+    if (out && m > 0) {
+        if (out_capacity_rows < m) { set_error("icpb200_submap_build: output holds %lld rows, %lld needed", (long long)out_capacity_rows, m); return ICPB200_ERR_ARG; }
+        ICPB_CUDA(cudaMemcpyAsync(out, sm->built.p, sizeof(double) * sm->dim * (size_t)m, cudaMemcpyDeviceToHost, g_ctx.stream));
+        ICPB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    }
+    return ICPB200_OK;
+}
+
+int icpb200_submap_icp(void* submap, double submap_voxel, int n_sources, const double* src, const int64_t* src_off,
+                       const double* R_init, const double* t_init, double error_threshold, int max_iterations,
+                       double voxel_size, int method, int normal_k, double max_corr_dist, int nn_mode, double* R_out,
+                       double* t_out, double* err_out, double* prev_err_out, int32_t* iters_out, int32_t* status_out) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!submap || !(submap_voxel > 0.0)) { set_error("icpb200_submap_icp: null handle or submap_voxel <= 0"); return ICPB200_ERR_ARG; }
+    Submap* sm = static_cast<Submap*>(submap);
+    const IcpCommon k{sm->dim, error_threshold, max_iterations, voxel_size, method, normal_k, max_corr_dist, nn_mode};
+    int rc = check_common(k, "icpb200_submap_icp");
+    if (rc) return rc;
+    if (n_sources < 0 || (n_sources > 0 && (!src || !src_off || !R_out || !t_out || !err_out || !iters_out || !status_out))) {
+        set_error("icpb200_submap_icp: null pointer or negative count");
+        return ICPB200_ERR_ARG;
+    }
+    if (n_sources == 0) return ICPB200_OK;
+    long long max_s;
+    if ((rc = check_offsets(src_off, n_sources, "src_off", &max_s))) return rc;
+    if ((rc = init_locked(-1))) return rc;
+    Context& c = g_ctx;
+    long long m = 0;
+    if ((rc = submap_build(c, *sm, submap_voxel, &m, c.stream))) return rc;
+    if (m <= 0) { set_error("icpb200_submap_icp: the submap is empty"); return ICPB200_ERR_ARG; }
+    const int dim = sm->dim;
+    const size_t ns = (size_t)src_off[n_sources];
+    if (c.pts_a.reserve(sizeof(double) * dim * ns) || c.off_a.reserve(sizeof(int64_t) * ((size_t)n_sources + 1)) ||
+        c.idx_b.reserve(sizeof(int32_t) * (size_t)n_sources))
+        return ICPB200_ERR_CUDA;
+    if ((rc = reserve_outputs(c, n_sources, dim))) return rc;
+    ICPB_CUDA(cudaMemcpyAsync(c.pts_a.p, src, sizeof(double) * dim * ns, cudaMemcpyHostToDevice, c.stream));
+    ICPB_CUDA(cudaMemcpyAsync(c.off_a.p, src_off, sizeof(int64_t) * ((size_t)n_sources + 1), cudaMemcpyHostToDevice, c.stream));
+    ICPB_CUDA(cudaMemsetAsync(c.idx_b.p, 0, sizeof(int32_t) * (size_t)n_sources, c.stream));       // every pair: target cloud 0
+    const double *d_Ri, *d_ti;
+    if ((rc = upload_init(c, n_sources, dim, R_init, t_init, &d_Ri, &d_ti))) return rc;
+    const int64_t h_toff[2] = {0, m};
+    const DevClouds s{c.pts_a.as<double>(), c.off_a.as<long long>(), src_off, n_sources, max_s, max_s, (long long)ns};
+    const DevClouds t{sm->built.as<double>(), sm->built_off.as<long long>(), h_toff, 1, m, m, m};
+    if (sm->prep_version != sm->version) { sm->prep.ready = false; sm->prep_version = sm->version; }
+    rc = icp_enqueue(k, n_sources, s, t, false, nullptr, c.idx_b.as<int>(), d_Ri, d_ti, c.out_r.as<double>(), c.out_t.as<double>(),
+                     c.out_err.as<double>(), c.out_prev.as<double>(), c.out_iters.as<int>(), c.out_status.as<int>(),
+                     c.stream, IcpTrace{}, nullptr, nullptr, &sm->prep);
+    if (rc) { cudaStreamSynchronize(c.stream); return rc; }
+    return fetch_outputs(c, n_sources, dim, IcpOutputs{R_out, t_out, err_out, prev_err_out, iters_out, status_out});
 }
 
 int icpb200_grid_last_stats(void* grid, int64_t* stats4) {

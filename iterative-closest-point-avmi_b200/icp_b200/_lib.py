@@ -64,6 +64,14 @@ PROTOTYPES = {
     "icpb200_grid_device_ptr": (ctypes.c_void_p, [ctypes.c_void_p]),
     "icpb200_grid_tile_profile": (ctypes.c_int, [ctypes.c_void_p, c_int64_p, ctypes.c_int64]),
     "icpb200_grid_last_stats": (ctypes.c_int, [ctypes.c_void_p, c_int64_p]),
+    "icpb200_submap_create": (ctypes.c_void_p, [ctypes.c_int, ctypes.c_int]),
+    "icpb200_submap_destroy": (None, [ctypes.c_void_p]),
+    "icpb200_submap_push": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int64]),
+    "icpb200_submap_clear": (ctypes.c_int, [ctypes.c_void_p]),
+    "icpb200_submap_size": (ctypes.c_int, [ctypes.c_void_p, c_int64_p, c_int64_p]),
+    "icpb200_submap_build": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, c_double_p, ctypes.c_int64, c_int64_p]),
+    "icpb200_submap_icp": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_int, c_double_p, c_int64_p, c_double_p,
+                                          c_double_p] + _ICP_TAIL + _ICP_OUT),
     "icpb200_rotation_scores": (ctypes.c_int, [ctypes.c_int, c_double_p, c_int64_p, c_double_p, c_int64_p, c_double_p,
                                                c_int64_p, c_double_p, c_double_p, c_double_p, c_int32_p]),
     "icpb200_pin_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),

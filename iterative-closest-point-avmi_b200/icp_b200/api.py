@@ -310,3 +310,72 @@ class DeviceGrid:
         st = np.zeros(4, dtype=np.int64)
         check(self._lib.icpb200_grid_last_stats(self._h, _ptr(st, c_int64_p)), "icpb200_grid_last_stats")
         return dict(rays=int(st[0]), traversed=int(st[1]), hits=int(st[2]), runs=int(st[3]))
+
+
+class DeviceSubmap:
+    """The rolling window of global-frame scans (slam.py:559-562), resident on the device.
+
+    ``append`` / ``pop`` / ``clear`` / ``len`` mirror the list the reference keeps (``submap_buffer``); ``build(voxel)`` is
+    ``_build_submap`` (slam.py:103-108: vstack + voxel_downsample) and ``icp(...)`` is ``ICP(scan, build(voxel), ...)``
+    (slam.py:217-225) without the 52k-point target ever crossing PCIe again: the window's two downsamples and its hash
+    grid are computed on the device and cached until the window changes."""
+
+    def __init__(self, capacity_scans=40, dim=2):
+        self._lib = _lib.load()
+        self.dim, self.capacity = int(dim), int(capacity_scans)
+        self._h = self._lib.icpb200_submap_create(self.dim, self.capacity)
+        if not self._h:
+            raise RuntimeError(f"icpb200_submap_create failed: {_lib.last_error()}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.icpb200_submap_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def append(self, points):
+        pts = _f64(points).reshape(-1, self.dim)
+        check(self._lib.icpb200_submap_push(self._h, _ptr(pts, c_double_p), pts.shape[0]), "icpb200_submap_push")
+
+    def clear(self):
+        check(self._lib.icpb200_submap_clear(self._h), "icpb200_submap_clear")
+
+    def size(self):
+        a, b = ctypes.c_int64(0), ctypes.c_int64(0)
+        check(self._lib.icpb200_submap_size(self._h, ctypes.byref(a), ctypes.byref(b)), "icpb200_submap_size")
+        return int(a.value), int(b.value)
+
+    def __len__(self):
+        return self.size()[0]
+
+    def build(self, voxel_size, fetch=True):
+        """``voxel_downsample(np.vstack(window), voxel_size)``; ``fetch=False`` only returns the row count."""
+        n = ctypes.c_int64(0)
+        cap = self.size()[1]
+        out = np.empty((cap, self.dim)) if fetch else None
+        check(self._lib.icpb200_submap_build(self._h, float(voxel_size), _ptr(out, c_double_p) if fetch else None, cap,
+                                             ctypes.byref(n)), "icpb200_submap_build")
+        return out[:int(n.value)].copy() if fetch else int(n.value)
+
+    def icp(self, sources, submap_voxel, error_threshold, max_iterations, voxel_size, R_init=None, t_init=None,
+            method="point_to_point", normal_k=10, max_corr_dist=None, nn_mode="auto"):
+        """Register every cloud of ``sources`` (a list, or one (N, dim) array) onto the window's submap."""
+        single = isinstance(sources, np.ndarray) and sources.ndim == 2
+        clouds = [sources] if single else list(sources)
+        from .synth import pack_ragged
+        src, off = pack_ragged([_f64(s) for s in clouds], self.dim)
+        n = len(clouds)
+        r0, t0 = _init_arrays(R_init, t_init, n, self.dim)
+        R, t, err, prev, iters, status = _alloc_out(n, self.dim)
+        check(self._lib.icpb200_submap_icp(
+            self._h, float(submap_voxel), n, _ptr(src, c_double_p), _ptr(off, c_int64_p), _ptr(r0, c_double_p), _ptr(t0, c_double_p),
+            float(error_threshold), int(max_iterations), float(voxel_size), _method_code(method), int(normal_k),
+            -1.0 if max_corr_dist is None else float(max_corr_dist), NN_MODES[nn_mode],
+            _ptr(R, c_double_p), _ptr(t, c_double_p), _ptr(err, c_double_p), _ptr(prev, c_double_p), _ptr(iters, c_int32_p),
+            _ptr(status, c_int32_p)), "icpb200_submap_icp")
+        return dict(R=R, t=t, error=err, prev_error=prev, iters=iters, status=status)

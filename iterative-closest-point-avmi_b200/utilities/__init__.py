@@ -30,9 +30,10 @@ from .icp import ICP, voxel_downsample                                      # no
 from .mapping import OccupancyGrid2D                                        # noqa: E402
 from .features import rotation_search, submap_rotation_search               # noqa: E402
 from .features import feature_based_alignment                               # noqa: E402  (the reference's, when it is on the path)
+from .submap import DeviceSubmap                                            # noqa: E402
 
 __all__ = ["ICP", "voxel_downsample", "OccupancyGrid2D", "rotation_search", "submap_rotation_search",
-           "feature_based_alignment"]
+           "feature_based_alignment", "DeviceSubmap"]
 
 if len(__path__) > 1:                                                       # utilities/__init__.py:4-9 of the reference
     try:
