@@ -852,21 +852,21 @@ def bench_extras(args, api):
     src1 = flat[off[1]:off[2]]
     with contextlib.redirect_stdout(io.StringIO()):
         t0 = time.perf_counter()
-        first = sm.ICP(src1, 1e-7, 1e-10, 150, 0.04, R_init=R1, t_init=t1, method="point_to_point", max_corr_dist=1.5)
+        first = sm.ICP(src1, 1e-4, 1e-10, 150, 0.04, R_init=R1, t_init=t1, method="point_to_point", max_corr_dist=1.5)
         first_ms = (time.perf_counter() - t0) * 1e3
         lat = []
         for k in range(20):
             t0 = time.perf_counter()
-            again = sm.ICP(src1, 1e-7, 1e-10, 150, 0.04, R_init=R1, t_init=t1, method="point_to_point", max_corr_dist=1.5)
+            again = sm.ICP(src1, 1e-4, 1e-10, 150, 0.04, R_init=R1, t_init=t1, method="point_to_point", max_corr_dist=1.5)
             lat.append(time.perf_counter() - t0)
         t0 = time.perf_counter()
         sm.append(target[:step] + 1e-3)
-        moved = sm.ICP(src1, 1e-7, 1e-10, 150, 0.04, R_init=R1, t_init=t1, method="point_to_point", max_corr_dist=1.5)
+        moved = sm.ICP(src1, 1e-4, 1e-10, 150, 0.04, R_init=R1, t_init=t1, method="point_to_point", max_corr_dist=1.5)
         push_ms = (time.perf_counter() - t0) * 1e3
     out["F2_device_resident_submap"] = dict(window_scans=40, window_points=int(sm.size()[1]),
                                             call_ms_window_unchanged=float(np.median(lat)) * 1e3, first_call_ms=first_ms,
                                             push_plus_call_ms=push_ms, single_call_ms_host_target=one_t * 1e3,
-                                            note="ICP(scan, submap) with the window resident on the device (submap voxel 1e-7: the window "
+                                            note="ICP(scan, submap) with the window resident on the device (submap voxel 1e-4: the window "
                                                  "itself is the target, as in C3): unchanged window -> cached downsample + hash grid, the call "
                                                  "is source upload + pair kernel; after a push both downsamples and the grid are redone on the "
                                                  "device (no 52k-point upload)")

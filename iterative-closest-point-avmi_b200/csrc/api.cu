@@ -1345,7 +1345,7 @@ int icpb200_pin_host(void* ptr, size_t bytes) {
     if (!ptr || bytes == 0) { set_error("icpb200_pin_host: null pointer or empty range"); return ICPB200_ERR_ARG; }
     int rc = init_locked(-1);
     if (rc) return rc;
-    ICPB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    ICPB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));      // mapped: read-outs may write it in place
     return ICPB200_OK;
 }
 

@@ -1046,6 +1046,28 @@ __global__ void __launch_bounds__(256) occ_pack_tiles(const float* __restrict__ 
     }
 }
 
+// The caller's array is page-locked (icpb200_pin_host): every touched tile is written straight to its place in host memory
+// over PCIe, 256-byte row segments at a time -- no staging block, no list of tiles on the host, no scatter by the CPU.
+__global__ void __launch_bounds__(256) occ_write_tiles_mapped(const float* __restrict__ grid, int nx, int ny, int tiles_x,
+                                                              const unsigned char* __restrict__ dirty, float* __restrict__ host_out,
+                                                              unsigned* __restrict__ count, int view) {
+    const int t = blockIdx.x;
+    if (!dirty[t]) return;
+    if (threadIdx.x == 0) atomicAdd(count, 1u);
+    const int tx0 = (t % tiles_x) * TS, ty0 = (t / tiles_x) * TS;
+    for (int c4 = threadIdx.x; c4 < TCELLS / 4; c4 += 256) {
+        const int x = tx0 + (c4 % (TS / 4)) * 4, y = ty0 + c4 / (TS / 4);
+        if (y >= ny || x >= nx) continue;
+        const size_t at = (size_t)y * nx + x;
+        if (x + 3 < nx && (at & 3) == 0) {
+            const float4 v = *reinterpret_cast<const float4*>(grid + at);
+            *reinterpret_cast<float4*>(host_out + at) = make_float4(occ_view(v.x, view), occ_view(v.y, view), occ_view(v.z, view), occ_view(v.w, view));
+        } else {
+            for (int u = 0; u < 4 && x + u < nx; ++u) host_out[at + u] = occ_view(grid[at + u], view);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) occ_view_all(const float* __restrict__ grid, float* __restrict__ out, size_t n, int view) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         out[i] = occ_view(grid[i], view);
@@ -1078,6 +1100,25 @@ int occ_read_view(OccGrid& g, float* out, int view, bool dirty_only, int* tiles_
         }
         ICPB_CUDA(cudaStreamSynchronize(st));
         return ICPB200_OK;
+    }
+    {   // page-locked destination: the device writes the touched tiles in place
+        cudaPointerAttributes attr;
+        void* d_out = nullptr;
+        if (cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+            cudaHostGetDevicePointer(&d_out, out, 0) == cudaSuccess && d_out) {
+            if (g.small.reserve(256)) return ICPB200_ERR_CUDA;
+            unsigned* d_count = g.small.as<unsigned>() + 48;
+            ICPB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned), st));
+            occ_write_tiles_mapped<<<(unsigned)n_tiles, 256, 0, st>>>(g.grid.as<float>(), g.nx, g.ny, tiles_x, g.dirty.as<unsigned char>(),
+                                                                        static_cast<float*>(d_out), d_count, view);
+            ICPB_LAUNCH_CHECK();
+            unsigned n = 0;
+            ICPB_CUDA(cudaMemcpyAsync(&n, d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            ICPB_CUDA(cudaStreamSynchronize(st));
+            if (tiles_out) *tiles_out = (int)n;
+            return ICPB200_OK;
+        }
+        cudaGetLastError();                                      // a pageable destination is not an error: staging path below
     }
     int rc = ensure_host_stage(g, (size_t)n_tiles * (1 + sizeof(int)));
     if (rc) return rc;
