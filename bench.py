@@ -639,6 +639,7 @@ def bench_raycast(args, lib, api, dev, local_rank, pk, rank=0, world=1, verify=F
     grid = OccupancyGrid2D(*GRID_BOUNDS, **GRID_CFG)
     if world > 1:
         grid._dev.set_shard(rank, world)
+        icpd.grid_share_setup(grid._dev)            # CUDA IPC handles of every rank's grid, once
     d_org = torch.from_numpy(origins).to(dev)
     d_hits = torch.from_numpy(flat).to(dev)
     d_off = torch.from_numpy(off).to(dev)
@@ -663,7 +664,7 @@ def bench_raycast(args, lib, api, dev, local_rank, pk, rank=0, world=1, verify=F
                                  stream.cuda_stream)
             m.record(stream)
             if world > 1:
-                icpd.grid_gather_device(grid._dev, sync=False)      # stream-ordered behind the update
+                icpd.grid_push_device(grid._dev, stream.cuda_stream)   # touched tiles -> every peer's grid (NVLink peer stores) + barrier
             b.record(stream)
             torch.cuda.synchronize()
             if k >= 3:
@@ -683,14 +684,12 @@ def bench_raycast(args, lib, api, dev, local_rank, pk, rank=0, world=1, verify=F
         t0 = time.perf_counter()
         grid._dev.update(origins, flat, off)
         if world > 1:
-            icpd.grid_gather_device(grid._dev)
-        if rank == 0:                                   # one consumer reads the map: one GPU -> only the tiles the scans touched
-            if world > 1:
-                grid._dev.read(host_out)                # (reassembled from every rank's bands: the whole map)
-            else:
-                if k == 0:
-                    host_out[...] = 0.0                 # the caller's mirror; untouched tiles are never written again
-                grid._dev.read_dirty(host_out)
+            icpd.grid_push_device(grid._dev, stream.cuda_stream)
+            torch.cuda.synchronize()
+        if rank == 0:                                   # one consumer reads the map: only the tiles the scans touched
+            if k == 0:
+                host_out[...] = 0.0                     # the caller's mirror; untouched tiles are never written again
+            grid._dev.read_dirty(host_out)
         if k >= 1:
             e2e_t.append(time.perf_counter() - t0)
     e2e_s = float(np.mean(e2e_t))
@@ -728,13 +727,13 @@ def bench_raycast(args, lib, api, dev, local_rank, pk, rank=0, world=1, verify=F
                 config=dict(workload=f"C4 occupancy log-odds raycast: {len(off) - 1} scans, {n_rays} rays, "
                                      f"{grid.nx}x{grid.ny} grid @ 0.05 m, campus world", **GRID_CFG,
                             cells_per_ray=cells / n_rays, tile_runs=st["runs"],
-                            sharding="bands of 64 rows dealt round-robin over the GPUs; every rank walks every ray clipped to its own bands, in scan order; one NCCL all_gather of the packed bands inside the timed region (update_only_ms = the slowest rank's update without it, gather_ms = the rest); e2e: one rank reads the reassembled map"),
+                            sharding="bands of 64 rows dealt round-robin over the GPUs; every rank walks every ray clipped to its own bands, in scan order; then every rank stores the tiles it touched into every peer's grid (NVLink peer stores through CUDA IPC mappings, icpb200_grid_push_tiles) and a one-element all_reduce is the barrier -- both inside the timed region (update_only_ms = the slowest rank's update without them, gather_ms = the rest); e2e: one rank reads the touched tiles of the reassembled map"),
                 e2e=dict(value=n_rays / e2e_s, unit="rays/s",
                          h2d_bytes_per_step=int(origins.nbytes + flat.nbytes + off.nbytes),
-                         d2h_bytes_per_step=int(host_out.nbytes if world > 1 else grid._dev.last_tiles_copied * 64 * 64 * 4),
-                         api="icpb200_grid_update + icpb200_grid_read" if world > 1 else
-                             "icpb200_grid_update + icpb200_grid_read_view(log-odds, touched tiles only) into the caller's mirror",
-                         tiles_copied=None if world > 1 else int(grid._dev.last_tiles_copied)),
+                         d2h_bytes_per_step=int(grid._dev.last_tiles_copied * 64 * 64 * 4),
+                         api="icpb200_grid_update (+ icpb200_grid_push_tiles and a barrier at N > 1) + icpb200_grid_read_view(log-odds, "
+                             "touched tiles only) into the caller's page-locked mirror",
+                         tiles_copied=int(grid._dev.last_tiles_copied)),
                 gpu_launches=int(launches),
                 verify=checked,
                 roofline=dict(bound="hbm", achieved=alg_bytes / sec / 1e9 / world, peak=pk["hbm_gbs"], unit="GB/s",

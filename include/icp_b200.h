@@ -248,7 +248,21 @@ int icpb200_grid_read(void *grid, float *out);
 int icpb200_grid_read_view(void *grid, int view, int dirty_only, float *out, int32_t *tiles_copied);
 /* mapping.py:143-145 */
 int icpb200_grid_reset(void *grid);
-/* Raw device pointer of the ny*nx float32 grid (for NCCL reductions issued by
+/* Multi-GPU exchange of touched tiles by peer stores over NVLink (one process per
+ * GPU on one node).  Every rank exports CUDA IPC handles of its grid and of its
+ * touched-tile flags (2 x 64 bytes), the host framework gathers the handles of
+ * all ranks (icp_b200.dist.grid_share_setup does it with one all_gather) and
+ * every rank attaches them (rank-major, world x 128 bytes; call after
+ * icpb200_grid_set_shard).  icpb200_grid_push_tiles then stores every tile this
+ * rank owns and has touched since its last push into the same place of every
+ * peer's grid and marks it touched there -- one kernel, stream-ordered, no
+ * staging, only the explored part of the map moves.  A cross-rank barrier after
+ * the push (any stream-ordered collective) makes the tiles visible to the
+ * peers' readers; icpb200_grid_reset on all ranks must not overlap a peer's push. */
+int icpb200_grid_ipc_export(void *grid, unsigned char *handles128);
+int icpb200_grid_ipc_attach(void *grid, int world, int rank, const unsigned char *handles);
+int icpb200_grid_push_tiles(void *grid, void *stream);
+/* Raw device pointer of the ny*nx float32 grid (for NCCL collectives issued by
  * the host framework). */
 void *icpb200_grid_device_ptr(void *grid);
 /* Counters of the most recent update call: stats[0] = rays, stats[1] =

@@ -1112,6 +1112,11 @@ void OccGrid::release_all() {
     if (pending_host) { cudaFreeHost(pending_host); pending_host = nullptr; }
     if (h_in_pack) { cudaFreeHost(h_in_pack); h_in_pack = nullptr; h_in_cap = 0; }
     if (h_pack) { cudaFreeHost(h_pack); h_pack = nullptr; h_pack_cap = 0; }
+    if (peers_attached) {
+        for (int p = 0; p < world && p < 16; ++p)
+            if (p != rank) { if (peer_grid[p]) cudaIpcCloseMemHandle(peer_grid[p]); if (peer_dirty[p]) cudaIpcCloseMemHandle(peer_dirty[p]); }
+        peers_attached = false;
+    }
     stats_pending = false;
 }
 
@@ -1321,6 +1326,53 @@ int icpb200_grid_read_view(void* grid, int view, int dirty_only, float* out, int
     rc = occ_read_view(*g, out, view, dirty_only != 0, &n, g_ctx.stream);
     if (tiles_copied) *tiles_copied = n;
     return rc;
+}
+
+int icpb200_grid_ipc_export(void* grid, unsigned char* handles128) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!grid || !handles128) { set_error("icpb200_grid_ipc_export: null pointer"); return ICPB200_ERR_ARG; }
+    int rc = init_locked(-1);
+    if (rc) return rc;
+    OccGrid* g = static_cast<OccGrid*>(grid);
+    if ((rc = occ_ensure_dirty(*g, g_ctx.stream))) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h0, h1;
+    ICPB_CUDA(cudaIpcGetMemHandle(&h0, g->grid.p));
+    ICPB_CUDA(cudaIpcGetMemHandle(&h1, g->dirty.p));
+    memcpy(handles128, &h0, 64);
+    memcpy(handles128 + 64, &h1, 64);
+    return ICPB200_OK;
+}
+
+int icpb200_grid_ipc_attach(void* grid, int world, int rank, const unsigned char* handles) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!grid || !handles || world < 1 || world > 16 || rank < 0 || rank >= world) {
+        set_error("icpb200_grid_ipc_attach: null pointer or bad rank / world (at most 16 ranks)");
+        return ICPB200_ERR_ARG;
+    }
+    int rc = init_locked(-1);
+    if (rc) return rc;
+    OccGrid* g = static_cast<OccGrid*>(grid);
+    if (g->world != world || g->rank != rank) { set_error("icpb200_grid_ipc_attach: call icpb200_grid_set_shard(rank, world) first"); return ICPB200_ERR_ARG; }
+    for (int p = 0; p < world; ++p) {
+        if (p == rank) { g->peer_grid[p] = g->grid.p; g->peer_dirty[p] = g->dirty.p; continue; }
+        cudaIpcMemHandle_t h0, h1;
+        memcpy(&h0, handles + (size_t)p * 128, 64);
+        memcpy(&h1, handles + (size_t)p * 128 + 64, 64);
+        ICPB_CUDA(cudaIpcOpenMemHandle(&g->peer_grid[p], h0, cudaIpcMemLazyEnablePeerAccess));
+        ICPB_CUDA(cudaIpcOpenMemHandle(&g->peer_dirty[p], h1, cudaIpcMemLazyEnablePeerAccess));
+    }
+    g->peers_attached = true;
+    return ICPB200_OK;
+}
+
+int icpb200_grid_push_tiles(void* grid, void* stream) {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (!grid) { set_error("icpb200_grid_push_tiles: null handle"); return ICPB200_ERR_ARG; }
+    int rc = init_locked(-1);
+    if (rc) return rc;
+    OccGrid* g = static_cast<OccGrid*>(grid);
+    return occ_push_to_peers(*g, stream ? (cudaStream_t)stream : g_ctx.stream);
 }
 
 void* icpb200_grid_device_ptr(void* grid) {

@@ -47,6 +47,10 @@ struct OccGrid {
     // read-out: tiles (64 x 64 cells) touched since the last reset; the ordered path does not track them (all_dirty)
     DevBuf dirty, pack, pack_ids;
     bool all_dirty = false;
+    // multi-GPU: the peers' grids and touched-tile flags, mapped through CUDA IPC (icpb200_grid_ipc_attach)
+    void* peer_grid[16] = {};
+    void* peer_dirty[16] = {};
+    bool peers_attached = false;
     unsigned char* h_pack = nullptr;               // page-locked staging of the packed tiles
     size_t h_pack_cap = 0;
     cudaStream_t aux_stream = nullptr;             // the hit cells' replay runs here, under the remaining tiles
@@ -81,6 +85,9 @@ int occ_collect(OccGrid& g);
 // Read-out as log-odds (view 0), probability (1) or display value (2), mapping.py:150-160; dirty_only copies just the tiles
 // touched since the last reset (occupancy_fast.cu).
 int occ_read_view(OccGrid& g, float* out, int view, bool dirty_only, int* tiles_out, cudaStream_t st);
+// multi-GPU exchange of touched tiles by peer stores (occupancy_fast.cu)
+int occ_push_to_peers(OccGrid& g, cudaStream_t st);
+int occ_ensure_dirty(OccGrid& g, cudaStream_t st);
 // slam.py:46-50 for every scan of a history: world = local @ R.T + t, origin = t (device pointers)
 int occ_transform_history(int n_scans, long long n_points, const double* d_poses, const double* d_local,
                           const long long* d_off, double* d_world, double* d_origins, cudaStream_t st);

@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(1024) occ_tile_scan(const unsigned* __restrict
         uint4 cc = make_uint4(0u, 0u, 0u, 0u), cd = cc;
         if (t < n_tiles) { cc = reinterpret_cast<const uint4*>(counts)[2 * t]; cd = reinterpret_cast<const uint4*>(counts)[2 * t + 1]; }
         const unsigned v = cc.x + cc.y + cc.z + cc.w + cd.x + cd.y + cd.z + cd.w;
-        if (t < n_tiles && (v || tile_flag[t])) dirty[t] = 1;       // touched since the last reset (icpb200_grid_read_view copies only these)
+        if (t < n_tiles && (v || tile_flag[t])) dirty[t] = 3;       // bit 0: touched since the last reset (read-out); bit 1: since the last push to the peers
         if (v) atomicAdd(&hist[tile_flag[t] ? 0 : 1][32 - __clz(v)], (int)((v + kItemRuns - 1) / kItemRuns));
         unsigned inc = v;
 #pragma unroll
@@ -1052,7 +1052,7 @@ __global__ void __launch_bounds__(256) occ_write_tiles_mapped(const float* __res
                                                               const unsigned char* __restrict__ dirty, float* __restrict__ host_out,
                                                               unsigned* __restrict__ count, int view) {
     const int t = blockIdx.x;
-    if (!dirty[t]) return;
+    if (!(dirty[t] & 1)) return;
     if (threadIdx.x == 0) atomicAdd(count, 1u);
     const int tx0 = (t % tiles_x) * TS, ty0 = (t / tiles_x) * TS;
     for (int c4 = threadIdx.x; c4 < TCELLS / 4; c4 += 256) {
@@ -1066,6 +1066,72 @@ __global__ void __launch_bounds__(256) occ_write_tiles_mapped(const float* __res
             for (int u = 0; u < 4 && x + u < nx; ++u) host_out[at + u] = occ_view(grid[at + u], view);
         }
     }
+}
+
+// ---- multi-GPU: push the touched tiles this rank owns straight into every peer's grid (NVLink peer stores) ------------
+// The map is sharded by bands of 64 rows (occ_owner); a tile is written by exactly one rank.  Instead of gathering whole
+// bands (64 MiB through NCCL plus pack / unpack copies) every rank stores the tiles it has touched since its last push
+// into the same place of every peer's grid, whose device pointers were exchanged once (CUDA IPC handles): the exchange
+// moves the explored part of the map only, in one kernel, with no staging.  The peers' touched-tile flags are set as well,
+// so their read-outs see the tiles.  A cross-rank barrier after the push is the caller's (icp_b200.dist.grid_push_device).
+struct PeerTable {
+    float* grid[16];
+    unsigned char* dirty[16];
+};
+
+__global__ void __launch_bounds__(256) occ_push_tiles(const float* __restrict__ grid, int nx, int ny, int tiles_x, int rank, int world,
+                                                      unsigned char* __restrict__ dirty, const PeerTable peers, int push_all,
+                                                      unsigned* __restrict__ count) {
+    const int t = blockIdx.x;
+    const int ty0 = (t / tiles_x) * TS, tx0 = (t % tiles_x) * TS;
+    if (occ_owner(tx0, ty0, nx, ny, world) != rank) return;
+    const unsigned char flag = dirty[t];
+    if (!push_all && !(flag & 2)) return;
+    if (threadIdx.x == 0) atomicAdd(count, 1u);
+    for (int c4 = threadIdx.x; c4 < TCELLS / 4; c4 += 256) {
+        const int x = tx0 + (c4 % (TS / 4)) * 4, y = ty0 + c4 / (TS / 4);
+        if (y >= ny || x >= nx) continue;
+        const size_t at = (size_t)y * nx + x;
+        if (x + 3 < nx && (at & 3) == 0) {
+            const float4 v = *reinterpret_cast<const float4*>(grid + at);
+            for (int p = 0; p < world; ++p)
+                if (p != rank) *reinterpret_cast<float4*>(peers.grid[p] + at) = v;
+        } else {
+            for (int u = 0; u < 4 && x + u < nx; ++u)
+                for (int p = 0; p < world; ++p)
+                    if (p != rank) peers.grid[p][at + u] = grid[at + u];
+        }
+    }
+    if (threadIdx.x == 0) {
+        for (int p = 0; p < world; ++p)
+            if (p != rank) peers.dirty[p][t] = (unsigned char)(peers.dirty[p][t] | 1);    // (only this rank ever writes tile t's flag on a peer)
+        dirty[t] = (unsigned char)(flag & ~2);
+    }
+}
+
+int occ_push_to_peers(OccGrid& g, cudaStream_t st) {
+    if (g.world <= 1) return ICPB200_OK;
+    if (!g.peers_attached) { set_error("icpb200_grid_push_tiles: icpb200_grid_ipc_attach has not been called"); return ICPB200_ERR_ARG; }
+    const int tiles_x = (g.nx + TS - 1) / TS, tiles_y = (g.ny + TS - 1) / TS, n_tiles = tiles_x * tiles_y;
+    if (g.small.reserve(256)) return ICPB200_ERR_CUDA;
+    PeerTable pt;
+    for (int p = 0; p < 16; ++p) { pt.grid[p] = static_cast<float*>(g.peer_grid[p]); pt.dirty[p] = static_cast<unsigned char*>(g.peer_dirty[p]); }
+    unsigned* d_count = g.small.as<unsigned>() + 49;
+    ICPB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned), st));
+    occ_push_tiles<<<(unsigned)n_tiles, 256, 0, st>>>(g.grid.as<float>(), g.nx, g.ny, tiles_x, g.rank, g.world, g.dirty.as<unsigned char>(), pt,
+                                                       g.all_dirty ? 1 : 0, d_count);
+    ICPB_LAUNCH_CHECK();
+    return ICPB200_OK;
+}
+
+int occ_ensure_dirty(OccGrid& g, cudaStream_t st) {
+    const int n_tiles = ((g.nx + TS - 1) / TS) * ((g.ny + TS - 1) / TS);
+    if (!g.dirty.p) {
+        if (g.dirty.reserve((size_t)n_tiles)) return ICPB200_ERR_CUDA;
+        ICPB_CUDA(cudaMemsetAsync(g.dirty.p, 0, g.dirty.cap, st));
+        ICPB_CUDA(cudaStreamSynchronize(st));
+    }
+    return ICPB200_OK;
 }
 
 __global__ void __launch_bounds__(256) occ_view_all(const float* __restrict__ grid, float* __restrict__ out, size_t n, int view) {
@@ -1127,7 +1193,7 @@ int occ_read_view(OccGrid& g, float* out, int view, bool dirty_only, int* tiles_
     ICPB_CUDA(cudaStreamSynchronize(st));
     std::vector<int> ids;
     ids.reserve(1024);
-    for (int t = 0; t < n_tiles; ++t) if (h_dirty[t]) ids.push_back(t);
+    for (int t = 0; t < n_tiles; ++t) if (h_dirty[t] & 1) ids.push_back(t);
     const size_t n = ids.size();
     if (tiles_out) *tiles_out = (int)n;
     if (n == 0) return ICPB200_OK;

@@ -61,6 +61,9 @@ PROTOTYPES = {
     "icpb200_grid_read_view": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_float_p, c_int32_p]),
     "icpb200_grid_reset": (ctypes.c_int, [ctypes.c_void_p]),
     "icpb200_grid_rebuild": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_double_p, c_double_p, c_int64_p]),
+    "icpb200_grid_ipc_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
+    "icpb200_grid_ipc_attach": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]),
+    "icpb200_grid_push_tiles": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "icpb200_grid_device_ptr": (ctypes.c_void_p, [ctypes.c_void_p]),
     "icpb200_grid_tile_profile": (ctypes.c_int, [ctypes.c_void_p, c_int64_p, ctypes.c_int64]),
     "icpb200_grid_last_stats": (ctypes.c_int, [ctypes.c_void_p, c_int64_p]),

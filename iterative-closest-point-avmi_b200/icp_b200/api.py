@@ -233,6 +233,7 @@ class DeviceGrid:
     def __init__(self, nx, ny, min_x, min_y, resolution, l_hit, l_miss, lo_min, lo_max):
         self.nx, self.ny = int(nx), int(ny)
         self.sharded = False
+        self.peers_attached = False
         self.last_tiles_copied = 0
         self._lib = _lib.load()
         self._h = self._lib.icpb200_grid_create(self.nx, self.ny, float(min_x), float(min_y), float(resolution),
@@ -302,6 +303,19 @@ class DeviceGrid:
 
     def reset(self):
         check(self._lib.icpb200_grid_reset(self._h), "icpb200_grid_reset")
+
+    def ipc_export(self):
+        buf = ctypes.create_string_buffer(128)
+        check(self._lib.icpb200_grid_ipc_export(self._h, buf), "icpb200_grid_ipc_export")
+        return buf.raw
+
+    def ipc_attach(self, world, rank, handles):
+        assert len(handles) == 128 * int(world)
+        check(self._lib.icpb200_grid_ipc_attach(self._h, int(world), int(rank), bytes(handles)), "icpb200_grid_ipc_attach")
+        self.peers_attached = True
+
+    def push_tiles(self, stream=0):
+        check(self._lib.icpb200_grid_push_tiles(self._h, stream), "icpb200_grid_push_tiles")
 
     def device_ptr(self):
         return int(self._lib.icpb200_grid_device_ptr(self._h) or 0)
