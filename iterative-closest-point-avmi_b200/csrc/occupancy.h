@@ -17,9 +17,12 @@ constexpr size_t kOccOrdBudget = 1ull << 30;       // order-free path: (hit cell
 // eight contiguous strips carried 44 % of the traversed cells); neighbouring bands see nearly the same load, so dealing
 // them out balances the ranks, and a ray is still clipped to a band in closed form: a rank walks only the parts of every
 // ray that cross its own bands.  Both device paths use this one rule, so a cell never changes owner between calls.
+__host__ __device__ inline int occ_mod_world(int b, int world) {       // b >= 0; the usual rank counts are powers of two
+    return (world & (world - 1)) == 0 ? (b & (world - 1)) : b % world;
+}
 __host__ __device__ inline int occ_owner(int x, int y, int nx, int ny, int world) {
     (void)x; (void)nx; (void)ny;
-    return (y / kOccOwnTile) % world;
+    return occ_mod_world(y / kOccOwnTile, world);
 }
 
 struct OccGrid {

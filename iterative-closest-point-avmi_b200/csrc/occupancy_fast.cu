@@ -134,7 +134,7 @@ struct FastTileIter {
         ylo = max(ylo, 0); yhi = min(yhi, ny - 1);
         const int blo = ylo / TS;
         band_last = yhi / TS;
-        band = blo + ((rank - blo) % world + world) % world;      // first owned band at or after blo
+        band = blo + occ_mod_world(rank - blo + (blo / world + 1) * world, world);      // first owned band at or after blo
     }
     __device__ __forceinline__ int minor_at(int nn) const {
         if (small) return (int)((2u * (unsigned)nn * (unsigned)g.dmin + (unsigned)g.dmaj - 1u) / (2u * (unsigned)g.dmaj));
@@ -207,6 +207,21 @@ __global__ void __launch_bounds__(256, 8) occ_fast_rays(const FastArgs a) {
     const long long r = a.ray_begin + rl;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
+    __shared__ int cta_scan0_s;
+    int cta_scan0 = 0;
+    if (!FILL) {
+        if (threadIdx.x == 0) {
+            const long long r0 = a.ray_begin + (long long)blockIdx.x * blockDim.x;
+            int lo = a.scan_begin, hi = a.scan_begin + a.chunk_scans;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (a.hit_off[mid] <= r0) lo = mid; else hi = mid;
+            }
+            cta_scan0_s = lo;
+        }
+        __syncthreads();
+        cta_scan0 = cta_scan0_s;
+    }
     unsigned long long cells = 0, nhits = 0, nruns = 0;
     FastTileIter<SHARDED> it;
     it.init_empty();
@@ -219,12 +234,11 @@ __global__ void __launch_bounds__(256, 8) occ_fast_rays(const FastArgs a) {
             const double2 p = a.hits[r];
             // mapping.py:94-98
             h = make_int2(sat_cell(floor((p.x - a.min_x) / a.res)), sat_cell(floor((p.y - a.min_y) / a.res)));
-            int lo = a.scan_begin, hi = a.scan_begin + a.chunk_scans;      // largest s with hit_off[s] <= r
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (a.hit_off[mid] <= r) lo = mid; else hi = mid;
-            }
-            s = lo;
+            // largest s with hit_off[s] <= r: one binary search per CTA (its first ray), then a short walk -- the rays of
+            // a CTA belong to one or two scans
+            s = cta_scan0;
+            const int s_end = a.scan_begin + a.chunk_scans;
+            while (s + 1 < s_end && a.hit_off[s + 1] <= r) ++s;
             a.ray_cell[rl] = h;
             a.ray_scan[rl] = s;
         } else {
@@ -324,13 +338,14 @@ __global__ void __launch_bounds__(256, 8) occ_fast_rays(const FastArgs a) {
 // Work items: a tile's runs are cut into pieces of at most kItemRuns, so that the busiest
 // tiles (tens of thousands of runs) do not set the length of the tile kernel.  Tiles with
 // several items combine their partial counts in a global per-cell counter (`multi` lists them).
-constexpr unsigned kItemRuns = 2048;
+constexpr unsigned kItemRuns = 2048;         // one GPU; a rank of a sharded grid holds 1 / world of the tiles and cuts them finer (item_runs)
+__host__ __device__ inline unsigned occ_item_runs(int world) { return world >= 8 ? 512u : world >= 2 ? 1024u : kItemRuns; }
 
 __global__ void __launch_bounds__(1024) occ_tile_scan(const unsigned* __restrict__ counts, int n_tiles,
                                                       unsigned* __restrict__ offsets /* n_tiles + 1 */,
                                                       unsigned* __restrict__ class_off /* [tile][class] */,
                                                       const unsigned* __restrict__ tile_flag, uint2* __restrict__ items, int* __restrict__ multi,
-                                                      unsigned* __restrict__ small, unsigned char* __restrict__ dirty) {
+                                                      unsigned* __restrict__ small, unsigned char* __restrict__ dirty, unsigned item_runs) {
     __shared__ unsigned wsum[32];
     __shared__ unsigned carry;
     __shared__ int hist[2][33], start[2][33];      // [0] tiles with hit cells, [1] the others
@@ -345,7 +360,7 @@ __global__ void __launch_bounds__(1024) occ_tile_scan(const unsigned* __restrict
         if (t < n_tiles) { cc = reinterpret_cast<const uint4*>(counts)[2 * t]; cd = reinterpret_cast<const uint4*>(counts)[2 * t + 1]; }
         const unsigned v = cc.x + cc.y + cc.z + cc.w + cd.x + cd.y + cd.z + cd.w;
         if (t < n_tiles && (v || tile_flag[t])) dirty[t] = 3;       // bit 0: touched since the last reset (read-out); bit 1: since the last push to the peers
-        if (v) atomicAdd(&hist[tile_flag[t] ? 0 : 1][32 - __clz(v)], (int)((v + kItemRuns - 1) / kItemRuns));
+        if (v) atomicAdd(&hist[tile_flag[t] ? 0 : 1][32 - __clz(v)], (int)((v + item_runs - 1) / item_runs));
         unsigned inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -382,7 +397,7 @@ __global__ void __launch_bounds__(1024) occ_tile_scan(const unsigned* __restrict
         const uint4 cc = reinterpret_cast<const uint4*>(counts)[2 * t], cd = reinterpret_cast<const uint4*>(counts)[2 * t + 1];
         const unsigned v = cc.x + cc.y + cc.z + cc.w + cd.x + cd.y + cd.z + cd.w;
         if (v) {
-            const int n_it = (int)((v + kItemRuns - 1) / kItemRuns);
+            const int n_it = (int)((v + item_runs - 1) / item_runs);
             const int base = atomicAdd(&start[tile_flag[t] ? 0 : 1][32 - __clz(v)], n_it);
             for (int i = 0; i < n_it; ++i) items[base + i] = make_uint2((unsigned)t, (unsigned)i);
             if (n_it > 1) multi[atomicAdd(&n_multi, 1u)] = t;
@@ -445,7 +460,7 @@ struct TileArgs {
     const unsigned* tile_off;
     const uint4* runs;
     const uint2* items;                       // (tile, piece); tiles with hit cells first
-    unsigned n_hit_items, item_first, item_end;
+    unsigned n_hit_items, item_first, item_end, item_runs;
     int persistent;
     const int* multi;                         // tiles cut into several items
     unsigned* small;                          // [1] n_items [2] queue [5] n_multi
@@ -561,14 +576,14 @@ __global__ void __launch_bounds__(kTileNT) occ_fast_tiles(const TileArgs a) {
         }
         __syncthreads();
         const unsigned t_beg = a.tile_off[t], t_end = a.tile_off[t + 1];
-        const unsigned beg = t_beg + cur_item.y * kItemRuns, end = min(beg + kItemRuns, t_end);
+        const unsigned beg = t_beg + cur_item.y * a.item_runs, end = min(beg + a.item_runs, t_end);
         unsigned cnt_base = (unsigned)__cvta_generic_to_shared(cnt), slot_base = (unsigned)__cvta_generic_to_shared(slot);
         unsigned dummy_addr = (unsigned)__cvta_generic_to_shared(&dummy[tid]);
         asm volatile("" : "+r"(cnt_base), "+r"(slot_base), "+r"(dummy_addr));     // keep them in registers: no re-derivation per step
         if (HITS) walk_runs<true>(a, beg, end, cnt_base, slot_base, dummy_addr, warp, lane);
         else      walk_runs<false>(a, beg, end, cnt_base, slot_base, dummy_addr, warp, lane);
         __syncthreads();
-        const bool whole = t_end - t_beg <= kItemRuns;
+        const bool whole = t_end - t_beg <= a.item_runs;
         for (int c = tid; c < TCELLS; c += kTileNT) {
             const unsigned n = cnt[pad_cell(c)];
             if (n) {
@@ -831,7 +846,7 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
     const int tiles_x = (g.nx + TS - 1) / TS, tiles_y = (g.ny + TS - 1) / TS;
     const int n_tiles = tiles_x * tiles_y;
     // a ray crosses at most tiles_x + tiles_y + 1 tiles, which bounds the number of work items
-    const size_t max_items = (size_t)n_tiles + (size_t)(((unsigned long long)nr * (tiles_x + tiles_y + 1)) / kItemRuns) + 1;
+    const size_t max_items = (size_t)n_tiles + (size_t)(((unsigned long long)nr * (tiles_x + tiles_y + 1)) / occ_item_runs(g.world)) + 1;
     if (g.tile_count.reserve(sizeof(unsigned) * kLenClasses * (size_t)n_tiles) || g.offsets.reserve(sizeof(unsigned) * ((size_t)n_tiles + 1)) ||
         g.class_off.reserve(sizeof(unsigned) * kLenClasses * (size_t)n_tiles) ||
         g.slot_cell.reserve(sizeof(unsigned) * (size_t)nr) || g.items.reserve(sizeof(uint2) * max_items) ||
@@ -879,7 +894,7 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
     else occ_fast_rays<false, false, false><<<nblk, 256, 0, st>>>(a);
     ICPB_LAUNCH_CHECK();
     tm.mark("count");
-    occ_tile_scan<<<1, 1024, 0, st>>>(g.tile_count.as<unsigned>(), n_tiles, g.offsets.as<unsigned>(), g.class_off.as<unsigned>(), g.tile_flag.as<unsigned>(), g.items.as<uint2>(), g.multi.as<int>(), d_small, g.dirty.as<unsigned char>());
+    occ_tile_scan<<<1, 1024, 0, st>>>(g.tile_count.as<unsigned>(), n_tiles, g.offsets.as<unsigned>(), g.class_off.as<unsigned>(), g.tile_flag.as<unsigned>(), g.items.as<uint2>(), g.multi.as<int>(), d_small, g.dirty.as<unsigned char>(), occ_item_runs(g.world));
     ICPB_LAUNCH_CHECK();
     unsigned h_small[40];
     tm.mark("scan");
@@ -965,6 +980,7 @@ static int fast_chunk(OccGrid& g, int n_scans, int s0, int cs, const double* d_o
         t.l_hit = g.l_hit; t.l_miss = g.l_miss; t.lo = lo; t.hi = hi;
         const unsigned n_items = h_small[1], n_multi = h_small[5];
         t.n_hit_items = h_small[6];
+        t.item_runs = occ_item_runs(g.world);
         // Two launches side by side.  The tiles that hold hit cells go to the priority stream (persistent CTAs pulling
         // from a queue, heaviest first) followed by the hit cells' replay; the other tiles go to the main stream, one
         // item per CTA, and fill every SM slot the first launch leaves free -- its tail and the replay run underneath.
