@@ -48,11 +48,14 @@ for name, launches in per_kernel.items():
     mean = sum(l["dram"] for l in launches) / len(launches)
     detail[s] = dict(launches=len(launches), dram_bytes_mean=mean, lts_bytes_mean=sum(l["lts"] for l in launches) / len(launches),
                      per_launch=[dict(dram=l["dram"], lts=l["lts"], ns=l["ns"]) for l in launches])
-# one ICP step = one bulk launch + one hand-over launch: take the first pair of captured launches of the brute kernels
-brute = [(n, l) for n, ls in per_kernel.items() if "icp_pairs_kernel<2, false" in n.replace("(bool)0", "false") or "icp_pairs_kernel<(int)2, (bool)0" in n for l in ls]
-grid = [(n, l) for n, ls in per_kernel.items() if "icp_pairs_kernel<(int)2, (bool)1" in n for l in ls]
-bulk = [l for n, l in brute if "(int)2, (int)256" in n]
-hand = [l for n, l in brute if "(int)1, (int)512" in n or "(int)1, (int)256" in n]
+# one ICP step = one bulk launch + one hand-over launch: take the first captured launch of each of the brute kernels
+import re
+def variant(name):
+    m = re.search(r"icp_pairs_kernel<\(int\)(\d), \(bool\)(\d), \(int\)(\d), \(int\)(\d+)>", name)
+    return tuple(int(x) for x in m.groups()) if m else None
+bulk = [l for n, ls in per_kernel.items() if variant(n) and variant(n)[:2] == (2, 0) and variant(n)[3] == 256 and variant(n)[2] > 1 for l in ls]
+hand = [l for n, ls in per_kernel.items() if variant(n) and variant(n)[:2] == (2, 0) and variant(n)[2] == 1 for l in ls]
+grid = [(n, l) for n, ls in per_kernel.items() if variant(n) and variant(n)[1] == 1 for l in ls]
 if bulk and hand:
     groups["icp_pairs_kernel"] = bulk[0]["dram"] + hand[0]["dram"]
 if grid:
