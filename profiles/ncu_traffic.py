@@ -51,9 +51,13 @@ for name, launches in per_kernel.items():
 # one ICP step = one bulk launch + one hand-over launch: take the first captured launch of each of the brute kernels
 import re
 def variant(name):
-    m = re.search(r"icp_pairs_kernel<\(int\)(\d), \(bool\)(\d), \(int\)(\d), \(int\)(\d+)>", name)
-    return tuple(int(x) for x in m.groups()) if m else None
-bulk = [l for n, ls in per_kernel.items() if variant(n) and variant(n)[:2] == (2, 0) and variant(n)[3] == 256 and variant(n)[2] > 1 for l in ls]
+    """(dim, grid, min blocks, threads) of an icp_pairs_kernel instantiation, however ncu spells the template arguments."""
+    m = re.search(r"icp_pairs_kernel<\s*(?:\(int\))?(\d),\s*(?:\(bool\))?(\d|true|false),\s*(?:\(int\))?(\d),\s*(?:\(int\))?(\d+)>", name)
+    if not m:
+        return None
+    g = m.group(2)
+    return (int(m.group(1)), 1 if g in ("1", "true") else 0, int(m.group(3)), int(m.group(4)))
+bulk = [l for n, ls in per_kernel.items() if variant(n) and variant(n)[:2] == (2, 0) and variant(n)[2] > 1 for l in ls]
 hand = [l for n, ls in per_kernel.items() if variant(n) and variant(n)[:2] == (2, 0) and variant(n)[2] == 1 for l in ls]
 grid = [(n, l) for n, ls in per_kernel.items() if variant(n) and variant(n)[1] == 1 for l in ls]
 if bulk and hand:
