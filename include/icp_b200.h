@@ -175,10 +175,11 @@ int icpb200_icp_phase_profile(int64_t *out8);
 int icpb200_icp_extra_stats(int64_t *out8);
 
 /* Profiling aid: the first call switches per-pair counters on; after the next
- * registration call, a call with a buffer of 4*cap_pairs int64 receives, per
+ * registration call, a call with a buffer of 8*cap_pairs int64 receives, per
  * pair of that call, {SM cycles spent on the pair (both launches), source
- * points swept, points re-decided by the fp64 fallback, iterations} and
- * returns the number of pairs written. */
+ * points swept, points re-decided by the fp64 fallback, iterations, cycles of
+ * the classify phase, of the nearest-neighbour phase, of the rest (iterations
+ * >= 8 only), 0} and returns the number of pairs written. */
 int icpb200_icp_pair_profile(int64_t *out, int64_t cap_pairs);
 
 /* Voxel-grid mean downsample (replaces utilities/icp.py:117-129).  `out`

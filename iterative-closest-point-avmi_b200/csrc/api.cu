@@ -283,9 +283,9 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
         const size_t np_ = (size_t)n_pairs, cs_ = (size_t)a.cap_s;
         if (c.cont_cur.reserve(sizeof(double) * k.dim * cs_ * np_) || c.cont_match.reserve(sizeof(int) * cs_ * np_) ||
             c.cont_d2lb.reserve(sizeof(float) * cs_ * np_) || c.cont_moved.reserve(sizeof(float) * k.dim * cs_ * np_) ||
-            c.cont_scalar.reserve(sizeof(double) * 16 * np_) || c.cont_list.reserve(sizeof(int) * 4 * np_))
+            c.cont_scalar.reserve(sizeof(double) * 16 * np_) || c.cont_list.reserve(sizeof(int) * 5 * np_))
             return ICPB200_ERR_CUDA;
-        a.cont_count = a.queue + 8;                                   // [8] total, [9..11] per cost class
+        a.cont_count = a.queue + 8;                                   // [8] total, [9..12] per cost class
         a.cont_list = c.cont_list.as<int>();
         a.cont_bucket = a.cont_list + np_;
         a.cont_cap = n_pairs;
@@ -299,8 +299,8 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
     a.trace_match = tr.match; a.trace_iters = tr.iters; a.trace_stride = tr.stride;
     a.pair_prof = nullptr;
     if (c.pair_prof_on) {                                          // icpb200_icp_pair_profile() asked for per-pair counters
-        if (c.pair_prof.reserve(sizeof(unsigned long long) * 4 * (size_t)n_pairs)) return ICPB200_ERR_CUDA;
-        ICPB_CUDA(cudaMemsetAsync(c.pair_prof.p, 0, sizeof(unsigned long long) * 4 * (size_t)n_pairs, st));
+        if (c.pair_prof.reserve(sizeof(unsigned long long) * 8 * (size_t)n_pairs)) return ICPB200_ERR_CUDA;
+        ICPB_CUDA(cudaMemsetAsync(c.pair_prof.p, 0, sizeof(unsigned long long) * 8 * (size_t)n_pairs, st));
         a.pair_prof = c.pair_prof.as<unsigned long long>();
         c.pair_prof_n = n_pairs;
     }
@@ -416,8 +416,25 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
         b.resume = 1;
         b.queue = a.queue + 1;
         // (two or three CTAs per SM were measured slower: the hand-over pairs are latency-bound and want the SM alone)
-        const size_t smem2 = std::max(smem, (size_t)c.max_smem_optin / 2 + 1024);
-        if ((rc = launch_icp_pairs(b, k.dim, grid, c.sm_count, std::min(smem2, (size_t)c.max_smem_optin), st))) return rc;
+        const size_t smem2 = std::min(std::max(smem, (size_t)c.max_smem_optin / 2 + 1024), (size_t)c.max_smem_optin);
+        static const bool no_cluster = getenv("ICPB200_NO_CLUSTER") != nullptr;      // A/B switch (profiles/README.md)
+        b.class_lo = 0; b.class_hi = 4;                                  // every cost class (IcpArgs::cont_bucket), expensive first
+        if (icp_cluster_variant(k.dim, grid) && !no_cluster) {
+            // two launches side by side, clusters of CTAs (a CTA that runs out of pairs helps a cluster mate with its
+            // sweeps) and plain CTAs; the kernels decide from the handed-over lists which of them does the work
+            // (coop_plan in icp_kernel.cu: clusters when a few long chains bound the launch, plain CTAs otherwise)
+            int n_cl = 0;
+            cudaStream_t side = c.chunk_stream[0];
+            ICPB_CUDA(cudaEventRecord(c.fork_ev, st));                      // the bulk launch and its hand-over lists
+            if ((rc = launch_icp_pairs_cluster(b, c.sm_count, smem2, st, &n_cl))) return rc;
+            b.coop_ctas = n_cl;
+            ICPB_CUDA(cudaStreamWaitEvent(side, c.fork_ev, 0));
+            if ((rc = launch_icp_pairs(b, k.dim, grid, c.sm_count, smem2, side))) return rc;
+            ICPB_CUDA(cudaEventRecord(c.group_done[0], side));
+            ICPB_CUDA(cudaStreamWaitEvent(st, c.group_done[0], 0));
+        } else {
+            if ((rc = launch_icp_pairs(b, k.dim, grid, c.sm_count, smem2, st))) return rc;
+        }
     }
     ICPB_CUDA(cudaEventRecord(c.ev[3], st));
     ICPB_CUDA(cudaEventRecord(c.icp_done, st));
@@ -939,6 +956,13 @@ int icpb200_icp_extra_stats(int64_t* out8) {
     ICPB_CUDA(cudaStreamSynchronize(st));
     out8[0] = h[0];                                // far-field iterations
     out8[1] = h[2]; out8[2] = h[3]; out8[3] = h[4];   // grid mode: queries, candidates evaluated, cells visited
+    out8[7] = h[1];                                // times a CTA joined a cluster mate's pair as a helper
+    if (c.queue.p) {                               // handed-over pairs per cost class (two-phase batches)
+        unsigned q[5] = {0, 0, 0, 0, 0};
+        ICPB_CUDA(cudaMemcpyAsync(q, c.queue.as<unsigned>() + 8, sizeof(q), cudaMemcpyDeviceToHost, st));
+        ICPB_CUDA(cudaStreamSynchronize(st));
+        out8[4] = q[1]; out8[5] = q[2]; out8[6] = q[3] + q[4];      // chains, heavy, the rest
+    }
     return ICPB200_OK;
 }
 
@@ -951,7 +975,7 @@ int icpb200_icp_pair_profile(int64_t* out, int64_t cap_pairs) {
     if (!out || cap_pairs <= 0 || !c.pair_prof.p || c.pair_prof_n <= 0) return 0;
     cudaStream_t st = c.last_icp_stream ? c.last_icp_stream : c.stream;
     const int64_t n = std::min<int64_t>(cap_pairs, c.pair_prof_n);
-    ICPB_CUDA(cudaMemcpyAsync(out, c.pair_prof.p, sizeof(int64_t) * 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    ICPB_CUDA(cudaMemcpyAsync(out, c.pair_prof.p, sizeof(int64_t) * 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
     ICPB_CUDA(cudaStreamSynchronize(st));
     return (int)n;
 }
@@ -1388,7 +1412,7 @@ int icpb200_grid_tile_profile(void* grid, int64_t* out, int64_t cap_tiles) {
     int rc = init_locked(-1);
     if (rc) return rc;
     const int64_t n = std::min<int64_t>(cap_tiles, (int64_t)g->tiles_x * g->tiles_y);
-    ICPB_CUDA(cudaMemcpy(out, g->tile_prof.p, sizeof(int64_t) * 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    ICPB_CUDA(cudaMemcpy(out, g->tile_prof.p, sizeof(int64_t) * 8 * (size_t)n, cudaMemcpyDeviceToHost));
     return (int)n;
 }
 

@@ -59,7 +59,7 @@ struct Context {
     // big-cloud path: radix-sort scratch and hash grids
     DevBuf big_keys, big_idx, grid_start, grid_items, grid_cell, grid_desc, grid_off, grid_buckets;
     DevBuf cont_cur, cont_match, cont_d2lb, cont_moved, cont_scalar, cont_list;
-    DevBuf pair_prof;                  // icpb200_icp_pair_profile: [pair][4] counters of the last registration call
+    DevBuf pair_prof;                  // icpb200_icp_pair_profile: [pair][8] counters of the last registration call
     bool pair_prof_on = false;
     int pair_prof_n = 0;
     void* h_stage = nullptr;           // page-locked staging for the result read-back (one wait, then host copies)

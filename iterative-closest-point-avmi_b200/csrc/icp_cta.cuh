@@ -35,9 +35,32 @@ struct CtaSharedT {
     // split-sweep partials (K3): [warp][lane]
     float part_b1[NW_][32], part_b2[NW_][32], part_b3[NW_][32];
     int part_bt[NW_][32], part_bt2[NW_][32];
+    float part_gap[NW_][32];           // slab sweep split by direction: the partner's x-gap to what it left unvisited
     int bins[65];                      // x-bins of the points to decide (K3: todo list ordered for the slab sweep)
     int front_n;                       // K3 far-field front set size
     int slab_off;                      // K3: sweeps left before the slab sweep is tried again (it pruned too little last time)
+    long long ph_seen[3];              // per-pair profile: phase cycles already attributed to earlier pairs of this CTA
+    // K3, cluster variant of the hand-over launch: a CTA that ran out of pairs helps a cluster mate that is still running
+    // one.  These words are read and written by the mates through distributed shared memory.
+    unsigned long long coop_pub;       // owner -> helpers, one atomic word per publication:
+                                       //   epoch << 32 | helper mask << 20 | flags << 16 | points to decide
+                                       //   flags: bit 0 the pair is finished, bit 1 slab sweep, bit 2 the list is todo2
+    unsigned int coop_word;            // bit 31: a pair runs here and takes helpers; bits 8..30: its sequence number on this
+                                       //   CTA; bits 0..7: the cluster ranks registered as helpers
+    unsigned int coop_arrived;         // helpers done with the current publication
+    unsigned int coop_idle;            // this CTA has no pair of its own any more
+    unsigned int coop_pair;            // the pair running here and where its state was parked
+    int coop_slot;
+    int coop_parts;                    // owner, this iteration: CTAs sharing the sweep (1: nobody helps)
+    int coop_load;                     // points the pair running here had to decide in its last iteration
+    // helper side (local copies of what the owner published, broadcast to the CTA)
+    int help_rank;                     // the mate this CTA is about to help (-1: none)
+    unsigned int help_word;            // its coop_word when it was chosen
+    int help_ok;
+    int help_dry;                      // the queue gave this CTA nothing any more
+    int coop_first;                    // this CTA has not taken its first pair yet (it is dealt statically)
+    unsigned int coop_seq, coop_epoch; // owner: pairs opened here, publications made (kept here, not in registers)
+    unsigned long long help_pub;
 };
 using CtaShared = CtaSharedT<kNW>;     // the 256-thread kernels (K1, K2, K8, bulk K3)
 

@@ -34,6 +34,8 @@
 // no atomics in any sum, so results are bitwise reproducible run to run.
 #include <stdlib.h>
 
+#include <cooperative_groups.h>
+
 #include "icp_b200.h"
 #include "common.cuh"
 #include "icp_cta.cuh"
@@ -43,7 +45,7 @@
 namespace icpb {
 
 constexpr int kSMax = 8;               // chunks (of 32 source points) per warp per sweep round
-constexpr unsigned kContClasses = 3;   // cost classes of the handed-over pairs (IcpArgs::cont_bucket)
+constexpr unsigned kContClasses = 4;   // cost classes of the handed-over pairs (IcpArgs::cont_bucket)
 constexpr int kKnnMax = 64;            // normal_k + 1 upper bound
 constexpr int kGridCells = 4096;       // shared-memory uniform grid for the normals kNN
 constexpr float kFar = 3.0e18f;        // padding target coordinate (distance^2 ~ 1.8e37, finite)
@@ -859,6 +861,8 @@ struct Loop {
     const unsigned short* list;   // what the sweeps read: todo or todo2
     unsigned short* amb;     // points whose fp32 ranking could not be separated: decided in fp64
     const double2* nrm_s;    // 512-thread variant: the target's normals in shared memory (nullptr: read them through L2)
+    int* amb_n;              // number of entries of amb[]                  } this CTA's own, or -- in a helper CTA of a
+    unsigned* slab_evals;    // candidates the slab sweeps looked at (statistics) } cluster -- the owner's, through DSMEM
     int n_s, n_t, n_tiles;
     double c0, c1, c2;       // recentring offset
     float ta;                // sum over axes of max |target - centre|
@@ -936,7 +940,7 @@ __device__ __forceinline__ void decide(const Loop<DIM>& L, SH& sh, int i, float 
     const double d1 = sqrt(best);
     if (!(other > d1)) {
         L.match[i] = m_pack(bj, -1);                   // the best known candidate: the fp64 fallback starts from it
-        L.amb[atomicAdd(&sh.amb_n, 1)] = (unsigned short)i;
+        L.amb[atomicAdd(L.amb_n, 1)] = (unsigned short)i;
     } else {
         L.match[i] = m_pack(bj, j2);
         L.d2lb[i] = f32_down(fmin(other, sqrt(third) * (1.0 - 1e-12)));       // everything but bj and j2
@@ -1051,12 +1055,54 @@ __device__ __forceinline__ void nn_split(const Loop<DIM>& L, SH& sh, int n_todo,
         const double other = sqrt((double)(two ? m3 : m2)) * (1.0 - kRel32) - 1.8e-7 * (double)mag;
         if (!(other > d1)) {
             L.match[pt] = m_pack(j1, -1);
-            L.amb[atomicAdd(&sh.amb_n, 1)] = (unsigned short)pt;
+            L.amb[atomicAdd(L.amb_n, 1)] = (unsigned short)pt;
         } else {
             L.match[pt] = m_pack(j1, j2);
             L.d2lb[pt] = f32_down(other);
             stamp_p0<DIM>(L, pt);
         }
+    }
+}
+
+// The same split for lists of 3 chunks up to half the CTA's warps (pairs that keep re-deciding a few hundred points, the
+// helpers' stretches of a shared sweep): tracking three candidates costs 13 instructions per evaluation, 8 of them on the
+// half-rate pipe, and made a list of 8 chunks as expensive as a bulk sweep of 20.  Here each warp sweeps its share of
+// the target's TILES with the tile sweep's bookkeeping (one min per evaluation; the best tile and the best of the other
+// tiles per point); the partial results meet in shared memory and the first warp of the chunk decides as the bulk sweep
+// does -- the winning tile re-evaluated in fp64, everything else bounded by the runner-up tile.
+template <int DIM, int NT, class SH>
+__device__ __forceinline__ void nn_split_tiles(const Loop<DIM>& L, SH& sh, int n_todo, int n_chunks, int F) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunk = w / F, part = w % F;
+    const bool live = chunk < n_chunks;
+    float sx[1] = {0.f}, sy[1] = {0.f}, sz[1] = {0.f};
+    int pt = -1;
+    if (live) {
+        const int q = chunk * 32 + lane;
+        pt = q < n_todo ? (int)L.list[q] : -1;
+        const int i = max(pt, 0);
+        sx[0] = pt >= 0 ? (float)(L.cx[i] - L.c0) : 0.f;
+        sy[0] = pt >= 0 ? (float)(L.cy[i] - L.c1) : 0.f;
+        sz[0] = (DIM == 3 && pt >= 0) ? (float)(L.cz[i] - L.c2) : 0.f;
+        const int t0 = (int)((long long)part * L.n_tiles / F), t1 = (int)((long long)(part + 1) * L.n_tiles / F);
+        float b1[1], b2[1];
+        int bt[1];
+        if (DIM == 2) sweep2d<1>(L.t32, t0, t1, sx, sy, b1, b2, bt);
+        else          sweep3d<1>(L.t32, t0, t1, sx, sy, sz, b1, b2, bt);
+        sh.part_b1[w][lane] = b1[0]; sh.part_b2[w][lane] = b2[0]; sh.part_bt[w][lane] = bt[0];
+    }
+    __syncthreads();
+    if (live && part == 0 && pt >= 0) {
+        float m1 = INFINITY, m2 = INFINITY;
+        int mt = 0;
+        for (int f = 0; f < F; ++f) {
+            const float v1 = sh.part_b1[w + f][lane], v2 = sh.part_b2[w + f][lane];
+            const bool lt = v1 < m1;
+            m2 = fminf(fminf(m2, v2), lt ? m1 : v1);           // the best of all tiles but the winner
+            mt = lt ? sh.part_bt[w + f][lane] : mt;
+            m1 = fminf(m1, v1);
+        }
+        decide<DIM>(L, sh, pt, sx[0], sy[0], sz[0], m2, mt);
     }
 }
 
@@ -1070,14 +1116,19 @@ __device__ __forceinline__ void nn_split(const Loop<DIM>& L, SH& sh, int n_todo,
 // min(third best, gaps) minus the fp32 slack; otherwise the full fp64 scan decides.  On C2 a chunk
 // visits ~60 of the 800 targets instead of all of them, and the 32-target fp64 re-evaluation of
 // the tile sweep is gone.
-template <int DIM, int NT, class SH>
+// DS (lists of at most half as many chunks as the CTA has warps): two warps per chunk, one walks down, the other up; the
+// up-walker leaves its three best and its gap in shared memory and the down-walker merges them in front of the decision.
+template <int DIM, int NT, bool DS, class SH>
 __device__ __forceinline__ void nn_slab(const Loop<DIM>& L, SH& sh, int n_todo, float vox) {
     const unsigned full = 0xffffffffu;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_chunks = (n_todo + 31) >> 5;
     const float* tf = reinterpret_cast<const float*>(L.t32);
     constexpr int kStride = DIM == 2 ? 2 : 4;                 // floats per target in t32
-    for (int chunk = w; chunk < n_chunks; chunk += (NT / 32)) {
+    for (int chunk = DS ? (w >> 1) : w; chunk < (DS ? (NT / 64) : n_chunks); chunk += (NT / 32)) {
+        const bool live = !DS || chunk < n_chunks;            // (DS: one round, every warp reaches the barrier below)
+        const bool walk_dn = !DS || (w & 1) == 0, walk_up = !DS || (w & 1) == 1;
+        if (DS && !live) { __syncthreads(); continue; }
         const int q = chunk * 32 + lane;
         const int pt = q < n_todo ? (int)L.list[q] : -1;
         const int i = pt >= 0 ? pt : (int)L.list[chunk * 32];   // idle lanes shadow the chunk's first point
@@ -1121,7 +1172,7 @@ __device__ __forceinline__ void nn_slab(const Loop<DIM>& L, SH& sh, int n_todo, 
             if (tf[mid * kStride] < x0) lo = mid + 1; else hi = mid;
         }
         int dn = lo - 1, up = lo;
-        bool ddone = dn < 0, udone = up >= L.n_t;
+        bool ddone = dn < 0 || !walk_dn, udone = up >= L.n_t || !walk_up;
         float gdn = INFINITY, gup = INFINITY;                 // x-gap to the unvisited part, per lane
         while (!ddone || !udone) {
             if (!ddone) {
@@ -1153,9 +1204,21 @@ __device__ __forceinline__ void nn_slab(const Loop<DIM>& L, SH& sh, int n_todo, 
                 }
             }
         }
-        if (lane == 0) atomicAdd(&sh.slab_evals, (unsigned)((lo - 1 - dn) + (up - lo)) * 32u);      // statistics only
+        if (lane == 0) atomicAdd(L.slab_evals, (unsigned)((walk_dn ? lo - 1 - dn : 0) + (walk_up ? up - lo : 0)) * 32u);      // statistics only
+        if (DS) {
+            if (walk_up) {
+                sh.part_b1[w][lane] = b1; sh.part_b2[w][lane] = b2; sh.part_b3[w][lane] = b3;
+                sh.part_bt[w][lane] = bj; sh.part_bt2[w][lane] = bj2; sh.part_gap[w][lane] = gup;
+            }
+            __syncthreads();
+            if (walk_up) continue;
+            offer_d(sh.part_b1[w + 1][lane], sh.part_bt[w + 1][lane]);
+            offer_d(sh.part_b2[w + 1][lane], sh.part_bt2[w + 1][lane]);
+            b3 = fminf(b3, sh.part_b3[w + 1][lane]);
+            gup = sh.part_gap[w + 1][lane];
+        }
         if (pt < 0) continue;
-        const bool two = bj2 >= 0 && bj2 != bj;
+        const bool two = bj2 >= 0 && bj2 != bj && b2 < 1.0e30f;
         const double px = L.cx[pt], py = L.cy[pt], pz = DIM == 3 ? L.cz[pt] : 0.0;
         double e1 = dist2_64<DIM>(L, px, py, pz, bj);
         int j1 = bj, j2 = -1;
@@ -1170,7 +1233,7 @@ __device__ __forceinline__ void nn_slab(const Loop<DIM>& L, SH& sh, int n_todo, 
         const double other = rest - 1.8e-7 * (double)mag;
         if (!(other > d1)) {
             L.match[pt] = m_pack(j1, -1);
-            L.amb[atomicAdd(&sh.amb_n, 1)] = (unsigned short)pt;
+            L.amb[atomicAdd(L.amb_n, 1)] = (unsigned short)pt;
         } else {
             L.match[pt] = m_pack(j1, j2);
             L.d2lb[pt] = f32_down(other);
@@ -1179,13 +1242,24 @@ __device__ __forceinline__ void nn_slab(const Loop<DIM>& L, SH& sh, int n_todo, 
     }
 }
 
+// lists of fewer chunks go to the split sweep (every warp takes a share of the target: lowest latency for a few points)
+constexpr int kSlabMinChunks = 3;
+
 template <int DIM, int NT, class SH>
 __device__ __forceinline__ void nn_dispatch(const Loop<DIM>& L, SH& sh, int n_todo, float vox) {
     const int w = threadIdx.x >> 5;
     const int n_chunks = (n_todo + 31) >> 5;
     const int F = n_chunks > 0 ? (NT / 32) / n_chunks : 1;
-    if (F >= 2) { nn_split<DIM, NT>(L, sh, n_todo, n_chunks, F); return; }
-    if (vox > 0.f) { nn_slab<DIM, NT>(L, sh, n_todo, vox); return; }
+    if (vox > 0.f && n_chunks >= kSlabMinChunks) {
+        if (F >= 2) nn_slab<DIM, NT, true>(L, sh, n_todo, vox);
+        else nn_slab<DIM, NT, false>(L, sh, n_todo, vox);
+        return;
+    }
+    if (F >= 2) {
+        if (n_chunks >= kSlabMinChunks) nn_split_tiles<DIM, NT>(L, sh, n_todo, n_chunks, F);
+        else nn_split<DIM, NT>(L, sh, n_todo, n_chunks, F);
+        return;
+    }
     for (int base = 0; base < n_chunks; base += kSMax * (NT / 32)) {
         const int first = base + w;
         const int mine = first < n_chunks ? min(kSMax, (n_chunks - first + (NT / 32) - 1) / (NT / 32)) : 0;   // warp-uniform
@@ -1467,12 +1541,119 @@ __device__ __forceinline__ void grid_nn(const Loop<DIM>& L, int n_todo, unsigned
 // ---- K3: the kernel ----------------------------------------------------------------
 // MINB = CTAs per SM the register allocation must allow: 2 for the 2-D bulk launch (3 for 3-D and grid mode), 1 for the
 // hand-over launch (one CTA per SM anyway); at 1 and 2 everything stays in registers instead of spilling.
-template <int DIM, bool GRID, int MINB, int NT>
+// CL = CTAs of a thread-block cluster (1: no cluster).  The CL = 4 variant is the hand-over launch of the 2-D brute-force
+// path.  Its CTAs take pairs from the queue independently, like the plain variant; the launch ends with a handful of
+// pairs that re-decide hundreds of points in every one of 150 iterations -- 3-6 ms chains on one SM each, while the SMs
+// around them have run out of work (a rank of an 8-GPU job holds 5-20 of them and 1.5-2 ms of work per SM).  A CTA that
+// finds the queue empty therefore looks for a cluster mate that is still running a pair, stages the same target and
+// takes a share of every bulk nearest-neighbour sweep of that pair: it reads the points to decide from the owner's shared
+// memory and writes the decisions back (distributed shared memory).  Owner and helpers meet through three words in the
+// owner's shared memory: coop_word (helpers register with a compare-and-swap while the pair is open), coop_pub (one
+// 64-bit publication per shared sweep: epoch, helper mask, list length) and coop_arrived (helpers done).  The decisions
+// are the same exact nearest neighbours whoever computes them, so the results do not depend on who helped.
+__device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+constexpr unsigned kCoopOpen = 0x80000000u;
+constexpr int kCoopMinShare = 96;           // sweeps of fewer points are not worth a publication
+constexpr int kCoopCluster = 8;             // CTAs per cluster of the hand-over launch
+// The hand-over of a 2-D brute-force batch is launched twice, side by side: as clusters (a.coop_ctas CTAs) and as plain
+// CTAs (one per SM).  Which of the two does the work is decided here, from what the bulk launch handed over, the same in
+// every CTA of both launches:
+//   - cluster mode when long chains, not throughput, will bound the launch: a few pairs that re-decided 96+ points per
+//     iteration when they were parked among at most four handed-over pairs per CTA (a rank's share of a multi-GPU batch).
+//     The plain launch then only fills the SMs the cluster shape leaves unused.  The cluster kernel runs every phase ~12 %
+//     slower than the plain one (register pressure), which a chain-bound launch does not feel;
+//   - plain mode otherwise (C2 and C5 on one GPU: throughput-bound): the cluster CTAs leave at once.
+// In cluster mode class 0 of the handed-over pairs (256+ points per iteration) are the likely chains: when they are few,
+// each gets its cluster's rank 0 and `h` mates that help from the first iteration on instead of taking pairs of their own.
+// *skip = queue positions dealt statically to the cluster CTAs (the dynamic queue continues behind them).
+__device__ __forceinline__ bool coop_plan(const IcpArgs& a, unsigned& n_chain, unsigned& h, unsigned& skip) {
+    const unsigned n_cl_ctas = (unsigned)a.coop_ctas, n_clusters = n_cl_ctas / kCoopCluster;
+    n_chain = 0; h = 0; skip = 0;
+    if (n_cl_ctas == 0u) return false;
+    const unsigned total = a.cont_count[0], heavy = a.cont_count[1] + a.cont_count[2];
+    if (heavy < 4u || total > 4u * n_cl_ctas) return false;
+    n_chain = min(a.cont_count[1], n_clusters);
+    if (n_chain > 0) h = min((unsigned)kCoopCluster, n_cl_ctas / (3u * n_chain));
+    h = h > 0 ? h - 1 : 0;
+    skip = n_cl_ctas - n_chain * h;
+    return true;
+}
+// a wait that is never satisfied is a protocol bug: fail the launch instead of hanging the device
+#define ICPB_COOP_SPIN(cond)                                            \
+    for (unsigned spin_ = 0; !(cond); ++spin_) {                        \
+        __nanosleep(64);                                                \
+        if (spin_ > (1u << 26)) __trap();                               \
+    }
+
+// A CTA of the cluster variant helping a mate (see icp_pairs_kernel): the target staged in L is this CTA's own copy, the
+// source side (points, decisions, lists) is the owner's, reached through distributed shared memory.  Not inlined: kept
+// out of the kernel's register allocation (inlined, the 512-thread variant spilled five times as much in its own loop).
+template <int DIM, int NT, class SH>
+__device__ __forceinline__ void coop_help(const Loop<DIM>& L, SH& sh, unsigned cl_rank, float slab_vox, unsigned long long* stats) {
+    namespace cg = cooperative_groups;
+    const int tid = threadIdx.x;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned orank = (unsigned)sh.help_rank;
+    SH* osh = cluster.map_shared_rank(&sh, orank);
+    Loop<DIM> H = L;
+    H.cx = cluster.map_shared_rank(L.cx, orank); H.cy = cluster.map_shared_rank(L.cy, orank);
+    H.cz = cluster.map_shared_rank(L.cz, orank);
+    H.match = cluster.map_shared_rank(L.match, orank); H.d2lb = cluster.map_shared_rank(L.d2lb, orank);
+    H.p0 = cluster.map_shared_rank(L.p0, orank); H.amb = cluster.map_shared_rank(L.amb, orank);
+    H.amb_n = &osh->amb_n; H.slab_evals = &osh->slab_evals;
+    const unsigned short* o_todo = cluster.map_shared_rank(L.todo, orank);
+    const unsigned short* o_todo2 = cluster.map_shared_rank(L.todo2, orank);
+    const unsigned my_bit = 1u << cl_rank;
+    unsigned seen = 0;
+    if (tid == 0) {
+        // register -- only while the pair this target was staged for is still the one running there
+        seen = (unsigned)(*(volatile unsigned long long*)&osh->coop_pub >> 32);
+        const unsigned want = sh.help_word & ~0xffu;
+        int ok = 0;
+        for (;;) {
+            const unsigned cur = *(volatile unsigned*)&osh->coop_word;
+            if ((cur & ~0xffu) != want) break;
+            if (atomicCAS(&osh->coop_word, cur, cur | my_bit) == cur) { ok = 1; break; }
+        }
+        sh.help_ok = ok;
+        if (ok && stats) atomicAdd(&stats[15], 1ull);      // statistics: helpers that joined a pair
+    }
+    __syncthreads();
+    while (sh.help_ok) {
+        if (tid == 0) {
+            unsigned long long pub;
+            ICPB_COOP_SPIN((unsigned)((pub = *(volatile unsigned long long*)&osh->coop_pub) >> 32) != seen);
+            seen = (unsigned)(pub >> 32);
+            fence_cluster();
+            sh.help_pub = pub;
+        }
+        __syncthreads();
+        const unsigned long long pub = sh.help_pub;
+        const unsigned mask = (unsigned)(pub >> 20) & 0xffu;
+        const int flags = (int)(pub >> 16) & 0xf, n = (int)(pub & 0xffffu);
+        __syncthreads();                               // (sh.help_pub is rewritten in the next round)
+        if (!(mask & my_bit)) continue;                // published before this CTA registered
+        if (!(flags & 1)) {
+            const int parts = __popc(mask) + 1, k = __popc(mask & (my_bit - 1u)) + 1;      // the owner is part 0
+            const int per = ((n + parts * 32 - 1) / (parts * 32)) * 32;
+            const int lo = k * per, cnt = min(per, n - lo);
+            H.list = ((flags & 4) ? o_todo2 : o_todo) + lo;
+            if (cnt > 0) nn_dispatch<DIM, NT>(H, sh, cnt, (flags & 2) ? slab_vox : 0.f);
+            __syncthreads();
+        }
+        if (tid == 0) { fence_cluster(); atomicAdd(&osh->coop_arrived, 1u); }
+        if (flags & 1) break;                          // the pair is finished
+    }
+}
+
+template <int DIM, bool GRID, int MINB, int NT, int CL = 1>
 __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     using SH = CtaSharedT<NT / 32>;
     SH& sh = *reinterpret_cast<SH*>(smem);
     const int tid = threadIdx.x;
+    namespace cg = cooperative_groups;
+    // (the cluster variant keeps its few words of state in shared memory: the kernel sits at the register limit)
     const int tstride = a.cap_t + a.cap_t / 32;
     Loop<DIM> L;
     {
@@ -1493,6 +1674,8 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
         L.todo2 = reinterpret_cast<unsigned short*>(q); q += sizeof(unsigned short) * (size_t)a.cap_s;
         L.amb = reinterpret_cast<unsigned short*>(q);       q += sizeof(unsigned short) * (size_t)a.cap_s;
         L.list = L.todo;
+        L.amb_n = &sh.amb_n;
+        L.slab_evals = &sh.slab_evals;
         L.nrm_s = nullptr;
         if (NT == 512 && DIM == 2 && !GRID) L.nrm_s = reinterpret_cast<const double2*>(smem + align16((size_t)(q - smem)));
     }
@@ -1508,6 +1691,12 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
 
     __shared__ __align__(8) unsigned long long nrm_bar;      // completion of the normals' bulk copy (512-thread variant)
     unsigned nrm_parity = 0;
+    if (tid == 0) sh.ph_seen[0] = sh.ph_seen[1] = sh.ph_seen[2] = 0;      // (the loop below opens with a barrier)
+    if (CL > 1) {
+        if (tid == 0) { sh.coop_word = 0u; sh.coop_idle = 0u; sh.coop_arrived = 0u; sh.coop_pub = 0ull; sh.coop_parts = 1; sh.coop_load = 0;
+                        sh.help_rank = -1; sh.help_dry = 0; sh.coop_first = 1; sh.coop_seq = 0u; sh.coop_epoch = 0u; }
+        cg::this_cluster().sync();      // no mate reads these words before they are set
+    }
     if (NT == 512 && DIM == 2 && !GRID) {
         if (tid == 0) mbar_init(&nrm_bar, 1);
         __syncthreads();
@@ -1516,19 +1705,107 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
         __syncthreads();
         // phase 1 takes pairs in order; phase 2 (a.resume) takes the pairs phase 1 handed over
         if (tid == 0) {
-            const unsigned q = atomicAdd(a.queue, 1u);
-            if (a.resume) {
-                // the handed-over pairs, most expensive class first (longest processing time first: the last CTAs to
-                // finish should be running short pairs, not a 150-iteration chain of full sweeps)
-                unsigned rest = q, b = 0;
-                while (b < kContClasses && rest >= a.cont_count[1 + b]) { rest -= a.cont_count[1 + b]; ++b; }
-                const int slot = b < kContClasses ? a.cont_bucket[(size_t)b * a.cont_cap + rest] : -1;
-                sh.pair = slot >= 0 ? (unsigned)a.cont_list[slot] : 0xffffffffu;
-                sh.bcast_i[2] = slot;               // where the pair's state was parked
+            const unsigned cl_rank = CL > 1 ? cg::this_cluster().block_rank() : 0u;
+            if (CL > 1) sh.help_rank = -1;
+            if (CL > 1 && sh.help_dry) {
+                sh.pair = 0xffffffffu;
+            } else if (a.resume) {
+                // the handed-over pairs of this launch's classes, most expensive class first (longest processing time first:
+                // the last CTAs to finish should be running short pairs, not a 150-iteration chain of full sweeps)
+                unsigned n_chain, h, skip;
+                const bool cluster_mode = coop_plan(a, n_chain, h, skip);
+                bool joined = false;
+                unsigned q;
+                // the launch that is not in charge leaves: every cluster CTA in plain mode, the plain CTAs beyond the SMs
+                // the cluster launch leaves free in cluster mode (all of them when it leaves none)
+                const bool leave = CL > 1 ? !cluster_mode
+                                          : (cluster_mode && (int)blockIdx.x >= (int)gridDim.x - a.coop_ctas);
+                if (leave) {
+                    q = 0xffffffffu;
+                } else if (CL > 1 && sh.coop_first) {
+                    // cluster variant, first pair: the head of the queue is dealt statically, rank 0 of cluster c takes
+                    // position c -- one of the most expensive pairs per cluster, so that every long chain has mates that
+                    // run dry and come to help -- then the other ranks in turn, minus the CTAs reserved for the chains
+                    const unsigned n_clusters = gridDim.x / CL, c = blockIdx.x / CL, r = cl_rank;
+                    if (r >= 1 && r <= h && c < n_chain) {
+                        // reserved: help rank 0 with its chain from its first iteration on (if it is one: long lists)
+                        cg::cluster_group cluster = cg::this_cluster();
+                        SH* m = cluster.map_shared_rank(&sh, 0);
+                        unsigned w = 0;
+                        int load = 0;
+                        ICPB_COOP_SPIN((((w = *(volatile unsigned*)&m->coop_word) & kCoopOpen) &&
+                                        (load = *(volatile int*)&m->coop_load) > 0) || *(volatile unsigned*)&m->coop_idle);
+                        if ((w & kCoopOpen) && load >= kCoopMinShare) {
+                            fence_cluster();
+                            sh.help_rank = 0; sh.help_word = w;
+                            sh.pair = *(volatile unsigned*)&m->coop_pair;
+                            sh.bcast_i[2] = *(volatile int*)&m->coop_slot;
+                            joined = true;
+                        }
+                        q = joined ? 0u : skip + atomicAdd(a.queue, 1u);
+                    } else {
+                        q = c;
+                        if (r >= 1) {
+                            q = n_clusters + c - (r <= h ? n_chain : 0u);
+                            for (unsigned rr = 1; rr < r; ++rr) q += n_clusters - (rr <= h ? n_chain : 0u);
+                        }
+                    }
+                } else {
+                    q = skip + atomicAdd(a.queue, 1u);
+                }
+                if (CL > 1) sh.coop_first = 0;
+                if (!joined) {
+                    unsigned rest = q, b = (unsigned)a.class_lo;
+                    while (b < (unsigned)a.class_hi && rest >= a.cont_count[1 + b]) { rest -= a.cont_count[1 + b]; ++b; }
+                    const int slot = b < (unsigned)a.class_hi ? a.cont_bucket[(size_t)b * a.cont_cap + rest] : -1;
+                    sh.pair = slot >= 0 ? (unsigned)a.cont_list[slot] : 0xffffffffu;
+                    sh.bcast_i[2] = slot;               // where the pair's state was parked
+                    if (CL > 1 && slot < 0) sh.help_dry = 1;
+                }
             } else {
+                const unsigned q = atomicAdd(a.queue, 1u);
                 sh.pair = q < (unsigned)a.n_pairs ? (a.pair_order ? (unsigned)a.pair_order[a.pair_first + q] : (unsigned)a.pair_first + q)
                                                   : 0xffffffffu;
                 sh.bcast_i[2] = (int)q;
+            }
+        }
+        if (CL > 1 && tid == 0) {
+            const unsigned cl_rank = cg::this_cluster().block_rank();
+            if (sh.help_rank < 0 && sh.pair == 0xffffffffu) {
+                // nothing left in the queue: help a cluster mate that is still running a pair (the one with the fewest
+                // helpers), wait while a mate is between pairs, leave when every mate is as idle as this CTA
+                *(volatile unsigned*)&sh.coop_idle = 1u;
+                cg::cluster_group cluster = cg::this_cluster();
+                for (unsigned spin = 0;; ++spin) {
+                    bool busy = false;
+                    int best = -1, best_n = 0;
+                    unsigned best_w = 0;
+                    for (unsigned r = 0; r < (unsigned)CL; ++r) {
+                        if (r == cl_rank) continue;
+                        SH* m = cluster.map_shared_rank(&sh, r);
+                        const unsigned w = *(volatile unsigned*)&m->coop_word;
+                        if (w & kCoopOpen) {
+                            // worth helping: long lists; between several, the most points per CTA already on it
+                            const int load = *(volatile int*)&m->coop_load;
+                            const int n = load >= kCoopMinShare ? load / (__popc(w & 0xffu) + 1) : 0;
+                            if (n > best_n) { best = (int)r; best_n = n; best_w = w; }
+                            if (n == 0) busy = true;           // a light pair for now: it may turn heavy, or end
+                        } else if (*(volatile unsigned*)&m->coop_idle == 0u) {
+                            busy = true;
+                        }
+                    }
+                    if (best >= 0) {
+                        fence_cluster();
+                        SH* m = cluster.map_shared_rank(&sh, (unsigned)best);
+                        sh.help_rank = best; sh.help_word = best_w;
+                        sh.pair = *(volatile unsigned*)&m->coop_pair;
+                        sh.bcast_i[2] = *(volatile int*)&m->coop_slot;
+                        break;
+                    }
+                    if (!busy) break;
+                    __nanosleep(256);
+                    if (spin > (1u << 26)) __trap();
+                }
             }
         }
         __syncthreads();
@@ -1537,6 +1814,7 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
         const int slot_in = sh.bcast_i[2];
         const long long pair_t0 = (tid == 0 && a.pair_prof) ? clock64() : 0;
         const unsigned long long pp_swept0 = st_swept, pp_amb0 = st_amb, pp_it0 = st_iters;
+        unsigned long long st_recent = 0;              // thread 0: points swept in the last iterations before a hand-over
 
         const int cs = a.src_idx ? a.src_idx[p] : p;
         const int ct = a.tgt_idx ? a.tgt_idx[p] : p;
@@ -1674,6 +1952,19 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
         bool handed_over = false;
         // clouds come out of K1 ordered by voxel column: x is sorted up to one voxel (plus fp32 rounding)
         const float slab_vox = a.brute_slab ? __double2float_ru(a.voxel * 1.000001) + 1e-6f * L.ta : 0.f;
+        if (CL > 1 && sh.help_rank < 0) {
+            // this pair takes helpers from now on
+            if (tid == 0) {
+                sh.coop_pair = (unsigned)p; sh.coop_slot = slot_in; sh.coop_arrived = 0u; sh.coop_load = 0;
+                sh.coop_seq = (sh.coop_seq + 1u) & 0x7fffffu;
+                fence_cluster();
+                *(volatile unsigned*)&sh.coop_word = kCoopOpen | (sh.coop_seq << 8);
+            }
+        }
+        if (CL > 1 && sh.help_rank >= 0) {
+            // ---- helping a cluster mate: a share of every bulk sweep of its pair, nothing else (coop_help)
+            coop_help<DIM, NT, SH>(L, sh, cg::this_cluster().block_rank(), slab_vox, a.stats);
+        } else
         for (int it = iters; it < a.max_iter; ++it) {
             if (!a.resume && a.phase_cap > 0 && it == a.phase_cap) {
                 // not converged within the bulk budget: park the state, a dedicated launch finishes it
@@ -1695,9 +1986,11 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
                     for (int k = 0; k < DIM; ++k) sc[9 + k] = sh.t_tot[k];
                     sc[12] = prev; sc[13] = err; sc[14] = (double)iters;
                     a.cont_list[slot] = p;
-                    // cost class from the points swept so far: a pair that kept re-deciding most of its points will go on doing so
-                    const unsigned long long per_it = (st_swept - pp_swept0) / (unsigned long long)max(iters, 1);
-                    const int cls = per_it * 4ull >= (unsigned long long)n_s ? 0 : per_it * 10ull >= (unsigned long long)n_s ? 1 : 2;
+                    // cost class from the points swept in the last four iterations: a pair that is still re-deciding most of
+                    // its points after eight iterations will go on doing so (early iterations sweep a lot in every pair)
+                    const unsigned long long per_it = st_recent / 4ull;
+                    // (absolute counts: the sweeps' cost goes with the points to decide, not with their share of the cloud)
+                    const int cls = per_it >= 256ull ? 0 : per_it >= 96ull ? 1 : per_it >= 24ull ? 2 : 3;      // (class 0: coop_plan)
                     a.cont_bucket[(size_t)cls * a.cont_cap + atomicAdd(&a.cont_count[1 + cls], 1u)] = slot;
                 }
                 handed_over = true;
@@ -1747,10 +2040,43 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
                     // align) its walks cover most of the target, one candidate block after the other, and the register-
                     // blocked tile sweep is the faster way to look at everything.  The sweep measures itself (slab_off).
                     use_slab = slab_vox > 0.f && sh.slab_off == 0;
-                    if (use_slab && ((n_todo + 31) >> 5) > (NT / 32) / 2)                 // the slab sweep will run
+                    if (use_slab && ((n_todo + 31) >> 5) >= kSlabMinChunks)              // the slab sweep will run
                         order_todo_by_x<DIM, NT>(L, sh, n_todo, tgt_xlo, tgt_xhi);
-                    nn_dispatch<DIM, NT>(L, sh, n_todo, use_slab ? slab_vox : 0.f);
+                }
+            }
+            if (!GRID) {
+                int my_n = n_todo;
+                if (CL > 1) {
+                    // helpers registered with this pair take a stretch each of a sweep of more than a few chunks (a stretch
+                    // of 1-2 chunks is swept by all 16 warps of its CTA together, nn_split)
+                    if (tid == 0) {
+                        *(volatile int*)&sh.coop_load = n_todo;
+                        const unsigned mask = *(volatile unsigned*)&sh.coop_word & 0xffu;
+                        const bool share = mask != 0u && n_todo >= kCoopMinShare;
+                        sh.coop_parts = share ? __popc(mask) + 1 : 1;
+                        if (share) {
+                            const int flags = (use_slab ? 2 : 0) | (L.list == L.todo2 ? 4 : 0);
+                            fence_cluster();                   // the list and the points (written before the last barrier)
+                            *(volatile unsigned long long*)&sh.coop_pub = ((unsigned long long)++sh.coop_epoch << 32) |
+                                ((unsigned long long)mask << 20) | ((unsigned long long)flags << 16) | (unsigned long long)n_todo;
+                        }
+                    }
                     __syncthreads();
+                    const int parts = sh.coop_parts;
+                    if (parts > 1) my_n = min(((n_todo + parts * 32 - 1) / (parts * 32)) * 32, n_todo);
+                }
+                if (n_todo > 0) nn_dispatch<DIM, NT>(L, sh, my_n, use_slab ? slab_vox : 0.f);
+                __syncthreads();
+                if (CL > 1 && my_n != n_todo) {
+                    if (tid == 0) {
+                        const unsigned want = (unsigned)sh.coop_parts - 1u;
+                        ICPB_COOP_SPIN(*(volatile unsigned*)&sh.coop_arrived == want);
+                        *(volatile unsigned*)&sh.coop_arrived = 0u;
+                        fence_cluster();                       // the helpers' decisions are in this CTA's shared memory
+                    }
+                    __syncthreads();
+                }
+                if (n_todo > 0) {
                     // a few undecided points: one warp each scans the target; many: a lane each, tiles filtered in fp32
                     if (sh.amb_n > NT / 32) resolve_ambiguous_lockstep<DIM, NT>(L, sh);
                     else if (sh.amb_n > 0) resolve_ambiguous<DIM, NT>(L, sh);
@@ -1759,15 +2085,16 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
             if (tid == 0) {
                 const int n_chunks = (n_todo + 31) >> 5;
                 if (!GRID) {
-                    const bool bulk = n_chunks > (NT / 32) / 2;                      // nn_dispatch's choice: not the split sweep
+                    const bool bulk = n_chunks >= kSlabMinChunks;                    // nn_dispatch's choice: not the split sweep
                     const bool slab = use_slab && bulk;
                     const unsigned long long all = (unsigned long long)n_chunks * 32ull * (unsigned long long)L.n_tiles * 32ull;
                     st_evals += slab ? (unsigned long long)sh.slab_evals : all;
-                    if (slab) { if ((unsigned long long)sh.slab_evals * 20ull > all * 9ull) sh.slab_off = 4; }   // walked > 45 % of the target
+                    if (slab) { if ((unsigned long long)sh.slab_evals * 5ull > all) sh.slab_off = 4; }   // walked > 20 % of the target: the tile sweep is 3-4x cheaper per candidate
                     else if (bulk && sh.slab_off > 0) --sh.slab_off;
                     sh.slab_evals = 0u;
                 }
                 st_swept += n_todo; st_kept += n_s - n_todo; st_iters += 1;
+                if (!a.resume && a.phase_cap > 0 && it >= a.phase_cap - 4) st_recent += n_todo;
             }
             __syncthreads();
             if (prof) { const long long c = clock64(); ph[1] += c - ph_t; ph_t = c; }
@@ -1935,18 +2262,37 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
             if (delta < a.err_thr) { status = ICPB200_CONVERGED; break; }   // icp.py:217-219
             prev = err;
         }
+        if (CL > 1 && tid == 0 && sh.help_rank < 0) {
+            // close the pair: nobody registers any more, and whoever did is told to leave and has left before this CTA
+            // touches its shared memory for the next pair
+            const unsigned mask = atomicAnd(&sh.coop_word, ~kCoopOpen) & 0xffu;
+            if (mask) {
+                fence_cluster();
+                *(volatile unsigned long long*)&sh.coop_pub = ((unsigned long long)++sh.coop_epoch << 32) | ((unsigned long long)mask << 20) | (1ull << 16);
+                const unsigned want = (unsigned)__popc(mask);
+                ICPB_COOP_SPIN(*(volatile unsigned*)&sh.coop_arrived == want);
+                *(volatile unsigned*)&sh.coop_arrived = 0u;
+            }
+        }
         if (nrm_pending) { mbar_wait(&nrm_bar, nrm_parity); nrm_parity ^= 1u; }      // never used (no iteration ran): still drain it
         __syncthreads();
-        if (tid == 0 && a.pair_prof) {
+        if (tid == 0 && a.pair_prof && !(CL > 1 && sh.help_rank >= 0)) {
             st_amb += sh.amb_n;                    // (a break may leave the last iteration's count uncollected; profiling only)
-            unsigned long long* pp = a.pair_prof + 4 * (size_t)p;
+            unsigned long long* pp = a.pair_prof + 8 * (size_t)p;
             atomicAdd(&pp[0], (unsigned long long)(clock64() - pair_t0));
             atomicAdd(&pp[1], st_swept - pp_swept0);
             atomicAdd(&pp[2], st_amb - pp_amb0);
             atomicAdd(&pp[3], st_iters - pp_it0);
+            // cycles by phase (iterations >= 8): classify, nearest neighbours, the rest; what the previous pairs of this
+            // CTA added is remembered in shared memory
+            const long long ph_rest = ph[2] + ph[3] + ph[4];
+            atomicAdd(&pp[4], (unsigned long long)(ph[0] - sh.ph_seen[0]));
+            atomicAdd(&pp[5], (unsigned long long)(ph[1] - sh.ph_seen[1]));
+            atomicAdd(&pp[6], (unsigned long long)(ph_rest - sh.ph_seen[2]));
+            sh.ph_seen[0] = ph[0]; sh.ph_seen[1] = ph[1]; sh.ph_seen[2] = ph_rest;
             st_amb -= sh.amb_n;
         }
-        if (tid == 0 && !handed_over) {
+        if (tid == 0 && !handed_over && !(CL > 1 && sh.help_rank >= 0)) {
             for (int k = 0; k < DIM * DIM; ++k) a.R_out[(size_t)p * DIM * DIM + k] = sh.r_tot[k];
             for (int k = 0; k < DIM; ++k) a.t_out[(size_t)p * DIM + k] = sh.t_tot[k];
             a.err_out[p] = err;
@@ -1955,6 +2301,7 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
             a.status_out[p] = status;
         }
     }
+    if (CL > 1) cg::this_cluster().sync();      // no CTA of a cluster may leave while a peer can still touch its shared memory
     if (GRID && a.stats) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -2244,6 +2591,38 @@ int launch_icp_pairs(const IcpArgs& a, int dim, bool grid, int n_ctas, size_t sm
     if (roomy && nt == 512) return launch_pairs_t<3, false, 1, kRoomyNT>(a, n_ctas, smem, stream);
     if (roomy) return launch_pairs_t<3, false, 1, kNT>(a, n_ctas, smem, stream);
     return launch_pairs_t<3, false, bulk_minb(3, false), kNT>(a, n_ctas, smem, stream);
+}
+
+bool icp_cluster_variant(int dim, bool grid) { return dim == 2 && !grid; }
+
+// The hand-over launch of the 2-D brute-force path: 512-thread CTAs in clusters of kCoopCluster (see icp_pairs_kernel).
+// *n_ctas_out = the CTAs launched: as many whole clusters as the device can hold at once, at most max_ctas (the cluster
+// shape may leave a few SMs unused -- the caller puts plain CTAs of the same queue on those).
+int launch_icp_pairs_cluster(const IcpArgs& a, int max_ctas, size_t smem_min, cudaStream_t stream, int* n_ctas_out) {
+    const size_t smem = std::max(smem_min, icp_pair_smem_bytes(2, a.cap_s, a.cap_t, kRoomyNT));
+    auto kern = icp_pairs_kernel<2, false, 1, kRoomyNT, kCoopCluster>;
+    ICPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(max_ctas / kCoopCluster * kCoopCluster));
+    cfg.blockDim = dim3(kRoomyNT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCoopCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n_clusters = 0;
+    ICPB_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg));
+    const int n_ctas = std::min(max_ctas / kCoopCluster, n_clusters) * kCoopCluster;
+    *n_ctas_out = n_ctas;
+    if (n_ctas <= 0) return ICPB200_OK;
+    cfg.gridDim = dim3((unsigned)n_ctas);
+    IcpArgs b = a;
+    b.coop_ctas = n_ctas;
+    ICPB_CUDA(cudaLaunchKernelEx(&cfg, kern, b));
+    ICPB_LAUNCH_CHECK();
+    return ICPB200_OK;
 }
 
 template <int DIM, bool GRID, int MINB>

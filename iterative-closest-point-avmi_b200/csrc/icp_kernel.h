@@ -84,12 +84,14 @@ struct IcpArgs {
     int* cont_list;            // [slot] -> pair
     int* cont_bucket;          // [class][cont_cap] -> slot: the second launch takes the expensive classes first
     int cont_cap;              // pairs of the whole call (row length of cont_bucket)
+    int class_lo, class_hi;    // resume launches: the cost classes [class_lo, class_hi) this launch takes
+    int coop_ctas;             // resume launches: CTAs of the cluster-variant launch running beside this one (0: none)
     double* cont_cur;          // [slot][dim][cap_s]
     int* cont_match;           // [slot][cap_s]
     float* cont_d2lb;
     float* cont_moved;
     double* cont_scalar;       // [slot][16]: r_tot(9) t_tot(3) prev err iters
-    unsigned long long* pair_prof; // optional [pair][4]: SM cycles, points swept, fp64 rescans, iterations (both launches add up)
+    unsigned long long* pair_prof; // optional [pair][8]: SM cycles, points swept, fp64 rescans, iterations, cycles of classify / NN / rest (launches add up)
     int* trace_match;          // optional: correspondences of the first trace_iters iterations (pair 0)
     int trace_iters;
     int trace_stride;
@@ -123,6 +125,9 @@ int launch_mark_used(const IcpArgs& a, bool p2l, cudaStream_t stream);
 int launch_voxel_clouds(const CloudSet& cs, int dim, double voxel, int sort_pad, cudaStream_t stream, int first = 0, int count = -1);
 int launch_normals(const CloudSet& cs, int cap_t, int normal_k, double voxel, cudaStream_t stream, int first = 0, int count = -1);
 int launch_icp_pairs(const IcpArgs& a, int dim, bool grid, int n_ctas, size_t smem_min, cudaStream_t stream);
+// the most expensive class of handed-over pairs on clusters of 4 CTAs (2-D brute mode only); false: not available
+bool icp_cluster_variant(int dim, bool grid);
+int launch_icp_pairs_cluster(const IcpArgs& a, int max_ctas, size_t smem_min, cudaStream_t stream, int* n_ctas_out);
 
 // big-cloud kernels (icp_big.cu)
 int launch_big_voxel(const CloudSet& cs, int dim, double voxel, unsigned long long* key_buf, unsigned* idx_buf,

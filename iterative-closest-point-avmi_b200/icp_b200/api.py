@@ -142,13 +142,15 @@ def icp_phase_profile():
 def icp_extra_stats():
     st = np.zeros(8, dtype=np.int64)
     check(_lib.load().icpb200_icp_extra_stats(_ptr(st, c_int64_p)), "icpb200_icp_extra_stats")
-    return dict(far_field_iterations=int(st[0]), grid_queries=int(st[1]), grid_candidates=int(st[2]), grid_cells=int(st[3]))
+    return dict(far_field_iterations=int(st[0]), grid_queries=int(st[1]), grid_candidates=int(st[2]), grid_cells=int(st[3]),
+                handed_over_by_class=[int(st[4]), int(st[5]), int(st[6])], helper_joins=int(st[7]))
 
 
 def icp_pair_profile(n_pairs=0):
-    """Per-pair counters of the last registration call: (n, 4) int64 = cycles, points swept, fp64 fallbacks, iterations.
+    """Per-pair counters of the last registration call: (n, 8) int64 = cycles, points swept, fp64 fallbacks, iterations,
+    then cycles (iterations >= 8 only) of the classify phase, the nearest-neighbour phase and the rest, one spare column.
     The first call only switches the counters on (returns an empty array)."""
-    out = np.zeros((max(int(n_pairs), 1), 4), dtype=np.int64)
+    out = np.zeros((max(int(n_pairs), 1), 8), dtype=np.int64)
     n = _lib.load().icpb200_icp_pair_profile(_ptr(out, c_int64_p), int(n_pairs))
     if n < 0:
         check(n, "icpb200_icp_pair_profile")

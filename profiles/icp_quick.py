@@ -40,5 +40,5 @@ for name in which:
           f"CTA cycles total {cyc.sum() / 1e9:.2f} G, longest pair {cyc.max() / 1.965e3:.0f} us | "
           f"phases(it>=8) {{{', '.join(f'{k}: {v:.0f}' for k, v in ph['phases'].items())}}} | max-iter pairs {(out['status'] == 1).sum()}")
     if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
-        np.savez_compressed(os.path.join(ROOT, "gpurun_out", f"icp_quick_{name}.npz"), si=si, ti=ti, **out)
+        np.savez_compressed(os.path.join(ROOT, "gpurun_out", f"icp_quick_{name}.npz"), si=si, ti=ti, prof=prof, **out)
 pin.release()
