@@ -171,7 +171,10 @@ int icpb200_icp_phase_profile(int64_t *out8);
 /* More counters of the most recent registration call: out8[0] iterations
  * decided against the far-field front set (a diverged source), out8[1..3] grid
  * mode: nearest-neighbour queries, target points evaluated, grid cells
- * visited (bench.py: bytes per query of the hash-grid roofline). */
+ * visited (bench.py: bytes per query of the hash-grid roofline); two-phase
+ * batches: out8[4..6] pairs handed over to the second launch by cost class
+ * (256+ points to decide per iteration, 96+, fewer), out8[7] how many times a
+ * CTA of the cluster variant joined a cluster mate's pair as a helper. */
 int icpb200_icp_extra_stats(int64_t *out8);
 
 /* Profiling aid: the first call switches per-pair counters on; after the next

@@ -418,6 +418,8 @@ static int icp_enqueue(const IcpCommon& k, int n_pairs, const DevClouds& s, cons
         // (two or three CTAs per SM were measured slower: the hand-over pairs are latency-bound and want the SM alone)
         const size_t smem2 = std::min(std::max(smem, (size_t)c.max_smem_optin / 2 + 1024), (size_t)c.max_smem_optin);
         static const bool no_cluster = getenv("ICPB200_NO_CLUSTER") != nullptr;      // A/B switch (profiles/README.md)
+        static const int coop_factor = getenv("ICPB200_COOP_FACTOR") ? atoi(getenv("ICPB200_COOP_FACTOR")) : 10;     // tuning switch (profiles/README.md)
+        b.coop_factor = coop_factor;
         b.class_lo = 0; b.class_hi = 4;                                  // every cost class (IcpArgs::cont_bucket), expensive first
         if (icp_cluster_variant(k.dim, grid) && !no_cluster) {
             // two launches side by side, clusters of CTAs (a CTA that runs out of pairs helps a cluster mate with its

@@ -1571,7 +1571,7 @@ __device__ __forceinline__ bool coop_plan(const IcpArgs& a, unsigned& n_chain, u
     n_chain = 0; h = 0; skip = 0;
     if (n_cl_ctas == 0u) return false;
     const unsigned total = a.cont_count[0], heavy = a.cont_count[1] + a.cont_count[2];
-    if (heavy < 4u || total > 4u * n_cl_ctas) return false;
+    if (heavy < 4u || total > (unsigned)a.coop_factor * n_cl_ctas) return false;
     n_chain = min(a.cont_count[1], n_clusters);
     if (n_chain > 0) h = min((unsigned)kCoopCluster, n_cl_ctas / (3u * n_chain));
     h = h > 0 ? h - 1 : 0;

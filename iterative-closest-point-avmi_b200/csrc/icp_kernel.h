@@ -86,6 +86,7 @@ struct IcpArgs {
     int cont_cap;              // pairs of the whole call (row length of cont_bucket)
     int class_lo, class_hi;    // resume launches: the cost classes [class_lo, class_hi) this launch takes
     int coop_ctas;             // resume launches: CTAs of the cluster-variant launch running beside this one (0: none)
+    int coop_factor;           // ... which takes the work when at most this many pairs per cluster CTA were handed over
     double* cont_cur;          // [slot][dim][cap_s]
     int* cont_match;           // [slot][cap_s]
     float* cont_d2lb;

@@ -6,7 +6,7 @@ CMD="python bench.py --steps 1 --warmup 3 --no-cpu --no-extras --no-c5"
 OUT=gpurun_out
 $CMD > $OUT/r02_plain.json 2> $OUT/r02_plain.err || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $OUT/r02_launches.csv $CMD > /tmp/ncu_a.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:icp_pairs_kernel -c 2 -o /tmp/r02_icp $CMD > /tmp/ncu_b.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:icp_pairs_kernel -c 3 -o /tmp/r02_icp $CMD > /tmp/ncu_b.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:occ_ -s 10 -c 9 -o /tmp/r02_occ $CMD > /tmp/ncu_c.log 2>&1
 ncu --set full --clock-control none -k regex:"normals_sweep|voxel_clouds" -c 2 -o /tmp/r02_pre $CMD > /tmp/ncu_d.log 2>&1
 python profiles/c3_once.py > $OUT/r02_c3.log 2>&1 && \

@@ -5,7 +5,7 @@ a figure captured on other sources is reported as null by the bench, not silentl
 
     python profiles/ncu_traffic.py gpurun_out/r2_prof_icp.ncu-rep gpurun_out/r2_prof_occ.ncu-rep ... [--command "..."]
 
-Groups: icp_pairs_kernel = bulk + hand-over launch of one step (brute mode); icp_pairs_kernel_grid = the grid-mode
+Groups: icp_pairs_kernel = bulk + hand-over launches of one step (brute mode); icp_pairs_kernel_grid = the grid-mode
 launch; occupancy_update = every kernel of one update."""
 import csv
 import io
@@ -52,16 +52,17 @@ for name, launches in per_kernel.items():
 import re
 def variant(name):
     """(dim, grid, min blocks, threads) of an icp_pairs_kernel instantiation, however ncu spells the template arguments."""
-    m = re.search(r"icp_pairs_kernel<\s*(?:\(int\))?(\d),\s*(?:\(bool\))?(\d|true|false),\s*(?:\(int\))?(\d),\s*(?:\(int\))?(\d+)>", name)
+    m = re.search(r"icp_pairs_kernel<\s*(?:\(int\))?(\d),\s*(?:\(bool\))?(\d|true|false),\s*(?:\(int\))?(\d),\s*(?:\(int\))?(\d+)(?:,\s*(?:\(int\))?\d+)?>", name)
     if not m:
         return None
     g = m.group(2)
     return (int(m.group(1)), 1 if g in ("1", "true") else 0, int(m.group(3)), int(m.group(4)))
 bulk = [l for n, ls in per_kernel.items() if variant(n) and variant(n)[:2] == (2, 0) and variant(n)[2] > 1 for l in ls]
-hand = [l for n, ls in per_kernel.items() if variant(n) and variant(n)[:2] == (2, 0) and variant(n)[2] == 1 for l in ls]
+# (the hand-over goes out as two launches side by side, clusters and plain CTAs: the first launch of each variant)
+hand = [ls[0] for n, ls in per_kernel.items() if variant(n) and variant(n)[:2] == (2, 0) and variant(n)[2] == 1]
 grid = [(n, l) for n, ls in per_kernel.items() if variant(n) and variant(n)[1] == 1 for l in ls]
 if bulk and hand:
-    groups["icp_pairs_kernel"] = bulk[0]["dram"] + hand[0]["dram"]
+    groups["icp_pairs_kernel"] = bulk[0]["dram"] + sum(l["dram"] for l in hand)
 if grid:
     groups["icp_pairs_kernel_grid"] = sum(l["dram"] for _, l in grid) / len(grid)
 occ = {short(n): ls for n, ls in per_kernel.items() if "occ_" in n}
