@@ -26,6 +26,7 @@ struct CtaSharedT {
     unsigned int pair;
     // registration state (ICP kernel only)
     double r_tot[9], t_tot[3], r[9], t[3];
+    double kab_v[9];                   // 3-D point-to-point: right singular basis of the last solve (warm start of the next)
     double center[3], lo_t[3], hi_t[3];
     double grid_h;
     int grid_nx, grid_ny;

@@ -1559,7 +1559,8 @@ constexpr int kCoopCluster = 8;             // CTAs per cluster of the hand-over
 // CTAs (one per SM).  Which of the two does the work is decided here, from what the bulk launch handed over, the same in
 // every CTA of both launches:
 //   - cluster mode when long chains, not throughput, will bound the launch: a few pairs that re-decided 96+ points per
-//     iteration when they were parked among at most four handed-over pairs per CTA (a rank's share of a multi-GPU batch).
+//     iteration when they were parked among at most a.coop_factor (10) handed-over pairs per cluster CTA (a rank's share
+//     of a multi-GPU batch).
 //     The plain launch then only fills the SMs the cluster shape leaves unused.  The cluster kernel runs every phase ~12 %
 //     slower than the plain one (register pressure), which a chain-bound launch does not feel;
 //   - plain mode otherwise (C2 and C5 on one GPU: throughput-bound): the cluster CTAs leave at once.
@@ -1862,6 +1863,7 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
             sh.slab_evals = 0u;
             sh.bcast_i[0] = 0;                     // todo counter
             sh.slab_off = 0;
+            if (DIM == 3) for (int k = 0; k < 9; ++k) sh.kab_v[k] = (k % 4 == 0) ? 1.0 : 0.0;
         }
         // ---- stage the target: fp64 (tile-padded SoA) and recentred fp32
         if (GRID) {
@@ -2199,7 +2201,7 @@ __global__ void __launch_bounds__(NT, MINB) icp_pairs_kernel(const IcpArgs a) {
                 }
                 block_reduce<DIM * DIM, SumOp>(w, sh, phase);
                 if (tid == 0) {
-                    if (DIM == 2) kabsch2(w, sh.r); else kabsch3(w, sh.r);
+                    if (DIM == 2) kabsch2(w, sh.r); else kabsch3(w, sh.r, sh.kab_v);
                     for (int u = 0; u < DIM; ++u) {                          // t = mu_t - r mu_s
                         double s = mu_t[u];
                         for (int v = 0; v < DIM; ++v) s -= sh.r[u * DIM + v] * mu_s[v];

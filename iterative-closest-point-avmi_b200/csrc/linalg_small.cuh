@@ -108,12 +108,21 @@ ICPB_HDL void kabsch2(const double* w, double* r) {
 // R = V U^T; if det(R) < 0 the column pair of the smallest singular value is
 // negated, which is what flipping the last row of vt does when LAPACK returns
 // singular values in descending order (icp.py:204-206).
-ICPB_HDL void kabsch3(const double* w, double* r) {
+// `vwarm` (optional, 9 doubles, in/out): the right singular basis of the previous
+// call.  Successive ICP iterations solve nearly the same problem, and starting from
+// w V_prev instead of w leaves 2-3 sweeps to do instead of 6-8 (the rotations
+// accumulate in V, which stays orthogonal to a few ulp over hundreds of calls).
+// A sweep is three rotations; a rotation costs two divisions, a square root and a
+// reciprocal square root (the convergence test compares squares).
+ICPB_HDL void kabsch3(const double* w, double* r, double* vwarm = nullptr) {
     double a[3][3], v[3][3];
     for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) { a[i][j] = w[3 * i + j]; v[i][j] = (i == j) ? 1.0 : 0.0; }
+        for (int j = 0; j < 3; ++j) v[i][j] = vwarm ? vwarm[3 * i + j] : ((i == j) ? 1.0 : 0.0);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            a[i][j] = vwarm ? w[3 * i] * v[0][j] + w[3 * i + 1] * v[1][j] + w[3 * i + 2] * v[2][j] : w[3 * i + j];
     for (int sweep = 0; sweep < 60; ++sweep) {
-        double off = 0.0;
+        bool big = false;                       // some pair of columns is still farther than 1e-16 from orthogonal
         for (int p = 0; p < 2; ++p)
             for (int q = p + 1; q < 3; ++q) {
                 double alpha = 0, beta = 0, gamma = 0;
@@ -122,12 +131,16 @@ ICPB_HDL void kabsch3(const double* w, double* r) {
                     beta += a[i][q] * a[i][q];
                     gamma += a[i][p] * a[i][q];
                 }
-                const double lim = 1e-17 * sqrt(alpha * beta);
-                if (fabs(gamma) <= lim || gamma == 0.0) continue;
-                off = fmax(off, fabs(gamma) / sqrt(alpha * beta));
+                const double g2 = gamma * gamma, ab = alpha * beta;
+                if (g2 <= 1e-34 * ab || gamma == 0.0) continue;          // |gamma| <= 1e-17 sqrt(alpha beta)
+                big = big || g2 >= 1e-32 * ab;
                 const double zeta = (beta - alpha) / (2.0 * gamma);
                 const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+#ifdef __CUDA_ARCH__
+                const double c = rsqrt(1.0 + t * t), s = c * t;
+#else
                 const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+#endif
                 for (int i = 0; i < 3; ++i) {
                     const double ap = a[i][p], aq = a[i][q];
                     a[i][p] = c * ap - s * aq;
@@ -137,8 +150,11 @@ ICPB_HDL void kabsch3(const double* w, double* r) {
                     v[i][q] = s * vp + c * vq;
                 }
             }
-        if (off < 1e-16) break;
+        if (!big) break;
     }
+    if (vwarm)
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) vwarm[3 * i + j] = v[i][j];
     double sig[3], u[3][3];
     int kmin = 0;
     double smax = 0.0;

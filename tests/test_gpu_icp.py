@@ -266,3 +266,28 @@ def test_far_away_sources_get_the_exact_nearest_neighbours():
     out = api.icp_batch([src0], [tgt0], 1e-10, 40, 0.04, R_init=np.eye(2)[None], t_init=np.array([[5.0e5, -2.0e5]]),
                         method="point_to_line", normal_k=12)
     assert out["status"][0] in (0, 1) and np.isfinite(out["t"]).all()
+
+
+def test_3d_point_to_point_batch_against_the_oracle():
+    """C1's path in a batch: the teapot cloud under twelve random rigid motions, 3-D point-to-point.
+    Same iteration counts and exit status as the oracle, poses within the north-star tolerance -- covers the Kabsch
+    solve's warm start (the right singular basis is carried from one iteration to the next, csrc/linalg_small.cuh)."""
+    g = load_golden("teapot.npz")
+    base = np.ascontiguousarray(g["teapot"])
+    rng = np.random.default_rng(11)
+    srcs = []
+    for _ in range(12):
+        axis = rng.normal(size=3)
+        axis /= np.linalg.norm(axis)
+        ang = rng.uniform(-0.35, 0.35)
+        K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+        rot = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+        srcs.append(base @ rot.T + rng.uniform(-0.3, 0.3, size=3))
+    cfg = dict(error_threshold=1e-10, max_iterations=80, voxel_size=0.01, method="point_to_point")
+    out = api.icp_batch(srcs, [base] * len(srcs), **cfg)
+    for i, s in enumerate(srcs):
+        R, t, err, iters, status = icp_oracle.register(s, base, **cfg)
+        assert int(out["iters"][i]) == iters and int(out["status"][i]) == status, f"pair {i}: {out['iters'][i]} vs {iters}"
+        dt, dr = pose_delta(out["R"][i], out["t"][i], R, t)
+        assert dt < POS_TOL and dr < ROT_TOL, f"pair {i}: dt={dt:.3e} dr={dr:.3e}"
+        assert abs(out["error"][i] - err) <= 1e-9 * max(1.0, abs(err))
