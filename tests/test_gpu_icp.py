@@ -291,3 +291,20 @@ def test_3d_point_to_point_batch_against_the_oracle():
         dt, dr = pose_delta(out["R"][i], out["t"][i], R, t)
         assert dt < POS_TOL and dr < ROT_TOL, f"pair {i}: dt={dt:.3e} dr={dr:.3e}"
         assert abs(out["error"][i] - err) <= 1e-9 * max(1.0, abs(err))
+
+
+def test_pair_profile_columns():
+    """icpb200_icp_pair_profile: eight counters per pair; the phase cycles (iterations >= 8) stay below the pair's total."""
+    scans, _ = synth.make_sequence(40, world="room", seed=4)
+    cfg = dict(error_threshold=1e-10, max_iterations=150, voxel_size=0.04, method="point_to_line", normal_k=12)
+    flat, off = synth.pack_ragged(scans)
+    si = np.arange(len(scans) - 1, dtype=np.int32)
+    api.icp_pair_profile(0)                                  # switches the counters on
+    out = api.icp_pairs(flat, off, si, si + 1, **cfg)
+    prof = api.icp_pair_profile(len(si))
+    assert prof.shape == (len(si), 8)
+    assert np.array_equal(prof[:, 3], out["iters"])          # iterations
+    assert (prof[:, 0] > 0).all() and (prof[:, 1] > 0).all()
+    assert (prof[:, 4:7].sum(axis=1) <= prof[:, 0]).all() and (prof[:, 7] == 0).all()
+    long_ones = out["iters"] > 8
+    assert (prof[long_ones, 4:7].sum(axis=1) > 0).all()
