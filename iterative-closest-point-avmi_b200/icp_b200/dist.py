@@ -51,7 +51,13 @@ def plan_pair_shards(src_idx, tgt_idx, size, chunks_per_rank=4):
     src_idx = np.asarray(src_idx)
     tgt_idx = np.asarray(tgt_idx)
     n = len(src_idx)
-    order = np.argsort(np.minimum(src_idx, tgt_idx), kind="stable")
+    key = np.minimum(src_idx, tgt_idx)
+    # (a stable sort either way; numpy sorts 16-bit keys by radix, ten times faster than its merge sort of int32:
+    # 0.06 against 0.7 ms for 8192 pairs -- this runs inside every sharded call)
+    if n and 0 <= int(key.min()) and int(key.max()) < 65536:
+        order = np.argsort(key.astype(np.uint16), kind="stable")
+    else:
+        order = np.argsort(key, kind="stable")
     n_chunks = max(1, size * chunks_per_rank)
     bounds = (np.arange(n_chunks + 1, dtype=np.int64) * n) // n_chunks
     plan = []
@@ -74,17 +80,30 @@ def result_layout(n_max, dim):
     return out, at
 
 
-def _unpack_results(blocks, plan, dim):
-    """blocks: (size, bytes) uint8 array of the gathered result blocks -> full result dict in the caller's pair order."""
-    n = sum(len(p) for p in plan)
+def _take_rows(plan):
+    """For a plan: the row of the gathered (size * n_max)-row table that holds pair i, for every i in the caller's order."""
+    n_max = max(len(p) for p in plan)
+    where = np.concatenate([r * n_max + np.arange(len(p), dtype=np.int64) for r, p in enumerate(plan)])
+    perm = np.concatenate(plan)
+    take = np.empty(len(perm), dtype=np.int64)
+    take[perm] = where
+    return take
+
+
+def _unpack_results(blocks, plan, dim, take=None):
+    """blocks: (size, bytes) uint8 array of the gathered result blocks -> full result dict in the caller's pair order.
+    One gather per field through ``take`` (:func:`_take_rows`)."""
     n_max = max(len(p) for p in plan)
     layout, _ = result_layout(n_max, dim)
-    full = dict(R=np.empty((n, dim, dim)), t=np.empty((n, dim)), error=np.empty(n), prev_error=np.empty(n),
-                iters=np.empty(n, dtype=np.int32), status=np.empty(n, dtype=np.int32))
-    for r, mine in enumerate(plan):
-        for name, (at, dt, width) in layout.items():
-            vals = np.frombuffer(blocks[r], dtype=dt, count=len(mine) * width, offset=at)
-            full[name][mine] = vals.reshape((len(mine),) + full[name].shape[1:])
+    if take is None:
+        take = _take_rows(plan)
+    blocks = np.ascontiguousarray(blocks)
+    full = {}
+    for name, (at, dt, width) in layout.items():
+        nb = n_max * width * np.dtype(dt).itemsize
+        table = np.ascontiguousarray(blocks[:, at:at + nb]).view(dt).reshape(len(plan) * n_max, width)
+        rows = np.take(table, take, axis=0)               # (10x faster than table[take] on rows)
+        full[name] = rows.reshape((len(take), dim, dim)) if name == "R" else rows.reshape(len(take), width) if width > 1 else rows.reshape(-1)
     return full
 
 
@@ -106,6 +125,7 @@ def icp_pairs_sharded(points, cloud_off, src_idx, tgt_idx, *args, compute=None, 
             kw = dict(kw, R_init=R_init, t_init=t_init)
         return compute(points, cloud_off, src_idx, tgt_idx, *args, **kw)
     plan = plan_pair_shards(src_idx, tgt_idx, size, chunks_per_rank)
+    take = _take_rows(plan)
     mine = plan[rank]
     if R_init is not None and t_init is not None:
         kw = dict(kw, R_init=np.asarray(R_init)[mine], t_init=np.asarray(t_init)[mine])
@@ -127,7 +147,7 @@ def icp_pairs_sharded(points, cloud_off, src_idx, tgt_idx, *args, compute=None, 
         bufs = [torch.empty_like(send) for _ in range(size)]
         dist.all_gather(bufs, send)
         blocks = np.stack([b.cpu().numpy() for b in bufs])
-    return _unpack_results(blocks, plan, dim)
+    return _unpack_results(blocks, plan, dim, take)
 
 
 def gather_result_blocks(part, dim):
