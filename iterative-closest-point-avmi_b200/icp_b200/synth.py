@@ -194,6 +194,10 @@ def submap_cloud(n_raw=52000, seed=3, extent=60.0, spacing=0.04, sigma=0.01):
 
 def pack_ragged(clouds, dim=2):
     """Concatenate clouds -> (flat (sum,dim) float64 C-contiguous, offsets int64 (n+1,))."""
+    if len(clouds) == 1:                                        # one cloud (every ICP() call): no copy
+        c = np.ascontiguousarray(clouds[0], dtype=np.float64)
+        if c.ndim == 2 and c.shape[1] == dim:
+            return c, np.array([0, len(c)], dtype=np.int64)
     off = np.zeros(len(clouds) + 1, dtype=np.int64)
     for i, c in enumerate(clouds):
         off[i + 1] = off[i] + len(c)
