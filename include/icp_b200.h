@@ -53,6 +53,8 @@ extern "C" {
                                      entry point) a cloud index outside the set */
 
 /* method (icp.py:133, 162) */
+#define ICPB200_SINGULAR      4   /* pose graph only: the normal matrix is not positive definite (pose_graph.py:115-119) */
+
 #define ICPB200_POINT_TO_POINT 0
 #define ICPB200_POINT_TO_LINE  1  /* 2-D only; silently point-to-point for dim 3, as the reference */
 
@@ -326,6 +328,26 @@ int icpb200_rotation_scores(int n_problems, const double *src, const int64_t *sr
                             const double *tgt, const int64_t *tgt_off, const double *angles,
                             const int64_t *ang_off, const double *shift, double *scores_out,
                             double *nn_dist_out, int32_t *nn_idx_out);
+
+/* ---- pose graph --------------------------------
+ * Replaces PoseGraph2D.optimize (utilities/pose_graph.py:83-134): Gauss-Newton
+ * on SE(2) over `n_nodes` poses [x, y, theta] (row-major, updated in place) and
+ * `n_edges` relative-pose constraints edge_i[e] -> edge_j[e] with measurement
+ * meas[3e..] = [dx, dy, dtheta] and information matrix info[9e..] (row-major
+ * 3 x 3).  The pose `fix_node` is anchored as the reference does it (1e10 on its
+ * diagonal block, pose_graph.py:107-112).  Up to n_iterations steps; stops when
+ * |step| < convergence_eps.  iters_out = the iteration index the loop ended on
+ * (n_iterations at the limit: what the reference prints), step_norm_out = |step|
+ * of the last iteration, status_out = ICPB200_CONVERGED, ICPB200_MAX_ITER or
+ * ICPB200_SINGULAR.  The reference assembles a dense 3n x 3n matrix and calls
+ * np.linalg.solve (O(n^3)); this is a block-skyline Cholesky on the HOST (cost
+ * proportional to nodes + loop lengths) -- the one entry point that needs no CUDA
+ * device (SURVEY: "a sparse Cholesky on host is the pragmatic fix").  Poses agree
+ * with the reference to rounding (the linear solve differs), not bit for bit. */
+int icpb200_pose_graph_optimize(int64_t n_nodes, double *poses, int64_t n_edges, const int32_t *edge_i,
+                                const int32_t *edge_j, const double *meas, const double *info,
+                                int n_iterations, int fix_node, double convergence_eps,
+                                int32_t *iters_out, double *step_norm_out, int32_t *status_out);
 
 /* ---- host buffers ----------------------------------------------------------
  * The host-buffer entry points above accept any host pointer.  Buffers that

@@ -19,7 +19,7 @@ c_int32_p = ctypes.POINTER(ctypes.c_int32)
 c_int64_p = ctypes.POINTER(ctypes.c_int64)
 
 OK, ERR_CUDA, ERR_ARG, ERR_LIMIT = 0, -1, -2, -3
-CONVERGED, MAX_ITER, FEW_INLIERS, BAD_VOXELS = 0, 1, 2, 3
+CONVERGED, MAX_ITER, FEW_INLIERS, BAD_VOXELS, SINGULAR = 0, 1, 2, 3, 4
 POINT_TO_POINT, POINT_TO_LINE = 0, 1
 NN_AUTO, NN_BRUTE, NN_GRID = 0, 1, 2
 
@@ -77,6 +77,9 @@ PROTOTYPES = {
                                           c_double_p] + _ICP_TAIL + _ICP_OUT),
     "icpb200_rotation_scores": (ctypes.c_int, [ctypes.c_int, c_double_p, c_int64_p, c_double_p, c_int64_p, c_double_p,
                                                c_int64_p, c_double_p, c_double_p, c_double_p, c_int32_p]),
+    "icpb200_pose_graph_optimize": (ctypes.c_int, [ctypes.c_int64, c_double_p, ctypes.c_int64, c_int32_p, c_int32_p, c_double_p,
+                                                   c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, c_int32_p,
+                                                   c_double_p, c_int32_p]),
     "icpb200_pin_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),
     "icpb200_unpin_host": (ctypes.c_int, [ctypes.c_void_p]),
 }

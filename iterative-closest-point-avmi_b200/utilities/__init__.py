@@ -1,11 +1,10 @@
 """Drop-in replacements for the reference's hot-path modules.
 
-Two ways to use them: overlay ``icp.py``, ``mapping.py`` and ``features.py`` on the
-reference's ``utilities`` package, or put this directory's parent AHEAD of the reference root on ``sys.path``.  In the
-second case this package shadows the reference's ``utilities``; the modules it does not replace
-(``utilities.pose_graph``, slam.py:11, and the feature pipeline behind ``feature_based_alignment``, slam.py:9) are found
-through ``__path__``: every other ``utilities`` directory on ``sys.path`` is appended to it, so
-``import utilities.pose_graph`` resolves to the reference's own file and the unmodified ``slam.py`` imports cleanly.
+Two ways to use them: overlay ``icp.py``, ``mapping.py``, ``features.py`` and
+``pose_graph.py`` on the reference's ``utilities`` package, or put this directory's parent AHEAD of the reference root on
+``sys.path``.  In the second case this package shadows the reference's ``utilities``; what it does not replace (the
+feature pipeline behind ``feature_based_alignment``, slam.py:9) is found through ``__path__``: every other
+``utilities`` directory on ``sys.path`` is appended to it, so the unmodified ``slam.py`` imports cleanly.
 """
 import os as _os
 import sys as _sys
@@ -35,10 +34,7 @@ from .submap import DeviceSubmap                                            # no
 __all__ = ["ICP", "voxel_downsample", "OccupancyGrid2D", "rotation_search", "submap_rotation_search",
            "feature_based_alignment", "DeviceSubmap"]
 
-if len(__path__) > 1:                                                       # utilities/__init__.py:4-9 of the reference
-    try:
-        from .pose_graph import (PoseGraph2D, pose_matrix_to_vec, pose_vec_to_matrix,      # noqa: F401
-                                 relative_transform_vec)
-        __all__ += ["PoseGraph2D", "pose_matrix_to_vec", "pose_vec_to_matrix", "relative_transform_vec"]
-    except ImportError:
-        pass
+from .pose_graph import (PoseGraph2D, pose_matrix_to_vec, pose_vec_to_matrix,      # noqa: E402,F401  (utilities/__init__.py:4-9)
+                         relative_transform_vec)
+
+__all__ += ["PoseGraph2D", "pose_matrix_to_vec", "pose_vec_to_matrix", "relative_transform_vec"]

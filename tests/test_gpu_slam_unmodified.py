@@ -3,15 +3,15 @@
 `oracle/_ref/reference_py.tar.gz` (made by oracle/make_ref.py in the build container, shipped by gpurun; git-ignored) is
 unpacked to a temporary directory; the shim package `iterative-closest-point-avmi_b200/` goes AHEAD of it on sys.path
 (second option), so `slam.py`'s own imports (slam.py:6-16) bind `utilities.icp.ICP`,
-`utilities.icp.voxel_downsample` and `utilities.mapping.OccupancyGrid2D` to the GPU versions while
-`utilities.pose_graph`, `feature_based_alignment` and `services.*` stay the reference's.  `slam.run_slam(cfg)` then runs
+`utilities.icp.voxel_downsample`, `utilities.mapping.OccupancyGrid2D` and `utilities.pose_graph.PoseGraph2D` to the
+library's versions while `feature_based_alignment` and `services.*` stay the reference's.  `slam.run_slam(cfg)` then runs
 on the synthetic lidar CSV the golden fixture was made from (oracle/make_slam_golden.py ran the same slam.py on the
 reference's own numpy/scipy utilities) and the trajectory and the map are compared.
 
 Three configurations, each with its own golden run of the reference: the plain scan-to-scan loop; the same with the
 rotation-search pre-alignment (slam.py:60-66 -> the shim's GPU rotation_search); and submap + loop closure enabled
 (slam.py:103-225, 230-277, 564-620: _build_submap, _submap_rotation_search, gated ICP against the submap, loop-closure
-candidates, the reference's own pose graph, _rebuild_map)."""
+candidates, the pose graph (the library's block-skyline solver against the golden run's dense solve), _rebuild_map)."""
 import contextlib
 import io
 import os
@@ -37,7 +37,7 @@ DRIVER = textwrap.dedent('''
     assert os.path.dirname(os.path.abspath(slam.__file__)) == os.path.abspath(ref)
     assert slam.ICP.__module__ == "utilities.icp" and "iterative-closest-point-avmi_b200" in sys.modules["utilities.icp"].__file__
     assert "iterative-closest-point-avmi_b200" in sys.modules["utilities.mapping"].__file__
-    assert os.path.abspath(ref) in sys.modules["utilities.pose_graph"].__file__
+    assert "iterative-closest-point-avmi_b200" in sys.modules["utilities.pose_graph"].__file__
     cfg = dict(data_file=csv, imu=dict(enabled=False),
                icp=dict(method="point_to_line", normal_k=12, voxel_size=0.04, error_threshold=1e-10,
                         max_iterations=150, error_reject_threshold=0.15),
