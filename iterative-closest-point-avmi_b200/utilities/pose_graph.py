@@ -43,13 +43,16 @@ class PoseGraph2D:
         self.edges = []
 
     def add_node(self, pose_vec):
-        self.nodes.append(np.asarray(pose_vec, dtype=float).copy())
-        return len(self.nodes) - 1
+        """Append a pose [x, y, theta] (copied); returns its index (pose_graph.py:63-66)."""
+        index = len(self.nodes)
+        self.nodes.append(np.array(pose_vec, dtype=np.float64))
+        return index
 
     def add_edge(self, i, j, measurement, information=None):
-        z = np.asarray(measurement, dtype=float).copy()
-        omega = np.eye(3) if information is None else np.asarray(information, dtype=float).copy()
-        self.edges.append((i, j, z, omega))
+        """Constraint i -> j: relative pose [dx, dy, dtheta] in frame i and its 3 x 3 information matrix, identity when
+        omitted (pose_graph.py:68-79).  Both are copied."""
+        weight = np.identity(3) if information is None else np.array(information, dtype=np.float64)
+        self.edges.append((i, j, np.array(measurement, dtype=np.float64), weight))
 
     def _pack(self):
         poses = np.ascontiguousarray(np.array(self.nodes, dtype=np.float64).reshape(-1, 3))
